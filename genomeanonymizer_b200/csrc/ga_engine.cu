@@ -1,0 +1,286 @@
+// ga_engine.cu - engine handle, reference upload, session assignment and the C ABI of include/ga_b200.h.
+// Built for sm_100a only; there is no CPU fallback: ga_engine_create fails without a CUDA device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ga_session_kernel.cuh"
+
+namespace ga {
+
+// ------------------------------------------------------------------ small kernels
+
+// ASCII reference -> resident 4-bit codes, upper-cased (variation_classifier.py:89,194 apply .upper()).
+// Output word w (w >= 1) holds bases [8(w-1), 8(w-1)+8); word 0 and the tail are N padding.
+__global__ void pack_reference_kernel(const uint8_t* __restrict__ asc, int64_t n, uint32_t* __restrict__ out, int64_t n_words) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t v = 0xffffffffu;
+    if (w >= 1) {
+        v = 0;
+        const int64_t p0 = (w - 1) * 8;
+        for (int k = 0; k < 8; ++k) {
+            uint32_t code = 15u;
+            if (p0 + k < n) {
+                uint8_t ch = asc[p0 + k];
+                if (ch >= 'a' && ch <= 'z') ch -= 32;
+                switch (ch) {
+                    case '=': code = 0; break;  case 'A': code = 1; break;  case 'C': code = 2; break;  case 'M': code = 3; break;
+                    case 'G': code = 4; break;  case 'R': code = 5; break;  case 'S': code = 6; break;  case 'V': code = 7; break;
+                    case 'T': code = 8; break;  case 'W': code = 9; break;  case 'Y': code = 10; break; case 'H': code = 11; break;
+                    case 'K': code = 12; break; case 'D': code = 13; break; case 'B': code = 14; break; default: code = 15; break;
+                }
+            }
+            v |= code << (k * 4);
+        }
+    }
+    out[w] = v;
+}
+
+// max over reads of the reference span (only when the caller did not provide ga_reads.max_ref_span)
+__global__ void max_span_kernel(const uint32_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar, int64_t n, int32_t* out) {
+    int m = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, ref_span_of(cigar, cigar_off[r], cigar_off[r + 1]));
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+__device__ __forceinline__ int32_t lower_bound_pos(const int32_t* __restrict__ pos, int64_t b, int64_t e, int64_t v) {
+    while (b < e) { const int64_t m = (b + e) >> 1; if ((int64_t)__ldg(pos + m) < v) b = m + 1; else e = m; }
+    return (int32_t)b;
+}
+
+// K-assign: binary search of the coordinate-sorted read positions for every session
+// (replaces the index fetch inside pileup(), pileup_io.pyx:12-17).
+__global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* __restrict__ maxspan_p, SessionDesc* __restrict__ descs,
+                                       int32_t* __restrict__ big_list, int32_t* __restrict__ n_big) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S.n_sessions) return;
+    const int maxspan = max(1, *maxspan_p);
+    const int64_t first = S.first[s], last = S.last[s];
+    SessionDesc d;
+    d.t_begin = lower_bound_pos(B.pos, 0, B.n_tumor, first - maxspan + 1);
+    d.t_end = lower_bound_pos(B.pos, 0, B.n_tumor, last);
+    d.n_begin = lower_bound_pos(B.pos, B.n_tumor, B.n_reads, first - maxspan + 1);
+    d.n_end = lower_bound_pos(B.pos, B.n_tumor, B.n_reads, last);
+    int64_t lo = last;
+    if (d.t_end > d.t_begin) lo = min(lo, (int64_t)B.pos[d.t_begin]);
+    if (d.n_end > d.n_begin) lo = min(lo, (int64_t)B.pos[d.n_begin]);
+    d.col_begin = (int32_t)lo;
+    d.n_cols = (int32_t)max((int64_t)0, last - 1 + maxspan - lo + 1);
+    const int n_range = (d.t_end - d.t_begin) + (d.n_end - d.n_begin);
+    int64_t ops = 0;
+    if (d.t_end > d.t_begin) ops += (int64_t)B.cigar_off[d.t_end] - B.cigar_off[d.t_begin];
+    if (d.n_end > d.n_begin) ops += (int64_t)B.cigar_off[d.n_end] - B.cigar_off[d.n_begin];
+    d.obs_bound = (int32_t)max((int64_t)0, ops - n_range);
+    d.big = (d.n_cols > kColsCap || n_range > kReadsCap || d.obs_bound > kObsCap) ? 1 : 0;
+    if (n_range == 0) { d.n_cols = 0; d.big = 0; }
+    descs[s] = d;
+    if (d.big) big_list[atomicAdd(n_big, 1)] = s;
+}
+
+__global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* tickets, int32_t* maxspan, int32_t given_span) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        memset(totals, 0, sizeof(ga_totals));
+        *n_big = 0; tickets[0] = 0; tickets[1] = 0; *maxspan = given_span;
+    }
+}
+
+}  // namespace ga
+
+// ------------------------------------------------------------------ engine
+
+struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
+
+struct ga_engine {
+    int device = 0;
+    int n_sm = 0;
+    std::string err;
+    std::map<int, RefEntry> refs;
+    // scratch
+    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int64_t cap_sessions = 0;
+    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, then tickets (2 x u32)
+    uint8_t* d_big_scratch = nullptr; int64_t big_bytes_per_cta = 0; int big_ctas = 0;
+    int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
+    uint8_t* d_stage = nullptr; int64_t cap_stage = 0;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+static int fail(ga_engine* e, int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (e) {
+        e->err = what;
+        if (ce != cudaSuccess) { e->err += ": "; e->err += cudaGetErrorString(ce); }
+    }
+    return code;
+}
+#define GA_CUDA(call) do { cudaError_t _ce = (call); if (_ce != cudaSuccess) return fail(e, GA_ERR_CUDA, #call, _ce); } while (0)
+
+extern "C" {
+
+int ga_abi_version(void) { return GA_ABI_VERSION; }
+
+const char* ga_status_string(int status) {
+    switch (status) {
+        case GA_OK: return "ok";
+        case GA_ERR_BAD_ARGUMENT: return "bad argument";
+        case GA_ERR_OFFSET_RANGE: return "offset out of range";
+        case GA_ERR_LENGTH_MISMATCH: return "length mismatch";
+        case GA_ERR_CUDA: return "CUDA error";
+        case GA_ERR_CAPACITY: return "output or scratch capacity exceeded";
+        case GA_ERR_UNSUPPORTED: return "unsupported input";
+        case GA_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+
+int ga_engine_create(int device, ga_engine** out) {
+    if (!out) return GA_ERR_BAD_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return GA_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GA_ERR_NO_DEVICE;
+    if (prop.major < 10) return GA_ERR_NO_DEVICE;             // kernels are built for sm_100a only
+    ga_engine* e = new ga_engine();
+    e->device = device;
+    e->n_sm = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
+    if (cudaMalloc(&e->d_small, 64) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    cudaFuncSetAttribute(ga::session_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemLayout));
+    *out = e;
+    return GA_OK;
+}
+
+void ga_engine_destroy(ga_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (auto& kv : e->refs) cudaFree(kv.second.d_ref4);
+    cudaFree(e->d_descs); cudaFree(e->d_big_list); cudaFree(e->d_small); cudaFree(e->d_big_scratch); cudaFree(e->d_stage);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+}
+
+const char* ga_last_error(const ga_engine* e) { return e ? e->err.c_str() : "null engine"; }
+int64_t ga_launch_count(const ga_engine* e) { return e ? e->launches : 0; }
+
+int ga_upload_reference(ga_engine* e, int contig_id, const uint8_t* bases, int64_t n_bases, void* stream_) {
+    if (!e || !bases || n_bases < 0) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_upload_reference: null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    GA_CUDA(cudaSetDevice(e->device));
+    cudaPointerAttributes attr;
+    const uint8_t* d_asc = bases;
+    uint8_t* tmp = nullptr;
+    bool is_dev = (cudaPointerGetAttributes(&attr, bases) == cudaSuccess) && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (!is_dev) {
+        GA_CUDA(cudaMalloc(&tmp, (size_t)n_bases + 16));
+        GA_CUDA(cudaMemcpyAsync(tmp, bases, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+        d_asc = tmp;
+    }
+    RefEntry& re = e->refs[contig_id];
+    if (re.d_ref4) { cudaFree(re.d_ref4); re.d_ref4 = nullptr; }
+    const int64_t n_words = (n_bases + 7) / 8 + 1 + 8;          // 1 pad word in front, 8 behind
+    GA_CUDA(cudaMalloc(&re.d_ref4, (size_t)n_words * 4));
+    re.n = n_bases;
+    const int threads = 256;
+    ga::pack_reference_kernel<<<(unsigned)((n_words + threads - 1) / threads), threads, 0, st>>>(d_asc, n_bases, re.d_ref4, n_words);
+    e->launches++;
+    GA_CUDA(cudaGetLastError());
+    if (tmp) { GA_CUDA(cudaStreamSynchronize(st)); cudaFree(tmp); }
+    return GA_OK;
+}
+
+static int ensure_session_scratch(ga_engine* e, int64_t n_sessions) {
+    if (n_sessions <= e->cap_sessions) return GA_OK;
+    cudaFree(e->d_descs); cudaFree(e->d_big_list);
+    e->d_descs = nullptr; e->d_big_list = nullptr;
+    const int64_t cap = n_sessions + n_sessions / 4 + 1024;
+    GA_CUDA(cudaMalloc(&e->d_descs, (size_t)cap * sizeof(ga::SessionDesc)));
+    GA_CUDA(cudaMalloc(&e->d_big_list, (size_t)cap * sizeof(int32_t)));
+    e->cap_sessions = cap;
+    return GA_OK;
+}
+
+static int ensure_big_scratch(ga_engine* e) {
+    if (e->d_big_scratch) return GA_OK;
+    const int64_t per = 4ll * e->big_cols_cap * 2 + 4ll * ((e->big_reads_cap + 31) / 32) + 20ll * e->big_obs_cap + 8ll * e->big_reads_cap;
+    e->big_bytes_per_cta = (per + 255) / 256 * 256;
+    e->big_ctas = e->n_sm;
+    GA_CUDA(cudaMalloc(&e->d_big_scratch, (size_t)e->big_bytes_per_cta * e->big_ctas));
+    return GA_OK;
+}
+
+int ga_run(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result* out, void* stream_) {
+    if (!e || !R || !S || !out || !out->totals) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: null argument");
+    if (R->n_reads < 0 || R->n_tumor < 0 || R->n_tumor > R->n_reads || S->n_sessions < 0)
+        return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: negative or inconsistent sizes");
+    if (R->n_reads > 0x7fffffffll) return fail(e, GA_ERR_UNSUPPORTED, "ga_run: more than 2^31-1 reads in one batch");
+    auto it = e->refs.find(R->contig_id);
+    if (it == e->refs.end()) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: reference contig was not uploaded");
+    cudaStream_t st = (cudaStream_t)stream_;
+    GA_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_session_scratch(e, S->n_sessions); if (rc) return rc;
+    rc = ensure_big_scratch(e); if (rc) return rc;
+
+    ga::BatchView B;
+    B.pos = R->pos; B.len_flag = R->len_flag; B.seq_off16 = R->seq_off16; B.cigar_off = R->cigar_off; B.cigar = R->cigar;
+    B.seq4 = R->seq4; B.qual = R->qual; B.qual_reads = R->qual_reads; B.qual_off16 = R->qual_off16;
+    B.n_reads = R->n_reads; B.n_tumor = R->n_tumor; B.n_qual = R->qual_reads ? R->n_qual : 0;
+    B.ref4 = it->second.d_ref4; B.ref_len = it->second.n;
+    ga::SessView V;
+    V.first = S->first; V.last = S->last; V.keep_type = S->keep_type; V.keep_pos = S->keep_pos; V.keep_end = S->keep_end;
+    V.keep_len = S->keep_len; V.keep_allele_off = S->keep_allele_off; V.keep_alleles = S->keep_alleles; V.n_sessions = S->n_sessions;
+    ga::ResultView O;
+    O.cap_records = out->cap_records; O.cap_seq16 = out->cap_seq16; O.cap_qual16 = out->cap_qual16;
+    O.mod_session = out->mod_session; O.mod_read = out->mod_read; O.mod_len = out->mod_len;
+    O.mod_seq_off16 = out->mod_seq_off16; O.mod_qual_off16 = out->mod_qual_off16;
+    O.out_seq4 = out->out_seq4; O.out_qual = out->out_qual; O.sess_counts = out->sess_counts; O.totals = out->totals;
+
+    int32_t* d_nbig = e->d_small;
+    int32_t* d_maxspan = e->d_small + 1;
+    unsigned int* d_tickets = reinterpret_cast<unsigned int*>(e->d_small + 2);
+    ga::clear_kernel<<<1, 32, 0, st>>>(out->totals, d_nbig, d_tickets, d_maxspan, R->max_ref_span);
+    e->launches++;
+    if (S->n_sessions == 0 || R->n_reads == 0) {
+        if (S->n_sessions > 0) GA_CUDA(cudaMemsetAsync(out->sess_counts, 0, 16ull * S->n_sessions, st));
+        GA_CUDA(cudaGetLastError());
+        return GA_OK;
+    }
+    if (R->max_ref_span <= 0) {
+        ga::max_span_kernel<<<e->n_sm * 4, 256, 0, st>>>(R->cigar_off, R->cigar, R->n_reads, d_maxspan);
+        e->launches++;
+    }
+    ga::assign_sessions_kernel<<<(S->n_sessions + 127) / 128, 128, 0, st>>>(B, V, d_maxspan, e->d_descs, e->d_big_list, d_nbig);
+    e->launches++;
+    ga::BigScratch scr;
+    scr.base = e->d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
+    scr.cols_cap = e->big_cols_cap; scr.reads_cap = e->big_reads_cap; scr.obs_cap = e->big_obs_cap;
+    const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 2, S->n_sessions);
+    GA_CUDA(cudaEventRecord(e->ev0, st));
+    ga::session_kernel<false><<<grid_small, ga::kThreads, sizeof(ga::SmemLayout), st>>>(B, V, e->d_descs, e->d_big_list, d_nbig, O, scr, d_tickets);
+    GA_CUDA(cudaEventRecord(e->ev1, st));
+    e->timed = true;
+    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, e->d_descs, e->d_big_list, d_nbig, O, scr, d_tickets + 1);
+    e->launches += 2;
+    GA_CUDA(cudaGetLastError());
+    return GA_OK;
+}
+
+float ga_last_kernel_ms(ga_engine* e) {
+    if (!e || !e->timed) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+}  // extern "C"

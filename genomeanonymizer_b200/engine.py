@@ -1,0 +1,192 @@
+"""Python host side above the C ABI: device buffers (torch tensors), engine handle, result decoding.
+
+PyTorch is used for device memory, streams and torch.distributed only; every kernel is in
+libga_b200.so (csrc/).  Nothing here computes masking on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi, _lib
+from .batch import MaskResult, ReadBatch, SessionTable, decode_result
+
+
+def _dev(a: Optional[np.ndarray], device, pad=0):
+    if a is None:
+        return None
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if pad:
+        t = torch.cat([t, torch.zeros(pad, dtype=t.dtype)])
+    return t.to(device, non_blocking=False)
+
+
+class DeviceBatch:
+    """ReadBatch resident in HBM (one torch tensor per array)."""
+
+    def __init__(self, b: ReadBatch, device):
+        self.n_reads, self.n_tumor = b.n_reads, b.n_tumor
+        self.max_ref_span, self.contig_id = b.max_ref_span, b.contig_id
+        v = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)) if a is not None else None
+        self.pos = _dev(b.pos, device)
+        self.len_flag = v(b.len_flag).to(device)
+        self.seq_off16 = v(b.seq_off16).to(device)
+        self.cigar_off = v(b.cigar_off).to(device)
+        self.cigar = torch.cat([v(b.cigar), torch.zeros(4, dtype=torch.int32)]).to(device)
+        self.seq4 = _dev(b.seq4, device, pad=64)
+        self.qual = _dev(b.qual, device, pad=64) if b.qual is not None else None
+        self.qual_reads = _dev(b.qual_reads, device) if b.qual_reads is not None else None
+        self.qual_off16 = v(b.qual_off16).to(device) if b.qual_off16 is not None else None
+        self.seq4_bytes = int(b.seq4.shape[0])
+
+    def as_struct(self) -> _abi.GaReads:
+        p = lambda t: t.data_ptr() if t is not None else None
+        s = _abi.GaReads()
+        s.n_reads, s.n_tumor = self.n_reads, self.n_tumor
+        s.pos, s.len_flag, s.seq_off16 = p(self.pos), p(self.len_flag), p(self.seq_off16)
+        s.cigar_off, s.cigar, s.seq4, s.qual = p(self.cigar_off), p(self.cigar), p(self.seq4), p(self.qual)
+        s.seq4_bytes = self.seq4_bytes
+        s.n_qual = 0 if self.qual_reads is None else int(self.qual_reads.shape[0])
+        s.qual_reads, s.qual_off16 = p(self.qual_reads), p(self.qual_off16)
+        s.max_ref_span, s.contig_id = int(self.max_ref_span), int(self.contig_id)
+        return s
+
+
+class DeviceSessions:
+    def __init__(self, t: SessionTable, device):
+        self.n_sessions = t.n_sessions
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32) if a.dtype == np.uint32 else np.ascontiguousarray(a)).to(device)
+        self.first, self.last = f(t.first), f(t.last)
+        self.keep_type, self.keep_pos, self.keep_end, self.keep_len = f(t.keep_type), f(t.keep_pos), f(t.keep_end), f(t.keep_len)
+        self.keep_allele_off = f(t.keep_allele_off)
+        self.keep_alleles = torch.from_numpy(np.ascontiguousarray(t.keep_alleles)).to(device)
+
+    def as_struct(self) -> _abi.GaSessions:
+        s = _abi.GaSessions()
+        s.n_sessions = self.n_sessions
+        s.first, s.last = self.first.data_ptr(), self.last.data_ptr()
+        s.keep_type, s.keep_pos = self.keep_type.data_ptr(), self.keep_pos.data_ptr()
+        s.keep_end, s.keep_len = self.keep_end.data_ptr(), self.keep_len.data_ptr()
+        s.keep_allele_off, s.keep_alleles = self.keep_allele_off.data_ptr(), self.keep_alleles.data_ptr()
+        return s
+
+
+class DeviceResult:
+    """Caller-owned output buffers in HBM."""
+
+    def __init__(self, n_sessions, cap_records, cap_seq16, cap_qual16, device):
+        i32 = dict(dtype=torch.int32, device=device)
+        self.n_sessions = n_sessions
+        self.cap_records, self.cap_seq16, self.cap_qual16 = int(cap_records), int(cap_seq16), int(cap_qual16)
+        self.mod_session = torch.empty(self.cap_records, **i32)
+        self.mod_read = torch.empty(self.cap_records, **i32)
+        self.mod_len = torch.empty(self.cap_records, **i32)
+        self.mod_seq_off16 = torch.empty(self.cap_records, **i32)
+        self.mod_qual_off16 = torch.empty(self.cap_records, **i32)
+        self.out_seq4 = torch.empty(self.cap_seq16 * 16, dtype=torch.uint8, device=device)
+        self.out_qual = torch.empty(self.cap_qual16 * 32, dtype=torch.uint8, device=device)
+        self.sess_counts = torch.zeros(max(1, n_sessions) * 4, **i32)
+        self.totals = torch.zeros(_abi.TOTALS_BYTES, dtype=torch.uint8, device=device)
+
+    def as_struct(self) -> _abi.GaResult:
+        r = _abi.GaResult()
+        r.cap_records, r.cap_seq16, r.cap_qual16 = self.cap_records, self.cap_seq16, self.cap_qual16
+        r.mod_session, r.mod_read, r.mod_len = self.mod_session.data_ptr(), self.mod_read.data_ptr(), self.mod_len.data_ptr()
+        r.mod_seq_off16, r.mod_qual_off16 = self.mod_seq_off16.data_ptr(), self.mod_qual_off16.data_ptr()
+        r.out_seq4, r.out_qual = self.out_seq4.data_ptr(), self.out_qual.data_ptr()
+        r.sess_counts, r.totals = self.sess_counts.data_ptr(), self.totals.data_ptr()
+        return r
+
+    def read_totals(self) -> _abi.GaTotals:
+        raw = self.totals.cpu().numpy().tobytes()
+        return _abi.GaTotals.from_buffer_copy(raw)
+
+    def to_host(self) -> MaskResult:
+        t = self.read_totals()
+        n = int(t.n_modified)
+        u32 = lambda x, k: x[:k].cpu().numpy().view(np.uint32)
+        return decode_result(self.n_sessions, t, self.mod_session[:n].cpu().numpy(), self.mod_read[:n].cpu().numpy(),
+                             u32(self.mod_len, n), u32(self.mod_seq_off16, n), u32(self.mod_qual_off16, n),
+                             self.out_seq4[:int(t.seq16_used) * 16].cpu().numpy(),
+                             self.out_qual[:int(t.qual16_used) * 32].cpu().numpy(),
+                             self.sess_counts[:self.n_sessions * 4].cpu().numpy().view(np.uint32))
+
+
+class Engine:
+    """Owns a ga_engine handle on one GPU."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("genomeanonymizer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._L = _lib.lib()
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        st = self._L.ga_engine_create(self.device_index, C.byref(h))
+        if st != _abi.GA_OK:
+            raise _abi.GaError(st, self._L.ga_status_string(st).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ga_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != _abi.GA_OK:
+            _abi.raise_for_status(st, self._L.ga_last_error(self._h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ga_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._L.ga_last_kernel_ms(self._h))
+
+    def upload_reference(self, contig_id: int, bases) -> None:
+        """bases: str / bytes (host) or a uint8 CUDA tensor of ASCII codes."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if isinstance(bases, torch.Tensor):
+            assert bases.dtype == torch.uint8 and bases.is_cuda
+            self._check(self._L.ga_upload_reference(self._h, contig_id, bases.data_ptr(), bases.numel(), stream))
+            torch.cuda.current_stream(self.device).synchronize()
+            return
+        if isinstance(bases, str):
+            bases = bases.encode("ascii")
+        buf = np.frombuffer(bases, dtype=np.uint8)
+        self._check(self._L.ga_upload_reference(self._h, contig_id, buf.ctypes.data, len(buf), stream))
+
+    def run_device(self, dbatch: DeviceBatch, dsess: DeviceSessions, dres: DeviceResult, stream=None) -> None:
+        """Asynchronous launch over device-resident buffers (the `value` path of bench.py)."""
+        s = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        R, S, O = dbatch.as_struct(), dsess.as_struct(), dres.as_struct()
+        self._check(self._L.ga_run(self._h, C.byref(R), C.byref(S), C.byref(O), s))
+
+    def check_device_status(self, dres: DeviceResult) -> _abi.GaTotals:
+        t = dres.read_totals()
+        if t.error:
+            _abi.raise_for_status(int(t.error), f"device raised status {t.error} at index {t.error_detail} "
+                                                f"(needs records={t.n_modified} seq16={t.seq16_used} qual16={t.qual16_used})")
+        return t
+
+    def run(self, batch: ReadBatch, sessions: SessionTable, cap_frac: float = 1.0) -> MaskResult:
+        """Synchronous convenience: upload, run, download, decode."""
+        with torch.cuda.device(self.device):
+            db, ds = DeviceBatch(batch, self.device), DeviceSessions(sessions, self.device)
+            units = batch.seq4.shape[0] // 16
+            dres = DeviceResult(sessions.n_sessions, max(16, int(2 * batch.n_reads * cap_frac) + 16),
+                                int(2 * units * cap_frac) + 64, int(2 * units * cap_frac) + 64, self.device)
+            self.run_device(db, ds, dres)
+            torch.cuda.synchronize(self.device)
+            self.check_device_status(dres)
+            return dres.to_host()
