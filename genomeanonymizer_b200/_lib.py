@@ -10,8 +10,7 @@ _LIB = None
 
 # every entry point declared in include/ga_b200.h
 EXPORTS = ["ga_abi_version", "ga_status_string", "ga_engine_create", "ga_engine_destroy", "ga_last_error",
-           "ga_upload_reference", "ga_run", "ga_run_host", "ga_launch_count", "ga_last_kernel_ms",
-           "ga_synth_plan", "ga_synth_generate", "ga_synth_reference"]
+           "ga_upload_reference", "ga_run", "ga_launch_count", "ga_last_kernel_ms"]
 
 
 def lib():
@@ -37,8 +36,6 @@ def lib():
     L.ga_upload_reference.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.ga_run.restype = C.c_int
     L.ga_run.argtypes = [C.c_void_p, C.POINTER(_abi.GaReads), C.POINTER(_abi.GaSessions), C.POINTER(_abi.GaResult), C.c_void_p]
-    L.ga_run_host.restype = C.c_int
-    L.ga_run_host.argtypes = [C.c_void_p, C.POINTER(_abi.GaReads), C.POINTER(_abi.GaSessions), C.POINTER(_abi.GaResult), C.c_int64]
     L.ga_launch_count.restype = C.c_int64
     L.ga_launch_count.argtypes = [C.c_void_p]
     L.ga_last_kernel_ms.restype = C.c_float

@@ -1,0 +1,140 @@
+"""Parity of the CUDA engine (through the C ABI of include/ga_b200.h) with the reference's golden
+vectors and with the CPU oracle on seeded random sessions.  Bit-exact: sequence codes, printed
+qualities, per-session counters."""
+import numpy as np
+import pytest
+
+from genomeanonymizer_b200 import batch as B
+from genomeanonymizer_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GOLD = H.load_golden("session_cases.json")["cases"]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from genomeanonymizer_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("entry", GOLD, ids=[e["case"]["name"] for e in GOLD])
+@pytest.mark.parametrize("sparse_qual", [False, True], ids=["dense-qual", "sparse-qual"])
+def test_engine_matches_reference_sessions(engine, entry, sparse_qual):
+    case = entry["case"]
+    batch = B.pack_reads(H.ordered_reads(case), sparse_qual=sparse_qual)
+    dense = B.pack_reads(H.ordered_reads(case)) if sparse_qual else batch
+    engine.upload_reference(0, case["reference"])
+    for widx, (w, exp) in enumerate(zip(case["windows"], entry["expected"])):
+        res = engine.run(batch, B.pack_sessions([w]))
+        H.check_session_against_golden(case, widx, exp, dense, res)
+
+
+def assert_same_result(a, b, what):
+    assert a.totals == b.totals, (what, a.totals, b.totals)
+    assert sorted(a.records) == sorted(b.records), what
+    for k, v in a.records.items():
+        w = b.records[k]
+        assert np.array_equal(v["seq"], w["seq"]), (what, k)
+        assert (v["qual"] is None) == (w["qual"] is None), (what, k)
+        if v["qual"] is not None:
+            assert np.array_equal(v["qual"], w["qual"]), (what, k)
+    assert np.array_equal(a.sess_counts, b.sess_counts), what
+
+
+RANDOM_CASES = [
+    dict(seed=101, contig_len=6000, n_pairs=(200, 200), read_len=100),
+    dict(seed=102, contig_len=9000, n_pairs=(400, 250), read_len=150, somatic_positions=[2500, 4700, 6900]),
+    dict(seed=103, contig_len=5000, n_pairs=(300, 300), read_len=75, indel_rate=3e-3, clip_frac=0.5),
+    dict(seed=104, contig_len=7000, n_pairs=(250, 250), read_len=151, ref_n_runs=0.05, ref_lower=0.2),
+    dict(seed=105, contig_len=8000, n_pairs=(500, 60), read_len=120, somatic_positions=[3000, 3900]),   # overlapping windows
+    dict(seed=106, contig_len=4000, n_pairs=(100, 0), read_len=100),                                   # no normal reads
+    dict(seed=107, contig_len=12000, n_pairs=(900, 900), read_len=250, snp_rate=5e-3, indel_rate=1e-3,
+         somatic_positions=[3000, 6000, 9000], max_indel=20),
+]
+
+
+@pytest.mark.parametrize("kw", RANDOM_CASES, ids=[f"seed{k['seed']}" for k in RANDOM_CASES])
+@pytest.mark.parametrize("sparse_qual", [False, True], ids=["dense-qual", "sparse-qual"])
+def test_engine_matches_oracle_random(engine, kw, sparse_qual):
+    from oracle import oracle
+    case = synth.make_case(**kw)
+    batch = B.pack_reads(H.ordered_reads(case), sparse_qual=sparse_qual)
+    sessions = B.pack_sessions(case["windows"])
+    exp, st = oracle.run(batch, sessions, case["reference"])
+    assert st == 0
+    engine.upload_reference(0, case["reference"])
+    got = engine.run(batch, sessions)
+    assert_same_result(got, exp, kw["seed"])
+    assert got.totals["n_modified"] > 0 or kw["n_pairs"][1] == 0
+
+
+def test_engine_deep_session_uses_big_path(engine):
+    """A session deeper than the shared-memory tables (SmemLayout caps) takes the global-scratch path."""
+    from oracle import oracle
+    case = synth.make_case(seed=201, contig_len=3000, n_pairs=(2600, 2600), read_len=100, somatic_positions=[1500])
+    batch = B.pack_reads(H.ordered_reads(case), sparse_qual=True)
+    sessions = B.pack_sessions(case["windows"])
+    exp, st = oracle.run(batch, sessions, case["reference"])
+    assert st == 0
+    engine.upload_reference(0, case["reference"])
+    got = engine.run(batch, sessions)
+    assert int(got.sess_counts[0, 3]) > 4096
+    assert_same_result(got, exp, "deep")
+
+
+def test_engine_empty_inputs(engine):
+    case = synth.make_case(seed=301, contig_len=3000, n_pairs=(20, 20), read_len=100)
+    engine.upload_reference(0, case["reference"])
+    batch = B.pack_reads(H.ordered_reads(case))
+    none = B.pack_sessions([])
+    res = engine.run(batch, none)
+    assert res.totals["n_modified"] == 0 and res.totals["session_reads"] == 0
+    empty = B.pack_reads([])
+    res = engine.run(empty, B.pack_sessions(case["windows"]))
+    assert res.totals["n_modified"] == 0
+    far = B.pack_sessions([{"first": 100000, "last": 102001, "keep": None}])
+    res = engine.run(batch, far)
+    assert res.totals["session_reads"] == 0
+
+
+def test_engine_capacity_error_reports_needed_sizes(engine):
+    from genomeanonymizer_b200 import _abi
+    from genomeanonymizer_b200.engine import DeviceBatch, DeviceResult, DeviceSessions
+    import torch
+    case = synth.make_case(seed=102, contig_len=9000, n_pairs=(400, 250), read_len=150, somatic_positions=[2500, 4700, 6900])
+    batch = B.pack_reads(H.ordered_reads(case))
+    sessions = B.pack_sessions(case["windows"])
+    engine.upload_reference(0, case["reference"])
+    db, ds = DeviceBatch(batch, engine.device), DeviceSessions(sessions, engine.device)
+    small = DeviceResult(sessions.n_sessions, 4, 8, 8, engine.device)
+    engine.run_device(db, ds, small)
+    torch.cuda.synchronize()
+    t = small.read_totals()
+    assert t.error == _abi.GA_ERR_CAPACITY
+    with pytest.raises(_abi.GaError):
+        engine.check_device_status(small)
+    # the totals say how much is needed: a second run with exactly that capacity succeeds
+    exact = DeviceResult(sessions.n_sessions, int(t.n_modified), int(t.seq16_used), max(1, int(t.qual16_used)), engine.device)
+    engine.run_device(db, ds, exact)
+    torch.cuda.synchronize()
+    engine.check_device_status(exact)
+
+
+def test_engine_rejects_unknown_contig(engine):
+    case = synth.make_case(seed=301, contig_len=3000, n_pairs=(20, 20), read_len=100)
+    batch = B.pack_reads(H.ordered_reads(case), contig_id=77)
+    with pytest.raises(ValueError):
+        engine.run(batch, B.pack_sessions(case["windows"]))
+
+
+def test_engine_read_past_reference_end_is_index_error(engine):
+    """A read whose alignment runs off the contig raises like the reference's IndexError path."""
+    case = synth.make_case(seed=301, contig_len=3000, n_pairs=(20, 20), read_len=100)
+    engine.upload_reference(0, case["reference"][:1600])
+    batch = B.pack_reads(H.ordered_reads(case))
+    with pytest.raises(IndexError):
+        engine.run(batch, B.pack_sessions(case["windows"]))
