@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - reads/s of the per-read germline-masking hot path on synthetic tumor-normal sessions.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one pass of the whole hot path (session assignment, allele discovery, germline resolution,
+masking, compaction) over every session of the workload.  `value` times ga_run() on a batch already
+resident in HBM; `e2e` times ga_run_host() - host SoA buffers in pinned memory in, compacted modified
+records in host memory out, H2D/D2H inside the timed region.  `roofline` is the session kernel against
+the measured HBM copy peak; `cpu_baseline` is the CPU oracle (a C restatement of the reference's
+algorithm, all host threads) on a bounded sample of the same sessions.
+
+N > 1 (torchrun): each rank owns one contig-sized shard of the genome (region sharding),
+no data-path collective; the masking counters are all-reduced once per step over NCCL.  Weak scaling.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "session reads/s masked (germline-variant masking hot path)"
+UNIT = "reads/s"
+
+
+def algorithmic_bytes(read_len, n_reads, n_cigar_ops, n_sessions, n_cols_per_session, n_modified, n_indel_records, seq16_used, qual16_used):
+    """Compulsory traffic of ONE pass with every array touched once (DESIGN.md "Algorithmic bytes").
+
+    This is the conservative single-pass figure.  SURVEY.md 8(d) counts the read arrays twice (discover,
+    then mask); the fused session kernel stages a session once, so the single-pass figure is the honest
+    floor for this design.  Both are reported."""
+    per_read = (read_len + 1) // 2 + 4 + 4 + 4 + 8          # seq4 + pos + len_flag + seq_off16 + two cigar offsets
+    once = n_reads * per_read + 4 * n_cigar_ops + n_sessions * (n_cols_per_session // 2 + 40)
+    out = 20 * n_modified + 16 * seq16_used + 32 * qual16_used + 16 * n_sessions
+    out_reads = 16 * seq16_used + 32 * qual16_used           # modified records are re-read (sequence, qualities)
+    single = once + out + out_reads
+    survey = 2 * (n_reads * per_read + 4 * n_cigar_ops) + n_sessions * n_cols_per_session + out + out_reads
+    return single, survey
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.t:
+            self._stop.set()
+            self.t.join()
+            self.t = None
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def host_sample(cfg, n_windows, device=None):
+    """Host copy (ReadBatch, SessionTable, reference prefix bytes) of windows [0, n_windows) of `cfg`."""
+    from genomeanonymizer_b200 import synthdev as SD
+    pl = cfg.plan(0, n_windows)
+    prefix = min(cfg.contig_len, (n_windows + 1) * int(pl.window_stride) + 8 * cfg.window_half)
+    if device is not None:
+        db, ds = SD.generate_device(cfg, device, 0, n_windows)
+        ref = SD.reference_device(cfg, device, 0, prefix).cpu().numpy().tobytes()
+        return db.to_host(), ds.to_host(), ref
+    import ctypes as C
+    import numpy as np
+    from genomeanonymizer_b200 import _lib
+    b, s, _ = SD.generate_host(cfg, 0, n_windows, with_reference=False)
+    buf = np.zeros(prefix, np.uint8)
+    p = cfg.params(0, 0)
+    _lib.lib().ga_synth_reference_host(C.byref(p), buf.ctypes.data, 0, prefix)
+    return b, s, buf.tobytes()
+
+
+def time_oracle(batch, sessions, ref, threads):
+    from oracle import oracle
+    t0 = time.perf_counter()
+    raw, st = oracle.run(batch, sessions, ref, threads=threads, decode=False)
+    dt = time.perf_counter() - t0
+    if st != 0:
+        raise RuntimeError(f"oracle failed with status {st}")
+    return dt, raw
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path (oracle port; the Python reference needs pysam and
+    cannot travel to the box) on all host threads, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from genomeanonymizer_b200 import synthdev as SD
+    from oracle import oracle
+    oracle.build()
+    cfg = SD.WORKLOADS[args.workload]
+    threads = oracle.n_threads()
+    n_w = min(cfg.total_windows, args.sample_windows or 1500)
+    batch, sessions, ref = host_sample(cfg, n_w, device=None if not _has_cuda() else 0)
+    for _ in range(args.warmup):
+        time_oracle(batch, sessions, ref, threads)
+    t = 0.0
+    reads = bases = 0
+    for _ in range(args.steps):
+        dt, raw = time_oracle(batch, sessions, ref, threads)
+        t += dt
+        reads, bases = int(raw["totals"].session_reads), int(raw["totals"].session_bases)
+    v = reads * args.steps / t
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "impl": "reference",
+            "config": {"workload": cfg.name, "sample": f"windows [0,{n_w}) of {cfg.total_windows}", "read_len": cfg.read_len,
+                       "session_reads_per_step": reads},
+            "bases_per_s": bases * args.steps / t,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n_w} of {cfg.total_windows} windows ({reads} session reads) per step"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chr1-30x-50k")
+    ap.add_argument("--windows", type=int, default=0, help="debug: use only the first WINDOWS windows per rank")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--chunk-sessions", type=int, default=1024)
+    ap.add_argument("--sample-windows", type=int, default=0, help="CPU baseline sample (0 = auto, ~10 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from genomeanonymizer_b200 import synthdev as SD
+    from genomeanonymizer_b200.engine import DeviceResult, Engine, HostBatch, HostResult
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the masking path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    base = SD.WORKLOADS[args.workload]
+    # region sharding: rank r owns contig r of the synthetic genome (same shape, its own seed)
+    from dataclasses import replace
+    cfg = replace(base, seed=base.seed + 7919 * rank, name=base.name)
+    n_w = args.windows or cfg.total_windows
+    eng = Engine(local)
+    db, ds = SD.generate_device(cfg, dev, 0, n_w)
+    ref_dev = SD.reference_device(cfg, dev)
+    eng.upload_reference(0, ref_dev)
+    del ref_dev
+    torch.cuda.empty_cache()
+    units = db.seq4_bytes // 16
+    cap_rec = db.n_reads // 3 + 1024
+    upr = max(1, units // max(1, db.n_reads))
+    dres = DeviceResult(n_w, cap_rec, cap_rec * (upr + 1), cap_rec * (upr + 1) // 2 + 1024, dev)
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def step():
+        eng.run_device(db, ds, dres)
+        if world > 1:
+            # the only collective of the path: masking counters (SR.py:198-204) summed over the shards
+            counters.zero_()
+            counters[:3] = dres.sess_counts.view(-1, 4)[:, :3].sum(0)
+            dist.all_reduce(counters)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    tot = eng.check_device_status(dres)
+    session_reads, session_bases = int(tot.session_reads), int(tot.session_bases)
+
+    sampler = ClockSampler(local)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    kernel_ms = [x for x in eng.kernel_ms_history(min(args.steps, 32)) if x > 0]
+    eng.check_device_status(dres)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    work = torch.tensor([session_reads, session_bases, launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work)
+    ms_max = float(t_ms.item())
+    total_reads, total_bases, total_launches = (int(x) for x in work.tolist())
+    value = total_reads * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the session kernel (rank 0's shard)
+    n_cigar = int(db.cigar_off[-1].item())
+    n_cols = 2 * cfg.window_half + 1 + 2 * (cfg.read_len - 1)
+    single, survey = algorithmic_bytes(cfg.read_len, session_reads, n_cigar, n_w, n_cols, int(tot.n_modified),
+                                       int(tot.indel_records), int(tot.seq16_used), int(tot.qual16_used))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else float("nan")
+    ach = single / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "kernel": "session_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms / args.steps),
+                "algorithmic_bytes_per_launch": single, "bytes_per_session_read": single / max(1, session_reads),
+                "survey_8d_bytes_per_launch": survey, "survey_8d_achieved": survey / (k_ms * 1e-3) / 1e9,
+                "survey_8d_frac": survey / (k_ms * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the host entry (pinned host SoA in, host records out)
+    e2e = None
+    if not args.no_e2e:
+        hb = HostBatch(db.to_host(), ds.to_host())
+        hres = HostResult(n_w, cap_rec, cap_rec * (upr + 1), cap_rec * (upr + 1) // 2 + 1024)
+        eng.run_host(hb, hres, args.chunk_sessions)            # warm-up: allocates the lane buffers
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            th = eng.run_host(hb, hres, args.chunk_sessions)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        sampler.stop()
+        h2d, d2h = eng.host_traffic()
+        assert int(th.session_reads) == session_reads and int(th.n_modified) == int(tot.n_modified), "host path disagrees with device path"
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        io = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(io)
+        e2e = {"value": total_reads * args.e2e_steps / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * float(t_e.item()) / args.e2e_steps,
+               "api": "ga_run_host (C ABI), pinned host SoA in / host records out", "chunk_sessions": args.chunk_sessions}
+        del hb, hres
+
+    # ---- CPU baseline on a bounded sample + parity of the sampled sessions (rank 0, N=1)
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        threads = oracle.n_threads()
+        n_s = args.sample_windows
+        if not n_s:
+            pb, ps, pref = host_sample(cfg, min(n_w, 64), dev)
+            dt, _ = time_oracle(pb, ps, pref, threads)
+            dt, _ = time_oracle(pb, ps, pref, threads)
+            n_s = int(min(n_w, max(64, 12.0 / max(dt / min(n_w, 64), 1e-6))))
+        sb, ss, sref = host_sample(cfg, n_s, dev)
+        dt, raw = time_oracle(sb, ss, sref, threads)
+        cpu_reads = int(raw["totals"].session_reads)
+        cpu = {"value": cpu_reads / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n_s} of {n_w} windows ({cpu_reads} session reads), one pass, {dt:.2f} s"}
+        got = dres.sess_counts.view(-1, 4)[:n_s].cpu().numpy().view(np.uint32)
+        parity = "ok" if np.array_equal(got, raw["counts"][:n_s]) else "MISMATCH"
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": cfg.name, "windows_per_gpu": n_w, "read_len": cfg.read_len,
+                           "coverage": [cfg.cov_tumor, cfg.cov_normal], "session_reads_per_gpu": session_reads,
+                           "modified_records_per_gpu": int(tot.n_modified), "masked_snv_del_ins": [int(x) for x in tot.masked],
+                           "sharding": "one contig-sized region per GPU, no data-path collective" if world > 1 else "single GPU",
+                           "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
+                "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches,
+                "clocks": sampler.summary(), "parity_vs_oracle_on_sample": parity}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

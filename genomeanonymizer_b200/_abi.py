@@ -41,11 +41,16 @@ class GaResult(C.Structure):
 
 class GaSynthParams(C.Structure):
     _fields_ = [("contig_len", C.c_int64), ("seed", C.c_uint64), ("read_len", C.c_int32),
-                ("n_windows", C.c_int32), ("window_half", C.c_int32),
+                ("total_windows", C.c_int32), ("window_begin", C.c_int32), ("n_windows", C.c_int32),
+                ("window_half", C.c_int32), ("max_indel", C.c_int32), ("max_clip", C.c_int32), ("reserved", C.c_int32),
                 ("cov_tumor", C.c_float), ("cov_normal", C.c_float),
                 ("snp_rate", C.c_float), ("indel_rate", C.c_float), ("err_rate", C.c_float),
-                ("n_rate", C.c_float), ("somatic_vaf", C.c_float), ("clip_frac", C.c_float),
-                ("max_indel", C.c_int32)]
+                ("n_rate", C.c_float), ("somatic_vaf", C.c_float), ("clip_frac", C.c_float)]
+
+
+class GaSynthPlan(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_tumor", C.c_int64), ("seq4_bytes", C.c_int64),
+                ("reads_per_window", C.c_int32 * 2), ("units_per_read", C.c_int32), ("window_stride", C.c_int32)]
 
 
 TOTALS_BYTES = C.sizeof(GaTotals)

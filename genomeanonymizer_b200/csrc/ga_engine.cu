@@ -7,7 +7,9 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <algorithm>
 
+#include "ga_engine_internal.h"
 #include "ga_session_kernel.cuh"
 
 namespace ga {
@@ -95,32 +97,14 @@ __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* ti
 
 // ------------------------------------------------------------------ engine
 
-struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
-
-struct ga_engine {
-    int device = 0;
-    int n_sm = 0;
-    std::string err;
-    std::map<int, RefEntry> refs;
-    // scratch
-    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int64_t cap_sessions = 0;
-    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, then tickets (2 x u32)
-    uint8_t* d_big_scratch = nullptr; int64_t big_bytes_per_cta = 0; int big_ctas = 0;
-    int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
-    uint8_t* d_stage = nullptr; int64_t cap_stage = 0;
-    int64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-};
-
-static int fail(ga_engine* e, int code, const char* what, cudaError_t ce = cudaSuccess) {
+int ga_fail(ga_engine* e, int code, const char* what, cudaError_t ce) {
     if (e) {
         e->err = what;
         if (ce != cudaSuccess) { e->err += ": "; e->err += cudaGetErrorString(ce); }
     }
     return code;
 }
-#define GA_CUDA(call) do { cudaError_t _ce = (call); if (_ce != cudaSuccess) return fail(e, GA_ERR_CUDA, #call, _ce); } while (0)
+static int fail(ga_engine* e, int code, const char* what, cudaError_t ce = cudaSuccess) { return ga_fail(e, code, what, ce); }
 
 extern "C" {
 
@@ -152,8 +136,10 @@ int ga_engine_create(int device, ga_engine** out) {
     e->device = device;
     e->n_sm = prop.multiProcessorCount;
     if (cudaSetDevice(device) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
-    if (cudaMalloc(&e->d_small, 64) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
-    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    for (int l = 0; l < kLanes; ++l) {
+        if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
+        for (int k = 0; k < kTimedRuns; ++k) { cudaEventCreate(&e->lanes[l].ev0[k]); cudaEventCreate(&e->lanes[l].ev1[k]); }
+    }
     cudaFuncSetAttribute(ga::session_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemLayout));
     *out = e;
     return GA_OK;
@@ -162,10 +148,14 @@ int ga_engine_create(int device, ga_engine** out) {
 void ga_engine_destroy(ga_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    ga_host_slots_destroy(e);
     for (auto& kv : e->refs) cudaFree(kv.second.d_ref4);
-    cudaFree(e->d_descs); cudaFree(e->d_big_list); cudaFree(e->d_small); cudaFree(e->d_big_scratch); cudaFree(e->d_stage);
-    if (e->ev0) cudaEventDestroy(e->ev0);
-    if (e->ev1) cudaEventDestroy(e->ev1);
+    for (int l = 0; l < kLanes; ++l) {
+        Lane& L = e->lanes[l];
+        cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
+        for (int k = 0; k < kTimedRuns; ++k) { if (L.ev0[k]) cudaEventDestroy(L.ev0[k]); if (L.ev1[k]) cudaEventDestroy(L.ev1[k]); }
+    }
     delete e;
 }
 
@@ -199,37 +189,62 @@ int ga_upload_reference(ga_engine* e, int contig_id, const uint8_t* bases, int64
     return GA_OK;
 }
 
-static int ensure_session_scratch(ga_engine* e, int64_t n_sessions) {
-    if (n_sessions <= e->cap_sessions) return GA_OK;
-    cudaFree(e->d_descs); cudaFree(e->d_big_list);
-    e->d_descs = nullptr; e->d_big_list = nullptr;
+static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
+    if (n_sessions <= L.cap_sessions) return GA_OK;
+    cudaFree(L.d_descs); cudaFree(L.d_big_list);
+    L.d_descs = nullptr; L.d_big_list = nullptr; L.cap_sessions = 0;
     const int64_t cap = n_sessions + n_sessions / 4 + 1024;
-    GA_CUDA(cudaMalloc(&e->d_descs, (size_t)cap * sizeof(ga::SessionDesc)));
-    GA_CUDA(cudaMalloc(&e->d_big_list, (size_t)cap * sizeof(int32_t)));
-    e->cap_sessions = cap;
+    GA_CUDA(cudaMalloc(&L.d_descs, (size_t)cap * sizeof(ga::SessionDesc)));
+    GA_CUDA(cudaMalloc(&L.d_big_list, (size_t)cap * sizeof(int32_t)));
+    L.cap_sessions = cap;
     return GA_OK;
 }
 
-static int ensure_big_scratch(ga_engine* e) {
-    if (e->d_big_scratch) return GA_OK;
+static int ensure_big_scratch(ga_engine* e, Lane& L) {
+    if (L.d_big_scratch) return GA_OK;
     const int64_t per = 4ll * e->big_cols_cap * 2 + 4ll * ((e->big_reads_cap + 31) / 32) + 20ll * e->big_obs_cap + 8ll * e->big_reads_cap;
     e->big_bytes_per_cta = (per + 255) / 256 * 256;
     e->big_ctas = e->n_sm;
-    GA_CUDA(cudaMalloc(&e->d_big_scratch, (size_t)e->big_bytes_per_cta * e->big_ctas));
+    GA_CUDA(cudaMalloc(&L.d_big_scratch, (size_t)e->big_bytes_per_cta * e->big_ctas));
     return GA_OK;
 }
 
 int ga_run(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result* out, void* stream_) {
+    return ga_run_lane(e, 0, R, S, out, (cudaStream_t)stream_);
+}
+
+int ga_kernel_ms_history(ga_engine* e, float* out, int n) {
+    if (!e || !out || n < 0) return 0;
+    Lane& L = e->lanes[0];
+    const int have = (int)std::min<int64_t>(std::min<int64_t>(L.runs, kTimedRuns), n);
+    for (int k = 0; k < have; ++k) {                       // out[0] = most recent run
+        const int slot = (int)((L.runs - 1 - k) % kTimedRuns);
+        float ms = -1.f;
+        if (cudaEventSynchronize(L.ev1[slot]) != cudaSuccess || cudaEventElapsedTime(&ms, L.ev0[slot], L.ev1[slot]) != cudaSuccess) ms = -1.f;
+        out[k] = ms;
+    }
+    return have;
+}
+
+float ga_last_kernel_ms(ga_engine* e) {
+    float ms = -1.f;
+    return ga_kernel_ms_history(e, &ms, 1) == 1 ? ms : -1.f;
+}
+
+}  // extern "C"
+
+int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S, ga_result* out, cudaStream_t st) {
     if (!e || !R || !S || !out || !out->totals) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: null argument");
+    if (lane < 0 || lane >= kLanes) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: bad lane");
     if (R->n_reads < 0 || R->n_tumor < 0 || R->n_tumor > R->n_reads || S->n_sessions < 0)
         return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: negative or inconsistent sizes");
     if (R->n_reads > 0x7fffffffll) return fail(e, GA_ERR_UNSUPPORTED, "ga_run: more than 2^31-1 reads in one batch");
     auto it = e->refs.find(R->contig_id);
     if (it == e->refs.end()) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: reference contig was not uploaded");
-    cudaStream_t st = (cudaStream_t)stream_;
+    Lane& L = e->lanes[lane];
     GA_CUDA(cudaSetDevice(e->device));
-    int rc = ensure_session_scratch(e, S->n_sessions); if (rc) return rc;
-    rc = ensure_big_scratch(e); if (rc) return rc;
+    int rc = ensure_session_scratch(e, L, S->n_sessions); if (rc) return rc;
+    rc = ensure_big_scratch(e, L); if (rc) return rc;
 
     ga::BatchView B;
     B.pos = R->pos; B.len_flag = R->len_flag; B.seq_off16 = R->seq_off16; B.cigar_off = R->cigar_off; B.cigar = R->cigar;
@@ -245,9 +260,9 @@ int ga_run(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result* out
     O.mod_seq_off16 = out->mod_seq_off16; O.mod_qual_off16 = out->mod_qual_off16;
     O.out_seq4 = out->out_seq4; O.out_qual = out->out_qual; O.sess_counts = out->sess_counts; O.totals = out->totals;
 
-    int32_t* d_nbig = e->d_small;
-    int32_t* d_maxspan = e->d_small + 1;
-    unsigned int* d_tickets = reinterpret_cast<unsigned int*>(e->d_small + 2);
+    int32_t* d_nbig = L.d_small;
+    int32_t* d_maxspan = L.d_small + 1;
+    unsigned int* d_tickets = reinterpret_cast<unsigned int*>(L.d_small + 2);
     ga::clear_kernel<<<1, 32, 0, st>>>(out->totals, d_nbig, d_tickets, d_maxspan, R->max_ref_span);
     e->launches++;
     if (S->n_sessions == 0 || R->n_reads == 0) {
@@ -259,28 +274,19 @@ int ga_run(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result* out
         ga::max_span_kernel<<<e->n_sm * 4, 256, 0, st>>>(R->cigar_off, R->cigar, R->n_reads, d_maxspan);
         e->launches++;
     }
-    ga::assign_sessions_kernel<<<(S->n_sessions + 127) / 128, 128, 0, st>>>(B, V, d_maxspan, e->d_descs, e->d_big_list, d_nbig);
+    ga::assign_sessions_kernel<<<(S->n_sessions + 127) / 128, 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
     e->launches++;
     ga::BigScratch scr;
-    scr.base = e->d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
+    scr.base = L.d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
     scr.cols_cap = e->big_cols_cap; scr.reads_cap = e->big_reads_cap; scr.obs_cap = e->big_obs_cap;
     const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 2, S->n_sessions);
-    GA_CUDA(cudaEventRecord(e->ev0, st));
-    ga::session_kernel<false><<<grid_small, ga::kThreads, sizeof(ga::SmemLayout), st>>>(B, V, e->d_descs, e->d_big_list, d_nbig, O, scr, d_tickets);
-    GA_CUDA(cudaEventRecord(e->ev1, st));
-    e->timed = true;
-    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, e->d_descs, e->d_big_list, d_nbig, O, scr, d_tickets + 1);
+    const int tslot = (int)(L.runs % kTimedRuns);
+    GA_CUDA(cudaEventRecord(L.ev0[tslot], st));
+    ga::session_kernel<false><<<grid_small, ga::kThreads, sizeof(ga::SmemLayout), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets);
+    GA_CUDA(cudaEventRecord(L.ev1[tslot], st));
+    L.runs++;
+    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
     e->launches += 2;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }
-
-float ga_last_kernel_ms(ga_engine* e) {
-    if (!e || !e->timed) return -1.f;
-    float ms = -1.f;
-    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.f;
-    return ms;
-}
-
-}  // extern "C"

@@ -1,0 +1,45 @@
+// ga_engine_internal.h - engine handle shared by ga_engine.cu and ga_host_pipeline.cu (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include "ga_device.cuh"
+
+struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
+
+// Scratch of one in-flight ga_run: two lanes let the host pipeline overlap consecutive chunks.
+struct Lane {
+    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int64_t cap_sessions = 0;
+    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, then tickets (2 x u32)
+    uint8_t* d_big_scratch = nullptr;
+    // CUDA events around the session kernel of the most recent kTimedRuns runs (ring), recorded on the
+    // launching stream so bench.py can read per-launch durations after its timed region without syncing inside it
+    cudaEvent_t ev0[32] = {}, ev1[32] = {};
+    int64_t runs = 0;
+};
+constexpr int kTimedRuns = 32;
+
+constexpr int kLanes = 2;
+
+struct HostSlot;   // ga_host_pipeline.cu
+
+struct ga_engine {
+    int device = 0;
+    int n_sm = 0;
+    std::string err;
+    std::map<int, RefEntry> refs;
+    Lane lanes[kLanes];
+    int64_t big_bytes_per_cta = 0; int big_ctas = 0;
+    int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
+    int64_t launches = 0;
+    HostSlot* slots = nullptr;           // lazily created by ga_run_host
+    int64_t last_h2d = 0, last_d2h = 0;
+};
+
+int ga_fail(ga_engine* e, int code, const char* what, cudaError_t ce = cudaSuccess);
+#define GA_CUDA(call) do { cudaError_t _ce = (call); if (_ce != cudaSuccess) return ga_fail(e, GA_ERR_CUDA, #call, _ce); } while (0)
+
+// ga_run on an explicit lane (ga_run itself uses lane 0).
+int ga_run_lane(ga_engine* e, int lane, const ga_reads* reads, const ga_sessions* sessions, ga_result* result, cudaStream_t st);
+void ga_host_slots_destroy(ga_engine* e);

@@ -153,6 +153,11 @@ class Engine:
     def last_kernel_ms(self) -> float:
         return float(self._L.ga_last_kernel_ms(self._h))
 
+    def kernel_ms_history(self, n: int = 32):
+        buf = (C.c_float * n)()
+        k = int(self._L.ga_kernel_ms_history(self._h, buf, n))
+        return [float(buf[i]) for i in range(k)]
+
     def upload_reference(self, contig_id: int, bases) -> None:
         """bases: str / bytes (host) or a uint8 CUDA tensor of ASCII codes."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -190,3 +195,120 @@ class Engine:
             torch.cuda.synchronize(self.device)
             self.check_device_status(dres)
             return dres.to_host()
+
+
+def _to_host_batch(db: DeviceBatch) -> ReadBatch:
+    """Copy a device-resident batch back to host arrays (tests, CPU baseline sampling)."""
+    u32 = lambda t: t.cpu().numpy().view(np.uint32)
+    n_cigar = int(db.cigar_off[-1].item())
+    return ReadBatch(n_tumor=db.n_tumor, pos=db.pos.cpu().numpy(), len_flag=u32(db.len_flag), seq_off16=u32(db.seq_off16),
+                     cigar_off=u32(db.cigar_off), cigar=u32(db.cigar[:n_cigar]), seq4=db.seq4[:db.seq4_bytes].cpu().numpy(),
+                     qual=None if db.qual is None else db.qual.cpu().numpy(), max_ref_span=db.max_ref_span,
+                     contig_id=db.contig_id,
+                     qual_reads=None if db.qual_reads is None else db.qual_reads.cpu().numpy(),
+                     qual_off16=None if db.qual_off16 is None else u32(db.qual_off16))
+
+
+def _to_host_sessions(ds: DeviceSessions) -> SessionTable:
+    n = ds.n_sessions
+    c = lambda t, k=n: t[:k].cpu().numpy()
+    return SessionTable(c(ds.first), c(ds.last), c(ds.keep_type), c(ds.keep_pos), c(ds.keep_end), c(ds.keep_len),
+                        c(ds.keep_allele_off, n + 1).view(np.uint32), ds.keep_alleles.cpu().numpy())
+
+
+DeviceBatch.to_host = _to_host_batch
+DeviceSessions.to_host = _to_host_sessions
+
+
+class HostBatch:
+    """A ReadBatch + SessionTable in pinned host memory: what the reference-facing plugin hands to ga_run_host."""
+
+    def __init__(self, batch: ReadBatch, sessions: SessionTable, pin: bool = True):
+        def pin_arr(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+            if pin and torch.cuda.is_available():
+                t = t.pin_memory()
+            return t
+        self.batch, self.sessions = batch, sessions
+        b, s = batch, sessions
+        self._t = {k: pin_arr(getattr(b, k)) for k in ("pos", "len_flag", "seq_off16", "cigar_off", "cigar", "seq4", "qual", "qual_reads", "qual_off16")}
+        self._s = {k: pin_arr(getattr(s, k)) for k in ("first", "last", "keep_type", "keep_pos", "keep_end", "keep_len", "keep_allele_off", "keep_alleles")}
+        # CIGAR / seq4 slices are copied with their natural sizes; keep 64 spare bytes mapped behind seq4
+        self.bytes = sum(t.numel() for t in self._t.values() if t is not None) + sum(t.numel() for t in self._s.values())
+
+    def reads_struct(self) -> _abi.GaReads:
+        p = lambda k: self._t[k].data_ptr() if self._t[k] is not None else None
+        b = self.batch
+        r = _abi.GaReads()
+        r.n_reads, r.n_tumor = b.n_reads, b.n_tumor
+        r.pos, r.len_flag, r.seq_off16, r.cigar_off, r.cigar = p("pos"), p("len_flag"), p("seq_off16"), p("cigar_off"), p("cigar")
+        r.seq4, r.qual, r.seq4_bytes = p("seq4"), p("qual"), int(b.seq4.shape[0])
+        r.n_qual = 0 if b.qual_reads is None else int(b.qual_reads.shape[0])
+        r.qual_reads, r.qual_off16 = p("qual_reads"), p("qual_off16")
+        r.max_ref_span, r.contig_id = int(b.max_ref_span), int(b.contig_id)
+        return r
+
+    def sessions_struct(self) -> _abi.GaSessions:
+        p = lambda k: self._s[k].data_ptr()
+        s = _abi.GaSessions()
+        s.n_sessions = self.sessions.n_sessions
+        s.first, s.last, s.keep_type, s.keep_pos = p("first"), p("last"), p("keep_type"), p("keep_pos")
+        s.keep_end, s.keep_len, s.keep_allele_off, s.keep_alleles = p("keep_end"), p("keep_len"), p("keep_allele_off"), p("keep_alleles")
+        return s
+
+
+class HostResult:
+    """Caller-owned host output buffers (pinned) for ga_run_host."""
+
+    def __init__(self, n_sessions, cap_records, cap_seq16, cap_qual16, pin: bool = True):
+        def buf(nbytes):
+            t = torch.zeros(max(16, int(nbytes)), dtype=torch.uint8)
+            return t.pin_memory() if pin and torch.cuda.is_available() else t
+        self.n_sessions = n_sessions
+        self.cap_records, self.cap_seq16, self.cap_qual16 = int(cap_records), int(cap_seq16), int(cap_qual16)
+        self.mod_session, self.mod_read, self.mod_len = buf(4 * cap_records), buf(4 * cap_records), buf(4 * cap_records)
+        self.mod_seq_off16, self.mod_qual_off16 = buf(4 * cap_records), buf(4 * cap_records)
+        self.out_seq4, self.out_qual = buf(16 * cap_seq16), buf(32 * cap_qual16)
+        self.sess_counts = buf(16 * max(1, n_sessions))
+        self.totals = _abi.GaTotals()
+
+    def as_struct(self) -> _abi.GaResult:
+        r = _abi.GaResult()
+        r.cap_records, r.cap_seq16, r.cap_qual16 = self.cap_records, self.cap_seq16, self.cap_qual16
+        r.mod_session, r.mod_read, r.mod_len = self.mod_session.data_ptr(), self.mod_read.data_ptr(), self.mod_len.data_ptr()
+        r.mod_seq_off16, r.mod_qual_off16 = self.mod_seq_off16.data_ptr(), self.mod_qual_off16.data_ptr()
+        r.out_seq4, r.out_qual, r.sess_counts = self.out_seq4.data_ptr(), self.out_qual.data_ptr(), self.sess_counts.data_ptr()
+        r.totals = C.addressof(self.totals)
+        return r
+
+    def decode(self) -> MaskResult:
+        t = self.totals
+        n = int(t.n_modified)
+        v = lambda x, dt, k: x.numpy().view(dt)[:k]
+        return decode_result(self.n_sessions, t, v(self.mod_session, np.int32, n), v(self.mod_read, np.int32, n),
+                             v(self.mod_len, np.uint32, n), v(self.mod_seq_off16, np.uint32, n), v(self.mod_qual_off16, np.uint32, n),
+                             self.out_seq4.numpy()[:int(t.seq16_used) * 16], self.out_qual.numpy()[:int(t.qual16_used) * 32],
+                             v(self.sess_counts, np.uint32, self.n_sessions * 4))
+
+
+def _run_host(self, hb: HostBatch, hres: HostResult, chunk_sessions: int = 0) -> _abi.GaTotals:
+    """Host buffers in, host buffers out: chunked H2D / kernels / D2H inside the C library (ga_run_host)."""
+    R, S, O = hb.reads_struct(), hb.sessions_struct(), hres.as_struct()
+    st = self._L.ga_run_host(self._h, C.byref(R), C.byref(S), C.byref(O), int(chunk_sessions))
+    if st != _abi.GA_OK:
+        t = hres.totals
+        _abi.raise_for_status(st, f"{self._L.ga_last_error(self._h).decode()} (device status {t.error} at {t.error_detail}; "
+                                  f"needs records={t.n_modified} seq16={t.seq16_used} qual16={t.qual16_used})")
+    return hres.totals
+
+
+def _host_traffic(self):
+    a, b = C.c_int64(0), C.c_int64(0)
+    self._L.ga_last_host_traffic(self._h, C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+Engine.run_host = _run_host
+Engine.host_traffic = _host_traffic
