@@ -10,7 +10,7 @@
 #include <algorithm>
 
 #include "ga_engine_internal.h"
-#include "ga_session_kernel.cuh"
+#include "ga_session_v2.cuh"
 
 namespace ga {
 
@@ -80,7 +80,8 @@ __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* _
     if (d.t_end > d.t_begin) ops += (int64_t)B.cigar_off[d.t_end] - B.cigar_off[d.t_begin];
     if (d.n_end > d.n_begin) ops += (int64_t)B.cigar_off[d.n_end] - B.cigar_off[d.n_begin];
     d.obs_bound = (int32_t)max((int64_t)0, ops - n_range);
-    d.big = (d.n_cols > kColsCap || n_range > kReadsCap || d.obs_bound > kObsCap) ? 1 : 0;
+    // oversize sessions go to the global-scratch kernel; table overflows found at run time join them
+    d.big = (d.n_cols > kCols2 || n_range > kReads2) ? 1 : 0;
     if (n_range == 0) { d.n_cols = 0; d.big = 0; }
     descs[s] = d;
     if (d.big) big_list[atomicAdd(n_big, 1)] = s;
@@ -140,7 +141,8 @@ int ga_engine_create(int device, ga_engine** out) {
         if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
         for (int k = 0; k < kTimedRuns; ++k) { cudaEventCreate(&e->lanes[l].ev0[k]); cudaEventCreate(&e->lanes[l].ev1[k]); }
     }
-    cudaFuncSetAttribute(ga::session_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemLayout));
+    cudaFuncSetAttribute(ga::session_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::Smem2));
+    cudaFuncSetAttribute(ga::session_kernel_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = e;
     return GA_OK;
 }
@@ -279,10 +281,10 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     ga::BigScratch scr;
     scr.base = L.d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
     scr.cols_cap = e->big_cols_cap; scr.reads_cap = e->big_reads_cap; scr.obs_cap = e->big_obs_cap;
-    const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 2, S->n_sessions);
+    const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 4, S->n_sessions);
     const int tslot = (int)(L.runs % kTimedRuns);
     GA_CUDA(cudaEventRecord(L.ev0[tslot], st));
-    ga::session_kernel<false><<<grid_small, ga::kThreads, sizeof(ga::SmemLayout), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets);
+    ga::session_kernel_v2<<<grid_small, ga::kThreads, sizeof(ga::Smem2), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, d_tickets);
     GA_CUDA(cudaEventRecord(L.ev1[tslot], st));
     L.runs++;
     ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);

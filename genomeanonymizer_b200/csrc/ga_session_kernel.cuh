@@ -162,6 +162,7 @@ __device__ __forceinline__ int find_my_obs(const SessCtx& c, int col, uint32_t i
 // Walks the read once: detects germline SNV hits and collects the germline indel edits in application
 // order (all DELs, then all INSs: stable sort by VariantType value, anonymizer_methods.py:264).
 // Returns the new length; *any_snv, *n_edits report what was found.
+template <bool SCAN_SNV = true>
 __device__ int analyse_read(const SessCtx& c, int i, int64_t r, Edit* edits, int* n_edits, bool* any_snv, bool* too_many) {
     const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
     const int pos = __ldg(c.B.pos + r);
@@ -176,9 +177,10 @@ __device__ int analyse_read(const SessCtx& c, int i, int64_t r, Edit* edits, int
             const uint32_t w = __ldg(c.B.cigar + ci), op = w & 15u;
             const int ln = (int)(w >> 4);
             if (op == 0u || op == 7u || op == 8u) {
-                scan_segment(rec, c.B.ref4, q, q + ln, rc, [&](int, int rp, uint32_t b, uint32_t) {
-                    if ((c.T.snv[rp - c.d.col_begin] >> b) & 1u) hit = true;
-                });
+                if (SCAN_SNV)
+                    scan_segment(rec, c.B.ref4, q, q + ln, rc, [&](int, int rp, uint32_t b, uint32_t) {
+                        if ((c.T.snv[rp - c.d.col_begin] >> b) & 1u) hit = true;
+                    });
                 q += ln; rc += ln; ccl += ln;
             } else if (op == 2u) {
                 if (find_my_obs(c, rc - c.d.col_begin, 0u, i) >= 0) {

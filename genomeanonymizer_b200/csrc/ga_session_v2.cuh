@@ -1,0 +1,549 @@
+// ga_session_v2.cuh - the production session kernel: persistent CTAs, one session (= one anonymize() call of
+// the reference, anonymizer_methods.py:431-535) at a time per CTA, working set in shared memory.
+//
+// Differences from the first kernel (ga_session_kernel.cuh, kept as the global-scratch fallback for
+// oversize sessions):
+//   * clean reads (one M/=/X op covering the whole read - the overwhelming majority) take a vector path:
+//     the record is fetched with 128-bit loads, compared against the 4-bit reference 32 bases at a time,
+//     and only mismatching words are looked at nibble by nibble;
+//   * discovery appends every SNV candidate to an entry list, so after the germline set is resolved the
+//     modified reads are found from the entries instead of re-walking every candidate read;
+//   * per-session counters are warp-reduced, the next session's ticket is fetched while the current one
+//     runs, and the three output cursors are scanned together: 7 block barriers per session instead of ~20;
+//   * modified records are written by one warp each with coalesced word-per-lane accesses ("vectorised
+//     substitution"), indel-masked ones through a shared-memory staging of the SNV-masked sequence;
+//   * the working set is 54 KB, so four CTAs (32 warps) share an SM.
+#pragma once
+#include "ga_session_kernel.cuh"
+
+namespace ga {
+
+constexpr int kCols2 = 3072;           // allele-table columns per session
+constexpr int kReads2 = 4096;          // candidate reads per session
+constexpr int kObs2 = 768;             // indel observations per session
+constexpr int kEnt2 = 3072;            // SNV candidate entries per session
+constexpr int kMod2 = 768;            // modified reads per session
+constexpr int kStageWords = 64;        // per-warp staging of an SNV-masked record (reads up to 512 bases)
+
+struct Smem2 {
+    uint32_t snv[kCols2];
+    int32_t ihead[kCols2];
+    uint32_t ent[kEnt2];               // (session-relative read << 16) | (column << 4) | base code; dead after phase M,
+                                       // then reused as clist | msize | mseq | mqual, kMod2 words each
+    uint32_t modbits[kReads2 / 32];
+    uint32_t indelbits[kReads2 / 32];
+    int32_t o_col[kObs2];
+    uint32_t o_meta[kObs2];
+    uint32_t o_read[kObs2];
+    int32_t o_irp[kObs2];
+    int32_t o_next[kObs2];
+    uint32_t stage[kThreads / 32][kStageWords];
+};
+static_assert(kEnt2 >= 4 * kMod2, "clist, msize, mseq and mqual alias the entry list");
+
+__device__ __forceinline__ uint4 ldg128(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg128(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t tail_mask(int L, int word) {           // valid nibbles of query word `word`
+    const int nv = L - word * 8;
+    return nv >= 8 ? 0xffffffffu : (nv <= 0 ? 0u : (0xffffffffu >> ((8 - nv) * 4)));
+}
+
+// Record words [0, 4U) of a clean read plus a bitmask of the words that differ from the reference.
+// Only the record stays in registers; a mismatching word re-fetches its reference word (an L1 hit).
+template <int U>
+struct CleanRead {
+    uint32_t rw[4 * U];
+    __device__ __forceinline__ uint32_t load(const uint4* __restrict__ rec, const uint32_t* __restrict__ ref4, int pos, int L) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint4 v = ldg128(rec + u);
+            rw[4 * u] = v.x; rw[4 * u + 1] = v.y; rw[4 * u + 2] = v.z; rw[4 * u + 3] = v.w;
+        }
+        const int64_t ni = (int64_t)pos + 8;
+        const uint32_t* rp = ref4 + (ni >> 3);
+        const uint32_t sh = (uint32_t)(ni & 7) * 4u;
+        uint32_t prev = __ldg(rp);
+        uint32_t wm = 0u;
+#pragma unroll
+        for (int k = 0; k < 4 * U; ++k) {
+            const uint32_t next = __ldg(rp + k + 1);
+            const uint32_t fw = __funnelshift_r(prev, next, sh);     // sh == 0 returns prev
+            prev = next;
+            if (k >= 4 * (U - 1)) {                                   // only the last unit can hold padding
+                rw[k] &= tail_mask(L, k);
+                if ((rw[k] ^ fw) & tail_mask(L, k)) wm |= 1u << k;
+            } else if (rw[k] != fw) wm |= 1u << k;
+        }
+        return wm;
+    }
+};
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+struct DiscoverAcc { uint32_t reads, bases; bool overflow; };
+
+// ------------------------------------------------------------------ discovery, clean read
+template <int U>
+__device__ __forceinline__ void discover_clean(const SessCtx& c, Smem2* sm, int i, int64_t r, int pos, int L, uint32_t ds,
+                                               uint32_t* n_ent, DiscoverAcc& acc) {
+    CleanRead<U> cr;
+    const uint4* rec = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * __ldg(c.B.seq_off16 + r));
+    const uint32_t wm = cr.load(rec, c.B.ref4, pos, L);
+    if (wm == 0u) return;
+    const int colb = pos - c.d.col_begin;
+#pragma unroll
+    for (int k = 0; k < 4 * U; ++k) {
+        if (!((wm >> k) & 1u)) continue;
+        const uint32_t fw = ref_word(c.B.ref4, (int64_t)pos + 8 * k);
+        uint32_t x = (cr.rw[k] ^ fw) & tail_mask(L, k);
+        while (x) {
+            const int n = (__ffs(x) - 1) >> 2;
+            x &= ~(0xfu << (n * 4));
+            const uint32_t b = (cr.rw[k] >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+            if (b != 15u && is_acgt(rf)) {                               // variation_classifier.py:147-150
+                const int col = colb + 8 * k + n;
+                atomicOr(&sm->snv[col], 1u << (b + 16u * ds));
+                const uint32_t e = atomicAdd(n_ent, 1u);
+                if (e < (uint32_t)kEnt2) sm->ent[e] = ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
+                else acc.overflow = true;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ discovery, any read
+__device__ void discover_read2(const SessCtx& c, Smem2* sm, int i, uint32_t* n_obs, uint32_t* n_ent, DiscoverAcc& acc) {
+    const int64_t r = read_of(c, i);
+    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+    const int pos = __ldg(c.B.pos + r);
+    const uint32_t lf = __ldg(c.B.len_flag + r);
+    const int L = (int)(lf & 0xffffu);
+    const uint32_t ds = i < c.nt ? 0u : 1u;
+    const uint32_t w0 = c1 > c0 ? __ldg(c.B.cigar + c0) : 0u;
+    const uint32_t op0 = w0 & 15u;
+    const bool clean = (c1 - c0 == 1u) && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(w0 >> 4) == L);
+    const int span = clean ? L : ref_span_of(c.B.cigar, c0, c1);
+    if (pos + span <= c.first) return;                                   // fetched by range, does not reach the region
+    acc.reads += 1u; acc.bases += (uint32_t)L;
+    if ((int64_t)pos + span > c.B.ref_len || pos < 0 || pos < c.d.col_begin || pos + span - c.d.col_begin >= c.d.n_cols) {
+        raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
+        return;
+    }
+    if (clean) {
+        const int units = (L + 31) >> 5;
+        switch (units) {
+            case 5: discover_clean<5>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
+            case 4: discover_clean<4>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
+            case 3: discover_clean<3>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
+            case 8: discover_clean<8>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
+            default: break;
+        }
+    }
+    const uint32_t* rec = rec_of(c, r);
+    int rc = pos, q = 0, ccl = 0, rcb = 0;
+    for (uint32_t ci = c0; ci < c1; ++ci) {
+        const uint32_t w = __ldg(c.B.cigar + ci), op = w & 15u;
+        const int ln = (int)(w >> 4);
+        if (op == 0u || op == 7u || op == 8u) {
+            if (q + ln > L) { raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r); return; }
+            scan_segment(rec, c.B.ref4, q, q + ln, rc, [&](int, int rp, uint32_t b, uint32_t) {
+                const int col = rp - c.d.col_begin;
+                atomicOr(&sm->snv[col], 1u << (b + 16u * ds));
+                const uint32_t e = atomicAdd(n_ent, 1u);
+                if (e < (uint32_t)kEnt2) sm->ent[e] = ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
+                else acc.overflow = true;
+            });
+            q += ln; rc += ln; ccl += ln;
+        } else if (op == 1u || op == 2u) {
+            const uint32_t slot = atomicAdd(n_obs, 1u);
+            if (slot >= (uint32_t)kObs2) { acc.overflow = true; return; }
+            const int col = rc - c.d.col_begin;
+            sm->o_col[slot] = col;
+            sm->o_meta[slot] = (op == 1u ? kMetaIns : 0u) | (ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+            sm->o_read[slot] = (uint32_t)i;
+            sm->o_irp[slot] = ccl + rcb;                                  // variation_classifier.py:82
+            __threadfence_block();
+            sm->o_next[slot] = atomicExch(&sm->ihead[col], (int)slot);
+            if (op == 1u) { q += ln; rcb += ln; } else { rc += ln; ccl += ln; rcb -= ln; }
+        } else if (op == 3u) { rc += ln; ccl += ln; }
+        else if (op == 4u) { q += ln; rcb += ln; }
+        else if (op == 5u) { rcb += ln; }
+    }
+}
+
+// ------------------------------------------------------------------ warp-cooperative emission
+// One warp writes one modified record.  Lane w owns query words w, w+32, ...: it takes the record word,
+// finds the aligned (M/=/X) segments that overlap its 8 bases, and replaces every base whose allele is in
+// the germline set by the reference base (anonymizer_methods.py:170-176).  Loads and stores are coalesced.
+template <class Store>
+__device__ __forceinline__ void masked_words(const SessCtx& c, const Smem2* sm, int64_t r, int pos, int L, uint32_t c0, uint32_t c1,
+                                             int n_words, int lane, Store&& store) {
+    const uint32_t* rec = rec_of(c, r);
+    for (int w = lane; w < n_words; w += 32) {
+        const int qb = w << 3;
+        uint32_t v = qb < L ? (__ldg(rec + w) & tail_mask(L, w)) : 0u;
+        if (qb < L) {
+            int rc = pos, q = 0;
+            for (uint32_t ci = c0; ci < c1; ++ci) {
+                const uint32_t cw = __ldg(c.B.cigar + ci), op = cw & 15u;
+                const int ln = (int)(cw >> 4);
+                if (op == 0u || op == 7u || op == 8u) {
+                    const int lo = max(q, qb), hi = min(min(q + ln, qb + 8), L);
+                    if (lo < hi) {
+                        const int p0 = rc - q + qb;                       // reference position of query base qb under this segment
+                        const uint32_t fw = ref_word(c.B.ref4, (int64_t)p0);
+                        uint32_t mask = 0xffffffffu;
+                        if (lo > qb) mask &= 0xffffffffu << ((lo - qb) * 4);
+                        if (hi < qb + 8) mask &= 0xffffffffu >> ((qb + 8 - hi) * 4);
+                        uint32_t x = (v ^ fw) & mask;
+                        while (x) {
+                            const int n = (__ffs(x) - 1) >> 2;
+                            x &= ~(0xfu << (n * 4));
+                            const uint32_t b = (v >> (n * 4)) & 15u;
+                            if (b != 15u && ((sm->snv[p0 + n - c.d.col_begin] >> b) & 1u))
+                                v = (v & ~(0xfu << (n * 4))) | (((fw >> (n * 4)) & 15u) << (n * 4));
+                        }
+                    }
+                    q += ln; rc += ln;
+                } else if (op == 1u || op == 4u) q += ln;
+                else if (op == 2u || op == 3u) rc += ln;
+                if (q >= qb + 8) break;
+            }
+        }
+        store(w, v);
+    }
+}
+
+__device__ __forceinline__ void write_record_meta(const ResultView& O, uint64_t rec_idx, int s, int64_t r, int new_len, uint64_t seq16, uint32_t qual16) {
+    O.mod_session[rec_idx] = s;
+    O.mod_read[rec_idx] = (int32_t)r;
+    O.mod_len[rec_idx] = (uint32_t)new_len;
+    O.mod_seq_off16[rec_idx] = (uint32_t)seq16;
+    O.mod_qual_off16[rec_idx] = qual16;
+}
+
+// SNV-only record: sequence rewritten in place of the copy, qualities untouched (AM.py:170-176).
+__device__ __forceinline__ void emit_snv_warp(const SessCtx& c, const Smem2* sm, const ResultView& O, int64_t r, uint64_t rec_idx, uint64_t seq16,
+                                              int L, int lane) {
+    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+    const int pos = __ldg(c.B.pos + r);
+    int units = (L + 31) >> 5; if (units < 1) units = 1;
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+    masked_words(c, sm, r, pos, L, c0, c1, units * 4, lane, [&](int w, uint32_t v) { oseq[w] = v; });
+    if (lane == 0) write_record_meta(O, rec_idx, c.s, r, L, seq16, 0xffffffffu);
+}
+
+// Indel-masked record: the SNV-masked sequence is staged in shared memory, then every output base / quality
+// is pulled through the backward index map of the edits (all DELs, then all INSs, at original offsets:
+// anonymizer_methods.py:254-270, 178-203).  One base (one quality) per lane and iteration.
+__device__ void emit_indel_warp(const SessCtx& c, Smem2* sm, const ResultView& O, int i, int64_t r, uint64_t rec_idx, uint64_t seq16, uint64_t qual16,
+                                int new_len, int lane, int warp) {
+    const uint32_t lf = __ldg(c.B.len_flag + r);
+    const int L = (int)(lf & 0xffffu);
+    if (((L + 7) >> 3) > kStageWords) {                              // very long read: single-lane fallback
+        if (lane == 0) emit_read(c, O, i, r, rec_idx, seq16, qual16, new_len, true);
+        return;
+    }
+    Edit edits[GA_MAX_EDITS];
+    int ne = 0; bool any_snv = false, too_many = false;
+    analyse_read<false>(c, i, r, edits, &ne, &any_snv, &too_many);
+    int n_del = 0;
+    while (n_del < ne && !edits[n_del].is_ins) ++n_del;
+    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+    const int pos = __ldg(c.B.pos + r);
+    uint32_t* stage = sm->stage[warp];
+    masked_words(c, sm, r, pos, L, c0, c1, (L + 7) >> 3, lane, [&](int w, uint32_t v) { stage[w] = v; });
+    const uint8_t* qrec = qual_record(c.B, r);
+    if (!qrec) { if (lane == 0) raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); return; }
+    const bool reverse = ((lf >> 16) & 0x10u) != 0u;
+    {   // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (AM.py:193)
+        uint32_t part = 0;
+        for (int k = lane; k < L; k += 32) part += qrec[k];
+        uint32_t sum = warp_sum(part), n = (uint32_t)L;
+        for (int k = 0; k < n_del; ++k) {
+            const uint32_t m = n ? sum / n : 0u;
+            edits[k].mean = m;
+            sum += m * (uint32_t)edits[k].len; n += (uint32_t)edits[k].len;
+            if (lane == 0 && (int64_t)edits[k].pos + edits[k].len > c.B.ref_len) raise_error(c.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
+        }
+    }
+    __syncwarp();
+    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+    for (int j = lane; j < units * 32; j += 32) {
+        uint32_t code = 0u;
+        if (j < new_len) {
+            int kin = 0;
+            const int src = map_back(edits, n_del, ne, j, &kin);
+            code = src >= 0 ? (stage[src >> 3] >> ((src & 7) * 4)) & 15u : ref_code(c.B.ref4, (int64_t)edits[-1 - src].pos + kin);
+        }
+        uint32_t v = code << ((j & 7) * 4);
+        v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        if ((lane & 7) == 0) oseq[j >> 3] = v;
+    }
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    for (int jp = lane; jp < units * 32; jp += 32) {
+        uint32_t qv = 0u;
+        if (jp < new_len) {
+            // printed order = reversed forward-orientation array for reverse reads (anonymizer_methods.py:95,213)
+            const int jf = reverse ? new_len - 1 - jp : jp;
+            int kin = 0;
+            const int src = map_back(edits, n_del, ne, jf, &kin);
+            qv = src >= 0 ? (uint32_t)qrec[reverse ? L - 1 - src : src] : edits[-1 - src].mean;
+        }
+        uint32_t v = qv << ((jp & 3) * 8);
+        v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        if ((lane & 3) == 0) oq[jp >> 2] = v;
+    }
+    if (lane == 0) write_record_meta(O, rec_idx, c.s, r, new_len, seq16, (uint32_t)qual16);
+    __syncwarp();                                                     // stage is reused by this warp's next record
+}
+
+// Block-wide exclusive scan of a 64-bit value per thread.
+__device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned long long v, unsigned long long* tmp, unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) tmp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long s = lane < kThreads / 32 ? tmp[lane] : 0ull;
+        unsigned long long si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long n = __shfl_up_sync(0xffffffffu, si, d);
+            if (lane >= d) si += n;
+        }
+        if (lane < kThreads / 32) tmp[lane] = si - s;
+        if (lane == kThreads / 32 - 1) tmp[kThreads / 32] = si;
+    }
+    __syncthreads();
+    *total = tmp[kThreads / 32];
+    return tmp[warp] + inc - v;
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+                                                                 int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
+                                                                 ResultView O, unsigned int* __restrict__ ticket) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Smem2* sm = reinterpret_cast<Smem2*>(smem_raw);
+    __shared__ unsigned long long s_scan64[kThreads / 32 + 1];
+    __shared__ uint32_t s_scan[kThreads / 32 + 1];
+    __shared__ uint32_t s_nobs, s_nent, s_reads, s_bases, s_cnt[3], s_overflow;
+    __shared__ int s_next_session;
+    __shared__ unsigned long long s_base[3];
+
+    SessCtx c;
+    c.B = B;
+    c.totals = O.totals;
+    c.T.snv = sm->snv; c.T.ihead = sm->ihead; c.T.cand = sm->modbits;
+    c.T.o_col = sm->o_col; c.T.o_meta = sm->o_meta; c.T.o_read = sm->o_read; c.T.o_irp = sm->o_irp; c.T.o_next = sm->o_next;
+    uint32_t* const clist = sm->ent; uint32_t* const msize = sm->ent + kMod2;
+    uint32_t* const mseq = sm->ent + 2 * kMod2; uint32_t* const mqual = sm->ent + 3 * kMod2;
+    c.T.clist = clist; c.T.msize = msize;
+    c.T.obs_cap = kObs2; c.T.reads_cap = kReads2; c.T.cols_cap = kCols2;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_work = S.n_sessions;
+
+    if (tid == 0) s_next_session = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    for (;;) {
+        const int s = s_next_session;
+        if (s >= n_work) break;
+        c.d = descs[s];
+        const int n_cols = c.d.n_cols;
+        c.s = s;
+        c.nt = c.d.t_end - c.d.t_begin;
+        c.n_range = c.nt + (c.d.n_end - c.d.n_begin);
+        const int n_cw = (c.n_range + 31) >> 5;
+        // ---- zero the working set (skipped for sessions the fallback kernel owns)
+        if (!c.d.big) {
+            for (int k = tid; k < n_cols; k += kThreads) { sm->snv[k] = 0u; sm->ihead[k] = -1; }
+            for (int k = tid; k < n_cw; k += kThreads) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; }
+        }
+        __syncthreads();                                              // every thread has read s_next_session
+        if (tid == 0) {
+            s_next_session = (int)atomicAdd(ticket, 1u);              // prefetch the next ticket
+            s_nobs = 0; s_nent = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
+        }
+        if (c.d.big) { __syncthreads(); continue; }
+        c.first = S.first[s];
+        c.keep_type = S.keep_type[s]; c.keep_pos = S.keep_pos[s]; c.keep_end = S.keep_end[s]; c.keep_len = S.keep_len[s];
+        c.keep_allele = S.keep_alleles + S.keep_allele_off[s];
+        c.keep_alen = (int)(S.keep_allele_off[s + 1] - S.keep_allele_off[s]);
+        __syncthreads();
+
+        // ---- phase A: discover
+        {
+            DiscoverAcc acc; acc.reads = 0; acc.bases = 0; acc.overflow = false;
+            for (int i = tid; i < c.n_range; i += kThreads) discover_read2(c, sm, i, &s_nobs, &s_nent, acc);
+            const uint32_t wr = warp_sum(acc.reads), wb = warp_sum(acc.bases);
+            if (lane == 0 && wr) { atomicAdd(&s_reads, wr); atomicAdd(&s_bases, wb); }
+            if (acc.overflow) s_overflow = 1u;
+        }
+        __syncthreads();
+        if (s_overflow) {                                             // tables too small: hand the session to the fallback kernel
+            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            __syncthreads();
+            continue;
+        }
+        const int n_obs = (int)s_nobs;
+        const int n_ent = (int)s_nent;
+
+        // ---- phase R: germline = seen in tumor AND normal, minus variant_to_keep (AM.py:546-547)
+        {
+            uint32_t keep_bit = 0u; int keep_col = -1;
+            if (c.keep_type == GA_VT_SNV && c.keep_end == c.keep_pos && c.keep_len == 1 && c.keep_alen == 1) {
+                const char* code2asc = "=ACMGRSVTWYHKDBN";
+                const uint8_t ch = c.keep_allele[0];
+                for (int k = 0; k < 16; ++k) if ((uint8_t)code2asc[k] == ch) { keep_bit = 1u << k; keep_col = c.keep_pos - c.d.col_begin; }
+            }
+            uint32_t cnt = 0;
+            for (int k = tid; k < n_cols; k += kThreads) {
+                const uint32_t w = sm->snv[k];
+                uint32_t g = (w & (w >> 16)) & 0xffffu;
+                if (k == keep_col) g &= ~keep_bit;
+                sm->snv[k] = g;
+                cnt += __popc(g);
+            }
+            cnt = warp_sum(cnt);
+            if (lane == 0 && cnt) atomicAdd(&s_cnt[0], cnt);
+        }
+        for (int o = tid; o < n_obs; o += kThreads) {                 // indels: exact key equality (variants.py:83-96)
+            const uint32_t m = sm->o_meta[o];
+            bool germ = false, rep = true;
+            for (int o2 = sm->ihead[sm->o_col[o]]; o2 >= 0; o2 = sm->o_next[o2]) {
+                if (o2 == o) continue;
+                if (!obs_equal(c, o, o2)) continue;
+                if ((sm->o_meta[o2] ^ m) & kMetaDs) germ = true;
+                if (o2 < o) rep = false;
+            }
+            if (germ && obs_equals_keep(c, o)) germ = false;
+            if (germ) {
+                atomicOr(&sm->o_meta[o], kMetaGerm | (rep ? kMetaRep : 0u));
+                if (rep) atomicAdd(&s_cnt[(m & kMetaIns) ? 2 : 1], 1u);
+                const uint32_t i = sm->o_read[o];
+                atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
+                atomicOr(&sm->indelbits[i >> 5], 1u << (i & 31));
+            }
+        }
+        __syncthreads();
+
+        // ---- phase M: reads that carry a germline SNV allele
+        for (int e = tid; e < n_ent; e += kThreads) {
+            const uint32_t w = sm->ent[e];
+            if ((sm->snv[(w >> 4) & 0xfffu] >> (w & 15u)) & 1u) {
+                const uint32_t i = w >> 16;
+                atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
+            }
+        }
+        __syncthreads();
+
+        // ---- phase L: ordered list of the modified reads (n_cw <= 128 words, one per thread)
+        uint32_t n_mod;
+        {
+            const uint32_t bits = tid < n_cw ? sm->modbits[tid] : 0u;
+            uint32_t off = block_exclusive_scan(__popc(bits), s_scan, &n_mod);
+            uint32_t b = bits;
+            while (b) {
+                const int k = __ffs(b) - 1; b &= b - 1;
+                if (off < (uint32_t)kMod2) clist[off] = (uint32_t)(tid * 32 + k);
+                ++off;
+            }
+        }
+        if (n_mod > (uint32_t)kMod2) {
+            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+
+        // ---- phase B1: new length of every modified read; indel-masked reads need the edit analysis
+        const int per = ((int)n_mod + kThreads - 1) / kThreads;
+        const int k0 = min(tid * per, (int)n_mod), k1 = min(k0 + per, (int)n_mod);
+        unsigned long long mine = 0ull;                               // [records:16 | seq units:24 | qual units:24]
+        for (int k = k0; k < k1; ++k) {
+            const int i = (int)clist[k];
+            const int64_t r = read_of(c, i);
+            uint32_t m;
+            if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
+                Edit edits[GA_MAX_EDITS];
+                int ne = 0; bool any_snv = false, too_many = false;
+                const int new_len = analyse_read<false>(c, i, r, edits, &ne, &any_snv, &too_many);
+                if (too_many) raise_error(O.totals, GA_ERR_UNSUPPORTED, (uint32_t)r);
+                m = kModFlag | kQualFlag | ((uint32_t)new_len & kLenMask);
+            } else {
+                m = kModFlag | (__ldg(c.B.len_flag + r) & 0xffffu);
+            }
+            msize[k] = m;
+            uint32_t units = ((m & kLenMask) + 31u) / 32u; if (units < 1u) units = 1u;
+            mine += (1ull << 48) | ((unsigned long long)units << 24) | ((m & kQualFlag) ? (unsigned long long)units : 0ull);
+        }
+        unsigned long long total;
+        const unsigned long long off = block_exclusive_scan64(mine, s_scan64, &total);
+        const uint32_t tot_rec = (uint32_t)(total >> 48), tot_seq = (uint32_t)((total >> 24) & 0xffffffu), tot_qual = (uint32_t)(total & 0xffffffu);
+        if (tid == 0) {
+            s_base[0] = atomicAdd((unsigned long long*)&O.totals->n_modified, (unsigned long long)tot_rec);
+            s_base[1] = atomicAdd((unsigned long long*)&O.totals->seq16_used, (unsigned long long)tot_seq);
+            s_base[2] = atomicAdd((unsigned long long*)&O.totals->qual16_used, (unsigned long long)tot_qual);
+            atomicAdd((unsigned long long*)&O.totals->session_reads, (unsigned long long)s_reads);
+            atomicAdd((unsigned long long*)&O.totals->session_bases, (unsigned long long)s_bases);
+            for (int k = 0; k < 3; ++k) {
+                O.sess_counts[4 * (size_t)s + k] = s_cnt[k];
+                if (s_cnt[k]) atomicAdd((unsigned long long*)&O.totals->masked[k], (unsigned long long)s_cnt[k]);
+            }
+            O.sess_counts[4 * (size_t)s + 3] = s_reads;
+        }
+        __syncthreads();
+        const bool fits = (int64_t)(s_base[0] + tot_rec) <= O.cap_records && (int64_t)(s_base[1] + tot_seq) <= O.cap_seq16 &&
+                          (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
+        if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
+
+        // ---- per-record output offsets (session-relative), then phase B2: one warp per record
+        {
+            uint32_t so = (uint32_t)((off >> 24) & 0xffffffu), qo = (uint32_t)(off & 0xffffffu);
+            for (int k = k0; k < k1; ++k) {
+                const uint32_t m = msize[k];
+                uint32_t units = ((m & kLenMask) + 31u) / 32u; if (units < 1u) units = 1u;
+                mseq[k] = so; mqual[k] = qo;
+                so += units; if (m & kQualFlag) qo += units;
+            }
+        }
+        __syncthreads();
+        uint32_t n_q = 0;
+        for (int k = warp; k < (int)n_mod; k += kThreads / 32) {
+            const uint32_t m = msize[k];
+            const int i = (int)clist[k];
+            const int64_t r = read_of(c, i);
+            if (m & kQualFlag) {
+                emit_indel_warp(c, sm, O, i, r, s_base[0] + k, s_base[1] + mseq[k], s_base[2] + mqual[k], (int)(m & kLenMask), lane, warp);
+                ++n_q;
+            } else {
+                emit_snv_warp(c, sm, O, r, s_base[0] + k, s_base[1] + mseq[k], (int)(m & kLenMask), lane);
+            }
+        }
+        if (lane != 0) n_q = 0;
+        n_q = warp_sum(n_q);
+        if (lane == 0 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
+        __syncthreads();                                              // tables are reused by the next session
+    }
+}
+
+}  // namespace ga
