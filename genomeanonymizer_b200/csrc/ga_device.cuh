@@ -34,6 +34,7 @@ struct SessionDesc {
     int32_t col_begin, n_cols;                // allele-table span (conservative)
     int32_t obs_bound;                        // upper bound on I/D ops among the candidates
     int32_t big;                              // 1: tables live in the CTA's global scratch
+    int32_t qt_begin, qt_end, qn_begin, qn_end; // sparse quality records (ga_reads.qual_reads) of the candidate ranges
 };
 
 // View of one batch + reference, passed by value to kernels.

@@ -83,6 +83,11 @@ __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* _
     // oversize sessions go to the global-scratch kernel; table overflows found at run time join them
     d.big = (d.n_cols > kCols2 || n_range > kReads2) ? 1 : 0;
     if (n_range == 0) { d.n_cols = 0; d.big = 0; }
+    d.qt_begin = d.qt_end = d.qn_begin = d.qn_end = 0;
+    if (B.qual_reads) {
+        d.qt_begin = lower_bound_pos(B.qual_reads, 0, B.n_qual, d.t_begin); d.qt_end = lower_bound_pos(B.qual_reads, d.qt_begin, B.n_qual, d.t_end);
+        d.qn_begin = lower_bound_pos(B.qual_reads, d.qt_end, B.n_qual, d.n_begin); d.qn_end = lower_bound_pos(B.qual_reads, d.qn_begin, B.n_qual, d.n_end);
+    }
     descs[s] = d;
     if (d.big) big_list[atomicAdd(n_big, 1)] = s;
 }

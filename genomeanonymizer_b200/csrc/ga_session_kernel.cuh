@@ -238,6 +238,16 @@ __device__ __forceinline__ const uint8_t* qual_record(const BatchView& B, int64_
     return nullptr;
 }
 
+// Same lookup restricted to the session's slice [lo, hi) of the sparse quality index.
+__device__ __forceinline__ const uint8_t* qual_record_in(const BatchView& B, int64_t r, int64_t lo, int64_t hi) {
+    if (!B.qual) return nullptr;
+    if (!B.qual_reads) return B.qual + 32ull * __ldg(B.seq_off16 + r);
+    int64_t b = lo, e = hi;
+    while (b < e) { const int64_t m = (b + e) >> 1; if (__ldg(B.qual_reads + m) < r) b = m + 1; else e = m; }
+    if (b < hi && __ldg(B.qual_reads + b) == r) return B.qual + 32ull * __ldg(B.qual_off16 + b);
+    return nullptr;
+}
+
 // Maps a final array index back through the edits (last applied first).  Returns the original index,
 // or -1 - (edit index) when the element was inserted by that DEL edit (then *k_in is its offset).
 __device__ __forceinline__ int map_back(const Edit* edits, int n_del, int ne, int j, int* k_in) {

@@ -1,37 +1,45 @@
 // ga_session_v2.cuh - the production session kernel: persistent CTAs, one session (= one anonymize() call of
 // the reference, anonymizer_methods.py:431-535) at a time per CTA, working set in shared memory.
 //
-// Differences from the first kernel (ga_session_kernel.cuh, kept as the global-scratch fallback for
-// oversize sessions):
-//   * clean reads (one M/=/X op covering the whole read - the overwhelming majority) take a vector path:
-//     the record is fetched with 128-bit loads, compared against the 4-bit reference 32 bases at a time,
-//     and only mismatching words are looked at nibble by nibble;
-//   * discovery appends every SNV candidate to an entry list, so after the germline set is resolved the
-//     modified reads are found from the entries instead of re-walking every candidate read;
-//   * per-session counters are warp-reduced, the next session's ticket is fetched while the current one
-//     runs, and the three output cursors are scanned together: 7 block barriers per session instead of ~20;
-//   * modified records are written by one warp each with coalesced word-per-lane accesses ("vectorised
-//     substitution"), indel-masked ones through a shared-memory staging of the SNV-masked sequence;
-//   * the working set is 54 KB, so four CTAs (32 warps) share an SM.
+// Pipeline of one session (block-synchronous phases, 256 threads):
+//   A1 scan      thread per read.  Clean reads (one M/=/X op over the whole read - nearly all of them) are
+//                fetched with 128-bit loads and compared with the 4-bit reference 32 bases per unit; only the
+//                indices of mismatching 8-base words are queued.  Reads with any other CIGAR are queued too.
+//   A2 discover  thread per queued word / queued read, lanes dense: SNV alleles are OR-ed into the
+//                per-column table and appended to an entry list, indel observations chained per column
+//                (variation_classifier.py:52-182).
+//   R  resolve   germline = seen in tumor AND normal, minus variant_to_keep (anonymizer_methods.py:546-547)
+//   M  mark      entries / observations whose allele is germline mark their read as modified
+//   L  list      ordered list of the modified reads, B1 their new lengths, one scan for the output slots
+//   B2 emit      one warp per record, coalesced word-per-lane copies; SNV masking of clean reads is applied
+//                afterwards from the entry list (one 4-bit XOR per hit), other reads are re-walked by their
+//                warp; indel-masked reads go through a shared-memory staging and the backward edit map.
+// The first kernel (ga_session_kernel.cuh) remains as the global-scratch fallback for oversize sessions.
 #pragma once
 #include "ga_session_kernel.cuh"
 
 namespace ga {
 
-constexpr int kCols2 = 3072;           // allele-table columns per session
+constexpr int kCols2 = 2688;           // allele-table columns per session
 constexpr int kReads2 = 4096;          // candidate reads per session
-constexpr int kObs2 = 768;             // indel observations per session
-constexpr int kEnt2 = 3072;            // SNV candidate entries per session
-constexpr int kMod2 = 768;            // modified reads per session
+constexpr int kObs2 = 512;             // indel observations per session
+constexpr int kEnt2 = 2048;            // SNV candidate entries per session
+constexpr int kMod2 = 512;             // modified reads per session
+constexpr int kWords2 = 1024;          // queued mismatching words per session
+constexpr int kGen2 = 1024;            // queued non-clean reads per session
 constexpr int kStageWords = 64;        // per-warp staging of an SNV-masked record (reads up to 512 bases)
 
 struct Smem2 {
-    uint32_t snv[kCols2];
+    uint32_t snv[kCols2];              // bit c: tumor saw base code c, bit 16+c: normal; after resolve: germline codes
     int32_t ihead[kCols2];
-    uint32_t ent[kEnt2];               // (session-relative read << 16) | (column << 4) | base code; dead after phase M,
-                                       // then reused as clist | msize | mseq | mqual, kMod2 words each
+    uint32_t ent[kEnt2];               // (session-relative read << 16) | (column << 4) | base code
+    uint32_t wlist[kWords2];           // (session-relative read << 5) | word index; after phase A2 reused as clist
+    uint32_t lists[3 * kMod2];         // msize | mseq | mqual
+    uint16_t glist[kGen2];
     uint32_t modbits[kReads2 / 32];
     uint32_t indelbits[kReads2 / 32];
+    uint32_t genbits[kReads2 / 32];
+    uint32_t woff[kReads2 / 32];       // modified reads before bitmap word w
     int32_t o_col[kObs2];
     uint32_t o_meta[kObs2];
     uint32_t o_read[kObs2];
@@ -39,15 +47,12 @@ struct Smem2 {
     int32_t o_next[kObs2];
     uint32_t stage[kThreads / 32][kStageWords];
 };
-static_assert(kEnt2 >= 4 * kMod2, "clist, msize, mseq and mqual alias the entry list");
+static_assert(kWords2 >= kMod2, "clist aliases the word queue");
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
-}
-__device__ __forceinline__ void stg128(uint4* p, const uint4& v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ uint32_t tail_mask(int L, int word) {           // valid nibbles of query word `word`
@@ -55,100 +60,118 @@ __device__ __forceinline__ uint32_t tail_mask(int L, int word) {           // va
     return nv >= 8 ? 0xffffffffu : (nv <= 0 ? 0u : (0xffffffffu >> ((8 - nv) * 4)));
 }
 
-// Record words [0, 4U) of a clean read plus a bitmask of the words that differ from the reference.
-// Only the record stays in registers; a mismatching word re-fetches its reference word (an L1 hit).
-template <int U>
-struct CleanRead {
-    uint32_t rw[4 * U];
-    __device__ __forceinline__ uint32_t load(const uint4* __restrict__ rec, const uint32_t* __restrict__ ref4, int pos, int L) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint4 v = ldg128(rec + u);
-            rw[4 * u] = v.x; rw[4 * u + 1] = v.y; rw[4 * u + 2] = v.z; rw[4 * u + 3] = v.w;
-        }
-        const int64_t ni = (int64_t)pos + 8;
-        const uint32_t* rp = ref4 + (ni >> 3);
-        const uint32_t sh = (uint32_t)(ni & 7) * 4u;
-        uint32_t prev = __ldg(rp);
-        uint32_t wm = 0u;
-#pragma unroll
-        for (int k = 0; k < 4 * U; ++k) {
-            const uint32_t next = __ldg(rp + k + 1);
-            const uint32_t fw = __funnelshift_r(prev, next, sh);     // sh == 0 returns prev
-            prev = next;
-            if (k >= 4 * (U - 1)) {                                   // only the last unit can hold padding
-                rw[k] &= tail_mask(L, k);
-                if ((rw[k] ^ fw) & tail_mask(L, k)) wm |= 1u << k;
-            } else if (rw[k] != fw) wm |= 1u << k;
-        }
-        return wm;
-    }
-};
-
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
 }
 
-struct DiscoverAcc { uint32_t reads, bases; bool overflow; };
-
-// ------------------------------------------------------------------ discovery, clean read
+// Bitmask of the 8-base words of a clean read that differ from the reference (U 16-byte units).
 template <int U>
-__device__ __forceinline__ void discover_clean(const SessCtx& c, Smem2* sm, int i, int64_t r, int pos, int L, uint32_t ds,
-                                               uint32_t* n_ent, DiscoverAcc& acc) {
-    CleanRead<U> cr;
-    const uint4* rec = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * __ldg(c.B.seq_off16 + r));
-    const uint32_t wm = cr.load(rec, c.B.ref4, pos, L);
-    if (wm == 0u) return;
-    const int colb = pos - c.d.col_begin;
+__device__ __forceinline__ uint32_t clean_word_mask(const uint4* __restrict__ rec, const uint32_t* __restrict__ ref4, int pos, int L) {
+    uint32_t rw[4 * U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint4 v = ldg128(rec + u);
+        rw[4 * u] = v.x; rw[4 * u + 1] = v.y; rw[4 * u + 2] = v.z; rw[4 * u + 3] = v.w;
+    }
+    const int64_t ni = (int64_t)pos + 8;
+    const uint32_t* rp = ref4 + (ni >> 3);
+    const uint32_t sh = (uint32_t)(ni & 7) * 4u;
+    uint32_t prev = __ldg(rp);
+    uint32_t wm = 0u;
 #pragma unroll
     for (int k = 0; k < 4 * U; ++k) {
-        if (!((wm >> k) & 1u)) continue;
-        const uint32_t fw = ref_word(c.B.ref4, (int64_t)pos + 8 * k);
-        uint32_t x = (cr.rw[k] ^ fw) & tail_mask(L, k);
-        while (x) {
-            const int n = (__ffs(x) - 1) >> 2;
-            x &= ~(0xfu << (n * 4));
-            const uint32_t b = (cr.rw[k] >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
-            if (b != 15u && is_acgt(rf)) {                               // variation_classifier.py:147-150
-                const int col = colb + 8 * k + n;
-                atomicOr(&sm->snv[col], 1u << (b + 16u * ds));
-                const uint32_t e = atomicAdd(n_ent, 1u);
-                if (e < (uint32_t)kEnt2) sm->ent[e] = ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
-                else acc.overflow = true;
-            }
-        }
+        const uint32_t next = __ldg(rp + k + 1);
+        const uint32_t fw = __funnelshift_r(prev, next, sh);             // sh == 0 returns prev
+        prev = next;
+        if (k >= 4 * (U - 1)) {                                           // only the last unit can hold padding
+            if ((rw[k] ^ fw) & tail_mask(L, k)) wm |= 1u << k;
+        } else if (rw[k] != fw) wm |= 1u << k;
     }
+    return wm;
 }
 
-// ------------------------------------------------------------------ discovery, any read
-__device__ void discover_read2(const SessCtx& c, Smem2* sm, int i, uint32_t* n_obs, uint32_t* n_ent, DiscoverAcc& acc) {
+struct Queues { uint32_t* n_words; uint32_t* n_gen; uint32_t* n_ent; uint32_t* n_obs; uint32_t* overflow; };
+
+__device__ __forceinline__ void push_entry(Smem2* sm, const Queues& Q, int i, int col, uint32_t b, uint32_t ds) {
+    atomicOr(&sm->snv[col], 1u << (b + 16u * ds));
+    const uint32_t e = atomicAdd(Q.n_ent, 1u);
+    if (e < (uint32_t)kEnt2) sm->ent[e] = ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
+    else *Q.overflow = 1u;
+}
+
+// ------------------------------------------------------------------ phase A1: one read
+__device__ __forceinline__ void scan_read(const SessCtx& c, Smem2* sm, const Queues& Q, int i, uint32_t& n_reads, uint32_t& n_bases) {
     const int64_t r = read_of(c, i);
     const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
     const int pos = __ldg(c.B.pos + r);
-    const uint32_t lf = __ldg(c.B.len_flag + r);
-    const int L = (int)(lf & 0xffffu);
-    const uint32_t ds = i < c.nt ? 0u : 1u;
+    const int L = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
+    const uint32_t so = __ldg(c.B.seq_off16 + r);
     const uint32_t w0 = c1 > c0 ? __ldg(c.B.cigar + c0) : 0u;
     const uint32_t op0 = w0 & 15u;
-    const bool clean = (c1 - c0 == 1u) && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(w0 >> 4) == L);
-    const int span = clean ? L : ref_span_of(c.B.cigar, c0, c1);
-    if (pos + span <= c.first) return;                                   // fetched by range, does not reach the region
-    acc.reads += 1u; acc.bases += (uint32_t)L;
-    if ((int64_t)pos + span > c.B.ref_len || pos < 0 || pos < c.d.col_begin || pos + span - c.d.col_begin >= c.d.n_cols) {
+    const int units = (L + 31) >> 5;
+    const bool clean = (c1 - c0 == 1u) && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(w0 >> 4) == L) &&
+                       (units == 5 || units == 4 || units == 3 || units == 8);
+    if (!clean) {                                                        // any other CIGAR: queued for phase A2
+        const uint32_t g = atomicAdd(Q.n_gen, 1u);
+        if (g < (uint32_t)kGen2) sm->glist[g] = (uint16_t)i; else *Q.overflow = 1u;
+        atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
+        return;
+    }
+    if (pos + L <= c.first) return;                                      // fetched by range, does not reach the region
+    n_reads += 1u; n_bases += (uint32_t)L;
+    if ((int64_t)pos + L > c.B.ref_len || pos < 0 || pos < c.d.col_begin || pos + L - c.d.col_begin >= c.d.n_cols) {
         raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
         return;
     }
-    if (clean) {
-        const int units = (L + 31) >> 5;
-        switch (units) {
-            case 5: discover_clean<5>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
-            case 4: discover_clean<4>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
-            case 3: discover_clean<3>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
-            case 8: discover_clean<8>(c, sm, i, r, pos, L, ds, n_ent, acc); return;
-            default: break;
-        }
+    const uint4* rec = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * so);
+    uint32_t wm;
+    switch (units) {
+        case 5: wm = clean_word_mask<5>(rec, c.B.ref4, pos, L); break;
+        case 4: wm = clean_word_mask<4>(rec, c.B.ref4, pos, L); break;
+        case 3: wm = clean_word_mask<3>(rec, c.B.ref4, pos, L); break;
+        default: wm = clean_word_mask<8>(rec, c.B.ref4, pos, L); break;
+    }
+    while (wm) {
+        const int k = __ffs(wm) - 1; wm &= wm - 1;
+        const uint32_t e = atomicAdd(Q.n_words, 1u);
+        if (e < (uint32_t)kWords2) sm->wlist[e] = ((uint32_t)i << 5) | (uint32_t)k; else *Q.overflow = 1u;
+    }
+}
+
+// ------------------------------------------------------------------ phase A2: one queued word of a clean read
+__device__ __forceinline__ void discover_word(const SessCtx& c, Smem2* sm, const Queues& Q, uint32_t item) {
+    const int i = (int)(item >> 5), k = (int)(item & 31u);
+    const int64_t r = read_of(c, i);
+    const int pos = __ldg(c.B.pos + r);
+    const int L = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
+    const uint32_t rw = __ldg(rec_of(c, r) + k);
+    const uint32_t fw = ref_word(c.B.ref4, (int64_t)pos + 8 * k);
+    uint32_t x = (rw ^ fw) & tail_mask(L, k);
+    const uint32_t ds = i < c.nt ? 0u : 1u;
+    const int colb = pos - c.d.col_begin + 8 * k;
+    while (x) {
+        const int n = (__ffs(x) - 1) >> 2;
+        x &= ~(0xfu << (n * 4));
+        const uint32_t b = (rw >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+        if (b != 15u && is_acgt(rf)) push_entry(sm, Q, i, colb + n, b, ds);   // variation_classifier.py:147-150
+    }
+}
+
+// ------------------------------------------------------------------ phase A2: one queued non-clean read
+__device__ void discover_generic(const SessCtx& c, Smem2* sm, const Queues& Q, int i, uint32_t& n_reads, uint32_t& n_bases) {
+    const int64_t r = read_of(c, i);
+    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+    const int pos = __ldg(c.B.pos + r);
+    const int L = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
+    const uint32_t ds = i < c.nt ? 0u : 1u;
+    const int span = ref_span_of(c.B.cigar, c0, c1);
+    if (pos + span <= c.first) return;
+    n_reads += 1u; n_bases += (uint32_t)L;
+    if ((int64_t)pos + span > c.B.ref_len || pos < 0 || pos < c.d.col_begin || pos + span - c.d.col_begin >= c.d.n_cols) {
+        raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
+        return;
     }
     const uint32_t* rec = rec_of(c, r);
     int rc = pos, q = 0, ccl = 0, rcb = 0;
@@ -157,17 +180,11 @@ __device__ void discover_read2(const SessCtx& c, Smem2* sm, int i, uint32_t* n_o
         const int ln = (int)(w >> 4);
         if (op == 0u || op == 7u || op == 8u) {
             if (q + ln > L) { raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r); return; }
-            scan_segment(rec, c.B.ref4, q, q + ln, rc, [&](int, int rp, uint32_t b, uint32_t) {
-                const int col = rp - c.d.col_begin;
-                atomicOr(&sm->snv[col], 1u << (b + 16u * ds));
-                const uint32_t e = atomicAdd(n_ent, 1u);
-                if (e < (uint32_t)kEnt2) sm->ent[e] = ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
-                else acc.overflow = true;
-            });
+            scan_segment(rec, c.B.ref4, q, q + ln, rc, [&](int, int rp, uint32_t b, uint32_t) { push_entry(sm, Q, i, rp - c.d.col_begin, b, ds); });
             q += ln; rc += ln; ccl += ln;
         } else if (op == 1u || op == 2u) {
-            const uint32_t slot = atomicAdd(n_obs, 1u);
-            if (slot >= (uint32_t)kObs2) { acc.overflow = true; return; }
+            const uint32_t slot = atomicAdd(Q.n_obs, 1u);
+            if (slot >= (uint32_t)kObs2) { *Q.overflow = 1u; return; }
             const int col = rc - c.d.col_begin;
             sm->o_col[slot] = col;
             sm->o_meta[slot] = (op == 1u ? kMetaIns : 0u) | (ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
@@ -183,9 +200,9 @@ __device__ void discover_read2(const SessCtx& c, Smem2* sm, int i, uint32_t* n_o
 }
 
 // ------------------------------------------------------------------ warp-cooperative emission
-// One warp writes one modified record.  Lane w owns query words w, w+32, ...: it takes the record word,
-// finds the aligned (M/=/X) segments that overlap its 8 bases, and replaces every base whose allele is in
-// the germline set by the reference base (anonymizer_methods.py:170-176).  Loads and stores are coalesced.
+// Lane w owns query words w, w+32, ...: it takes the record word, finds the aligned (M/=/X) segments that
+// overlap its 8 bases, and replaces every base whose allele is in the germline set by the reference base
+// (anonymizer_methods.py:170-176).  Loads and stores are coalesced.
 template <class Store>
 __device__ __forceinline__ void masked_words(const SessCtx& c, const Smem2* sm, int64_t r, int pos, int L, uint32_t c0, uint32_t c1,
                                              int n_words, int lane, Store&& store) {
@@ -233,17 +250,6 @@ __device__ __forceinline__ void write_record_meta(const ResultView& O, uint64_t 
     O.mod_qual_off16[rec_idx] = qual16;
 }
 
-// SNV-only record: sequence rewritten in place of the copy, qualities untouched (AM.py:170-176).
-__device__ __forceinline__ void emit_snv_warp(const SessCtx& c, const Smem2* sm, const ResultView& O, int64_t r, uint64_t rec_idx, uint64_t seq16,
-                                              int L, int lane) {
-    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
-    const int pos = __ldg(c.B.pos + r);
-    int units = (L + 31) >> 5; if (units < 1) units = 1;
-    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-    masked_words(c, sm, r, pos, L, c0, c1, units * 4, lane, [&](int w, uint32_t v) { oseq[w] = v; });
-    if (lane == 0) write_record_meta(O, rec_idx, c.s, r, L, seq16, 0xffffffffu);
-}
-
 // Indel-masked record: the SNV-masked sequence is staged in shared memory, then every output base / quality
 // is pulled through the backward index map of the edits (all DELs, then all INSs, at original offsets:
 // anonymizer_methods.py:254-270, 178-203).  One base (one quality) per lane and iteration.
@@ -264,7 +270,7 @@ __device__ void emit_indel_warp(const SessCtx& c, Smem2* sm, const ResultView& O
     const int pos = __ldg(c.B.pos + r);
     uint32_t* stage = sm->stage[warp];
     masked_words(c, sm, r, pos, L, c0, c1, (L + 7) >> 3, lane, [&](int w, uint32_t v) { stage[w] = v; });
-    const uint8_t* qrec = qual_record(c.B, r);
+    const uint8_t* qrec = qual_record_in(c.B, r, i < c.nt ? c.d.qt_begin : c.d.qn_begin, i < c.nt ? c.d.qt_end : c.d.qn_end);
     if (!qrec) { if (lane == 0) raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); return; }
     const bool reverse = ((lf >> 16) & 0x10u) != 0u;
     {   // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (AM.py:193)
@@ -345,19 +351,20 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
     Smem2* sm = reinterpret_cast<Smem2*>(smem_raw);
     __shared__ unsigned long long s_scan64[kThreads / 32 + 1];
     __shared__ uint32_t s_scan[kThreads / 32 + 1];
-    __shared__ uint32_t s_nobs, s_nent, s_reads, s_bases, s_cnt[3], s_overflow;
+    __shared__ uint32_t s_nobs, s_nent, s_nwords, s_ngen, s_reads, s_bases, s_cnt[3], s_overflow;
     __shared__ int s_next_session;
     __shared__ unsigned long long s_base[3];
 
     SessCtx c;
     c.B = B;
     c.totals = O.totals;
+    uint32_t* const clist = sm->wlist;
+    uint32_t* const msize = sm->lists; uint32_t* const mseq = sm->lists + kMod2; uint32_t* const mqual = sm->lists + 2 * kMod2;
     c.T.snv = sm->snv; c.T.ihead = sm->ihead; c.T.cand = sm->modbits;
     c.T.o_col = sm->o_col; c.T.o_meta = sm->o_meta; c.T.o_read = sm->o_read; c.T.o_irp = sm->o_irp; c.T.o_next = sm->o_next;
-    uint32_t* const clist = sm->ent; uint32_t* const msize = sm->ent + kMod2;
-    uint32_t* const mseq = sm->ent + 2 * kMod2; uint32_t* const mqual = sm->ent + 3 * kMod2;
     c.T.clist = clist; c.T.msize = msize;
     c.T.obs_cap = kObs2; c.T.reads_cap = kReads2; c.T.cols_cap = kCols2;
+    Queues Q; Q.n_words = &s_nwords; Q.n_gen = &s_ngen; Q.n_ent = &s_nent; Q.n_obs = &s_nobs; Q.overflow = &s_overflow;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n_work = S.n_sessions;
@@ -376,12 +383,12 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         // ---- zero the working set (skipped for sessions the fallback kernel owns)
         if (!c.d.big) {
             for (int k = tid; k < n_cols; k += kThreads) { sm->snv[k] = 0u; sm->ihead[k] = -1; }
-            for (int k = tid; k < n_cw; k += kThreads) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; }
+            for (int k = tid; k < n_cw; k += kThreads) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
         }
         __syncthreads();                                              // every thread has read s_next_session
         if (tid == 0) {
             s_next_session = (int)atomicAdd(ticket, 1u);              // prefetch the next ticket
-            s_nobs = 0; s_nent = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
+            s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
         }
         if (c.d.big) { __syncthreads(); continue; }
         c.first = S.first[s];
@@ -390,16 +397,20 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         c.keep_alen = (int)(S.keep_allele_off[s + 1] - S.keep_allele_off[s]);
         __syncthreads();
 
-        // ---- phase A: discover
+        // ---- phase A1: scan every read, queue what needs a closer look
+        uint32_t n_reads = 0, n_bases = 0;
+        for (int i = tid; i < c.n_range; i += kThreads) scan_read(c, sm, Q, i, n_reads, n_bases);
+        __syncthreads();
+        // ---- phase A2: dense discovery over the queues
         {
-            DiscoverAcc acc; acc.reads = 0; acc.bases = 0; acc.overflow = false;
-            for (int i = tid; i < c.n_range; i += kThreads) discover_read2(c, sm, i, &s_nobs, &s_nent, acc);
-            const uint32_t wr = warp_sum(acc.reads), wb = warp_sum(acc.bases);
+            const int nw = min((int)s_nwords, kWords2), ng = min((int)s_ngen, kGen2);
+            for (int k = tid; k < nw; k += kThreads) discover_word(c, sm, Q, sm->wlist[k]);
+            for (int k = tid; k < ng; k += kThreads) discover_generic(c, sm, Q, (int)sm->glist[k], n_reads, n_bases);
+            const uint32_t wr = warp_sum(n_reads), wb = warp_sum(n_bases);
             if (lane == 0 && wr) { atomicAdd(&s_reads, wr); atomicAdd(&s_bases, wb); }
-            if (acc.overflow) s_overflow = 1u;
         }
         __syncthreads();
-        if (s_overflow) {                                             // tables too small: hand the session to the fallback kernel
+        if (s_overflow) {                                             // queues or tables too small: hand the session to the fallback kernel
             if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
             __syncthreads();
             continue;
@@ -456,11 +467,12 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         }
         __syncthreads();
 
-        // ---- phase L: ordered list of the modified reads (n_cw <= 128 words, one per thread)
+        // ---- phase L: ordered list of the modified reads (n_cw <= 128 bitmap words, one per thread)
         uint32_t n_mod;
         {
             const uint32_t bits = tid < n_cw ? sm->modbits[tid] : 0u;
             uint32_t off = block_exclusive_scan(__popc(bits), s_scan, &n_mod);
+            if (tid < n_cw) sm->woff[tid] = off;
             uint32_t b = bits;
             while (b) {
                 const int k = __ffs(b) - 1; b &= b - 1;
@@ -511,13 +523,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             }
             O.sess_counts[4 * (size_t)s + 3] = s_reads;
         }
-        __syncthreads();
-        const bool fits = (int64_t)(s_base[0] + tot_rec) <= O.cap_records && (int64_t)(s_base[1] + tot_seq) <= O.cap_seq16 &&
-                          (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
-        if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
-
-        // ---- per-record output offsets (session-relative), then phase B2: one warp per record
-        {
+        {   // per-record output offsets (session-relative)
             uint32_t so = (uint32_t)((off >> 24) & 0xffffffu), qo = (uint32_t)(off & 0xffffffu);
             for (int k = k0; k < k1; ++k) {
                 const uint32_t m = msize[k];
@@ -527,21 +533,52 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             }
         }
         __syncthreads();
+        const bool fits = (int64_t)(s_base[0] + tot_rec) <= O.cap_records && (int64_t)(s_base[1] + tot_seq) <= O.cap_seq16 &&
+                          (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
+        if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
+
+        // ---- phase B2: one warp per record
         uint32_t n_q = 0;
         for (int k = warp; k < (int)n_mod; k += kThreads / 32) {
             const uint32_t m = msize[k];
             const int i = (int)clist[k];
             const int64_t r = read_of(c, i);
+            const int L = (int)(m & kLenMask);
+            const uint64_t seq16 = s_base[1] + mseq[k];
             if (m & kQualFlag) {
-                emit_indel_warp(c, sm, O, i, r, s_base[0] + k, s_base[1] + mseq[k], s_base[2] + mqual[k], (int)(m & kLenMask), lane, warp);
+                emit_indel_warp(c, sm, O, i, r, s_base[0] + k, seq16, s_base[2] + mqual[k], L, lane, warp);
                 ++n_q;
-            } else {
-                emit_snv_warp(c, sm, O, r, s_base[0] + k, s_base[1] + mseq[k], (int)(m & kLenMask), lane);
+                continue;
             }
+            int units = (L + 31) >> 5; if (units < 1) units = 1;
+            uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+            if ((sm->genbits[i >> 5] >> (i & 31)) & 1u) {             // other CIGARs: re-walk, mask while copying
+                const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+                masked_words(c, sm, r, __ldg(c.B.pos + r), L, c0, c1, units * 4, lane, [&](int w, uint32_t v) { oseq[w] = v; });
+            } else {                                                  // clean read: plain coalesced copy, hits are patched below
+                const uint32_t* rec = rec_of(c, r);
+                for (int w = lane; w < units * 4; w += 32) oseq[w] = __ldg(rec + w) & tail_mask(L, w);
+            }
+            if (lane == 0) write_record_meta(O, s_base[0] + k, s, r, L, seq16, 0xffffffffu);
         }
         if (lane != 0) n_q = 0;
         n_q = warp_sum(n_q);
         if (lane == 0 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
+        __syncthreads();                                              // the copies are in place
+
+        // ---- phase B3: SNV masking of the copied clean reads, one 4-bit XOR per germline hit (AM.py:170-176)
+        for (int e = tid; e < n_ent; e += kThreads) {
+            const uint32_t w = sm->ent[e];
+            const uint32_t col = (w >> 4) & 0xfffu, b = w & 15u, i = w >> 16;
+            if (!((sm->snv[col] >> b) & 1u)) continue;
+            if ((sm->genbits[i >> 5] >> (i & 31)) & 1u) continue;     // re-walked by its warp above
+            const uint32_t k = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
+            const int64_t r = read_of(c, (int)i);
+            const int q = (int)col + c.d.col_begin - __ldg(c.B.pos + r);
+            const uint32_t rf = ref_code(c.B.ref4, (int64_t)col + c.d.col_begin);
+            uint32_t* word = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * (s_base[1] + mseq[k])) + (q >> 3);
+            atomicXor(word, (b ^ rf) << ((q & 7) * 4));
+        }
         __syncthreads();                                              // tables are reused by the next session
     }
 }
