@@ -35,6 +35,8 @@ struct SessionDesc {
     int32_t obs_bound;                        // upper bound on I/D ops among the candidates
     int32_t big;                              // 1: tables live in the CTA's global scratch
     int32_t qt_begin, qt_end, qn_begin, qn_end; // sparse quality records (ga_reads.qual_reads) of the candidate ranges
+    uint32_t t_seq_lo, t_seq_n, n_seq_lo, n_seq_n;   // seq4 units [lo, lo+n) holding the candidate records (prefetch hint)
+    uint32_t t_cig_lo, t_cig_n, n_cig_lo, n_cig_n;   // CIGAR words of the candidate reads (prefetch hint)
 };
 
 // View of one batch + reference, passed by value to kernels.

@@ -83,6 +83,22 @@ __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* _
     // oversize sessions go to the global-scratch kernel; table overflows found at run time join them
     d.big = (d.n_cols > kCols2 || n_range > kReads2) ? 1 : 0;
     if (n_range == 0) { d.n_cols = 0; d.big = 0; }
+    d.t_seq_lo = d.t_seq_n = d.n_seq_lo = d.n_seq_n = 0u;
+    d.t_cig_lo = d.t_cig_n = d.n_cig_lo = d.n_cig_n = 0u;
+    if (d.t_end > d.t_begin) {
+        const uint32_t L = B.len_flag[d.t_end - 1] & 0xffffu;
+        d.t_seq_lo = B.seq_off16[d.t_begin];
+        const uint32_t hi = B.seq_off16[d.t_end - 1] + (L ? (L + 31u) / 32u : 1u);
+        d.t_seq_n = hi > d.t_seq_lo ? hi - d.t_seq_lo : 0u;
+        d.t_cig_lo = B.cigar_off[d.t_begin]; d.t_cig_n = B.cigar_off[d.t_end] - d.t_cig_lo;
+    }
+    if (d.n_end > d.n_begin) {
+        const uint32_t L = B.len_flag[d.n_end - 1] & 0xffffu;
+        d.n_seq_lo = B.seq_off16[d.n_begin];
+        const uint32_t hi = B.seq_off16[d.n_end - 1] + (L ? (L + 31u) / 32u : 1u);
+        d.n_seq_n = hi > d.n_seq_lo ? hi - d.n_seq_lo : 0u;
+        d.n_cig_lo = B.cigar_off[d.n_begin]; d.n_cig_n = B.cigar_off[d.n_end] - d.n_cig_lo;
+    }
     d.qt_begin = d.qt_end = d.qn_begin = d.qn_end = 0;
     if (B.qual_reads) {
         d.qt_begin = lower_bound_pos(B.qual_reads, 0, B.n_qual, d.t_begin); d.qt_end = lower_bound_pos(B.qual_reads, d.qt_begin, B.n_qual, d.t_end);

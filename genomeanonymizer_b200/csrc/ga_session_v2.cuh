@@ -55,6 +55,30 @@ __device__ __forceinline__ uint4 ldg128(const uint4* p) {
     return r;
 }
 
+// Bulk prefetch of a byte range into L2 (TMA engine, no shared memory or registers tied up).
+__device__ __forceinline__ void prefetch_l2(const void* p, uint64_t bytes) {
+    uint64_t a = reinterpret_cast<uint64_t>(p) & ~15ull;
+    bytes = (bytes + (reinterpret_cast<uint64_t>(p) - a) + 15ull) & ~15ull;
+    while (bytes) {
+        const uint32_t n = bytes > (1u << 20) ? (1u << 20) : (uint32_t)bytes;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+        a += n; bytes -= n;
+    }
+}
+
+// Everything phase A1 of session `d` will read, requested while the previous session is still running.
+__device__ __forceinline__ void prefetch_session(const BatchView& B, const SessionDesc& d) {
+    if (d.big) return;
+    prefetch_l2(B.seq4 + 16ull * d.t_seq_lo, 16ull * d.t_seq_n);
+    prefetch_l2(B.seq4 + 16ull * d.n_seq_lo, 16ull * d.n_seq_n);
+    const int64_t nt = d.t_end - d.t_begin, nn = d.n_end - d.n_begin;
+    prefetch_l2(B.pos + d.t_begin, 4 * nt);       prefetch_l2(B.pos + d.n_begin, 4 * nn);
+    prefetch_l2(B.len_flag + d.t_begin, 4 * nt);  prefetch_l2(B.len_flag + d.n_begin, 4 * nn);
+    prefetch_l2(B.seq_off16 + d.t_begin, 4 * nt); prefetch_l2(B.seq_off16 + d.n_begin, 4 * nn);
+    prefetch_l2(B.cigar_off + d.t_begin, 4 * nt + 4); prefetch_l2(B.cigar_off + d.n_begin, 4 * nn + 4);
+    prefetch_l2(B.cigar + d.t_cig_lo, 4ull * d.t_cig_n); prefetch_l2(B.cigar + d.n_cig_lo, 4ull * d.n_cig_n);
+}
+
 __device__ __forceinline__ uint32_t tail_mask(int L, int word) {           // valid nibbles of query word `word`
     const int nv = L - word * 8;
     return nv >= 8 ? 0xffffffffu : (nv <= 0 ? 0u : (0xffffffffu >> ((8 - nv) * 4)));
@@ -102,18 +126,41 @@ __device__ __forceinline__ void push_entry(Smem2* sm, const Queues& Q, int i, in
 }
 
 // ------------------------------------------------------------------ phase A1: one read
-__device__ __forceinline__ void scan_read(const SessCtx& c, Smem2* sm, const Queues& Q, int i, uint32_t& n_reads, uint32_t& n_bases) {
+struct ReadMeta { int pos; uint32_t lf, so, c0, c1; };
+
+__device__ __forceinline__ ReadMeta load_meta(const SessCtx& c, int i) {
     const int64_t r = read_of(c, i);
-    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
-    const int pos = __ldg(c.B.pos + r);
-    const int L = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
-    const uint32_t so = __ldg(c.B.seq_off16 + r);
-    const uint32_t w0 = c1 > c0 ? __ldg(c.B.cigar + c0) : 0u;
-    const uint32_t op0 = w0 & 15u;
+    ReadMeta m;
+    m.pos = __ldg(c.B.pos + r); m.lf = __ldg(c.B.len_flag + r); m.so = __ldg(c.B.seq_off16 + r);
+    m.c0 = __ldg(c.B.cigar_off + r); m.c1 = __ldg(c.B.cigar_off + r + 1);
+    return m;
+}
+
+// The record and reference loads are issued together with the load of the first CIGAR word (they only need
+// the prefetched meta), so a read costs two dependent memory round trips instead of three.
+__device__ __forceinline__ void scan_read(const SessCtx& c, Smem2* sm, const Queues& Q, int i, const ReadMeta& m, uint32_t& n_reads, uint32_t& n_bases) {
+    const int pos = m.pos;
+    const int L = (int)(m.lf & 0xffffu);
     const int units = (L + 31) >> 5;
-    const bool clean = (c1 - c0 == 1u) && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(w0 >> 4) == L) &&
-                       (units == 5 || units == 4 || units == 3 || units == 8);
-    if (!clean) {                                                        // any other CIGAR: queued for phase A2
+    const bool one_op = (m.c1 - m.c0 == 1u);
+    // speculative: a single-op read whose span L stays inside the reference and the session table
+    const bool spec = one_op && pos >= 0 && (int64_t)pos + L <= c.B.ref_len && pos >= c.d.col_begin && pos + L - c.d.col_begin < c.d.n_cols;
+    const uint32_t w0 = m.c1 > m.c0 ? __ldg(c.B.cigar + m.c0) : 0u;
+    const uint4* rec = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * m.so);
+    uint32_t wm = 0u;
+    bool supported = spec;
+    if (spec) {
+        switch (units) {
+            case 5: wm = clean_word_mask<5>(rec, c.B.ref4, pos, L); break;
+            case 4: wm = clean_word_mask<4>(rec, c.B.ref4, pos, L); break;
+            case 3: wm = clean_word_mask<3>(rec, c.B.ref4, pos, L); break;
+            case 8: wm = clean_word_mask<8>(rec, c.B.ref4, pos, L); break;
+            default: supported = false; break;
+        }
+    }
+    const uint32_t op0 = w0 & 15u;
+    const bool clean = supported && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(w0 >> 4) == L);
+    if (!clean) {                                                        // any other CIGAR (or an error case): queued for phase A2
         const uint32_t g = atomicAdd(Q.n_gen, 1u);
         if (g < (uint32_t)kGen2) sm->glist[g] = (uint16_t)i; else *Q.overflow = 1u;
         atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
@@ -121,18 +168,6 @@ __device__ __forceinline__ void scan_read(const SessCtx& c, Smem2* sm, const Que
     }
     if (pos + L <= c.first) return;                                      // fetched by range, does not reach the region
     n_reads += 1u; n_bases += (uint32_t)L;
-    if ((int64_t)pos + L > c.B.ref_len || pos < 0 || pos < c.d.col_begin || pos + L - c.d.col_begin >= c.d.n_cols) {
-        raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
-        return;
-    }
-    const uint4* rec = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * so);
-    uint32_t wm;
-    switch (units) {
-        case 5: wm = clean_word_mask<5>(rec, c.B.ref4, pos, L); break;
-        case 4: wm = clean_word_mask<4>(rec, c.B.ref4, pos, L); break;
-        case 3: wm = clean_word_mask<3>(rec, c.B.ref4, pos, L); break;
-        default: wm = clean_word_mask<8>(rec, c.B.ref4, pos, L); break;
-    }
     while (wm) {
         const int k = __ffs(wm) - 1; wm &= wm - 1;
         const uint32_t e = atomicAdd(Q.n_words, 1u);
@@ -386,8 +421,12 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             for (int k = tid; k < n_cw; k += kThreads) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
         }
         __syncthreads();                                              // every thread has read s_next_session
+        if (tid == kThreads - 32) {                                   // next ticket, and its reads on their way into L2
+            const int nx = (int)atomicAdd(ticket, 1u);
+            s_next_session = nx;
+            if (nx < n_work) prefetch_session(B, descs[nx]);
+        }
         if (tid == 0) {
-            s_next_session = (int)atomicAdd(ticket, 1u);              // prefetch the next ticket
             s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
         }
         if (c.d.big) { __syncthreads(); continue; }
@@ -399,7 +438,18 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
 
         // ---- phase A1: scan every read, queue what needs a closer look
         uint32_t n_reads = 0, n_bases = 0;
-        for (int i = tid; i < c.n_range; i += kThreads) scan_read(c, sm, Q, i, n_reads, n_bases);
+        {
+            int i = tid;
+            ReadMeta m = {};
+            if (i < c.n_range) m = load_meta(c, i);
+            while (i < c.n_range) {                                   // the next read's meta is in flight while this one is compared
+                const int inext = i + kThreads;
+                ReadMeta mn = {};
+                if (inext < c.n_range) mn = load_meta(c, inext);
+                scan_read(c, sm, Q, i, m, n_reads, n_bases);
+                m = mn; i = inext;
+            }
+        }
         __syncthreads();
         // ---- phase A2: dense discovery over the queues
         {
@@ -537,11 +587,31 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
                           (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
         if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
 
-        // ---- phase B2: one warp per record
+        // ---- phase B2: clean SNV-only records are plain copies, one 16-byte unit per thread and iteration
+        // (their germline hits are patched in phase B3); every other record is written by one warp
+        for (uint32_t idx = tid; idx < tot_seq; idx += kThreads) {
+            int lo = 0, hi = (int)n_mod;                              // last record with mseq[k] <= idx
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (mseq[mid] <= idx) lo = mid; else hi = mid; }
+            const uint32_t m = msize[lo];
+            const int i = (int)clist[lo];
+            if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u)) continue;
+            const int u = (int)(idx - mseq[lo]), L = (int)(m & kLenMask);
+            const int64_t r = read_of(c, i);
+            uint4 v = ldg128(reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * __ldg(c.B.seq_off16 + r)) + u);
+            if (32 * u + 32 > L) { v.x &= tail_mask(L, 4 * u); v.y &= tail_mask(L, 4 * u + 1); v.z &= tail_mask(L, 4 * u + 2); v.w &= tail_mask(L, 4 * u + 3); }
+            *reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (s_base[1] + idx)) = v;
+        }
+        for (int k = tid; k < (int)n_mod; k += kThreads) {            // record headers, coalesced
+            const uint32_t m = msize[k];
+            if (m & kQualFlag) continue;                              // written by emit_indel_warp
+            write_record_meta(O, s_base[0] + k, s, read_of(c, (int)clist[k]), (int)(m & kLenMask), s_base[1] + mseq[k], 0xffffffffu);
+        }
         uint32_t n_q = 0;
         for (int k = warp; k < (int)n_mod; k += kThreads / 32) {
             const uint32_t m = msize[k];
             const int i = (int)clist[k];
+            const bool gen = ((sm->genbits[i >> 5] >> (i & 31)) & 1u) != 0u;
+            if (!(m & kQualFlag) && !gen) continue;
             const int64_t r = read_of(c, i);
             const int L = (int)(m & kLenMask);
             const uint64_t seq16 = s_base[1] + mseq[k];
@@ -550,16 +620,10 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
                 ++n_q;
                 continue;
             }
-            int units = (L + 31) >> 5; if (units < 1) units = 1;
+            int units = (L + 31) >> 5; if (units < 1) units = 1;       // other CIGARs: re-walk, mask while copying
             uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-            if ((sm->genbits[i >> 5] >> (i & 31)) & 1u) {             // other CIGARs: re-walk, mask while copying
-                const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
-                masked_words(c, sm, r, __ldg(c.B.pos + r), L, c0, c1, units * 4, lane, [&](int w, uint32_t v) { oseq[w] = v; });
-            } else {                                                  // clean read: plain coalesced copy, hits are patched below
-                const uint32_t* rec = rec_of(c, r);
-                for (int w = lane; w < units * 4; w += 32) oseq[w] = __ldg(rec + w) & tail_mask(L, w);
-            }
-            if (lane == 0) write_record_meta(O, s_base[0] + k, s, r, L, seq16, 0xffffffffu);
+            const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+            masked_words(c, sm, r, __ldg(c.B.pos + r), L, c0, c1, units * 4, lane, [&](int w, uint32_t v) { oseq[w] = v; });
         }
         if (lane != 0) n_q = 0;
         n_q = warp_sum(n_q);
