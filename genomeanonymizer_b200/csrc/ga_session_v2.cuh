@@ -25,13 +25,13 @@ constexpr int kReads2 = 4096;          // candidate reads per session
 constexpr int kObs2 = 512;             // indel observations per session
 constexpr int kEnt2 = 2048;            // SNV candidate entries per session
 constexpr int kMod2 = 512;             // modified reads per session
-constexpr int kWords2 = 1024;          // queued mismatching words per session
+constexpr int kWords2 = 768;           // queued mismatching words per session
 constexpr int kGen2 = 1024;            // queued non-clean reads per session
 constexpr int kStageWords = 64;        // per-warp staging of an SNV-masked record (reads up to 512 bases)
 
 struct Smem2 {
     uint32_t snv[kCols2];              // bit c: tumor saw base code c, bit 16+c: normal; after resolve: germline codes
-    int32_t ihead[kCols2];
+    int16_t ihead[kCols2];             // head of the indel-observation chain of the column (-1: none)
     uint32_t ent[kEnt2];               // (session-relative read << 16) | (column << 4) | base code
     uint32_t wlist[kWords2];           // (session-relative read << 5) | word index; after phase A2 reused as clist
     uint32_t lists[3 * kMod2];         // msize | mseq | mqual
@@ -40,11 +40,15 @@ struct Smem2 {
     uint32_t indelbits[kReads2 / 32];
     uint32_t genbits[kReads2 / 32];
     uint32_t woff[kReads2 / 32];       // modified reads before bitmap word w
-    int32_t o_col[kObs2];
-    uint32_t o_meta[kObs2];
-    uint32_t o_read[kObs2];
-    int32_t o_irp[kObs2];
-    int32_t o_next[kObs2];
+    int32_t o_col[kObs2];              // indel observations: column,
+    uint32_t o_meta[kObs2];            //   type / dataset / germline flags / op length,
+    uint32_t o_read[kObs2];            //   session-relative read (low 16) | allele length (high 16),
+    int32_t o_irp[kObs2];              //   in_read_pos with the reference's H/N quirk,
+    uint32_t o_sig0[kObs2];            //   first 16 allele bases, 4 bits each,
+    uint32_t o_sig1[kObs2];
+    int16_t o_next[kObs2];             //   next observation at the same column,
+    int16_t o_rnext[kObs2];            //   next germline observation of the same modified read
+    int32_t mhead[kMod2];              // per modified read: chain of its germline indel observations
     uint32_t stage[kThreads / 32][kStageWords];
 };
 static_assert(kWords2 >= kMod2, "clist aliases the word queue");
@@ -208,6 +212,7 @@ __device__ void discover_generic(const SessCtx& c, Smem2* sm, const Queues& Q, i
         raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
         return;
     }
+    if (L > 8 * kStageWords) { *Q.overflow = 1u; return; }              // very long read: the fallback kernel takes the session
     const uint32_t* rec = rec_of(c, r);
     int rc = pos, q = 0, ccl = 0, rcb = 0;
     for (uint32_t ci = c0; ci < c1; ++ci) {
@@ -222,16 +227,114 @@ __device__ void discover_generic(const SessCtx& c, Smem2* sm, const Queues& Q, i
             if (slot >= (uint32_t)kObs2) { *Q.overflow = 1u; return; }
             const int col = rc - c.d.col_begin;
             sm->o_col[slot] = col;
-            sm->o_meta[slot] = (op == 1u ? kMetaIns : 0u) | (ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
-            sm->o_read[slot] = (uint32_t)i;
-            sm->o_irp[slot] = ccl + rcb;                                  // variation_classifier.py:82
-            __threadfence_block();
-            sm->o_next[slot] = atomicExch(&sm->ihead[col], (int)slot);
+            const uint32_t meta = (op == 1u ? kMetaIns : 0u) | (ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+            const int irp = ccl + rcb;                                    // variation_classifier.py:82
+            const int alen = allele_len(meta, irp, L);                    // Python-slice clamped (variation_classifier.py:87-88)
+            uint32_t s0 = 0u, s1 = 0u;
+            for (int j = 0; j < alen && j < 16; ++j) {
+                const uint32_t code = read_code(rec, irp + j);
+                if (j < 8) s0 |= code << (4 * j); else s1 |= code << (4 * (j - 8));
+            }
+            sm->o_meta[slot] = meta;
+            sm->o_read[slot] = (uint32_t)i | ((uint32_t)alen << 16);
+            sm->o_irp[slot] = irp;
+            sm->o_sig0[slot] = s0; sm->o_sig1[slot] = s1;
+            // push on the column's chain: 16-bit heads are updated with a CAS on the containing word
+            {
+                uint32_t* hw = reinterpret_cast<uint32_t*>(sm->ihead) + (col >> 1);
+                const int shift = (col & 1) * 16;
+                uint32_t old = *hw, assumed;
+                do {
+                    assumed = old;
+                    sm->o_next[slot] = (int16_t)((assumed >> shift) & 0xffffu);
+                    __threadfence_block();
+                    old = atomicCAS(hw, assumed, (assumed & ~(0xffffu << shift)) | ((slot & 0xffffu) << shift));
+                } while (old != assumed);
+            }
             if (op == 1u) { q += ln; rcb += ln; } else { rc += ln; ccl += ln; rcb -= ln; }
         } else if (op == 3u) { rc += ln; ccl += ln; }
         else if (op == 4u) { q += ln; rcb += ln; }
         else if (op == 5u) { rcb += ln; }
     }
+}
+
+// ------------------------------------------------------------------ indel observations (shared memory only)
+__device__ __forceinline__ int obs_read(const Smem2* sm, int o) { return (int)(sm->o_read[o] & 0xffffu); }
+__device__ __forceinline__ int obs_alen(const Smem2* sm, int o) { return (int)(sm->o_read[o] >> 16); }
+
+// CalledGenomicVariant.__eq__ (variants.py:83-96) between two observations of the same column: type, length
+// and allele bases.  Alleles up to 16 bases are decided by the stored signature, longer ones re-read the records.
+__device__ __forceinline__ bool obs_equal2(const SessCtx& c, const Smem2* sm, int a, int b) {
+    if (((sm->o_meta[a] ^ sm->o_meta[b]) & (kMetaIns | kMetaLenMask)) != 0u) return false;
+    const int na = obs_alen(sm, a);
+    if (na != obs_alen(sm, b) || sm->o_sig0[a] != sm->o_sig0[b] || sm->o_sig1[a] != sm->o_sig1[b]) return false;
+    if (na <= 16) return true;
+    const uint32_t* pa = rec_of(c, read_of(c, obs_read(sm, a)));
+    const uint32_t* pb = rec_of(c, read_of(c, obs_read(sm, b)));
+    const int ia = sm->o_irp[a], ib = sm->o_irp[b];
+    for (int j = 16; j < na; ++j)
+        if (read_code(pa, ia + j) != read_code(pb, ib + j)) return false;
+    return true;
+}
+
+__device__ bool obs_equals_keep2(const SessCtx& c, const Smem2* sm, int a) {
+    const uint32_t m = sm->o_meta[a];
+    const int type = (m & kMetaIns) ? GA_VT_INS : GA_VT_DEL;
+    const int len = (int)(m & kMetaLenMask);
+    const int pos = sm->o_col[a] + c.d.col_begin;
+    if (c.keep_type != type || c.keep_pos != pos || c.keep_len != len) return false;
+    const int end = (type == GA_VT_INS) ? pos + 1 : pos + len - 1;         // variation_classifier.py:86
+    if (c.keep_end != end) return false;
+    const int na = obs_alen(sm, a);
+    if (na != c.keep_alen) return false;
+    const uint32_t* p = rec_of(c, read_of(c, obs_read(sm, a)));
+    const int irp = sm->o_irp[a];
+    const char* code2asc = "=ACMGRSVTWYHKDBN";
+    for (int j = 0; j < na; ++j)
+        if (c.keep_allele[j] != (uint8_t)code2asc[read_code(p, irp + j)]) return false;
+    return true;
+}
+
+// The germline indel edits of modified read k in application order (all DELs, then all INSs, each in CIGAR
+// order: stable sort by VariantType value, anonymizer_methods.py:264) with the offsets clamped exactly as
+// Python slicing applies them (anonymizer_methods.py:186-195).  The read's germline observations hang on
+// mhead[k]; their slots ascend in CIGAR order (one thread allocated them), so sorting by slot restores it.
+// Returns the new length.
+__device__ int collect_edits(const SessCtx& c, const Smem2* sm, int k, int L, Edit* edits, int* n_edits, int* n_dels, bool* too_many) {
+    int16_t slots[GA_MAX_EDITS];
+    int ns = 0;
+    for (int o = sm->mhead[k]; o >= 0; o = sm->o_rnext[o]) {
+        if (ns >= GA_MAX_EDITS) { *too_many = true; break; }
+        int p = ns++;
+        while (p > 0 && slots[p - 1] > o) { slots[p] = slots[p - 1]; --p; }
+        slots[p] = (int16_t)o;
+    }
+    int ne = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int q = 0; q < ns; ++q) {
+            const int o = slots[q];
+            const uint32_t m = sm->o_meta[o];
+            if (((m & kMetaIns) != 0u) != (pass == 1)) continue;
+            edits[ne].irp = sm->o_irp[o]; edits[ne].len = (int)(m & kMetaLenMask); edits[ne].pos = sm->o_col[o] + c.d.col_begin;
+            edits[ne].is_ins = pass ? 1u : 0u; edits[ne].mean = 0u; ++ne;
+        }
+        if (pass == 0) *n_dels = ne;
+    }
+    const int n_del = *n_dels;
+    int cur = L;
+    for (int q = 0; q < n_del; ++q) {
+        edits[q].p_eff = edits[q].irp < cur ? edits[q].irp : cur;
+        edits[q].e_eff = edits[q].p_eff + edits[q].len;
+        cur += edits[q].len;
+    }
+    for (int q = n_del; q < ne; ++q) {
+        const int p = edits[q].irp < cur ? edits[q].irp : cur;
+        const int e = edits[q].irp + edits[q].len < cur ? edits[q].irp + edits[q].len : cur;
+        edits[q].p_eff = p; edits[q].e_eff = e > p ? e : p;
+        cur -= (edits[q].e_eff - p);
+    }
+    *n_edits = ne;
+    return cur;
 }
 
 // ------------------------------------------------------------------ warp-cooperative emission
@@ -288,19 +391,13 @@ __device__ __forceinline__ void write_record_meta(const ResultView& O, uint64_t 
 // Indel-masked record: the SNV-masked sequence is staged in shared memory, then every output base / quality
 // is pulled through the backward index map of the edits (all DELs, then all INSs, at original offsets:
 // anonymizer_methods.py:254-270, 178-203).  One base (one quality) per lane and iteration.
-__device__ void emit_indel_warp(const SessCtx& c, Smem2* sm, const ResultView& O, int i, int64_t r, uint64_t rec_idx, uint64_t seq16, uint64_t qual16,
+__device__ void emit_indel_warp(const SessCtx& c, Smem2* sm, const ResultView& O, int k, int i, int64_t r, uint64_t rec_idx, uint64_t seq16, uint64_t qual16,
                                 int new_len, int lane, int warp) {
     const uint32_t lf = __ldg(c.B.len_flag + r);
-    const int L = (int)(lf & 0xffffu);
-    if (((L + 7) >> 3) > kStageWords) {                              // very long read: single-lane fallback
-        if (lane == 0) emit_read(c, O, i, r, rec_idx, seq16, qual16, new_len, true);
-        return;
-    }
+    const int L = (int)(lf & 0xffffu);                               // <= 8 * kStageWords (longer reads go to the fallback kernel)
     Edit edits[GA_MAX_EDITS];
-    int ne = 0; bool any_snv = false, too_many = false;
-    analyse_read<false>(c, i, r, edits, &ne, &any_snv, &too_many);
-    int n_del = 0;
-    while (n_del < ne && !edits[n_del].is_ins) ++n_del;
+    int ne = 0, n_del = 0; bool too_many = false;
+    collect_edits(c, sm, k, L, edits, &ne, &n_del, &too_many);
     const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
     const int pos = __ldg(c.B.pos + r);
     uint32_t* stage = sm->stage[warp];
@@ -395,10 +492,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
     c.totals = O.totals;
     uint32_t* const clist = sm->wlist;
     uint32_t* const msize = sm->lists; uint32_t* const mseq = sm->lists + kMod2; uint32_t* const mqual = sm->lists + 2 * kMod2;
-    c.T.snv = sm->snv; c.T.ihead = sm->ihead; c.T.cand = sm->modbits;
-    c.T.o_col = sm->o_col; c.T.o_meta = sm->o_meta; c.T.o_read = sm->o_read; c.T.o_irp = sm->o_irp; c.T.o_next = sm->o_next;
-    c.T.clist = clist; c.T.msize = msize;
-    c.T.obs_cap = kObs2; c.T.reads_cap = kReads2; c.T.cols_cap = kCols2;
+    memset(&c.T, 0, sizeof c.T);                                      // the shared-memory tables are reached through `sm`
     Queues Q; Q.n_words = &s_nwords; Q.n_gen = &s_ngen; Q.n_ent = &s_nent; Q.n_obs = &s_nobs; Q.overflow = &s_overflow;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -417,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         const int n_cw = (c.n_range + 31) >> 5;
         // ---- zero the working set (skipped for sessions the fallback kernel owns)
         if (!c.d.big) {
-            for (int k = tid; k < n_cols; k += kThreads) { sm->snv[k] = 0u; sm->ihead[k] = -1; }
+            for (int k = tid; k < n_cols; k += kThreads) { sm->snv[k] = 0u; sm->ihead[k] = (int16_t)-1; }
             for (int k = tid; k < n_cw; k += kThreads) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
         }
         __syncthreads();                                              // every thread has read s_next_session
@@ -492,15 +586,15 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             bool germ = false, rep = true;
             for (int o2 = sm->ihead[sm->o_col[o]]; o2 >= 0; o2 = sm->o_next[o2]) {
                 if (o2 == o) continue;
-                if (!obs_equal(c, o, o2)) continue;
+                if (!obs_equal2(c, sm, o, o2)) continue;
                 if ((sm->o_meta[o2] ^ m) & kMetaDs) germ = true;
                 if (o2 < o) rep = false;
             }
-            if (germ && obs_equals_keep(c, o)) germ = false;
+            if (germ && obs_equals_keep2(c, sm, o)) germ = false;
             if (germ) {
                 atomicOr(&sm->o_meta[o], kMetaGerm | (rep ? kMetaRep : 0u));
                 if (rep) atomicAdd(&s_cnt[(m & kMetaIns) ? 2 : 1], 1u);
-                const uint32_t i = sm->o_read[o];
+                const uint32_t i = (uint32_t)obs_read(sm, o);
                 atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
                 atomicOr(&sm->indelbits[i >> 5], 1u << (i & 31));
             }
@@ -535,7 +629,17 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             __syncthreads();
             continue;
         }
+        for (int k = tid; k < (int)n_mod; k += kThreads) sm->mhead[k] = -1;
         __syncthreads();
+        if (n_obs > 0) {                                              // hang every germline observation on its modified read
+            for (int o = tid; o < n_obs; o += kThreads) {
+                if (!(sm->o_meta[o] & kMetaGerm)) continue;
+                const uint32_t i = (uint32_t)obs_read(sm, o);
+                const uint32_t k = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
+                sm->o_rnext[o] = (int16_t)atomicExch(&sm->mhead[k], o);
+            }
+            __syncthreads();
+        }
 
         // ---- phase B1: new length of every modified read; indel-masked reads need the edit analysis
         const int per = ((int)n_mod + kThreads - 1) / kThreads;
@@ -547,8 +651,8 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             uint32_t m;
             if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
                 Edit edits[GA_MAX_EDITS];
-                int ne = 0; bool any_snv = false, too_many = false;
-                const int new_len = analyse_read<false>(c, i, r, edits, &ne, &any_snv, &too_many);
+                int ne = 0, nd = 0; bool too_many = false;
+                const int new_len = collect_edits(c, sm, k, (int)(__ldg(c.B.len_flag + r) & 0xffffu), edits, &ne, &nd, &too_many);
                 if (too_many) raise_error(O.totals, GA_ERR_UNSUPPORTED, (uint32_t)r);
                 m = kModFlag | kQualFlag | ((uint32_t)new_len & kLenMask);
             } else {
@@ -616,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             const int L = (int)(m & kLenMask);
             const uint64_t seq16 = s_base[1] + mseq[k];
             if (m & kQualFlag) {
-                emit_indel_warp(c, sm, O, i, r, s_base[0] + k, seq16, s_base[2] + mqual[k], L, lane, warp);
+                emit_indel_warp(c, sm, O, k, i, r, s_base[0] + k, seq16, s_base[2] + mqual[k], L, lane, warp);
                 ++n_q;
                 continue;
             }
