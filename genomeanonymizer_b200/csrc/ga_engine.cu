@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -157,6 +158,7 @@ int ga_engine_create(int device, ga_engine** out) {
     ga_engine* e = new ga_engine();
     e->device = device;
     e->n_sm = prop.multiProcessorCount;
+    if (const char* sa = getenv("GA_STOP_AFTER")) e->stop_after = atoi(sa);   // profiling knob, see session_kernel_v2
     if (cudaSetDevice(device) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
     for (int l = 0; l < kLanes; ++l) {
         if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
@@ -305,7 +307,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 4, S->n_sessions);
     const int tslot = (int)(L.runs % kTimedRuns);
     GA_CUDA(cudaEventRecord(L.ev0[tslot], st));
-    ga::session_kernel_v2<<<grid_small, ga::kThreads, sizeof(ga::Smem2), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, d_tickets);
+    ga::session_kernel_v2<<<grid_small, ga::kThreads, sizeof(ga::Smem2), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, d_tickets, e->stop_after);
     GA_CUDA(cudaEventRecord(L.ev1[tslot], st));
     L.runs++;
     ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);

@@ -55,7 +55,7 @@ static_assert(kWords2 >= kMod2, "clist aliases the word queue");
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 
@@ -198,29 +198,67 @@ __device__ __forceinline__ void discover_word(const SessCtx& c, Smem2* sm, const
     }
 }
 
-// ------------------------------------------------------------------ phase A2: one queued non-clean read
-__device__ void discover_generic(const SessCtx& c, Smem2* sm, const Queues& Q, int i, uint32_t& n_reads, uint32_t& n_bases) {
+// ------------------------------------------------------------------ phase A2: one queued non-clean read per warp
+// Lane w owns query words w, w+32, ...: it walks the CIGAR (a warp-uniform loop) and compares the part of every
+// aligned segment that overlaps its 8 bases with the reference; lane 0 records the I/D observations
+// (variation_classifier.py:52-107: pos, in_read_pos with the H/N quirk, Python-slice clamped allele).
+__device__ void discover_generic_warp(const SessCtx& c, Smem2* sm, const Queues& Q, int i, int lane, uint32_t& n_reads, uint32_t& n_bases) {
     const int64_t r = read_of(c, i);
     const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
     const int pos = __ldg(c.B.pos + r);
     const int L = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
     const uint32_t ds = i < c.nt ? 0u : 1u;
-    const int span = ref_span_of(c.B.cigar, c0, c1);
+    int span = 0;
+    for (uint32_t ci = c0; ci < c1; ++ci) {
+        const uint32_t w = __ldg(c.B.cigar + ci), op = w & 15u;
+        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
+    }
     if (pos + span <= c.first) return;
-    n_reads += 1u; n_bases += (uint32_t)L;
+    if (lane == 0) { n_reads += 1u; n_bases += (uint32_t)L; }
     if ((int64_t)pos + span > c.B.ref_len || pos < 0 || pos < c.d.col_begin || pos + span - c.d.col_begin >= c.d.n_cols) {
-        raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
+        if (lane == 0) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
         return;
     }
     if (L > 8 * kStageWords) { *Q.overflow = 1u; return; }              // very long read: the fallback kernel takes the session
     const uint32_t* rec = rec_of(c, r);
+    // ---- SNV candidates, one 8-base word per lane
+    for (int w = lane; w < ((L + 7) >> 3); w += 32) {
+        const int qb = w << 3;
+        const uint32_t v = __ldg(rec + w);
+        int rc = pos, q = 0;
+        for (uint32_t ci = c0; ci < c1; ++ci) {
+            const uint32_t cw = __ldg(c.B.cigar + ci), op = cw & 15u;
+            const int ln = (int)(cw >> 4);
+            if (op == 0u || op == 7u || op == 8u) {
+                const int lo = max(q, qb), hi = min(min(q + ln, qb + 8), L);
+                if (lo < hi) {
+                    const int p0 = rc - q + qb;                           // reference position of query base qb under this segment
+                    const uint32_t fw = ref_word(c.B.ref4, (int64_t)p0);
+                    uint32_t mask = 0xffffffffu;
+                    if (lo > qb) mask &= 0xffffffffu << ((lo - qb) * 4);
+                    if (hi < qb + 8) mask &= 0xffffffffu >> ((qb + 8 - hi) * 4);
+                    uint32_t x = (v ^ fw) & mask;
+                    while (x) {
+                        const int n = (__ffs(x) - 1) >> 2;
+                        x &= ~(0xfu << (n * 4));
+                        const uint32_t b = (v >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+                        if (b != 15u && is_acgt(rf)) push_entry(sm, Q, i, p0 + n - c.d.col_begin, b, ds);   // variation_classifier.py:147-150
+                    }
+                }
+                q += ln; rc += ln;
+            } else if (op == 1u || op == 4u) q += ln;
+            else if (op == 2u || op == 3u) rc += ln;
+            if (q >= qb + 8) break;
+        }
+    }
+    // ---- indel observations
+    if (lane != 0) return;
     int rc = pos, q = 0, ccl = 0, rcb = 0;
     for (uint32_t ci = c0; ci < c1; ++ci) {
         const uint32_t w = __ldg(c.B.cigar + ci), op = w & 15u;
         const int ln = (int)(w >> 4);
         if (op == 0u || op == 7u || op == 8u) {
-            if (q + ln > L) { raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r); return; }
-            scan_segment(rec, c.B.ref4, q, q + ln, rc, [&](int, int rp, uint32_t b, uint32_t) { push_entry(sm, Q, i, rp - c.d.col_begin, b, ds); });
+            if (q + ln > L) { raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r); return; }   // IndexError in variation_classifier.py:148
             q += ln; rc += ln; ccl += ln;
         } else if (op == 1u || op == 2u) {
             const uint32_t slot = atomicAdd(Q.n_obs, 1u);
@@ -478,7 +516,8 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned lo
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                  int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
-                                                                 ResultView O, unsigned int* __restrict__ ticket) {
+                                                                 ResultView O, unsigned int* __restrict__ ticket, int stop_after) {
+    // stop_after: profiling knob (GA_STOP_AFTER, 0 = run everything): sessions end after phase 1=A1 2=A2 3=R 4=M 5=L 6=B1 7=B2
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem2* sm = reinterpret_cast<Smem2*>(smem_raw);
     __shared__ unsigned long long s_scan64[kThreads / 32 + 1];
@@ -545,11 +584,12 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             }
         }
         __syncthreads();
+        if (stop_after == 1) { __syncthreads(); continue; }
         // ---- phase A2: dense discovery over the queues
         {
             const int nw = min((int)s_nwords, kWords2), ng = min((int)s_ngen, kGen2);
             for (int k = tid; k < nw; k += kThreads) discover_word(c, sm, Q, sm->wlist[k]);
-            for (int k = tid; k < ng; k += kThreads) discover_generic(c, sm, Q, (int)sm->glist[k], n_reads, n_bases);
+            for (int k = warp; k < ng; k += kThreads / 32) discover_generic_warp(c, sm, Q, (int)sm->glist[k], lane, n_reads, n_bases);
             const uint32_t wr = warp_sum(n_reads), wb = warp_sum(n_bases);
             if (lane == 0 && wr) { atomicAdd(&s_reads, wr); atomicAdd(&s_bases, wb); }
         }
@@ -562,6 +602,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         const int n_obs = (int)s_nobs;
         const int n_ent = (int)s_nent;
 
+        if (stop_after == 2) { __syncthreads(); continue; }
         // ---- phase R: germline = seen in tumor AND normal, minus variant_to_keep (AM.py:546-547)
         {
             uint32_t keep_bit = 0u; int keep_col = -1;
@@ -601,6 +642,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         }
         __syncthreads();
 
+        if (stop_after == 3) { __syncthreads(); continue; }
         // ---- phase M: reads that carry a germline SNV allele
         for (int e = tid; e < n_ent; e += kThreads) {
             const uint32_t w = sm->ent[e];
@@ -611,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         }
         __syncthreads();
 
+        if (stop_after == 4) { __syncthreads(); continue; }
         // ---- phase L: ordered list of the modified reads (n_cw <= 128 bitmap words, one per thread)
         uint32_t n_mod;
         {
@@ -641,6 +684,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             __syncthreads();
         }
 
+        if (stop_after == 5) { __syncthreads(); continue; }
         // ---- phase B1: new length of every modified read; indel-masked reads need the edit analysis
         const int per = ((int)n_mod + kThreads - 1) / kThreads;
         const int k0 = min(tid * per, (int)n_mod), k1 = min(k0 + per, (int)n_mod);
@@ -691,6 +735,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
                           (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
         if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
 
+        if (stop_after == 6) { __syncthreads(); continue; }
         // ---- phase B2: clean SNV-only records are plain copies, one 16-byte unit per thread and iteration
         // (their germline hits are patched in phase B3); every other record is written by one warp
         for (uint32_t idx = tid; idx < tot_seq; idx += kThreads) {
@@ -734,6 +779,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         if (lane == 0 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
         __syncthreads();                                              // the copies are in place
 
+        if (stop_after == 7) { __syncthreads(); continue; }
         // ---- phase B3: SNV masking of the copied clean reads, one 4-bit XOR per germline hit (AM.py:170-176)
         for (int e = tid; e < n_ent; e += kThreads) {
             const uint32_t w = sm->ent[e];
