@@ -27,7 +27,8 @@ constexpr int kEnt2 = 2048;            // SNV candidate entries per session
 constexpr int kMod2 = 512;             // modified reads per session
 constexpr int kWords2 = 768;           // queued mismatching words per session
 constexpr int kGen2 = 1024;            // queued non-clean reads per session
-constexpr int kStageWords = 64;        // per-warp staging of an SNV-masked record (reads up to 512 bases)
+constexpr int kStageWords = 64;        // reads longer than 8*kStageWords bases send their session to the fallback kernel
+constexpr int kGroup = 8;              // lanes that cooperate on one non-trivial output record
 
 struct Smem2 {
     uint32_t snv[kCols2];              // bit c: tumor saw base code c, bit 16+c: normal; after resolve: germline codes
@@ -35,7 +36,7 @@ struct Smem2 {
     uint32_t ent[kEnt2];               // (session-relative read << 16) | (column << 4) | base code
     uint32_t wlist[kWords2];           // (session-relative read << 5) | word index; after phase A2 reused as clist
     uint32_t lists[3 * kMod2];         // msize | mseq | mqual
-    uint16_t glist[kGen2];
+    uint16_t glist[kGen2];             // queued non-clean reads (phase A); after A2: indices of the records that need a lane group
     uint32_t modbits[kReads2 / 32];
     uint32_t indelbits[kReads2 / 32];
     uint32_t genbits[kReads2 / 32];
@@ -49,7 +50,6 @@ struct Smem2 {
     int16_t o_next[kObs2];             //   next observation at the same column,
     int16_t o_rnext[kObs2];            //   next germline observation of the same modified read
     int32_t mhead[kMod2];              // per modified read: chain of its germline indel observations
-    uint32_t stage[kThreads / 32][kStageWords];
 };
 static_assert(kWords2 >= kMod2, "clist aliases the word queue");
 
@@ -381,9 +381,9 @@ __device__ int collect_edits(const SessCtx& c, const Smem2* sm, int k, int L, Ed
 // (anonymizer_methods.py:170-176).  Loads and stores are coalesced.
 template <class Store>
 __device__ __forceinline__ void masked_words(const SessCtx& c, const Smem2* sm, int64_t r, int pos, int L, uint32_t c0, uint32_t c1,
-                                             int n_words, int lane, Store&& store) {
+                                             int n_words, int lane, int stride, Store&& store) {
     const uint32_t* rec = rec_of(c, r);
-    for (int w = lane; w < n_words; w += 32) {
+    for (int w = lane; w < n_words; w += stride) {
         const int qb = w << 3;
         uint32_t v = qb < L ? (__ldg(rec + w) & tail_mask(L, w)) : 0u;
         if (qb < L) {
@@ -426,64 +426,301 @@ __device__ __forceinline__ void write_record_meta(const ResultView& O, uint64_t 
     O.mod_qual_off16[rec_idx] = qual16;
 }
 
-// Indel-masked record: the SNV-masked sequence is staged in shared memory, then every output base / quality
-// is pulled through the backward index map of the edits (all DELs, then all INSs, at original offsets:
-// anonymizer_methods.py:254-270, 178-203).  One base (one quality) per lane and iteration.
-__device__ void emit_indel_warp(const SessCtx& c, Smem2* sm, const ResultView& O, int k, int i, int64_t r, uint64_t rec_idx, uint64_t seq16, uint64_t qual16,
-                                int new_len, int lane, int warp) {
-    const uint32_t lf = __ldg(c.B.len_flag + r);
-    const int L = (int)(lf & 0xffffu);                               // <= 8 * kStageWords (longer reads go to the fallback kernel)
+// Base code at original query index j after SNV masking (anonymizer_methods.py:170-176).
+__device__ __forceinline__ uint32_t masked_base2(const SessCtx& c, const Smem2* sm, const uint32_t* rec, uint32_t c0, uint32_t c1, int pos, int j) {
+    const uint32_t b = read_code(rec, j);
+    if (b == 15u) return b;
+    int rc = pos, q = 0;
+    for (uint32_t ci = c0; ci < c1; ++ci) {
+        const uint32_t w = __ldg(c.B.cigar + ci), op = w & 15u;
+        const int ln = (int)(w >> 4);
+        if (op == 0u || op == 7u || op == 8u) {
+            if (j < q + ln) {
+                const int rp = rc + (j - q);
+                return ((sm->snv[rp - c.d.col_begin] >> b) & 1u) ? ref_code(c.B.ref4, rp) : b;
+            }
+            q += ln; rc += ln;
+        } else if (op == 1u || op == 4u) { if (j < q + ln) return b; q += ln; }
+        else if (op == 2u || op == 3u) rc += ln;
+    }
+    return b;
+}
+
+constexpr int kGroupStage = 32;        // words of SNV-masked input staged per lane group (reads up to 256 bases)
+
+// General form (any number of edits, kept in a local array): used for the rare records with more than two edits.
+// Indel-masked records, one per group of kGroup lanes (four records per warp at a time).  The SNV-masked input is
+// staged in shared memory; every output word is then pulled through the backward index map of the record's
+// edits (all DELs, then all INSs, at original offsets: anonymizer_methods.py:254-270, 178-203).  A word whose
+// 8 bases (4 qualities) come from consecutive source positions is one funnel shift of two staged words;
+// words that straddle an edit are assembled base by base.  `act` is false for the lanes of a group without a
+// record; they only take part in the shuffles.
+__device__ __noinline__ void emit_indel_group_slow(const SessCtx& c, Smem2* sm, const ResultView& O, bool act, int k, int i, uint64_t seq16, uint64_t qual16,
+                                 int new_len, int glane, int group) {
+    const int64_t r = act ? read_of(c, i) : 0;
+    uint32_t lf = 0u, c0 = 0u, c1 = 0u; int pos = 0;
+    if (act) { lf = __ldg(c.B.len_flag + r); c0 = __ldg(c.B.cigar_off + r); c1 = __ldg(c.B.cigar_off + r + 1); pos = __ldg(c.B.pos + r); }
+    const int L = (int)(lf & 0xffffu);
     Edit edits[GA_MAX_EDITS];
     int ne = 0, n_del = 0; bool too_many = false;
-    collect_edits(c, sm, k, L, edits, &ne, &n_del, &too_many);
-    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
-    const int pos = __ldg(c.B.pos + r);
-    uint32_t* stage = sm->stage[warp];
-    masked_words(c, sm, r, pos, L, c0, c1, (L + 7) >> 3, lane, [&](int w, uint32_t v) { stage[w] = v; });
-    const uint8_t* qrec = qual_record_in(c.B, r, i < c.nt ? c.d.qt_begin : c.d.qn_begin, i < c.nt ? c.d.qt_end : c.d.qn_end);
-    if (!qrec) { if (lane == 0) raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); return; }
+    const uint8_t* qrec = nullptr;
+    if (act) {
+        collect_edits(c, sm, k, L, edits, &ne, &n_del, &too_many);
+        qrec = qual_record_in(c.B, r, i < c.nt ? c.d.qt_begin : c.d.qn_begin, i < c.nt ? c.d.qt_end : c.d.qn_end);
+        if (!qrec) { if (glane == 0) raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
+    }
     const bool reverse = ((lf >> 16) & 0x10u) != 0u;
+    const uint32_t* rec = act ? rec_of(c, r) : nullptr;
+    // ---- stage the SNV-masked input (o_sig0/o_sig1 are dead after phase R: 4 KB = 32 groups x 32 words)
+    uint32_t* stage = sm->o_sig0 + group * kGroupStage;
+    const bool staged = act && ((L + 7) >> 3) <= kGroupStage - 1;
+    if (staged) {
+        masked_words(c, sm, r, pos, L, c0, c1, (L + 7) >> 3, glane, kGroup, [&](int w, uint32_t v) { stage[w] = v; });
+        if (glane == 0) stage[(L + 7) >> 3] = 0u;                      // the funnel shift may touch one word past the end
+    }
     {   // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (AM.py:193)
         uint32_t part = 0;
-        for (int k = lane; k < L; k += 32) part += qrec[k];
-        uint32_t sum = warp_sum(part), n = (uint32_t)L;
-        for (int k = 0; k < n_del; ++k) {
+        if (act) {
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+            for (int q = glane; q < ((L + 3) >> 2); q += kGroup) {
+                uint32_t v = __ldg(qw + q);
+                if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
+                part += (v & 0xffu) + ((v >> 8) & 0xffu) + ((v >> 16) & 0xffu) + (v >> 24);
+            }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
+        uint32_t sum = part, n = (uint32_t)L;
+        for (int q = 0; q < n_del; ++q) {
             const uint32_t m = n ? sum / n : 0u;
-            edits[k].mean = m;
-            sum += m * (uint32_t)edits[k].len; n += (uint32_t)edits[k].len;
-            if (lane == 0 && (int64_t)edits[k].pos + edits[k].len > c.B.ref_len) raise_error(c.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
+            edits[q].mean = m;
+            sum += m * (uint32_t)edits[q].len; n += (uint32_t)edits[q].len;
+            if (glane == 0 && (int64_t)edits[q].pos + edits[q].len > c.B.ref_len) raise_error(c.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
         }
     }
-    __syncwarp();
+    __syncwarp();                                                     // staged words visible to the group
+    if (!act) return;
+    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
+    // ---- sequence words
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+    for (int w = glane; w < units * 4; w += kGroup) {
+        const int j0 = w << 3;
+        uint32_t v = 0u;
+        if (j0 < new_len) {
+            int kin0 = 0, kin7 = 0;
+            const int jl = min(j0 + 7, new_len - 1);
+            const int s0 = map_back(edits, n_del, ne, j0, &kin0), s7 = map_back(edits, n_del, ne, jl, &kin7);
+            if (staged && ne == 1 && s0 >= 0 && s7 - s0 == jl - j0) {  // one contiguous run of input bases (exact for a single edit)
+                v = __funnelshift_r(stage[s0 >> 3], stage[(s0 >> 3) + 1], (uint32_t)(s0 & 7) * 4u);
+                if (jl - j0 < 7) v &= 0xffffffffu >> ((7 - (jl - j0)) * 4);
+            } else {
+                for (int n = 0; n <= jl - j0; ++n) {
+                    int kin = 0;
+                    const int src = map_back(edits, n_del, ne, j0 + n, &kin);
+                    uint32_t code;
+                    if (src < 0) code = ref_code(c.B.ref4, (int64_t)edits[-1 - src].pos + kin);
+                    else if (staged) code = (stage[src >> 3] >> ((src & 7) * 4)) & 15u;
+                    else code = masked_base2(c, sm, rec, c0, c1, pos, src);
+                    v |= code << (n * 4);
+                }
+            }
+        }
+        oseq[w] = v;
+    }
+    // ---- quality words (printed order = reversed forward-orientation array for reverse reads, AM.py:95,213)
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+    for (int w = glane; w < units * 8; w += kGroup) {
+        const int p0 = w << 2;
+        uint32_t v = 0u;
+        if (p0 < new_len) {
+            const int pl = min(p0 + 3, new_len - 1);
+            int kin0 = 0, kin3 = 0;
+            const int f0 = reverse ? new_len - 1 - p0 : p0, f3 = reverse ? new_len - 1 - pl : pl;
+            const int s0 = map_back(edits, n_del, ne, f0, &kin0), s3 = map_back(edits, n_del, ne, f3, &kin3);
+            const int b0 = reverse ? L - 1 - s0 : s0;                   // byte of the BAM-order quality record
+            const bool run = ne == 1 && s0 >= 0 && s3 >= 0 && (reverse ? s0 - s3 : s3 - s0) == pl - p0;
+            if (run) {
+                const uint32_t lo = __ldg(qw + (b0 >> 2)), hi = (b0 & 3) ? __ldg(qw + (b0 >> 2) + 1) : 0u;
+                v = __funnelshift_r(lo, hi, (uint32_t)(b0 & 3) * 8u);
+                if (pl - p0 < 3) v &= 0xffffffffu >> ((3 - (pl - p0)) * 8);
+            } else {
+                for (int n = 0; n <= pl - p0; ++n) {
+                    int kin = 0;
+                    const int f = reverse ? new_len - 1 - (p0 + n) : p0 + n;
+                    const int src = map_back(edits, n_del, ne, f, &kin);
+                    const uint32_t qv = src >= 0 ? (uint32_t)qrec[reverse ? L - 1 - src : src] : edits[-1 - src].mean;
+                    v |= qv << (n * 8);
+                }
+            }
+        }
+        oq[w] = v;
+    }
+}
+
+__device__ __noinline__ int new_len_slow(const SessCtx& c, const Smem2* sm, const ResultView& O, int k, int L, int64_t r) {
+    Edit edits[GA_MAX_EDITS];
+    int ne = 0, nd = 0; bool too_many = false;
+    const int new_len = collect_edits(c, sm, k, L, edits, &ne, &nd, &too_many);
+    if (too_many) raise_error(O.totals, GA_ERR_UNSUPPORTED, (uint32_t)r);
+    return new_len;
+}
+
+// ------------------------------------------------------------------ up to two edits, entirely in registers
+// (local-memory arrays are expensive here: with ~216 KB of the SM's 256 KB configured as shared memory there is
+// almost no L1 left to hold them)
+struct Ed2 {
+    int irp[2], len[2], pos[2], p[2], e[2];
+    uint32_t mean[2];
+    int ne, n_del;
+};
+
+// Germline indel edits of modified read k when there are at most two; false otherwise.  Same ordering and
+// clamping rules as collect_edits.
+__device__ __forceinline__ bool collect2(const SessCtx& c, const Smem2* sm, int k, int L, Ed2& E, int* new_len) {
+    const int oa = sm->mhead[k];
+    const int ob = oa >= 0 ? (int)sm->o_rnext[oa] : -1;
+    if (ob >= 0 && sm->o_rnext[ob] >= 0) return false;
+    int x = oa, y = ob;
+    if (y >= 0 && y < x) { const int t = x; x = y; y = t; }          // CIGAR order = slot order
+    E.ne = (x >= 0) + (y >= 0);
+    const uint32_t mx = x >= 0 ? sm->o_meta[x] : 0u, my = y >= 0 ? sm->o_meta[y] : 0u;
+    if (y >= 0 && (mx & kMetaIns) && !(my & kMetaIns)) { const int t = x; x = y; y = t; }   // DELs before INSs (AM.py:264)
+    const int o[2] = {x, y};
+    E.n_del = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const bool has = o[q] >= 0;
+        const uint32_t m = has ? sm->o_meta[o[q]] : kMetaIns;
+        E.irp[q] = has ? sm->o_irp[o[q]] : 0; E.len[q] = has ? (int)(m & kMetaLenMask) : 0;
+        E.pos[q] = has ? sm->o_col[o[q]] + c.d.col_begin : 0; E.mean[q] = 0u;
+        if (has && !(m & kMetaIns)) ++E.n_del;
+    }
+    int cur = L;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q >= E.ne) { E.p[q] = 0x7fffffff; E.e[q] = 0x7fffffff; continue; }
+        if (q < E.n_del) {
+            E.p[q] = E.irp[q] < cur ? E.irp[q] : cur; E.e[q] = E.p[q] + E.len[q]; cur += E.len[q];
+        } else {
+            const int pp = E.irp[q] < cur ? E.irp[q] : cur;
+            const int ee = E.irp[q] + E.len[q] < cur ? E.irp[q] + E.len[q] : cur;
+            E.p[q] = pp; E.e[q] = ee > pp ? ee : pp; cur -= (E.e[q] - pp);
+        }
+    }
+    *new_len = cur;
+    return true;
+}
+
+// Final index -> original index (>= 0), or -1 - q when the element was inserted by DEL edit q (*kin = offset in it).
+__device__ __forceinline__ int map_back2(const Ed2& E, int j, int* kin) {
+#pragma unroll
+    for (int q = 1; q >= 0; --q)
+        if (q < E.ne && q >= E.n_del && j >= E.p[q]) j += E.e[q] - E.p[q];
+#pragma unroll
+    for (int q = 1; q >= 0; --q)
+        if (q < E.n_del) {
+            if (j >= E.e[q]) j -= E.len[q];
+            else if (j >= E.p[q]) { *kin = j - E.p[q]; return -1 - q; }
+        }
+    return j;
+}
+
+// Indel-masked records with at most two edits, one per group of kGroup lanes (see emit_indel_group_slow for the
+// general form and the references).  A word whose bases (qualities) come from consecutive source positions is one
+// funnel shift of two staged words; words that straddle an edit are assembled element by element.
+__device__ void emit_indel_group(const SessCtx& c, Smem2* sm, const ResultView& O, bool act, const Ed2& E, int i, uint64_t seq16, uint64_t qual16,
+                                 int new_len, int glane, int group) {
+    const int64_t r = act ? read_of(c, i) : 0;
+    uint32_t lf = 0u, c0 = 0u, c1 = 0u; int pos = 0;
+    if (act) { lf = __ldg(c.B.len_flag + r); c0 = __ldg(c.B.cigar_off + r); c1 = __ldg(c.B.cigar_off + r + 1); pos = __ldg(c.B.pos + r); }
+    const int L = (int)(lf & 0xffffu);
+    const uint8_t* qrec = nullptr;
+    if (act) {
+        qrec = qual_record_in(c.B, r, i < c.nt ? c.d.qt_begin : c.d.qn_begin, i < c.nt ? c.d.qt_end : c.d.qn_end);
+        if (!qrec) { if (glane == 0) raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
+    }
+    const bool reverse = ((lf >> 16) & 0x10u) != 0u;
+    const uint32_t* rec = act ? rec_of(c, r) : nullptr;
+    uint32_t* stage = sm->o_sig0 + group * kGroupStage;              // o_sig0/o_sig1 are dead after phase R
+    const bool staged = act && ((L + 7) >> 3) <= kGroupStage - 1;
+    if (staged) {
+        masked_words(c, sm, r, pos, L, c0, c1, (L + 7) >> 3, glane, kGroup, [&](int w, uint32_t v) { stage[w] = v; });
+        if (glane == 0) stage[(L + 7) >> 3] = 0u;
+    }
+    uint32_t mean0 = 0u, mean1 = 0u;
+    {   // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (AM.py:193)
+        uint32_t part = 0;
+        if (act) {
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+            for (int q = glane; q < ((L + 3) >> 2); q += kGroup) {
+                uint32_t v = __ldg(qw + q);
+                if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
+                part += (v & 0xffu) + ((v >> 8) & 0xffu) + ((v >> 16) & 0xffu) + (v >> 24);
+            }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
+        uint32_t sum = part, n = (uint32_t)L;
+        if (E.n_del >= 1) { mean0 = n ? sum / n : 0u; sum += mean0 * (uint32_t)E.len[0]; n += (uint32_t)E.len[0]; }
+        if (E.n_del >= 2) { mean1 = n ? sum / n : 0u; }
+        if (act && glane == 0) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (q < E.n_del && (int64_t)E.pos[q] + E.len[q] > c.B.ref_len) raise_error(c.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
+        }
+    }
+    __syncwarp();                                                     // staged words visible to the group
+    if (!act) return;
     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-    for (int j = lane; j < units * 32; j += 32) {
-        uint32_t code = 0u;
-        if (j < new_len) {
+    for (int w = glane; w < units * 4; w += kGroup) {
+        const int j0 = w << 3;
+        uint32_t v = 0u;
+        if (j0 < new_len) {
             int kin = 0;
-            const int src = map_back(edits, n_del, ne, j, &kin);
-            code = src >= 0 ? (stage[src >> 3] >> ((src & 7) * 4)) & 15u : ref_code(c.B.ref4, (int64_t)edits[-1 - src].pos + kin);
+            const int jl = min(j0 + 7, new_len - 1);
+            const int s0 = map_back2(E, j0, &kin), s7 = map_back2(E, jl, &kin);
+            if (staged && E.ne == 1 && s0 >= 0 && s7 - s0 == jl - j0) {   // one contiguous run (exact for a single edit)
+                v = __funnelshift_r(stage[s0 >> 3], stage[(s0 >> 3) + 1], (uint32_t)(s0 & 7) * 4u);
+                if (jl - j0 < 7) v &= 0xffffffffu >> ((7 - (jl - j0)) * 4);
+            } else {
+                for (int n = 0; n <= jl - j0; ++n) {
+                    const int src = map_back2(E, j0 + n, &kin);
+                    uint32_t code;
+                    if (src < 0) code = ref_code(c.B.ref4, (int64_t)(src == -1 ? E.pos[0] : E.pos[1]) + kin);
+                    else if (staged) code = (stage[src >> 3] >> ((src & 7) * 4)) & 15u;
+                    else code = masked_base2(c, sm, rec, c0, c1, pos, src);
+                    v |= code << (n * 4);
+                }
+            }
         }
-        uint32_t v = code << ((j & 7) * 4);
-        v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
-        if ((lane & 7) == 0) oseq[j >> 3] = v;
+        oseq[w] = v;
     }
     uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
-    for (int jp = lane; jp < units * 32; jp += 32) {
-        uint32_t qv = 0u;
-        if (jp < new_len) {
-            // printed order = reversed forward-orientation array for reverse reads (anonymizer_methods.py:95,213)
-            const int jf = reverse ? new_len - 1 - jp : jp;
+    const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+    for (int w = glane; w < units * 8; w += kGroup) {
+        const int p0 = w << 2;
+        uint32_t v = 0u;
+        if (p0 < new_len) {
+            const int pl = min(p0 + 3, new_len - 1);
             int kin = 0;
-            const int src = map_back(edits, n_del, ne, jf, &kin);
-            qv = src >= 0 ? (uint32_t)qrec[reverse ? L - 1 - src : src] : edits[-1 - src].mean;
+            const int f0 = reverse ? new_len - 1 - p0 : p0, f3 = reverse ? new_len - 1 - pl : pl;
+            const int s0 = map_back2(E, f0, &kin), s3 = map_back2(E, f3, &kin);
+            const int b0 = reverse ? L - 1 - s0 : s0;                   // byte of the BAM-order quality record
+            if (E.ne == 1 && s0 >= 0 && s3 >= 0 && (reverse ? s0 - s3 : s3 - s0) == pl - p0) {
+                const uint32_t lo = __ldg(qw + (b0 >> 2)), hi = (b0 & 3) ? __ldg(qw + (b0 >> 2) + 1) : 0u;
+                v = __funnelshift_r(lo, hi, (uint32_t)(b0 & 3) * 8u);
+                if (pl - p0 < 3) v &= 0xffffffffu >> ((3 - (pl - p0)) * 8);
+            } else {
+                for (int n = 0; n <= pl - p0; ++n) {
+                    const int f = reverse ? new_len - 1 - (p0 + n) : p0 + n;
+                    const int src = map_back2(E, f, &kin);
+                    const uint32_t qv = src >= 0 ? (uint32_t)qrec[reverse ? L - 1 - src : src] : (src == -1 ? mean0 : mean1);
+                    v |= qv << (n * 8);
+                }
+            }
         }
-        uint32_t v = qv << ((jp & 3) * 8);
-        v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2);
-        if ((lane & 3) == 0) oq[jp >> 2] = v;
+        oq[w] = v;
     }
-    if (lane == 0) write_record_meta(O, rec_idx, c.s, r, new_len, seq16, (uint32_t)qual16);
-    __syncwarp();                                                     // stage is reused by this warp's next record
 }
 
 // Block-wide exclusive scan of a 64-bit value per thread.
@@ -522,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
     Smem2* sm = reinterpret_cast<Smem2*>(smem_raw);
     __shared__ unsigned long long s_scan64[kThreads / 32 + 1];
     __shared__ uint32_t s_scan[kThreads / 32 + 1];
-    __shared__ uint32_t s_nobs, s_nent, s_nwords, s_ngen, s_reads, s_bases, s_cnt[3], s_overflow;
+    __shared__ uint32_t s_nobs, s_nent, s_nwords, s_ngen, s_nx, s_reads, s_bases, s_cnt[3], s_overflow;
     __shared__ int s_next_session;
     __shared__ unsigned long long s_base[3];
 
@@ -560,7 +797,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             if (nx < n_work) prefetch_session(B, descs[nx]);
         }
         if (tid == 0) {
-            s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
+            s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_nx = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
         }
         if (c.d.big) { __syncthreads(); continue; }
         c.first = S.first[s];
@@ -694,15 +931,16 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             const int64_t r = read_of(c, i);
             uint32_t m;
             if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
-                Edit edits[GA_MAX_EDITS];
-                int ne = 0, nd = 0; bool too_many = false;
-                const int new_len = collect_edits(c, sm, k, (int)(__ldg(c.B.len_flag + r) & 0xffffu), edits, &ne, &nd, &too_many);
-                if (too_many) raise_error(O.totals, GA_ERR_UNSUPPORTED, (uint32_t)r);
+                const int L0 = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
+                Ed2 E2;
+                int new_len = L0;
+                if (!collect2(c, sm, k, L0, E2, &new_len)) new_len = new_len_slow(c, sm, O, k, L0, r);
                 m = kModFlag | kQualFlag | ((uint32_t)new_len & kLenMask);
             } else {
                 m = kModFlag | (__ldg(c.B.len_flag + r) & 0xffffu);
             }
             msize[k] = m;
+            if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u)) sm->glist[atomicAdd(&s_nx, 1u)] = (uint16_t)k;
             uint32_t units = ((m & kLenMask) + 31u) / 32u; if (units < 1u) units = 1u;
             mine += (1ull << 48) | ((unsigned long long)units << 24) | ((m & kQualFlag) ? (unsigned long long)units : 0ull);
         }
@@ -750,31 +988,44 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             if (32 * u + 32 > L) { v.x &= tail_mask(L, 4 * u); v.y &= tail_mask(L, 4 * u + 1); v.z &= tail_mask(L, 4 * u + 2); v.w &= tail_mask(L, 4 * u + 3); }
             *reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (s_base[1] + idx)) = v;
         }
+        if (stop_after == 71) { __syncthreads(); continue; }
+        uint32_t n_q = 0;
         for (int k = tid; k < (int)n_mod; k += kThreads) {            // record headers, coalesced
             const uint32_t m = msize[k];
-            if (m & kQualFlag) continue;                              // written by emit_indel_warp
-            write_record_meta(O, s_base[0] + k, s, read_of(c, (int)clist[k]), (int)(m & kLenMask), s_base[1] + mseq[k], 0xffffffffu);
+            const bool q = (m & kQualFlag) != 0u;
+            n_q += q ? 1u : 0u;
+            write_record_meta(O, s_base[0] + k, s, read_of(c, (int)clist[k]), (int)(m & kLenMask), s_base[1] + mseq[k],
+                              q ? (uint32_t)(s_base[2] + mqual[k]) : 0xffffffffu);
         }
-        uint32_t n_q = 0;
-        for (int k = warp; k < (int)n_mod; k += kThreads / 32) {
-            const uint32_t m = msize[k];
-            const int i = (int)clist[k];
-            const bool gen = ((sm->genbits[i >> 5] >> (i & 31)) & 1u) != 0u;
-            if (!(m & kQualFlag) && !gen) continue;
-            const int64_t r = read_of(c, i);
-            const int L = (int)(m & kLenMask);
-            const uint64_t seq16 = s_base[1] + mseq[k];
-            if (m & kQualFlag) {
-                emit_indel_warp(c, sm, O, k, i, r, s_base[0] + k, seq16, s_base[2] + mqual[k], L, lane, warp);
-                ++n_q;
-                continue;
+        if (stop_after == 72) { __syncthreads(); continue; }
+        {   // records that are not plain copies: one group of kGroup lanes each
+            const int nx = (int)s_nx, group = tid / kGroup, glane = tid % kGroup;
+            for (int base = 0; base < nx; base += kThreads / kGroup) {
+                const int xi = base + group;
+                const bool have = xi < nx;
+                const int k = have ? (int)sm->glist[xi] : 0;
+                const uint32_t m = have ? msize[k] : 0u;
+                const int i = have ? (int)clist[k] : 0;
+                const int L = (int)(m & kLenMask);
+                const uint64_t seq16 = s_base[1] + (have ? mseq[k] : 0u);
+                const bool indel = have && (m & kQualFlag);
+                if (__any_sync(0xffffffffu, indel)) {
+                    Ed2 E2; E2.ne = 0; E2.n_del = 0;
+                    int nl = L;
+                    const bool fast = indel && collect2(c, sm, k, (int)(__ldg(c.B.len_flag + read_of(c, i)) & 0xffffu), E2, &nl);
+                    const uint64_t qual16 = s_base[2] + (have ? mqual[k] : 0u);
+                    emit_indel_group(c, sm, O, fast, E2, i, seq16, qual16, L, glane, group);
+                    if (__any_sync(0xffffffffu, indel && !fast)) emit_indel_group_slow(c, sm, O, indel && !fast, k, i, seq16, qual16, L, glane, group);
+                }
+                if (have && !indel) {                                 // other CIGARs, SNV-only: re-walk, mask while copying
+                    const int64_t r = read_of(c, i);
+                    int units = (L + 31) >> 5; if (units < 1) units = 1;
+                    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+                    const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
+                    masked_words(c, sm, r, __ldg(c.B.pos + r), L, c0, c1, units * 4, glane, kGroup, [&](int w, uint32_t v) { oseq[w] = v; });
+                }
             }
-            int units = (L + 31) >> 5; if (units < 1) units = 1;       // other CIGARs: re-walk, mask while copying
-            uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-            const uint32_t c0 = __ldg(c.B.cigar_off + r), c1 = __ldg(c.B.cigar_off + r + 1);
-            masked_words(c, sm, r, __ldg(c.B.pos + r), L, c0, c1, units * 4, lane, [&](int w, uint32_t v) { oseq[w] = v; });
         }
-        if (lane != 0) n_q = 0;
         n_q = warp_sum(n_q);
         if (lane == 0 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
         __syncthreads();                                              // the copies are in place
