@@ -5,7 +5,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libga_b200.so")
+LIB_PATH = os.environ.get("GA_B200_LIB") or os.path.join(_HERE, "libga_b200.so")   # override: A/B timing of kernel variants
 _LIB = None
 
 # every entry point declared in include/ga_b200.h

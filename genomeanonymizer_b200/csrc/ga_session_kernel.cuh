@@ -251,8 +251,10 @@ __device__ __forceinline__ const uint8_t* qual_record_in(const BatchView& B, int
 // Maps a final array index back through the edits (last applied first).  Returns the original index,
 // or -1 - (edit index) when the element was inserted by that DEL edit (then *k_in is its offset).
 __device__ __forceinline__ int map_back(const Edit* edits, int n_del, int ne, int j, int* k_in) {
+#pragma unroll 1
     for (int k = ne - 1; k >= n_del; --k)
         if (j >= edits[k].p_eff) j += edits[k].e_eff - edits[k].p_eff;
+#pragma unroll 1
     for (int k = n_del - 1; k >= 0; --k) {
         if (j >= edits[k].e_eff) j -= edits[k].len;
         else if (j >= edits[k].p_eff) { *k_in = j - edits[k].p_eff; return -1 - k; }

@@ -36,6 +36,7 @@ struct Smem2 {
     uint32_t ent[kEnt2];               // (session-relative read << 16) | (column << 4) | base code
     uint32_t wlist[kWords2];           // (session-relative read << 5) | word index; after phase A2 reused as clist
     uint32_t lists[3 * kMod2];         // msize | mseq | mqual
+    uint32_t sref[kCols2 / 8 + 8];     // 4-bit reference of the session's columns (word 0 = ref4 word of column col_begin)
     uint16_t glist[kGen2];             // queued non-clean reads (phase A); after A2: indices of the records that need a lane group
     uint32_t modbits[kReads2 / 32];
     uint32_t indelbits[kReads2 / 32];
@@ -71,10 +72,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint64_t bytes) {
 }
 
 // Everything phase A1 of session `d` will read, requested while the previous session is still running.
-__device__ __forceinline__ void prefetch_session(const BatchView& B, const SessionDesc& d) {
+__device__ __forceinline__ void prefetch_session(const BatchView& B, const SessionDesc& d, bool records) {
     if (d.big) return;
-    prefetch_l2(B.seq4 + 16ull * d.t_seq_lo, 16ull * d.t_seq_n);
-    prefetch_l2(B.seq4 + 16ull * d.n_seq_lo, 16ull * d.n_seq_n);
+    if (records) {
+        prefetch_l2(B.seq4 + 16ull * d.t_seq_lo, 16ull * d.t_seq_n);
+        prefetch_l2(B.seq4 + 16ull * d.n_seq_lo, 16ull * d.n_seq_n);
+    }
     const int64_t nt = d.t_end - d.t_begin, nn = d.n_end - d.n_begin;
     prefetch_l2(B.pos + d.t_begin, 4 * nt);       prefetch_l2(B.pos + d.n_begin, 4 * nn);
     prefetch_l2(B.len_flag + d.t_begin, 4 * nt);  prefetch_l2(B.len_flag + d.n_begin, 4 * nn);
@@ -94,28 +97,26 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     return v;
 }
 
-// Bitmask of the 8-base words of a clean read that differ from the reference (U 16-byte units).
+// Bitmask of the 8-base words of a clean read that differ from the reference (U 16-byte units).  The record
+// comes in with U independent 128-bit loads; the reference words come from the session's window in shared memory.
 template <int U>
-__device__ __forceinline__ uint32_t clean_word_mask(const uint4* __restrict__ rec, const uint32_t* __restrict__ ref4, int pos, int L) {
-    uint32_t rw[4 * U];
+__device__ __forceinline__ uint32_t clean_word_mask(const uint4* __restrict__ rec, const uint32_t* __restrict__ sref, int rel_nibble, int L) {
+    uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint4 v = ldg128(rec + u);
-        rw[4 * u] = v.x; rw[4 * u + 1] = v.y; rw[4 * u + 2] = v.z; rw[4 * u + 3] = v.w;
-    }
-    const int64_t ni = (int64_t)pos + 8;
-    const uint32_t* rp = ref4 + (ni >> 3);
-    const uint32_t sh = (uint32_t)(ni & 7) * 4u;
-    uint32_t prev = __ldg(rp);
+    for (int u = 0; u < U; ++u) v[u] = ldg128(rec + u);
+    const uint32_t* rp = sref + (rel_nibble >> 3);
+    const uint32_t sh = (uint32_t)(rel_nibble & 7) * 4u;
+    uint32_t prev = rp[0];
     uint32_t wm = 0u;
 #pragma unroll
     for (int k = 0; k < 4 * U; ++k) {
-        const uint32_t next = __ldg(rp + k + 1);
+        const uint32_t next = rp[k + 1];
         const uint32_t fw = __funnelshift_r(prev, next, sh);             // sh == 0 returns prev
         prev = next;
+        const uint32_t rw = (k & 3) == 0 ? v[k >> 2].x : (k & 3) == 1 ? v[k >> 2].y : (k & 3) == 2 ? v[k >> 2].z : v[k >> 2].w;
         if (k >= 4 * (U - 1)) {                                           // only the last unit can hold padding
-            if ((rw[k] ^ fw) & tail_mask(L, k)) wm |= 1u << k;
-        } else if (rw[k] != fw) wm |= 1u << k;
+            if ((rw ^ fw) & tail_mask(L, k)) wm |= 1u << k;
+        } else if (rw != fw) wm |= 1u << k;
     }
     return wm;
 }
@@ -153,12 +154,15 @@ __device__ __forceinline__ void scan_read(const SessCtx& c, Smem2* sm, const Que
     const uint4* rec = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * m.so);
     uint32_t wm = 0u;
     bool supported = spec;
+    // nibble offset of base `pos` inside the staged window (ref4 nibble of base p is p + 8; the window starts at
+    // the ref4 word holding column col_begin)
+    const int rel = pos + 8 - ((c.d.col_begin + 8) & ~7);
     if (spec) {
         switch (units) {
-            case 5: wm = clean_word_mask<5>(rec, c.B.ref4, pos, L); break;
-            case 4: wm = clean_word_mask<4>(rec, c.B.ref4, pos, L); break;
-            case 3: wm = clean_word_mask<3>(rec, c.B.ref4, pos, L); break;
-            case 8: wm = clean_word_mask<8>(rec, c.B.ref4, pos, L); break;
+            case 5: wm = clean_word_mask<5>(rec, sm->sref, rel, L); break;
+            case 4: wm = clean_word_mask<4>(rec, sm->sref, rel, L); break;
+            case 3: wm = clean_word_mask<3>(rec, sm->sref, rel, L); break;
+            case 8: wm = clean_word_mask<8>(rec, sm->sref, rel, L); break;
             default: supported = false; break;
         }
     }
@@ -176,6 +180,104 @@ __device__ __forceinline__ void scan_read(const SessCtx& c, Smem2* sm, const Que
         const int k = __ffs(wm) - 1; wm &= wm - 1;
         const uint32_t e = atomicAdd(Q.n_words, 1u);
         if (e < (uint32_t)kWords2) sm->wlist[e] = ((uint32_t)i << 5) | (uint32_t)k; else *Q.overflow = 1u;
+    }
+}
+
+// One tile of 32 consecutive reads of one dataset whose records are contiguous and equally long (the normal case):
+// the warp fetches the tile's records with U fully coalesced 128-bit loads per lane - every 32-byte sector is
+// requested exactly once - and each lane compares the 16-byte units it happens to hold (32 bases of some read
+// of the tile) with that read's reference bases, whose position comes from the owning lane by shuffle.
+// The record loads are issued before anything that depends on the CIGAR word, so a tile costs one memory
+// round trip (its meta was fetched while the previous tile was being compared).
+template <int U>
+__device__ __forceinline__ void scan_tile(const SessCtx& c, Smem2* sm, const Queues& Q, int i0, int n_valid, int lane, const ReadMeta& m,
+                                          uint32_t so0, uint32_t& n_reads, uint32_t& n_bases) {
+    const uint4* base = reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * so0);
+    const int n_chunks = n_valid * U;
+    uint4 v[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int g = j * 32 + lane;
+        v[j] = g < n_chunks ? ldg128(base + g) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int i = i0 + lane;
+    const bool valid = lane < n_valid;
+    const int pos = m.pos;
+    const int L = (int)(m.lf & 0xffffu);
+    const bool one_op = valid && (m.c1 - m.c0 == 1u);
+    const bool spec = one_op && pos >= 0 && (int64_t)pos + L <= c.B.ref_len && pos >= c.d.col_begin && pos + L - c.d.col_begin < c.d.n_cols;
+    const uint32_t w0 = one_op ? __ldg(c.B.cigar + m.c0) : 0u;
+    const uint32_t op0 = w0 & 15u;
+    const bool clean = spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(w0 >> 4) == L);
+    const int rel = pos + 8 - ((c.d.col_begin + 8) & ~7);              // nibble offset of base `pos` inside the staged window
+    const bool in_session = clean && pos + L > c.first;                  // fetched by range but not reaching the region: skipped
+    const uint32_t clean_mask = __ballot_sync(0xffffffffu, in_session);
+    if (in_session) { n_reads += 1u; n_bases += (uint32_t)L; }
+    if (valid && !clean) {                                               // any other CIGAR (or an error case): queued for phase A2
+        const uint32_t g = atomicAdd(Q.n_gen, 1u);
+        if (g < (uint32_t)kGen2) sm->glist[g] = (uint16_t)i; else *Q.overflow = 1u;
+        atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
+    }
+    uint32_t all = 0u;                                                   // bit 4*j + k: word k of chunk j differs from the reference
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int g = j * 32 + lane;
+        const int src = g / U, u = g - src * U;                          // owning read (lane of the tile) and unit inside it
+        const int rel_s = __shfl_sync(0xffffffffu, rel, src & 31);
+        const int L_s = __shfl_sync(0xffffffffu, L, src & 31);
+        const bool ok = g < n_chunks && ((clean_mask >> src) & 1u);     // only clean reads inside the table have a valid offset
+        const int nib = ok ? rel_s + 32 * u : 0;
+        const uint32_t* rp = sm->sref + (nib >> 3);
+        const uint32_t sh = (uint32_t)(nib & 7) * 4u;
+        const uint32_t r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4];
+        uint32_t x0 = v[j].x ^ __funnelshift_r(r0, r1, sh), x1 = v[j].y ^ __funnelshift_r(r1, r2, sh);
+        uint32_t x2 = v[j].z ^ __funnelshift_r(r2, r3, sh), x3 = v[j].w ^ __funnelshift_r(r3, r4, sh);
+        // padding: words of this unit with any valid base, and the partial mask of the read's last word
+        const int nvw = ((L_s + 7) >> 3) - 4 * u;
+        const uint32_t pm = (L_s & 7) ? (0xffffffffu >> ((8 - (L_s & 7)) * 4)) : 0xffffffffu;
+        x0 = nvw <= 0 ? 0u : (nvw == 1 ? x0 & pm : x0);
+        x1 = nvw <= 1 ? 0u : (nvw == 2 ? x1 & pm : x1);
+        x2 = nvw <= 2 ? 0u : (nvw == 3 ? x2 & pm : x2);
+        x3 = nvw <= 3 ? 0u : (nvw == 4 ? x3 & pm : x3);
+        uint32_t wm = (x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u);
+        if (!ok) wm = 0u;
+        all |= wm << (4 * j);
+    }
+    while (all) {                                                        // rare: queue the mismatching words for phase A2
+        const int b = __ffs(all) - 1; all &= all - 1;
+        const int g = (b >> 2) * 32 + lane;
+        const int src = g / U, u = g - src * U;
+        const uint32_t e = atomicAdd(Q.n_words, 1u);
+        if (e < (uint32_t)kWords2) sm->wlist[e] = ((uint32_t)(i0 + src) << 5) | (uint32_t)(4 * u + (b & 3)); else *Q.overflow = 1u;
+    }
+}
+
+// Phase A1: warp per tile of 32 reads.
+__device__ __forceinline__ void phase_scan(const SessCtx& c, Smem2* sm, const Queues& Q, uint32_t& n_reads, uint32_t& n_bases) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nn = c.n_range - c.nt;
+    const int tiles_t = (c.nt + 31) >> 5, tiles = tiles_t + ((nn + 31) >> 5);
+    auto tile_i0 = [&](int t) { return t < tiles_t ? 32 * t : c.nt + 32 * (t - tiles_t); };
+    auto tile_nv = [&](int t) { return min(32, (t < tiles_t ? c.nt : c.n_range) - tile_i0(t)); };
+    for (int t = warp; t < tiles; t += kThreads / 32) {
+        ReadMeta m = {};
+        if (lane < tile_nv(t)) m = load_meta(c, tile_i0(t) + lane);
+        const int i0 = tile_i0(t), n_valid = tile_nv(t);
+        const bool valid = lane < n_valid;
+        const int units = (int)(((m.lf & 0xffffu) + 31u) >> 5);
+        const int U0 = __shfl_sync(0xffffffffu, units, 0);
+        const uint32_t so0 = __shfl_sync(0xffffffffu, m.so, 0);
+        const bool fits = !valid || (units == U0 && m.so == so0 + (uint32_t)(lane * U0));
+        if (__all_sync(0xffffffffu, fits) && (U0 == 5 || U0 == 4 || U0 == 3 || U0 == 8)) {
+            switch (U0) {
+                case 5: scan_tile<5>(c, sm, Q, i0, n_valid, lane, m, so0, n_reads, n_bases); break;
+                case 4: scan_tile<4>(c, sm, Q, i0, n_valid, lane, m, so0, n_reads, n_bases); break;
+                case 3: scan_tile<3>(c, sm, Q, i0, n_valid, lane, m, so0, n_reads, n_bases); break;
+                default: scan_tile<8>(c, sm, Q, i0, n_valid, lane, m, so0, n_reads, n_bases); break;
+            }
+        } else if (valid) {
+            scan_read(c, sm, Q, i0 + lane, m, n_reads, n_bases);         // irregular tile: one read per lane
+        }
     }
 }
 
@@ -338,17 +440,21 @@ __device__ bool obs_equals_keep2(const SessCtx& c, const Smem2* sm, int a) {
 // Python slicing applies them (anonymizer_methods.py:186-195).  The read's germline observations hang on
 // mhead[k]; their slots ascend in CIGAR order (one thread allocated them), so sorting by slot restores it.
 // Returns the new length.
-__device__ int collect_edits(const SessCtx& c, const Smem2* sm, int k, int L, Edit* edits, int* n_edits, int* n_dels, bool* too_many) {
+__device__ __noinline__ int collect_edits(const SessCtx& c, const Smem2* sm, int k, int L, Edit* edits, int* n_edits, int* n_dels, bool* too_many) {
     int16_t slots[GA_MAX_EDITS];
     int ns = 0;
+#pragma unroll 1
     for (int o = sm->mhead[k]; o >= 0; o = sm->o_rnext[o]) {
         if (ns >= GA_MAX_EDITS) { *too_many = true; break; }
         int p = ns++;
+#pragma unroll 1
         while (p > 0 && slots[p - 1] > o) { slots[p] = slots[p - 1]; --p; }
         slots[p] = (int16_t)o;
     }
     int ne = 0;
+#pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
         for (int q = 0; q < ns; ++q) {
             const int o = slots[q];
             const uint32_t m = sm->o_meta[o];
@@ -360,11 +466,13 @@ __device__ int collect_edits(const SessCtx& c, const Smem2* sm, int k, int L, Ed
     }
     const int n_del = *n_dels;
     int cur = L;
+#pragma unroll 1
     for (int q = 0; q < n_del; ++q) {
         edits[q].p_eff = edits[q].irp < cur ? edits[q].irp : cur;
         edits[q].e_eff = edits[q].p_eff + edits[q].len;
         cur += edits[q].len;
     }
+#pragma unroll 1
     for (int q = n_del; q < ne; ++q) {
         const int p = edits[q].irp < cur ? edits[q].irp : cur;
         const int e = edits[q].irp + edits[q].len < cur ? edits[q].irp + edits[q].len : cur;
@@ -754,7 +862,8 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned lo
 __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                  int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
                                                                  ResultView O, unsigned int* __restrict__ ticket, int stop_after) {
-    // stop_after: profiling knob (GA_STOP_AFTER, 0 = run everything): sessions end after phase 1=A1 2=A2 3=R 4=M 5=L 6=B1 7=B2
+    // stop_after: profiling knob (GA_STOP_AFTER, 0 = run everything): low byte = sessions end after phase 1=A1 2=A2 3=R 4=M 5=L
+    // 6=B1 71/72=inside B2 7=B2; bit 8 switches the L2 bulk prefetch of the next session on
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem2* sm = reinterpret_cast<Smem2*>(smem_raw);
     __shared__ unsigned long long s_scan64[kThreads / 32 + 1];
@@ -789,12 +898,14 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         if (!c.d.big) {
             for (int k = tid; k < n_cols; k += kThreads) { sm->snv[k] = 0u; sm->ihead[k] = (int16_t)-1; }
             for (int k = tid; k < n_cw; k += kThreads) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
+            const uint32_t* gref = B.ref4 + ((c.d.col_begin + 8) >> 3);
+            for (int k = tid; k < (n_cols >> 3) + 8; k += kThreads) sm->sref[k] = __ldg(gref + k);   // + record padding, + funnel-shift lookahead
         }
         __syncthreads();                                              // every thread has read s_next_session
         if (tid == kThreads - 32) {                                   // next ticket, and its reads on their way into L2
             const int nx = (int)atomicAdd(ticket, 1u);
             s_next_session = nx;
-            if (nx < n_work) prefetch_session(B, descs[nx]);
+            if (nx < n_work && (stop_after & 0x100)) prefetch_session(B, descs[nx], !(stop_after & 0x200));   // knob bit 8: L2 prefetch of the next session (off by default: measured slower), bit 9: meta only
         }
         if (tid == 0) {
             s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_nx = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
@@ -808,20 +919,9 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
 
         // ---- phase A1: scan every read, queue what needs a closer look
         uint32_t n_reads = 0, n_bases = 0;
-        {
-            int i = tid;
-            ReadMeta m = {};
-            if (i < c.n_range) m = load_meta(c, i);
-            while (i < c.n_range) {                                   // the next read's meta is in flight while this one is compared
-                const int inext = i + kThreads;
-                ReadMeta mn = {};
-                if (inext < c.n_range) mn = load_meta(c, inext);
-                scan_read(c, sm, Q, i, m, n_reads, n_bases);
-                m = mn; i = inext;
-            }
-        }
+        phase_scan(c, sm, Q, n_reads, n_bases);
         __syncthreads();
-        if (stop_after == 1) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 1) { __syncthreads(); continue; }
         // ---- phase A2: dense discovery over the queues
         {
             const int nw = min((int)s_nwords, kWords2), ng = min((int)s_ngen, kGen2);
@@ -839,7 +939,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         const int n_obs = (int)s_nobs;
         const int n_ent = (int)s_nent;
 
-        if (stop_after == 2) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 2) { __syncthreads(); continue; }
         // ---- phase R: germline = seen in tumor AND normal, minus variant_to_keep (AM.py:546-547)
         {
             uint32_t keep_bit = 0u; int keep_col = -1;
@@ -879,7 +979,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         }
         __syncthreads();
 
-        if (stop_after == 3) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 3) { __syncthreads(); continue; }
         // ---- phase M: reads that carry a germline SNV allele
         for (int e = tid; e < n_ent; e += kThreads) {
             const uint32_t w = sm->ent[e];
@@ -890,7 +990,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         }
         __syncthreads();
 
-        if (stop_after == 4) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 4) { __syncthreads(); continue; }
         // ---- phase L: ordered list of the modified reads (n_cw <= 128 bitmap words, one per thread)
         uint32_t n_mod;
         {
@@ -921,7 +1021,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             __syncthreads();
         }
 
-        if (stop_after == 5) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 5) { __syncthreads(); continue; }
         // ---- phase B1: new length of every modified read; indel-masked reads need the edit analysis
         const int per = ((int)n_mod + kThreads - 1) / kThreads;
         const int k0 = min(tid * per, (int)n_mod), k1 = min(k0 + per, (int)n_mod);
@@ -973,7 +1073,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
                           (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
         if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
 
-        if (stop_after == 6) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 6) { __syncthreads(); continue; }
         // ---- phase B2: clean SNV-only records are plain copies, one 16-byte unit per thread and iteration
         // (their germline hits are patched in phase B3); every other record is written by one warp
         for (uint32_t idx = tid; idx < tot_seq; idx += kThreads) {
@@ -988,7 +1088,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             if (32 * u + 32 > L) { v.x &= tail_mask(L, 4 * u); v.y &= tail_mask(L, 4 * u + 1); v.z &= tail_mask(L, 4 * u + 2); v.w &= tail_mask(L, 4 * u + 3); }
             *reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (s_base[1] + idx)) = v;
         }
-        if (stop_after == 71) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 71) { __syncthreads(); continue; }
         uint32_t n_q = 0;
         for (int k = tid; k < (int)n_mod; k += kThreads) {            // record headers, coalesced
             const uint32_t m = msize[k];
@@ -997,7 +1097,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             write_record_meta(O, s_base[0] + k, s, read_of(c, (int)clist[k]), (int)(m & kLenMask), s_base[1] + mseq[k],
                               q ? (uint32_t)(s_base[2] + mqual[k]) : 0xffffffffu);
         }
-        if (stop_after == 72) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 72) { __syncthreads(); continue; }
         {   // records that are not plain copies: one group of kGroup lanes each
             const int nx = (int)s_nx, group = tid / kGroup, glane = tid % kGroup;
             for (int base = 0; base < nx; base += kThreads / kGroup) {
@@ -1030,7 +1130,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         if (lane == 0 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
         __syncthreads();                                              // the copies are in place
 
-        if (stop_after == 7) { __syncthreads(); continue; }
+        if ((stop_after & 0xff) == 7) { __syncthreads(); continue; }
         // ---- phase B3: SNV masking of the copied clean reads, one 4-bit XOR per germline hit (AM.py:170-176)
         for (int e = tid; e < n_ent; e += kThreads) {
             const uint32_t w = sm->ent[e];
