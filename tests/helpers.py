@@ -55,3 +55,31 @@ def check_session_against_golden(case, widx, expected, batch, result):
     got = [int(x) for x in result.sess_counts[0, :3]]
     assert got == expected["counts"][:3], (case["name"], widx, got, expected["counts"])
     assert int(result.sess_counts[0, 3]) == len(exp_reads), (case["name"], widx, "session read count")
+
+
+def load_pysam_stub():
+    """The duck-typed pysam stand-in (tests/ref_stub/pysam.py) as a module, without touching sys.modules['pysam']."""
+    import importlib.util
+    path = os.path.join(HERE, "ref_stub", "pysam.py")
+    spec = importlib.util.spec_from_file_location("ga_pysam_stub", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def iter_pileups_stub(stub, tumor_reads, normal_reads, contig, start, stop):
+    """Two pileups merged by reference_pos into (colT|None, colN|None) pairs - restatement of the reference's
+    pileup_io.iter_pileups (pileup_io.pyx:8-41) over the stub's emulated pileups."""
+    it_t = stub.emulate_pileup(tumor_reads, contig, start, stop)
+    it_n = stub.emulate_pileup(normal_reads, contig, start, stop)
+    ct, cn = next(it_t, None), next(it_n, None)
+    while ct is not None or cn is not None:
+        if cn is None or (ct is not None and ct.reference_pos < cn.reference_pos):
+            yield ct, None
+            ct = next(it_t, None)
+        elif ct is None or cn.reference_pos < ct.reference_pos:
+            yield None, cn
+            cn = next(it_n, None)
+        else:
+            yield ct, cn
+            ct, cn = next(it_t, None), next(it_n, None)
