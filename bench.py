@@ -252,6 +252,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - launches0
     kernel_ms = [x for x in eng.kernel_ms_history(min(args.steps, 32)) if x > 0]
+    emit_ms = [x for x in eng.emit_ms_history(min(args.steps, 32)) if x > 0]
     eng.check_device_status(dres)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     work = torch.tensor([session_reads, session_bases, launches], dtype=torch.int64, device=dev)
@@ -275,13 +276,18 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     k_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else float("nan")
-    ach = single / (k_ms * 1e-3) / 1e9
+    e_ms = sum(emit_ms) / len(emit_ms) if emit_ms else 0.0
+    # the algorithmic bytes cover the whole masking pass (scan/discover/resolve in session_kernel_v2, record bodies
+    # in emit_kernel), so the duration is the two kernels together
+    pass_ms = k_ms + e_ms
+    ach = single / (pass_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "kernel": "session_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms / args.steps),
+                "kernel": "session_kernel_v2 + emit_kernel (one masking pass)", "kernel_ms": pass_ms,
+                "session_kernel_ms": k_ms, "emit_kernel_ms": e_ms, "kernel_share_of_step": pass_ms / (ms / args.steps),
                 "algorithmic_bytes_per_launch": single, "bytes_per_session_read": single / max(1, session_reads),
-                "survey_8d_bytes_per_launch": survey, "survey_8d_achieved": survey / (k_ms * 1e-3) / 1e9,
-                "survey_8d_frac": survey / (k_ms * 1e-3) / 1e9 / peak}
+                "survey_8d_bytes_per_launch": survey, "survey_8d_achieved": survey / (pass_ms * 1e-3) / 1e9,
+                "survey_8d_frac": survey / (pass_ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the host entry (pinned host SoA in, host records out)
     e2e = None

@@ -11,7 +11,7 @@
 #include <algorithm>
 
 #include "ga_engine_internal.h"
-#include "ga_session_v2.cuh"
+#include "ga_emit_kernel.cuh"
 
 namespace ga {
 
@@ -162,7 +162,7 @@ int ga_engine_create(int device, ga_engine** out) {
     if (cudaSetDevice(device) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
     for (int l = 0; l < kLanes; ++l) {
         if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
-        for (int k = 0; k < kTimedRuns; ++k) { cudaEventCreate(&e->lanes[l].ev0[k]); cudaEventCreate(&e->lanes[l].ev1[k]); }
+        for (int k = 0; k < kTimedRuns; ++k) { cudaEventCreate(&e->lanes[l].ev0[k]); cudaEventCreate(&e->lanes[l].ev1[k]); cudaEventCreate(&e->lanes[l].ev2[k]); }
     }
     cudaFuncSetAttribute(ga::session_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::Smem2));
     cudaFuncSetAttribute(ga::session_kernel_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -179,7 +179,8 @@ void ga_engine_destroy(ga_engine* e) {
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = e->lanes[l];
         cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
-        for (int k = 0; k < kTimedRuns; ++k) { if (L.ev0[k]) cudaEventDestroy(L.ev0[k]); if (L.ev1[k]) cudaEventDestroy(L.ev1[k]); }
+        cudaFree(L.d_kind); cudaFree(L.d_germ); cudaFree(L.d_germ_n);
+        for (int k = 0; k < kTimedRuns; ++k) { if (L.ev0[k]) cudaEventDestroy(L.ev0[k]); if (L.ev1[k]) cudaEventDestroy(L.ev1[k]); if (L.ev2[k]) cudaEventDestroy(L.ev2[k]); }
     }
     delete e;
 }
@@ -225,6 +226,23 @@ static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
     return GA_OK;
 }
 
+static int ensure_emit_scratch(ga_engine* e, Lane& L, int64_t cap_records, int64_t n_sessions) {
+    if (cap_records > L.cap_kind) {
+        cudaFree(L.d_kind); L.d_kind = nullptr; L.cap_kind = 0;
+        const int64_t cap = cap_records + cap_records / 8 + 1024;
+        GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
+        L.cap_kind = cap;
+    }
+    if (n_sessions > L.cap_germ) {
+        cudaFree(L.d_germ); cudaFree(L.d_germ_n); L.d_germ = nullptr; L.d_germ_n = nullptr; L.cap_germ = 0;
+        const int64_t cap = n_sessions + n_sessions / 4 + 1024;
+        GA_CUDA(cudaMalloc(&L.d_germ, (size_t)cap * ga::kGermCap * sizeof(uint32_t)));
+        GA_CUDA(cudaMalloc(&L.d_germ_n, (size_t)cap * sizeof(uint32_t)));
+        L.cap_germ = cap;
+    }
+    return GA_OK;
+}
+
 static int ensure_big_scratch(ga_engine* e, Lane& L) {
     if (L.d_big_scratch) return GA_OK;
     const int64_t per = 4ll * e->big_cols_cap * 2 + 4ll * ((e->big_reads_cap + 31) / 32) + 20ll * e->big_obs_cap + 8ll * e->big_reads_cap;
@@ -246,6 +264,19 @@ int ga_kernel_ms_history(ga_engine* e, float* out, int n) {
         const int slot = (int)((L.runs - 1 - k) % kTimedRuns);
         float ms = -1.f;
         if (cudaEventSynchronize(L.ev1[slot]) != cudaSuccess || cudaEventElapsedTime(&ms, L.ev0[slot], L.ev1[slot]) != cudaSuccess) ms = -1.f;
+        out[k] = ms;
+    }
+    return have;
+}
+
+int ga_emit_ms_history(ga_engine* e, float* out, int n) {
+    if (!e || !out || n < 0) return 0;
+    Lane& L = e->lanes[0];
+    const int have = (int)std::min<int64_t>(std::min<int64_t>(L.runs, kTimedRuns), n);
+    for (int k = 0; k < have; ++k) {
+        const int slot = (int)((L.runs - 1 - k) % kTimedRuns);
+        float ms = -1.f;
+        if (cudaEventSynchronize(L.ev2[slot]) != cudaSuccess || cudaEventElapsedTime(&ms, L.ev1[slot], L.ev2[slot]) != cudaSuccess) ms = -1.f;
         out[k] = ms;
     }
     return have;
@@ -307,11 +338,16 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 4, S->n_sessions);
     const int tslot = (int)(L.runs % kTimedRuns);
     GA_CUDA(cudaEventRecord(L.ev0[tslot], st));
-    ga::session_kernel_v2<<<grid_small, ga::kThreads, sizeof(ga::Smem2), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, d_tickets, e->stop_after);
+    rc = ensure_emit_scratch(e, L, out->cap_records, S->n_sessions); if (rc) return rc;
+    ga::EmitScratch X; X.kind = L.d_kind; X.germ = L.d_germ; X.germ_n = L.d_germ_n;
+    GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
+    ga::session_kernel_v2<<<grid_small, ga::kThreads, sizeof(ga::Smem2), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, d_tickets, e->stop_after, X);
     GA_CUDA(cudaEventRecord(L.ev1[tslot], st));
     L.runs++;
     ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
-    e->launches += 2;
+    ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, X);
+    GA_CUDA(cudaEventRecord(L.ev2[tslot], st));
+    e->launches += 3;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

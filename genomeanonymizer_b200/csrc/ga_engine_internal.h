@@ -13,9 +13,11 @@ struct Lane {
     ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int64_t cap_sessions = 0;
     int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, then tickets (2 x u32)
     uint8_t* d_big_scratch = nullptr;
+    uint8_t* d_kind = nullptr; int64_t cap_kind = 0;           // hand-over to the emission kernel (ga::EmitScratch)
+    uint32_t* d_germ = nullptr; uint32_t* d_germ_n = nullptr; int64_t cap_germ = 0;
     // CUDA events around the session kernel of the most recent kTimedRuns runs (ring), recorded on the
     // launching stream so bench.py can read per-launch durations after its timed region without syncing inside it
-    cudaEvent_t ev0[32] = {}, ev1[32] = {};
+    cudaEvent_t ev0[32] = {}, ev1[32] = {}, ev2[32] = {};   // ev0..ev1: session kernel, ev1..ev2: fallback + emission kernels
     int64_t runs = 0;
 };
 constexpr int kTimedRuns = 32;

@@ -28,7 +28,22 @@ constexpr int kMod2 = 512;             // modified reads per session
 constexpr int kWords2 = 768;           // queued mismatching words per session
 constexpr int kGen2 = 1024;            // queued non-clean reads per session
 constexpr int kStageWords = 64;        // reads longer than 8*kStageWords bases send their session to the fallback kernel
+constexpr uint32_t kLen2 = (1u << 24) - 1;   // msize: length bits (flags above: kModFlag, kQualFlag, kSlowFlag)
+constexpr uint32_t kSlowFlag = 1u << 29;   // msize: indel-masked record with more than two edits (emitted in-kernel)
+constexpr int kGermCap = 32;           // germline SNV alleles per session handed to the emission kernel (more: emitted in-kernel)
 constexpr int kGroup = 8;              // lanes that cooperate on one non-trivial output record
+
+// Hand-over from the session kernel to the emission kernel (engine scratch, one per lane).
+// kind[k] of output record k: 0 = already written (or nothing to do), 1 = clean read, SNV-only: copy + patch,
+// 2 = other CIGAR, SNV-only: re-walk, 3 = indel-masked with <= 2 edits (their description sits in the first
+// 32 bytes of the record's out_qual slot until the emission kernel overwrites it with the qualities).
+struct EmitScratch {
+    uint8_t* kind;          // [cap_records]
+    uint32_t* germ;         // [n_sessions][kGermCap]  (column << 4) | base code, column relative to the session's col_begin
+    uint32_t* germ_n;       // [n_sessions]
+};
+struct EditAux { int32_t irp0, pos0; uint32_t len0; int32_t irp1, pos1; uint32_t len1; uint32_t ne, n_del; };   // len bit 31 = INS
+static_assert(sizeof(EditAux) == 32, "EditAux fills one 32-byte quality unit");
 
 struct Smem2 {
     uint32_t snv[kCols2];              // bit c: tumor saw base code c, bit 16+c: normal; after resolve: germline codes
@@ -682,6 +697,23 @@ struct Ed2 {
     int ne, n_del;
 };
 
+// Offsets clamped exactly as Python slicing applies them (anonymizer_methods.py:186-195); returns the new length.
+__device__ __forceinline__ int clamp_edits2(Ed2& E, int L) {
+    int cur = L;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q >= E.ne) { E.p[q] = 0x7fffffff; E.e[q] = 0x7fffffff; continue; }
+        if (q < E.n_del) {
+            E.p[q] = E.irp[q] < cur ? E.irp[q] : cur; E.e[q] = E.p[q] + E.len[q]; cur += E.len[q];
+        } else {
+            const int pp = E.irp[q] < cur ? E.irp[q] : cur;
+            const int ee = E.irp[q] + E.len[q] < cur ? E.irp[q] + E.len[q] : cur;
+            E.p[q] = pp; E.e[q] = ee > pp ? ee : pp; cur -= (E.e[q] - pp);
+        }
+    }
+    return cur;
+}
+
 // Germline indel edits of modified read k when there are at most two; false otherwise.  Same ordering and
 // clamping rules as collect_edits.
 __device__ __forceinline__ bool collect2(const SessCtx& c, const Smem2* sm, int k, int L, Ed2& E, int* new_len) {
@@ -703,18 +735,7 @@ __device__ __forceinline__ bool collect2(const SessCtx& c, const Smem2* sm, int 
         E.pos[q] = has ? sm->o_col[o[q]] + c.d.col_begin : 0; E.mean[q] = 0u;
         if (has && !(m & kMetaIns)) ++E.n_del;
     }
-    int cur = L;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        if (q >= E.ne) { E.p[q] = 0x7fffffff; E.e[q] = 0x7fffffff; continue; }
-        if (q < E.n_del) {
-            E.p[q] = E.irp[q] < cur ? E.irp[q] : cur; E.e[q] = E.p[q] + E.len[q]; cur += E.len[q];
-        } else {
-            const int pp = E.irp[q] < cur ? E.irp[q] : cur;
-            const int ee = E.irp[q] + E.len[q] < cur ? E.irp[q] + E.len[q] : cur;
-            E.p[q] = pp; E.e[q] = ee > pp ? ee : pp; cur -= (E.e[q] - pp);
-        }
-    }
+    const int cur = clamp_edits2(E, L);
     *new_len = cur;
     return true;
 }
@@ -733,26 +754,87 @@ __device__ __forceinline__ int map_back2(const Ed2& E, int j, int* kin) {
     return j;
 }
 
+// SNV-masked words of a read, context-free form shared by the session kernel and the emission kernel:
+// germ(column relative to col_begin, base code) says whether the allele is germline.
+template <class Germ, class Store>
+__device__ __forceinline__ void masked_words_g(const BatchView& B, int64_t r, int pos, int L, uint32_t c0, uint32_t c1, int col_begin,
+                                               int n_words, int lane, int stride, Germ&& germ, Store&& store) {
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * __ldg(B.seq_off16 + r));
+    for (int w = lane; w < n_words; w += stride) {
+        const int qb = w << 3;
+        uint32_t v = qb < L ? (__ldg(rec + w) & tail_mask(L, w)) : 0u;
+        if (qb < L) {
+            int rc = pos, q = 0;
+            for (uint32_t ci = c0; ci < c1; ++ci) {
+                const uint32_t cw = __ldg(B.cigar + ci), op = cw & 15u;
+                const int ln = (int)(cw >> 4);
+                if (op == 0u || op == 7u || op == 8u) {
+                    const int lo = max(q, qb), hi = min(min(q + ln, qb + 8), L);
+                    if (lo < hi) {
+                        const int p0 = rc - q + qb;                       // reference position of query base qb under this segment
+                        const uint32_t fw = ref_word(B.ref4, (int64_t)p0);
+                        uint32_t mask = 0xffffffffu;
+                        if (lo > qb) mask &= 0xffffffffu << ((lo - qb) * 4);
+                        if (hi < qb + 8) mask &= 0xffffffffu >> ((qb + 8 - hi) * 4);
+                        uint32_t x = (v ^ fw) & mask;
+                        while (x) {
+                            const int n = (__ffs(x) - 1) >> 2;
+                            x &= ~(0xfu << (n * 4));
+                            const uint32_t b = (v >> (n * 4)) & 15u;
+                            if (b != 15u && germ(p0 + n - col_begin, b))
+                                v = (v & ~(0xfu << (n * 4))) | (((fw >> (n * 4)) & 15u) << (n * 4));
+                        }
+                    }
+                    q += ln; rc += ln;
+                } else if (op == 1u || op == 4u) q += ln;
+                else if (op == 2u || op == 3u) rc += ln;
+                if (q >= qb + 8) break;
+            }
+        }
+        store(w, v);
+    }
+}
+
+template <class Germ>
+__device__ __forceinline__ uint32_t masked_base_g(const BatchView& B, const uint32_t* rec, uint32_t c0, uint32_t c1, int pos, int col_begin, int j, Germ&& germ) {
+    const uint32_t b = read_code(rec, j);
+    if (b == 15u) return b;
+    int rc = pos, q = 0;
+    for (uint32_t ci = c0; ci < c1; ++ci) {
+        const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
+        const int ln = (int)(w >> 4);
+        if (op == 0u || op == 7u || op == 8u) {
+            if (j < q + ln) {
+                const int rp = rc + (j - q);
+                return germ(rp - col_begin, b) ? ref_code(B.ref4, rp) : b;
+            }
+            q += ln; rc += ln;
+        } else if (op == 1u || op == 4u) { if (j < q + ln) return b; q += ln; }
+        else if (op == 2u || op == 3u) rc += ln;
+    }
+    return b;
+}
+
 // Indel-masked records with at most two edits, one per group of kGroup lanes (see emit_indel_group_slow for the
 // general form and the references).  A word whose bases (qualities) come from consecutive source positions is one
 // funnel shift of two staged words; words that straddle an edit are assembled element by element.
-__device__ void emit_indel_group(const SessCtx& c, Smem2* sm, const ResultView& O, bool act, const Ed2& E, int i, uint64_t seq16, uint64_t qual16,
-                                 int new_len, int glane, int group) {
-    const int64_t r = act ? read_of(c, i) : 0;
+// Context-free: used by the session kernel (in-kernel emission) and by the emission kernel.
+template <class Germ>
+__device__ void emit_indel_group_t(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r, int col_begin,
+                                   int64_t q_lo, int64_t q_hi, uint32_t* stage, uint64_t seq16, uint64_t qual16, int new_len, int glane, Germ&& germ) {
     uint32_t lf = 0u, c0 = 0u, c1 = 0u; int pos = 0;
-    if (act) { lf = __ldg(c.B.len_flag + r); c0 = __ldg(c.B.cigar_off + r); c1 = __ldg(c.B.cigar_off + r + 1); pos = __ldg(c.B.pos + r); }
+    if (act) { lf = __ldg(B.len_flag + r); c0 = __ldg(B.cigar_off + r); c1 = __ldg(B.cigar_off + r + 1); pos = __ldg(B.pos + r); }
     const int L = (int)(lf & 0xffffu);
     const uint8_t* qrec = nullptr;
     if (act) {
-        qrec = qual_record_in(c.B, r, i < c.nt ? c.d.qt_begin : c.d.qn_begin, i < c.nt ? c.d.qt_end : c.d.qn_end);
-        if (!qrec) { if (glane == 0) raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
+        qrec = qual_record_in(B, r, q_lo, q_hi);
+        if (!qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
     }
     const bool reverse = ((lf >> 16) & 0x10u) != 0u;
-    const uint32_t* rec = act ? rec_of(c, r) : nullptr;
-    uint32_t* stage = sm->o_sig0 + group * kGroupStage;              // o_sig0/o_sig1 are dead after phase R
+    const uint32_t* rec = act ? reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * __ldg(B.seq_off16 + r)) : nullptr;
     const bool staged = act && ((L + 7) >> 3) <= kGroupStage - 1;
     if (staged) {
-        masked_words(c, sm, r, pos, L, c0, c1, (L + 7) >> 3, glane, kGroup, [&](int w, uint32_t v) { stage[w] = v; });
+        masked_words_g(B, r, pos, L, c0, c1, col_begin, (L + 7) >> 3, glane, kGroup, germ, [&](int w, uint32_t v) { stage[w] = v; });
         if (glane == 0) stage[(L + 7) >> 3] = 0u;
     }
     uint32_t mean0 = 0u, mean1 = 0u;
@@ -773,7 +855,7 @@ __device__ void emit_indel_group(const SessCtx& c, Smem2* sm, const ResultView& 
         if (act && glane == 0) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
-                if (q < E.n_del && (int64_t)E.pos[q] + E.len[q] > c.B.ref_len) raise_error(c.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
+                if (q < E.n_del && (int64_t)E.pos[q] + E.len[q] > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
         }
     }
     __syncwarp();                                                     // staged words visible to the group
@@ -794,9 +876,9 @@ __device__ void emit_indel_group(const SessCtx& c, Smem2* sm, const ResultView& 
                 for (int n = 0; n <= jl - j0; ++n) {
                     const int src = map_back2(E, j0 + n, &kin);
                     uint32_t code;
-                    if (src < 0) code = ref_code(c.B.ref4, (int64_t)(src == -1 ? E.pos[0] : E.pos[1]) + kin);
+                    if (src < 0) code = ref_code(B.ref4, (int64_t)(src == -1 ? E.pos[0] : E.pos[1]) + kin);
                     else if (staged) code = (stage[src >> 3] >> ((src & 7) * 4)) & 15u;
-                    else code = masked_base2(c, sm, rec, c0, c1, pos, src);
+                    else code = masked_base_g(B, rec, c0, c1, pos, col_begin, src, germ);
                     v |= code << (n * 4);
                 }
             }
@@ -831,6 +913,15 @@ __device__ void emit_indel_group(const SessCtx& c, Smem2* sm, const ResultView& 
     }
 }
 
+// In-kernel form: the germline test is the session's shared-memory table.
+__device__ void emit_indel_group(const SessCtx& c, Smem2* sm, const ResultView& O, bool act, const Ed2& E, int i, uint64_t seq16, uint64_t qual16,
+                                 int new_len, int glane, int group) {
+    const int64_t r = act ? read_of(c, i) : 0;
+    emit_indel_group_t(c.B, c.totals, O, act, E, r, c.d.col_begin, i < c.nt ? c.d.qt_begin : c.d.qn_begin, i < c.nt ? c.d.qt_end : c.d.qn_end,
+                       sm->o_sig0 + group * kGroupStage, seq16, qual16, new_len, glane,
+                       [&](int col, uint32_t b) { return ((sm->snv[col] >> b) & 1u) != 0u; });
+}
+
 // Block-wide exclusive scan of a 64-bit value per thread.
 __device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned long long v, unsigned long long* tmp, unsigned long long* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -861,14 +952,14 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned lo
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                  int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
-                                                                 ResultView O, unsigned int* __restrict__ ticket, int stop_after) {
+                                                                 ResultView O, unsigned int* __restrict__ ticket, int stop_after, EmitScratch X) {
     // stop_after: profiling knob (GA_STOP_AFTER, 0 = run everything): low byte = sessions end after phase 1=A1 2=A2 3=R 4=M 5=L
     // 6=B1 71/72=inside B2 7=B2; bit 8 switches the L2 bulk prefetch of the next session on
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem2* sm = reinterpret_cast<Smem2*>(smem_raw);
     __shared__ unsigned long long s_scan64[kThreads / 32 + 1];
     __shared__ uint32_t s_scan[kThreads / 32 + 1];
-    __shared__ uint32_t s_nobs, s_nent, s_nwords, s_ngen, s_nx, s_reads, s_bases, s_cnt[3], s_overflow;
+    __shared__ uint32_t s_nobs, s_nent, s_nwords, s_ngen, s_nx, s_ngerm, s_reads, s_bases, s_cnt[3], s_overflow;
     __shared__ int s_next_session;
     __shared__ unsigned long long s_base[3];
 
@@ -908,7 +999,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             if (nx < n_work && (stop_after & 0x100)) prefetch_session(B, descs[nx], !(stop_after & 0x200));   // knob bit 8: L2 prefetch of the next session (off by default: measured slower), bit 9: meta only
         }
         if (tid == 0) {
-            s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_nx = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
+            s_nobs = 0; s_nent = 0; s_nwords = 0; s_ngen = 0; s_nx = 0; s_ngerm = 0; s_reads = 0; s_bases = 0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_overflow = 0;
         }
         if (c.d.big) { __syncthreads(); continue; }
         c.first = S.first[s];
@@ -955,6 +1046,11 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
                 if (k == keep_col) g &= ~keep_bit;
                 sm->snv[k] = g;
                 cnt += __popc(g);
+                while (g) {                                           // hand the allele to the emission kernel
+                    const uint32_t code = (uint32_t)(__ffs(g) - 1); g &= g - 1;
+                    const uint32_t e = atomicAdd(&s_ngerm, 1u);
+                    if (e < (uint32_t)kGermCap) X.germ[(size_t)s * kGermCap + e] = ((uint32_t)k << 4) | code;
+                }
             }
             cnt = warp_sum(cnt);
             if (lane == 0 && cnt) atomicAdd(&s_cnt[0], cnt);
@@ -1022,7 +1118,10 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         }
 
         if ((stop_after & 0xff) == 5) { __syncthreads(); continue; }
-        // ---- phase B1: new length of every modified read; indel-masked reads need the edit analysis
+        // ---- phase B1: new length of every modified read; indel-masked reads need the edit analysis.  Records are
+        // written by the emission kernel unless the session has more germline alleles than the hand-over holds
+        // (then everything is emitted here) or the record has more than two edits.
+        const bool inline_emit = s_ngerm > (uint32_t)kGermCap;
         const int per = ((int)n_mod + kThreads - 1) / kThreads;
         const int k0 = min(tid * per, (int)n_mod), k1 = min(k0 + per, (int)n_mod);
         unsigned long long mine = 0ull;                               // [records:16 | seq units:24 | qual units:24]
@@ -1030,18 +1129,21 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             const int i = (int)clist[k];
             const int64_t r = read_of(c, i);
             uint32_t m;
+            bool slow = false;
             if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
                 const int L0 = (int)(__ldg(c.B.len_flag + r) & 0xffffu);
                 Ed2 E2;
                 int new_len = L0;
-                if (!collect2(c, sm, k, L0, E2, &new_len)) new_len = new_len_slow(c, sm, O, k, L0, r);
-                m = kModFlag | kQualFlag | ((uint32_t)new_len & kLenMask);
+                if (!collect2(c, sm, k, L0, E2, &new_len)) { new_len = new_len_slow(c, sm, O, k, L0, r); slow = true; }
+                m = kModFlag | kQualFlag | ((uint32_t)new_len & kLen2);
             } else {
                 m = kModFlag | (__ldg(c.B.len_flag + r) & 0xffffu);
             }
+            if (slow) m |= kSlowFlag;
             msize[k] = m;
-            if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u)) sm->glist[atomicAdd(&s_nx, 1u)] = (uint16_t)k;
-            uint32_t units = ((m & kLenMask) + 31u) / 32u; if (units < 1u) units = 1u;
+            const bool special = (m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u);
+            if (inline_emit ? special : slow) sm->glist[atomicAdd(&s_nx, 1u)] = (uint16_t)k;
+            uint32_t units = ((m & kLen2) + 31u) / 32u; if (units < 1u) units = 1u;
             mine += (1ull << 48) | ((unsigned long long)units << 24) | ((m & kQualFlag) ? (unsigned long long)units : 0ull);
         }
         unsigned long long total;
@@ -1063,7 +1165,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
             uint32_t so = (uint32_t)((off >> 24) & 0xffffffu), qo = (uint32_t)(off & 0xffffffu);
             for (int k = k0; k < k1; ++k) {
                 const uint32_t m = msize[k];
-                uint32_t units = ((m & kLenMask) + 31u) / 32u; if (units < 1u) units = 1u;
+                uint32_t units = ((m & kLen2) + 31u) / 32u; if (units < 1u) units = 1u;
                 mseq[k] = so; mqual[k] = qo;
                 so += units; if (m & kQualFlag) qo += units;
             }
@@ -1074,28 +1176,47 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
 
         if ((stop_after & 0xff) == 6) { __syncthreads(); continue; }
-        // ---- phase B2: clean SNV-only records are plain copies, one 16-byte unit per thread and iteration
-        // (their germline hits are patched in phase B3); every other record is written by one warp
-        for (uint32_t idx = tid; idx < tot_seq; idx += kThreads) {
-            int lo = 0, hi = (int)n_mod;                              // last record with mseq[k] <= idx
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (mseq[mid] <= idx) lo = mid; else hi = mid; }
-            const uint32_t m = msize[lo];
-            const int i = (int)clist[lo];
-            if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u)) continue;
-            const int u = (int)(idx - mseq[lo]), L = (int)(m & kLenMask);
-            const int64_t r = read_of(c, i);
-            uint4 v = ldg128(reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * __ldg(c.B.seq_off16 + r)) + u);
-            if (32 * u + 32 > L) { v.x &= tail_mask(L, 4 * u); v.y &= tail_mask(L, 4 * u + 1); v.z &= tail_mask(L, 4 * u + 2); v.w &= tail_mask(L, 4 * u + 3); }
-            *reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (s_base[1] + idx)) = v;
+        // ---- phase B2: record headers and the hand-over to the emission kernel; in-kernel emission only for what the
+        // hand-over cannot describe
+        if (inline_emit) {
+            // clean SNV-only records are plain copies, one 16-byte unit per thread and iteration (hits patched in B3)
+            for (uint32_t idx = tid; idx < tot_seq; idx += kThreads) {
+                int lo = 0, hi = (int)n_mod;                          // last record with mseq[k] <= idx
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (mseq[mid] <= idx) lo = mid; else hi = mid; }
+                const uint32_t m = msize[lo];
+                const int i = (int)clist[lo];
+                if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u)) continue;
+                const int u = (int)(idx - mseq[lo]), L = (int)(m & kLen2);
+                const int64_t r = read_of(c, i);
+                uint4 v = ldg128(reinterpret_cast<const uint4*>(c.B.seq4 + 16ull * __ldg(c.B.seq_off16 + r)) + u);
+                if (32 * u + 32 > L) { v.x &= tail_mask(L, 4 * u); v.y &= tail_mask(L, 4 * u + 1); v.z &= tail_mask(L, 4 * u + 2); v.w &= tail_mask(L, 4 * u + 3); }
+                *reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (s_base[1] + idx)) = v;
+            }
         }
         if ((stop_after & 0xff) == 71) { __syncthreads(); continue; }
         uint32_t n_q = 0;
+        if (tid == 0) X.germ_n[s] = inline_emit ? 0u : s_ngerm;
         for (int k = tid; k < (int)n_mod; k += kThreads) {            // record headers, coalesced
             const uint32_t m = msize[k];
             const bool q = (m & kQualFlag) != 0u;
+            const int i = (int)clist[k];
             n_q += q ? 1u : 0u;
-            write_record_meta(O, s_base[0] + k, s, read_of(c, (int)clist[k]), (int)(m & kLenMask), s_base[1] + mseq[k],
-                              q ? (uint32_t)(s_base[2] + mqual[k]) : 0xffffffffu);
+            const uint32_t qual16 = q ? (uint32_t)(s_base[2] + mqual[k]) : 0xffffffffu;
+            write_record_meta(O, s_base[0] + k, s, read_of(c, i), (int)(m & kLen2), s_base[1] + mseq[k], qual16);
+            uint8_t kind = 0;
+            if (!inline_emit && !(m & kSlowFlag)) kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : 1);
+            X.kind[s_base[0] + k] = kind;
+            if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
+                Ed2 E2; int nl = 0;
+                collect2(c, sm, k, (int)(__ldg(c.B.len_flag + read_of(c, i)) & 0xffffu), E2, &nl);
+                EditAux a;
+                a.irp0 = E2.irp[0]; a.pos0 = E2.pos[0]; a.len0 = (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u);
+                a.irp1 = E2.irp[1]; a.pos1 = E2.pos[1]; a.len1 = (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u);
+                a.ne = (uint32_t)E2.ne; a.n_del = (uint32_t)E2.n_del;
+                uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
+                const uint4* src = reinterpret_cast<const uint4*>(&a);
+                dst[0] = src[0]; dst[1] = src[1];
+            }
         }
         if ((stop_after & 0xff) == 72) { __syncthreads(); continue; }
         {   // records that are not plain copies: one group of kGroup lanes each
@@ -1106,7 +1227,7 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
                 const int k = have ? (int)sm->glist[xi] : 0;
                 const uint32_t m = have ? msize[k] : 0u;
                 const int i = have ? (int)clist[k] : 0;
-                const int L = (int)(m & kLenMask);
+                const int L = (int)(m & kLen2);
                 const uint64_t seq16 = s_base[1] + (have ? mseq[k] : 0u);
                 const bool indel = have && (m & kQualFlag);
                 if (__any_sync(0xffffffffu, indel)) {
@@ -1131,7 +1252,8 @@ __global__ void __launch_bounds__(kThreads, 4) session_kernel_v2(BatchView B, Se
         __syncthreads();                                              // the copies are in place
 
         if ((stop_after & 0xff) == 7) { __syncthreads(); continue; }
-        // ---- phase B3: SNV masking of the copied clean reads, one 4-bit XOR per germline hit (AM.py:170-176)
+        // ---- phase B3 (in-kernel emission only): SNV masking of the copied clean reads, one 4-bit XOR per germline hit
+        if (inline_emit)
         for (int e = tid; e < n_ent; e += kThreads) {
             const uint32_t w = sm->ent[e];
             const uint32_t col = (w >> 4) & 0xfffu, b = w & 15u, i = w >> 16;

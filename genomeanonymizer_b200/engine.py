@@ -158,6 +158,11 @@ class Engine:
         k = int(self._L.ga_kernel_ms_history(self._h, buf, n))
         return [float(buf[i]) for i in range(k)]
 
+    def emit_ms_history(self, n: int = 32):
+        buf = (C.c_float * n)()
+        k = int(self._L.ga_emit_ms_history(self._h, buf, n))
+        return [float(buf[i]) for i in range(k)]
+
     def upload_reference(self, contig_id: int, bases) -> None:
         """bases: str / bytes (host) or a uint8 CUDA tensor of ASCII codes."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
