@@ -252,7 +252,10 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - launches0
     kernel_ms = [x for x in eng.kernel_ms_history(min(args.steps, 32)) if x > 0]
-    emit_ms = [x for x in eng.emit_ms_history(min(args.steps, 32)) if x > 0]
+    stage_ms = []
+    for st in range(4):
+        h = [x for x in eng.stage_ms_history(st, min(args.steps, 32)) if x >= 0]
+        stage_ms.append(sum(h) / len(h) if h else float("nan"))
     eng.check_device_status(dres)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     work = torch.tensor([session_reads, session_bases, launches], dtype=torch.int64, device=dev)
@@ -275,16 +278,18 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else float("nan")
-    e_ms = sum(emit_ms) / len(emit_ms) if emit_ms else 0.0
-    # the algorithmic bytes cover the whole masking pass (scan/discover/resolve in session_kernel_v2, record bodies
-    # in emit_kernel), so the duration is the two kernels together
-    pass_ms = k_ms + e_ms
+    # the algorithmic bytes cover the whole masking pass (scan -> resolve -> [fallback] -> emission kernels, back to
+    # back on one stream), so the duration is that of the pass; the per-kernel durations are listed beside it
+    pass_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else float("nan")
     ach = single / (pass_ms * 1e-3) / 1e9
+    scan_bytes = single - (int(tot.n_modified) * 20 + 2 * 16 * int(tot.seq16_used) + 2 * 32 * int(tot.qual16_used))
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "kernel": "session_kernel_v2 + emit_kernel (one masking pass)", "kernel_ms": pass_ms,
-                "session_kernel_ms": k_ms, "emit_kernel_ms": e_ms, "kernel_share_of_step": pass_ms / (ms / args.steps),
+                "kernel": "masking pass = scan_kernel + resolve_kernel + session_kernel<fallback> + emit_kernel", "kernel_ms": pass_ms,
+                "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernel": stage_ms[1], "fallback_kernel": stage_ms[2],
+                             "emit_kernel": stage_ms[3]},
+                "scan_kernel_gbs": scan_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else None,
+                "kernel_share_of_step": pass_ms / (ms / args.steps),
                 "algorithmic_bytes_per_launch": single, "bytes_per_session_read": single / max(1, session_reads),
                 "survey_8d_bytes_per_launch": survey, "survey_8d_achieved": survey / (pass_ms * 1e-3) / 1e9,
                 "survey_8d_frac": survey / (pass_ms * 1e-3) / 1e9 / peak}

@@ -158,14 +158,15 @@ int ga_engine_create(int device, ga_engine** out) {
     ga_engine* e = new ga_engine();
     e->device = device;
     e->n_sm = prop.multiProcessorCount;
-    if (const char* sa = getenv("GA_STOP_AFTER")) e->stop_after = atoi(sa);   // profiling knob, see session_kernel_v2
     if (cudaSetDevice(device) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
     for (int l = 0; l < kLanes; ++l) {
         if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
-        for (int k = 0; k < kTimedRuns; ++k) { cudaEventCreate(&e->lanes[l].ev0[k]); cudaEventCreate(&e->lanes[l].ev1[k]); cudaEventCreate(&e->lanes[l].ev2[k]); }
+        for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) cudaEventCreate(&e->lanes[l].ev[j][k]);
     }
-    cudaFuncSetAttribute(ga::session_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::Smem2));
-    cudaFuncSetAttribute(ga::session_kernel_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::WarpSmem) * (ga::kScanThreads / 32)));
+    cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemR));
+    cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = e;
     return GA_OK;
 }
@@ -179,8 +180,8 @@ void ga_engine_destroy(ga_engine* e) {
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = e->lanes[l];
         cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
-        cudaFree(L.d_kind); cudaFree(L.d_germ); cudaFree(L.d_germ_n);
-        for (int k = 0; k < kTimedRuns; ++k) { if (L.ev0[k]) cudaEventDestroy(L.ev0[k]); if (L.ev1[k]) cudaEventDestroy(L.ev1[k]); if (L.ev2[k]) cudaEventDestroy(L.ev2[k]); }
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
+        for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) if (L.ev[j][k]) cudaEventDestroy(L.ev[j][k]);
     }
     delete e;
 }
@@ -226,19 +227,27 @@ static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
     return GA_OK;
 }
 
-static int ensure_emit_scratch(ga_engine* e, Lane& L, int64_t cap_records, int64_t n_sessions) {
+static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int64_t n_sessions) {
     if (cap_records > L.cap_kind) {
-        cudaFree(L.d_kind); L.d_kind = nullptr; L.cap_kind = 0;
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); L.d_kind = nullptr; L.d_edesc = nullptr; L.cap_kind = 0;
         const int64_t cap = cap_records + cap_records / 8 + 1024;
         GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
+        GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
         L.cap_kind = cap;
     }
     if (n_sessions > L.cap_germ) {
-        cudaFree(L.d_germ); cudaFree(L.d_germ_n); L.d_germ = nullptr; L.d_germ_n = nullptr; L.cap_germ = 0;
+        cudaFree(L.d_germ); L.d_germ = nullptr; L.cap_germ = 0;
         const int64_t cap = n_sessions + n_sessions / 4 + 1024;
-        GA_CUDA(cudaMalloc(&L.d_germ, (size_t)cap * ga::kGermCap * sizeof(uint32_t)));
-        GA_CUDA(cudaMalloc(&L.d_germ_n, (size_t)cap * sizeof(uint32_t)));
+        GA_CUDA(cudaMalloc(&L.d_germ, (size_t)cap * ga::kGermStride * sizeof(uint32_t)));
         L.cap_germ = cap;
+    }
+    if (2 * n_sessions > L.cap_items) {
+        cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt); L.d_ent = nullptr; L.d_obs = nullptr; L.d_cnt = nullptr; L.cap_items = 0;
+        const int64_t cap = 2 * (n_sessions + n_sessions / 4 + 1024);
+        GA_CUDA(cudaMalloc(&L.d_ent, (size_t)cap * ga::kEntHalf * sizeof(uint32_t)));
+        GA_CUDA(cudaMalloc(&L.d_obs, (size_t)cap * ga::kObsHalf * sizeof(ga::ObsRec)));
+        GA_CUDA(cudaMalloc(&L.d_cnt, (size_t)cap * sizeof(uint4)));
+        L.cap_items = cap;
     }
     return GA_OK;
 }
@@ -256,30 +265,25 @@ int ga_run(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result* out
     return ga_run_lane(e, 0, R, S, out, (cudaStream_t)stream_);
 }
 
-int ga_kernel_ms_history(ga_engine* e, float* out, int n) {
-    if (!e || !out || n < 0) return 0;
-    Lane& L = e->lanes[0];
-    const int have = (int)std::min<int64_t>(std::min<int64_t>(L.runs, kTimedRuns), n);
-    for (int k = 0; k < have; ++k) {                       // out[0] = most recent run
-        const int slot = (int)((L.runs - 1 - k) % kTimedRuns);
-        float ms = -1.f;
-        if (cudaEventSynchronize(L.ev1[slot]) != cudaSuccess || cudaEventElapsedTime(&ms, L.ev0[slot], L.ev1[slot]) != cudaSuccess) ms = -1.f;
-        out[k] = ms;
-    }
-    return have;
-}
-
-int ga_emit_ms_history(ga_engine* e, float* out, int n) {
+// Duration (ms) between events ev[a] and ev[b] of the most recent runs, out[0] = latest.
+static int stage_history(ga_engine* e, int a, int b, float* out, int n) {
     if (!e || !out || n < 0) return 0;
     Lane& L = e->lanes[0];
     const int have = (int)std::min<int64_t>(std::min<int64_t>(L.runs, kTimedRuns), n);
     for (int k = 0; k < have; ++k) {
         const int slot = (int)((L.runs - 1 - k) % kTimedRuns);
         float ms = -1.f;
-        if (cudaEventSynchronize(L.ev2[slot]) != cudaSuccess || cudaEventElapsedTime(&ms, L.ev1[slot], L.ev2[slot]) != cudaSuccess) ms = -1.f;
+        if (cudaEventSynchronize(L.ev[b][slot]) != cudaSuccess || cudaEventElapsedTime(&ms, L.ev[a][slot], L.ev[b][slot]) != cudaSuccess) ms = -1.f;
         out[k] = ms;
     }
     return have;
+}
+
+int ga_kernel_ms_history(ga_engine* e, float* out, int n) { return stage_history(e, 0, 4, out, n); }
+
+int ga_stage_ms_history(ga_engine* e, int stage, float* out, int n) {
+    if (stage < 0 || stage > 3) return 0;
+    return stage_history(e, stage, stage + 1, out, n);
 }
 
 float ga_last_kernel_ms(ga_engine* e) {
@@ -335,19 +339,29 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     ga::BigScratch scr;
     scr.base = L.d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
     scr.cols_cap = e->big_cols_cap; scr.reads_cap = e->big_reads_cap; scr.obs_cap = e->big_obs_cap;
-    const int grid_small = (int)std::min<int64_t>((int64_t)e->n_sm * 4, S->n_sessions);
-    const int tslot = (int)(L.runs % kTimedRuns);
-    GA_CUDA(cudaEventRecord(L.ev0[tslot], st));
-    rc = ensure_emit_scratch(e, L, out->cap_records, S->n_sessions); if (rc) return rc;
-    ga::EmitScratch X; X.kind = L.d_kind; X.germ = L.d_germ; X.germ_n = L.d_germ_n;
+    rc = ensure_stream_scratch(e, L, out->cap_records, S->n_sessions); if (rc) return rc;
+    ga::ScanScratch X; X.ent = L.d_ent; X.obs = reinterpret_cast<ga::ObsRec*>(L.d_obs); X.cnt = reinterpret_cast<uint4*>(L.d_cnt);
+    ga::EmitScratch2 E; E.kind = L.d_kind; E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
-    ga::session_kernel_v2<<<grid_small, ga::kThreads, sizeof(ga::Smem2), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, d_tickets, e->stop_after, X);
-    GA_CUDA(cudaEventRecord(L.ev1[tslot], st));
+    const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;
+    // stage 1: allele discovery, one warp per (session, dataset) item, persistent CTAs
+    const int64_t n_items = 2 * (int64_t)S->n_sessions;
+    const int grid_scan = (int)std::min<int64_t>((int64_t)e->n_sm * 4, (n_items + ga::kScanThreads / 32 - 1) / (ga::kScanThreads / 32));
+    GA_CUDA(cudaEventRecord(L.ev[0][tslot], st));
+    ga::scan_kernel<<<grid_scan, ga::kScanThreads, sizeof(ga::WarpSmem) * (ga::kScanThreads / 32), st>>>(B, V, L.d_descs, X, d_tickets, out->totals);
+    GA_CUDA(cudaEventRecord(L.ev[1][tslot], st));
+    // stage 2: germline set, modified-record list, output slots, headers
+    const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * 7, S->n_sessions);
+    ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, X, E);
+    GA_CUDA(cudaEventRecord(L.ev[2][tslot], st));
+    // oversize sessions and whatever the tables of stages 1-2 could not hold: global-scratch kernel, complete records
     ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
-    ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, X);
-    GA_CUDA(cudaEventRecord(L.ev2[tslot], st));
-    e->launches += 3;
+    GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
+    // stage 3: record bodies
+    ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
+    GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
+    e->launches += 4;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

@@ -13,11 +13,14 @@ struct Lane {
     ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int64_t cap_sessions = 0;
     int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, then tickets (2 x u32)
     uint8_t* d_big_scratch = nullptr;
-    uint8_t* d_kind = nullptr; int64_t cap_kind = 0;           // hand-over to the emission kernel (ga::EmitScratch)
-    uint32_t* d_germ = nullptr; uint32_t* d_germ_n = nullptr; int64_t cap_germ = 0;
-    // CUDA events around the session kernel of the most recent kTimedRuns runs (ring), recorded on the
-    // launching stream so bench.py can read per-launch durations after its timed region without syncing inside it
-    cudaEvent_t ev0[32] = {}, ev1[32] = {}, ev2[32] = {};   // ev0..ev1: session kernel, ev1..ev2: fallback + emission kernels
+    // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)
+    uint32_t* d_ent = nullptr; void* d_obs = nullptr; void* d_cnt = nullptr; int64_t cap_items = 0;
+    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; int64_t cap_kind = 0;
+    uint32_t* d_germ = nullptr; int64_t cap_germ = 0;
+    // CUDA events between the stages of the most recent kTimedRuns runs (ring), recorded on the launching stream so
+    // bench.py can read per-launch durations after its timed region without syncing inside it:
+    // ev[0] start | scan | ev[1] | resolve | ev[2] | fallback | ev[3] | emission | ev[4]
+    cudaEvent_t ev[5][32] = {};
     int64_t runs = 0;
 };
 constexpr int kTimedRuns = 32;
@@ -35,7 +38,6 @@ struct ga_engine {
     int64_t big_bytes_per_cta = 0; int big_ctas = 0;
     int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
     int64_t launches = 0;
-    int stop_after = 0;                  // GA_STOP_AFTER profiling knob (0 = full pipeline)
     HostSlot* slots = nullptr;           // lazily created by ga_run_host
     int64_t last_h2d = 0, last_d2h = 0;
 };

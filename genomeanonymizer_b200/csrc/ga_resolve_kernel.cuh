@@ -1,0 +1,357 @@
+// ga_resolve_kernel.cuh - stage 2 of the streaming pipeline: one small CTA per session turns the scan kernel's
+// candidate entries and indel observations into the germline set (seen in tumor AND normal, minus
+// variant_to_keep: anonymizer_methods.py:546-547, variants.py:83-96), the ordered list of modified reads, their
+// new lengths and their slots in the compacted output (north_star jobs (1) + (4)); it writes the record headers,
+// the per-session counters (= AnonymizedVariantsStatistics.window_var_counts) and the hand-over to the emission
+// kernel (ga_emit_kernel.cuh), which writes the record bodies.
+//
+// 128 threads, ~30 KB of shared memory -> 7 CTAs per SM; per session three dependent memory round trips
+// (descriptor + counts, entries, per-record meta) and a handful of 4-warp barriers.
+// Anything the shared-memory tables cannot hold (or describe to the emission kernel) sends the whole session to
+// the global-scratch fallback kernel (ga_session_kernel.cuh) through big_list.
+#pragma once
+#include "ga_scan_kernel.cuh"
+
+namespace ga {
+
+constexpr int kResThreads = 128;
+constexpr int kEntR = 2 * kEntHalf;
+constexpr int kObsR = 2 * kObsHalf;
+constexpr int kHashR = 512;
+constexpr int kGermStride = kGermCap + 4;   // per session: [0] germline SNV alleles, [1] col_begin, [4..] (column << 4) | base code
+static_assert(kReads2 / 32 <= kResThreads, "phase L gives every bitmap word its own thread");
+
+// Hand-over to the emission kernel.  kind[k] of output record k: 0 = nothing to do (record written by the fallback
+// kernel), 1 = clean read, SNV-only: copy + patch, 2 = other CIGAR, SNV-only: re-walk, 3 = indel-masked with at
+// most two edits (their description sits in the first 32 bytes of the record's out_qual slot until the emission
+// kernel overwrites it with the qualities).
+struct EmitScratch2 {
+    uint8_t* kind;       // [cap_records]
+    uint4* edesc;        // [cap_records] {source record unit, pos, original length, session}
+    uint32_t* germ;      // [n_sessions][kGermStride]
+};
+
+struct SmemR {
+    uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
+    uint32_t ent[kEntR];                 // entries of the tumor item, then of the normal item
+    uint32_t msize[kMod2], mseq[kMod2], mqual[kMod2];
+    uint16_t clist[kMod2];
+    int16_t mhead[kMod2];                // per modified read: chain of its germline indel observations
+    uint32_t modbits[kReads2 / 32], indelbits[kReads2 / 32], genbits[kReads2 / 32], woff[kReads2 / 32];
+    int32_t o_col[kObsR];
+    uint32_t o_meta[kObsR];
+    uint32_t o_read[kObsR];              // session-relative read (low 16) | allele length (high 16)
+    int32_t o_irp[kObsR];
+    uint32_t o_sig0[kObsR], o_sig1[kObsR];
+    int16_t o_next[kObsR], o_rnext[kObsR];
+    int16_t ihash[kHashR];               // heads of the observation chains, hashed by column
+};
+
+template <int T>
+__device__ __forceinline__ uint32_t block_scan32(uint32_t v, uint32_t* tmp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+    if (lane == 31) tmp[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0u, all = 0u;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) { const uint32_t x = tmp[w]; if (w < warp) before += x; all += x; }
+    *total = all;
+    return before + inc - v;
+}
+template <int T>
+__device__ __forceinline__ unsigned long long block_scan64(unsigned long long v, unsigned long long* tmp, unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+    if (lane == 31) tmp[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0ull, all = 0ull;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) { const unsigned long long x = tmp[w]; if (w < warp) before += x; all += x; }
+    *total = all;
+    return before + inc - v;
+}
+
+__device__ __forceinline__ int acgt_index(uint32_t b) { return b == 1u ? 0 : b == 2u ? 1 : b == 4u ? 2 : b == 8u ? 3 : -1; }
+
+__global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+                                                                 int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
+                                                                 ResultView O, ScanScratch X, EmitScratch2 E) {
+    constexpr int T = kResThreads;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SmemR* sm = reinterpret_cast<SmemR*>(smem_raw);
+    __shared__ unsigned long long s_scan64[2][T / 32];
+    __shared__ uint32_t s_scan[T / 32];
+    __shared__ uint32_t s_cnt[3], s_ngerm, s_overflow;
+    __shared__ unsigned long long s_base[3];
+
+    SessCtx c;
+    c.B = B;
+    c.totals = O.totals;
+    memset(&c.T, 0, sizeof c.T);
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t round = 0;
+
+    for (int s = blockIdx.x; s < S.n_sessions; s += gridDim.x, ++round) {
+        c.d = descs[s];
+        if (c.d.big) continue;                                        // listed by the assignment kernel
+        const uint4 cnt0 = X.cnt[2 * (size_t)s], cnt1 = X.cnt[2 * (size_t)s + 1];
+        c.s = s;
+        c.nt = c.d.t_end - c.d.t_begin;
+        c.n_range = c.nt + (c.d.n_end - c.d.n_begin);
+        const int n_cols = c.d.n_cols;
+        const int n_cw = (c.n_range + 31) >> 5;
+        if (cnt0.x == kCntOverflow || cnt1.x == kCntOverflow) {       // the scan kernel could not hold the session
+            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            continue;
+        }
+        const int n_ent0 = (int)cnt0.x, n_ent = n_ent0 + (int)cnt1.x;
+        const int n_obs0 = (int)cnt0.y, n_obs = n_obs0 + (int)cnt1.y;
+        const uint32_t sess_reads = cnt0.z + cnt1.z, sess_bases = cnt0.w + cnt1.w;
+        c.first = S.first[s];
+        c.keep_type = S.keep_type[s]; c.keep_pos = S.keep_pos[s]; c.keep_end = S.keep_end[s]; c.keep_len = S.keep_len[s];
+        const uint32_t ka0 = S.keep_allele_off[s];
+        c.keep_allele = S.keep_alleles + ka0;
+        c.keep_alen = (int)(S.keep_allele_off[s + 1] - ka0);
+
+        // ---- stage the session: zeroed tables, entries and observations from the scan kernel's regions
+        for (int k = tid; k < ((n_cols + 3) >> 2); k += T) sm->tab[k] = 0u;
+        for (int k = tid; k < n_cw; k += T) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
+        if (n_obs > 0) for (int k = tid; k < kHashR; k += T) sm->ihash[k] = (int16_t)-1;
+        if (tid == 0) { s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u; s_ngerm = 0u; s_overflow = 0u; }
+        {
+            const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
+            const uint32_t* e1 = e0 + kEntHalf;
+            for (int k = tid; k < n_ent; k += T) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+            const ObsRec* o0 = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
+            const ObsRec* o1 = o0 + kObsHalf;
+            for (int o = tid; o < n_obs; o += T) {
+                const uint4* src = reinterpret_cast<const uint4*>(o < n_obs0 ? o0 + o : o1 + (o - n_obs0));
+                const uint4 a = __ldg(src), b = __ldg(src + 1);
+                sm->o_col[o] = (int32_t)a.x; sm->o_meta[o] = a.y; sm->o_read[o] = a.z; sm->o_irp[o] = (int32_t)a.w;
+                sm->o_sig0[o] = b.x; sm->o_sig1[o] = b.y;
+            }
+        }
+        // variant_to_keep as an SNV entry key (anonymizer_methods.py:546-547 compares with CalledGenomicVariant.__eq__)
+        uint32_t keep_key = 0xffffffffu;
+        if (c.keep_type == GA_VT_SNV && c.keep_end == c.keep_pos && c.keep_len == 1 && c.keep_alen == 1) {
+            const int kc = c.keep_pos - c.d.col_begin;
+            if (kc >= 0 && kc < n_cols) {
+                const uint8_t ch = c.keep_allele[0];
+                const uint32_t code = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : 0u;
+                if (code) keep_key = ((uint32_t)kc << 4) | code;
+            }
+        }
+        __syncthreads();
+
+        // ---- build: allele table and observation chains
+        for (int k = tid; k < n_ent; k += T) {
+            const uint32_t e = sm->ent[k];
+            const uint32_t col = (e >> 4) & 0xfffu;
+            const int idx = acgt_index(e & 15u);
+            if (idx < 0) { s_overflow = 1u; continue; }                // IUPAC read base: the fallback kernel keeps all 16 codes
+            atomicOr(&sm->tab[col >> 2], 1u << (idx + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
+        }
+        for (int o = tid; o < n_obs; o += T) {
+            // push on the column's chain: 16-bit heads are updated with a CAS on the containing word
+            const int h = sm->o_col[o] & (kHashR - 1);
+            uint32_t* hw = reinterpret_cast<uint32_t*>(sm->ihash) + (h >> 1);
+            const int shift = (h & 1) * 16;
+            uint32_t old = *hw, assumed;
+            do {
+                assumed = old;
+                sm->o_next[o] = (int16_t)((assumed >> shift) & 0xffffu);
+                __threadfence_block();
+                old = atomicCAS(hw, assumed, (assumed & ~(0xffffu << shift)) | (((uint32_t)o & 0xffffu) << shift));
+            } while (old != assumed);
+        }
+        __syncthreads();
+        if (s_overflow) {
+            __syncthreads();
+            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            continue;
+        }
+
+        // ---- resolve + mark: germline = seen in tumor AND normal, minus variant_to_keep
+        for (int k = tid; k < n_ent; k += T) {
+            const uint32_t e = sm->ent[k];
+            const uint32_t col = (e >> 4) & 0xfffu;
+            const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
+            const int idx = acgt_index(e & 15u);
+            if ((((byte & (byte >> 4)) >> idx) & 1u) && (e & 0xffffu) != keep_key) {
+                const uint32_t i = (e >> 16) & 0xfffu;
+                atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
+                if (e & kEntGen) atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
+            }
+        }
+        {   // distinct germline SNV alleles: the per-session counter and the emission kernel's list
+            uint32_t cnt = 0;
+            for (int k = tid; k < ((n_cols + 3) >> 2); k += T) {
+                const uint32_t w = sm->tab[k];
+                uint32_t g = w & (w >> 4) & 0x0f0f0f0fu;
+                while (g) {
+                    const int bit = __ffs(g) - 1; g &= g - 1;
+                    const uint32_t key = ((uint32_t)(4 * k + (bit >> 3)) << 4) | (1u << (bit & 7));
+                    if (key == keep_key) continue;
+                    ++cnt;
+                    const uint32_t slot = atomicAdd(&s_ngerm, 1u);
+                    if (slot < (uint32_t)kGermCap) E.germ[(size_t)s * kGermStride + 4 + slot] = key;
+                }
+            }
+            cnt = warp_sum(cnt);
+            if (lane == 0 && cnt) atomicAdd(&s_cnt[0], cnt);
+        }
+        for (int o = tid; o < n_obs; o += T) {                        // indels: exact key equality (variants.py:83-96)
+            const uint32_t m = sm->o_meta[o];
+            const int col = sm->o_col[o];
+            bool germ = false, rep = true;
+            for (int o2 = sm->ihash[col & (kHashR - 1)]; o2 >= 0; o2 = sm->o_next[o2]) {
+                if (o2 == o || sm->o_col[o2] != col) continue;
+                if (!obs_equal2(c, sm, o, o2)) continue;
+                if ((sm->o_meta[o2] ^ m) & kMetaDs) germ = true;
+                if (o2 < o) rep = false;
+            }
+            if (germ && obs_equals_keep2(c, sm, o)) germ = false;
+            if (germ) {
+                atomicOr(&sm->o_meta[o], kMetaGerm | (rep ? kMetaRep : 0u));
+                if (rep) atomicAdd(&s_cnt[(m & kMetaIns) ? 2 : 1], 1u);
+                const uint32_t i = (uint32_t)obs_read(sm, o);
+                atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
+                atomicOr(&sm->indelbits[i >> 5], 1u << (i & 31));
+            }
+        }
+        __syncthreads();
+
+        // ---- ordered list of the modified reads (one bitmap word per thread)
+        uint32_t n_mod;
+        {
+            const uint32_t bits = tid < n_cw ? sm->modbits[tid] : 0u;
+            uint32_t off = block_scan32<T>(__popc(bits), s_scan, &n_mod);
+            if (tid < n_cw) sm->woff[tid] = off;
+            uint32_t b = bits;
+            while (b) {
+                const int k = __ffs(b) - 1; b &= b - 1;
+                if (off < (uint32_t)kMod2) { sm->clist[off] = (uint16_t)(tid * 32 + k); sm->mhead[off] = (int16_t)-1; }
+                ++off;
+            }
+        }
+        if (n_mod > (uint32_t)kMod2 || s_ngerm > (uint32_t)kGermCap) {
+            __syncthreads();
+            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            continue;
+        }
+        __syncthreads();
+        if (n_obs > 0) {                                              // hang every germline observation on its modified read
+            for (int o = tid; o < n_obs; o += T) {
+                if (!(sm->o_meta[o] & kMetaGerm)) continue;
+                const uint32_t i = (uint32_t)obs_read(sm, o);
+                const uint32_t k = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
+                // 16-bit exchange on the containing word
+                uint32_t* hw = reinterpret_cast<uint32_t*>(sm->mhead) + (k >> 1);
+                const int shift = (int)(k & 1u) * 16;
+                uint32_t old = *hw, assumed;
+                do {
+                    assumed = old;
+                    sm->o_rnext[o] = (int16_t)((assumed >> shift) & 0xffffu);
+                    __threadfence_block();
+                    old = atomicCAS(hw, assumed, (assumed & ~(0xffffu << shift)) | (((uint32_t)o & 0xffffu) << shift));
+                } while (old != assumed);
+            }
+            __syncthreads();
+        }
+
+        // ---- new length of every modified read; indel-masked reads need the edit analysis
+        const int per = ((int)n_mod + T - 1) / T;
+        const int k0 = min(tid * per, (int)n_mod), k1 = min(k0 + per, (int)n_mod);
+        unsigned long long mine = 0ull;                               // [records:16 | seq units:24 | qual units:24]
+        uint32_t n_q = 0;
+        for (int k = k0; k < k1; ++k) {
+            const int i = (int)sm->clist[k];
+            const int64_t r = read_of(c, i);
+            const int L0 = (int)(__ldg(B.len_flag + r) & 0xffffu);
+            uint32_t m;
+            if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
+                Ed2 E2;
+                int new_len = L0;
+                if (!collect2(c, sm, k, L0, E2, &new_len)) s_overflow = 1u;   // more than two edits: the fallback kernel takes the session
+                m = kModFlag | kQualFlag | ((uint32_t)new_len & kLen2);
+                ++n_q;
+            } else {
+                m = kModFlag | (uint32_t)L0;
+            }
+            sm->msize[k] = m;
+            uint32_t units = ((m & kLen2) + 31u) / 32u; if (units < 1u) units = 1u;
+            mine += (1ull << 48) | ((unsigned long long)units << 24) | ((m & kQualFlag) ? (unsigned long long)units : 0ull);
+        }
+        unsigned long long total;
+        const unsigned long long off = block_scan64<T>(mine, s_scan64[round & 1u], &total);
+        if (s_overflow) {
+            __syncthreads();
+            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            continue;
+        }
+        const uint32_t tot_rec = (uint32_t)(total >> 48), tot_seq = (uint32_t)((total >> 24) & 0xffffffu), tot_qual = (uint32_t)(total & 0xffffffu);
+        if (tid == 0) {
+            s_base[0] = atomicAdd((unsigned long long*)&O.totals->n_modified, (unsigned long long)tot_rec);
+            s_base[1] = atomicAdd((unsigned long long*)&O.totals->seq16_used, (unsigned long long)tot_seq);
+            s_base[2] = atomicAdd((unsigned long long*)&O.totals->qual16_used, (unsigned long long)tot_qual);
+            atomicAdd((unsigned long long*)&O.totals->session_reads, (unsigned long long)sess_reads);
+            atomicAdd((unsigned long long*)&O.totals->session_bases, (unsigned long long)sess_bases);
+            for (int k = 0; k < 3; ++k) {
+                O.sess_counts[4 * (size_t)s + k] = s_cnt[k];
+                if (s_cnt[k]) atomicAdd((unsigned long long*)&O.totals->masked[k], (unsigned long long)s_cnt[k]);
+            }
+            O.sess_counts[4 * (size_t)s + 3] = sess_reads;
+            E.germ[(size_t)s * kGermStride] = s_ngerm;
+            E.germ[(size_t)s * kGermStride + 1] = (uint32_t)c.d.col_begin;
+        }
+        {   // per-record output offsets (session-relative)
+            uint32_t so = (uint32_t)((off >> 24) & 0xffffffu), qo = (uint32_t)(off & 0xffffffu);
+            for (int k = k0; k < k1; ++k) {
+                const uint32_t m = sm->msize[k];
+                uint32_t units = ((m & kLen2) + 31u) / 32u; if (units < 1u) units = 1u;
+                sm->mseq[k] = so; sm->mqual[k] = qo;
+                so += units; if (m & kQualFlag) qo += units;
+            }
+        }
+        n_q = warp_sum(n_q);
+        if (lane == 0 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
+        __syncthreads();
+        const bool fits = (int64_t)(s_base[0] + tot_rec) <= O.cap_records && (int64_t)(s_base[1] + tot_seq) <= O.cap_seq16 &&
+                          (int64_t)(s_base[2] + tot_qual) <= O.cap_qual16;
+        if (!fits) { if (tid == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); __syncthreads(); continue; }
+
+        // ---- record headers and the hand-over to the emission kernel
+        for (int k = tid; k < (int)n_mod; k += T) {
+            const uint32_t m = sm->msize[k];
+            const bool q = (m & kQualFlag) != 0u;
+            const int i = (int)sm->clist[k];
+            const int64_t r = read_of(c, i);
+            const uint64_t rec_idx = s_base[0] + k;
+            const uint32_t qual16 = q ? (uint32_t)(s_base[2] + sm->mqual[k]) : 0xffffffffu;
+            write_record_meta(O, rec_idx, s, r, (int)(m & kLen2), s_base[1] + sm->mseq[k], qual16);
+            const uint32_t lf = __ldg(B.len_flag + r);
+            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : 1);
+            E.kind[rec_idx] = kind;
+            E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)__ldg(B.pos + r), lf & 0xffffu, (uint32_t)s);
+            if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
+                Ed2 E2; int nl = 0;
+                collect2(c, sm, k, (int)(lf & 0xffffu), E2, &nl);
+                EditAux a;
+                a.irp0 = E2.irp[0]; a.pos0 = E2.pos[0]; a.len0 = (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u);
+                a.irp1 = E2.irp[1]; a.pos1 = E2.pos[1]; a.len1 = (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u);
+                a.ne = (uint32_t)E2.ne; a.n_del = (uint32_t)E2.n_del;
+                uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
+                const uint4* src = reinterpret_cast<const uint4*>(&a);
+                dst[0] = src[0]; dst[1] = src[1];
+            }
+        }
+        __syncthreads();                                              // tables and flags are reused by the next session
+    }
+}
+
+}  // namespace ga

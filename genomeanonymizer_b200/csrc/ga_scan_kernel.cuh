@@ -1,0 +1,371 @@
+// ga_scan_kernel.cuh - stage 1 of the streaming pipeline: allele discovery over every session read
+// (north_star jobs (2) + (3a): CIGAR walk and comparison against the reference).
+//
+// Work item = the tumor (or normal) candidate reads of one session, taken by ONE WARP from a ticket counter; no
+// block-level synchronisation anywhere.  The warp walks the item in tiles of up to 32 reads whose records are
+// contiguous in seq4: the tile's record bytes are fetched by one TMA bulk copy (cp.async.bulk + mbarrier) into
+// the warp's private two-stage shared-memory ring while the previous tile is being compared, the per-read
+// meta words (pos, length, record offset, CIGAR offsets) are prefetched two tiles ahead into registers, and the
+// session's reference window is staged once per item.  Lane = read: a clean read (one M/=/X op spanning the
+// read - nearly all of them) is compared 32 bases per 128-bit shared-memory load; mismatching 8-base words are
+// resolved right away from the staged bytes (variation_classifier.py:144-150); reads with any other CIGAR are
+// walked by the whole warp (variation_classifier.py:52-107).
+//
+// Output (engine scratch, one fixed region per item, written by its warp only - no atomics):
+//   ent[item][..]   SNV candidate entries  (read << 16) | (column << 4) | base code, bit 28 = read has another CIGAR
+//   obs[item][..]   indel observations (ObsRec)
+//   cnt[item]       {entries, observations, session reads, session bases}; entries == kCntOverflow hands the
+//                   session to the fallback kernel
+// The resolve kernel (ga_resolve_kernel.cuh) turns these into the germline set and the modified-record list.
+#pragma once
+#include "ga_session_v2.cuh"
+
+namespace ga {
+
+constexpr int kEntHalf = 768;            // SNV candidate entries per item (tumor or normal half of a session)
+constexpr int kObsHalf = 192;            // indel observations per item
+constexpr int kTileUnits = 160;          // 16-byte units staged per tile (32 reads of 150 bp)
+constexpr int kWbuf = 96;                // entries buffered per warp between flushes
+constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean single-op read
+constexpr uint32_t kCntOverflow = 0xffffffffu;
+constexpr int kScanThreads = 256;
+
+struct ObsRec { int32_t col; uint32_t meta; uint32_t read_alen; int32_t irp; uint32_t sig0, sig1, pad0, pad1; };
+static_assert(sizeof(ObsRec) == 32, "ObsRec is two 16-byte stores");
+
+struct ScanScratch {
+    uint32_t* ent;      // [2 * n_sessions][kEntHalf]
+    ObsRec* obs;        // [2 * n_sessions][kObsHalf]
+    uint4* cnt;         // [2 * n_sessions]
+};
+
+struct WarpSmem {
+    uint4 ring[2][kTileUnits];           // record bytes of the tile in flight and the tile being compared
+    uint32_t sref[kCols2 / 8 + 8];       // 4-bit reference of the session's columns (word 0 = ref4 word of column col_begin)
+    uint32_t wbuf[kWbuf];                // entries waiting for the next coalesced flush
+    uint64_t bar[2];                     // mbarriers of the two ring stages
+    uint32_t wcnt, ovf, pad[2];
+};
+static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp slices stay 16-byte aligned");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP.S.G)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+struct TileMeta { int pos; uint32_t lf, so, c0, c1; };
+struct TileStage { uint32_t staged, sof; };    // warp-uniform: records sit in the ring, first record unit
+
+// Everything a warp knows about the item it is working on.
+struct ItemCtx {
+    BatchView B;
+    WarpSmem* ws;
+    ga_totals* totals;
+    int64_t begin;          // first read of the item
+    int n;                  // reads of the item
+    int i_base;             // session-relative id of read `begin`
+    int col_begin, n_cols, first;
+    int relbase;            // (col_begin + 8) & ~7: reference nibble index of sref word 0
+    uint32_t ds;
+    uint32_t* ent; ObsRec* obs;
+    uint32_t n_ent, n_obs, n_reads, n_bases;   // n_ent / n_obs warp-uniform, n_reads / n_bases per lane (summed at the end)
+};
+
+__device__ __forceinline__ void push_entry_w(const ItemCtx& c, int i, int col, uint32_t b, uint32_t gen) {
+    const uint32_t slot = atomicAdd(&c.ws->wcnt, 1u);
+    if (slot < (uint32_t)kWbuf) c.ws->wbuf[slot] = gen | ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
+    else c.ws->ovf = 1u;
+}
+
+// Coalesced flush of the buffered entries into the item's region.
+__device__ __forceinline__ void flush_entries(ItemCtx& c, int lane) {
+    __syncwarp();
+    const uint32_t n = min(c.ws->wcnt, (uint32_t)kWbuf);
+    if (c.n_ent + n > (uint32_t)kEntHalf) c.ws->ovf = 1u;
+    else for (uint32_t k = lane; k < n; k += 32) c.ent[c.n_ent + k] = c.ws->wbuf[k];
+    c.n_ent += n;
+    __syncwarp();
+    if (lane == 0) c.ws->wcnt = 0u;
+    __syncwarp();
+}
+
+// One read with any CIGAR, walked by the whole warp (all arguments warp-uniform).  Lane w owns query words
+// w, w+32, ...: it compares the part of every aligned segment that overlaps its 8 bases with the reference;
+// lane 0 records the I/D observations (variation_classifier.py:52-107: pos, in_read_pos with the H/N quirk,
+// Python-slice clamped allele).
+__device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, int pos, int L, uint32_t c0, uint32_t c1, const uint32_t* rec, int lane) {
+    const BatchView& B = c.B;
+    int span = 0;
+    for (uint32_t ci = c0; ci < c1; ++ci) {
+        const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
+        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
+    }
+    if (pos + span <= c.first) return;                                   // fetched by range, does not reach the region
+    if (lane == 0) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
+    if ((int64_t)pos + span > B.ref_len || pos < 0 || pos < c.col_begin || pos + span - c.col_begin >= c.n_cols) {
+        if (lane == 0) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
+        return;
+    }
+    // ---- SNV candidates, one 8-base word per lane
+    for (int w = lane; w < ((L + 7) >> 3); w += 32) {
+        const int qb = w << 3;
+        const uint32_t v = rec[w];
+        int rc = pos, q = 0;
+        for (uint32_t ci = c0; ci < c1; ++ci) {
+            const uint32_t cw = __ldg(B.cigar + ci), op = cw & 15u;
+            const int ln = (int)(cw >> 4);
+            if (op == 0u || op == 7u || op == 8u) {
+                const int lo = max(q, qb), hi = min(min(q + ln, qb + 8), L);
+                if (lo < hi) {
+                    const int p0 = rc - q + qb;                           // reference position of query base qb under this segment
+                    const uint32_t fw = ref_word(B.ref4, (int64_t)p0);
+                    uint32_t mask = 0xffffffffu;
+                    if (lo > qb) mask &= 0xffffffffu << ((lo - qb) * 4);
+                    if (hi < qb + 8) mask &= 0xffffffffu >> ((qb + 8 - hi) * 4);
+                    uint32_t x = (v ^ fw) & mask;
+                    while (x) {
+                        const int n = (__ffs(x) - 1) >> 2;
+                        x &= ~(0xfu << (n * 4));
+                        const uint32_t b = (v >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+                        if (b != 15u && is_acgt(rf)) push_entry_w(c, i, p0 + n - c.col_begin, b, kEntGen);   // variation_classifier.py:147-150
+                    }
+                }
+                q += ln; rc += ln;
+            } else if (op == 1u || op == 4u) q += ln;
+            else if (op == 2u || op == 3u) rc += ln;
+            if (q >= qb + 8) break;
+        }
+    }
+    // ---- indel observations (lane 0; the count stays warp-uniform through the shuffle below)
+    uint32_t n_obs = c.n_obs;
+    if (lane == 0) {
+        int rc = pos, q = 0, ccl = 0, rcb = 0;
+        for (uint32_t ci = c0; ci < c1; ++ci) {
+            const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
+            const int ln = (int)(w >> 4);
+            if (op == 0u || op == 7u || op == 8u) {
+                if (q + ln > L) { raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r); break; }   // IndexError in variation_classifier.py:148
+                q += ln; rc += ln; ccl += ln;
+            } else if (op == 1u || op == 2u) {
+                if (n_obs >= (uint32_t)kObsHalf) { c.ws->ovf = 1u; break; }
+                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | (c.ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+                const int irp = ccl + rcb;                                // variation_classifier.py:82
+                const int alen = allele_len(meta, irp, L);                // Python-slice clamped (variation_classifier.py:87-88)
+                uint32_t s0 = 0u, s1 = 0u;
+                for (int j = 0; j < alen && j < 16; ++j) {
+                    const uint32_t code = (rec[(irp + j) >> 3] >> (((irp + j) & 7) * 4)) & 15u;
+                    if (j < 8) s0 |= code << (4 * j); else s1 |= code << (4 * (j - 8));
+                }
+                uint4* dst = reinterpret_cast<uint4*>(c.obs + n_obs);
+                dst[0] = make_uint4((uint32_t)(rc - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
+                dst[1] = make_uint4(s0, s1, 0u, 0u);
+                ++n_obs;
+                if (op == 1u) { q += ln; rcb += ln; } else { rc += ln; ccl += ln; rcb -= ln; }
+            } else if (op == 3u) { rc += ln; ccl += ln; }
+            else if (op == 4u) { q += ln; rcb += ln; }
+            else if (op == 5u) { rcb += ln; }
+        }
+    }
+    c.n_obs = __shfl_sync(0xffffffffu, n_obs, 0);
+}
+
+__device__ __forceinline__ TileMeta load_tile_meta(const ItemCtx& c, int t, int TR, int lane) {
+    TileMeta m = {0, 0u, 0u, 0u, 0u};
+    const int i = t * TR + lane;
+    if (lane < TR && i < c.n) {
+        const int64_t r = c.begin + i;
+        m.pos = __ldg(c.B.pos + r); m.lf = __ldg(c.B.len_flag + r); m.so = __ldg(c.B.seq_off16 + r);
+        m.c0 = __ldg(c.B.cigar_off + r); m.c1 = __ldg(c.B.cigar_off + r + 1);
+    }
+    return m;
+}
+
+// Starts the TMA copy of the tile's record bytes into ring stage `b` when the records are contiguous and fit.
+__device__ __forceinline__ TileStage issue_tile(const ItemCtx& c, const TileMeta& m, bool valid, int b, bool tma_ok, int lane) {
+    const uint32_t L = m.lf & 0xffffu;
+    const uint32_t units = valid ? (L + 31u) >> 5 : 0u;
+    const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);
+    const bool ok = !valid || (m.so >= sof && m.so - sof + units <= (uint32_t)kTileUnits);
+    const uint32_t end = valid ? m.so - sof + units : 0u;
+    const uint32_t total = __reduce_max_sync(0xffffffffu, ok ? end : 0u);
+    TileStage st;
+    st.sof = sof;
+    st.staged = (tma_ok && total > 0u && __all_sync(0xffffffffu, ok)) ? 1u : 0u;
+    if (st.staged && lane == 0) {
+        mbar_expect_tx(&c.ws->bar[b], total * 16u);
+        bulk_g2s(c.ws->ring[b], c.B.seq4 + 16ull * sof, total * 16u, &c.ws->bar[b]);
+    }
+    return st;
+}
+
+// Compare + discover one tile (lane = read).
+__device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, const TileStage& st, int b, int lane) {
+    const int idx = t * TR + lane;
+    const bool valid = lane < TR && idx < c.n;
+    const int i = c.i_base + idx;
+    const int pos = m.pos;
+    const int L = (int)(m.lf & 0xffffu);
+    const bool one_op = valid && (m.c1 - m.c0 == 1u);
+    // a single-op read whose span L stays inside the reference and the session table
+    const bool spec = one_op && L <= 256 && pos >= 0 && (int64_t)pos + L <= c.B.ref_len && pos >= c.col_begin && pos + L - c.col_begin < c.n_cols;
+    const uint32_t op0 = cw0 & 15u;
+    const bool clean = spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(cw0 >> 4) == L);
+    const bool in_sess = clean && pos + L > c.first;                     // fetched by range but not reaching the region: skipped
+    const uint32_t* rec = st.staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (m.so - st.sof))
+                                    : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * m.so);
+    if (in_sess) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
+    const int rel = pos + 8 - c.relbase;                                 // nibble offset of base `pos` inside the staged window
+    const int units = in_sess ? (L + 31) >> 5 : 0;
+    const int umax = __reduce_max_sync(0xffffffffu, units);
+    uint32_t wm = 0u;                                                    // bit k: 8-base word k differs from the reference
+    {
+        const uint32_t* rp = c.ws->sref + (in_sess ? (rel >> 3) : 0);
+        const uint32_t sh = (uint32_t)(rel & 7) * 4u;
+        uint32_t prev = rp[0];
+        const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
+#pragma unroll 1
+        for (int u = 0; u < umax; ++u) {
+            if (u < units) {
+                const uint4 v = rec4[u];
+                const uint32_t r1 = rp[4 * u + 1], r2 = rp[4 * u + 2], r3 = rp[4 * u + 3], r4 = rp[4 * u + 4];
+                uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
+                uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
+                prev = r4;
+                if (u == units - 1) {                                    // padding nibbles of the last unit
+                    x0 &= tail_mask(L, 4 * u); x1 &= tail_mask(L, 4 * u + 1); x2 &= tail_mask(L, 4 * u + 2); x3 &= tail_mask(L, 4 * u + 3);
+                }
+                const uint32_t bits = (x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u);
+                wm |= bits << (4 * u);
+            }
+        }
+    }
+    // ---- mismatching words: SNV candidates (variation_classifier.py:147-150), resolved from the staged bytes
+    while (wm) {
+        const int k = __ffs(wm) - 1; wm &= wm - 1;
+        const uint32_t rw = rec[k];
+        const int nib = rel + 8 * k;
+        const uint32_t fw = __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u);
+        uint32_t x = (rw ^ fw) & tail_mask(L, k);
+        const int colb = pos - c.col_begin + 8 * k;
+        while (x) {
+            const int n = (__ffs(x) - 1) >> 2;
+            x &= ~(0xfu << (n * 4));
+            const uint32_t bb = (rw >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+            if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, 0u);
+        }
+    }
+    // ---- reads with any other CIGAR (or an error case): the whole warp walks them one by one
+    uint32_t gm = __ballot_sync(0xffffffffu, valid && !clean);
+    while (gm) {
+        const int src = __ffs(gm) - 1; gm &= gm - 1;
+        const int g_pos = __shfl_sync(0xffffffffu, pos, src), g_L = __shfl_sync(0xffffffffu, L, src);
+        const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = __shfl_sync(0xffffffffu, m.c1, src);
+        const uint32_t g_so = __shfl_sync(0xffffffffu, m.so, src);
+        const uint32_t* g_rec = st.staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - st.sof))
+                                          : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * g_so);
+        scan_generic_read(c, c.i_base + t * TR + src, c.begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, lane);
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs, ScanScratch X,
+                                                               unsigned int* __restrict__ ticket, ga_totals* totals) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw) + warp;
+    if (lane == 0) {
+        mbar_init(&ws->bar[0], 1u); mbar_init(&ws->bar[1], 1u);
+        ws->wcnt = 0u; ws->ovf = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t parity = 0u;                                                // bit b: phase the next wait on bar[b] looks for
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(B.seq4) & 15u) == 0u;
+    const int64_t ref_words = ((B.ref_len + 7) >> 3) + 9;
+    const uint32_t n_items = 2u * (uint32_t)S.n_sessions;
+
+    ItemCtx c;
+    c.B = B; c.ws = ws; c.totals = totals;
+    uint32_t item = lane == 0 ? atomicAdd(ticket, 1u) : 0u;
+    item = __shfl_sync(0xffffffffu, item, 0);
+    while (item < n_items) {
+        const uint32_t next = lane == 0 ? atomicAdd(ticket, 1u) : 0u;    // next item's ticket travels while this one is processed
+        const int s = (int)(item >> 1);
+        c.ds = item & 1u;
+        const uint32_t dw = lane < 20 ? __ldg(reinterpret_cast<const uint32_t*>(descs + s) + lane) : 0u;
+        c.first = __ldg(S.first + s);
+        const int t_begin = (int)__shfl_sync(0xffffffffu, dw, 0), t_end = (int)__shfl_sync(0xffffffffu, dw, 1);
+        const int n_begin = (int)__shfl_sync(0xffffffffu, dw, 2), n_end = (int)__shfl_sync(0xffffffffu, dw, 3);
+        c.col_begin = (int)__shfl_sync(0xffffffffu, dw, 4); c.n_cols = (int)__shfl_sync(0xffffffffu, dw, 5);
+        const int big = (int)__shfl_sync(0xffffffffu, dw, 7);
+        const uint32_t seq_n = __shfl_sync(0xffffffffu, dw, c.ds ? 15 : 13);
+        c.begin = c.ds ? n_begin : t_begin;
+        c.n = c.ds ? n_end - n_begin : t_end - t_begin;
+        c.i_base = c.ds ? t_end - t_begin : 0;
+        c.relbase = (c.col_begin + 8) & ~7;
+        c.ent = X.ent + (size_t)item * kEntHalf;
+        c.obs = X.obs + (size_t)item * kObsHalf;
+        c.n_ent = 0u; c.n_obs = 0u; c.n_reads = 0u; c.n_bases = 0u;
+        if (!big && c.n > 0) {
+            // ---- the session's reference window (+ record padding, + funnel-shift lookahead)
+            {
+                const int64_t w0 = (int64_t)((c.col_begin + 8) >> 3);
+                const int nw = (c.n_cols >> 3) + 8;
+                for (int k = lane; k < nw; k += 32) ws->sref[k] = (w0 + k < ref_words) ? __ldg(B.ref4 + w0 + k) : 0xffffffffu;
+            }
+            const uint32_t avg_units = max(1u, (seq_n + (uint32_t)c.n - 1u) / (uint32_t)c.n);
+            const int TR = (int)max(1u, min(32u, (uint32_t)kTileUnits / avg_units));     // reads per tile
+            const int n_tiles = (c.n + TR - 1) / TR;
+            // ---- software pipeline: meta two tiles ahead, record bytes (TMA) one tile ahead
+            TileMeta mA = load_tile_meta(c, 0, TR, lane);
+            TileMeta mB = load_tile_meta(c, 1, TR, lane);
+            __syncwarp();                                                 // the previous item's ring reads are done
+            TileStage stA = issue_tile(c, mA, lane < TR && lane < c.n, 0, tma_ok, lane);
+            uint32_t cwA = (mA.c1 > mA.c0) ? __ldg(B.cigar + mA.c0) : 0u;
+            TileStage stB = {0u, 0u};
+            if (n_tiles > 1) stB = issue_tile(c, mB, lane < TR && TR + lane < c.n, 1, tma_ok, lane);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int b = t & 1;
+                uint32_t cwB = 0u;
+                if (mB.c1 > mB.c0) {
+                    cwB = __ldg(B.cigar + mB.c0);
+                    if (mB.c1 - mB.c0 > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
+                }
+                TileMeta mC = load_tile_meta(c, t + 2, TR, lane);
+                if (stA.staged) { mbar_wait(&ws->bar[b], (parity >> b) & 1u); parity ^= 1u << b; }
+                scan_tile_w(c, t, TR, mA, cwA, stA, b, lane);
+                __syncwarp();                                             // every lane is done with ring stage b
+                TileStage stC = {0u, 0u};
+                if (t + 2 < n_tiles) stC = issue_tile(c, mC, lane < TR && (t + 2) * TR + lane < c.n, b, tma_ok, lane);
+                if (ws->wcnt >= 32u) flush_entries(c, lane);
+                mA = mB; cwA = cwB; stA = stB;
+                mB = mC; stB = stC;
+            }
+            flush_entries(c, lane);
+        }
+        if (!big) {
+            const uint32_t nr = warp_sum(c.n_reads), nb = warp_sum(c.n_bases);
+            __syncwarp();
+            if (lane == 0) {
+                X.cnt[item] = make_uint4(ws->ovf ? kCntOverflow : c.n_ent, c.n_obs, nr, nb);
+                ws->ovf = 0u;
+            }
+            __syncwarp();
+        }
+        item = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+}  // namespace ga

@@ -414,12 +414,12 @@ __device__ void discover_generic_warp(const SessCtx& c, Smem2* sm, const Queues&
 }
 
 // ------------------------------------------------------------------ indel observations (shared memory only)
-__device__ __forceinline__ int obs_read(const Smem2* sm, int o) { return (int)(sm->o_read[o] & 0xffffu); }
-__device__ __forceinline__ int obs_alen(const Smem2* sm, int o) { return (int)(sm->o_read[o] >> 16); }
+template <class SM> __device__ __forceinline__ int obs_read(const SM* sm, int o) { return (int)(sm->o_read[o] & 0xffffu); }
+template <class SM> __device__ __forceinline__ int obs_alen(const SM* sm, int o) { return (int)(sm->o_read[o] >> 16); }
 
 // CalledGenomicVariant.__eq__ (variants.py:83-96) between two observations of the same column: type, length
 // and allele bases.  Alleles up to 16 bases are decided by the stored signature, longer ones re-read the records.
-__device__ __forceinline__ bool obs_equal2(const SessCtx& c, const Smem2* sm, int a, int b) {
+template <class SM> __device__ __forceinline__ bool obs_equal2(const SessCtx& c, const SM* sm, int a, int b) {
     if (((sm->o_meta[a] ^ sm->o_meta[b]) & (kMetaIns | kMetaLenMask)) != 0u) return false;
     const int na = obs_alen(sm, a);
     if (na != obs_alen(sm, b) || sm->o_sig0[a] != sm->o_sig0[b] || sm->o_sig1[a] != sm->o_sig1[b]) return false;
@@ -432,7 +432,7 @@ __device__ __forceinline__ bool obs_equal2(const SessCtx& c, const Smem2* sm, in
     return true;
 }
 
-__device__ bool obs_equals_keep2(const SessCtx& c, const Smem2* sm, int a) {
+template <class SM> __device__ bool obs_equals_keep2(const SessCtx& c, const SM* sm, int a) {
     const uint32_t m = sm->o_meta[a];
     const int type = (m & kMetaIns) ? GA_VT_INS : GA_VT_DEL;
     const int len = (int)(m & kMetaLenMask);
@@ -455,7 +455,7 @@ __device__ bool obs_equals_keep2(const SessCtx& c, const Smem2* sm, int a) {
 // Python slicing applies them (anonymizer_methods.py:186-195).  The read's germline observations hang on
 // mhead[k]; their slots ascend in CIGAR order (one thread allocated them), so sorting by slot restores it.
 // Returns the new length.
-__device__ __noinline__ int collect_edits(const SessCtx& c, const Smem2* sm, int k, int L, Edit* edits, int* n_edits, int* n_dels, bool* too_many) {
+template <class SM> __device__ __noinline__ int collect_edits(const SessCtx& c, const SM* sm, int k, int L, Edit* edits, int* n_edits, int* n_dels, bool* too_many) {
     int16_t slots[GA_MAX_EDITS];
     int ns = 0;
 #pragma unroll 1
@@ -716,7 +716,7 @@ __device__ __forceinline__ int clamp_edits2(Ed2& E, int L) {
 
 // Germline indel edits of modified read k when there are at most two; false otherwise.  Same ordering and
 // clamping rules as collect_edits.
-__device__ __forceinline__ bool collect2(const SessCtx& c, const Smem2* sm, int k, int L, Ed2& E, int* new_len) {
+template <class SM> __device__ __forceinline__ bool collect2(const SessCtx& c, const SM* sm, int k, int L, Ed2& E, int* new_len) {
     const int oa = sm->mhead[k];
     const int ob = oa >= 0 ? (int)sm->o_rnext[oa] : -1;
     if (ob >= 0 && sm->o_rnext[ob] >= 0) return false;

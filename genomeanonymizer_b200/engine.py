@@ -158,9 +158,10 @@ class Engine:
         k = int(self._L.ga_kernel_ms_history(self._h, buf, n))
         return [float(buf[i]) for i in range(k)]
 
-    def emit_ms_history(self, n: int = 32):
+    def stage_ms_history(self, stage: int, n: int = 32):
+        """stage: 0 scan, 1 resolve, 2 fallback, 3 emission kernel."""
         buf = (C.c_float * n)()
-        k = int(self._L.ga_emit_ms_history(self._h, buf, n))
+        k = int(self._L.ga_stage_ms_history(self._h, stage, buf, n))
         return [float(buf[i]) for i in range(k)]
 
     def upload_reference(self, contig_id: int, bases) -> None:

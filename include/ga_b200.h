@@ -183,12 +183,13 @@ int64_t ga_launch_count(const ga_engine* e);
 /* Duration in milliseconds of the session kernel in the most recent ga_run() on this engine, measured
  * with CUDA events on the launching stream (synchronises that stream). */
 float ga_last_kernel_ms(ga_engine* e);
-/* Durations (ms) of the session kernel in the most recent ga_run() calls, out[0] = latest; returns how many
- * were written (at most min(n, 32)).  Synchronises on the recorded events. */
+/* Durations (ms) of the whole masking pass (scan + resolve + fallback + emission kernels) of the most recent
+ * ga_run() calls, out[0] = latest; returns how many were written (at most min(n, 32)).  Synchronises on the
+ * recorded events. */
 int   ga_kernel_ms_history(ga_engine* e, float* out, int n);
-/* Same for what follows the session kernel in a ga_run(): the fallback kernel for oversize sessions and the
- * emission kernel that writes the compacted record bodies. */
-int   ga_emit_ms_history(ga_engine* e, float* out, int n);
+/* Same per stage: 0 = scan kernel (allele discovery), 1 = resolve kernel (germline set, record list, headers),
+ * 2 = fallback kernel for oversize sessions, 3 = emission kernel (record bodies). */
+int   ga_stage_ms_history(ga_engine* e, int stage, float* out, int n);
 
 /* ------------------------------------------------------------------ end-to-end host entry
  * ga_run_host: all pointers are HOST pointers (pinned for full speed).  Splits the session table into

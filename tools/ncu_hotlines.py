@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Top source lines by warp-stall samples from an .ncu-rep (needs -lineinfo and --import-source on).
 
-usage: tools/ncu_hotlines.py REPORT.ncu-rep [N]
+usage: tools/ncu_hotlines.py REPORT.ncu-rep [N] [KERNEL_REGEX] [samples|inst]
 """
 import csv
 import subprocess
@@ -11,8 +11,12 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"],
-                         capture_output=True, text=True).stdout
+    kern = sys.argv[3] if len(sys.argv) > 3 else None
+    by_inst = len(sys.argv) > 4 and sys.argv[4] == "inst"
+    cmd = ["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"]
+    if kern:
+        cmd += ["--kernel-name", "regex:" + kern]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     fname, hdr, data = None, None, []
     for r in rows:
@@ -32,7 +36,7 @@ def main():
     tot = sum(d[0] for d in data) or 1
     toti = sum(d[1] for d in data) or 1
     print(f"total samples {tot}, warp instructions {toti}")
-    for n, ie, f, ln, src in sorted(data, reverse=True)[:top]:
+    for n, ie, f, ln, src in sorted(data, key=(lambda d: d[1]) if by_inst else (lambda d: d[0]), reverse=True)[:top]:
         print(f"{n:7d} {100 * n / tot:5.1f}%  inst {100 * ie / toti:5.1f}%  {f}:{ln:<4d} {src}")
 
 
