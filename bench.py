@@ -257,6 +257,7 @@ def main():
         h = [x for x in eng.stage_ms_history(st, min(args.steps, 32)) if x >= 0]
         stage_ms.append(sum(h) / len(h) if h else float("nan"))
     eng.check_device_status(dres)
+    n_fallback, fallback_reasons = eng.fallback_sessions()
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     work = torch.tensor([session_reads, session_bases, launches], dtype=torch.int64, device=dev)
     if world > 1:
@@ -285,9 +286,9 @@ def main():
     scan_bytes = single - (int(tot.n_modified) * 20 + 2 * 16 * int(tot.seq16_used) + 2 * 32 * int(tot.qual16_used))
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "kernel": "masking pass = scan_kernel + resolve_kernel + session_kernel<fallback> + emit_kernel", "kernel_ms": pass_ms,
-                "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernel": stage_ms[1], "fallback_kernel": stage_ms[2],
-                             "emit_kernel": stage_ms[3]},
+                "kernel": "masking pass = scan_kernel + resolve_lean_kernel + resolve_kernel + emit_kernel (|| session_kernel<fallback>)", "kernel_ms": pass_ms,
+                "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernels": stage_ms[1], "emit_kernel": stage_ms[2],
+                             "fallback_kernel_tail": stage_ms[3]},
                 "scan_kernel_gbs": scan_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else None,
                 "kernel_share_of_step": pass_ms / (ms / args.steps),
                 "algorithmic_bytes_per_launch": single, "bytes_per_session_read": single / max(1, session_reads),
@@ -349,7 +350,8 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": cfg.name, "windows_per_gpu": n_w, "read_len": cfg.read_len,
                            "coverage": [cfg.cov_tumor, cfg.cov_normal], "session_reads_per_gpu": session_reads,
-                           "modified_records_per_gpu": int(tot.n_modified), "masked_snv_del_ins": [int(x) for x in tot.masked],
+                           "modified_records_per_gpu": int(tot.n_modified),
+                           "fallback_sessions_per_gpu": n_fallback, "fallback_reasons": fallback_reasons, "masked_snv_del_ins": [int(x) for x in tot.masked],
                            "sharding": "one contig-sized region per GPU, no data-path collective" if world > 1 else "single GPU",
                            "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
                 "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),

@@ -3,11 +3,14 @@
 //
 // The resolve kernel (ga_resolve_kernel.cuh) decides WHAT changes: it allocates the output slots, writes the record
 // headers and hands over, per record, a 16-byte descriptor and, per session, the list of germline SNV alleles.
-// This kernel writes the record bodies with full-chip parallelism and no block-level synchronisation.  A warp takes
-// 32 records at a time: their descriptors and germline lists arrive with two coalesced round trips, then a group
-// of 8 lanes copies each record with 128-bit loads / stores (four records per warp step).
-//   kind 1  clean read, SNV-only   copy, replacing every base whose allele is germline by the reference base
+// These kernels write the record bodies with full-chip parallelism and no block-level synchronisation.
+// emit_kernel: a warp takes 32 records at a time: kinds and descriptors arrive with two coalesced round trips, then
+// a group of 8 lanes copies and patches each record of kind 1 with 128-bit loads / stores (four records per step).
+// emit_special_kernel: the records of the other kinds, densely from the list the resolve kernels packed.
+//   kind 1  clean read, SNV-only   copy; the (at most two) bases whose allele is germline arrive in the descriptor
+//                                  together with the reference base that replaces them
 //                                  (anonymizer_methods.py:170-176); qualities untouched
+//   kind 4  same, any number of hits: every mismatch is looked up in the session's germline list
 //   kind 2  other CIGAR, SNV-only  same, walking the CIGAR per 8-base word
 //   kind 3  indel-masked           all DELs then all INSs at original offsets with the quality rules of
 //                                  anonymizer_methods.py:178-203, 254-270 (emit_indel_group_t)
@@ -33,84 +36,107 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
     const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (tid >> 5);
     const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * 32;
     for (int64_t k0 = warp_global * 32; k0 < n; k0 += stride) {
-        // ---- lane = record: descriptor, output slot and the session's germline list (two round trips)
+        // ---- lane = record: kind, descriptor and output slot (two coalesced round trips)
         const int64_t k = k0 + lane;
         const uint32_t kind = k < n ? E.kind[k] : 0u;
-        uint4 d = make_uint4(0u, 0u, 0u, 0u), gh = d, ga = d;
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);
         uint32_t dst16 = 0u;
-        if (kind) { d = E.edesc[k]; dst16 = O.mod_seq_off16[k]; }
-        if (kind) {
-            const uint4* gp = reinterpret_cast<const uint4*>(E.germ + (size_t)d.w * kGermStride);
-            gh = __ldg(gp); ga = __ldg(gp + 1);
-        }
-        const uint32_t m1 = __ballot_sync(0xffffffffu, kind == 1u), mx = __ballot_sync(0xffffffffu, kind >= 2u);
-        // ---- kind 1: four records per step, 8 lanes each
+        if (kind == 1u) { d = E.edesc[k]; dst16 = O.mod_seq_off16[k]; }
+        const uint32_t m1 = __ballot_sync(0xffffffffu, kind == 1u);
+        // ---- kind 1: copy + patch, four records per step, 8 lanes each
 #pragma unroll 2
         for (int step = 0; step < 8; ++step) {
             if (!((m1 >> (4 * step)) & 0xfu)) continue;
             const int rr = 4 * step + gw;
             const uint32_t r_kind = __shfl_sync(0xffffffffu, kind, rr);
             const uint32_t r_src = __shfl_sync(0xffffffffu, d.x, rr);
-            const int r_pos = (int)__shfl_sync(0xffffffffu, d.y, rr);
-            const int L = (int)__shfl_sync(0xffffffffu, d.z, rr);
+            const int rel0 = (int)__shfl_sync(0xffffffffu, d.y, rr);
+            const uint32_t lz = __shfl_sync(0xffffffffu, d.z, rr);
+            const uint32_t hits = __shfl_sync(0xffffffffu, d.w, rr);
             const uint32_t r_dst = __shfl_sync(0xffffffffu, dst16, rr);
-            const uint32_t g_n = __shfl_sync(0xffffffffu, gh.x, rr);
-            const int col_begin = (int)__shfl_sync(0xffffffffu, gh.y, rr);
-            const uint32_t a0 = __shfl_sync(0xffffffffu, ga.x, rr), a1 = __shfl_sync(0xffffffffu, ga.y, rr);
-            const uint32_t a2 = __shfl_sync(0xffffffffu, ga.z, rr), a3 = __shfl_sync(0xffffffffu, ga.w, rr);
-            const uint32_t r_s = __shfl_sync(0xffffffffu, d.w, rr);
             if (r_kind != 1u) continue;
+            const int L = (int)(lz & 0xffffu), nh = (int)(lz >> 16);
             const uint4* rec = reinterpret_cast<const uint4*>(B.seq4 + 16ull * r_src);
             uint4* out = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * r_dst);
             const int units = (L + 31) >> 5;
+            const int q0 = (int)((hits >> 4) & 0xfffu) - rel0, q1 = nh > 1 ? (int)(hits >> 20) - rel0 : -1;
+            const uint32_t f0 = hits & 15u, f1 = (hits >> 16) & 15u;
             for (int u = glane; u < units; u += kGroup) {
-                const uint4 vv = ldg128(rec + u);
-                const int64_t ni = (int64_t)r_pos + 32 * u + 8;
-                const uint32_t* rp = B.ref4 + (ni >> 3);
-                const uint32_t sh = (uint32_t)(ni & 7) * 4u;
-                const uint32_t r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3), r4 = __ldg(rp + 4);
-                uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
-                const uint32_t f[4] = {__funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh), __funnelshift_r(r2, r3, sh), __funnelshift_r(r3, r4, sh)};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int wi = 4 * u + q;
-                    const uint32_t tm = tail_mask(L, wi);
-                    uint32_t v = w[q] & tm;
-                    uint32_t x = (v ^ f[q]) & tm;
-                    while (x) {
-                        const int nb = (__ffs(x) - 1) >> 2;
-                        x &= ~(0xfu << (nb * 4));
-                        const uint32_t b = (v >> (nb * 4)) & 15u;
-                        if (b == 15u) continue;
-                        const uint32_t key = ((uint32_t)(r_pos + 8 * wi + nb - col_begin) << 4) | b;
-                        bool hit = (g_n > 0u && key == a0) || (g_n > 1u && key == a1) || (g_n > 2u && key == a2) || (g_n > 3u && key == a3);
-                        for (uint32_t e = 4; e < g_n && !hit; ++e) hit = __ldg(E.germ + (size_t)r_s * kGermStride + 4 + e) == key;
-                        if (hit) v = (v & ~(0xfu << (nb * 4))) | (((f[q] >> (nb * 4)) & 15u) << (nb * 4));
-                    }
-                    w[q] = v;
+                uint4 v = ldg128(rec + u);
+                if (32 * u + 32 > L) { v.x &= tail_mask(L, 4 * u); v.y &= tail_mask(L, 4 * u + 1); v.z &= tail_mask(L, 4 * u + 2); v.w &= tail_mask(L, 4 * u + 3); }
+                if ((q0 >> 5) == u) {                                  // anonymizer_methods.py:170-176: base <- reference base
+                    const uint32_t sh = (uint32_t)(q0 & 7) * 4u, keepm = ~(0xfu << sh), ins = f0 << sh;
+                    const int w = (q0 >> 3) & 3;
+                    if (w == 0) v.x = (v.x & keepm) | ins; else if (w == 1) v.y = (v.y & keepm) | ins;
+                    else if (w == 2) v.z = (v.z & keepm) | ins; else v.w = (v.w & keepm) | ins;
                 }
-                out[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                if (q1 >= 0 && (q1 >> 5) == u) {
+                    const uint32_t sh = (uint32_t)(q1 & 7) * 4u, keepm = ~(0xfu << sh), ins = f1 << sh;
+                    const int w = (q1 >> 3) & 3;
+                    if (w == 0) v.x = (v.x & keepm) | ins; else if (w == 1) v.y = (v.y & keepm) | ins;
+                    else if (w == 2) v.z = (v.z & keepm) | ins; else v.w = (v.w & keepm) | ins;
+                }
+                out[u] = v;
             }
         }
-        // ---- kinds 2 and 3 (reads with other CIGARs): one group of 8 lanes each, the read's arrays re-read
-        if (mx) {
-            int32_t my_r = 0; uint32_t my_len = 0u, my_q16 = 0u;
-            if (kind >= 2u) { my_r = O.mod_read[k]; my_len = O.mod_len[k]; my_q16 = O.mod_qual_off16[k]; }
-            for (int step = 0; step < 8; ++step) {
-                if (!((mx >> (4 * step)) & 0xfu)) continue;
-                const int rr = 4 * step + gw;
-                const uint32_t r_kind = __shfl_sync(0xffffffffu, kind, rr);
-                const int64_t r = (int64_t)__shfl_sync(0xffffffffu, my_r, rr);
-                const int new_len = (int)__shfl_sync(0xffffffffu, my_len, rr);
-                const uint64_t seq16 = __shfl_sync(0xffffffffu, dst16, rr), qual16 = __shfl_sync(0xffffffffu, my_q16, rr);
-                const int s = (int)__shfl_sync(0xffffffffu, d.w, rr);
-                const int col_begin = (int)__shfl_sync(0xffffffffu, gh.y, rr);
-                GermList germ; germ.e = E.germ + (size_t)s * kGermStride + 4; germ.n = __shfl_sync(0xffffffffu, gh.x, rr);
+    }
+}
+
+// Records of kind >= 2 (reads with other CIGARs, reads with many hits), taken densely from the list the resolve
+// kernels packed: four records per warp step, one group of 8 lanes each.
+__global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
+    __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
+    const int tid = threadIdx.x, group = tid / kGroup, glane = tid % kGroup;
+    const uint32_t n_x = *E.n_special;
+    const uint32_t groups_total = gridDim.x * (kThreads / kGroup);
+    for (uint32_t jb = blockIdx.x * (kThreads / kGroup) + (tid >> 5) * 4; jb < n_x; jb += groups_total) {   // warp-uniform
+        const uint32_t j = jb + ((tid & 31) >> 3);
+        const bool have = j < n_x;
+        const int64_t k = have ? (int64_t)E.special[j] : 0;
+        const uint32_t r_kind = have ? E.kind[k] : 0u;
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);
+        int64_t r = 0; int new_len = 0; uint64_t seq16 = 0, qual16 = 0;
+        if (r_kind) { d = E.edesc[k]; r = O.mod_read[k]; new_len = (int)O.mod_len[k]; seq16 = O.mod_seq_off16[k]; qual16 = O.mod_qual_off16[k]; }
+        const uint32_t r_src = d.x; const int r_pos = (int)d.y; const int s = (int)d.w;
+        int col_begin = 0;
+        GermList germ; germ.e = E.germ + (size_t)s * kGermStride + 4; germ.n = 0u;
+        if (r_kind) { germ.n = __ldg(E.germ + (size_t)s * kGermStride); col_begin = (int)__ldg(E.germ + (size_t)s * kGermStride + 1); }
+        {
+                if (r_kind == 4u) {
+                    const int L = new_len;
+                    const uint4* rec = reinterpret_cast<const uint4*>(B.seq4 + 16ull * r_src);
+                    uint4* out = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * seq16);
+                    const int units = (L + 31) >> 5;
+                    for (int u = glane; u < units; u += kGroup) {
+                        const uint4 vv = ldg128(rec + u);
+                        const int64_t ni = (int64_t)r_pos + 32 * u + 8;
+                        const uint32_t* rp = B.ref4 + (ni >> 3);
+                        const uint32_t sh = (uint32_t)(ni & 7) * 4u;
+                        const uint32_t r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3), r4 = __ldg(rp + 4);
+                        uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+                        const uint32_t f[4] = {__funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh), __funnelshift_r(r2, r3, sh), __funnelshift_r(r3, r4, sh)};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int wi = 4 * u + q;
+                            const uint32_t tm = tail_mask(L, wi);
+                            uint32_t v = w[q] & tm;
+                            uint32_t x = (v ^ f[q]) & tm;
+                            while (x) {
+                                const int nb = (__ffs(x) - 1) >> 2;
+                                x &= ~(0xfu << (nb * 4));
+                                const uint32_t b = (v >> (nb * 4)) & 15u;
+                                if (b != 15u && germ(r_pos + 8 * wi + nb - col_begin, b)) v = (v & ~(0xfu << (nb * 4))) | (((f[q] >> (nb * 4)) & 15u) << (nb * 4));
+                            }
+                            w[q] = v;
+                        }
+                        out[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
                 if (r_kind == 2u) {
                     const uint32_t c0 = __ldg(B.cigar_off + r), c1 = __ldg(B.cigar_off + r + 1);
                     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
                     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-                    masked_words_g(B, r, __ldg(B.pos + r), new_len, c0, c1, col_begin, units * 4, glane, kGroup, germ, [&](int wd, uint32_t v) { oseq[wd] = v; });
+                    masked_words_g(B, r, r_pos, new_len, c0, c1, col_begin, units * 4, glane, kGroup, germ, [&](int wd, uint32_t v) { oseq[wd] = v; });
                 }
                 const bool indel = r_kind == 3u;
                 if (__any_sync(0xffffffffu, indel)) {
@@ -134,6 +160,4 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
             }
         }
     }
-}
-
 }  // namespace ga

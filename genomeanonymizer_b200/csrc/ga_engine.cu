@@ -106,13 +106,14 @@ __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* _
         d.qn_begin = lower_bound_pos(B.qual_reads, d.qt_end, B.n_qual, d.n_begin); d.qn_end = lower_bound_pos(B.qual_reads, d.qn_begin, B.n_qual, d.n_end);
     }
     descs[s] = d;
-    if (d.big) big_list[atomicAdd(n_big, 1)] = s;
+    if (d.big) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4, 1); }
 }
 
 __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* tickets, int32_t* maxspan, int32_t given_span) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         memset(totals, 0, sizeof(ga_totals));
         *n_big = 0; tickets[0] = 0; tickets[1] = 0; *maxspan = given_span;
+        for (int k = 4; k < 14; ++k) n_big[k] = 0;                    // fallback reasons, n_large, n_special
     }
 }
 
@@ -162,11 +163,18 @@ int ga_engine_create(int device, ga_engine** out) {
     for (int l = 0; l < kLanes; ++l) {
         if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) cudaEventCreate(&e->lanes[l].ev[j][k]);
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&e->lanes[l].side, cudaStreamNonBlocking, hi);
+        cudaEventCreateWithFlags(&e->lanes[l].ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->lanes[l].ev_join, cudaEventDisableTiming);
     }
     cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::WarpSmem) * (ga::kScanThreads / 32)));
     cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemR));
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemL) * ga::kLeanWarps));
+    cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = e;
     return GA_OK;
 }
@@ -179,8 +187,11 @@ void ga_engine_destroy(ga_engine* e) {
     for (auto& kv : e->refs) cudaFree(kv.second.d_ref4);
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = e->lanes[l];
-        cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
+        cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
+        if (L.side) cudaStreamDestroy(L.side);
+        if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+        if (L.ev_join) cudaEventDestroy(L.ev_join);
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) if (L.ev[j][k]) cudaEventDestroy(L.ev[j][k]);
     }
     delete e;
@@ -218,21 +229,23 @@ int ga_upload_reference(ga_engine* e, int contig_id, const uint8_t* bases, int64
 
 static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
     if (n_sessions <= L.cap_sessions) return GA_OK;
-    cudaFree(L.d_descs); cudaFree(L.d_big_list);
-    L.d_descs = nullptr; L.d_big_list = nullptr; L.cap_sessions = 0;
+    cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list);
+    L.d_descs = nullptr; L.d_big_list = nullptr; L.d_large_list = nullptr; L.cap_sessions = 0;
     const int64_t cap = n_sessions + n_sessions / 4 + 1024;
     GA_CUDA(cudaMalloc(&L.d_descs, (size_t)cap * sizeof(ga::SessionDesc)));
     GA_CUDA(cudaMalloc(&L.d_big_list, (size_t)cap * sizeof(int32_t)));
+    GA_CUDA(cudaMalloc(&L.d_large_list, (size_t)cap * sizeof(int32_t)));
     L.cap_sessions = cap;
     return GA_OK;
 }
 
 static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int64_t n_sessions) {
     if (cap_records > L.cap_kind) {
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); L.d_kind = nullptr; L.d_edesc = nullptr; L.cap_kind = 0;
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); L.d_kind = nullptr; L.d_edesc = nullptr; L.d_special = nullptr; L.cap_kind = 0;
         const int64_t cap = cap_records + cap_records / 8 + 1024;
         GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
         GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
+        GA_CUDA(cudaMalloc(&L.d_special, (size_t)cap * sizeof(uint32_t)));
         L.cap_kind = cap;
     }
     if (n_sessions > L.cap_germ) {
@@ -284,6 +297,15 @@ int ga_kernel_ms_history(ga_engine* e, float* out, int n) { return stage_history
 int ga_stage_ms_history(ga_engine* e, int stage, float* out, int n) {
     if (stage < 0 || stage > 3) return 0;
     return stage_history(e, stage, stage + 1, out, n);
+}
+
+int ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons) {
+    if (!e) return -1;
+    int32_t h[16] = {0};
+    if (cudaSetDevice(e->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(h, e->lanes[0].d_small, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int k = 0; reasons && k < n_reasons && k < 9; ++k) reasons[k] = h[4 + k];
+    return h[0];
 }
 
 float ga_last_kernel_ms(ga_engine* e) {
@@ -342,6 +364,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     rc = ensure_stream_scratch(e, L, out->cap_records, S->n_sessions); if (rc) return rc;
     ga::ScanScratch X; X.ent = L.d_ent; X.obs = reinterpret_cast<ga::ObsRec*>(L.d_obs); X.cnt = reinterpret_cast<uint4*>(L.d_cnt);
     ga::EmitScratch2 E; E.kind = L.d_kind; E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
+    E.special = L.d_special; E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;
@@ -351,17 +374,27 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     GA_CUDA(cudaEventRecord(L.ev[0][tslot], st));
     ga::scan_kernel<<<grid_scan, ga::kScanThreads, sizeof(ga::WarpSmem) * (ga::kScanThreads / 32), st>>>(B, V, L.d_descs, X, d_tickets, out->totals);
     GA_CUDA(cudaEventRecord(L.ev[1][tslot], st));
-    // stage 2: germline set, modified-record list, output slots, headers
+    // stage 2: germline set, modified-record list, output slots, headers - one warp per session, then one CTA per
+    // session for those whose tables did not fit the lean capacities
+    int32_t* d_nlarge = L.d_small + 12;
+    const int lean_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * 8, (S->n_sessions + ga::kLeanWarps - 1) / ga::kLeanWarps);
+    ga::resolve_lean_kernel<<<lean_ctas, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
     const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * 7, S->n_sessions);
-    ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, X, E);
+    ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
     GA_CUDA(cudaEventRecord(L.ev[2][tslot], st));
-    // oversize sessions and whatever the tables of stages 1-2 could not hold: global-scratch kernel, complete records
-    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
-    GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
+    // oversize sessions and whatever the tables of stages 1-2 could not hold: global-scratch kernel, complete records;
+    // it runs on a side stream beside stage 3 (it only appends records, which the emission kernel skips)
+    GA_CUDA(cudaEventRecord(L.ev_fork, st));
+    GA_CUDA(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
+    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
+    GA_CUDA(cudaEventRecord(L.ev_join, L.side));
     // stage 3: record bodies
     ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
+    ga::emit_special_kernel<<<e->n_sm * 4, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
+    GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
+    GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
-    e->launches += 4;
+    e->launches += 6;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

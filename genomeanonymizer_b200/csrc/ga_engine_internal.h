@@ -10,16 +10,17 @@ struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
 
 // Scratch of one in-flight ga_run: two lanes let the host pipeline overlap consecutive chunks.
 struct Lane {
-    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int64_t cap_sessions = 0;
-    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, then tickets (2 x u32)
+    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int32_t* d_large_list = nullptr; int64_t cap_sessions = 0;
+    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the fallback kernel runs beside the emission kernel
     uint8_t* d_big_scratch = nullptr;
     // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)
     uint32_t* d_ent = nullptr; void* d_obs = nullptr; void* d_cnt = nullptr; int64_t cap_items = 0;
-    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; int64_t cap_kind = 0;
+    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; uint32_t* d_special = nullptr; int64_t cap_kind = 0;
     uint32_t* d_germ = nullptr; int64_t cap_germ = 0;
     // CUDA events between the stages of the most recent kTimedRuns runs (ring), recorded on the launching stream so
     // bench.py can read per-launch durations after its timed region without syncing inside it:
-    // ev[0] start | scan | ev[1] | resolve | ev[2] | fallback | ev[3] | emission | ev[4]
+    // ev[0] start | scan | ev[1] | resolve (lean + large) | ev[2] | emission | ev[3] | wait for the fallback kernel | ev[4]
     cudaEvent_t ev[5][32] = {};
     int64_t runs = 0;
 };

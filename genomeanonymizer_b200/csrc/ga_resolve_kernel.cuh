@@ -1,14 +1,17 @@
-// ga_resolve_kernel.cuh - stage 2 of the streaming pipeline: one small CTA per session turns the scan kernel's
+// ga_resolve_kernel.cuh - stage 2 of the streaming pipeline: one warp (lean variant, below) or one small CTA (large
+// variant, for sessions whose tables do not fit the lean capacities) per session turns the scan kernel's
 // candidate entries and indel observations into the germline set (seen in tumor AND normal, minus
 // variant_to_keep: anonymizer_methods.py:546-547, variants.py:83-96), the ordered list of modified reads, their
 // new lengths and their slots in the compacted output (north_star jobs (1) + (4)); it writes the record headers,
 // the per-session counters (= AnonymizedVariantsStatistics.window_var_counts) and the hand-over to the emission
 // kernel (ga_emit_kernel.cuh), which writes the record bodies.
 //
-// 128 threads, ~30 KB of shared memory -> 7 CTAs per SM; per session three dependent memory round trips
-// (descriptor + counts, entries, per-record meta) and a handful of 4-warp barriers.
+// Large variant: 128 threads, ~30 KB of shared memory -> 7 CTAs per SM; per session a few dependent memory round
+// trips (descriptor + counts, entries, per-record meta) and a handful of 4-warp barriers.
 // Anything the shared-memory tables cannot hold (or describe to the emission kernel) sends the whole session to
-// the global-scratch fallback kernel (ga_session_kernel.cuh) through big_list.
+// the global-scratch fallback kernel (ga_session_kernel.cuh) through big_list; n_big[4 + reason] counts why
+// (1 scan-kernel overflow, 2 IUPAC read base, 3 more modified reads / germline alleles than the tables hold,
+// 4 a read with more than two germline indels; 0 = oversize session found by the assignment kernel).
 #pragma once
 #include "ga_scan_kernel.cuh"
 
@@ -22,13 +25,17 @@ constexpr int kGermStride = kGermCap + 4;   // per session: [0] germline SNV all
 static_assert(kReads2 / 32 <= kResThreads, "phase L gives every bitmap word its own thread");
 
 // Hand-over to the emission kernel.  kind[k] of output record k: 0 = nothing to do (record written by the fallback
-// kernel), 1 = clean read, SNV-only: copy + patch, 2 = other CIGAR, SNV-only: re-walk, 3 = indel-masked with at
-// most two edits (their description sits in the first 32 bytes of the record's out_qual slot until the emission
-// kernel overwrites it with the qualities).
+// kernel), 1 = clean read, SNV-only, at most two germline hits: copy + patch from the descriptor, 2 = other CIGAR,
+// SNV-only: re-walk, 3 = indel-masked with at most two edits (their description sits in the first 32 bytes of the
+// record's out_qual slot until the emission kernel overwrites it with the qualities), 4 = clean read, SNV-only:
+// copy, looking every mismatch up in the session's germline list.
 struct EmitScratch2 {
     uint8_t* kind;       // [cap_records]
-    uint4* edesc;        // [cap_records] {source record unit, pos, original length, session}
+    uint4* edesc;        // [cap_records] kind 1: {source record unit, pos - col_begin, length | hits << 16, two hits ((column << 4) | reference code)}
+                         //               else:   {source record unit, pos, length, session}
     uint32_t* germ;      // [n_sessions][kGermStride]
+    uint32_t* special;   // [cap_records] indices of the records of kind >= 2, packed (emit_special_kernel walks them densely)
+    uint32_t* n_special;
 };
 
 struct SmemR {
@@ -80,6 +87,7 @@ __device__ __forceinline__ int acgt_index(uint32_t b) { return b == 1u ? 0 : b =
 
 __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                  int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
+                                                                 const int32_t* __restrict__ large_list, const int32_t* __restrict__ n_large,
                                                                  ResultView O, ScanScratch X, EmitScratch2 E) {
     constexpr int T = kResThreads;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -96,7 +104,9 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t round = 0;
 
-    for (int s = blockIdx.x; s < S.n_sessions; s += gridDim.x, ++round) {
+    const int n_list = *n_large;                                      // sessions the lean kernel handed over
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x, ++round) {
+        const int s = large_list[li];
         c.d = descs[s];
         if (c.d.big) continue;                                        // listed by the assignment kernel
         const uint4 cnt0 = X.cnt[2 * (size_t)s], cnt1 = X.cnt[2 * (size_t)s + 1];
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
         const int n_cols = c.d.n_cols;
         const int n_cw = (c.n_range + 31) >> 5;
         if (cnt0.x == kCntOverflow || cnt1.x == kCntOverflow) {       // the scan kernel could not hold the session
-            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            if (tid == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 1, 1); }
             continue;
         }
         const int n_ent0 = (int)cnt0.x, n_ent = n_ent0 + (int)cnt1.x;
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
         __syncthreads();
         if (s_overflow) {
             __syncthreads();
-            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            if (tid == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 2, 1); }
             continue;
         }
 
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
         }
         if (n_mod > (uint32_t)kMod2 || s_ngerm > (uint32_t)kGermCap) {
             __syncthreads();
-            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            if (tid == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 3, 1); }
             continue;
         }
         __syncthreads();
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
         const unsigned long long off = block_scan64<T>(mine, s_scan64[round & 1u], &total);
         if (s_overflow) {
             __syncthreads();
-            if (tid == 0) big_list[atomicAdd(n_big, 1)] = s;
+            if (tid == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 4, 1); }
             continue;
         }
         const uint32_t tot_rec = (uint32_t)(total >> 48), tot_seq = (uint32_t)((total >> 24) & 0xffffffu), tot_qual = (uint32_t)(total & 0xffffffu);
@@ -335,9 +345,10 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
             const uint32_t qual16 = q ? (uint32_t)(s_base[2] + sm->mqual[k]) : 0xffffffffu;
             write_record_meta(O, rec_idx, s, r, (int)(m & kLen2), s_base[1] + sm->mseq[k], qual16);
             const uint32_t lf = __ldg(B.len_flag + r);
-            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : 1);
+            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : 4);
             E.kind[rec_idx] = kind;
             E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)__ldg(B.pos + r), lf & 0xffffu, (uint32_t)s);
+            E.special[atomicAdd(E.n_special, 1u)] = (uint32_t)rec_idx;
             if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
                 collect2(c, sm, k, (int)(lf & 0xffffu), E2, &nl);
@@ -351,6 +362,356 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
             }
         }
         __syncthreads();                                              // tables and flags are reused by the next session
+    }
+}
+
+}  // namespace ga
+
+// ====================================================================================================================
+// Lean variant: ONE WARP per session, no block barrier, ~11 KB of shared memory per warp (18 warps per SM).
+// Takes every session whose tables fit the small capacities below (the normal case); the others are listed in
+// large_list for the CTA-per-session kernel above.  Clean SNV-only records get their (at most two) germline hits
+// written into the emission descriptor (kind 1), so the emission kernel copies and patches without touching the
+// reference or the germline list.
+namespace ga {
+
+constexpr int kLeanWarps = 2;            // warps per CTA
+constexpr int kReadsL = 2048;            // candidate reads per session
+constexpr int kModL = 384;               // modified reads per session
+constexpr int kObsL = 96;                // indel observations per session
+
+struct SmemL {
+    uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
+    uint32_t modbits[kReadsL / 32], indelbits[kReadsL / 32], genbits[kReadsL / 32], woff[kReadsL / 32];
+    uint32_t msize[kModL];
+    uint32_t moff[kModL];                // session-relative sequence unit | quality unit << 16
+    uint32_t mpatch[kModL];              // two germline hits of a clean read: (column << 4) | reference code, 16 bits each
+    int32_t mhead[kModL];                // per modified read: chain of its germline indel observations
+    uint16_t clist[kModL];
+    uint8_t mpc[kModL];                  // germline SNV hits per modified read
+    uint32_t o_meta[kObsL], o_ra[kObsL], o_s0[kObsL], o_s1[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
+    uint32_t ngerm, pad[3];
+};
+static_assert(sizeof(SmemL) % 16 == 0, "per-warp slices stay 16-byte aligned");
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
+__global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+                                                                        int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
+                                                                        int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
+                                                                        ResultView O, ScanScratch X, EmitScratch2 E) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SmemL* sm = reinterpret_cast<SmemL*>(smem_raw) + warp;
+    SessCtx c;
+    c.B = B;
+    c.totals = O.totals;
+    memset(&c.T, 0, sizeof c.T);
+    const int n_warps = gridDim.x * kLeanWarps;
+
+    for (int s = blockIdx.x * kLeanWarps + warp; s < S.n_sessions; s += n_warps) {
+        // ---- round trip 1: descriptor, scan counts, variant_to_keep
+        uint32_t w1 = 0u, w2 = 0u;
+        if (lane < 20) w1 = __ldg(reinterpret_cast<const uint32_t*>(descs + s) + lane);
+        else if (lane < 28) w1 = __ldg(reinterpret_cast<const uint32_t*>(X.cnt + 2 * (size_t)s) + (lane - 20));
+        if (lane == 0) w2 = (uint32_t)__ldg(S.keep_type + s); else if (lane == 1) w2 = (uint32_t)__ldg(S.keep_pos + s);
+        else if (lane == 2) w2 = (uint32_t)__ldg(S.keep_end + s); else if (lane == 3) w2 = (uint32_t)__ldg(S.keep_len + s);
+        else if (lane == 4) w2 = __ldg(S.keep_allele_off + s); else if (lane == 5) w2 = __ldg(S.keep_allele_off + s + 1);
+        {
+            uint32_t* dd = reinterpret_cast<uint32_t*>(&c.d);
+#pragma unroll
+            for (int k = 0; k < 20; ++k) dd[k] = __shfl_sync(0xffffffffu, w1, k);
+        }
+        if (c.d.big) continue;                                        // listed by the assignment kernel
+        const uint32_t n_ent0 = __shfl_sync(0xffffffffu, w1, 20), n_obs0 = __shfl_sync(0xffffffffu, w1, 21);
+        const uint32_t n_ent1 = __shfl_sync(0xffffffffu, w1, 24), n_obs1 = __shfl_sync(0xffffffffu, w1, 25);
+        const uint32_t sess_reads = __shfl_sync(0xffffffffu, w1, 22) + __shfl_sync(0xffffffffu, w1, 26);
+        const uint32_t sess_bases = __shfl_sync(0xffffffffu, w1, 23) + __shfl_sync(0xffffffffu, w1, 27);
+        c.keep_type = (int)__shfl_sync(0xffffffffu, w2, 0); c.keep_pos = (int)__shfl_sync(0xffffffffu, w2, 1);
+        c.keep_end = (int)__shfl_sync(0xffffffffu, w2, 2); c.keep_len = (int)__shfl_sync(0xffffffffu, w2, 3);
+        const uint32_t ka0 = __shfl_sync(0xffffffffu, w2, 4), ka1 = __shfl_sync(0xffffffffu, w2, 5);
+        c.keep_allele = S.keep_alleles + ka0;
+        c.keep_alen = (int)(ka1 - ka0);
+        c.s = s;
+        c.nt = c.d.t_end - c.d.t_begin;
+        c.n_range = c.nt + (c.d.n_end - c.d.n_begin);
+        const int n_cols = c.d.n_cols;
+        const int n_cw = (c.n_range + 31) >> 5;
+        if (n_ent0 == kCntOverflow || n_ent1 == kCntOverflow) {       // the scan kernel could not hold the session
+            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 1, 1); }
+            continue;
+        }
+        const int n_obs = (int)(n_obs0 + n_obs1);
+        if (c.n_range > kReadsL || n_obs > kObsL) {
+            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+            continue;
+        }
+        // ---- zeroed tables; round trip 2: entries (pass 1: allele table), observations, keep allele
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(sm->tab);
+            for (int k = lane; k < ((n_cols + 15) >> 4); k += 32) t4[k] = make_uint4(0u, 0u, 0u, 0u);
+            for (int k = lane; k < n_cw; k += 32) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
+            if (lane == 0) sm->ngerm = 0u;
+        }
+        const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
+        const uint32_t* e1 = e0 + kEntHalf;
+        uint32_t keep_key = 0xffffffffu;                              // variant_to_keep as an SNV entry key
+        if (c.keep_type == GA_VT_SNV && c.keep_end == c.keep_pos && c.keep_len == 1 && c.keep_alen == 1) {
+            const int kc = c.keep_pos - c.d.col_begin;
+            if (kc >= 0 && kc < n_cols) {
+                const uint8_t ch = c.keep_allele[0];
+                const uint32_t code = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : 0u;
+                if (code) keep_key = ((uint32_t)kc << 4) | code;
+            }
+        }
+        for (int o = lane; o < n_obs; o += 32) {
+            const ObsRec* op = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
+            const uint4* src = reinterpret_cast<const uint4*>(o < (int)n_obs0 ? op + o : op + kObsHalf + (o - (int)n_obs0));
+            const uint4 a = __ldg(src), b = __ldg(src + 1);
+            sm->o_col[o] = (int)a.x; sm->o_meta[o] = a.y; sm->o_ra[o] = a.z; sm->o_irp[o] = (int)a.w; sm->o_s0[o] = b.x; sm->o_s1[o] = b.y;
+        }
+        __syncwarp();
+        bool bad = false;
+        for (uint32_t k = lane; k < n_ent0 + n_ent1; k += 32) {
+            const uint32_t e = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+            const uint32_t col = (e >> 4) & 0xfffu;
+            const int idx = acgt_index(e & 15u);
+            if (idx < 0) { bad = true; continue; }                     // IUPAC read base: the fallback kernel keeps all 16 codes
+            atomicOr(&sm->tab[col >> 2], 1u << (idx + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
+        }
+        if (__any_sync(0xffffffffu, bad)) {
+            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 2, 1); }
+            continue;
+        }
+        bool long_allele = false;
+        for (int o = lane; o < n_obs; o += 32) long_allele |= (sm->o_ra[o] >> 16) > 16u;
+        if (__any_sync(0xffffffffu, long_allele)) {                  // allele longer than the signature: compared by the large variant
+            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+            continue;
+        }
+        __syncwarp();
+        // ---- resolve + mark (pass 2 over the entries): germline = seen in tumor AND normal, minus variant_to_keep
+        for (uint32_t k = lane; k < n_ent0 + n_ent1; k += 32) {
+            const uint32_t e = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+            const uint32_t col = (e >> 4) & 0xfffu;
+            const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
+            const int idx = acgt_index(e & 15u);
+            if ((((byte & (byte >> 4)) >> idx) & 1u) && (e & 0xffffu) != keep_key) {
+                const uint32_t i = (e >> 16) & 0xfffu;
+                atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
+                if (e & kEntGen) atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
+            }
+        }
+        uint32_t cnt_snv = 0;
+        {   // distinct germline SNV alleles: the per-session counter and the emission kernel's list
+            const uint4* t4 = reinterpret_cast<const uint4*>(sm->tab);
+            for (int k4 = lane; k4 < ((n_cols + 15) >> 4); k4 += 32) {
+                const uint4 q = t4[k4];
+                const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t g = ww[j] & (ww[j] >> 4) & 0x0f0f0f0fu;
+                    while (g) {
+                        const int bit = __ffs(g) - 1; g &= g - 1;
+                        const uint32_t key = ((uint32_t)(16 * k4 + 4 * j + (bit >> 3)) << 4) | (1u << (bit & 7));
+                        if (key == keep_key) continue;
+                        ++cnt_snv;
+                        const uint32_t slot = atomicAdd(&sm->ngerm, 1u);
+                        if (slot < (uint32_t)kGermCap) E.germ[(size_t)s * kGermStride + 4 + slot] = key;
+                    }
+                }
+            }
+            cnt_snv = warp_sum(cnt_snv);
+        }
+        // indels: exact key equality (variants.py:83-96), every observation against all the others
+        uint32_t cnt_del = 0, cnt_ins = 0;
+        for (int o = lane; o < n_obs; o += 32) {
+            const int o_col = sm->o_col[o];
+            const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o];
+            bool germ = false, rep = true;
+            for (int j = 0; j < n_obs; ++j) {
+                if (j == o || sm->o_col[j] != o_col) continue;
+                const uint32_t j_meta = sm->o_meta[j];
+                if (((j_meta ^ o_meta) & (kMetaIns | kMetaLenMask)) != 0u || (sm->o_ra[j] >> 16) != (o_ra >> 16) || sm->o_s0[j] != o_s0 || sm->o_s1[j] != o_s1) continue;
+                if ((j_meta ^ o_meta) & kMetaDs) germ = true;
+                if (j < o) rep = false;
+            }
+            if (germ) {                                               // variant_to_keep may be this indel
+                const int type = (o_meta & kMetaIns) ? GA_VT_INS : GA_VT_DEL;
+                const int len = (int)(o_meta & kMetaLenMask), pos = o_col + c.d.col_begin;
+                const int end = (type == GA_VT_INS) ? pos + 1 : pos + len - 1;       // variation_classifier.py:86
+                const int na = (int)(o_ra >> 16);
+                if (c.keep_type == type && c.keep_pos == pos && c.keep_len == len && c.keep_end == end && c.keep_alen == na) {
+                    const char* code2asc = "=ACMGRSVTWYHKDBN";
+                    bool same = true;
+                    for (int j = 0; j < na; ++j) {
+                        const uint32_t code = ((j < 8 ? o_s0 : o_s1) >> (4 * (j & 7))) & 15u;
+                        if (c.keep_allele[j] != (uint8_t)code2asc[code]) same = false;
+                    }
+                    if (same) germ = false;
+                }
+            }
+            if (germ) {
+                const uint32_t i = o_ra & 0xffffu;
+                atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
+                atomicOr(&sm->indelbits[i >> 5], 1u << (i & 31));
+                sm->o_meta[o] = o_meta | kMetaGerm;                  // own slot; the other lanes only compare the type / length / dataset bits
+                if (rep) { if (o_meta & kMetaIns) ++cnt_ins; else ++cnt_del; }
+            }
+        }
+        if (n_obs > 0) { cnt_del = warp_sum(cnt_del); cnt_ins = warp_sum(cnt_ins); }
+        __syncwarp();
+        const uint32_t ngerm = sm->ngerm;
+        // ---- ordered list of the modified reads (two bitmap words per lane)
+        uint32_t n_mod;
+        {
+            const uint32_t b0 = lane < n_cw ? sm->modbits[lane] : 0u, b1 = lane + 32 < n_cw ? sm->modbits[lane + 32] : 0u;
+            uint32_t t0, t1;
+            uint32_t off0 = warp_excl_scan(__popc(b0), lane, &t0);
+            uint32_t off1 = t0 + warp_excl_scan(__popc(b1), lane, &t1);
+            n_mod = t0 + t1;
+            if (lane < n_cw) sm->woff[lane] = off0;
+            if (lane + 32 < n_cw) sm->woff[lane + 32] = off1;
+            if (n_mod <= (uint32_t)kModL) {
+                uint32_t b = b0;
+                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off0] = (uint16_t)(lane * 32 + k); sm->mhead[off0] = -1; sm->mpc[off0] = 0; ++off0; }
+                b = b1;
+                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off1] = (uint16_t)((lane + 32) * 32 + k); sm->mhead[off1] = -1; sm->mpc[off1] = 0; ++off1; }
+            }
+        }
+        if (n_mod > (uint32_t)kModL) {
+            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+            continue;
+        }
+        if (ngerm > (uint32_t)kGermCap) {
+            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 3, 1); }
+            continue;
+        }
+        __syncwarp();
+        for (int o = lane; o < n_obs; o += 32) {                      // hang every germline observation on its modified read
+            if (!(sm->o_meta[o] & kMetaGerm)) continue;
+            const uint32_t i = sm->o_ra[o] & 0xffffu;
+            const uint32_t k = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
+            sm->o_rnext[o] = atomicExch(&sm->mhead[k], o);
+        }
+        // ---- pass 3 over the entries: the germline hits of every clean modified read
+        for (uint32_t k = lane; k < n_ent0 + n_ent1; k += 32) {
+            const uint32_t e = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+            if (e & kEntGen) continue;
+            const uint32_t col = (e >> 4) & 0xfffu;
+            const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
+            const int idx = acgt_index(e & 15u);
+            if (!((((byte & (byte >> 4)) >> idx) & 1u) && (e & 0xffffu) != keep_key)) continue;
+            const uint32_t i = (e >> 16) & 0xfffu;
+            const uint32_t m = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
+            uint32_t* cw = reinterpret_cast<uint32_t*>(sm->mpc) + (m >> 2);
+            const uint32_t have = (atomicAdd(cw, 1u << (8 * (m & 3u))) >> (8 * (m & 3u))) & 0xffu;   // at most kGermCap hits per read: no carry
+            if (have < 2u) reinterpret_cast<uint16_t*>(sm->mpatch)[2 * m + have] = (uint16_t)((col << 4) | (1u << ((e >> 29) & 3u)));
+        }
+        __syncwarp();
+        // ---- round trip 3: new length of every modified read; indel-masked reads need the edit analysis
+        uint32_t tot_seq = 0, tot_qual = 0, n_q = 0, n_spec = 0;
+        bool slow = false;
+        for (uint32_t kb = 0; kb < n_mod; kb += 32) {
+            const uint32_t k = kb + lane;
+            uint32_t units = 0u, qunits = 0u;
+            if (k < n_mod) {
+                const int i = (int)sm->clist[k];
+                const int64_t r = read_of(c, i);
+                const int L0 = (int)(__ldg(B.len_flag + r) & 0xffffu);
+                uint32_t m;
+                if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
+                    Ed2 E2;
+                    int new_len = L0;
+                    if (!collect2(c, sm, (int)k, L0, E2, &new_len)) slow = true;   // more than two edits: the fallback kernel takes the session
+                    m = kModFlag | kQualFlag | ((uint32_t)new_len & kLen2);
+                    ++n_q;
+                } else {
+                    m = kModFlag | (uint32_t)L0;
+                }
+                sm->msize[k] = m;
+                units = ((m & kLen2) + 31u) / 32u; if (units < 1u) units = 1u;
+                qunits = (m & kQualFlag) ? units : 0u;
+                if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u) || sm->mpc[k] > 2) ++n_spec;
+            }
+            uint32_t ts, tq;
+            const uint32_t so = tot_seq + warp_excl_scan(units, lane, &ts), qo = tot_qual + warp_excl_scan(qunits, lane, &tq);
+            if (k < n_mod) sm->moff[k] = so | (qo << 16);
+            tot_seq += ts; tot_qual += tq;
+        }
+        if (__any_sync(0xffffffffu, slow)) {
+            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 4, 1); }
+            continue;
+        }
+        if (tot_seq >= 65536u || tot_qual >= 65536u) {
+            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+            continue;
+        }
+        // ---- output slots: one atomicAdd per cursor per session (north_star job (4): compaction)
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd((unsigned long long*)&O.totals->n_modified, (unsigned long long)n_mod);
+        else if (lane == 1) base = atomicAdd((unsigned long long*)&O.totals->seq16_used, (unsigned long long)tot_seq);
+        else if (lane == 2) base = atomicAdd((unsigned long long*)&O.totals->qual16_used, (unsigned long long)tot_qual);
+        else if (lane == 3) atomicAdd((unsigned long long*)&O.totals->session_reads, (unsigned long long)sess_reads);
+        else if (lane == 4) atomicAdd((unsigned long long*)&O.totals->session_bases, (unsigned long long)sess_bases);
+        else if (lane == 5) { O.sess_counts[4 * (size_t)s + 0] = cnt_snv; if (cnt_snv) atomicAdd((unsigned long long*)&O.totals->masked[0], (unsigned long long)cnt_snv); }
+        else if (lane == 6) { O.sess_counts[4 * (size_t)s + 1] = cnt_del; if (cnt_del) atomicAdd((unsigned long long*)&O.totals->masked[1], (unsigned long long)cnt_del); }
+        else if (lane == 7) { O.sess_counts[4 * (size_t)s + 2] = cnt_ins; if (cnt_ins) atomicAdd((unsigned long long*)&O.totals->masked[2], (unsigned long long)cnt_ins); }
+        else if (lane == 8) O.sess_counts[4 * (size_t)s + 3] = sess_reads;
+        else if (lane == 9) { E.germ[(size_t)s * kGermStride] = ngerm; E.germ[(size_t)s * kGermStride + 1] = (uint32_t)c.d.col_begin; }
+        n_q = warp_sum(n_q);
+        n_spec = warp_sum(n_spec);
+        uint32_t spec_base = 0u;
+        if (lane == 10 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
+        else if (lane == 11 && n_spec) spec_base = atomicAdd(E.n_special, n_spec);
+        spec_base = __shfl_sync(0xffffffffu, spec_base, 11);
+        const unsigned long long base_rec = __shfl_sync(0xffffffffu, base, 0), base_seq = __shfl_sync(0xffffffffu, base, 1), base_qual = __shfl_sync(0xffffffffu, base, 2);
+        const bool fits = (int64_t)(base_rec + n_mod) <= O.cap_records && (int64_t)(base_seq + tot_seq) <= O.cap_seq16 &&
+                          (int64_t)(base_qual + tot_qual) <= O.cap_qual16;
+        if (!fits) { if (lane == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); continue; }
+        // ---- record headers and the hand-over to the emission kernel
+        for (uint32_t kb = 0; kb < n_mod; kb += 32) {
+            const uint32_t k = kb + lane;
+            const bool have_k = k < n_mod;
+            const uint32_t m = have_k ? sm->msize[k] : 0u;
+            const bool q = (m & kQualFlag) != 0u;
+            const int i = have_k ? (int)sm->clist[k] : 0;
+            const bool is_spec = have_k && (q || ((sm->genbits[i >> 5] >> (i & 31)) & 1u) || sm->mpc[k] > 2);
+            const uint32_t sb = __ballot_sync(0xffffffffu, is_spec);
+            if (is_spec) E.special[spec_base + __popc(sb & ((1u << lane) - 1u))] = (uint32_t)(base_rec + k);
+            spec_base += __popc(sb);
+            if (!have_k) continue;
+            const int64_t r = read_of(c, i);
+            const uint64_t rec_idx = base_rec + k;
+            const uint32_t mo = sm->moff[k];
+            const uint32_t qual16 = q ? (uint32_t)(base_qual + (mo >> 16)) : 0xffffffffu;
+            write_record_meta(O, rec_idx, s, r, (int)(m & kLen2), base_seq + (mo & 0xffffu), qual16);
+            const uint32_t L0 = __ldg(B.len_flag + r) & 0xffffu, so = __ldg(B.seq_off16 + r);
+            const int pos = __ldg(B.pos + r);
+            const uint32_t hits = sm->mpc[k];
+            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : (hits <= 2u ? 1 : 4));
+            E.kind[rec_idx] = kind;
+            if (kind == 1) E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | (hits << 16), sm->mpatch[k]);
+            else E.edesc[rec_idx] = make_uint4(so, (uint32_t)pos, L0, (uint32_t)s);
+            if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
+                Ed2 E2; int nl = 0;
+                collect2(c, sm, (int)k, (int)L0, E2, &nl);
+                EditAux a;
+                a.irp0 = E2.irp[0]; a.pos0 = E2.pos[0]; a.len0 = (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u);
+                a.irp1 = E2.irp[1]; a.pos1 = E2.pos[1]; a.len1 = (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u);
+                a.ne = (uint32_t)E2.ne; a.n_del = (uint32_t)E2.n_del;
+                uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
+                const uint4* src = reinterpret_cast<const uint4*>(&a);
+                dst[0] = src[0]; dst[1] = src[1];
+            }
+        }
+        __syncwarp();                                                 // tables are reused by the next session
     }
 }
 

@@ -12,7 +12,8 @@
 // walked by the whole warp (variation_classifier.py:52-107).
 //
 // Output (engine scratch, one fixed region per item, written by its warp only - no atomics):
-//   ent[item][..]   SNV candidate entries  (read << 16) | (column << 4) | base code, bit 28 = read has another CIGAR
+//   ent[item][..]   SNV candidate entries  (read << 16) | (column << 4) | base code, bit 28 = read has another CIGAR,
+//                   bits 29-30 = reference base (index into ACGT)
 //   obs[item][..]   indel observations (ObsRec)
 //   cnt[item]       {entries, observations, session reads, session bases}; entries == kCntOverflow hands the
 //                   session to the fallback kernel
@@ -25,7 +26,7 @@ namespace ga {
 constexpr int kEntHalf = 768;            // SNV candidate entries per item (tumor or normal half of a session)
 constexpr int kObsHalf = 192;            // indel observations per item
 constexpr int kTileUnits = 160;          // 16-byte units staged per tile (32 reads of 150 bp)
-constexpr int kWbuf = 96;                // entries buffered per warp between flushes
+constexpr int kWbuf = 144;                // entries buffered per warp between flushes
 constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean single-op read
 constexpr uint32_t kCntOverflow = 0xffffffffu;
 constexpr int kScanThreads = 256;
@@ -84,9 +85,9 @@ struct ItemCtx {
     uint32_t n_ent, n_obs, n_reads, n_bases;   // n_ent / n_obs warp-uniform, n_reads / n_bases per lane (summed at the end)
 };
 
-__device__ __forceinline__ void push_entry_w(const ItemCtx& c, int i, int col, uint32_t b, uint32_t gen) {
+__device__ __forceinline__ void push_entry_w(const ItemCtx& c, int i, int col, uint32_t b, uint32_t rf, uint32_t gen) {
     const uint32_t slot = atomicAdd(&c.ws->wcnt, 1u);
-    if (slot < (uint32_t)kWbuf) c.ws->wbuf[slot] = gen | ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
+    if (slot < (uint32_t)kWbuf) c.ws->wbuf[slot] = gen | ((uint32_t)(__ffs(rf) - 1) << 29) | ((uint32_t)i << 16) | ((uint32_t)col << 4) | b;
     else c.ws->ovf = 1u;
 }
 
@@ -140,7 +141,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                         const int n = (__ffs(x) - 1) >> 2;
                         x &= ~(0xfu << (n * 4));
                         const uint32_t b = (v >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
-                        if (b != 15u && is_acgt(rf)) push_entry_w(c, i, p0 + n - c.col_begin, b, kEntGen);   // variation_classifier.py:147-150
+                        if (b != 15u && is_acgt(rf)) push_entry_w(c, i, p0 + n - c.col_begin, b, rf, kEntGen);   // variation_classifier.py:147-150
                     }
                 }
                 q += ln; rc += ln;
@@ -264,7 +265,7 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
             const int n = (__ffs(x) - 1) >> 2;
             x &= ~(0xfu << (n * 4));
             const uint32_t bb = (rw >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
-            if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, 0u);
+            if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, rf, 0u);
         }
     }
     // ---- reads with any other CIGAR (or an error case): the whole warp walks them one by one

@@ -158,8 +158,14 @@ class Engine:
         k = int(self._L.ga_kernel_ms_history(self._h, buf, n))
         return [float(buf[i]) for i in range(k)]
 
+    def fallback_sessions(self):
+        """(sessions of the last run that took the fallback kernel, per-reason counts) - see ga_last_fallback_sessions."""
+        buf = (C.c_int32 * 9)()
+        n = int(self._L.ga_last_fallback_sessions(self._h, buf, 9))
+        return n, [int(x) for x in buf]
+
     def stage_ms_history(self, stage: int, n: int = 32):
-        """stage: 0 scan, 1 resolve, 2 fallback, 3 emission kernel."""
+        """stage: 0 scan, 1 resolve, 2 emission kernel, 3 tail of the fallback kernel."""
         buf = (C.c_float * n)()
         k = int(self._L.ga_stage_ms_history(self._h, stage, buf, n))
         return [float(buf[i]) for i in range(k)]

@@ -187,9 +187,16 @@ float ga_last_kernel_ms(ga_engine* e);
  * ga_run() calls, out[0] = latest; returns how many were written (at most min(n, 32)).  Synchronises on the
  * recorded events. */
 int   ga_kernel_ms_history(ga_engine* e, float* out, int n);
-/* Same per stage: 0 = scan kernel (allele discovery), 1 = resolve kernel (germline set, record list, headers),
- * 2 = fallback kernel for oversize sessions, 3 = emission kernel (record bodies). */
+/* Same per stage: 0 = scan kernel (allele discovery), 1 = resolve kernels (germline set, record list, headers),
+ * 2 = emission kernel (record bodies), 3 = what remains of the fallback kernel for oversize sessions, which runs
+ * beside the emission kernel, once that has finished. */
 int   ga_stage_ms_history(ga_engine* e, int stage, float* out, int n);
+/* Sessions of the most recent ga_run() that took the global-scratch fallback kernel (-1 on error), and why:
+ * reasons[0] oversize session, [1] scan-kernel table overflow, [2] IUPAC read base, [3] more modified reads or
+ * germline alleles than the shared-memory tables hold, [4] a read with more than two germline indels;
+ * reasons[8] = sessions the one-warp resolve kernel handed to the one-CTA resolve kernel (not a fallback).
+ * Synchronises the device. */
+int   ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons);
 
 /* ------------------------------------------------------------------ end-to-end host entry
  * ga_run_host: all pointers are HOST pointers (pinned for full speed).  Splits the session table into
