@@ -82,6 +82,128 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
     }
 }
 
+// Reads with other CIGARs, the common shapes: SNV-only (kind 2, E.ne == 0) and one germline indel (kind 3,
+// E.ne == 1), reads of at most 8 * (kGroupStage - 1) bases.  One group of 8 lanes per record; every lane of the warp
+// calls this (act = false for groups without such a record).
+//   1. the record is staged in shared memory, coalesced;
+//   2. SNV masking (anonymizer_methods.py:170-176): every germline allele of the session is carried through the
+//      CIGAR to its query offset and, when the read shows it, replaced by the reference base;
+//   3. the one edit is applied while copying: DEL -> the deleted reference bases come back with quality
+//      floor(mean(qualities)), INS -> the inserted bases and qualities go (anonymizer_methods.py:178-203); edits
+//      index the forward-orientation quality array, printed order = BAM order (anonymizer_methods.py:95, 213).
+__device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r,
+                                                   int pos, int L, uint32_t src_unit, int col_begin, const GermList& germ, int64_t q_lo, int64_t q_hi,
+                                                   uint32_t* stage, uint64_t seq16, uint64_t qual16, int new_len, int glane) {
+    const int nw = (L + 7) >> 3;
+    uint32_t c0 = 0u, c1 = 0u;
+    if (act) {
+        c0 = __ldg(B.cigar_off + r); c1 = __ldg(B.cigar_off + r + 1);
+        const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * src_unit);
+        for (int w = glane; w < nw; w += kGroup) stage[w] = __ldg(rec + w) & tail_mask(L, w);
+        if (glane == 0) stage[nw] = 0u;                                // the funnel shift may touch one word past the end
+    }
+    __syncwarp();
+    if (act) {
+        for (uint32_t a = glane; a < germ.n; a += kGroup) {
+            const uint32_t key = __ldg(germ.e + a), code = key & 15u;
+            const int at = col_begin + (int)(key >> 4);
+            int rc = pos, q = 0;
+            for (uint32_t ci = c0; ci < c1; ++ci) {
+                const uint32_t cw = __ldg(B.cigar + ci), op = cw & 15u;
+                const int ln = (int)(cw >> 4);
+                if (at < rc) break;                                    // the column lies before what is left of the read
+                if (op == 0u || op == 7u || op == 8u) {
+                    if (at < rc + ln) {
+                        const int qq = q + (at - rc);
+                        if (qq < L && ((stage[qq >> 3] >> ((qq & 7) * 4)) & 15u) == code)
+                            atomicXor(&stage[qq >> 3], (code ^ ref_code(B.ref4, at)) << ((qq & 7) * 4));
+                        break;
+                    }
+                    q += ln; rc += ln;
+                } else if (op == 1u || op == 4u) q += ln;
+                else if (op == 2u || op == 3u) { if (at < rc + ln) break; rc += ln; }
+            }
+        }
+    }
+    __syncwarp();
+    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+    const bool indel = act && E.ne == 1;
+    if (act && E.ne == 0) for (int w = glane; w < units * 4; w += kGroup) oseq[w] = w < nw ? stage[w] : 0u;
+    // ---- one edit
+    const bool is_del = E.n_del == 1;
+    const int p = E.p[0], len = E.len[0], shift = is_del ? -len : E.e[0] - E.p[0];      // source = final + shift behind the edit
+    const int ins_end = is_del ? p + len : p;                                             // [p, ins_end): re-inserted elements
+    const uint8_t* qrec = nullptr;
+    bool ok = indel;
+    if (indel) {
+        qrec = qual_record_in(B, r, q_lo, q_hi);
+        if (!qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); ok = false; }
+    }
+    uint32_t mean = 0u;
+    if (__any_sync(0xffffffffu, ok && is_del)) {                      // quality of re-inserted bases (anonymizer_methods.py:193)
+        uint32_t part = 0;
+        if (ok && is_del) {
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+            for (int q = glane; q < ((L + 3) >> 2); q += kGroup) {
+                uint32_t v = __ldg(qw + q);
+                if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
+                part += __vsadu4(v, 0u);
+            }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
+        mean = L ? part / (uint32_t)L : 0u;
+        if (ok && is_del && glane == 0 && (int64_t)E.pos[0] + len > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
+    }
+    if (!ok) return;
+    auto src_of = [&](int j) { return j < p ? j : (j < ins_end ? -1 : j + shift); };     // final index -> original index, -1: re-inserted
+    for (int w = glane; w < units * 4; w += kGroup) {
+        const int j0 = w << 3;
+        uint32_t v = 0u;
+        if (j0 < new_len) {
+            const int jl = min(j0 + 7, new_len - 1);
+            const int s0 = src_of(j0), sl = src_of(jl);
+            if (s0 >= 0 && sl - s0 == jl - j0) {                       // one contiguous run of input bases
+                v = __funnelshift_r(stage[s0 >> 3], stage[(s0 >> 3) + 1], (uint32_t)(s0 & 7) * 4u);
+            } else if (j0 >= p && jl < ins_end) {                      // inside the re-inserted reference bases
+                v = ref_word(B.ref4, (int64_t)E.pos[0] + (j0 - p));
+            } else {
+                for (int n = 0; n <= jl - j0; ++n) {
+                    const int sj = src_of(j0 + n);
+                    const uint32_t code = sj >= 0 ? (stage[sj >> 3] >> ((sj & 7) * 4)) & 15u : ref_code(B.ref4, (int64_t)E.pos[0] + (j0 + n - p));
+                    v |= code << (n * 4);
+                }
+            }
+            if (jl - j0 < 7) v &= 0xffffffffu >> ((7 - (jl - j0)) * 4);
+        }
+        oseq[w] = v;
+    }
+    const bool reverse = ((__ldg(B.len_flag + r) >> 16) & 0x10u) != 0u;
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+    for (int w = glane; w < units * 8; w += kGroup) {
+        const int p0 = w << 2;
+        uint32_t v = 0u;
+        if (p0 < new_len) {
+            const int pl = min(p0 + 3, new_len - 1);
+            const int s0 = src_of(reverse ? new_len - 1 - p0 : p0), s3 = src_of(reverse ? new_len - 1 - pl : pl);
+            if (s0 >= 0 && s3 >= 0 && (reverse ? s0 - s3 : s3 - s0) == pl - p0) {
+                const int b0 = reverse ? L - 1 - s0 : s0;               // byte of the BAM-order quality record
+                const uint32_t lo = __ldg(qw + (b0 >> 2)), hi = (b0 & 3) ? __ldg(qw + (b0 >> 2) + 1) : 0u;
+                v = __funnelshift_r(lo, hi, (uint32_t)(b0 & 3) * 8u);
+            } else {
+                for (int n = 0; n <= pl - p0; ++n) {
+                    const int sj = src_of(reverse ? new_len - 1 - (p0 + n) : p0 + n);
+                    const uint32_t qv = sj >= 0 ? (uint32_t)qrec[reverse ? L - 1 - sj : sj] : mean;
+                    v |= qv << (n * 8);
+                }
+            }
+            if (pl - p0 < 3) v &= 0xffffffffu >> ((3 - (pl - p0)) * 8);
+        }
+        oq[w] = v;
+    }
+}
+
 // Records of kind >= 2 (reads with other CIGARs, reads with many hits), taken densely from the list the resolve
 // kernels packed: four records per warp step, one group of 8 lanes each.
 __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
@@ -132,30 +254,37 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
                         out[u] = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-                if (r_kind == 2u) {
+                const bool indel = r_kind == 3u;
+                Ed2 Ed; Ed.ne = 0; Ed.n_del = 0;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) { Ed.irp[q] = 0; Ed.len[q] = 0; Ed.pos[q] = 0; Ed.mean[q] = 0u; Ed.p[q] = 0; Ed.e[q] = 0; }
+                int64_t q_lo = 0, q_hi = 0;
+                const int L = (int)d.z;
+                if (indel) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
+                    const uint4 x0 = ap[0], x1 = ap[1];              // EditAux written by the resolve kernel
+                    Ed.irp[0] = (int)x0.x; Ed.pos[0] = (int)x0.y; Ed.len[0] = (int)(x0.z & 0x7fffffffu);
+                    Ed.irp[1] = (int)x0.w; Ed.pos[1] = (int)x1.x; Ed.len[1] = (int)(x1.y & 0x7fffffffu);
+                    Ed.ne = (int)x1.z; Ed.n_del = (int)x1.w;
+                    clamp_edits2(Ed, L);
+                    const bool tumor = r < B.n_tumor;
+                    q_lo = tumor ? descs[s].qt_begin : descs[s].qn_begin; q_hi = tumor ? descs[s].qt_end : descs[s].qn_end;
+                }
+                __syncwarp();                                         // every lane of the group has read the aux before it is overwritten
+                // the common shapes take the staged path; two edits or very long reads take the general one
+                const bool fast = (r_kind == 2u || (indel && Ed.ne == 1)) && ((L + 7) >> 3) <= kGroupStage - 1;
+                if (__any_sync(0xffffffffu, fast))
+                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, col_begin, germ, q_lo, q_hi, stage[group], seq16, qual16, new_len, glane);
+                if (r_kind == 2u && !fast) {
                     const uint32_t c0 = __ldg(B.cigar_off + r), c1 = __ldg(B.cigar_off + r + 1);
                     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
                     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
                     masked_words_g(B, r, r_pos, new_len, c0, c1, col_begin, units * 4, glane, kGroup, germ, [&](int wd, uint32_t v) { oseq[wd] = v; });
                 }
-                const bool indel = r_kind == 3u;
-                if (__any_sync(0xffffffffu, indel)) {
-                    Ed2 Ed; Ed.ne = 0; Ed.n_del = 0;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) { Ed.irp[q] = 0; Ed.len[q] = 0; Ed.pos[q] = 0; Ed.mean[q] = 0u; }
-                    int64_t q_lo = 0, q_hi = 0;
-                    if (indel) {
-                        const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
-                        const uint4 x0 = ap[0], x1 = ap[1];              // EditAux written by the resolve kernel
-                        Ed.irp[0] = (int)x0.x; Ed.pos[0] = (int)x0.y; Ed.len[0] = (int)(x0.z & 0x7fffffffu);
-                        Ed.irp[1] = (int)x0.w; Ed.pos[1] = (int)x1.x; Ed.len[1] = (int)(x1.y & 0x7fffffffu);
-                        Ed.ne = (int)x1.z; Ed.n_del = (int)x1.w;
-                        clamp_edits2(Ed, (int)(__ldg(B.len_flag + r) & 0xffffu));
-                        const bool tumor = r < B.n_tumor;
-                        q_lo = tumor ? descs[s].qt_begin : descs[s].qn_begin; q_hi = tumor ? descs[s].qt_end : descs[s].qn_end;
-                    }
-                    __syncwarp();                                         // every lane of the group has read the aux before it is overwritten
-                    emit_indel_group_t(B, O.totals, O, indel, Ed, r, col_begin, q_lo, q_hi, stage[group], seq16, qual16, new_len, glane, germ);
+                const bool slow = indel && !fast;
+                if (__any_sync(0xffffffffu, slow)) {
+                    __syncwarp();
+                    emit_indel_group_t(B, O.totals, O, slow, Ed, r, col_begin, q_lo, q_hi, stage[group], seq16, qual16, new_len, glane, germ);
                 }
             }
         }

@@ -377,7 +377,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     // stage 2: germline set, modified-record list, output slots, headers - one warp per session, then one CTA per
     // session for those whose tables did not fit the lean capacities
     int32_t* d_nlarge = L.d_small + 12;
-    const int lean_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * 8, (S->n_sessions + ga::kLeanWarps - 1) / ga::kLeanWarps);
+    const int lean_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * 10, (S->n_sessions + ga::kLeanWarps - 1) / ga::kLeanWarps);
     ga::resolve_lean_kernel<<<lean_ctas, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
     const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * 7, S->n_sessions);
     ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);

@@ -368,31 +368,37 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
 }  // namespace ga
 
 // ====================================================================================================================
-// Lean variant: ONE WARP per session, no block barrier, ~11 KB of shared memory per warp (18 warps per SM).
+// Lean variant: ONE WARP per session, no block barrier, 10.4 KB of shared memory per warp (20 warps per SM), and
+// deliberately compact code (rolled loops): a warp runs the whole kernel body once per session, so the body has to
+// fit the instruction cache (an unrolled version of 123 KB spent 70 % of its time waiting for instructions).
 // Takes every session whose tables fit the small capacities below (the normal case); the others are listed in
-// large_list for the CTA-per-session kernel above.  Clean SNV-only records get their (at most two) germline hits
-// written into the emission descriptor (kind 1), so the emission kernel copies and patches without touching the
-// reference or the germline list.
+// large_list for the CTA-per-session kernel above.
+// Clean SNV-only records get their (at most two) germline hits written into the emission descriptor (kind 1), so
+// the emission kernel copies and patches without touching the reference or the germline list.
 namespace ga {
 
 constexpr int kLeanWarps = 2;            // warps per CTA
-constexpr int kReadsL = 2048;            // candidate reads per session
-constexpr int kModL = 384;               // modified reads per session
-constexpr int kObsL = 96;                // indel observations per session
+constexpr int kReadsL = 1536;            // candidate reads per session
+constexpr int kModL = 256;               // modified reads per session
+constexpr int kObsL = 64;                // indel observations per session
+constexpr int kEntL = 384;               // candidate entries per session
 
 struct SmemL {
     uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
     uint32_t modbits[kReadsL / 32], indelbits[kReadsL / 32], genbits[kReadsL / 32], woff[kReadsL / 32];
-    uint32_t msize[kModL];
-    uint32_t moff[kModL];                // session-relative sequence unit | quality unit << 16
     uint32_t mpatch[kModL];              // two germline hits of a clean read: (column << 4) | reference code, 16 bits each
     int32_t mhead[kModL];                // per modified read: chain of its germline indel observations
     uint16_t clist[kModL];
     uint8_t mpc[kModL];                  // germline SNV hits per modified read
     uint32_t o_meta[kObsL], o_ra[kObsL], o_s0[kObsL], o_s1[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
+    uint32_t ent[kEntL];                 // candidate entries (tumor item, then normal item); bit 31: germline hit
+    uint32_t rnew[kModL];                // per modified read: new length | kind << 24
     uint32_t ngerm, pad[3];
 };
 static_assert(sizeof(SmemL) % 16 == 0, "per-warp slices stay 16-byte aligned");
+
+// collect2 behind a call: the lean kernel needs it twice and must stay small enough for the instruction cache
+__device__ __noinline__ bool lean_collect(const SessCtx& c, const SmemL* sm, int k, int L, Ed2& E, int* new_len) { return collect2(c, sm, k, L, E, new_len); }
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
     uint32_t inc = v;
@@ -402,10 +408,10 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return inc - v;
 }
 
-__global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
-                                                                        int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
-                                                                        int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
-                                                                        ResultView O, ScanScratch X, EmitScratch2 E) {
+__global__ void __launch_bounds__(32 * kLeanWarps, 10) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+                                                                            int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
+                                                                            int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
+                                                                            ResultView O, ScanScratch X, EmitScratch2 E) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SmemL* sm = reinterpret_cast<SmemL*>(smem_raw) + warp;
@@ -414,7 +420,12 @@ __global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView
     c.totals = O.totals;
     memset(&c.T, 0, sizeof c.T);
     const int n_warps = gridDim.x * kLeanWarps;
+    // statistics counters are summed per warp and added to ga_totals once, at the end: every session already sends
+    // three atomics to that one cache line for its output slots, and same-address atomics serialise in L2
+    unsigned long long acc_reads = 0ull, acc_bases = 0ull;
+    uint32_t acc_snv = 0u, acc_del = 0u, acc_ins = 0u, acc_q = 0u;
 
+#pragma unroll 1
     for (int s = blockIdx.x * kLeanWarps + warp; s < S.n_sessions; s += n_warps) {
         // ---- round trip 1: descriptor, scan counts, variant_to_keep
         uint32_t w1 = 0u, w2 = 0u;
@@ -448,19 +459,33 @@ __global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView
             continue;
         }
         const int n_obs = (int)(n_obs0 + n_obs1);
-        if (c.n_range > kReadsL || n_obs > kObsL) {
+        const uint32_t n_ent = n_ent0 + n_ent1;
+        if (c.n_range > kReadsL || n_obs > kObsL || n_ent > (uint32_t)kEntL) {
             if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
-        // ---- zeroed tables; round trip 2: entries (pass 1: allele table), observations, keep allele
+        // ---- round trip 2: entries, observations, keep allele; tables zeroed meanwhile
+        {
+            const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
+            const uint32_t* e1 = e0 + kEntHalf;
+#pragma unroll 2
+            for (uint32_t k = lane; k < n_ent; k += 32) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+        }
+#pragma unroll 1
+        for (int o = lane; o < n_obs; o += 32) {
+            const ObsRec* op = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
+            const uint4* src = reinterpret_cast<const uint4*>(o < (int)n_obs0 ? op + o : op + kObsHalf + (o - (int)n_obs0));
+            const uint4 a = __ldg(src), b = __ldg(src + 1);
+            sm->o_col[o] = (int)a.x; sm->o_meta[o] = a.y; sm->o_ra[o] = a.z; sm->o_irp[o] = (int)a.w; sm->o_s0[o] = b.x; sm->o_s1[o] = b.y;
+        }
         {
             uint4* t4 = reinterpret_cast<uint4*>(sm->tab);
+#pragma unroll 1
             for (int k = lane; k < ((n_cols + 15) >> 4); k += 32) t4[k] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
             for (int k = lane; k < n_cw; k += 32) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
             if (lane == 0) sm->ngerm = 0u;
         }
-        const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
-        const uint32_t* e1 = e0 + kEntHalf;
         uint32_t keep_key = 0xffffffffu;                              // variant_to_keep as an SNV entry key
         if (c.keep_type == GA_VT_SNV && c.keep_end == c.keep_pos && c.keep_len == 1 && c.keep_alen == 1) {
             const int kc = c.keep_pos - c.d.col_begin;
@@ -470,71 +495,68 @@ __global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView
                 if (code) keep_key = ((uint32_t)kc << 4) | code;
             }
         }
-        for (int o = lane; o < n_obs; o += 32) {
-            const ObsRec* op = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
-            const uint4* src = reinterpret_cast<const uint4*>(o < (int)n_obs0 ? op + o : op + kObsHalf + (o - (int)n_obs0));
-            const uint4 a = __ldg(src), b = __ldg(src + 1);
-            sm->o_col[o] = (int)a.x; sm->o_meta[o] = a.y; sm->o_ra[o] = a.z; sm->o_irp[o] = (int)a.w; sm->o_s0[o] = b.x; sm->o_s1[o] = b.y;
-        }
         __syncwarp();
+        // ---- pass 1: allele table
         bool bad = false;
-        for (uint32_t k = lane; k < n_ent0 + n_ent1; k += 32) {
-            const uint32_t e = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+#pragma unroll 1
+        for (uint32_t k = lane; k < n_ent; k += 32) {
+            const uint32_t e = sm->ent[k], b = e & 15u;
+            if (b == 0u || (b & (b - 1u))) { bad = true; continue; }   // IUPAC read base: the fallback kernel keeps all 16 codes
             const uint32_t col = (e >> 4) & 0xfffu;
-            const int idx = acgt_index(e & 15u);
-            if (idx < 0) { bad = true; continue; }                     // IUPAC read base: the fallback kernel keeps all 16 codes
-            atomicOr(&sm->tab[col >> 2], 1u << (idx + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
+            atomicOr(&sm->tab[col >> 2], 1u << ((__ffs(b) - 1) + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
         }
         if (__any_sync(0xffffffffu, bad)) {
             if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 2, 1); }
             continue;
         }
         bool long_allele = false;
+#pragma unroll 1
         for (int o = lane; o < n_obs; o += 32) long_allele |= (sm->o_ra[o] >> 16) > 16u;
         if (__any_sync(0xffffffffu, long_allele)) {                  // allele longer than the signature: compared by the large variant
             if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
         __syncwarp();
-        // ---- resolve + mark (pass 2 over the entries): germline = seen in tumor AND normal, minus variant_to_keep
-        for (uint32_t k = lane; k < n_ent0 + n_ent1; k += 32) {
-            const uint32_t e = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+        // ---- pass 2: germline = seen in tumor AND normal, minus variant_to_keep; mark the reads that carry one.
+        // Bit 31 of an entry remembers that it is a germline hit (pass 3 needs only those).
+#pragma unroll 1
+        for (uint32_t k = lane; k < n_ent; k += 32) {
+            const uint32_t e = sm->ent[k];
             const uint32_t col = (e >> 4) & 0xfffu;
             const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
-            const int idx = acgt_index(e & 15u);
-            if ((((byte & (byte >> 4)) >> idx) & 1u) && (e & 0xffffu) != keep_key) {
+            if ((((byte & (byte >> 4)) >> (__ffs(e & 15u) - 1)) & 1u) && (e & 0xffffu) != keep_key) {
                 const uint32_t i = (e >> 16) & 0xfffu;
                 atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
                 if (e & kEntGen) atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
+                sm->ent[k] = e | 0x80000000u;
             }
         }
         uint32_t cnt_snv = 0;
         {   // distinct germline SNV alleles: the per-session counter and the emission kernel's list
-            const uint4* t4 = reinterpret_cast<const uint4*>(sm->tab);
-            for (int k4 = lane; k4 < ((n_cols + 15) >> 4); k4 += 32) {
-                const uint4 q = t4[k4];
-                const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t g = ww[j] & (ww[j] >> 4) & 0x0f0f0f0fu;
-                    while (g) {
-                        const int bit = __ffs(g) - 1; g &= g - 1;
-                        const uint32_t key = ((uint32_t)(16 * k4 + 4 * j + (bit >> 3)) << 4) | (1u << (bit & 7));
-                        if (key == keep_key) continue;
-                        ++cnt_snv;
-                        const uint32_t slot = atomicAdd(&sm->ngerm, 1u);
-                        if (slot < (uint32_t)kGermCap) E.germ[(size_t)s * kGermStride + 4 + slot] = key;
-                    }
+#pragma unroll 1
+            for (int kw = lane; kw < ((n_cols + 3) >> 2); kw += 32) {
+                const uint32_t w = sm->tab[kw];
+                uint32_t g = w & (w >> 4) & 0x0f0f0f0fu;
+#pragma unroll 1
+                while (g) {
+                    const int bit = __ffs(g) - 1; g &= g - 1;
+                    const uint32_t key = ((uint32_t)(4 * kw + (bit >> 3)) << 4) | (1u << (bit & 7));
+                    if (key == keep_key) continue;
+                    ++cnt_snv;
+                    const uint32_t slot = atomicAdd(&sm->ngerm, 1u);
+                    if (slot < (uint32_t)kGermCap) E.germ[(size_t)s * kGermStride + 4 + slot] = key;
                 }
             }
             cnt_snv = warp_sum(cnt_snv);
         }
         // indels: exact key equality (variants.py:83-96), every observation against all the others
         uint32_t cnt_del = 0, cnt_ins = 0;
+#pragma unroll 1
         for (int o = lane; o < n_obs; o += 32) {
             const int o_col = sm->o_col[o];
             const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o];
             bool germ = false, rep = true;
+#pragma unroll 1
             for (int j = 0; j < n_obs; ++j) {
                 if (j == o || sm->o_col[j] != o_col) continue;
                 const uint32_t j_meta = sm->o_meta[j];
@@ -550,6 +572,7 @@ __global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView
                 if (c.keep_type == type && c.keep_pos == pos && c.keep_len == len && c.keep_end == end && c.keep_alen == na) {
                     const char* code2asc = "=ACMGRSVTWYHKDBN";
                     bool same = true;
+#pragma unroll 1
                     for (int j = 0; j < na; ++j) {
                         const uint32_t code = ((j < 8 ? o_s0 : o_s1) >> (4 * (j & 7))) & 15u;
                         if (c.keep_allele[j] != (uint8_t)code2asc[code]) same = false;
@@ -580,9 +603,11 @@ __global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView
             if (lane + 32 < n_cw) sm->woff[lane + 32] = off1;
             if (n_mod <= (uint32_t)kModL) {
                 uint32_t b = b0;
-                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off0] = (uint16_t)(lane * 32 + k); sm->mhead[off0] = -1; sm->mpc[off0] = 0; ++off0; }
+#pragma unroll 1
+                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off0++] = (uint16_t)(lane * 32 + k); }
                 b = b1;
-                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off1] = (uint16_t)((lane + 32) * 32 + k); sm->mhead[off1] = -1; sm->mpc[off1] = 0; ++off1; }
+#pragma unroll 1
+                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off1++] = (uint16_t)((lane + 32) * 32 + k); }
             }
         }
         if (n_mod > (uint32_t)kModL) {
@@ -593,126 +618,118 @@ __global__ void __launch_bounds__(32 * kLeanWarps) resolve_lean_kernel(BatchView
             if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 3, 1); }
             continue;
         }
+        {
+            uint32_t* pc4 = reinterpret_cast<uint32_t*>(sm->mpc);
+#pragma unroll 1
+            for (int k = lane; k < (int)((n_mod + 3) >> 2); k += 32) pc4[k] = 0u;
+            if (n_obs > 0) for (int k = lane; k < (int)n_mod; k += 32) sm->mhead[k] = -1;
+        }
         __syncwarp();
+#pragma unroll 1
         for (int o = lane; o < n_obs; o += 32) {                      // hang every germline observation on its modified read
             if (!(sm->o_meta[o] & kMetaGerm)) continue;
             const uint32_t i = sm->o_ra[o] & 0xffffu;
             const uint32_t k = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
             sm->o_rnext[o] = atomicExch(&sm->mhead[k], o);
         }
-        // ---- pass 3 over the entries: the germline hits of every clean modified read
-        for (uint32_t k = lane; k < n_ent0 + n_ent1; k += 32) {
-            const uint32_t e = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
-            if (e & kEntGen) continue;
-            const uint32_t col = (e >> 4) & 0xfffu;
-            const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
-            const int idx = acgt_index(e & 15u);
-            if (!((((byte & (byte >> 4)) >> idx) & 1u) && (e & 0xffffu) != keep_key)) continue;
-            const uint32_t i = (e >> 16) & 0xfffu;
+        // ---- pass 3: the germline hits of every clean modified read
+#pragma unroll 1
+        for (uint32_t k = lane; k < n_ent; k += 32) {
+            const uint32_t e = sm->ent[k];
+            if ((e & (0x80000000u | kEntGen)) != 0x80000000u) continue;
+            const uint32_t col = (e >> 4) & 0xfffu, i = (e >> 16) & 0xfffu;
             const uint32_t m = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
             uint32_t* cw = reinterpret_cast<uint32_t*>(sm->mpc) + (m >> 2);
             const uint32_t have = (atomicAdd(cw, 1u << (8 * (m & 3u))) >> (8 * (m & 3u))) & 0xffu;   // at most kGermCap hits per read: no carry
             if (have < 2u) reinterpret_cast<uint16_t*>(sm->mpatch)[2 * m + have] = (uint16_t)((col << 4) | (1u << ((e >> 29) & 3u)));
         }
         __syncwarp();
-        // ---- round trip 3: new length of every modified read; indel-masked reads need the edit analysis
+        // ---- round trip 3: new length of every modified read (indel-masked reads need the edit analysis), output sizes
         uint32_t tot_seq = 0, tot_qual = 0, n_q = 0, n_spec = 0;
         bool slow = false;
-        for (uint32_t kb = 0; kb < n_mod; kb += 32) {
-            const uint32_t k = kb + lane;
-            uint32_t units = 0u, qunits = 0u;
-            if (k < n_mod) {
-                const int i = (int)sm->clist[k];
-                const int64_t r = read_of(c, i);
-                const int L0 = (int)(__ldg(B.len_flag + r) & 0xffffu);
-                uint32_t m;
-                if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
-                    Ed2 E2;
-                    int new_len = L0;
-                    if (!collect2(c, sm, (int)k, L0, E2, &new_len)) slow = true;   // more than two edits: the fallback kernel takes the session
-                    m = kModFlag | kQualFlag | ((uint32_t)new_len & kLen2);
-                    ++n_q;
-                } else {
-                    m = kModFlag | (uint32_t)L0;
-                }
-                sm->msize[k] = m;
-                units = ((m & kLen2) + 31u) / 32u; if (units < 1u) units = 1u;
-                qunits = (m & kQualFlag) ? units : 0u;
-                if ((m & kQualFlag) || ((sm->genbits[i >> 5] >> (i & 31)) & 1u) || sm->mpc[k] > 2) ++n_spec;
+#pragma unroll 2
+        for (uint32_t k = lane; k < n_mod; k += 32) {
+            const int i = (int)sm->clist[k];
+            const int L0 = (int)(__ldg(B.len_flag + read_of(c, i)) & 0xffffu);
+            int new_len = L0;
+            uint32_t kind;
+            if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
+                Ed2 E2;
+                if (!lean_collect(c, sm, (int)k, L0, E2, &new_len)) slow = true;   // more than two edits: the fallback kernel takes the session
+                kind = 3u; ++n_q;
+            } else {
+                kind = ((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2u : (sm->mpc[k] <= 2 ? 1u : 4u);
             }
-            uint32_t ts, tq;
-            const uint32_t so = tot_seq + warp_excl_scan(units, lane, &ts), qo = tot_qual + warp_excl_scan(qunits, lane, &tq);
-            if (k < n_mod) sm->moff[k] = so | (qo << 16);
-            tot_seq += ts; tot_qual += tq;
+            if (kind != 1u) ++n_spec;
+            uint32_t units = ((uint32_t)new_len + 31u) / 32u; if (units < 1u) units = 1u;
+            tot_seq += units; if (kind == 3u) tot_qual += units;
+            sm->rnew[k] = ((uint32_t)new_len & kLen2) | (kind << 24);
         }
         if (__any_sync(0xffffffffu, slow)) {
             if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 4, 1); }
             continue;
         }
-        if (tot_seq >= 65536u || tot_qual >= 65536u) {
-            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
-            continue;
-        }
+        tot_seq = warp_sum(tot_seq); tot_qual = warp_sum(tot_qual); n_q = warp_sum(n_q); n_spec = warp_sum(n_spec);
         // ---- output slots: one atomicAdd per cursor per session (north_star job (4): compaction)
         unsigned long long base = 0ull;
+        uint32_t spec_base = 0u;
         if (lane == 0) base = atomicAdd((unsigned long long*)&O.totals->n_modified, (unsigned long long)n_mod);
         else if (lane == 1) base = atomicAdd((unsigned long long*)&O.totals->seq16_used, (unsigned long long)tot_seq);
         else if (lane == 2) base = atomicAdd((unsigned long long*)&O.totals->qual16_used, (unsigned long long)tot_qual);
-        else if (lane == 3) atomicAdd((unsigned long long*)&O.totals->session_reads, (unsigned long long)sess_reads);
-        else if (lane == 4) atomicAdd((unsigned long long*)&O.totals->session_bases, (unsigned long long)sess_bases);
-        else if (lane == 5) { O.sess_counts[4 * (size_t)s + 0] = cnt_snv; if (cnt_snv) atomicAdd((unsigned long long*)&O.totals->masked[0], (unsigned long long)cnt_snv); }
-        else if (lane == 6) { O.sess_counts[4 * (size_t)s + 1] = cnt_del; if (cnt_del) atomicAdd((unsigned long long*)&O.totals->masked[1], (unsigned long long)cnt_del); }
-        else if (lane == 7) { O.sess_counts[4 * (size_t)s + 2] = cnt_ins; if (cnt_ins) atomicAdd((unsigned long long*)&O.totals->masked[2], (unsigned long long)cnt_ins); }
-        else if (lane == 8) O.sess_counts[4 * (size_t)s + 3] = sess_reads;
+        else if (lane >= 5 && lane < 9) O.sess_counts[4 * (size_t)s + (lane - 5)] = lane == 5 ? cnt_snv : lane == 6 ? cnt_del : lane == 7 ? cnt_ins : sess_reads;
         else if (lane == 9) { E.germ[(size_t)s * kGermStride] = ngerm; E.germ[(size_t)s * kGermStride + 1] = (uint32_t)c.d.col_begin; }
-        n_q = warp_sum(n_q);
-        n_spec = warp_sum(n_spec);
-        uint32_t spec_base = 0u;
-        if (lane == 10 && n_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)n_q);
-        else if (lane == 11 && n_spec) spec_base = atomicAdd(E.n_special, n_spec);
+        else if (lane == 11) { if (n_spec) spec_base = atomicAdd(E.n_special, n_spec); }
+        acc_reads += sess_reads; acc_bases += sess_bases; acc_snv += cnt_snv; acc_del += cnt_del; acc_ins += cnt_ins; acc_q += n_q;
         spec_base = __shfl_sync(0xffffffffu, spec_base, 11);
         const unsigned long long base_rec = __shfl_sync(0xffffffffu, base, 0), base_seq = __shfl_sync(0xffffffffu, base, 1), base_qual = __shfl_sync(0xffffffffu, base, 2);
         const bool fits = (int64_t)(base_rec + n_mod) <= O.cap_records && (int64_t)(base_seq + tot_seq) <= O.cap_seq16 &&
                           (int64_t)(base_qual + tot_qual) <= O.cap_qual16;
         if (!fits) { if (lane == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); continue; }
-        // ---- record headers and the hand-over to the emission kernel
+        // ---- record headers and the hand-over to the emission kernels
+        uint32_t run_seq = 0u, run_qual = 0u;
+#pragma unroll 1
         for (uint32_t kb = 0; kb < n_mod; kb += 32) {
             const uint32_t k = kb + lane;
             const bool have_k = k < n_mod;
-            const uint32_t m = have_k ? sm->msize[k] : 0u;
-            const bool q = (m & kQualFlag) != 0u;
+            const uint32_t rn = have_k ? sm->rnew[k] : 0u;
+            const uint32_t kind = rn >> 24, new_len = rn & kLen2;
             const int i = have_k ? (int)sm->clist[k] : 0;
-            const bool is_spec = have_k && (q || ((sm->genbits[i >> 5] >> (i & 31)) & 1u) || sm->mpc[k] > 2);
+            const int64_t r = read_of(c, i);
+            uint32_t lf = 0u, so = 0u; int pos = 0;
+            if (have_k) { lf = __ldg(B.len_flag + r); so = __ldg(B.seq_off16 + r); pos = __ldg(B.pos + r); }
+            uint32_t units = have_k ? (new_len + 31u) / 32u : 0u; if (have_k && units < 1u) units = 1u;
+            uint32_t ts, tq;
+            const uint32_t so_rel = run_seq + warp_excl_scan(units, lane, &ts);
+            const uint32_t qo_rel = run_qual + warp_excl_scan(kind == 3u ? units : 0u, lane, &tq);
+            run_seq += ts; run_qual += tq;
+            const bool is_spec = have_k && kind != 1u;
             const uint32_t sb = __ballot_sync(0xffffffffu, is_spec);
             if (is_spec) E.special[spec_base + __popc(sb & ((1u << lane) - 1u))] = (uint32_t)(base_rec + k);
             spec_base += __popc(sb);
             if (!have_k) continue;
-            const int64_t r = read_of(c, i);
             const uint64_t rec_idx = base_rec + k;
-            const uint32_t mo = sm->moff[k];
-            const uint32_t qual16 = q ? (uint32_t)(base_qual + (mo >> 16)) : 0xffffffffu;
-            write_record_meta(O, rec_idx, s, r, (int)(m & kLen2), base_seq + (mo & 0xffffu), qual16);
-            const uint32_t L0 = __ldg(B.len_flag + r) & 0xffffu, so = __ldg(B.seq_off16 + r);
-            const int pos = __ldg(B.pos + r);
-            const uint32_t hits = sm->mpc[k];
-            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : (hits <= 2u ? 1 : 4));
-            E.kind[rec_idx] = kind;
-            if (kind == 1) E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | (hits << 16), sm->mpatch[k]);
+            const uint32_t qual16 = kind == 3u ? (uint32_t)(base_qual + qo_rel) : 0xffffffffu;
+            write_record_meta(O, rec_idx, s, r, (int)new_len, base_seq + so_rel, qual16);
+            const uint32_t L0 = lf & 0xffffu;
+            E.kind[rec_idx] = (uint8_t)kind;
+            if (kind == 1u) E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
             else E.edesc[rec_idx] = make_uint4(so, (uint32_t)pos, L0, (uint32_t)s);
-            if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
+            if (kind == 3u) {                                         // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
-                collect2(c, sm, (int)k, (int)L0, E2, &nl);
-                EditAux a;
-                a.irp0 = E2.irp[0]; a.pos0 = E2.pos[0]; a.len0 = (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u);
-                a.irp1 = E2.irp[1]; a.pos1 = E2.pos[1]; a.len1 = (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u);
-                a.ne = (uint32_t)E2.ne; a.n_del = (uint32_t)E2.n_del;
+                lean_collect(c, sm, (int)k, (int)L0, E2, &nl);
                 uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
-                const uint4* src = reinterpret_cast<const uint4*>(&a);
-                dst[0] = src[0]; dst[1] = src[1];
+                dst[0] = make_uint4((uint32_t)E2.irp[0], (uint32_t)E2.pos[0], (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u), (uint32_t)E2.irp[1]);
+                dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u), (uint32_t)E2.ne, (uint32_t)E2.n_del);
             }
         }
         __syncwarp();                                                 // tables are reused by the next session
     }
+    if (lane == 3 && acc_reads) atomicAdd((unsigned long long*)&O.totals->session_reads, acc_reads);
+    else if (lane == 4 && acc_bases) atomicAdd((unsigned long long*)&O.totals->session_bases, acc_bases);
+    else if (lane == 5 && acc_snv) atomicAdd((unsigned long long*)&O.totals->masked[0], (unsigned long long)acc_snv);
+    else if (lane == 6 && acc_del) atomicAdd((unsigned long long*)&O.totals->masked[1], (unsigned long long)acc_del);
+    else if (lane == 7 && acc_ins) atomicAdd((unsigned long long*)&O.totals->masked[2], (unsigned long long)acc_ins);
+    else if (lane == 10 && acc_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)acc_q);
 }
 
 }  // namespace ga

@@ -80,6 +80,7 @@ struct ItemCtx {
     int i_base;             // session-relative id of read `begin`
     int col_begin, n_cols, first;
     int relbase;            // (col_begin + 8) & ~7: reference nibble index of sref word 0
+    bool table_in_ref;      // col_begin >= 0 and col_begin + n_cols <= ref_len
     uint32_t ds;
     uint32_t* ent; ObsRec* obs;
     uint32_t n_ent, n_obs, n_reads, n_bases;   // n_ent / n_obs warp-uniform, n_reads / n_bases per lane (summed at the end)
@@ -221,7 +222,10 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
     const int L = (int)(m.lf & 0xffffu);
     const bool one_op = valid && (m.c1 - m.c0 == 1u);
     // a single-op read whose span L stays inside the reference and the session table
-    const bool spec = one_op && L <= 256 && pos >= 0 && (int64_t)pos + L <= c.B.ref_len && pos >= c.col_begin && pos + L - c.col_begin < c.n_cols;
+    // (when the whole table lies inside the reference - checked once per item - two compares say the same)
+    const bool spec = one_op && L <= 256 &&
+                      (c.table_in_ref ? (uint32_t)(pos - c.col_begin) < (uint32_t)(c.n_cols - L) && L < c.n_cols
+                                      : pos >= 0 && (int64_t)pos + L <= c.B.ref_len && pos >= c.col_begin && pos + L - c.col_begin < c.n_cols);
     const uint32_t op0 = cw0 & 15u;
     const bool clean = spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(cw0 >> 4) == L);
     const bool in_sess = clean && pos + L > c.first;                     // fetched by range but not reaching the region: skipped
@@ -229,8 +233,9 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
                                     : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * m.so);
     if (in_sess) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
     const int rel = pos + 8 - c.relbase;                                 // nibble offset of base `pos` inside the staged window
-    const int units = in_sess ? (L + 31) >> 5 : 0;
-    const int umax = __reduce_max_sync(0xffffffffu, units);
+    // Full 32-base units are compared without any masking; the last, partial unit once, after the loop.
+    const int full = in_sess ? L >> 5 : 0;
+    const int fmax = __reduce_max_sync(0xffffffffu, full);
     uint32_t wm = 0u;                                                    // bit k: 8-base word k differs from the reference
     {
         const uint32_t* rp = c.ws->sref + (in_sess ? (rel >> 3) : 0);
@@ -238,19 +243,23 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
         uint32_t prev = rp[0];
         const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
 #pragma unroll 1
-        for (int u = 0; u < umax; ++u) {
-            if (u < units) {
+        for (int u = 0; u < fmax; ++u) {
+            if (u < full) {
                 const uint4 v = rec4[u];
                 const uint32_t r1 = rp[4 * u + 1], r2 = rp[4 * u + 2], r3 = rp[4 * u + 3], r4 = rp[4 * u + 4];
-                uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
-                uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
+                const uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
+                const uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
                 prev = r4;
-                if (u == units - 1) {                                    // padding nibbles of the last unit
-                    x0 &= tail_mask(L, 4 * u); x1 &= tail_mask(L, 4 * u + 1); x2 &= tail_mask(L, 4 * u + 2); x3 &= tail_mask(L, 4 * u + 3);
-                }
-                const uint32_t bits = (x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u);
-                wm |= bits << (4 * u);
+                if (x0 | x1 | x2 | x3) wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * u);
             }
+        }
+        if (in_sess && (L & 31)) {                                       // the partial unit: padding nibbles masked
+            const int u = full;
+            const uint4 v = rec4[u];
+            const uint32_t r1 = rp[4 * u + 1], r2 = rp[4 * u + 2], r3 = rp[4 * u + 3], r4 = rp[4 * u + 4];
+            const uint32_t x0 = (v.x ^ __funnelshift_r(prev, r1, sh)) & tail_mask(L, 4 * u), x1 = (v.y ^ __funnelshift_r(r1, r2, sh)) & tail_mask(L, 4 * u + 1);
+            const uint32_t x2 = (v.z ^ __funnelshift_r(r2, r3, sh)) & tail_mask(L, 4 * u + 2), x3 = (v.w ^ __funnelshift_r(r3, r4, sh)) & tail_mask(L, 4 * u + 3);
+            wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * u);
         }
     }
     // ---- mismatching words: SNV candidates (variation_classifier.py:147-150), resolved from the staged bytes
@@ -316,6 +325,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
         c.n = c.ds ? n_end - n_begin : t_end - t_begin;
         c.i_base = c.ds ? t_end - t_begin : 0;
         c.relbase = (c.col_begin + 8) & ~7;
+        c.table_in_ref = c.col_begin >= 0 && (int64_t)c.col_begin + c.n_cols <= B.ref_len;
         c.ent = X.ent + (size_t)item * kEntHalf;
         c.obs = X.obs + (size_t)item * kObsHalf;
         c.n_ent = 0u; c.n_obs = 0u; c.n_reads = 0u; c.n_bases = 0u;
