@@ -175,6 +175,14 @@ int ga_engine_create(int device, ga_engine** out) {
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemL) * ga::kLeanWarps));
     cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // persistent kernels: exactly one wave of resident CTAs (a partial second wave would wait for the first to drain)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_scan, ga::scan_kernel, ga::kScanThreads, sizeof(ga::WarpSmem) * (ga::kScanThreads / 32));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_lean, ga::resolve_lean_kernel, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_res, ga::resolve_kernel, ga::kResThreads, sizeof(ga::SmemR));
+    if (const char* v = getenv("GA_OCC_SCAN")) e->occ_scan = std::min(e->occ_scan, std::max(1, atoi(v)));   // tuning knob: CTAs per SM of the scan kernel
+    if (e->occ_scan < 1) e->occ_scan = 1;
+    if (e->occ_lean < 1) e->occ_lean = 1;
+    if (e->occ_res < 1) e->occ_res = 1;
     *out = e;
     return GA_OK;
 }
@@ -370,16 +378,16 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     L.runs++;
     // stage 1: allele discovery, one warp per (session, dataset) item, persistent CTAs
     const int64_t n_items = 2 * (int64_t)S->n_sessions;
-    const int grid_scan = (int)std::min<int64_t>((int64_t)e->n_sm * 4, (n_items + ga::kScanThreads / 32 - 1) / (ga::kScanThreads / 32));
+    const int grid_scan = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_scan, (n_items + ga::kScanThreads / 32 - 1) / (ga::kScanThreads / 32));
     GA_CUDA(cudaEventRecord(L.ev[0][tslot], st));
     ga::scan_kernel<<<grid_scan, ga::kScanThreads, sizeof(ga::WarpSmem) * (ga::kScanThreads / 32), st>>>(B, V, L.d_descs, X, d_tickets, out->totals);
     GA_CUDA(cudaEventRecord(L.ev[1][tslot], st));
     // stage 2: germline set, modified-record list, output slots, headers - one warp per session, then one CTA per
     // session for those whose tables did not fit the lean capacities
     int32_t* d_nlarge = L.d_small + 12;
-    const int lean_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * 10, (S->n_sessions + ga::kLeanWarps - 1) / ga::kLeanWarps);
+    const int lean_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_lean, (S->n_sessions + ga::kLeanWarps - 1) / ga::kLeanWarps);
     ga::resolve_lean_kernel<<<lean_ctas, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
-    const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * 7, S->n_sessions);
+    const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_res, S->n_sessions);
     ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
     GA_CUDA(cudaEventRecord(L.ev[2][tslot], st));
     // oversize sessions and whatever the tables of stages 1-2 could not hold: global-scratch kernel, complete records;

@@ -39,6 +39,7 @@ struct ga_engine {
     int64_t big_bytes_per_cta = 0; int big_ctas = 0;
     int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
     int64_t launches = 0;
+    int occ_scan = 4, occ_lean = 9, occ_res = 6;   // resident CTAs per SM of the persistent kernels
     HostSlot* slots = nullptr;           // lazily created by ga_run_host
     int64_t last_h2d = 0, last_d2h = 0;
 };

@@ -52,6 +52,8 @@ struct SmemR {
     uint32_t o_sig0[kObsR], o_sig1[kObsR];
     int16_t o_next[kObsR], o_rnext[kObsR];
     int16_t ihash[kHashR];               // heads of the observation chains, hashed by column
+    uint32_t mpatch[kMod2];              // two germline hits of a clean read: (column << 4) | reference code, 16 bits each
+    uint8_t mpc[kMod2];                  // germline SNV hits per modified read
 };
 
 template <int T>
@@ -85,7 +87,7 @@ __device__ __forceinline__ unsigned long long block_scan64(unsigned long long v,
 
 __device__ __forceinline__ int acgt_index(uint32_t b) { return b == 1u ? 0 : b == 2u ? 1 : b == 4u ? 2 : b == 8u ? 3 : -1; }
 
-__global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+__global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                  int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
                                                                  const int32_t* __restrict__ large_list, const int32_t* __restrict__ n_large,
                                                                  ResultView O, ScanScratch X, EmitScratch2 E) {
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
             uint32_t b = bits;
             while (b) {
                 const int k = __ffs(b) - 1; b &= b - 1;
-                if (off < (uint32_t)kMod2) { sm->clist[off] = (uint16_t)(tid * 32 + k); sm->mhead[off] = (int16_t)-1; }
+                if (off < (uint32_t)kMod2) { sm->clist[off] = (uint16_t)(tid * 32 + k); sm->mhead[off] = (int16_t)-1; sm->mpc[off] = 0; }
                 ++off;
             }
         }
@@ -274,6 +276,20 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
             __syncthreads();
         }
 
+        // ---- the germline hits of every clean modified read (they travel in the emission descriptor)
+        for (int k = tid; k < n_ent; k += T) {
+            const uint32_t e = sm->ent[k];
+            if (e & kEntGen) continue;
+            const uint32_t col = (e >> 4) & 0xfffu;
+            const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
+            if (!((((byte & (byte >> 4)) >> acgt_index(e & 15u)) & 1u) && (e & 0xffffu) != keep_key)) continue;
+            const uint32_t i = (e >> 16) & 0xfffu;
+            const uint32_t m = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
+            uint32_t* cw = reinterpret_cast<uint32_t*>(sm->mpc) + (m >> 2);
+            const uint32_t have = (atomicAdd(cw, 1u << (8 * (m & 3u))) >> (8 * (m & 3u))) & 0xffu;   // at most kGermCap hits per read: no carry
+            if (have < 2u) reinterpret_cast<uint16_t*>(sm->mpatch)[2 * m + have] = (uint16_t)((col << 4) | (1u << ((e >> 29) & 3u)));
+        }
+        __syncthreads();
         // ---- new length of every modified read; indel-masked reads need the edit analysis
         const int per = ((int)n_mod + T - 1) / T;
         const int k0 = min(tid * per, (int)n_mod), k1 = min(k0 + per, (int)n_mod);
@@ -345,10 +361,14 @@ __global__ void __launch_bounds__(kResThreads, 7) resolve_kernel(BatchView B, Se
             const uint32_t qual16 = q ? (uint32_t)(s_base[2] + sm->mqual[k]) : 0xffffffffu;
             write_record_meta(O, rec_idx, s, r, (int)(m & kLen2), s_base[1] + sm->mseq[k], qual16);
             const uint32_t lf = __ldg(B.len_flag + r);
-            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : 4);
+            const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : (sm->mpc[k] <= 2 ? 1 : 4));
             E.kind[rec_idx] = kind;
-            E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)__ldg(B.pos + r), lf & 0xffffu, (uint32_t)s);
-            E.special[atomicAdd(E.n_special, 1u)] = (uint32_t)rec_idx;
+            const int pos = __ldg(B.pos + r);
+            if (kind == 1) E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
+            else {
+                E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)pos, lf & 0xffffu, (uint32_t)s);
+                E.special[atomicAdd(E.n_special, 1u)] = (uint32_t)rec_idx;
+            }
             if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
                 collect2(c, sm, k, (int)(lf & 0xffffu), E2, &nl);
@@ -381,7 +401,7 @@ constexpr int kLeanWarps = 2;            // warps per CTA
 constexpr int kReadsL = 1536;            // candidate reads per session
 constexpr int kModL = 256;               // modified reads per session
 constexpr int kObsL = 64;                // indel observations per session
-constexpr int kEntL = 384;               // candidate entries per session
+constexpr int kEntL = 512;               // candidate entries per session
 
 struct SmemL {
     uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
@@ -408,7 +428,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return inc - v;
 }
 
-__global__ void __launch_bounds__(32 * kLeanWarps, 10) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+__global__ void __launch_bounds__(32 * kLeanWarps, 9) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                             int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
                                                                             int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
                                                                             ResultView O, ScanScratch X, EmitScratch2 E) {

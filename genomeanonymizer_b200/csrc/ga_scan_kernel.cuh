@@ -19,7 +19,7 @@
 //                   session to the fallback kernel
 // The resolve kernel (ga_resolve_kernel.cuh) turns these into the germline set and the modified-record list.
 #pragma once
-#include "ga_session_v2.cuh"
+#include "ga_record_ops.cuh"
 
 namespace ga {
 
