@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--workload", default="chr1-30x-50k")
     ap.add_argument("--windows", type=int, default=0, help="debug: use only the first WINDOWS windows per rank")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--chunk-sessions", type=int, default=1024)
+    ap.add_argument("--chunk-sessions", type=int, default=4096)
     ap.add_argument("--sample-windows", type=int, default=0, help="CPU baseline sample (0 = auto, ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

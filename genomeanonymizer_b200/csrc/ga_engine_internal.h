@@ -8,7 +8,7 @@
 
 struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
 
-// Scratch of one in-flight ga_run: two lanes let the host pipeline overlap consecutive chunks.
+// Scratch of one in-flight ga_run: three lanes let the host pipeline overlap consecutive chunks.
 struct Lane {
     ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int32_t* d_large_list = nullptr; int64_t cap_sessions = 0;
     int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special
@@ -26,7 +26,7 @@ struct Lane {
 };
 constexpr int kTimedRuns = 32;
 
-constexpr int kLanes = 2;
+constexpr int kLanes = 3;
 
 struct HostSlot;   // ga_host_pipeline.cu
 

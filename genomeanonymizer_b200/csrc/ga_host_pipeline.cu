@@ -3,7 +3,7 @@
 // This is the call the reference-facing plugin makes (bench.py's `e2e` line): the caller hands over HOST
 // buffers (pinned for full PCIe speed) holding the reads of one contig and the session table; the engine
 // cuts the table into chunks of consecutive sessions, uploads only the read slices each chunk needs,
-// runs the chunk on one of two lanes (streams + scratch) so chunk k+1's upload overlaps chunk k's kernels
+// runs the chunk on one of three lanes (streams + scratch) so the uploads of the next chunks overlap chunk k's kernels
 // and download, and appends the compacted modified records to the caller's host result.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -308,12 +308,12 @@ int ga_run_host(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result
             maxspan = std::max(maxspan, sp);
         }
     }
-    if (chunk_sessions <= 0) chunk_sessions = 1024;
+    if (chunk_sessions <= 0) chunk_sessions = 4096;
     const int32_t step = (int32_t)std::min<int64_t>(chunk_sessions, ns);
     struct Pending { int32_t s0, s1; int64_t cap_rec, cap_seq, cap_qual; };
     int lane = 0;
     int status = GA_OK;
-    Pending inflight[kLanes]; bool has[kLanes] = {false, false};
+    Pending inflight[kLanes]; bool has[kLanes] = {};
     auto default_caps = [&](int32_t s0, int32_t s1, Pending* p) {
         // generous first guess from the slice size; an overflowing chunk is re-run with the exact need
         int64_t max_last = S->last[s0];
@@ -349,19 +349,18 @@ int ga_run_host(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result
     };
     for (int32_t s0 = 0; s0 < ns && status == GA_OK; s0 += step) {
         const int32_t s1 = std::min<int32_t>(ns, s0 + step);
-        // results are appended in chunk order: the other lane holds the previous chunk and is collected
-        // after this one has been queued, so its download overlaps this chunk's upload and kernels
-        status = finish(lane);                              // lane reuse: the chunk from two steps ago
+        // results are appended in chunk order: the oldest chunk in flight is collected after this one has been
+        // queued, so its download overlaps the upload and the kernels of the younger ones
+        status = finish(lane);                              // lane reuse: the chunk from kLanes steps ago
         if (status) break;
         Pending p; default_caps(s0, s1, &p);
         status = submit_chunk(e, lane, R, S, s0, s1, maxspan, p.cap_rec, p.cap_seq, p.cap_qual);
         if (status) break;
         inflight[lane] = p; has[lane] = true;
-        status = finish(lane ^ 1);
-        lane ^= 1;
+        lane = (lane + 1) % kLanes;
+        status = finish(lane);                              // the oldest chunk still in flight
     }
-    if (status == GA_OK) status = finish(lane);
-    if (status == GA_OK) status = finish(lane ^ 1);
+    for (int k = 0; k < kLanes && status == GA_OK; ++k) { status = finish(lane); lane = (lane + 1) % kLanes; }
     for (int l = 0; l < kLanes; ++l) if (e->slots[l].busy) { cudaStreamSynchronize(e->slots[l].st); e->slots[l].busy = false; }
     *out->totals = acc;
     if (status) return status;
