@@ -221,6 +221,16 @@ def main():
     cap_rec = db.n_reads // 3 + 1024
     upr = max(1, units // max(1, db.n_reads))
     dres = DeviceResult(n_w, cap_rec, cap_rec * (upr + 1), cap_rec * (upr + 1) // 2 + 1024, dev)
+    # size the caller-owned result once: a trial run reports what the workload needs (ga_totals holds the need
+    # when the capacities are exceeded)
+    eng.run_device(db, ds, dres)
+    torch.cuda.synchronize()
+    t0 = dres.read_totals()
+    if int(t0.error) == 5:                                    # GA_ERR_CAPACITY
+        cap_rec = int(t0.n_modified * 1.05) + 1024
+        del dres
+        torch.cuda.empty_cache()
+        dres = DeviceResult(n_w, cap_rec, int(t0.seq16_used * 1.05) + 1024, int(t0.qual16_used * 1.05) + 1024, dev)
     counters = torch.zeros(8, dtype=torch.int64, device=dev)
 
     def step():
@@ -299,7 +309,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         hb = HostBatch(db.to_host(), ds.to_host())
-        hres = HostResult(n_w, cap_rec, cap_rec * (upr + 1), cap_rec * (upr + 1) // 2 + 1024)
+        hres = HostResult(n_w, dres.cap_records, dres.cap_seq16, dres.cap_qual16)
         eng.run_host(hb, hres, args.chunk_sessions)            # warm-up: allocates the lane buffers
         barrier()
         sampler.start()

@@ -242,23 +242,31 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
         const uint32_t sh = (uint32_t)(rel & 7) * 4u;
         uint32_t prev = rp[0];
         const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
-#pragma unroll 1
-        for (int u = 0; u < fmax; ++u) {
-            if (u < full) {
-                const uint4 v = rec4[u];
-                const uint32_t r1 = rp[4 * u + 1], r2 = rp[4 * u + 2], r3 = rp[4 * u + 3], r4 = rp[4 * u + 4];
-                const uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
-                const uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
-                prev = r4;
-                if (x0 | x1 | x2 | x3) wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * u);
-            }
+#define GA_CMP_UNIT(U)                                                                                                     \
+        {                                                                                                                  \
+            const uint4 v = rec4[U];                                                                                       \
+            const uint32_t r1 = rp[4 * (U) + 1], r2 = rp[4 * (U) + 2], r3 = rp[4 * (U) + 3], r4 = rp[4 * (U) + 4];         \
+            const uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);               \
+            const uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);                 \
+            prev = r4;                                                                                                     \
+            wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * (U));                        \
         }
+        if (fmax == 4 && __all_sync(0xffffffffu, full == 4 || full == 0)) {   // 129..159-base reads (the common shape): unrolled, constant offsets
+            if (full) { GA_CMP_UNIT(0) GA_CMP_UNIT(1) GA_CMP_UNIT(2) GA_CMP_UNIT(3) }
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < fmax; ++u)
+                if (u < full) GA_CMP_UNIT(u)
+        }
+#undef GA_CMP_UNIT
         if (in_sess && (L & 31)) {                                       // the partial unit: padding nibbles masked
-            const int u = full;
+            const int u = full, nv = L & 31;                             // nv valid nibbles in this unit
             const uint4 v = rec4[u];
             const uint32_t r1 = rp[4 * u + 1], r2 = rp[4 * u + 2], r3 = rp[4 * u + 3], r4 = rp[4 * u + 4];
-            const uint32_t x0 = (v.x ^ __funnelshift_r(prev, r1, sh)) & tail_mask(L, 4 * u), x1 = (v.y ^ __funnelshift_r(r1, r2, sh)) & tail_mask(L, 4 * u + 1);
-            const uint32_t x2 = (v.z ^ __funnelshift_r(r2, r3, sh)) & tail_mask(L, 4 * u + 2), x3 = (v.w ^ __funnelshift_r(r3, r4, sh)) & tail_mask(L, 4 * u + 3);
+            const unsigned long long lo = nv >= 16 ? ~0ull : ((1ull << (4 * nv)) - 1ull);
+            const unsigned long long hi = nv <= 16 ? 0ull : ((1ull << (4 * (nv - 16))) - 1ull);
+            const uint32_t x0 = (v.x ^ __funnelshift_r(prev, r1, sh)) & (uint32_t)lo, x1 = (v.y ^ __funnelshift_r(r1, r2, sh)) & (uint32_t)(lo >> 32);
+            const uint32_t x2 = (v.z ^ __funnelshift_r(r2, r3, sh)) & (uint32_t)hi, x3 = (v.w ^ __funnelshift_r(r3, r4, sh)) & (uint32_t)(hi >> 32);
             wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * u);
         }
     }
