@@ -39,6 +39,10 @@ class GaResult(C.Structure):
                 ("out_seq4", _vp), ("out_qual", _vp), ("sess_counts", _vp), ("totals", _vp)]
 
 
+class GaFastqItems(C.Structure):
+    _fields_ = [("n_items", C.c_int64), ("read", _vp), ("record", _vp), ("names", _vp), ("name_off", _vp)]
+
+
 class GaSynthParams(C.Structure):
     _fields_ = [("contig_len", C.c_int64), ("seed", C.c_uint64), ("read_len", C.c_int32),
                 ("total_windows", C.c_int32), ("window_begin", C.c_int32), ("n_windows", C.c_int32),

@@ -10,7 +10,7 @@ _LIB = None
 
 # every entry point declared in include/ga_b200.h
 EXPORTS = ["ga_abi_version", "ga_status_string", "ga_engine_create", "ga_engine_destroy", "ga_last_error",
-           "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions",
+           "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions", "ga_fastq_layout", "ga_fastq_render",
            "ga_synth_plan_sizes", "ga_synth_reference", "ga_synth_sessions", "ga_synth_reads_count", "ga_synth_reads_fill",
            "ga_synth_reference_host", "ga_synth_sessions_host", "ga_synth_reads_count_host", "ga_synth_reads_fill_host"]
 
@@ -48,6 +48,12 @@ def lib():
     L.ga_stage_ms_history.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]
     L.ga_last_fallback_sessions.restype = C.c_int
     L.ga_last_fallback_sessions.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
+    L.ga_fastq_layout.restype = C.c_int
+    L.ga_fastq_layout.argtypes = [C.c_void_p, C.POINTER(_abi.GaReads), C.POINTER(_abi.GaResult), C.c_int64, C.POINTER(_abi.GaFastqItems),
+                                  C.c_void_p, C.c_void_p]
+    L.ga_fastq_render.restype = C.c_int
+    L.ga_fastq_render.argtypes = [C.c_void_p, C.POINTER(_abi.GaReads), C.POINTER(_abi.GaResult), C.c_int64, C.POINTER(_abi.GaFastqItems),
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.ga_run_host.restype = C.c_int
     L.ga_run_host.argtypes = [C.c_void_p, C.POINTER(_abi.GaReads), C.POINTER(_abi.GaSessions), C.POINTER(_abi.GaResult), C.c_int64]
     L.ga_last_host_traffic.restype = None

@@ -193,6 +193,7 @@ void ga_engine_destroy(ga_engine* e) {
     cudaDeviceSynchronize();
     ga_host_slots_destroy(e);
     for (auto& kv : e->refs) cudaFree(kv.second.d_ref4);
+    cudaFree(e->d_fastq_sums);
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = e->lanes[l];
         cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);

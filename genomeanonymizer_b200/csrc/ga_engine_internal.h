@@ -42,6 +42,7 @@ struct ga_engine {
     int occ_scan = 4, occ_lean = 9, occ_res = 6;   // resident CTAs per SM of the persistent kernels
     HostSlot* slots = nullptr;           // lazily created by ga_run_host
     int64_t last_h2d = 0, last_d2h = 0;
+    int64_t* d_fastq_sums = nullptr; int64_t cap_fastq_blocks = 0;   // ga_fastq_layout scratch
 };
 
 int ga_fail(ga_engine* e, int code, const char* what, cudaError_t ce = cudaSuccess);

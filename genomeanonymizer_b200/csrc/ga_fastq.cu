@@ -1,0 +1,194 @@
+// ga_fastq.cu - N1 of SURVEY.md 8(f): FASTQ records rendered on the device.
+//
+// Reference: AnonymizedRead.get_anonymized_fastq_record (anonymizer_methods.py:205-243) + generate_anonymized_read
+// (anonymizer_methods.py:57-58) + the writer's trailing newline (short_read_tumor_normal_anonymizer.py:157-158):
+//     "@" query_name "/" (1 if READ1 else 2) "\n" SEQ "\n+\n" QUAL "\n"
+// Reverse-strand reads are reverse-complemented for output (anonymizer_methods.py:205-214, table at :22); their
+// qualities are kept in original-read orientation internally and reversed again at print time
+// (anonymizer_methods.py:95, 213), i.e. they are printed in BAM order next to the reverse-complemented sequence
+// (quirk Q1) - which is the order ga_reads.qual and ga_result.out_qual already hold.
+// The reference only knows A, C, G, T, N (anything else raises TypeError); IUPAC codes are
+// complemented here by reversing the 4 bits of the BAM code, which is their IUPAC complement.
+//
+// Two calls: ga_fastq_layout sizes every record and scans the sizes into byte offsets; ga_fastq_render writes the
+// text, one warp per record, one character per lane and step (coalesced byte stores).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+
+#include "ga_engine_internal.h"
+
+namespace ga {
+
+constexpr int kScanBlock = 1024;
+
+struct FastqView {
+    const int32_t* read; const int32_t* record; const uint8_t* names; const int64_t* name_off; int64_t n_items;
+    // reads
+    const uint32_t* len_flag; const uint32_t* seq_off16; const uint8_t* seq4; const uint8_t* qual;
+    const int32_t* qual_reads; const uint32_t* qual_off16; int64_t n_qual; int64_t n_reads;
+    // records
+    const uint32_t* mod_len; const uint32_t* mod_seq_off16; const uint32_t* mod_qual_off16; const uint8_t* out_seq4; const uint8_t* out_qual;
+    int64_t n_records;
+};
+
+__device__ __forceinline__ int64_t item_bytes(const FastqView& V, int64_t k) {
+    const int32_t r = V.read[k], rec = V.record[k];
+    const int64_t nl = V.name_off[r + 1] - V.name_off[r];
+    const int64_t L = rec >= 0 ? (int64_t)V.mod_len[rec] : (int64_t)(V.len_flag[r] & 0xffffu);
+    return nl + 2 * L + 8;                                               // '@' '/' mate '\n' | '\n' '+' '\n' | '\n'
+}
+
+// exclusive scan of the record sizes, three small kernels: block sums, scan of the block sums, offsets
+__global__ void fastq_block_sums_kernel(FastqView V, int64_t* __restrict__ block_sums) {
+    __shared__ long long s_part[kScanBlock / 32];
+    const int64_t k = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    long long v = k < V.n_items ? item_bytes(V, k) : 0;
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        long long t = threadIdx.x < kScanBlock / 32 ? s_part[threadIdx.x] : 0;
+        for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void fastq_scan_sums_kernel(int64_t* __restrict__ block_sums, int64_t n_blocks, int64_t* __restrict__ total_out) {
+    // one warp walks the block sums 32 at a time (n_blocks = n_items / 1024: a few thousand at most per call)
+    const int lane = threadIdx.x;
+    long long run = 0;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += 32) {
+        const int64_t b = b0 + lane;
+        const long long v = b < n_blocks ? block_sums[b] : 0;
+        long long inc = v;
+        for (int d = 1; d < 32; d <<= 1) { const long long n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+        if (b < n_blocks) block_sums[b] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) *total_out = run;
+}
+
+__global__ void fastq_offsets_kernel(FastqView V, const int64_t* __restrict__ block_sums, int64_t* __restrict__ text_off) {
+    __shared__ long long s_part[kScanBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    const long long v = k < V.n_items ? item_bytes(V, k) : 0;
+    long long inc = v;
+    for (int d = 1; d < 32; d <<= 1) { const long long n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    long long before = block_sums[blockIdx.x];
+    for (int w = 0; w < warp; ++w) before += s_part[w];
+    if (k < V.n_items) text_off[k] = before + inc - v;
+}
+
+__device__ __forceinline__ uint8_t base_char(uint32_t code) {
+    // "=ACMGRSVTWYHKDBN" as two little-endian 64-bit words
+    const unsigned long long w0 = ((unsigned long long)'=') | ((unsigned long long)'A' << 8) | ((unsigned long long)'C' << 16) | ((unsigned long long)'M' << 24) |
+                                  ((unsigned long long)'G' << 32) | ((unsigned long long)'R' << 40) | ((unsigned long long)'S' << 48) | ((unsigned long long)'V' << 56);
+    const unsigned long long w1 = ((unsigned long long)'T') | ((unsigned long long)'W' << 8) | ((unsigned long long)'Y' << 16) | ((unsigned long long)'H' << 24) |
+                                  ((unsigned long long)'K' << 32) | ((unsigned long long)'D' << 40) | ((unsigned long long)'B' << 48) | ((unsigned long long)'N' << 56);
+    return (uint8_t)(((code & 8u) ? w1 : w0) >> (8u * (code & 7u)));
+}
+
+// One warp per record.
+__global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const int64_t* __restrict__ text_off, uint8_t* __restrict__ text,
+                                                           int64_t text_cap, ga_totals* totals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t k = warp0; k < V.n_items; k += n_warps) {
+        const int32_t r = V.read[k], rec = V.record[k];
+        if (r < 0 || r >= V.n_reads || rec >= V.n_records) { if (lane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)k); continue; }
+        const int64_t nb = V.name_off[r];
+        const int nl = (int)(V.name_off[r + 1] - nb);
+        const uint32_t lf = V.len_flag[r];
+        const bool reverse = ((lf >> 16) & 0x10u) != 0u;
+        const uint8_t mate = ((lf >> 16) & 0x40u) ? '1' : '2';           // anonymizer_methods.py:218
+        const int L = rec >= 0 ? (int)V.mod_len[rec] : (int)(lf & 0xffffu);
+        const uint32_t* seqw = rec >= 0 ? reinterpret_cast<const uint32_t*>(V.out_seq4 + 16ull * V.mod_seq_off16[rec])
+                                        : reinterpret_cast<const uint32_t*>(V.seq4 + 16ull * V.seq_off16[r]);
+        // qualities in printed (= BAM) order: the record's own when it carries them, else the read's
+        const uint8_t* q = nullptr;
+        if (rec >= 0 && V.mod_qual_off16[rec] != 0xffffffffu) q = V.out_qual + 32ull * V.mod_qual_off16[rec];
+        else if (V.qual && !V.qual_reads) q = V.qual + 32ull * V.seq_off16[r];
+        else if (V.qual) {
+            int64_t b = 0, e = V.n_qual;
+            while (b < e) { const int64_t m = (b + e) >> 1; if (V.qual_reads[m] < r) b = m + 1; else e = m; }
+            if (b < V.n_qual && V.qual_reads[b] == r) q = V.qual + 32ull * V.qual_off16[b];
+        }
+        const int64_t off = text_off[k];
+        const int64_t total = (int64_t)nl + 2ll * L + 8;
+        if (!q || off + total > text_cap) { if (lane == 0) raise_error(totals, q ? GA_ERR_CAPACITY : GA_ERR_BAD_ARGUMENT, (uint32_t)k); continue; }
+        uint8_t* out = text + off;
+        // header "@name/m\n"
+        for (int c = lane; c < nl + 4; c += 32)
+            out[c] = c == 0 ? (uint8_t)'@' : c <= nl ? V.names[nb + c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
+        // sequence (reverse-complemented for reverse reads: complement of a BAM code = its 4 bits reversed)
+        uint8_t* os = out + nl + 4;
+        for (int j = lane; j < L; j += 32) {
+            const int bj = reverse ? L - 1 - j : j;
+            uint32_t code = (seqw[bj >> 3] >> ((bj & 7) * 4)) & 15u;
+            if (reverse) code = __brev(code) >> 28;
+            os[j] = base_char(code);
+        }
+        if (lane < 3) os[L + lane] = lane == 1 ? (uint8_t)'+' : (uint8_t)'\n';
+        uint8_t* oq = os + L + 3;
+        for (int j = lane; j < L; j += 32) oq[j] = (uint8_t)(q[j] + 33u);    // anonymizer_methods.py:232
+        if (lane == 0) oq[L] = (uint8_t)'\n';
+    }
+}
+
+}  // namespace ga
+
+static ga::FastqView make_view(const ga_reads* R, const ga_result* O, const ga_fastq_items* I, int64_t n_records) {
+    ga::FastqView V;
+    V.read = I->read; V.record = I->record; V.names = I->names; V.name_off = I->name_off; V.n_items = I->n_items;
+    V.len_flag = R->len_flag; V.seq_off16 = R->seq_off16; V.seq4 = R->seq4; V.qual = R->qual;
+    V.qual_reads = R->qual_reads; V.qual_off16 = R->qual_off16; V.n_qual = R->qual_reads ? R->n_qual : 0; V.n_reads = R->n_reads;
+    V.mod_len = O ? O->mod_len : nullptr; V.mod_seq_off16 = O ? O->mod_seq_off16 : nullptr; V.mod_qual_off16 = O ? O->mod_qual_off16 : nullptr;
+    V.out_seq4 = O ? O->out_seq4 : nullptr; V.out_qual = O ? O->out_qual : nullptr;
+    V.n_records = O ? n_records : 0;
+    return V;
+}
+
+extern "C" {
+
+int ga_fastq_layout(ga_engine* e, const ga_reads* R, const ga_result* O, int64_t n_records, const ga_fastq_items* I,
+                    int64_t* text_off, void* stream_) {
+    if (!e || !R || !I || !text_off || I->n_items < 0) return ga_fail(e, GA_ERR_BAD_ARGUMENT, "ga_fastq_layout: null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    GA_CUDA(cudaSetDevice(e->device));
+    if (I->n_items == 0) { GA_CUDA(cudaMemsetAsync(text_off, 0, sizeof(int64_t), st)); return GA_OK; }
+    const int64_t n_blocks = (I->n_items + ga::kScanBlock - 1) / ga::kScanBlock;
+    if (n_blocks > e->cap_fastq_blocks) {
+        cudaFree(e->d_fastq_sums); e->d_fastq_sums = nullptr; e->cap_fastq_blocks = 0;
+        GA_CUDA(cudaMalloc(&e->d_fastq_sums, (size_t)(n_blocks + 1024) * sizeof(int64_t)));
+        e->cap_fastq_blocks = n_blocks + 1024;
+    }
+    const ga::FastqView V = make_view(R, O, I, n_records);
+    ga::fastq_block_sums_kernel<<<(unsigned)n_blocks, ga::kScanBlock, 0, st>>>(V, e->d_fastq_sums);
+    ga::fastq_scan_sums_kernel<<<1, 32, 0, st>>>(e->d_fastq_sums, n_blocks, text_off + I->n_items);
+    ga::fastq_offsets_kernel<<<(unsigned)n_blocks, ga::kScanBlock, 0, st>>>(V, e->d_fastq_sums, text_off);
+    e->launches += 3;
+    GA_CUDA(cudaGetLastError());
+    return GA_OK;
+}
+
+int ga_fastq_render(ga_engine* e, const ga_reads* R, const ga_result* O, int64_t n_records, const ga_fastq_items* I,
+                    const int64_t* text_off, uint8_t* text, int64_t text_cap, ga_totals* status, void* stream_) {
+    if (!e || !R || !I || !text_off || !text || !status || I->n_items < 0) return ga_fail(e, GA_ERR_BAD_ARGUMENT, "ga_fastq_render: null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    GA_CUDA(cudaSetDevice(e->device));
+    if (I->n_items == 0) return GA_OK;
+    const ga::FastqView V = make_view(R, O, I, n_records);
+    const int64_t warps = (I->n_items + 7) / 8;
+    const unsigned grid = (unsigned)std::min<int64_t>(warps, (int64_t)e->n_sm * 32);
+    ga::fastq_render_kernel<<<grid, 256, 0, st>>>(V, text_off, text, text_cap, status);
+    e->launches += 1;
+    GA_CUDA(cudaGetLastError());
+    return GA_OK;
+}
+
+}  // extern "C"

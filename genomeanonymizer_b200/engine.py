@@ -189,6 +189,43 @@ class Engine:
         R, S, O = dbatch.as_struct(), dsess.as_struct(), dres.as_struct()
         self._check(self._L.ga_run(self._h, C.byref(R), C.byref(S), C.byref(O), s))
 
+    def render_fastq(self, dbatch: DeviceBatch, names, reads_idx, records_idx=None, dres: "DeviceResult" = None, n_records: int = 0):
+        """FASTQ text of reads `reads_idx` (ga_fastq_layout + ga_fastq_render on the device).
+
+        names: query name of every read of the batch (list of str).  records_idx[k] >= 0 renders read reads_idx[k]
+        with the sequence / length / qualities of modified record records_idx[k] of `dres` (the reference prints the
+        masked read, anonymizer_methods.py:205-243); -1 renders the read as it came in.
+        Returns (text: bytes, offsets: np.ndarray[int64] of n+1 entries)."""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream(self.device).cuda_stream
+            n = len(reads_idx)
+            enc = [nm.encode("ascii") for nm in names]
+            name_off = np.zeros(len(enc) + 1, np.int64)
+            np.cumsum([len(b) for b in enc], out=name_off[1:])
+            blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+            dev = self.device
+            t_names = torch.from_numpy(blob.copy()).to(dev)
+            t_noff = torch.from_numpy(name_off).to(dev)
+            t_read = torch.as_tensor(np.asarray(reads_idx, np.int32)).to(dev)
+            rec = np.full(n, -1, np.int32) if records_idx is None else np.asarray(records_idx, np.int32)
+            t_rec = torch.as_tensor(rec).to(dev)
+            t_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            items = _abi.GaFastqItems(n, t_read.data_ptr(), t_rec.data_ptr(), t_names.data_ptr(), t_noff.data_ptr())
+            R = dbatch.as_struct()
+            O = dres.as_struct() if dres is not None else None
+            pO = C.byref(O) if O is not None else None
+            self._check(self._L.ga_fastq_layout(self._h, C.byref(R), pO, int(n_records), C.byref(items), t_off.data_ptr(), s))
+            total = int(t_off[-1].item())
+            t_text = torch.empty(max(1, total), dtype=torch.uint8, device=dev)
+            status = torch.zeros(_abi.TOTALS_BYTES, dtype=torch.uint8, device=dev)
+            self._check(self._L.ga_fastq_render(self._h, C.byref(R), pO, int(n_records), C.byref(items), t_off.data_ptr(),
+                                                t_text.data_ptr(), total, status.data_ptr(), s))
+            torch.cuda.synchronize(dev)
+            t = _abi.GaTotals.from_buffer_copy(status.cpu().numpy().tobytes())
+            if t.error:
+                _abi.raise_for_status(int(t.error), f"ga_fastq_render failed at item {t.error_detail}")
+            return t_text[:total].cpu().numpy().tobytes(), t_off.cpu().numpy()
+
     def check_device_status(self, dres: DeviceResult) -> _abi.GaTotals:
         t = dres.read_totals()
         if t.error:

@@ -210,6 +210,34 @@ int  ga_run_host(ga_engine* e, const ga_reads* reads, const ga_sessions* session
 /* Bytes moved host->device / device->host by the most recent ga_run_host() (bench.py's e2e line). */
 void ga_last_host_traffic(const ga_engine* e, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* ------------------------------------------------------------------ FASTQ rendering
+ * The step right after the masking path: AnonymizedRead.get_anonymized_fastq_record (anonymizer_methods.py:205-243,
+ * 57-58) plus the writer's newline (short_read_tumor_normal_anonymizer.py:157-158), rendered on the device:
+ *     "@" query_name "/" (1 if flag & 0x40 else 2) "\n" SEQ "\n+\n" QUAL "\n"
+ * Reverse reads (flag & 0x10) are reverse-complemented; qualities are printed in BAM order.
+ * Item k renders read read[k] of `reads`; when record[k] >= 0 its sequence and length (and its qualities, when the
+ * record has a quality slot) come from record record[k] of `result` (a modified record of a ga_run), otherwise the
+ * read is rendered as it came in.  Every rendered read needs a quality record in `reads` (dense upload, or listed
+ * in qual_reads) unless its result record carries one.  All pointers are DEVICE pointers.
+ * Implemented in genomeanonymizer_b200/csrc/ga_fastq.cu. */
+typedef struct ga_fastq_items {
+    int64_t n_items;
+    const int32_t* read;        /* [n_items] read index                                              */
+    const int32_t* record;      /* [n_items] index of the modified record that replaces it, or -1    */
+    const uint8_t* names;       /* concatenated query names, no terminators                          */
+    const int64_t* name_off;    /* [n_reads + 1] name of read r = names[name_off[r] .. name_off[r+1]) */
+} ga_fastq_items;
+
+/* text_off[n_items + 1] (device, OUTPUT): byte offset of every record in the text, text_off[n_items] = total size.
+ * result may be NULL when every record[k] is -1; n_records = number of valid records in result. */
+int  ga_fastq_layout(ga_engine* e, const ga_reads* reads, const ga_result* result, int64_t n_records,
+                     const ga_fastq_items* items, int64_t* text_off, void* stream);
+/* Writes the text (device buffer of text_cap bytes) at the offsets ga_fastq_layout produced.  status->error /
+ * error_detail (device) receive the first device-side failure (bad index, read without qualities, capacity). */
+int  ga_fastq_render(ga_engine* e, const ga_reads* reads, const ga_result* result, int64_t n_records,
+                     const ga_fastq_items* items, const int64_t* text_off, uint8_t* text, int64_t text_cap,
+                     ga_totals* status, void* stream);
+
 /* ------------------------------------------------------------------ device-side synthetic data
  * Benchmark input generator (SURVEY.md 8(d) "Synthetic generator"): counter-based hashing, so any
  * shard of windows can be generated independently on its own GPU and regenerated bit-identically.
