@@ -158,6 +158,67 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def bench_fastq(eng, cfg, dev, n_w, peak):
+    """ga_fastq_layout + ga_fastq_render over every read of the first n_w windows: masked where a session modified
+    the read (lowest record index wins), as it came in otherwise.  Dense synthetic qualities, 10-character names."""
+    import ctypes as C
+    import torch
+    from genomeanonymizer_b200 import _abi
+    from genomeanonymizer_b200 import synthdev as SD
+    from genomeanonymizer_b200.engine import DeviceResult
+    db, ds = SD.generate_device(cfg, dev, 0, n_w)
+    n = db.n_reads
+    units = db.seq4_bytes // 16 // max(1, n)
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    db.qual = torch.randint(2, 41, (db.seq4_bytes * 2 + 64,), dtype=torch.uint8, device=dev, generator=g)   # dense: record r at 32 * seq_off16[r]
+    db.qual_reads, db.qual_off16 = None, None
+    cap = n // 3 + 1024
+    dres = DeviceResult(n_w, cap, cap * (units + 1), cap * (units + 1) // 2 + 1024, dev)
+    eng.run_device(db, ds, dres)
+    torch.cuda.synchronize()
+    tot = eng.check_device_status(dres)
+    n_mod = int(tot.n_modified)
+    rec = torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+    rec.scatter_reduce_(0, dres.mod_read[:n_mod].long(), torch.arange(n_mod, dtype=torch.int32, device=dev), reduce="amin")
+    rec[rec == 2 ** 31 - 1] = -1
+    ids = torch.arange(n, device=dev)
+    digits = torch.stack([(ids // 10 ** k) % 10 for k in range(8, -1, -1)], 1).to(torch.uint8) + 48
+    lead = torch.where(ids < db.n_tumor, 84, 78).to(torch.uint8).unsqueeze(1)                          # 'T' / 'N'
+    names = torch.cat([lead, digits], 1).contiguous().flatten()
+    name_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * 10
+    reads_idx = torch.arange(n, dtype=torch.int32, device=dev)
+    t_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    items = _abi.GaFastqItems(n, reads_idx.data_ptr(), rec.data_ptr(), names.data_ptr(), name_off.data_ptr())
+    R, O = db.as_struct(), dres.as_struct()
+    L, st = eng._L, torch.cuda.current_stream(dev).cuda_stream
+    status = torch.zeros(_abi.TOTALS_BYTES, dtype=torch.uint8, device=dev)
+    eng._check(L.ga_fastq_layout(eng._h, C.byref(R), C.byref(O), n_mod, C.byref(items), t_off.data_ptr(), st))
+    total = int(t_off[-1].item())
+    text = torch.empty(total, dtype=torch.uint8, device=dev)
+    def once():
+        eng._check(L.ga_fastq_layout(eng._h, C.byref(R), C.byref(O), n_mod, C.byref(items), t_off.data_ptr(), st))
+        eng._check(L.ga_fastq_render(eng._h, C.byref(R), C.byref(O), n_mod, C.byref(items), t_off.data_ptr(), text.data_ptr(), total,
+                                     status.data_ptr(), st))
+    for _ in range(3):
+        once()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    err = _abi.GaTotals.from_buffer_copy(status.cpu().numpy().tobytes()).error
+    L_read = cfg.read_len
+    in_bytes = n * ((L_read + 1) // 2 + L_read + 10 + 4 + 4 + 4 + 8)       # seq4 + qual + name + len_flag + seq_off16 + indices + name offsets
+    bytes_all = in_bytes + total + 8 * n
+    return {"api": "ga_fastq_layout + ga_fastq_render (C ABI), device resident", "reads": n, "masked_reads": int((rec >= 0).sum().item()),
+            "text_bytes": total, "ms": ms, "reads_per_s": n / (ms * 1e-3), "achieved_gbs": bytes_all / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": bytes_all / (ms * 1e-3) / 1e9 / peak, "device_error": int(err),
+            "sample": f"every read of the first {n_w} windows"}
+
+
 def _has_cuda():
     try:
         import torch
@@ -179,6 +240,8 @@ def main():
     ap.add_argument("--sample-windows", type=int, default=0, help="CPU baseline sample (0 = auto, ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fastq", action="store_true")
+    ap.add_argument("--fastq-windows", type=int, default=10000, help="windows rendered by the FASTQ measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -333,6 +396,11 @@ def main():
                "api": "ga_run_host (C ABI), pinned host SoA in / host records out", "chunk_sessions": args.chunk_sessions}
         del hb, hres
 
+    # ---- next row of the scope table: FASTQ rendering of the masked reads, device resident
+    fastq = None
+    if rank == 0 and world == 1 and not args.no_fastq:
+        fastq = bench_fastq(eng, cfg, dev, min(n_w, args.fastq_windows), peak)
+
     # ---- CPU baseline on a bounded sample + parity of the sampled sessions (rank 0, N=1)
     cpu = None
     parity = None
@@ -365,7 +433,7 @@ def main():
                            "sharding": "one contig-sized region per GPU, no data-path collective" if world > 1 else "single GPU",
                            "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
                 "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "gpu_launches": total_launches,
                 "clocks": sampler.summary(), "parity_vs_oracle_on_sample": parity}
         print(json.dumps(line))
     if world > 1:
