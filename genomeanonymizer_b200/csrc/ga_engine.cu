@@ -113,7 +113,7 @@ __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* ti
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         memset(totals, 0, sizeof(ga_totals));
         *n_big = 0; tickets[0] = 0; tickets[1] = 0; *maxspan = given_span;
-        for (int k = 4; k < 14; ++k) n_big[k] = 0;                    // fallback reasons, n_large, n_special
+        for (int k = 4; k < 15; ++k) n_big[k] = 0;                    // fallback reasons, n_large, n_special, second fallback ticket
     }
 }
 
@@ -173,6 +173,7 @@ int ga_engine_create(int device, ga_engine** out) {
     cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemR));
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ga::session_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemLayout));
     cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemL) * ga::kLeanWarps));
     cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // persistent kernels: exactly one wave of resident CTAs (a partial second wave would wait for the first to drain)
@@ -395,6 +396,8 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     // it runs on a side stream beside stage 3 (it only appends records, which the emission kernel skips)
     GA_CUDA(cudaEventRecord(L.ev_fork, st));
     GA_CUDA(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
+    ga::session_kernel<false><<<e->n_sm * 2, ga::kThreads, sizeof(ga::SmemLayout), L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr,
+                                                                                               reinterpret_cast<unsigned int*>(L.d_small + 14));
     ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
     GA_CUDA(cudaEventRecord(L.ev_join, L.side));
     // stage 3: record bodies
@@ -403,7 +406,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
     GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
-    e->launches += 6;
+    e->launches += 7;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

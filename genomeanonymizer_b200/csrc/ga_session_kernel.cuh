@@ -395,6 +395,8 @@ struct BigScratch {       // per-CTA slice of global scratch for oversized sessi
     int32_t cols_cap, reads_cap, obs_cap;
 };
 
+// BIG: tables in the CTA's slice of global scratch, otherwise in shared memory (SmemLayout).  The engine launches both
+// over big_list: the shared-memory variant takes the listed sessions whose tables fit it, the global-scratch one the rest.
 template <bool BIG>
 __global__ void __launch_bounds__(kThreads) session_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                            const int32_t* __restrict__ big_list, const int32_t* __restrict__ n_big,
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kThreads) session_kernel(BatchView B, SessView
         c.T.obs_cap = kObsCap; c.T.reads_cap = kReadsCap; c.T.cols_cap = kColsCap;
     }
     const int tid = threadIdx.x;
-    const int n_work = BIG ? *n_big : S.n_sessions;
+    const int n_work = *n_big;
 
     for (;;) {
         __syncthreads();
@@ -437,12 +439,13 @@ __global__ void __launch_bounds__(kThreads) session_kernel(BatchView B, SessView
         __syncthreads();
         const int widx = s_session;
         if (widx >= n_work) break;
-        const int s = BIG ? big_list[widx] : widx;
+        const int s = big_list[widx];
         c.d = descs[s];
-        if (!BIG && c.d.big) continue;
         c.s = s;
         c.nt = c.d.t_end - c.d.t_begin;
         c.n_range = c.nt + (c.d.n_end - c.d.n_begin);
+        const bool fits_smem = c.d.n_cols <= kColsCap && c.n_range <= kReadsCap && c.d.obs_bound <= kObsCap;
+        if (BIG == fits_smem) continue;                              // the other variant's session
         c.first = S.first[s];
         c.keep_type = S.keep_type[s]; c.keep_pos = S.keep_pos[s]; c.keep_end = S.keep_end[s]; c.keep_len = S.keep_len[s];
         c.keep_allele = S.keep_alleles + S.keep_allele_off[s];
