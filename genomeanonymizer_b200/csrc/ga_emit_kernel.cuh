@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
 //      floor(mean(qualities)), INS -> the inserted bases and qualities go (anonymizer_methods.py:178-203); edits
 //      index the forward-orientation quality array, printed order = BAM order (anonymizer_methods.py:95, 213).
 __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r,
-                                                   int pos, int L, uint32_t src_unit, int col_begin, const GermList& germ, int64_t q_lo, int64_t q_hi,
+                                                   int pos, int L, uint32_t src_unit, int col_begin, const GermList& germ, const uint8_t* qrec,
                                                    uint32_t* stage, uint64_t seq16, uint64_t qual16, int new_len, int glane) {
     const int nw = (L + 7) >> 3;
     uint32_t c0 = 0u, c1 = 0u;
@@ -134,12 +134,8 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     const bool is_del = E.n_del == 1;
     const int p = E.p[0], len = E.len[0], shift = is_del ? -len : E.e[0] - E.p[0];      // source = final + shift behind the edit
     const int ins_end = is_del ? p + len : p;                                             // [p, ins_end): re-inserted elements
-    const uint8_t* qrec = nullptr;
     bool ok = indel;
-    if (indel) {
-        qrec = qual_record_in(B, r, q_lo, q_hi);
-        if (!qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); ok = false; }
-    }
+    if (indel && !qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); ok = false; }
     uint32_t mean = 0u;
     if (__any_sync(0xffffffffu, ok && is_del)) {                      // quality of re-inserted bases (anonymizer_methods.py:193)
         uint32_t part = 0;
@@ -156,49 +152,48 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
         if (ok && is_del && glane == 0 && (int64_t)E.pos[0] + len > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
     }
     if (!ok) return;
-    auto src_of = [&](int j) { return j < p ? j : (j < ins_end ? -1 : j + shift); };     // final index -> original index, -1: re-inserted
+    // The final array is three pieces: [0, p) = source as is, [p, ins_end) = re-inserted reference bases (DEL only),
+    // [ins_end, new_len) = source shifted by `shift`.  Every output word is merged from the (at most three) pieces it
+    // overlaps with nibble / byte masks - no per-element loop.
+    auto low_nibbles = [](int cnt) -> uint32_t { return cnt >= 8 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((8 - cnt) * 4))); };
+    auto low_bytes = [](int cnt) -> uint32_t { return cnt >= 4 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((4 - cnt) * 8))); };
+    auto stage_at = [&](int sidx) -> uint32_t {                        // 8 staged bases from source index sidx (>= -7; nibbles outside the read are masked by the caller)
+        if (sidx < 0) return stage[0] << ((-sidx) * 4);
+        return __funnelshift_r(stage[sidx >> 3], stage[(sidx >> 3) + 1], (uint32_t)(sidx & 7) * 4u);
+    };
     for (int w = glane; w < units * 4; w += kGroup) {
         const int j0 = w << 3;
         uint32_t v = 0u;
         if (j0 < new_len) {
-            const int jl = min(j0 + 7, new_len - 1);
-            const int s0 = src_of(j0), sl = src_of(jl);
-            if (s0 >= 0 && sl - s0 == jl - j0) {                       // one contiguous run of input bases
-                v = __funnelshift_r(stage[s0 >> 3], stage[(s0 >> 3) + 1], (uint32_t)(s0 & 7) * 4u);
-            } else if (j0 >= p && jl < ins_end) {                      // inside the re-inserted reference bases
-                v = ref_word(B.ref4, (int64_t)E.pos[0] + (j0 - p));
-            } else {
-                for (int n = 0; n <= jl - j0; ++n) {
-                    const int sj = src_of(j0 + n);
-                    const uint32_t code = sj >= 0 ? (stage[sj >> 3] >> ((sj & 7) * 4)) & 15u : ref_code(B.ref4, (int64_t)E.pos[0] + (j0 + n - p));
-                    v |= code << (n * 4);
-                }
-            }
-            if (jl - j0 < 7) v &= 0xffffffffu >> ((7 - (jl - j0)) * 4);
+            const uint32_t mA = low_nibbles(p - j0), mAB = low_nibbles(ins_end - j0);
+            if (mA) v = stage_at(j0) & mA;
+            if (mAB & ~mA) v |= ref_word(B.ref4, (int64_t)E.pos[0] + (j0 - p)) & (mAB & ~mA);
+            if (~mAB) v |= stage_at(j0 + shift) & ~mAB;
+            v &= low_nibbles(new_len - j0);
         }
         oseq[w] = v;
     }
+    // qualities in printed (= BAM) order.  The edit indexes the forward-orientation array (anonymizer_methods.py:95,
+    // 187, 195: quirk Q2), so for a reverse read the pieces come in the opposite order: printed [0, b1) = BAM bytes as
+    // they are, [b1, b2) = the mean, [b2, new_len) = BAM bytes shifted by d3.
     const bool reverse = ((__ldg(B.len_flag + r) >> 16) & 0x10u) != 0u;
-    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    const int b1 = reverse ? new_len - ins_end : p, b2 = reverse ? new_len - p : ins_end, d3 = reverse ? L - new_len : shift;
     const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+    auto qual_at = [&](int bidx) -> uint32_t {                         // 4 quality bytes from BAM byte bidx (>= -3)
+        if (bidx < 0) return __ldg(qw) << ((-bidx) * 8);
+        const uint32_t lo = __ldg(qw + (bidx >> 2)), hi = (bidx & 3) ? __ldg(qw + (bidx >> 2) + 1) : 0u;
+        return __funnelshift_r(lo, hi, (uint32_t)(bidx & 3) * 8u);
+    };
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
     for (int w = glane; w < units * 8; w += kGroup) {
         const int p0 = w << 2;
         uint32_t v = 0u;
         if (p0 < new_len) {
-            const int pl = min(p0 + 3, new_len - 1);
-            const int s0 = src_of(reverse ? new_len - 1 - p0 : p0), s3 = src_of(reverse ? new_len - 1 - pl : pl);
-            if (s0 >= 0 && s3 >= 0 && (reverse ? s0 - s3 : s3 - s0) == pl - p0) {
-                const int b0 = reverse ? L - 1 - s0 : s0;               // byte of the BAM-order quality record
-                const uint32_t lo = __ldg(qw + (b0 >> 2)), hi = (b0 & 3) ? __ldg(qw + (b0 >> 2) + 1) : 0u;
-                v = __funnelshift_r(lo, hi, (uint32_t)(b0 & 3) * 8u);
-            } else {
-                for (int n = 0; n <= pl - p0; ++n) {
-                    const int sj = src_of(reverse ? new_len - 1 - (p0 + n) : p0 + n);
-                    const uint32_t qv = sj >= 0 ? (uint32_t)qrec[reverse ? L - 1 - sj : sj] : mean;
-                    v |= qv << (n * 8);
-                }
-            }
-            if (pl - p0 < 3) v &= 0xffffffffu >> ((3 - (pl - p0)) * 8);
+            const uint32_t m1 = low_bytes(b1 - p0), m12 = low_bytes(b2 - p0);
+            if (m1) v = qual_at(p0) & m1;
+            if (m12 & ~m1) v |= (mean * 0x01010101u) & (m12 & ~m1);
+            if (~m12) v |= qual_at(p0 + d3) & ~m12;
+            v &= low_bytes(new_len - p0);
         }
         oq[w] = v;
     }
@@ -259,22 +254,31 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
 #pragma unroll
                 for (int q = 0; q < 2; ++q) { Ed.irp[q] = 0; Ed.len[q] = 0; Ed.pos[q] = 0; Ed.mean[q] = 0u; Ed.p[q] = 0; Ed.e[q] = 0; }
                 int64_t q_lo = 0, q_hi = 0;
+                const uint8_t* qrec = nullptr;
                 const int L = (int)d.z;
                 if (indel) {
                     const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
                     const uint4 x0 = ap[0], x1 = ap[1];              // EditAux written by the resolve kernel
                     Ed.irp[0] = (int)x0.x; Ed.pos[0] = (int)x0.y; Ed.len[0] = (int)(x0.z & 0x7fffffffu);
                     Ed.irp[1] = (int)x0.w; Ed.pos[1] = (int)x1.x; Ed.len[1] = (int)(x1.y & 0x7fffffffu);
-                    Ed.ne = (int)x1.z; Ed.n_del = (int)x1.w;
+                    Ed.ne = (int)(x1.z & 0xffu); Ed.n_del = (int)((x1.z >> 8) & 0xffu);
                     clamp_edits2(Ed, L);
                     const bool tumor = r < B.n_tumor;
                     q_lo = tumor ? descs[s].qt_begin : descs[s].qn_begin; q_hi = tumor ? descs[s].qt_end : descs[s].qn_end;
+                    // the read's quality record: dense upload, or the slot the resolve kernel predicted in the sparse
+                    // index (verified; a caller may list more reads than those with I/D ops), or a search of the slice
+                    if (B.qual && !B.qual_reads) qrec = B.qual + 32ull * r_src;
+                    else if (B.qual) {
+                        const int64_t qi = (int64_t)x1.w;
+                        if (qi < B.n_qual && __ldg(B.qual_reads + qi) == (int32_t)r) qrec = B.qual + 32ull * __ldg(B.qual_off16 + qi);
+                        else qrec = qual_record_in(B, r, q_lo, q_hi);
+                    }
                 }
                 __syncwarp();                                         // every lane of the group has read the aux before it is overwritten
                 // the common shapes take the staged path; two edits or very long reads take the general one
                 const bool fast = (r_kind == 2u || (indel && Ed.ne == 1)) && ((L + 7) >> 3) <= kGroupStage - 1;
                 if (__any_sync(0xffffffffu, fast))
-                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, col_begin, germ, q_lo, q_hi, stage[group], seq16, qual16, new_len, glane);
+                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, col_begin, germ, qrec, stage[group], seq16, qual16, new_len, glane);
                 if (r_kind == 2u && !fast) {
                     const uint32_t c0 = __ldg(B.cigar_off + r), c1 = __ldg(B.cigar_off + r + 1);
                     int units = (new_len + 31) >> 5; if (units < 1) units = 1;

@@ -16,7 +16,9 @@ constexpr uint32_t kLen2 = (1u << 24) - 1;   // msize: length bits (flags above:
 constexpr int kGermCap = 32;           // germline SNV alleles per session handed to the emission kernels
 constexpr int kGroup = 8;              // lanes that cooperate on one non-trivial output record
 
-struct EditAux { int32_t irp0, pos0; uint32_t len0; int32_t irp1, pos1; uint32_t len1; uint32_t ne, n_del; };   // len bit 31 = INS
+struct EditAux { int32_t irp0, pos0; uint32_t len0; int32_t irp1, pos1; uint32_t len1; uint32_t ne_ndel, qidx; };   // len bit 31 = INS; ne | n_del << 8;
+// qidx = the read's expected slot in ga_reads.qual_reads (its slice begin + the read's ordinal among the item's
+// reads with an I/D op), 0xffffffff when unknown: the emission kernel verifies it and searches otherwise
 static_assert(sizeof(EditAux) == 32, "EditAux fills one 32-byte quality unit");
 
 

@@ -375,7 +375,13 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
                 EditAux a;
                 a.irp0 = E2.irp[0]; a.pos0 = E2.pos[0]; a.len0 = (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u);
                 a.irp1 = E2.irp[1]; a.pos1 = E2.pos[1]; a.len1 = (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u);
-                a.ne = (uint32_t)E2.ne; a.n_del = (uint32_t)E2.n_del;
+                a.ne_ndel = (uint32_t)E2.ne | ((uint32_t)E2.n_del << 8);
+                {   // where the read's quality record should sit in the sparse index
+                    const int o = (int)sm->mhead[k];
+                    const ObsRec* ob = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
+                    const uint32_t qord = __ldg(&(o < n_obs0 ? ob + o : ob + kObsHalf + (o - n_obs0))->qord);
+                    a.qidx = (uint32_t)(i < c.nt ? c.d.qt_begin : c.d.qn_begin) + qord;
+                }
                 uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
                 const uint4* src = reinterpret_cast<const uint4*>(&a);
                 dst[0] = src[0]; dst[1] = src[1];
@@ -739,7 +745,12 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 9) resolve_lean_kernel(BatchV
                 lean_collect(c, sm, (int)k, (int)L0, E2, &nl);
                 uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
                 dst[0] = make_uint4((uint32_t)E2.irp[0], (uint32_t)E2.pos[0], (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u), (uint32_t)E2.irp[1]);
-                dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u), (uint32_t)E2.ne, (uint32_t)E2.n_del);
+                const int o = sm->mhead[k];                           // any germline observation of the read knows its ordinal
+                const ObsRec* ob = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
+                const uint32_t qord = __ldg(&(o < (int)n_obs0 ? ob + o : ob + kObsHalf + (o - (int)n_obs0))->qord);
+                const uint32_t qidx = (uint32_t)(i < c.nt ? c.d.qt_begin : c.d.qn_begin) + qord;
+                dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u),
+                                    (uint32_t)E2.ne | ((uint32_t)E2.n_del << 8), qidx);
             }
         }
         __syncwarp();                                                 // tables are reused by the next session

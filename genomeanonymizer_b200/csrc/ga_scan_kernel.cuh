@@ -31,7 +31,7 @@ constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean 
 constexpr uint32_t kCntOverflow = 0xffffffffu;
 constexpr int kScanThreads = 256;
 
-struct ObsRec { int32_t col; uint32_t meta; uint32_t read_alen; int32_t irp; uint32_t sig0, sig1, pad0, pad1; };
+struct ObsRec { int32_t col; uint32_t meta; uint32_t read_alen; int32_t irp; uint32_t sig0, sig1, qord, pad1; };   // qord: the read's ordinal among the item's reads with an I/D op
 static_assert(sizeof(ObsRec) == 32, "ObsRec is two 16-byte stores");
 
 struct ScanScratch {
@@ -84,6 +84,7 @@ struct ItemCtx {
     uint32_t ds;
     uint32_t* ent; ObsRec* obs;
     uint32_t n_ent, n_obs, n_reads, n_bases;   // n_ent / n_obs warp-uniform, n_reads / n_bases per lane (summed at the end)
+    uint32_t n_qord;                           // reads with an I or D op seen so far in the item (= their order in ga_reads.qual_reads)
 };
 
 __device__ __forceinline__ void push_entry_w(const ItemCtx& c, int i, int col, uint32_t b, uint32_t rf, uint32_t gen) {
@@ -111,10 +112,14 @@ __device__ __forceinline__ void flush_entries(ItemCtx& c, int lane) {
 __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, int pos, int L, uint32_t c0, uint32_t c1, const uint32_t* rec, int lane) {
     const BatchView& B = c.B;
     int span = 0;
+    bool has_id = false;
     for (uint32_t ci = c0; ci < c1; ++ci) {
         const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
         if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
+        has_id |= (op == 1u || op == 2u);
     }
+    const uint32_t qord = c.n_qord;                                      // counted before any early exit: the quality index lists every such read
+    if (has_id) c.n_qord += 1u;
     if (pos + span <= c.first) return;                                   // fetched by range, does not reach the region
     if (lane == 0) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
     if ((int64_t)pos + span > B.ref_len || pos < 0 || pos < c.col_begin || pos + span - c.col_begin >= c.n_cols) {
@@ -173,7 +178,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                 }
                 uint4* dst = reinterpret_cast<uint4*>(c.obs + n_obs);
                 dst[0] = make_uint4((uint32_t)(rc - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
-                dst[1] = make_uint4(s0, s1, 0u, 0u);
+                dst[1] = make_uint4(s0, s1, qord, 0u);
                 ++n_obs;
                 if (op == 1u) { q += ln; rcb += ln; } else { rc += ln; ccl += ln; rcb -= ln; }
             } else if (op == 3u) { rc += ln; ccl += ln; }
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
         c.table_in_ref = c.col_begin >= 0 && (int64_t)c.col_begin + c.n_cols <= B.ref_len;
         c.ent = X.ent + (size_t)item * kEntHalf;
         c.obs = X.obs + (size_t)item * kObsHalf;
-        c.n_ent = 0u; c.n_obs = 0u; c.n_reads = 0u; c.n_bases = 0u;
+        c.n_ent = 0u; c.n_obs = 0u; c.n_reads = 0u; c.n_bases = 0u; c.n_qord = 0u;
         if (!big && c.n > 0) {
             // ---- the session's reference window (+ record padding, + funnel-shift lookahead)
             {

@@ -4,7 +4,7 @@
 out=${OUT:-gpurun_out/launches_tmp.csv}
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none \
   -k regex:"scan_kernel|resolve|emit|session_kernel|assign_sessions|clear_kernel" -c 80 --csv --log-file $out \
-  python bench.py --steps 1 --no-e2e --no-cpu-baseline "$@" > /dev/null 2>&1
+  python bench.py --steps 1 --no-e2e --no-cpu-baseline --no-fastq "$@" > /dev/null 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open("$out")) if len(r)>5]
