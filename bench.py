@@ -357,7 +357,17 @@ def main():
     pass_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else float("nan")
     ach = single / (pass_ms * 1e-3) / 1e9
     scan_bytes = single - (int(tot.n_modified) * 20 + 2 * 16 * int(tot.seq16_used) + 2 * 32 * int(tot.qual16_used))
-    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # DRAM bytes of one pass from the committed ncu --set full capture (profiles/), when it is of this workload
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_stream_traffic.json")) as f:
+            tj = json.load(f)
+        if tj["workload"] == cfg.name and tj["windows"] == n_w:
+            traffic, traffic_src = tj["dram_bytes_per_pass"], tj["source"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "masking pass = scan_kernel + resolve_lean_kernel + resolve_kernel + emit_kernel (|| session_kernel<fallback>)", "kernel_ms": pass_ms,
                 "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernels": stage_ms[1], "emit_kernel": stage_ms[2],
