@@ -204,13 +204,15 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
 __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
     __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
     const int tid = threadIdx.x, group = tid / kGroup, glane = tid % kGroup;
-    const uint32_t n_x = *E.n_special;
+    const unsigned long long n_all = O.totals->n_modified;
+    const int64_t n_rec = (int64_t)(n_all < (unsigned long long)O.cap_records ? n_all : (unsigned long long)O.cap_records);
+    const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
     const uint32_t groups_total = gridDim.x * (kThreads / kGroup);
     for (uint32_t jb = blockIdx.x * (kThreads / kGroup) + (tid >> 5) * 4; jb < n_x; jb += groups_total) {   // warp-uniform
         const uint32_t j = jb + ((tid & 31) >> 3);
         const bool have = j < n_x;
         const int64_t k = have ? (int64_t)E.special[j] : 0;
-        const uint32_t r_kind = have ? E.kind[k] : 0u;
+        const uint32_t r_kind = (have && k < n_rec) ? E.kind[k] : 0u;    // 0xffffffff marks a slot of a session that did not fit
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
         int64_t r = 0; int new_len = 0; uint64_t seq16 = 0, qual16 = 0;
         if (r_kind) { d = E.edesc[k]; r = O.mod_read[k]; new_len = (int)O.mod_len[k]; seq16 = O.mod_seq_off16[k]; qual16 = O.mod_qual_off16[k]; }

@@ -331,6 +331,9 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     if (R->n_reads < 0 || R->n_tumor < 0 || R->n_tumor > R->n_reads || S->n_sessions < 0)
         return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: negative or inconsistent sizes");
     if (R->n_reads > 0x7fffffffll) return fail(e, GA_ERR_UNSUPPORTED, "ga_run: more than 2^31-1 reads in one batch");
+    if ((reinterpret_cast<uintptr_t>(R->seq4) & 15u) || (reinterpret_cast<uintptr_t>(R->qual) & 15u) ||
+        (reinterpret_cast<uintptr_t>(out->out_seq4) & 15u) || (reinterpret_cast<uintptr_t>(out->out_qual) & 15u))
+        return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: seq4 / qual / out_seq4 / out_qual must be 16-byte aligned (128-bit and TMA accesses)");
     auto it = e->refs.find(R->contig_id);
     if (it == e->refs.end()) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: reference contig was not uploaded");
     Lane& L = e->lanes[lane];

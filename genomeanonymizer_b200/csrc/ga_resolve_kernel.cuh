@@ -367,7 +367,8 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             if (kind == 1) E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
             else {
                 E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)pos, lf & 0xffffu, (uint32_t)s);
-                E.special[atomicAdd(E.n_special, 1u)] = (uint32_t)rec_idx;
+                const uint32_t slot = atomicAdd(E.n_special, 1u);
+                if ((int64_t)slot < O.cap_records) E.special[slot] = (uint32_t)rec_idx;
             }
             if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
@@ -710,7 +711,11 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 9) resolve_lean_kernel(BatchV
         const unsigned long long base_rec = __shfl_sync(0xffffffffu, base, 0), base_seq = __shfl_sync(0xffffffffu, base, 1), base_qual = __shfl_sync(0xffffffffu, base, 2);
         const bool fits = (int64_t)(base_rec + n_mod) <= O.cap_records && (int64_t)(base_seq + tot_seq) <= O.cap_seq16 &&
                           (int64_t)(base_qual + tot_qual) <= O.cap_qual16;
-        if (!fits) { if (lane == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu); continue; }
+        if (!fits) {                                                  // the reserved special slots must not stay undefined
+            for (uint32_t t = lane; t < n_spec; t += 32) if ((int64_t)(spec_base + t) < O.cap_records) E.special[spec_base + t] = 0xffffffffu;
+            if (lane == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu);
+            continue;
+        }
         // ---- record headers and the hand-over to the emission kernels
         uint32_t run_seq = 0u, run_qual = 0u;
 #pragma unroll 1
@@ -730,7 +735,8 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 9) resolve_lean_kernel(BatchV
             run_seq += ts; run_qual += tq;
             const bool is_spec = have_k && kind != 1u;
             const uint32_t sb = __ballot_sync(0xffffffffu, is_spec);
-            if (is_spec) E.special[spec_base + __popc(sb & ((1u << lane) - 1u))] = (uint32_t)(base_rec + k);
+            if (is_spec && (int64_t)(spec_base + __popc(sb & ((1u << lane) - 1u))) < O.cap_records)
+                E.special[spec_base + __popc(sb & ((1u << lane) - 1u))] = (uint32_t)(base_rec + k);
             spec_base += __popc(sb);
             if (!have_k) continue;
             const uint64_t rec_idx = base_rec + k;

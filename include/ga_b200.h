@@ -65,6 +65,8 @@ typedef enum ga_status {
  * seq4: 4-bit BAM base codes, base k of a read in bits [4*(k&1), 4*(k&1)+4) of byte k/2
  *       (LOW nibble first - note BAM itself stores the high nibble first; the packer swaps).
  *       Record r starts at byte 16*seq_off16[r]; record capacity is a multiple of 16 bytes.
+ *       The array itself (and qual, out_seq4, out_qual) must be 16-byte aligned: records are moved with
+ *       128-bit accesses and TMA bulk copies.
  * qual: phred bytes in BAM (alignment) order; record r starts at byte 32*seq_off16[r].
  *       May be NULL together with qual_reads==NULL only if no read has an I or D op.
  * qual_reads: optional sparse quality upload.  NULL = every read has a quality record at

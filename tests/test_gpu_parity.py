@@ -72,6 +72,55 @@ def test_engine_matches_oracle_random(engine, kw, sparse_qual):
     assert got.totals["n_modified"] > 0 or kw["n_pairs"][1] == 0
 
 
+def _trim_clean_reads(case, seed, keep_min):
+    """Mixed read lengths (trimmed reads): every other clean read loses a random tail."""
+    rng = np.random.default_rng(seed)
+    for r in case["reads"]:
+        L = len(r["seq"])
+        if r["cigar"] == f"{L}M" and rng.random() < 0.5:
+            n = int(rng.integers(keep_min, L + 1))
+            r["seq"], r["qual"], r["cigar"] = r["seq"][:n], r["qual"][:n], f"{n}M"
+    return case
+
+
+@pytest.mark.parametrize("kw,keep_min", [(dict(seed=401, contig_len=7000, n_pairs=(400, 400), read_len=150, indel_rate=1e-3, clip_frac=0.2), 1),
+                                         (dict(seed=402, contig_len=9000, n_pairs=(300, 300), read_len=300, snp_rate=3e-3), 20),
+                                         (dict(seed=403, contig_len=4000, n_pairs=(2500, 2000), read_len=36, snp_rate=3e-3), 30)],
+                         ids=["mixed-150", "mixed-300", "short-36"])
+def test_engine_mixed_read_lengths(engine, kw, keep_min):
+    """Tiles whose records differ in length (variable TMA tile sizes, reads above the 256-base clean path, very
+    short reads) against the oracle."""
+    from oracle import oracle
+    case = _trim_clean_reads(synth.make_case(**kw), kw["seed"], keep_min)
+    batch = B.pack_reads(H.ordered_reads(case), sparse_qual=True)
+    sessions = B.pack_sessions(case["windows"])
+    exp, st = oracle.run(batch, sessions, case["reference"])
+    assert st == 0
+    engine.upload_reference(0, case["reference"])
+    got = engine.run(batch, sessions)
+    assert_same_result(got, exp, kw["seed"])
+    assert got.totals["n_modified"] > 0
+
+
+def test_engine_reports_fallback_sessions_and_stage_times(engine):
+    """The diagnostic entry points: a read with three germline indels sends its session to the fallback kernel."""
+    from oracle import oracle
+    case = synth.make_case(seed=103, contig_len=5000, n_pairs=(300, 300), read_len=75, indel_rate=3e-3, clip_frac=0.5)
+    batch = B.pack_reads(H.ordered_reads(case), sparse_qual=True)
+    sessions = B.pack_sessions(case["windows"])
+    engine.upload_reference(0, case["reference"])
+    got = engine.run(batch, sessions)
+    exp, st = oracle.run(batch, sessions, case["reference"])
+    assert st == 0
+    assert_same_result(got, exp, "diag")
+    n, reasons = engine.fallback_sessions()
+    assert n >= 0 and len(reasons) >= 9 and sum(reasons[:5]) == n
+    for stage in range(4):
+        h = engine.stage_ms_history(stage, 4)
+        assert len(h) >= 1 and all(x >= 0 for x in h)
+    assert engine.kernel_ms_history(1)[0] > 0
+
+
 def test_engine_deep_session_uses_big_path(engine):
     """A session deeper than the shared-memory tables (SmemLayout caps) takes the global-scratch path."""
     from oracle import oracle
