@@ -195,26 +195,32 @@ def bench_fastq(eng, cfg, dev, n_w, peak):
     eng._check(L.ga_fastq_layout(eng._h, C.byref(R), C.byref(O), n_mod, C.byref(items), t_off.data_ptr(), st))
     total = int(t_off[-1].item())
     text = torch.empty(total, dtype=torch.uint8, device=dev)
-    def once():
+    def layout():
         eng._check(L.ga_fastq_layout(eng._h, C.byref(R), C.byref(O), n_mod, C.byref(items), t_off.data_ptr(), st))
+
+    def render():
         eng._check(L.ga_fastq_render(eng._h, C.byref(R), C.byref(O), n_mod, C.byref(items), t_off.data_ptr(), text.data_ptr(), total,
                                      status.data_ptr(), st))
-    for _ in range(3):
-        once()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(5):
-        once()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms_layout, ms_render = timed(layout), timed(render)
+    ms = ms_layout + ms_render
     err = _abi.GaTotals.from_buffer_copy(status.cpu().numpy().tobytes()).error
     L_read = cfg.read_len
     in_bytes = n * ((L_read + 1) // 2 + L_read + 10 + 4 + 4 + 4 + 8)       # seq4 + qual + name + len_flag + seq_off16 + indices + name offsets
     bytes_all = in_bytes + total + 8 * n
     return {"api": "ga_fastq_layout + ga_fastq_render (C ABI), device resident", "reads": n, "masked_reads": int((rec >= 0).sum().item()),
-            "text_bytes": total, "ms": ms, "reads_per_s": n / (ms * 1e-3), "achieved_gbs": bytes_all / (ms * 1e-3) / 1e9,
+            "text_bytes": total, "ms": ms, "ms_layout": ms_layout, "ms_render": ms_render, "reads_per_s": n / (ms * 1e-3), "achieved_gbs": bytes_all / (ms * 1e-3) / 1e9,
             "frac_of_hbm_peak": bytes_all / (ms * 1e-3) / 1e9 / peak, "device_error": int(err),
             "sample": f"every read of the first {n_w} windows"}
 

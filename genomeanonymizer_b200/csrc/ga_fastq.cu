@@ -11,7 +11,8 @@
 // complemented here by reversing the 4 bits of the BAM code, which is their IUPAC complement.
 //
 // Two calls: ga_fastq_layout sizes every record and scans the sizes into byte offsets; ga_fastq_render writes the
-// text, one warp per record, one character per lane and step (coalesced byte stores).
+// text, one warp per record: characters are produced into shared memory (8 bases per lane through byte permutes, 4
+// qualities per lane) with the alignment of their destination and leave with aligned 128-bit stores.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
@@ -92,51 +93,135 @@ __device__ __forceinline__ uint8_t base_char(uint32_t code) {
     return (uint8_t)(((code & 8u) ? w1 : w0) >> (8u * (code & 7u)));
 }
 
-// One warp per record.
+constexpr int kStageBytes = 1024;        // staged text per warp (records of up to ~500 bases)
+
+struct FastqItem {                       // everything one record needs, gathered lane-per-record and broadcast by shuffle
+    const uint32_t* seqw; const uint8_t* q; const uint8_t* name; int64_t off; int nl, L; uint32_t flag; int ok;
+};
+
+__device__ __forceinline__ FastqItem shfl_item(const FastqItem& it, int src) {
+    FastqItem o;
+    o.seqw = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(it.seqw), src));
+    o.q = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(it.q), src));
+    o.name = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(it.name), src));
+    o.off = (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)it.off, src);
+    o.nl = __shfl_sync(0xffffffffu, it.nl, src); o.L = __shfl_sync(0xffffffffu, it.L, src);
+    o.flag = __shfl_sync(0xffffffffu, it.flag, src); o.ok = __shfl_sync(0xffffffffu, it.ok, src);
+    return o;
+}
+
+// A warp takes 32 records at a time: their indices, lengths, offsets and source pointers are gathered lane-per-record
+// (three dependent round trips for the whole batch), then the records are rendered one after the other.
 __global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const int64_t* __restrict__ text_off, uint8_t* __restrict__ text,
                                                            int64_t text_cap, ga_totals* totals) {
+    __shared__ __align__(16) uint8_t stage[8][kStageBytes];
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t k = warp0; k < V.n_items; k += n_warps) {
-        const int32_t r = V.read[k], rec = V.record[k];
-        if (r < 0 || r >= V.n_reads || rec >= V.n_records) { if (lane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)k); continue; }
-        const int64_t nb = V.name_off[r];
-        const int nl = (int)(V.name_off[r + 1] - nb);
-        const uint32_t lf = V.len_flag[r];
-        const bool reverse = ((lf >> 16) & 0x10u) != 0u;
-        const uint8_t mate = ((lf >> 16) & 0x40u) ? '1' : '2';           // anonymizer_methods.py:218
-        const int L = rec >= 0 ? (int)V.mod_len[rec] : (int)(lf & 0xffffu);
-        const uint32_t* seqw = rec >= 0 ? reinterpret_cast<const uint32_t*>(V.out_seq4 + 16ull * V.mod_seq_off16[rec])
-                                        : reinterpret_cast<const uint32_t*>(V.seq4 + 16ull * V.seq_off16[r]);
-        // qualities in printed (= BAM) order: the record's own when it carries them, else the read's
-        const uint8_t* q = nullptr;
-        if (rec >= 0 && V.mod_qual_off16[rec] != 0xffffffffu) q = V.out_qual + 32ull * V.mod_qual_off16[rec];
-        else if (V.qual && !V.qual_reads) q = V.qual + 32ull * V.seq_off16[r];
-        else if (V.qual) {
-            int64_t b = 0, e = V.n_qual;
-            while (b < e) { const int64_t m = (b + e) >> 1; if (V.qual_reads[m] < r) b = m + 1; else e = m; }
-            if (b < V.n_qual && V.qual_reads[b] == r) q = V.qual + 32ull * V.qual_off16[b];
+    for (int64_t k0 = warp0 * 32; k0 < V.n_items; k0 += n_warps * 32) {
+        // ---- lane = record
+        FastqItem me; me.seqw = nullptr; me.q = nullptr; me.name = nullptr; me.off = 0; me.nl = 0; me.L = 0; me.flag = 0u; me.ok = 0;
+        const int64_t k = k0 + lane;
+        if (k < V.n_items) {
+            const int32_t r = V.read[k], rec = V.record[k];
+            if (r < 0 || r >= V.n_reads || rec >= V.n_records) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)k);
+            else {
+                const int64_t nb = V.name_off[r];
+                me.name = V.names + nb; me.nl = (int)(V.name_off[r + 1] - nb);
+                const uint32_t lf = V.len_flag[r];
+                me.flag = lf >> 16;
+                me.L = rec >= 0 ? (int)V.mod_len[rec] : (int)(lf & 0xffffu);
+                me.seqw = rec >= 0 ? reinterpret_cast<const uint32_t*>(V.out_seq4 + 16ull * V.mod_seq_off16[rec])
+                                   : reinterpret_cast<const uint32_t*>(V.seq4 + 16ull * V.seq_off16[r]);
+                // qualities in printed (= BAM) order: the record's own when it carries them, else the read's
+                if (rec >= 0 && V.mod_qual_off16[rec] != 0xffffffffu) me.q = V.out_qual + 32ull * V.mod_qual_off16[rec];
+                else if (V.qual && !V.qual_reads) me.q = V.qual + 32ull * V.seq_off16[r];
+                else if (V.qual) {
+                    int64_t b = 0, e = V.n_qual;
+                    while (b < e) { const int64_t m = (b + e) >> 1; if (V.qual_reads[m] < r) b = m + 1; else e = m; }
+                    if (b < V.n_qual && V.qual_reads[b] == r) me.q = V.qual + 32ull * V.qual_off16[b];
+                }
+                me.off = text_off[k];
+                if (!me.q) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)k);
+                else if (me.off + me.nl + 2ll * me.L + 8 > text_cap) raise_error(totals, GA_ERR_CAPACITY, (uint32_t)k);
+                else me.ok = 1;
+            }
         }
-        const int64_t off = text_off[k];
-        const int64_t total = (int64_t)nl + 2ll * L + 8;
-        if (!q || off + total > text_cap) { if (lane == 0) raise_error(totals, q ? GA_ERR_CAPACITY : GA_ERR_BAD_ARGUMENT, (uint32_t)k); continue; }
-        uint8_t* out = text + off;
-        // header "@name/m\n"
-        for (int c = lane; c < nl + 4; c += 32)
-            out[c] = c == 0 ? (uint8_t)'@' : c <= nl ? V.names[nb + c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
-        // sequence (reverse-complemented for reverse reads: complement of a BAM code = its 4 bits reversed)
-        uint8_t* os = out + nl + 4;
-        for (int j = lane; j < L; j += 32) {
-            const int bj = reverse ? L - 1 - j : j;
-            uint32_t code = (seqw[bj >> 3] >> ((bj & 7) * 4)) & 15u;
-            if (reverse) code = __brev(code) >> 28;
-            os[j] = base_char(code);
+        const int n_here = (int)min((int64_t)32, V.n_items - k0);
+        // ---- one record after the other, all lanes
+        for (int j = 0; j < n_here; ++j) {
+            const FastqItem it = shfl_item(me, j);
+            if (!it.ok) continue;
+            const int nl = it.nl, L = it.L;
+            const bool reverse = (it.flag & 0x10u) != 0u;
+            const uint8_t mate = (it.flag & 0x40u) ? '1' : '2';           // anonymizer_methods.py:218
+            const int64_t total = (int64_t)nl + 2ll * L + 8;
+            uint8_t* out = text + it.off;
+            const int pad = (int)(reinterpret_cast<uintptr_t>(out) & 15u);   // the staged copy has the alignment of its destination
+            if (pad + total <= (int64_t)kStageBytes) {
+                // ---- staged path: characters are produced into the warp's shared-memory slice (8 bases / 4 qualities
+                // per lane and step), then written out with aligned 128-bit stores
+                uint8_t* sg = stage[threadIdx.x >> 5] + pad;
+                for (int c = lane; c < nl + 4; c += 32)
+                    sg[c] = c == 0 ? (uint8_t)'@' : c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
+                uint8_t* ss = sg + nl + 4;
+                for (int w = lane; w < ((L + 7) >> 3); w += 32) {
+                    uint32_t cw = it.seqw[w];
+                    int j0 = 8 * w;                                       // output position of the word's first character
+                    if (reverse) {                                        // reversed nibble order + complemented codes = the word bit-reversed
+                        cw = __brev(cw);
+                        j0 = L - 8 - 8 * w;
+                    }
+                    uint32_t ch[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                         // four codes -> four characters with three byte permutes
+                        const uint32_t n16 = (cw >> (16 * h)) & 0xffffu;
+                        const uint32_t sel = n16 & 0x7777u;
+                        const uint32_t lo = __byte_perm(0x4d43413du, 0x56535247u, sel);      // "=ACM" "GRSV"
+                        const uint32_t hi = __byte_perm(0x48595754u, 0x4e42444bu, sel);      // "TWYH" "KDBN"
+                        ch[h] = __byte_perm(lo, hi, 0x3210u + ((n16 & 0x8888u) >> 1));
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int jj = j0 + t;
+                        if (jj >= 0 && jj < L) ss[jj] = (uint8_t)(ch[t >> 2] >> (8 * (t & 3)));
+                    }
+                }
+                if (lane < 3) ss[L + lane] = lane == 1 ? (uint8_t)'+' : (uint8_t)'\n';
+                uint8_t* sq = ss + L + 3;
+                const uint32_t* qw = reinterpret_cast<const uint32_t*>(it.q);
+                for (int w = lane; w < ((L + 3) >> 2); w += 32) {
+                    const uint32_t v = qw[w] + 0x21212121u;               // anonymizer_methods.py:232 (phred <= 93: no carry between bytes)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) if (4 * w + t < L) sq[4 * w + t] = (uint8_t)(v >> (8 * t));
+                }
+                if (lane == 0) sq[L] = (uint8_t)'\n';
+                __syncwarp();
+                const uint8_t* sb = stage[threadIdx.x >> 5];
+                uint8_t* gb = out - pad;                                  // 16-byte aligned
+                const int end = pad + (int)total;
+                for (int c16 = lane * 16; c16 < end; c16 += 32 * 16) {
+                    if (c16 >= pad && c16 + 16 <= end) *reinterpret_cast<uint4*>(gb + c16) = *reinterpret_cast<const uint4*>(sb + c16);
+                    else for (int t = max(c16, pad); t < min(c16 + 16, end); ++t) gb[t] = sb[t];   // the neighbours' bytes share these chunks
+                }
+                __syncwarp();
+                continue;
+            }
+            // ---- general path (records longer than the staging slice): one character per lane and step
+            for (int c = lane; c < nl + 4; c += 32)
+                out[c] = c == 0 ? (uint8_t)'@' : c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
+            uint8_t* os = out + nl + 4;
+            for (int jj = lane; jj < L; jj += 32) {
+                const int bj = reverse ? L - 1 - jj : jj;
+                uint32_t code = (it.seqw[bj >> 3] >> ((bj & 7) * 4)) & 15u;
+                if (reverse) code = __brev(code) >> 28;
+                os[jj] = base_char(code);
+            }
+            if (lane < 3) os[L + lane] = lane == 1 ? (uint8_t)'+' : (uint8_t)'\n';
+            uint8_t* oq = os + L + 3;
+            for (int jj = lane; jj < L; jj += 32) oq[jj] = (uint8_t)(it.q[jj] + 33u);    // anonymizer_methods.py:232
+            if (lane == 0) oq[L] = (uint8_t)'\n';
         }
-        if (lane < 3) os[L + lane] = lane == 1 ? (uint8_t)'+' : (uint8_t)'\n';
-        uint8_t* oq = os + L + 3;
-        for (int j = lane; j < L; j += 32) oq[j] = (uint8_t)(q[j] + 33u);    // anonymizer_methods.py:232
-        if (lane == 0) oq[L] = (uint8_t)'\n';
     }
 }
 
@@ -183,8 +268,8 @@ int ga_fastq_render(ga_engine* e, const ga_reads* R, const ga_result* O, int64_t
     GA_CUDA(cudaSetDevice(e->device));
     if (I->n_items == 0) return GA_OK;
     const ga::FastqView V = make_view(R, O, I, n_records);
-    const int64_t warps = (I->n_items + 7) / 8;
-    const unsigned grid = (unsigned)std::min<int64_t>(warps, (int64_t)e->n_sm * 32);
+    const int64_t ctas = (I->n_items + 255) / 256;                    // 32 records per warp, 8 warps per CTA
+    const unsigned grid = (unsigned)std::min<int64_t>(ctas, (int64_t)e->n_sm * 32);
     ga::fastq_render_kernel<<<grid, 256, 0, st>>>(V, text_off, text, text_cap, status);
     e->launches += 1;
     GA_CUDA(cudaGetLastError());
