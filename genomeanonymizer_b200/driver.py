@@ -1,0 +1,289 @@
+"""Batched sample driver: the reference's per-sample orchestration, planned on the host, executed on the engine.
+
+SURVEY.md 8(f) N2 + N3.  The reference walks a sample section by section (`anonymize_genome`,
+short_read_tumor_normal_anonymizer.py:625-760): variant windows become sessions (`anonymize_window`, :279-372), the
+regions between them are fetched and passed through unless a tumor and a normal read island overlap, which makes one
+more session (`anonymize_inter_window_region`, :498-558 over `pileup_io.iter_fetch_pair`, pileup_io.pyx:124-298).
+Mates meet through `to_pair_anonymized_reads`, and a pair is written once (`written_read_ids`, :134-165) - by the
+first section that completes it, so a read that was fetched and paired in the region before a window leaves
+unmasked even though the window's session masks it.
+
+None of this needs the bases: `plan_sample` works on (name, flag, dataset, start, end) alone and returns
+  * the session table (variant windows and island sessions, in processing order), and
+  * the write plan: for every output record which read it is and which session's result it shows (-1: as fetched).
+The engine then masks all sessions in one `ga_run`, and `ga_fastq_render` prints the planned records.
+`tests/test_genome_files.py` checks the four files byte for byte against what the reference itself wrote.
+
+Scope: one contig per call, mapped primary alignments (no unmapped / supplementary / secondary records - SURVEY.md
+Appendix B), windows as `get_windows` makes them for SNVs and short indels.
+"""
+from __future__ import annotations
+
+import bisect
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+WINDOW_HALF = 1000                      # window_size // 2, short_read_tumor_normal_anonymizer.py:71
+
+
+def window_of_variant(pos: int, end: int) -> Tuple[int, int]:
+    """(first, last) of the window around a VCF record with 1-based pos / end
+    (short_read_tumor_normal_anonymizer.py:112-128: SNVs and indels shorter than the window)."""
+    return pos - WINDOW_HALF, end + WINDOW_HALF + 1
+
+
+def genome_sections(windows: Sequence[dict], contig_len: int) -> List[Tuple[int, int, Optional[int]]]:
+    """(first, last, window index or None) in processing order for one contig
+    (get_genome_sections, short_read_tumor_normal_anonymizer.py:245-276)."""
+    if not windows:
+        return [(0, 0, None)]                                     # the whole contig is one inter-window region
+    out = []
+    nxt = 1
+    for k, w in enumerate(windows):
+        out.append((nxt, w["first"] - 1, None))
+        out.append((w["first"], w["last"], k))
+        nxt = w["last"] + 1
+    out.append((nxt, contig_len - 1, None))
+    out.sort(key=lambda t: (t[0], t[1]))                          # sort_window_list, :67-68 (stable: a window keeps its place among ties)
+    return out
+
+
+@dataclass
+class Plan:
+    sessions: List[dict] = field(default_factory=list)            # {"first", "last", "keep", "window": index or None}
+    pairs: List[Tuple[int, int, int, int, int]] = field(default_factory=list)   # (dataset, read1, version1, read2, version2) in write order
+    singles: List[Tuple[int, int, int]] = field(default_factory=list)           # (dataset, read, version)
+
+
+def _session_yield_order(reads, t_idx: List[int], n_idx: List[int]):
+    """Pairs of one session in the order `CompleteGermlineAnonymizer.anonymize` yields them
+    (anonymizer_methods.py:472-476, 489-512, 521-532): a pair whose two mates are in the session leaves at the first
+    normal pileup column right of both mates, pairs in first-appearance order; everything else at the end, in
+    registry order.  Reads appear at their own start (truncate=False, pileup_io.pyx:12-17), tumor column before
+    normal column, file order inside a column.  Returns [(name, read index of mate 1 or None, of mate 2 or None)]."""
+    order: Dict[str, int] = {}
+    slots: Dict[str, list] = {}
+    max_end: Dict[str, int] = {}
+    seq = sorted([(reads[i]["pos"], 0, i) for i in t_idx] + [(reads[i]["pos"], 1, i) for i in n_idx])
+    for _, _, i in seq:
+        r = reads[i]
+        order.setdefault(r["name"], len(order))
+        slot = slots.setdefault(r["name"], [None, None])
+        m = 0 if r["flag"] & 0x40 else 1
+        if slot[m] is None:                                       # the first alignment of a (name, mate) is the read
+            slot[m] = i
+        max_end[r["name"]] = max(max_end.get(r["name"], -1), r["end"])
+    # normal pileup columns = positions covered by a normal read of the session
+    cover = sorted((reads[i]["pos"], reads[i]["end"]) for i in n_idx)
+    merged: List[List[int]] = []
+    for a, b in cover:
+        if merged and a <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], b)
+        else:
+            merged.append([a, b])
+    starts = [m[0] for m in merged]
+
+    def first_normal_column_after(p: int) -> Optional[int]:      # smallest covered position > p
+        k = bisect.bisect_right(starts, p + 1) - 1
+        if k >= 0 and merged[k][1] > p + 1:
+            return p + 1
+        k += 1
+        return merged[k][0] if k < len(merged) else None
+
+    early, late = [], []
+    for name, o in order.items():
+        s = slots[name]
+        col = first_normal_column_after(max_end[name]) if (s[0] is not None and s[1] is not None) else None
+        if col is not None:
+            early.append((col, o, name))
+        else:
+            late.append((o, name))
+    return [(n, slots[n][0], slots[n][1]) for _, _, n in sorted(early)] + [(n, slots[n][0], slots[n][1]) for _, n in sorted(late)]
+
+
+def _islands(reads, idx: List[int]) -> List[List[int]]:
+    """Chains of reads in which every read overlaps (or touches, or ends with) the one before it
+    (collect_intersecting_reads, pileup_io.pyx:78-106 with compare, :44-59)."""
+    out: List[List[int]] = []
+    for i in idx:
+        if out:
+            last = reads[out[-1][-1]]
+            r = reads[i]
+            if (r["pos"] <= last["end"] and r["end"] >= last["pos"]) or r["end"] == last["end"]:
+                out[-1].append(i)
+                continue
+        out.append([i])
+    return out
+
+
+def _cmp_islands(reads, a: List[int], b: List[int]) -> int:
+    """compare() of pileup_io.pyx:44-59 on (first read's start, rightmost end) of two islands of one contig."""
+    f1, l1 = reads[a[0]]["pos"], max(reads[i]["end"] for i in a)
+    f2, l2 = reads[b[0]]["pos"], max(reads[i]["end"] for i in b)
+    overlap = f2 <= l1 and l2 >= f1
+    if l1 < l2:
+        return -1 if overlap else -2
+    if l2 < l1:
+        return 1 if overlap else 2
+    return -1 if f1 < f2 else (1 if f2 < f1 else 0)
+
+
+def _fetch_pair_events(reads, t_idx: List[int], n_idx: List[int]):
+    """What iter_fetch_pair (pileup_io.pyx:124-298) yields for the fetched tumor / normal reads of one region:
+    ("single", dataset, [reads]) or ("both", (left, right)).  The last island of each dataset is always yielded
+    singly, and when one dataset runs out the other's remaining islands are yielded singly too."""
+    if not t_idx and not n_idx:
+        return
+    ti, ni = _islands(reads, t_idx), _islands(reads, n_idx)
+    a = b = 0                                                     # current island of each dataset
+    # "r is not None" in the reference = there is another island after the current one
+    while True:
+        more_t, more_n = a + 1 < len(ti), b + 1 < len(ni)
+        if not more_t and not more_n:
+            yield ("single", 0, ti[a] if a < len(ti) else [])
+            yield ("single", 1, ni[b] if b < len(ni) else [])
+            return
+        if more_t and more_n:
+            c = _cmp_islands(reads, ti[a], ni[b])
+            if c < -1:
+                yield ("single", 0, ti[a]); a += 1
+            elif c > 1:
+                yield ("single", 1, ni[b]); b += 1
+            else:
+                left = min(reads[ti[a][0]]["pos"], reads[ni[b][0]]["pos"])
+                right = max(max(reads[i]["end"] for i in ti[a]), max(reads[i]["end"] for i in ni[b]))
+                yield ("both", (left, right)); a += 1; b += 1
+        else:
+            if more_t:
+                yield ("single", 0, ti[a]); a += 1
+            if more_n:
+                yield ("single", 1, ni[b]); b += 1
+
+
+def plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int) -> Plan:
+    """reads: every read of the sample on this contig, each {"name", "flag", "dataset", "pos", "end"} with `end` the
+    exclusive reference end, tumor and normal each in file (coordinate) order; windows: [{"first", "last", "keep"}]
+    sorted as the reference sorts them."""
+    plan = Plan()
+    t_all = [i for i, r in enumerate(reads) if r["dataset"] == 0]
+    n_all = [i for i, r in enumerate(reads) if r["dataset"] == 1]
+    to_pair: Dict[str, list] = {}                                 # name -> [(read, version) or None] * 2
+    written = set()
+
+    def overlapping(idx, start, stop):                            # AlignmentFile.fetch / pileup read selection
+        return [i for i in idx if reads[i]["pos"] < stop and reads[i]["end"] > start]
+
+    def write_pair(name, s1, s2):                                 # write_pair, :134-165
+        if name in written:
+            return
+        written.add(name)
+        plan.pairs.append((reads[s1[0]]["dataset"], s1[0], s1[1], s2[0], s2[1]))
+
+    def store(name, mate, value):                                 # add_*_to_collection: an occupied slot keeps its read
+        slot = to_pair.setdefault(name, [None, None])
+        if slot[mate] is None:
+            slot[mate] = value
+        return slot
+
+    def run_session(first, last, keep, window_index):
+        s = len(plan.sessions)
+        plan.sessions.append({"first": first, "last": last, "keep": keep, "window": window_index})
+        for name, m1, m2 in _session_yield_order(reads, overlapping(t_all, first, last), overlapping(n_all, first, last)):
+            if m1 is not None and m2 is not None:                 # writeable as it comes (:310-312)
+                write_pair(name, (m1, s), (m2, s))
+                continue
+            slot = None
+            for mate, m in ((0, m1), (1, m2)):                    # :320-333
+                if m is not None:
+                    slot = store(name, mate, (m, s))
+            if slot[0] is not None and slot[1] is not None:       # :348-359
+                write_pair(name, slot[0], slot[1])
+                to_pair.pop(name)
+
+    for first, last, k in genome_sections(windows, contig_len):
+        if k is not None:
+            run_session(first, last, windows[k].get("keep"), k)
+            continue
+        if first + last == 0:
+            start, stop = 0, contig_len
+        else:
+            if first < 0 or first > last:                         # pysam rejects these coordinates
+                raise ValueError(f"inter-window region ({first}, {last}) is not fetchable: variants closer than a window")
+            start, stop = first, last
+        for ev in _fetch_pair_events(reads, overlapping(t_all, start, stop), overlapping(n_all, start, stop)):
+            if ev[0] == "both":
+                run_session(ev[1][0], ev[1][1], None, None)       # an island session has no variant to keep (:523-534)
+                continue
+            for i in ev[2]:                                       # pair_unmapped_or_non_pileup_pairs_and_write, :375-406
+                r = reads[i]
+                slot = store(r["name"], 0 if r["flag"] & 0x40 else 1, (i, -1))
+                if slot[0] is not None and slot[1] is not None:
+                    write_pair(r["name"], slot[0], slot[1])       # (stays in the collection until the end, :737-741)
+    for name in written:
+        to_pair.pop(name, None)
+    for name, slot in to_pair.items():                            # write_single_end_reads, :603-622
+        i, v = slot[0] if slot[0] is not None else slot[1]
+        plan.singles.append((reads[i]["dataset"], i, v))
+    return plan
+
+
+def statistics_text(contig: str, plan: Plan, sess_counts) -> str:
+    """The `<normal_bam>.statistics.txt` file (AnonymizedVariantsStatistics.write_statistics,
+    short_read_tumor_normal_anonymizer.py:212-242): one row per variant window with the masked variants by type
+    (SNV, DEL, INS and the five structural types this path never calls), island sessions summed into the
+    `outside_windows` row, then total / mean / median / max / min over ALL rows."""
+    import numpy as np
+    rows = [("outside_windows", "-", "-", [0] * 8)]
+    for s, ses in enumerate(plan.sessions):
+        c = [int(x) for x in sess_counts[s][:3]] + [0] * 5
+        if ses["window"] is None:
+            rows[0] = rows[0][:3] + ([a + b for a, b in zip(rows[0][3], c)],)
+        else:
+            rows.append((contig, str(ses["first"]), str(ses["last"]), c))
+    out = ["\t".join(["#SEQ", "#FIRST", "#LAST", "#SNV", "#DEL", "#INS", "#DUP", "#INV", "#CNV", "#TRA", "#SGL"])]
+    out += ["\t".join([a, b, c] + [str(x) for x in counts]) for a, b, c, counts in rows]
+    out.append("### Overall statistics:")
+    out.append("\t".join(["#SNV", "#DEL", "#INS", "#DUP", "#INV", "#CNV", "#TRA", "#SGL"]))
+    cols = [np.array([r[3][k] for r in rows], dtype=np.int64) for k in range(8)]
+    for stat, fn in (("total_counts", np.sum), ("average_counts", np.mean), ("median_counts", np.median), ("max_counts", np.max),
+                     ("min_counts", np.min)):
+        out.append(f"#{stat}\t" + "\t".join(str(fn(a)) for a in cols))
+    return "\n".join(out) + "\n"
+
+
+def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], reference: str, contig: str = "c") -> Dict[str, str]:
+    """One contig of a tumor-normal sample through the engine: plan, one masking pass over every session, FASTQ
+    rendering on the device.  reads: tumor then normal, each in file order, dicts with name / flag / dataset / pos /
+    cigar / seq / qual.  Returns the reference's output files as {suffix: text}: "T.1", "T.2", "T.single_end",
+    "N.1", "N.2", "N.single_end", "statistics"."""
+    import re
+    import torch
+    from . import batch as B
+    from .engine import DeviceBatch, DeviceResult, DeviceSessions
+    cig = re.compile(r"(\d+)([MIDNSHP=X])")
+    rs = [dict(r, end=r["pos"] + sum(int(n) for n, op in cig.findall(r["cigar"]) if op in "MDN=X")) for r in reads]
+    plan = plan_sample(rs, windows, len(reference))
+    batch = B.pack_reads(rs)                                      # dense qualities: every read is printed
+    sessions = B.pack_sessions(plan.sessions)
+    engine.upload_reference(0, reference)
+    db, ds = DeviceBatch(batch, engine.device), DeviceSessions(sessions, engine.device)
+    units = batch.seq4.shape[0] // 16
+    dres = DeviceResult(sessions.n_sessions, 2 * batch.n_reads + 16, 2 * units + 64, 2 * units + 64, engine.device)
+    engine.run_device(db, ds, dres)
+    torch.cuda.synchronize(engine.device)
+    n = int(engine.check_device_status(dres).n_modified)
+    rec_of = {(int(s), int(r)): k for k, (s, r) in enumerate(zip(dres.mod_session[:n].cpu().numpy(), dres.mod_read[:n].cpu().numpy()))}
+    order = [(r1, v1) for _, r1, v1, _, _ in plan.pairs] + [(r2, v2) for _, _, _, r2, v2 in plan.pairs] + [(r, v) for _, r, v in plan.singles]
+    text, off = engine.render_fastq(db, [r["name"] for r in rs], [i for i, _ in order], [rec_of.get((v, i), -1) for i, v in order], dres, n)
+    piece = lambda k: text[off[k]:off[k + 1]].decode("ascii")
+    files = {f"{p}.{s}": [] for p in "TN" for s in ("1", "2", "single_end")}
+    np_ = len(plan.pairs)
+    for k, (d, _, _, _, _) in enumerate(plan.pairs):
+        files[f"{'TN'[d]}.1"].append(piece(k))
+        files[f"{'TN'[d]}.2"].append(piece(np_ + k))
+    for k, (d, _, _) in enumerate(plan.singles):
+        files[f"{'TN'[d]}.single_end"].append(piece(2 * np_ + k))
+    out = {k: "".join(v) for k, v in files.items()}
+    counts = dres.sess_counts.view(-1, 4)[:sessions.n_sessions].cpu().numpy()
+    out["statistics"] = statistics_text(contig, plan, counts)
+    return out
