@@ -173,11 +173,11 @@ def plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int)
     def overlapping(idx, start, stop):                            # AlignmentFile.fetch / pileup read selection
         return [i for i in idx if reads[i]["pos"] < stop and reads[i]["end"] > start]
 
-    def write_pair(name, s1, s2):                                 # write_pair, :134-165
+    def write_pair(name, s1, s2, sink=None):                      # write_pair, :134-165
         if name in written:
             return
         written.add(name)
-        plan.pairs.append((reads[s1[0]]["dataset"], s1[0], s1[1], s2[0], s2[1]))
+        (plan.pairs if sink is None else sink).append((reads[s1[0]]["dataset"], s1[0], s1[1], s2[0], s2[1]))
 
     def store(name, mate, value):                                 # add_*_to_collection: an occupied slot keeps its read
         slot = to_pair.setdefault(name, [None, None])
@@ -210,6 +210,11 @@ def plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int)
             if first < 0 or first > last:                         # pysam rejects these coordinates
                 raise ValueError(f"inter-window region ({first}, {last}) is not fetchable: variants closer than a window")
             start, stop = first, last
+        # The region keeps its four output streams open from its first to its last read (:516-518, :558) while every
+        # island session opens, writes and closes its own (:297-299, :366): the region's own records sit in the stream
+        # buffers and reach the files when the region ends, behind the records of its island sessions.  (Exact while a
+        # region's pass-through text per file stays below the platform's stream buffer; see DESIGN.md.)
+        deferred: List[Tuple[int, int, int, int, int]] = []
         for ev in _fetch_pair_events(reads, overlapping(t_all, start, stop), overlapping(n_all, start, stop)):
             if ev[0] == "both":
                 run_session(ev[1][0], ev[1][1], None, None)       # an island session has no variant to keep (:523-534)
@@ -218,7 +223,8 @@ def plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int)
                 r = reads[i]
                 slot = store(r["name"], 0 if r["flag"] & 0x40 else 1, (i, -1))
                 if slot[0] is not None and slot[1] is not None:
-                    write_pair(r["name"], slot[0], slot[1])       # (stays in the collection until the end, :737-741)
+                    write_pair(r["name"], slot[0], slot[1], deferred)   # (stays in the collection until the end, :737-741)
+        plan.pairs.extend(deferred)
     for name in written:
         to_pair.pop(name, None)
     for name, slot in to_pair.items():                            # write_single_end_reads, :603-622

@@ -248,11 +248,25 @@ def run_genome(case, vcf_records):
 
 def genome_cases():
     out = []
-    for seed, kw, label in ((21, dict(snp_rate=2e-3, indel_rate=0.0, clip_frac=0.0), "snv-only"),
-                            (22, dict(snp_rate=2e-3, indel_rate=1.5e-3, clip_frac=0.1), "with-indels")):
+    specs = [
         # two windows 2,150 bp apart: reads of length 80 can overlap both (gap of 149 bp)
-        case = synth.make_case(seed, contig_len=9000, n_pairs=(260, 240), read_len=80,
-                               somatic_positions=[2500, 4650], name=f"genome-{label}", **kw)
+        (21, dict(contig_len=9000, n_pairs=(260, 240), read_len=80, somatic_positions=[2500, 4650], snp_rate=2e-3, indel_rate=0.0,
+                  clip_frac=0.0), "snv-only", None),
+        (22, dict(contig_len=9000, n_pairs=(260, 240), read_len=80, somatic_positions=[2500, 4650], snp_rate=2e-3, indel_rate=1.5e-3,
+                  clip_frac=0.1), "with-indels", None),
+        # ~2x coverage: many read islands between the windows, tumor / normal island pairs become extra sessions
+        (23, dict(contig_len=9000, n_pairs=(70, 60), read_len=80, somatic_positions=[2500, 4650], snp_rate=4e-3, indel_rate=1e-3,
+                  clip_frac=0.1), "sparse-islands", None),
+        # reads whose mate is missing: the single_end files and pairs completed across sections
+        (24, dict(contig_len=9000, n_pairs=(200, 180), read_len=100, somatic_positions=[2300, 4600, 6900], snp_rate=3e-3,
+                  indel_rate=8e-4, clip_frac=0.1), "orphans-three-windows", 7),
+        # no somatic variant at all: the whole contig is one inter-window region
+        (25, dict(contig_len=5000, n_pairs=(40, 35), read_len=70, somatic_positions=[], snp_rate=4e-3, indel_rate=1e-3), "no-variants", None),
+    ]
+    for seed, kw, label, drop in specs:
+        case = synth.make_case(seed, name=f"genome-{label}", **kw)
+        if drop:                                                  # deterministic orphans: every `drop`-th read disappears
+            case["reads"] = [r for k, r in enumerate(case["reads"]) if k % drop != 3]
         vcf = []
         for w in case["windows"]:
             k = w["keep"]
