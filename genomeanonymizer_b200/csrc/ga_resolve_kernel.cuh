@@ -415,13 +415,19 @@ struct SmemL {
     uint32_t modbits[kReadsL / 32], indelbits[kReadsL / 32], genbits[kReadsL / 32], woff[kReadsL / 32];
     uint32_t mpatch[kModL];              // two germline hits of a clean read: (column << 4) | reference code, 16 bits each
     int32_t mhead[kModL];                // per modified read: chain of its germline indel observations
-    uint16_t clist[kModL];
     uint8_t mpc[kModL];                  // germline SNV hits per modified read
-    uint32_t o_meta[kObsL], o_ra[kObsL], o_s0[kObsL], o_s1[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
-    uint32_t ent[kEntL];                 // candidate entries (tumor item, then normal item); bit 31: germline hit
-    uint32_t rnew[kModL];                // per modified read: new length | kind << 24
+    uint32_t o_meta[kObsL], o_ra[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
+    union {                              // the allele signatures are dead once the observations are compared,
+        struct { uint32_t o_s0[kObsL], o_s1[kObsL]; };
+        uint16_t clist[kModL];           // ... which is before the list of modified reads is built
+    };
+    union {                              // the entries are dead after their third pass,
+        uint32_t ent[kEntL];             // candidate entries (tumor item, then normal item); bit 31: germline hit
+        uint32_t rnew[kModL];            // ... which is before the new lengths are known: new length | kind << 24
+    };
     uint32_t ngerm, pad[3];
 };
+static_assert(sizeof(uint16_t) * kModL <= 2 * sizeof(uint32_t) * kObsL && kModL <= kEntL, "aliases fit");
 static_assert(sizeof(SmemL) % 16 == 0, "per-warp slices stay 16-byte aligned");
 
 // collect2 behind a call: the lean kernel needs it twice and must stay small enough for the instruction cache
@@ -435,7 +441,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return inc - v;
 }
 
-__global__ void __launch_bounds__(32 * kLeanWarps, 9) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+__global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                             int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
                                                                             int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
                                                                             ResultView O, ScanScratch X, EmitScratch2 E) {
