@@ -749,6 +749,38 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
             const uint32_t qual16 = kind == 3u ? (uint32_t)(base_qual + qo_rel) : 0xffffffffu;
             write_record_meta(O, rec_idx, s, r, (int)new_len, base_seq + so_rel, qual16);
             const uint32_t L0 = lf & 0xffffu;
+            if (kind == 1u && L0 <= 160u) {
+                // clean read, at most two germline hits, up to five 16-byte units (the common record): the lane writes
+                // the body itself - copy, base <- reference base at the hits (anonymizer_methods.py:170-176).  The
+                // loads of the 32 records of this step are in flight together; the emission kernel skips kind 0.
+                const uint4* src = reinterpret_cast<const uint4*>(B.seq4 + 16ull * so);
+                uint4* dst = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (base_seq + so_rel));
+                const int nu = (int)((L0 + 31u) >> 5);
+                uint4 v[5];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) v[u] = u < nu ? ldg128(src + u) : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t hits = sm->mpatch[k];
+                const int rel0 = pos - c.d.col_begin;
+                const int q0 = (int)((hits >> 4) & 0xfffu) - rel0, q1 = sm->mpc[k] > 1 ? (int)(hits >> 20) - rel0 : -1;
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    if (u >= nu) break;
+                    uint4 w = v[u];
+                    if (32 * u + 32 > (int)L0) { w.x &= tail_mask((int)L0, 4 * u); w.y &= tail_mask((int)L0, 4 * u + 1); w.z &= tail_mask((int)L0, 4 * u + 2); w.w &= tail_mask((int)L0, 4 * u + 3); }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = h ? q1 : q0;
+                        if (q >= 0 && (q >> 5) == u) {
+                            const uint32_t sh = (uint32_t)(q & 7) * 4u, keepm = ~(0xfu << sh), ins = ((h ? hits >> 16 : hits) & 15u) << sh;
+                            const int ww = (q >> 3) & 3;
+                            if (ww == 0) w.x = (w.x & keepm) | ins; else if (ww == 1) w.y = (w.y & keepm) | ins;
+                            else if (ww == 2) w.z = (w.z & keepm) | ins; else w.w = (w.w & keepm) | ins;
+                        }
+                    }
+                    dst[u] = w;
+                }
+                continue;                                             // E.kind stays 0: nothing left for the emission kernels
+            }
             E.kind[rec_idx] = (uint8_t)kind;
             if (kind == 1u) E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
             else E.edesc[rec_idx] = make_uint4(so, (uint32_t)pos, L0, (uint32_t)s);
