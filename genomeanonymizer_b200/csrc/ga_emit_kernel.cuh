@@ -92,12 +92,10 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
 //      floor(mean(qualities)), INS -> the inserted bases and qualities go (anonymizer_methods.py:178-203); edits
 //      index the forward-orientation quality array, printed order = BAM order (anonymizer_methods.py:95, 213).
 __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r,
-                                                   int pos, int L, uint32_t src_unit, int col_begin, const GermList& germ, const uint8_t* qrec,
+                                                   int pos, int L, uint32_t src_unit, uint32_t c0, uint32_t c1, bool reverse, int col_begin, const GermList& germ, const uint8_t* qrec,
                                                    uint32_t* stage, uint64_t seq16, uint64_t qual16, int new_len, int glane) {
     const int nw = (L + 7) >> 3;
-    uint32_t c0 = 0u, c1 = 0u;
     if (act) {
-        c0 = __ldg(B.cigar_off + r); c1 = __ldg(B.cigar_off + r + 1);
         const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * src_unit);
         for (int w = glane; w < nw; w += kGroup) stage[w] = __ldg(rec + w) & tail_mask(L, w);
         if (glane == 0) stage[nw] = 0u;                                // the funnel shift may touch one word past the end
@@ -176,7 +174,6 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     // qualities in printed (= BAM) order.  The edit indexes the forward-orientation array (anonymizer_methods.py:95,
     // 187, 195: quirk Q2), so for a reverse read the pieces come in the opposite order: printed [0, b1) = BAM bytes as
     // they are, [b1, b2) = the mean, [b2, new_len) = BAM bytes shifted by d3.
-    const bool reverse = ((__ldg(B.len_flag + r) >> 16) & 0x10u) != 0u;
     const int b1 = reverse ? new_len - ins_end : p, b2 = reverse ? new_len - p : ins_end, d3 = reverse ? L - new_len : shift;
     const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
     auto qual_at = [&](int bidx) -> uint32_t {                         // 4 quality bytes from BAM byte bidx (>= -3)
@@ -204,22 +201,30 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
 __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
     __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
     const int tid = threadIdx.x, group = tid / kGroup, glane = tid % kGroup;
-    const unsigned long long n_all = O.totals->n_modified;
-    const int64_t n_rec = (int64_t)(n_all < (unsigned long long)O.cap_records ? n_all : (unsigned long long)O.cap_records);
     const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
     const uint32_t groups_total = gridDim.x * (kThreads / kGroup);
     for (uint32_t jb = blockIdx.x * (kThreads / kGroup) + (tid >> 5) * 4; jb < n_x; jb += groups_total) {   // warp-uniform
         const uint32_t j = jb + ((tid & 31) >> 3);
         const bool have = j < n_x;
-        const int64_t k = have ? (int64_t)E.special[j] : 0;
-        const uint32_t r_kind = (have && k < n_rec) ? E.kind[k] : 0u;    // 0xffffffff marks a slot of a session that did not fit
-        uint4 d = make_uint4(0u, 0u, 0u, 0u);
-        int64_t r = 0; int new_len = 0; uint64_t seq16 = 0, qual16 = 0;
-        if (r_kind) { d = E.edesc[k]; r = O.mod_read[k]; new_len = (int)O.mod_len[k]; seq16 = O.mod_seq_off16[k]; qual16 = O.mod_qual_off16[k]; }
-        const uint32_t r_src = d.x; const int r_pos = (int)d.y; const int s = (int)d.w;
-        int col_begin = 0;
+        // ---- the record's 64-byte descriptor: one round trip, one 16-byte part per lane of the group
+        uint4 part = make_uint4(0u, 0u, 0u, 0u);
+        if (have && glane < 4) part = E.sdesc[4ull * j + glane];
+        const int gbase = (tid & 31) & ~7;
+        uint4 d0, d1, d2, d3;
+        d0.x = __shfl_sync(0xffffffffu, part.x, gbase);     d0.y = __shfl_sync(0xffffffffu, part.y, gbase);
+        d0.z = __shfl_sync(0xffffffffu, part.z, gbase);     d0.w = __shfl_sync(0xffffffffu, part.w, gbase);
+        d1.x = __shfl_sync(0xffffffffu, part.x, gbase + 1); d1.y = __shfl_sync(0xffffffffu, part.y, gbase + 1);
+        d1.z = __shfl_sync(0xffffffffu, part.z, gbase + 1); d1.w = __shfl_sync(0xffffffffu, part.w, gbase + 1);
+        d2.x = __shfl_sync(0xffffffffu, part.x, gbase + 2); d2.y = __shfl_sync(0xffffffffu, part.y, gbase + 2);
+        d2.z = __shfl_sync(0xffffffffu, part.z, gbase + 2);
+        d3.x = __shfl_sync(0xffffffffu, part.x, gbase + 3); d3.y = __shfl_sync(0xffffffffu, part.y, gbase + 3);
+        const uint32_t r_kind = (d0.z >> 16) & 15u;                      // 0: the slot of a session that did not fit
+        const uint32_t r_src = d0.x; const int r_pos = (int)d0.y; const int s = (int)d0.w;
+        const int64_t r = (int64_t)d1.x; const int new_len = (int)d1.y; const uint64_t seq16 = d1.z, qual16 = d1.w;
+        const uint32_t c0 = d2.x, c1 = d2.y; const int col_begin = (int)d2.z;
+        const bool reverse = ((d0.z >> 20) & 1u) != 0u;
         GermList germ; germ.e = E.germ + (size_t)s * kGermStride + 4; germ.n = 0u;
-        if (r_kind) { germ.n = __ldg(E.germ + (size_t)s * kGermStride); col_begin = (int)__ldg(E.germ + (size_t)s * kGermStride + 1); }
+        if (r_kind) germ.n = __ldg(E.germ + (size_t)s * kGermStride);
         {
                 if (r_kind == 4u) {
                     const int L = new_len;
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
                 for (int q = 0; q < 2; ++q) { Ed.irp[q] = 0; Ed.len[q] = 0; Ed.pos[q] = 0; Ed.mean[q] = 0u; Ed.p[q] = 0; Ed.e[q] = 0; }
                 int64_t q_lo = 0, q_hi = 0;
                 const uint8_t* qrec = nullptr;
-                const int L = (int)d.z;
+                const int L = (int)(d0.z & 0xffffu);
                 if (indel) {
                     const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
                     const uint4 x0 = ap[0], x1 = ap[1];              // EditAux written by the resolve kernel
@@ -265,8 +270,7 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
                     Ed.irp[1] = (int)x0.w; Ed.pos[1] = (int)x1.x; Ed.len[1] = (int)(x1.y & 0x7fffffffu);
                     Ed.ne = (int)(x1.z & 0xffu); Ed.n_del = (int)((x1.z >> 8) & 0xffu);
                     clamp_edits2(Ed, L);
-                    const bool tumor = r < B.n_tumor;
-                    q_lo = tumor ? descs[s].qt_begin : descs[s].qn_begin; q_hi = tumor ? descs[s].qt_end : descs[s].qn_end;
+                    q_lo = (int64_t)d3.x; q_hi = (int64_t)d3.y;
                     // the read's quality record: dense upload, or the slot the resolve kernel predicted in the sparse
                     // index (verified; a caller may list more reads than those with I/D ops), or a search of the slice
                     if (B.qual && !B.qual_reads) qrec = B.qual + 32ull * r_src;
@@ -280,9 +284,8 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
                 // the common shapes take the staged path; two edits or very long reads take the general one
                 const bool fast = (r_kind == 2u || (indel && Ed.ne == 1)) && ((L + 7) >> 3) <= kGroupStage - 1;
                 if (__any_sync(0xffffffffu, fast))
-                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, col_begin, germ, qrec, stage[group], seq16, qual16, new_len, glane);
+                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, c0, c1, reverse, col_begin, germ, qrec, stage[group], seq16, qual16, new_len, glane);
                 if (r_kind == 2u && !fast) {
-                    const uint32_t c0 = __ldg(B.cigar_off + r), c1 = __ldg(B.cigar_off + r + 1);
                     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
                     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
                     masked_words_g(B, r, r_pos, new_len, c0, c1, col_begin, units * 4, glane, kGroup, germ, [&](int wd, uint32_t v) { oseq[wd] = v; });

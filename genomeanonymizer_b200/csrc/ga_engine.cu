@@ -255,7 +255,7 @@ static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int
         const int64_t cap = cap_records + cap_records / 8 + 1024;
         GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
         GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
-        GA_CUDA(cudaMalloc(&L.d_special, (size_t)cap * sizeof(uint32_t)));
+        GA_CUDA(cudaMalloc(&L.d_special, (size_t)cap * 4 * sizeof(uint4)));
         L.cap_kind = cap;
     }
     if (n_sessions > L.cap_germ) {
@@ -377,7 +377,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     rc = ensure_stream_scratch(e, L, out->cap_records, S->n_sessions); if (rc) return rc;
     ga::ScanScratch X; X.ent = L.d_ent; X.obs = reinterpret_cast<ga::ObsRec*>(L.d_obs); X.cnt = reinterpret_cast<uint4*>(L.d_cnt);
     ga::EmitScratch2 E; E.kind = L.d_kind; E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
-    E.special = L.d_special; E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
+    E.sdesc = reinterpret_cast<uint4*>(L.d_special); E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;

@@ -16,7 +16,7 @@ struct Lane {
     uint8_t* d_big_scratch = nullptr;
     // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)
     uint32_t* d_ent = nullptr; void* d_obs = nullptr; void* d_cnt = nullptr; int64_t cap_items = 0;
-    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; uint32_t* d_special = nullptr; int64_t cap_kind = 0;
+    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; void* d_special = nullptr; int64_t cap_kind = 0;
     uint32_t* d_germ = nullptr; int64_t cap_germ = 0;
     // CUDA events between the stages of the most recent kTimedRuns runs (ring), recorded on the launching stream so
     // bench.py can read per-launch durations after its timed region without syncing inside it:

@@ -34,9 +34,23 @@ struct EmitScratch2 {
     uint4* edesc;        // [cap_records] kind 1: {source record unit, pos - col_begin, length | hits << 16, two hits ((column << 4) | reference code)}
                          //               else:   {source record unit, pos, length, session}
     uint32_t* germ;      // [n_sessions][kGermStride]
-    uint32_t* special;   // [cap_records] indices of the records of kind >= 2, packed (emit_special_kernel walks them densely)
+    uint4* sdesc;        // [cap_records][4] everything emit_special_kernel needs about one record of kind >= 2, packed densely:
+                         //   {source record unit, pos, length | kind << 16 | reverse << 20, session}
+                         //   {read, new length, output sequence unit, output quality unit}
+                         //   {first CIGAR word, one past the last, col_begin, -}   {quality-index slice begin, end, -, -}
+                         // kind 0 marks a slot whose session did not fit the caller's capacities
     uint32_t* n_special;
 };
+
+__device__ __forceinline__ void write_special(const EmitScratch2& E, const BatchView& B, const SessionDesc& d, uint32_t slot, uint32_t kind,
+                                              uint32_t so, int pos, uint32_t lf, int s, int64_t r, uint32_t new_len, uint64_t seq16, uint32_t qual16) {
+    uint4* dp = E.sdesc + 4ull * slot;
+    const bool tumor = r < B.n_tumor;
+    dp[0] = make_uint4(so, (uint32_t)pos, (lf & 0xffffu) | (kind << 16) | (((lf >> 20) & 1u) << 20), (uint32_t)s);
+    dp[1] = make_uint4((uint32_t)r, new_len, (uint32_t)seq16, qual16);
+    dp[2] = make_uint4(__ldg(B.cigar_off + r), __ldg(B.cigar_off + r + 1), (uint32_t)d.col_begin, 0u);
+    dp[3] = make_uint4((uint32_t)(tumor ? d.qt_begin : d.qn_begin), (uint32_t)(tumor ? d.qt_end : d.qn_end), 0u, 0u);
+}
 
 struct SmemR {
     uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
@@ -366,9 +380,8 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             const int pos = __ldg(B.pos + r);
             if (kind == 1) E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
             else {
-                E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)pos, lf & 0xffffu, (uint32_t)s);
                 const uint32_t slot = atomicAdd(E.n_special, 1u);
-                if ((int64_t)slot < O.cap_records) E.special[slot] = (uint32_t)rec_idx;
+                if ((int64_t)slot < O.cap_records) write_special(E, B, c.d, slot, kind, __ldg(B.seq_off16 + r), pos, lf, s, r, m & kLen2, s_base[1] + sm->mseq[k], qual16);
             }
             if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
@@ -718,7 +731,7 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
         const bool fits = (int64_t)(base_rec + n_mod) <= O.cap_records && (int64_t)(base_seq + tot_seq) <= O.cap_seq16 &&
                           (int64_t)(base_qual + tot_qual) <= O.cap_qual16;
         if (!fits) {                                                  // the reserved special slots must not stay undefined
-            for (uint32_t t = lane; t < n_spec; t += 32) if ((int64_t)(spec_base + t) < O.cap_records) E.special[spec_base + t] = 0xffffffffu;
+            for (uint32_t t = lane; t < n_spec; t += 32) if ((int64_t)(spec_base + t) < O.cap_records) E.sdesc[4ull * (spec_base + t)] = make_uint4(0u, 0u, 0u, 0u);
             if (lane == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu);
             continue;
         }
@@ -741,8 +754,7 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
             run_seq += ts; run_qual += tq;
             const bool is_spec = have_k && kind != 1u;
             const uint32_t sb = __ballot_sync(0xffffffffu, is_spec);
-            if (is_spec && (int64_t)(spec_base + __popc(sb & ((1u << lane) - 1u))) < O.cap_records)
-                E.special[spec_base + __popc(sb & ((1u << lane) - 1u))] = (uint32_t)(base_rec + k);
+            const uint32_t my_slot = spec_base + __popc(sb & ((1u << lane) - 1u));
             spec_base += __popc(sb);
             if (!have_k) continue;
             const uint64_t rec_idx = base_rec + k;
@@ -781,9 +793,12 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
                 }
                 continue;                                             // E.kind stays 0: nothing left for the emission kernels
             }
-            E.kind[rec_idx] = (uint8_t)kind;
-            if (kind == 1u) E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
-            else E.edesc[rec_idx] = make_uint4(so, (uint32_t)pos, L0, (uint32_t)s);
+            if (kind == 1u) {                                         // a long clean read: the copy kernel takes it
+                E.kind[rec_idx] = 1;
+                E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
+            } else if ((int64_t)my_slot < O.cap_records) {
+                write_special(E, B, c.d, my_slot, kind, so, pos, lf, s, r, new_len, base_seq + so_rel, qual16);
+            }
             if (kind == 3u) {                                         // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
                 lean_collect(c, sm, (int)k, (int)L0, E2, &nl);
