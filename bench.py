@@ -158,6 +158,59 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def bench_bam_decode(n_reads=400_000, read_len=150):
+    """N4 measurement (host only, SURVEY.md 8(d) level iii input side): BGZF inflate + CRC + BAM record packing into
+    the engine's SoA batch by genome_files (csrc/ga_genome_io.cpp) on all host threads.  The BAM is synthetic:
+    fixed-shape records built with numpy and deflated per 64 KiB block by Python's zlib (test-side writer)."""
+    import struct, tempfile, zlib
+    import numpy as np
+    from genomeanonymizer_b200 import genome_files as GF
+    rng = np.random.default_rng(7)
+    name_len, nb = 9, (read_len + 1) // 2
+    rec_len = 4 + 32 + name_len + 4 + nb + read_len
+    recs = np.zeros((n_reads, rec_len), np.uint8)
+    pos = np.sort(rng.integers(0, 50_000_000, n_reads)).astype("<i4")
+    fixed = np.zeros(n_reads, dtype=[("bs", "<u4"), ("ref", "<i4"), ("pos", "<i4"), ("lname", "u1"), ("mapq", "u1"), ("bin", "<u2"),
+                                     ("ncig", "<u2"), ("flag", "<u2"), ("lseq", "<u4"), ("nref", "<i4"), ("npos", "<i4"), ("tlen", "<i4")])
+    fixed["bs"], fixed["pos"], fixed["lname"], fixed["mapq"], fixed["ncig"] = rec_len - 4, pos, name_len, 60, 1
+    fixed["flag"], fixed["lseq"], fixed["nref"], fixed["npos"] = 99, read_len, -1, -1
+    recs[:, :36] = fixed.view(np.uint8).reshape(n_reads, 36)
+    names = np.char.add("T", np.char.zfill(np.arange(n_reads).astype(str), 7)).astype("S8")
+    recs[:, 36:44] = np.frombuffer(names.tobytes(), np.uint8).reshape(n_reads, 8)
+    recs[:, 45:49] = np.frombuffer(struct.pack("<I", read_len << 4), np.uint8)
+    codes = np.array([1, 2, 4, 8], np.uint8)[rng.integers(0, 4, (n_reads, 2 * nb))]
+    recs[:, 49:49 + nb] = (codes[:, 0::2] << 4) | codes[:, 1::2]
+    recs[:, 49 + nb:] = rng.integers(2, 41, (n_reads, read_len), dtype=np.uint8)
+    text = "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chr22\tLN:50818468\n"
+    stream = (b"BAM\1" + struct.pack("<I", len(text)) + text.encode() + struct.pack("<I", 1) + struct.pack("<I", 6) + b"chr22\0" +
+              struct.pack("<I", 50818468) + recs.tobytes())
+    tmp = tempfile.mkdtemp(prefix="ga_bam_")
+    path = os.path.join(tmp, "synthetic.bam")
+    with open(path, "wb") as fh:
+        for o in range(0, len(stream), 0xff00):
+            d = stream[o:o + 0xff00]
+            co = zlib.compressobj(1, zlib.DEFLATED, -15)
+            cd = co.compress(d) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cd) + 25) + cd +
+                     struct.pack("<II", zlib.crc32(d) & 0xffffffff, len(d)))
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    size = os.path.getsize(path)
+    best_open = best_pack = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        f = GF.BamFile(path)
+        t1 = time.perf_counter()
+        cb = GF.pack_tumor_normal(f, f, "chr22")
+        t2 = time.perf_counter()
+        f.close()
+        best_open, best_pack = min(best_open, t1 - t0), min(best_pack, (t2 - t1) / 2)
+    assert cb.batch.n_reads == 2 * n_reads and np.array_equal(cb.batch.pos[:n_reads], pos)
+    os.remove(path); os.rmdir(tmp)
+    return {"api": "ga_bam_open + ga_bam_pack_contig (C ABI, host threads)", "reads": n_reads, "bam_bytes": size, "inflated_bytes": len(stream),
+            "threads": os.cpu_count(), "open_ms": best_open * 1e3, "pack_ms": best_pack * 1e3,
+            "reads_per_s": n_reads / (best_open + best_pack), "inflated_gbs": len(stream) / (best_open + best_pack) / 1e9}
+
+
 def bench_fastq(eng, cfg, dev, n_w, peak):
     """ga_fastq_layout + ga_fastq_render over every read of the first n_w windows: masked where a session modified
     the read (lowest record index wins), as it came in otherwise.  Dense synthetic qualities, 10-character names."""
@@ -247,6 +300,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fastq", action="store_true")
+    ap.add_argument("--no-bam", action="store_true")
     ap.add_argument("--fastq-windows", type=int, default=10000, help="windows rendered by the FASTQ measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -418,6 +472,9 @@ def main():
         del hb, hres
 
     # ---- next row of the scope table: FASTQ rendering of the masked reads, device resident
+    bam = None
+    if rank == 0 and world == 1 and not args.no_bam:
+        bam = bench_bam_decode()
     fastq = None
     if rank == 0 and world == 1 and not args.no_fastq:
         fastq = bench_fastq(eng, cfg, dev, min(n_w, args.fastq_windows), peak)
@@ -454,7 +511,7 @@ def main():
                            "sharding": "one contig-sized region per GPU, no data-path collective" if world > 1 else "single GPU",
                            "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
                 "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "gpu_launches": total_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "bam_decode": bam, "gpu_launches": total_launches,
                 "clocks": sampler.summary(), "parity_vs_oracle_on_sample": parity}
         print(json.dumps(line))
     if world > 1:

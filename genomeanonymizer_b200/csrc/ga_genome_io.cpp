@@ -1,0 +1,351 @@
+// ga_genome_io.cpp - host-side readers behind include/ga_genome_io.h: BGZF/BAM -> the
+// structure-of-arrays read batch of ga_b200.h, FASTA -> contig bases.  zlib only; every stage that touches all
+// the bytes (inflate + CRC, record packing) runs on all host threads.
+//
+// Formats restated from the SAM/BAM specification (SAMv1 4.1 BGZF, 4.2 BAM): a BGZF file is a series of gzip
+// members of at most 64 KiB with a 'BC' extra subfield holding the member size; the inflated stream is
+// "BAM\1", header text, the reference dictionary, then alignment records (block_size, refID, pos, l_read_name,
+// mapq, bin, n_cigar_op, flag, l_seq, next_refID, next_pos, tlen, name, CIGAR words, 4-bit bases HIGH nibble
+// first, qualities, tags).  The reference reads the same files through pysam / htslib
+// (short_read_tumor_normal_anonymizer.py:661-664, pileup_io.pyx:12-17, 138-139).
+#include "../../include/ga_genome_io.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+int n_workers(int requested) {
+    if (requested > 0) return requested;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+
+template <class F> void parallel_for(int64_t n, int threads, int64_t grain, F&& body) {
+    if (n <= 0) return;
+    const int64_t n_chunks = (n + grain - 1) / grain;
+    const int t = (int)std::min<int64_t>(threads, n_chunks);
+    if (t <= 1) { body(0, n); return; }
+    std::atomic<int64_t> next(0);
+    std::vector<std::thread> pool;
+    pool.reserve(t);
+    for (int k = 0; k < t; ++k)
+        pool.emplace_back([&] {
+            for (;;) {
+                const int64_t c = next.fetch_add(1);
+                if (c >= n_chunks) return;
+                body(c * grain, std::min(n, (c + 1) * grain));
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
+bool read_file(const char* path, std::vector<uint8_t>& out) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    if (n < 0) { std::fclose(f); return false; }
+    out.resize((size_t)n);
+    const size_t got = n ? std::fread(out.data(), 1, (size_t)n, f) : 0;
+    std::fclose(f);
+    return got == (size_t)n;
+}
+
+inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+struct Block { uint64_t in_off; uint32_t in_size; uint64_t out_off; uint32_t out_size; };
+
+// Walks the gzip members of a BGZF file; false when the container is malformed.
+bool index_bgzf(const std::vector<uint8_t>& file, std::vector<Block>& blocks, uint64_t* total, std::string* why) {
+    uint64_t off = 0, out = 0;
+    const uint64_t n = file.size();
+    while (off < n) {
+        if (n - off < 18) { *why = "truncated BGZF block header"; return false; }
+        const uint8_t* h = file.data() + off;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) { *why = "not a BGZF block (gzip magic / FEXTRA missing)"; return false; }
+        const uint32_t xlen = le16(h + 10);
+        if (n - off < 12 + xlen) { *why = "truncated BGZF extra field"; return false; }
+        int64_t bsize = -1;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t* sf = h + 12 + x;
+            const uint32_t slen = le16(sf + 2);
+            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (int64_t)le16(sf + 4) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < (int64_t)(12 + xlen + 8) || (uint64_t)bsize > n - off) { *why = "BGZF block size field missing or beyond the file"; return false; }
+        const uint32_t isize = le32(h + bsize - 4);
+        if (isize > 65536u) { *why = "BGZF block inflates to more than 64 KiB"; return false; }
+        blocks.push_back({off, (uint32_t)bsize, out, isize});
+        off += (uint64_t)bsize;
+        out += isize;
+    }
+    *total = out;
+    return true;
+}
+
+bool inflate_block(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint32_t dst_size) {
+    const uint32_t xlen = le16(src + 10);
+    const uint8_t* cdata = src + 12 + xlen;
+    const uint32_t clen = src_size - 12 - xlen - 8;
+    z_stream zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef*>(cdata); zs.avail_in = clen;
+    zs.next_out = dst; zs.avail_out = dst_size;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = (rc == Z_STREAM_END) && zs.total_out == dst_size;
+    inflateEnd(&zs);
+    if (!ok) return false;
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, dst_size);
+    return crc == le32(src + src_size - 8);
+}
+
+inline int ref_span_of(const uint8_t* cigar, uint32_t n_ops) {
+    int span = 0;
+    for (uint32_t k = 0; k < n_ops; ++k) {
+        const uint32_t w = le32(cigar + 4 * k), op = w & 15u;
+        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
+    }
+    return span;
+}
+
+}  // namespace
+
+struct ga_bam {
+    std::vector<uint8_t> data;                    // the inflated BAM stream
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    std::vector<std::vector<uint64_t>> by_ref;    // per reference: offsets (of refID, i.e. past block_size) in file order
+    int64_t n_records = 0;
+};
+
+struct ga_fasta {
+    std::vector<std::string> names;
+    std::vector<std::string> seqs;                // newline-free bases, case kept
+};
+
+extern "C" {
+
+const char* ga_io_last_error(void) { return g_err.c_str(); }
+
+int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
+    if (!path || !out) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_open: NULL argument");
+    *out = nullptr;
+    std::vector<uint8_t> file;
+    if (!read_file(path, file)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
+    std::vector<Block> blocks;
+    uint64_t total = 0;
+    std::string why;
+    if (!index_bgzf(file, blocks, &total, &why)) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + why);
+    ga_bam* b = new ga_bam();
+    b->data.resize(total);
+    std::atomic<int> bad(0);
+    parallel_for((int64_t)blocks.size(), n_workers(n_threads), 64, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const Block& bl = blocks[k];
+            if (bl.out_size == 0) continue;                               // the EOF marker block
+            if (!inflate_block(file.data() + bl.in_off, bl.in_size, b->data.data() + bl.out_off, bl.out_size)) bad.store(1);
+        }
+    });
+    if (bad.load()) { delete b; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": a BGZF block failed to inflate or its CRC32 does not match"); }
+    file.clear(); file.shrink_to_fit();
+    // ---- header
+    const uint8_t* d = b->data.data();
+    const uint64_t n = b->data.size();
+    auto corrupt = [&](const char* what) { delete b; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + what); };
+    if (n < 12 || std::memcmp(d, "BAM\1", 4) != 0) return corrupt("BAM magic missing");
+    uint64_t off = 4;
+    const uint32_t l_text = le32(d + off); off += 4;
+    if (off + l_text + 4 > n) return corrupt("truncated header text");
+    off += l_text;
+    const uint32_t n_ref = le32(d + off); off += 4;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (off + 4 > n) return corrupt("truncated reference dictionary");
+        const uint32_t l_name = le32(d + off); off += 4;
+        if (off + l_name + 4 > n || l_name == 0) return corrupt("truncated reference dictionary");
+        b->ref_names.emplace_back(reinterpret_cast<const char*>(d + off), l_name - 1);
+        off += l_name;
+        b->ref_lens.push_back((int64_t)le32(d + off)); off += 4;
+    }
+    b->by_ref.resize(n_ref);
+    // ---- record index (one hop per record)
+    while (off < n) {
+        if (off + 4 > n) return corrupt("truncated alignment record");
+        const uint32_t block_size = le32(d + off);
+        if (block_size < 32 || off + 4 + block_size > n) return corrupt("alignment record runs past the end of the stream");
+        const int32_t ref_id = (int32_t)le32(d + off + 4);
+        if (ref_id >= 0 && (uint32_t)ref_id < n_ref) b->by_ref[ref_id].push_back(off + 4);
+        else if (ref_id != -1) return corrupt("alignment record names a reference that is not in the header");
+        b->n_records++;
+        off += 4 + (uint64_t)block_size;
+    }
+    *out = b;
+    return GA_IO_OK;
+}
+
+void ga_bam_close(ga_bam* b) { delete b; }
+int ga_bam_n_references(const ga_bam* b) { return b ? (int)b->ref_names.size() : 0; }
+const char* ga_bam_reference_name(const ga_bam* b, int ref_id) {
+    return (b && ref_id >= 0 && ref_id < (int)b->ref_names.size()) ? b->ref_names[ref_id].c_str() : nullptr;
+}
+int64_t ga_bam_reference_length(const ga_bam* b, int ref_id) {
+    return (b && ref_id >= 0 && ref_id < (int)b->ref_lens.size()) ? b->ref_lens[ref_id] : -1;
+}
+int64_t ga_bam_n_records(const ga_bam* b) { return b ? b->n_records : 0; }
+int64_t ga_bam_inflated_bytes(const ga_bam* b) { return b ? (int64_t)b->data.size() : 0; }
+
+// Fixed part of an alignment record, p = address of refID.
+struct RecView {
+    int32_t pos; uint32_t l_name, n_cigar, flag, l_seq;
+    const uint8_t *name, *cigar, *seq, *qual;
+};
+static inline RecView view_of(const uint8_t* p) {
+    RecView v;
+    v.pos = (int32_t)le32(p + 4);
+    v.l_name = p[8];
+    v.n_cigar = le16(p + 12);
+    v.flag = le16(p + 14);
+    v.l_seq = le32(p + 16);
+    v.name = p + 32;
+    v.cigar = v.name + v.l_name;
+    v.seq = v.cigar + 4ull * v.n_cigar;
+    v.qual = v.seq + (v.l_seq + 1) / 2;
+    return v;
+}
+static inline uint32_t units_of(uint32_t l_seq) { const uint32_t u = (l_seq + 31u) / 32u; return u ? u : 1u; }
+
+int ga_bam_contig_sizes(const ga_bam* b, int ref_id, uint32_t flag_exclude, ga_bam_sizes* out) {
+    if (!b || !out || ref_id < 0 || ref_id >= (int)b->by_ref.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_contig_sizes: bad argument");
+    ga_bam_sizes s;
+    std::memset(&s, 0, sizeof(s));
+    s.sorted = 1;
+    int32_t prev = INT32_MIN;
+    for (const uint64_t off : b->by_ref[ref_id]) {
+        const uint8_t* p = b->data.data() + off;
+        const RecView v = view_of(p);
+        if (v.flag & flag_exclude) continue;
+        if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
+        const uint32_t block_size = le32(p - 4);
+        if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > block_size)
+            return fail(GA_IO_ERR_FORMAT, "alignment record fields exceed its block size");
+        s.n_reads++;
+        s.seq16_units += units_of(v.l_seq);
+        s.n_cigar += v.n_cigar;
+        s.name_bytes += v.l_name ? v.l_name - 1 : 0;
+        s.max_ref_span = std::max(s.max_ref_span, (int32_t)ref_span_of(v.cigar, v.n_cigar));
+        if (v.pos < prev) s.sorted = 0;
+        prev = v.pos;
+    }
+    *out = s;
+    return GA_IO_OK;
+}
+
+int ga_bam_pack_contig(const ga_bam* b, int ref_id, uint32_t flag_exclude, const ga_bam_dest* dst, int n_threads) {
+    if (!b || !dst || ref_id < 0 || ref_id >= (int)b->by_ref.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_pack_contig: bad argument");
+    if (!dst->pos || !dst->len_flag || !dst->seq_off16 || !dst->cigar_off || !dst->seq4 || !dst->cigar)
+        return fail(GA_IO_ERR_ARGUMENT, "ga_bam_pack_contig: NULL destination array");
+    // ---- pass 1 (sequential, one hop per record): which records, and where each one goes
+    std::vector<uint64_t> recs;
+    recs.reserve(b->by_ref[ref_id].size());
+    for (const uint64_t off : b->by_ref[ref_id])
+        if (!(le16(b->data.data() + off + 14) & flag_exclude)) recs.push_back(off);
+    const int64_t n = (int64_t)recs.size();
+    uint64_t u = dst->seq16_base, c = dst->cigar_base, nm = dst->name_base;
+    for (int64_t k = 0; k < n; ++k) {
+        const RecView v = view_of(b->data.data() + recs[k]);
+        if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
+        dst->seq_off16[k] = (uint32_t)u;
+        dst->cigar_off[k] = (uint32_t)c;
+        if (dst->name_off) dst->name_off[k] = nm;
+        u += units_of(v.l_seq); c += v.n_cigar; nm += v.l_name ? v.l_name - 1 : 0;
+        if (u > 0xffffffffull || c > 0xffffffffull) return fail(GA_IO_ERR_UNSUPPORTED, "batch exceeds the 32-bit record offsets: pack the contig in chunks");
+    }
+    dst->cigar_off[n] = (uint32_t)c;
+    if (dst->name_off) dst->name_off[n] = nm;
+    // ---- pass 2 (parallel): the record bytes
+    parallel_for(n, n_workers(n_threads), 4096, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const RecView v = view_of(b->data.data() + recs[k]);
+            dst->pos[k] = v.pos;
+            dst->len_flag[k] = (v.flag << 16) | v.l_seq;
+            if (dst->ref_end) dst->ref_end[k] = v.pos + ref_span_of(v.cigar, v.n_cigar);
+            std::memcpy(dst->cigar + dst->cigar_off[k], v.cigar, 4ull * v.n_cigar);       // BAM words are little endian, as is the host
+            const uint32_t cap = units_of(v.l_seq) * 16u, nb = (v.l_seq + 1) / 2;
+            uint8_t* s = dst->seq4 + 16ull * dst->seq_off16[k];
+            for (uint32_t j = 0; j < nb; ++j) s[j] = (uint8_t)((v.seq[j] >> 4) | (v.seq[j] << 4));   // HIGH-nibble-first -> LOW-nibble-first
+            std::memset(s + nb, 0, cap - nb);
+            if (dst->qual) {
+                uint8_t* q = dst->qual + 32ull * dst->seq_off16[k];
+                std::memcpy(q, v.qual, v.l_seq);
+                std::memset(q + v.l_seq, 0, 2ull * cap - v.l_seq);
+            }
+            if (dst->names && dst->name_off && v.l_name) std::memcpy(dst->names + dst->name_off[k], v.name, v.l_name - 1);
+        }
+    });
+    return GA_IO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ FASTA
+int ga_fasta_open(const char* path, ga_fasta** out) {
+    if (!path || !out) return fail(GA_IO_ERR_ARGUMENT, "ga_fasta_open: NULL argument");
+    *out = nullptr;
+    std::vector<uint8_t> file;
+    if (!read_file(path, file)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
+    if (file.size() >= 2 && file[0] == 31 && file[1] == 139) return fail(GA_IO_ERR_UNSUPPORTED, std::string(path) + ": compressed FASTA is not supported");
+    ga_fasta* f = new ga_fasta();
+    const uint8_t* p = file.data();
+    const uint8_t* end = p + file.size();
+    while (p < end) {
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p, '\n', (size_t)(end - p)));
+        const uint8_t* le = nl ? nl : end;
+        const uint8_t* stop = le;
+        if (stop > p && stop[-1] == '\r') --stop;
+        if (p < stop && *p == '>') {
+            const uint8_t* q = p + 1;
+            while (q < stop && *q != ' ' && *q != '\t') ++q;                 // the name ends at the first blank
+            f->names.emplace_back(reinterpret_cast<const char*>(p + 1), (size_t)(q - p - 1));
+            f->seqs.emplace_back();
+        } else if (p < stop) {
+            if (f->seqs.empty()) { delete f; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": sequence data before the first '>' line"); }
+            f->seqs.back().append(reinterpret_cast<const char*>(p), (size_t)(stop - p));
+        }
+        p = nl ? nl + 1 : end;
+    }
+    if (f->names.empty()) { delete f; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": no FASTA record"); }
+    *out = f;
+    return GA_IO_OK;
+}
+
+void ga_fasta_close(ga_fasta* f) { delete f; }
+int ga_fasta_n_references(const ga_fasta* f) { return f ? (int)f->names.size() : 0; }
+const char* ga_fasta_reference_name(const ga_fasta* f, int idx) {
+    return (f && idx >= 0 && idx < (int)f->names.size()) ? f->names[idx].c_str() : nullptr;
+}
+int64_t ga_fasta_reference_length(const ga_fasta* f, int idx) {
+    return (f && idx >= 0 && idx < (int)f->seqs.size()) ? (int64_t)f->seqs[idx].size() : -1;
+}
+int64_t ga_fasta_fetch(const ga_fasta* f, int idx, int64_t start, int64_t end, uint8_t* out) {
+    if (!f || !out || idx < 0 || idx >= (int)f->seqs.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_fasta_fetch: bad argument");
+    const int64_t n = (int64_t)f->seqs[idx].size();
+    if (start < 0) start = 0;
+    if (end > n) end = n;
+    if (end <= start) return 0;
+    std::memcpy(out, f->seqs[idx].data() + start, (size_t)(end - start));
+    return end - start;
+}
+
+}  // extern "C"

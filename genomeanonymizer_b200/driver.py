@@ -233,19 +233,23 @@ def plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int)
     return plan
 
 
-def statistics_text(contig: str, plan: Plan, sess_counts) -> str:
+def statistics_text(contig, plan: Optional[Plan] = None, sess_counts=None) -> str:
     """The `<normal_bam>.statistics.txt` file (AnonymizedVariantsStatistics.write_statistics,
     short_read_tumor_normal_anonymizer.py:212-242): one row per variant window with the masked variants by type
     (SNV, DEL, INS and the five structural types this path never calls), island sessions summed into the
-    `outside_windows` row, then total / mean / median / max / min over ALL rows."""
+    `outside_windows` row, then total / mean / median / max / min over ALL rows.
+    statistics_text(contig, plan, counts) for one contig, or statistics_text([(contig, plan, counts), ...]) for a
+    sample of several contigs in genome order."""
     import numpy as np
+    parts = [(contig, plan, sess_counts)] if plan is not None else list(contig)
     rows = [("outside_windows", "-", "-", [0] * 8)]
-    for s, ses in enumerate(plan.sessions):
-        c = [int(x) for x in sess_counts[s][:3]] + [0] * 5
-        if ses["window"] is None:
-            rows[0] = rows[0][:3] + ([a + b for a, b in zip(rows[0][3], c)],)
-        else:
-            rows.append((contig, str(ses["first"]), str(ses["last"]), c))
+    for name, pl, counts8 in parts:
+        for s, ses in enumerate(pl.sessions):
+            c = [int(x) for x in counts8[s][:3]] + [0] * 5
+            if ses["window"] is None:
+                rows[0] = rows[0][:3] + ([a + b for a, b in zip(rows[0][3], c)],)
+            else:
+                rows.append((name, str(ses["first"]), str(ses["last"]), c))
     out = ["\t".join(["#SEQ", "#FIRST", "#LAST", "#SNV", "#DEL", "#INS", "#DUP", "#INV", "#CNV", "#TRA", "#SGL"])]
     out += ["\t".join([a, b, c] + [str(x) for x in counts]) for a, b, c, counts in rows]
     out.append("### Overall statistics:")
@@ -263,15 +267,25 @@ def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], ref
     cigar / seq / qual.  Returns the reference's output files as {suffix: text}: "T.1", "T.2", "T.single_end",
     "N.1", "N.2", "N.single_end", "statistics"."""
     import re
+    from . import batch as B
+    cig = re.compile(r"(\d+)([MIDNSHP=X])")
+    rs = [dict(r, end=r["pos"] + sum(int(n) for n, op in cig.findall(r["cigar"]) if op in "MDN=X")) for r in reads]
+    batch = B.pack_reads(rs)                                      # dense qualities: every read is printed
+    return anonymize_packed(engine, batch, [r["name"] for r in rs], rs, windows, reference, contig)
+
+
+def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: Sequence[dict], reference,
+                     contig: str = "c", plan: Optional[Plan] = None) -> Dict[str, str]:
+    """Same for an already packed batch (batch.ReadBatch with dense qualities, e.g. from
+    genome_files.pack_tumor_normal): names = list of str or (uint8 blob, int64 offsets); read_table = rows with name /
+    flag / dataset / pos / end for the planner; reference = str / bytes / uint8 array of the contig."""
     import torch
     from . import batch as B
     from .engine import DeviceBatch, DeviceResult, DeviceSessions
-    cig = re.compile(r"(\d+)([MIDNSHP=X])")
-    rs = [dict(r, end=r["pos"] + sum(int(n) for n, op in cig.findall(r["cigar"]) if op in "MDN=X")) for r in reads]
-    plan = plan_sample(rs, windows, len(reference))
-    batch = B.pack_reads(rs)                                      # dense qualities: every read is printed
+    if plan is None:
+        plan = plan_sample(read_table, windows, len(reference))
     sessions = B.pack_sessions(plan.sessions)
-    engine.upload_reference(0, reference)
+    engine.upload_reference(batch.contig_id, reference if isinstance(reference, (str, bytes)) else np.ascontiguousarray(reference, np.uint8).tobytes())
     db, ds = DeviceBatch(batch, engine.device), DeviceSessions(sessions, engine.device)
     units = batch.seq4.shape[0] // 16
     dres = DeviceResult(sessions.n_sessions, 2 * batch.n_reads + 16, 2 * units + 64, 2 * units + 64, engine.device)
@@ -280,7 +294,7 @@ def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], ref
     n = int(engine.check_device_status(dres).n_modified)
     rec_of = {(int(s), int(r)): k for k, (s, r) in enumerate(zip(dres.mod_session[:n].cpu().numpy(), dres.mod_read[:n].cpu().numpy()))}
     order = [(r1, v1) for _, r1, v1, _, _ in plan.pairs] + [(r2, v2) for _, _, _, r2, v2 in plan.pairs] + [(r, v) for _, r, v in plan.singles]
-    text, off = engine.render_fastq(db, [r["name"] for r in rs], [i for i, _ in order], [rec_of.get((v, i), -1) for i, v in order], dres, n)
+    text, off = engine.render_fastq(db, names, [i for i, _ in order], [rec_of.get((v, i), -1) for i, v in order], dres, n)
     piece = lambda k: text[off[k]:off[k + 1]].decode("ascii")
     files = {f"{p}.{s}": [] for p in "TN" for s in ("1", "2", "single_end")}
     np_ = len(plan.pairs)
@@ -292,4 +306,6 @@ def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], ref
     out = {k: "".join(v) for k, v in files.items()}
     counts = dres.sess_counts.view(-1, 4)[:sessions.n_sessions].cpu().numpy()
     out["statistics"] = statistics_text(contig, plan, counts)
+    out["_plan"] = plan
+    out["_counts"] = counts
     return out

@@ -199,10 +199,15 @@ class Engine:
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream(self.device).cuda_stream
             n = len(reads_idx)
-            enc = [nm.encode("ascii") for nm in names]
-            name_off = np.zeros(len(enc) + 1, np.int64)
-            np.cumsum([len(b) for b in enc], out=name_off[1:])
-            blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+            if isinstance(names, tuple):                              # (uint8 blob, int64 offsets), e.g. from genome_files
+                blob, name_off = np.ascontiguousarray(names[0], np.uint8), np.ascontiguousarray(names[1], np.int64)
+                if blob.size == 0:
+                    blob = np.zeros(1, np.uint8)
+            else:
+                enc = [nm.encode("ascii") for nm in names]
+                name_off = np.zeros(len(enc) + 1, np.int64)
+                np.cumsum([len(b) for b in enc], out=name_off[1:])
+                blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
             dev = self.device
             t_names = torch.from_numpy(blob.copy()).to(dev)
             t_noff = torch.from_numpy(name_off).to(dev)

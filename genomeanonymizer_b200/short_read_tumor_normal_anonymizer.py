@@ -1,0 +1,108 @@
+"""File-level entry point of the B200 path: tumor / normal BAM + somatic VCF + reference FASTA in, the reference's
+FASTQ files and statistics file out (SURVEY.md 8(b) "Python entry point", 8(f) N4).
+
+Mirrors `run_short_read_tumor_normal_anonymizer` (short_read_tumor_normal_anonymizer.py:889-893: same name, same
+positional arguments) and `name_output` (:55-58).  Per sample the reference runs `anonymize_genome` (:625-760), which
+walks the genome section by section through pysam; here every contig of the sample is decoded by the C++ readers
+(genome_files.py -> csrc/ga_genome_io.cpp), planned on the host (driver.plan_sample: sections, island sessions,
+mate pairing, first write wins), masked by ONE engine pass over all of its sessions and printed by the device
+FASTQ renderer.  Outputs, named as the reference names them:
+    <tumor_output>.1.fastq / .2.fastq, <normal_output>.1.fastq / .2.fastq       (:652-655)
+    <tumor_output>.single_end.fastq, <normal_output>.single_end.fastq             (:603-622; only when a read stayed unpaired)
+    <normal_bam_file>.statistics.txt                                              (:641, when record_statistics)
+
+Differences that are stated rather than hidden: `cpus` is the number of host threads of the file decoders (the
+reference forks one process per sample); `enhance_parallelization` (the reference splits a sample's BAMs into
+per-region files for its process pool, :795-885) has no counterpart - one GPU pass needs no such split - and is
+accepted and ignored; mates aligned to different contigs are planned per contig and therefore reach the
+single-end files (the reference pairs them when the second mate is fetched); VCF records other than plain SNV /
+DEL / INS / MNV are rejected (genome_files.read_vcf).  There is no CPU fallback: without a CUDA device the engine
+constructor raises.
+"""
+import logging
+import re
+from typing import List, Optional, Tuple
+
+from . import genome_files as GF
+from .driver import anonymize_packed, plan_sample, statistics_text
+
+DATASET_IDX_TUMORAL = 0      # variation_classifier.py:13
+DATASET_IDX_NORMAL = 1       # variation_classifier.py:14
+
+
+def name_output(sample: str) -> str:
+    """short_read_tumor_normal_anonymizer.py:55-58 (the reference's own, unescaped pattern)."""
+    return re.sub('.bam|.sam|.cram', '.anonymized', sample)
+
+
+def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: str, ref_genome_file: str, engine,
+                     tumor_output_fastq: str, normal_output_fastq: str, record_statistics: bool = True, cpus: int = 0):
+    """One tumor-normal sample, file to file.  Returns {"reads": n, "sessions": n, "modified_pairs_or_reads": ...}."""
+    fasta = GF.FastaFile(ref_genome_file)
+    outs = {("T", "1"): tumor_output_fastq + ".1.fastq", ("T", "2"): tumor_output_fastq + ".2.fastq",
+            ("N", "1"): normal_output_fastq + ".1.fastq", ("N", "2"): normal_output_fastq + ".2.fastq"}
+    handles = {k: open(p, "w") for k, p in outs.items()}       # truncated first, as the reference does (:652-655)
+    singles = {"T": [], "N": []}
+    stats_parts = []
+    n_reads = n_sessions = 0
+    try:
+        with GF.BamFile(tumor_bam_file, cpus) as tumor, GF.BamFile(normal_bam_file, cpus) as normal:
+            for contig_id, contig in enumerate(fasta.references):
+                windows = windows_by_contig.get(contig, [])
+                cb = GF.pack_tumor_normal(tumor, normal, contig, contig_id=contig_id)
+                if cb.batch.n_reads == 0 and not windows:
+                    continue
+                reference = fasta.fetch_bytes(contig)
+                table = cb.read_table()
+                plan = plan_sample(table, windows, len(reference))
+                if cb.batch.n_reads == 0:
+                    stats_parts.append((contig, plan, [[0, 0, 0, 0]] * len(plan.sessions)))
+                    continue
+                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), table, windows, reference, contig, plan=plan)
+                for p in "TN":
+                    handles[(p, "1")].write(got[f"{p}.1"])
+                    handles[(p, "2")].write(got[f"{p}.2"])
+                    singles[p].append(got[f"{p}.single_end"])
+                stats_parts.append((contig, plan, got["_counts"]))
+                n_reads += cb.batch.n_reads
+                n_sessions += len(plan.sessions)
+    finally:
+        for h in handles.values():
+            h.close()
+        fasta.close()
+    if any("".join(v) for v in singles.values()):                  # write_single_end_reads opens both files (:603-605)
+        with open(tumor_output_fastq + ".single_end.fastq", "w") as t, open(normal_output_fastq + ".single_end.fastq", "w") as n:
+            t.write("".join(singles["T"]))
+            n.write("".join(singles["N"]))
+    if record_statistics:
+        with open(f"{normal_bam_file}.statistics.txt", "w") as fh:
+            fh.write(statistics_text(stats_parts))
+    logging.info(f"Anonymization complete for samples {tumor_output_fastq} and {normal_output_fastq}")
+    return {"reads": n_reads, "sessions": n_sessions}
+
+
+def run_short_read_tumor_normal_anonymizer(vcf_variants_per_sample: List[str],
+                                           tumor_normal_samples: List[Tuple[str, str]],
+                                           ref_genome_file: str, anonymizer,
+                                           output_filenames: List[Tuple[str, str]], record_statistics: bool,
+                                           cpus: int, enhance_parallelization: bool = False):
+    """Same signature as the reference's (short_read_tumor_normal_anonymizer.py:889-893).  `anonymizer` is a
+    B200GermlineAnonymizer (its engine is used), an engine.Engine, or None (an engine on cuda:0 is created)."""
+    from .engine import Engine
+    engine: Optional[Engine] = None
+    if isinstance(anonymizer, Engine):
+        engine = anonymizer
+    elif anonymizer is not None and hasattr(anonymizer, "_get_engine"):
+        engine = anonymizer._get_engine()
+    if engine is None:
+        engine = Engine(0)
+    fasta = GF.FastaFile(ref_genome_file)
+    order = {name: k for k, name in enumerate(fasta.references)}          # get_ref_idxs (:60-63)
+    fasta.close()
+    results = []
+    for vcf, samples, outputs in zip(vcf_variants_per_sample, tumor_normal_samples, output_filenames):
+        windows = GF.windows_by_contig(GF.read_vcf(vcf), order)
+        results.append(anonymize_genome(windows, samples[DATASET_IDX_TUMORAL], samples[DATASET_IDX_NORMAL], ref_genome_file,
+                                        engine, outputs[DATASET_IDX_TUMORAL], outputs[DATASET_IDX_NORMAL],
+                                        record_statistics, cpus))
+    return results

@@ -83,3 +83,94 @@ def iter_pileups_stub(stub, tumor_reads, normal_reads, contig, start, stop):
         else:
             yield ct, cn
             ct, cn = next(it_t, None), next(it_n, None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Genome files for the N4 tests: a minimal BAM / FASTA / VCF WRITER.  Test infrastructure only - the
+# product reads these formats (csrc/ga_genome_io.cpp), it never writes them.  Written from the SAM/BAM specification
+# (BGZF members of <= 64 KiB with the 'BC' subfield, the 28-byte EOF marker, little-endian alignment records).
+import re as _re
+import struct as _struct
+import zlib as _zlib
+
+_CIGAR_RE = _re.compile(r"(\d+)([MIDNSHP=X])")
+_BAM_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _bgzf_block(data: bytes, level: int = 6) -> bytes:
+    co = _zlib.compressobj(level, _zlib.DEFLATED, -15)
+    cdata = co.compress(data) + co.flush()
+    bsize = len(cdata) + 25
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + _struct.pack("<H", bsize) + cdata +
+            _struct.pack("<II", _zlib.crc32(data) & 0xffffffff, len(data)))
+
+
+def _reg2bin(beg: int, end: int) -> int:
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0
+
+
+def bam_record(r: dict, ref_id: int) -> bytes:
+    ops = [(int(n), "MIDNSHP=X".index(op)) for n, op in _CIGAR_RE.findall(r["cigar"])]
+    span = sum(n for n, op in ops if op in (0, 2, 3, 7, 8))
+    name = r["name"].encode("ascii") + b"\0"
+    seq = r["seq"]
+    codes = ["=ACMGRSVTWYHKDBN".index(c) for c in seq.upper()]
+    if len(codes) & 1:
+        codes.append(0)
+    packed = bytes((codes[k] << 4) | codes[k + 1] for k in range(0, len(codes), 2))
+    qual = bytes(int(q) for q in r["qual"])
+    body = _struct.pack("<iiBBHHHIiii", ref_id, r["pos"], len(name), 60, _reg2bin(r["pos"], r["pos"] + max(span, 1)), len(ops),
+                        r["flag"], len(seq), -1, -1, 0)
+    body += name + b"".join(_struct.pack("<I", (n << 4) | op) for n, op in ops) + packed + qual
+    return _struct.pack("<I", len(body)) + body
+
+
+def write_bam(path, contigs, reads, block_bytes: int = 0xff00, level: int = 6):
+    """contigs: [(name, length)]; reads: dicts with name / flag / pos / cigar / seq / qual and optionally contig
+    (default: the first), written in the order given."""
+    names = [c for c, _ in contigs]
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{c}\tLN:{n}\n" for c, n in contigs)
+    stream = bytearray(b"BAM\1" + _struct.pack("<I", len(text)) + text.encode() + _struct.pack("<I", len(contigs)))
+    for c, n in contigs:
+        stream += _struct.pack("<I", len(c) + 1) + c.encode() + b"\0" + _struct.pack("<I", n)
+    for r in reads:
+        stream += bam_record(r, names.index(r.get("contig", names[0])))
+    with open(path, "wb") as fh:
+        for o in range(0, len(stream), block_bytes):
+            fh.write(_bgzf_block(bytes(stream[o:o + block_bytes]), level))
+        fh.write(_BAM_EOF)
+
+
+def write_fasta(path, contigs, width: int = 60):
+    """contigs: [(name, bases)]"""
+    with open(path, "w") as fh:
+        for name, seq in contigs:
+            fh.write(f">{name} test contig\n")
+            for o in range(0, len(seq), width):
+                fh.write(seq[o:o + width] + "\n")
+
+
+def write_vcf(path, records):
+    """records: [contig, pos, end, length, ref, alt, type] rows (the layout of genome_cases.json's "vcf")."""
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        for c, pos, _end, _len, ref, alt, _t in records:
+            fh.write(f"{c}\t{pos}\t.\t{ref}\t{alt}\t.\tPASS\t.\n")
+
+
+def write_sample_files(tmp, case, vcf, contig_len=None):
+    """Tumor / normal BAM, FASTA and VCF of one genome_cases.json case; returns the four paths."""
+    import os
+    contig = case["contig"]
+    contigs = [(contig, contig_len or len(case["reference"]))]
+    t, n = os.path.join(tmp, "T.bam"), os.path.join(tmp, "N.bam")
+    write_bam(t, contigs, [r for r in case["reads"] if r["dataset"] == 0])
+    write_bam(n, contigs, [r for r in case["reads"] if r["dataset"] == 1])
+    fa, vc = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "somatic.vcf")
+    write_fasta(fa, [(contig, case["reference"])])
+    write_vcf(vc, vcf)
+    return t, n, fa, vc

@@ -1,0 +1,190 @@
+"""N4: BGZF/BAM, FASTA and VCF readers feeding the engine, and the file-level entry point.
+
+CPU: the C++ readers (include/ga_genome_io.h) against files written by the test-side writers of tests/helpers.py -
+the packed batch must equal batch.pack_reads of the same reads array for array, so everything proven for packed
+batches (tests/test_genome_files.py, the golden samples of the reference) carries over to BAM input.
+GPU: run_short_read_tumor_normal_anonymizer file to file = the files the reference's anonymize_genome wrote
+(tests/golden/genome_cases.json), byte for byte."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from genomeanonymizer_b200 import batch as B
+from genomeanonymizer_b200 import genome_files as GF
+from genomeanonymizer_b200 import _lib
+from tests import helpers as H
+
+GOLD = H.load_golden("genome_cases.json")
+GENOME = GOLD["cases"]
+IDS = [e["case"]["name"] for e in GENOME]
+ARRAYS = ["pos", "len_flag", "seq_off16", "cigar_off", "cigar", "seq4", "qual"]
+
+
+def test_library_exports_the_genome_io_abi():
+    L = _lib.lib()
+    for name in GF.IO_EXPORTS:
+        assert hasattr(L, name), name
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "ga_genome_io.h")).read()
+    for name in GF.IO_EXPORTS:
+        assert name + "(" in hdr, name
+
+
+@pytest.mark.parametrize("entry", GENOME, ids=IDS)
+def test_bam_reader_packs_the_same_batch_as_the_array_packer(entry, tmp_path):
+    case = entry["case"]
+    t, n, fa, vc = H.write_sample_files(str(tmp_path), case, entry["vcf"])
+    assert gzip.open(t).read(4) == b"BAM\1"                          # the test writer makes real gzip members
+    with GF.BamFile(t, 3) as T, GF.BamFile(n, 1) as N:
+        assert T.references == (case["contig"],) and T.lengths == (len(case["reference"]),)
+        assert T.n_records + N.n_records == len(case["reads"])
+        cb = GF.pack_tumor_normal(T, N, case["contig"])
+    ref = B.pack_reads(H.ordered_reads(case))
+    for f in ARRAYS:
+        assert np.array_equal(getattr(cb.batch, f), getattr(ref, f)), f
+    assert cb.batch.n_tumor == ref.n_tumor and cb.batch.max_ref_span == ref.max_ref_span
+    assert cb.batch.seq4.ctypes.data % 16 == 0 and cb.batch.qual.ctypes.data % 16 == 0
+    assert [cb.name(k) for k in range(cb.batch.n_reads)] == ref.names
+    rows = cb.read_table()
+    want = [dict(name=r["name"], flag=r["flag"], dataset=r["dataset"], pos=r["pos"]) for r in H.ordered_reads(case)]
+    assert [{k: r[k] for k in ("name", "flag", "dataset", "pos")} for r in rows] == want
+    spans = [B.ref_span(B.parse_cigar(r["cigar"])) for r in H.ordered_reads(case)]
+    assert [r["end"] - r["pos"] for r in rows] == spans
+    F = GF.FastaFile(fa)
+    assert F.references == (case["contig"],) and F.fetch(case["contig"]) == case["reference"]
+    assert F.fetch(case["contig"], 7, 131) == case["reference"][7:131]
+    assert F.fetch(case["contig"], len(case["reference"]) - 3, len(case["reference"]) + 50) == case["reference"][-3:]
+    assert GF.windows_by_contig(GF.read_vcf(vc), {case["contig"]: 0}).get(case["contig"], []) == case["windows"]
+
+
+def test_windows_of_indel_records_match_the_reference_geometry(tmp_path):
+    kat = GOLD["windows_kat"]
+    vc = str(tmp_path / "k.vcf")
+    H.write_vcf(vc, kat["vcf"])
+    got = GF.windows_by_contig(GF.read_vcf(vc), {c: k for k, c in enumerate(kat["contigs"])})
+    rows = [[c, w["first"], w["last"], w["keep"]["pos"], w["keep"]["end"], w["keep"]["type"], w["keep"]["length"], w["keep"]["allele"]]
+            for c, ws in got.items() for w in ws]
+    assert rows == kat["windows"]
+    gz = str(tmp_path / "k.vcf.gz")
+    with gzip.open(gz, "wt") as fh:
+        fh.write(open(vc).read())
+    assert GF.read_vcf(gz) == GF.read_vcf(vc)
+    H.write_vcf(vc, [["c1", 10, 10, 1, "A", "<DEL>", "DEL"]])
+    with pytest.raises(ValueError):
+        GF.read_vcf(vc)
+
+
+def test_multi_contig_bam_flag_filter_small_blocks_and_sort_check(tmp_path):
+    case = GENOME[1]["case"]
+    reads = [r for r in case["reads"] if r["dataset"] == 0]
+    two = [dict(r, contig="a") for r in reads[:200]] + [dict(r, contig="b") for r in reads[200:300]]
+    two[5] = dict(two[5], flag=two[5]["flag"] | 0x400)
+    p = str(tmp_path / "two.bam")
+    H.write_bam(p, [("a", 9000), ("b", 9000), ("empty", 10)], two, block_bytes=777)    # records straddle BGZF blocks
+    with GF.BamFile(p) as f:
+        assert f.references == ("a", "b", "empty")
+        assert [int(f.contig_sizes(c).n_reads) for c in f.references] == [200, 100, 0]
+        assert int(f.contig_sizes("a", 0x400).n_reads) == 199
+        cb = GF.pack_tumor_normal(f, f, "b")
+        ref = B.pack_reads([dict(r, dataset=0) for r in reads[200:300]] + [dict(r, dataset=1) for r in reads[200:300]])
+        for k in ARRAYS:
+            assert np.array_equal(getattr(cb.batch, k), getattr(ref, k)), k
+        cb = GF.pack_tumor_normal(f, f, "a", flag_exclude=0x400)
+        assert cb.batch.n_reads == 398 and cb.batch.n_tumor == 199
+        assert GF.pack_tumor_normal(f, f, "empty").batch.n_reads == 0
+        assert GF.pack_tumor_normal(f, f, "not-there").batch.n_reads == 0
+    H.write_bam(p, [("a", 9000)], list(reversed(reads[:50])))
+    with GF.BamFile(p) as f:
+        assert not f.contig_sizes("a").sorted
+        with pytest.raises(ValueError):
+            GF.pack_tumor_normal(f, f, "a")
+
+
+def test_corrupt_and_missing_files_fail_loudly(tmp_path):
+    case = GENOME[0]["case"]
+    p = str(tmp_path / "x.bam")
+    H.write_bam(p, [("c", 100)], [r for r in case["reads"] if r["dataset"] == 0][:20])
+    raw = bytearray(open(p, "rb").read())
+    raw[40] ^= 0x55                                                     # inside the first block's deflate stream
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(GF.GenomeFileError):
+        GF.BamFile(p)
+    open(p, "wb").write(b"not a bam file at all, just text")
+    with pytest.raises(GF.GenomeFileError):
+        GF.BamFile(p)
+    with pytest.raises(GF.GenomeFileError):
+        GF.BamFile(str(tmp_path / "missing.bam"))
+    with pytest.raises(GF.GenomeFileError):
+        GF.FastaFile(str(tmp_path / "missing.fa"))
+    fa = str(tmp_path / "two.fa")
+    open(fa, "w").write(">s1 first\r\nACGT\r\nac\r\n>s2\nNNNN\n\nGG")
+    F = GF.FastaFile(fa)
+    assert F.references == ("s1", "s2") and F.lengths == (6, 6)
+    assert F.fetch("s1") == "ACGTac" and F.fetch("s2", 3) == "NGG"
+    with pytest.raises(KeyError):
+        F.fetch("s3")
+
+
+# --------------------------------------------------------------------------------------------------------- GPU
+def _run_files(tmp, entry, eng):
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import name_output, run_short_read_tumor_normal_anonymizer
+    case = entry["case"]
+    t, n, fa, vc = H.write_sample_files(tmp, case, entry["vcf"])
+    outs = (name_output(t), name_output(n))
+    assert outs[0].endswith("T.anonymized")
+    run_short_read_tumor_normal_anonymizer([vc], [(t, n)], fa, eng, [outs], True, 2, False)
+    return t, n, outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("entry", GENOME, ids=IDS)
+def test_entry_point_writes_the_reference_files_from_bam_input(entry, tmp_path):
+    from genomeanonymizer_b200.engine import Engine
+    eng = Engine(0)
+    try:
+        t, n, outs = _run_files(str(tmp_path), entry, eng)
+    finally:
+        eng.close()
+    gold = entry["expected"]["files"]
+    for name, text in gold.items():
+        path = os.path.join(str(tmp_path), name)
+        if text is None:
+            assert not os.path.exists(path), name                      # the reference writes no single-end files then
+        else:
+            assert open(path).read() == text, (entry["case"]["name"], name)
+
+
+@pytest.mark.gpu
+def test_entry_point_with_the_method_object_two_contigs_and_two_samples(tmp_path):
+    """Sample 0: contig c = golden case 0, contig d = golden case 1 (one BAM pair, one VCF, one FASTA): every file is
+    the concatenation of the two golden samples' files, contig by contig.  Sample 1: case 0 alone against the same
+    two-contig FASTA."""
+    from genomeanonymizer_b200.anonymizer_methods import B200GermlineAnonymizer
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import run_short_read_tumor_normal_anonymizer
+    c0, c1 = GENOME[0]["case"], GENOME[1]["case"]
+    contigs = [("c", len(c0["reference"])), ("d", len(c1["reference"]))]
+    fa = str(tmp_path / "ref.fa")
+    H.write_fasta(fa, [("c", c0["reference"]), ("d", c1["reference"])], width=70)
+    reads = [dict(r, contig="c") for r in c0["reads"]] + [dict(r, contig="d") for r in c1["reads"]]
+    t, n = str(tmp_path / "T.bam"), str(tmp_path / "N.bam")
+    H.write_bam(t, contigs, [r for r in reads if r["dataset"] == 0])
+    H.write_bam(n, contigs, [r for r in reads if r["dataset"] == 1])
+    vc = str(tmp_path / "s.vcf")
+    H.write_vcf(vc, GENOME[0]["vcf"] + [["d"] + v[1:] for v in GENOME[1]["vcf"]])
+    d1 = tmp_path / "one"
+    d1.mkdir()
+    t1, n1, _, vc1 = H.write_sample_files(str(d1), c0, GENOME[0]["vcf"])
+    res = run_short_read_tumor_normal_anonymizer([vc, vc1], [(t, n), (t1, n1)], fa, B200GermlineAnonymizer(),
+                                                 [(str(tmp_path / "T.out"), str(tmp_path / "N.out")), (str(d1 / "T.out"), str(d1 / "N.out"))],
+                                                 True, 1, False)
+    assert [r["reads"] for r in res] == [len(reads), len(c0["reads"])]
+    g0, g1 = GENOME[0]["expected"]["files"], GENOME[1]["expected"]["files"]
+    for p in "TN":
+        for m in "12":
+            assert open(str(tmp_path / f"{p}.out.{m}.fastq")).read() == g0[f"{p}.anonymized.{m}.fastq"] + g1[f"{p}.anonymized.{m}.fastq"]
+            assert open(str(d1 / f"{p}.out.{m}.fastq")).read() == g0[f"{p}.anonymized.{m}.fastq"]
+    assert open(n1 + ".statistics.txt").read() == g0["N.bam.statistics.txt"]
+    rows = lambda text: [ln for ln in text.split("\n") if ln and ln[0] != "#" and not ln.startswith("outside")]
+    stats = open(n + ".statistics.txt").read()
+    assert rows(stats) == rows(g0["N.bam.statistics.txt"]) + [ln.replace("c\t", "d\t", 1) for ln in rows(g1["N.bam.statistics.txt"])]
