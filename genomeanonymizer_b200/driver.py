@@ -279,6 +279,7 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     """Same for an already packed batch (batch.ReadBatch with dense qualities, e.g. from
     genome_files.pack_tumor_normal): names = list of str or (uint8 blob, int64 offsets); read_table = rows with name /
     flag / dataset / pos / end for the planner; reference = str / bytes / uint8 array of the contig."""
+    import numpy as np
     import torch
     from . import batch as B
     from .engine import DeviceBatch, DeviceResult, DeviceSessions
