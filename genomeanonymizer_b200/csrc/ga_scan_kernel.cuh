@@ -67,22 +67,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-struct TileMeta { int pos; uint32_t lf, so, c0, c1; };
-struct TileStage { uint32_t staged, sof; };    // warp-uniform: records sit in the ring, first record unit
+// Per-lane meta words of one read of a tile, packed to keep three tiles' worth in registers without spilling:
+// lc = query length | CIGAR op count << 16 (BAM holds at most 65535 ops per record).
+struct TileMeta { int pos; uint32_t lc, so, c0; };
+__device__ __forceinline__ uint32_t meta_len(const TileMeta& m) { return m.lc & 0xffffu; }
+__device__ __forceinline__ uint32_t meta_ops(const TileMeta& m) { return m.lc >> 16; }
 
 // Everything a warp knows about the item it is working on.
 struct ItemCtx {
     BatchView B;
     WarpSmem* ws;
     ga_totals* totals;
-    int64_t begin;          // first read of the item
+    int begin;              // first read of the item (read indices fit 31 bits: ga_result.mod_read is int32)
     int n;                  // reads of the item
     int i_base;             // session-relative id of read `begin`
     int col_begin, n_cols, first;
     int relbase;            // (col_begin + 8) & ~7: reference nibble index of sref word 0
     bool table_in_ref;      // col_begin >= 0 and col_begin + n_cols <= ref_len
     uint32_t ds;
-    uint32_t* ent; ObsRec* obs;
+    uint32_t item;          // ent / obs regions of the item are derived from it where they are written (rare)
+    ScanScratch X;
     uint32_t n_ent, n_obs, n_reads, n_bases;   // n_ent / n_obs warp-uniform, n_reads / n_bases per lane (summed at the end)
     uint32_t n_qord;                           // reads with an I or D op seen so far in the item (= their order in ga_reads.qual_reads)
 };
@@ -98,7 +102,7 @@ __device__ __forceinline__ void flush_entries(ItemCtx& c, int lane) {
     __syncwarp();
     const uint32_t n = min(c.ws->wcnt, (uint32_t)kWbuf);
     if (c.n_ent + n > (uint32_t)kEntHalf) c.ws->ovf = 1u;
-    else for (uint32_t k = lane; k < n; k += 32) c.ent[c.n_ent + k] = c.ws->wbuf[k];
+    else { uint32_t* ent = c.X.ent + (size_t)c.item * kEntHalf + c.n_ent; for (uint32_t k = lane; k < n; k += 32) ent[k] = c.ws->wbuf[k]; }
     c.n_ent += n;
     __syncwarp();
     if (lane == 0) c.ws->wcnt = 0u;
@@ -176,7 +180,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                     const uint32_t code = (rec[(irp + j) >> 3] >> (((irp + j) & 7) * 4)) & 15u;
                     if (j < 8) s0 |= code << (4 * j); else s1 |= code << (4 * (j - 8));
                 }
-                uint4* dst = reinterpret_cast<uint4*>(c.obs + n_obs);
+                uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.item * kObsHalf + n_obs);
                 dst[0] = make_uint4((uint32_t)(rc - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
                 dst[1] = make_uint4(s0, s1, qord, 0u);
                 ++n_obs;
@@ -190,42 +194,42 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
 }
 
 __device__ __forceinline__ TileMeta load_tile_meta(const ItemCtx& c, int t, int TR, int lane) {
-    TileMeta m = {0, 0u, 0u, 0u, 0u};
+    TileMeta m = {0, 0u, 0u, 0u};
     const int i = t * TR + lane;
     if (lane < TR && i < c.n) {
-        const int64_t r = c.begin + i;
-        m.pos = __ldg(c.B.pos + r); m.lf = __ldg(c.B.len_flag + r); m.so = __ldg(c.B.seq_off16 + r);
-        m.c0 = __ldg(c.B.cigar_off + r); m.c1 = __ldg(c.B.cigar_off + r + 1);
+        const int64_t r = (int64_t)c.begin + i;
+        m.pos = __ldg(c.B.pos + r); m.so = __ldg(c.B.seq_off16 + r);
+        m.c0 = __ldg(c.B.cigar_off + r);
+        m.lc = (__ldg(c.B.len_flag + r) & 0xffffu) | ((__ldg(c.B.cigar_off + r + 1) - m.c0) << 16);
     }
     return m;
 }
 
 // Starts the TMA copy of the tile's record bytes into ring stage `b` when the records are contiguous and fit.
-__device__ __forceinline__ TileStage issue_tile(const ItemCtx& c, const TileMeta& m, bool valid, int b, bool tma_ok, int lane) {
-    const uint32_t L = m.lf & 0xffffu;
+__device__ __forceinline__ uint32_t issue_tile(const ItemCtx& c, const TileMeta& m, bool valid, int b, bool tma_ok, int lane) {
+    const uint32_t L = meta_len(m);
     const uint32_t units = valid ? (L + 31u) >> 5 : 0u;
     const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);
     const bool ok = !valid || (m.so >= sof && m.so - sof + units <= (uint32_t)kTileUnits);
     const uint32_t end = valid ? m.so - sof + units : 0u;
     const uint32_t total = __reduce_max_sync(0xffffffffu, ok ? end : 0u);
-    TileStage st;
-    st.sof = sof;
-    st.staged = (tma_ok && total > 0u && __all_sync(0xffffffffu, ok)) ? 1u : 0u;
-    if (st.staged && lane == 0) {
+    const uint32_t staged = (tma_ok && total > 0u && __all_sync(0xffffffffu, ok)) ? 1u : 0u;
+    if (staged && lane == 0) {
         mbar_expect_tx(&c.ws->bar[b], total * 16u);
         bulk_g2s(c.ws->ring[b], c.B.seq4 + 16ull * sof, total * 16u, &c.ws->bar[b]);
     }
-    return st;
+    return staged;
 }
 
 // Compare + discover one tile (lane = read).
-__device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, const TileStage& st, int b, int lane) {
+__device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, bool staged, int b, int lane) {
+    const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);                // first record unit of the tile (what issue_tile copied from)
     const int idx = t * TR + lane;
     const bool valid = lane < TR && idx < c.n;
     const int i = c.i_base + idx;
     const int pos = m.pos;
-    const int L = (int)(m.lf & 0xffffu);
-    const bool one_op = valid && (m.c1 - m.c0 == 1u);
+    const int L = (int)meta_len(m);
+    const bool one_op = valid && meta_ops(m) == 1u;
     // a single-op read whose span L stays inside the reference and the session table
     // (when the whole table lies inside the reference - checked once per item - two compares say the same)
     const bool spec = one_op && L <= 256 &&
@@ -234,7 +238,7 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
     const uint32_t op0 = cw0 & 15u;
     const bool clean = spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(cw0 >> 4) == L);
     const bool in_sess = clean && pos + L > c.first;                     // fetched by range but not reaching the region: skipped
-    const uint32_t* rec = st.staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (m.so - st.sof))
+    const uint32_t* rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (m.so - sof))
                                     : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * m.so);
     if (in_sess) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
     const int rel = pos + 8 - c.relbase;                                 // nibble offset of base `pos` inside the staged window
@@ -295,11 +299,11 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
     while (gm) {
         const int src = __ffs(gm) - 1; gm &= gm - 1;
         const int g_pos = __shfl_sync(0xffffffffu, pos, src), g_L = __shfl_sync(0xffffffffu, L, src);
-        const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = __shfl_sync(0xffffffffu, m.c1, src);
+        const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = g_c0 + (__shfl_sync(0xffffffffu, m.lc, src) >> 16);
         const uint32_t g_so = __shfl_sync(0xffffffffu, m.so, src);
-        const uint32_t* g_rec = st.staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - st.sof))
+        const uint32_t* g_rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - sof))
                                           : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * g_so);
-        scan_generic_read(c, c.i_base + t * TR + src, c.begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, lane);
+        scan_generic_read(c, c.i_base + t * TR + src, (int64_t)c.begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, lane);
     }
 }
 
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
     const uint32_t n_items = 2u * (uint32_t)S.n_sessions;
 
     ItemCtx c;
-    c.B = B; c.ws = ws; c.totals = totals;
+    c.B = B; c.ws = ws; c.totals = totals; c.X = X;
     uint32_t item = lane == 0 ? atomicAdd(ticket, 1u) : 0u;
     item = __shfl_sync(0xffffffffu, item, 0);
     while (item < n_items) {
@@ -339,8 +343,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
         c.i_base = c.ds ? t_end - t_begin : 0;
         c.relbase = (c.col_begin + 8) & ~7;
         c.table_in_ref = c.col_begin >= 0 && (int64_t)c.col_begin + c.n_cols <= B.ref_len;
-        c.ent = X.ent + (size_t)item * kEntHalf;
-        c.obs = X.obs + (size_t)item * kObsHalf;
+        c.item = item;
         c.n_ent = 0u; c.n_obs = 0u; c.n_reads = 0u; c.n_bases = 0u; c.n_qord = 0u;
         if (!big && c.n > 0) {
             // ---- the session's reference window (+ record padding, + funnel-shift lookahead)
@@ -356,22 +359,22 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
             TileMeta mA = load_tile_meta(c, 0, TR, lane);
             TileMeta mB = load_tile_meta(c, 1, TR, lane);
             __syncwarp();                                                 // the previous item's ring reads are done
-            TileStage stA = issue_tile(c, mA, lane < TR && lane < c.n, 0, tma_ok, lane);
-            uint32_t cwA = (mA.c1 > mA.c0) ? __ldg(B.cigar + mA.c0) : 0u;
-            TileStage stB = {0u, 0u};
+            uint32_t stA = issue_tile(c, mA, lane < TR && lane < c.n, 0, tma_ok, lane);
+            uint32_t cwA = meta_ops(mA) ? __ldg(B.cigar + mA.c0) : 0u;
+            uint32_t stB = 0u;
             if (n_tiles > 1) stB = issue_tile(c, mB, lane < TR && TR + lane < c.n, 1, tma_ok, lane);
             for (int t = 0; t < n_tiles; ++t) {
                 const int b = t & 1;
                 uint32_t cwB = 0u;
-                if (mB.c1 > mB.c0) {
+                if (meta_ops(mB)) {
                     cwB = __ldg(B.cigar + mB.c0);
-                    if (mB.c1 - mB.c0 > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
+                    if (meta_ops(mB) > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
                 }
                 TileMeta mC = load_tile_meta(c, t + 2, TR, lane);
-                if (stA.staged) { mbar_wait(&ws->bar[b], (parity >> b) & 1u); parity ^= 1u << b; }
-                scan_tile_w(c, t, TR, mA, cwA, stA, b, lane);
+                if (stA) { mbar_wait(&ws->bar[b], (parity >> b) & 1u); parity ^= 1u << b; }
+                scan_tile_w(c, t, TR, mA, cwA, stA != 0u, b, lane);
                 __syncwarp();                                             // every lane is done with ring stage b
-                TileStage stC = {0u, 0u};
+                uint32_t stC = 0u;
                 if (t + 2 < n_tiles) stC = issue_tile(c, mC, lane < TR && (t + 2) * TR + lane < c.n, b, tma_ok, lane);
                 if (ws->wcnt >= 32u) flush_entries(c, lane);
                 mA = mB; cwA = cwB; stA = stB;
