@@ -236,10 +236,11 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
                       (c.table_in_ref ? (uint32_t)(pos - c.col_begin) < (uint32_t)(c.n_cols - L) && L < c.n_cols
                                       : pos >= 0 && (int64_t)pos + L <= c.B.ref_len && pos >= c.col_begin && pos + L - c.col_begin < c.n_cols);
     const uint32_t op0 = cw0 & 15u;
-    const bool clean = spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(cw0 >> 4) == L);
+    // lane = read works on records staged in the ring only (shared-memory loads); a tile that could not be staged
+    // (records not contiguous, or longer than the ring) goes read by read through the whole-warp walk below
+    const bool clean = staged && spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(cw0 >> 4) == L);
     const bool in_sess = clean && pos + L > c.first;                     // fetched by range but not reaching the region: skipped
-    const uint32_t* rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (m.so - sof))
-                                    : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * m.so);
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (clean ? m.so - sof : 0u));
     if (in_sess) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
     const int rel = pos + 8 - c.relbase;                                 // nibble offset of base `pos` inside the staged window
     // Full 32-base units are compared without any masking; the last, partial unit once, after the loop.
