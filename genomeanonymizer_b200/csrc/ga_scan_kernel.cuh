@@ -2,7 +2,7 @@
 // (north_star jobs (2) + (3a): CIGAR walk and comparison against the reference).
 //
 // Work item = the tumor (or normal) candidate reads of one session, taken by ONE WARP from a ticket counter; no
-// block-level synchronisation anywhere.  The warp walks the item in tiles of up to 32 reads whose records are
+// block-level synchronisation anywhere.  The warp walks the item in tiles of up to 31 reads whose records are
 // contiguous in seq4: the tile's record bytes are fetched by one TMA bulk copy (cp.async.bulk + mbarrier) into
 // the warp's private two-stage shared-memory ring while the previous tile is being compared, the per-read
 // meta words (pos, length, record offset, CIGAR offsets) are prefetched two tiles ahead into registers, and the
@@ -25,8 +25,8 @@ namespace ga {
 
 constexpr int kEntHalf = 768;            // SNV candidate entries per item (tumor or normal half of a session)
 constexpr int kObsHalf = 192;            // indel observations per item
-constexpr int kTileUnits = 160;          // 16-byte units staged per tile (32 reads of 150 bp)
-constexpr int kWbuf = 144;                // entries buffered per warp between flushes
+constexpr int kTileUnits = 156;          // 16-byte units staged per tile (31 reads of 150 bp and room to spare)
+constexpr int kWbuf = 168;                // entries buffered per warp between flushes
 constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean single-op read
 constexpr uint32_t kCntOverflow = 0xffffffffu;
 constexpr int kScanThreads = 256;
@@ -45,7 +45,17 @@ struct WarpSmem {
     uint32_t sref[kCols2 / 8 + 8];       // 4-bit reference of the session's columns (word 0 = ref4 word of column col_begin)
     uint32_t wbuf[kWbuf];                // entries waiting for the next coalesced flush
     uint64_t bar[2];                     // mbarriers of the two ring stages
-    uint32_t wcnt, ovf, pad[2];
+    uint32_t wcnt, ovf;
+    uint32_t n_ent, n_obs, n_qord;       // the item's running counts (lane 0 writes them; rare paths only, so not in registers)
+    // warp-uniform facts about the item, read where they are used (one LDS each) instead of living in registers:
+    // the tile pipeline keeps three tiles of per-read meta words in flight and needs the registers
+    int begin;                           // first read of the item (read indices fit 31 bits: ga_result.mod_read is int32)
+    int n;                               // reads of the item
+    int i_base;                          // session-relative id of read `begin`
+    int first;                           // region start of the session
+    int relbase;                         // (col_begin + 8) & ~7: reference nibble index of sref word 0
+    uint32_t item;                       // 2 * session + dataset; the ent / obs regions are derived from it
+    uint32_t pad;
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp slices stay 16-byte aligned");
 
@@ -67,28 +77,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Per-lane meta words of one read of a tile, packed to keep three tiles' worth in registers without spilling:
-// lc = query length | CIGAR op count << 16 (BAM holds at most 65535 ops per record).
-struct TileMeta { int pos; uint32_t lc, so, c0; };
-__device__ __forceinline__ uint32_t meta_len(const TileMeta& m) { return m.lc & 0xffffu; }
-__device__ __forceinline__ uint32_t meta_ops(const TileMeta& m) { return m.lc >> 16; }
+// Per-lane meta words of one read of a tile: four registers, three tiles' worth live at a time without spilling,
+// and nothing computed from them at load time (the loads stay in flight for two tiles).  A tile has at most 31
+// reads: the lane behind the last read loads the CIGAR offset that closes the last read's op range, so a read's op
+// count is the neighbour lane's c0 minus its own.
+struct TileMeta { int pos; uint32_t lf, so, c0; };
+__device__ __forceinline__ uint32_t meta_len(const TileMeta& m) { return m.lf & 0xffffu; }
+__device__ __forceinline__ uint32_t meta_ops(const TileMeta& m) { return __shfl_down_sync(0xffffffffu, m.c0, 1) - m.c0; }   // lanes holding a read
 
 // Everything a warp knows about the item it is working on.
 struct ItemCtx {
     BatchView B;
     WarpSmem* ws;
     ga_totals* totals;
-    int begin;              // first read of the item (read indices fit 31 bits: ga_result.mod_read is int32)
-    int n;                  // reads of the item
-    int i_base;             // session-relative id of read `begin`
-    int col_begin, n_cols, first;
-    int relbase;            // (col_begin + 8) & ~7: reference nibble index of sref word 0
+    int col_begin, n_cols;
     bool table_in_ref;      // col_begin >= 0 and col_begin + n_cols <= ref_len
-    uint32_t ds;
-    uint32_t item;          // ent / obs regions of the item are derived from it where they are written (rare)
     ScanScratch X;
-    uint32_t n_ent, n_obs, n_reads, n_bases;   // n_ent / n_obs warp-uniform, n_reads / n_bases per lane (summed at the end)
-    uint32_t n_qord;                           // reads with an I or D op seen so far in the item (= their order in ga_reads.qual_reads)
+    uint32_t n_reads, n_bases;                 // per lane (summed at the end)
 };
 
 __device__ __forceinline__ void push_entry_w(const ItemCtx& c, int i, int col, uint32_t b, uint32_t rf, uint32_t gen) {
@@ -100,12 +105,11 @@ __device__ __forceinline__ void push_entry_w(const ItemCtx& c, int i, int col, u
 // Coalesced flush of the buffered entries into the item's region.
 __device__ __forceinline__ void flush_entries(ItemCtx& c, int lane) {
     __syncwarp();
-    const uint32_t n = min(c.ws->wcnt, (uint32_t)kWbuf);
-    if (c.n_ent + n > (uint32_t)kEntHalf) c.ws->ovf = 1u;
-    else { uint32_t* ent = c.X.ent + (size_t)c.item * kEntHalf + c.n_ent; for (uint32_t k = lane; k < n; k += 32) ent[k] = c.ws->wbuf[k]; }
-    c.n_ent += n;
+    const uint32_t n = min(c.ws->wcnt, (uint32_t)kWbuf), n_ent = c.ws->n_ent;
+    if (n_ent + n > (uint32_t)kEntHalf) c.ws->ovf = 1u;
+    else { uint32_t* ent = c.X.ent + (size_t)c.ws->item * kEntHalf + n_ent; for (uint32_t k = lane; k < n; k += 32) ent[k] = c.ws->wbuf[k]; }
     __syncwarp();
-    if (lane == 0) c.ws->wcnt = 0u;
+    if (lane == 0) { c.ws->wcnt = 0u; c.ws->n_ent = n_ent + n; }
     __syncwarp();
 }
 
@@ -122,9 +126,9 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
         if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
         has_id |= (op == 1u || op == 2u);
     }
-    const uint32_t qord = c.n_qord;                                      // counted before any early exit: the quality index lists every such read
-    if (has_id) c.n_qord += 1u;
-    if (pos + span <= c.first) return;                                   // fetched by range, does not reach the region
+    uint32_t qord = 0u;                                                  // counted before any early exit: the quality index lists every such read
+    if (lane == 0) { qord = c.ws->n_qord; if (has_id) c.ws->n_qord = qord + 1u; }
+    if (pos + span <= c.ws->first) return;                                   // fetched by range, does not reach the region
     if (lane == 0) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
     if ((int64_t)pos + span > B.ref_len || pos < 0 || pos < c.col_begin || pos + span - c.col_begin >= c.n_cols) {
         if (lane == 0) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
@@ -161,8 +165,8 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
         }
     }
     // ---- indel observations (lane 0; the count stays warp-uniform through the shuffle below)
-    uint32_t n_obs = c.n_obs;
     if (lane == 0) {
+        uint32_t n_obs = c.ws->n_obs;
         int rc = pos, q = 0, ccl = 0, rcb = 0;
         for (uint32_t ci = c0; ci < c1; ++ci) {
             const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
@@ -172,7 +176,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                 q += ln; rc += ln; ccl += ln;
             } else if (op == 1u || op == 2u) {
                 if (n_obs >= (uint32_t)kObsHalf) { c.ws->ovf = 1u; break; }
-                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | (c.ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
                 const int irp = ccl + rcb;                                // variation_classifier.py:82
                 const int alen = allele_len(meta, irp, L);                // Python-slice clamped (variation_classifier.py:87-88)
                 uint32_t s0 = 0u, s1 = 0u;
@@ -180,7 +184,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                     const uint32_t code = (rec[(irp + j) >> 3] >> (((irp + j) & 7) * 4)) & 15u;
                     if (j < 8) s0 |= code << (4 * j); else s1 |= code << (4 * (j - 8));
                 }
-                uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.item * kObsHalf + n_obs);
+                uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.ws->item * kObsHalf + n_obs);
                 dst[0] = make_uint4((uint32_t)(rc - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
                 dst[1] = make_uint4(s0, s1, qord, 0u);
                 ++n_obs;
@@ -189,19 +193,16 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
             else if (op == 4u) { q += ln; rcb += ln; }
             else if (op == 5u) { rcb += ln; }
         }
+        c.ws->n_obs = n_obs;
     }
-    c.n_obs = __shfl_sync(0xffffffffu, n_obs, 0);
 }
 
 __device__ __forceinline__ TileMeta load_tile_meta(const ItemCtx& c, int t, int TR, int lane) {
     TileMeta m = {0, 0u, 0u, 0u};
     const int i = t * TR + lane;
-    if (lane < TR && i < c.n) {
-        const int64_t r = (int64_t)c.begin + i;
-        m.pos = __ldg(c.B.pos + r); m.so = __ldg(c.B.seq_off16 + r);
-        m.c0 = __ldg(c.B.cigar_off + r);
-        m.lc = (__ldg(c.B.len_flag + r) & 0xffffu) | ((__ldg(c.B.cigar_off + r + 1) - m.c0) << 16);
-    }
+    const int64_t r = (int64_t)c.ws->begin + i;
+    if (lane < TR && i < c.ws->n) { m.pos = __ldg(c.B.pos + r); m.lf = __ldg(c.B.len_flag + r); m.so = __ldg(c.B.seq_off16 + r); }
+    if (lane <= TR && i <= c.ws->n) m.c0 = __ldg(c.B.cigar_off + r);      // one lane more: cigar_off has n_reads + 1 entries
     return m;
 }
 
@@ -225,11 +226,12 @@ __device__ __forceinline__ uint32_t issue_tile(const ItemCtx& c, const TileMeta&
 __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, bool staged, int b, int lane) {
     const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);                // first record unit of the tile (what issue_tile copied from)
     const int idx = t * TR + lane;
-    const bool valid = lane < TR && idx < c.n;
-    const int i = c.i_base + idx;
+    const bool valid = lane < TR && idx < c.ws->n;
+    const int i = c.ws->i_base + idx;
     const int pos = m.pos;
     const int L = (int)meta_len(m);
-    const bool one_op = valid && meta_ops(m) == 1u;
+    const uint32_t n_ops = meta_ops(m);
+    const bool one_op = valid && n_ops == 1u;
     // a single-op read whose span L stays inside the reference and the session table
     // (when the whole table lies inside the reference - checked once per item - two compares say the same)
     const bool spec = one_op && L <= 256 &&
@@ -239,10 +241,10 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
     // lane = read works on records staged in the ring only (shared-memory loads); a tile that could not be staged
     // (records not contiguous, or longer than the ring) goes read by read through the whole-warp walk below
     const bool clean = staged && spec && (op0 == 0u || op0 == 7u || op0 == 8u) && ((int)(cw0 >> 4) == L);
-    const bool in_sess = clean && pos + L > c.first;                     // fetched by range but not reaching the region: skipped
+    const bool in_sess = clean && pos + L > c.ws->first;                     // fetched by range but not reaching the region: skipped
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (clean ? m.so - sof : 0u));
     if (in_sess) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
-    const int rel = pos + 8 - c.relbase;                                 // nibble offset of base `pos` inside the staged window
+    const int rel = pos + 8 - c.ws->relbase;                                 // nibble offset of base `pos` inside the staged window
     // Full 32-base units are compared without any masking; the last, partial unit once, after the loop.
     const int full = in_sess ? L >> 5 : 0;
     const int fmax = __reduce_max_sync(0xffffffffu, full);
@@ -300,11 +302,11 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
     while (gm) {
         const int src = __ffs(gm) - 1; gm &= gm - 1;
         const int g_pos = __shfl_sync(0xffffffffu, pos, src), g_L = __shfl_sync(0xffffffffu, L, src);
-        const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = g_c0 + (__shfl_sync(0xffffffffu, m.lc, src) >> 16);
+        const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = g_c0 + __shfl_sync(0xffffffffu, n_ops, src);
         const uint32_t g_so = __shfl_sync(0xffffffffu, m.so, src);
         const uint32_t* g_rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - sof))
                                           : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * g_so);
-        scan_generic_read(c, c.i_base + t * TR + src, (int64_t)c.begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, lane);
+        scan_generic_read(c, c.ws->i_base + t * TR + src, (int64_t)c.ws->begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, lane);
     }
 }
 
@@ -331,52 +333,55 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
     while (item < n_items) {
         const uint32_t next = lane == 0 ? atomicAdd(ticket, 1u) : 0u;    // next item's ticket travels while this one is processed
         const int s = (int)(item >> 1);
-        c.ds = item & 1u;
+        const uint32_t ds = item & 1u;
         const uint32_t dw = lane < 20 ? __ldg(reinterpret_cast<const uint32_t*>(descs + s) + lane) : 0u;
-        c.first = __ldg(S.first + s);
+        c.ws->first = __ldg(S.first + s);
         const int t_begin = (int)__shfl_sync(0xffffffffu, dw, 0), t_end = (int)__shfl_sync(0xffffffffu, dw, 1);
         const int n_begin = (int)__shfl_sync(0xffffffffu, dw, 2), n_end = (int)__shfl_sync(0xffffffffu, dw, 3);
         c.col_begin = (int)__shfl_sync(0xffffffffu, dw, 4); c.n_cols = (int)__shfl_sync(0xffffffffu, dw, 5);
         const int big = (int)__shfl_sync(0xffffffffu, dw, 7);
-        const uint32_t seq_n = __shfl_sync(0xffffffffu, dw, c.ds ? 15 : 13);
-        c.begin = c.ds ? n_begin : t_begin;
-        c.n = c.ds ? n_end - n_begin : t_end - t_begin;
-        c.i_base = c.ds ? t_end - t_begin : 0;
-        c.relbase = (c.col_begin + 8) & ~7;
+        const uint32_t seq_n = __shfl_sync(0xffffffffu, dw, ds ? 15 : 13);
+        c.ws->begin = ds ? n_begin : t_begin;
+        c.ws->n = ds ? n_end - n_begin : t_end - t_begin;
+        c.ws->i_base = ds ? t_end - t_begin : 0;
+        c.ws->relbase = (c.col_begin + 8) & ~7;
         c.table_in_ref = c.col_begin >= 0 && (int64_t)c.col_begin + c.n_cols <= B.ref_len;
-        c.item = item;
-        c.n_ent = 0u; c.n_obs = 0u; c.n_reads = 0u; c.n_bases = 0u; c.n_qord = 0u;
-        if (!big && c.n > 0) {
+        c.ws->item = item;
+        c.n_reads = 0u; c.n_bases = 0u;
+        if (lane == 0) { ws->n_ent = 0u; ws->n_obs = 0u; ws->n_qord = 0u; }
+        __syncwarp();
+        if (!big && c.ws->n > 0) {
             // ---- the session's reference window (+ record padding, + funnel-shift lookahead)
             {
                 const int64_t w0 = (int64_t)((c.col_begin + 8) >> 3);
                 const int nw = (c.n_cols >> 3) + 8;
                 for (int k = lane; k < nw; k += 32) ws->sref[k] = (w0 + k < ref_words) ? __ldg(B.ref4 + w0 + k) : 0xffffffffu;
             }
-            const uint32_t avg_units = max(1u, (seq_n + (uint32_t)c.n - 1u) / (uint32_t)c.n);
-            const int TR = (int)max(1u, min(32u, (uint32_t)kTileUnits / avg_units));     // reads per tile
-            const int n_tiles = (c.n + TR - 1) / TR;
+            const uint32_t avg_units = max(1u, (seq_n + (uint32_t)c.ws->n - 1u) / (uint32_t)c.ws->n);
+            const int TR = (int)max(1u, min(31u, (uint32_t)kTileUnits / avg_units));     // reads per tile (31: see TileMeta)
+            const int n_tiles = (c.ws->n + TR - 1) / TR;
             // ---- software pipeline: meta two tiles ahead, record bytes (TMA) one tile ahead
             TileMeta mA = load_tile_meta(c, 0, TR, lane);
             TileMeta mB = load_tile_meta(c, 1, TR, lane);
             __syncwarp();                                                 // the previous item's ring reads are done
-            uint32_t stA = issue_tile(c, mA, lane < TR && lane < c.n, 0, tma_ok, lane);
-            uint32_t cwA = meta_ops(mA) ? __ldg(B.cigar + mA.c0) : 0u;
+            uint32_t stA = issue_tile(c, mA, lane < TR && lane < c.ws->n, 0, tma_ok, lane);
+            uint32_t cwA = (meta_ops(mA) && lane < TR && lane < c.ws->n) ? __ldg(B.cigar + mA.c0) : 0u;
             uint32_t stB = 0u;
-            if (n_tiles > 1) stB = issue_tile(c, mB, lane < TR && TR + lane < c.n, 1, tma_ok, lane);
+            if (n_tiles > 1) stB = issue_tile(c, mB, lane < TR && TR + lane < c.ws->n, 1, tma_ok, lane);
             for (int t = 0; t < n_tiles; ++t) {
                 const int b = t & 1;
                 uint32_t cwB = 0u;
-                if (meta_ops(mB)) {
+                const uint32_t opsB = meta_ops(mB);
+                if (opsB && lane < TR && (t + 1) * TR + lane < c.ws->n) {
                     cwB = __ldg(B.cigar + mB.c0);
-                    if (meta_ops(mB) > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
+                    if (opsB > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
                 }
                 TileMeta mC = load_tile_meta(c, t + 2, TR, lane);
                 if (stA) { mbar_wait(&ws->bar[b], (parity >> b) & 1u); parity ^= 1u << b; }
                 scan_tile_w(c, t, TR, mA, cwA, stA != 0u, b, lane);
                 __syncwarp();                                             // every lane is done with ring stage b
                 uint32_t stC = 0u;
-                if (t + 2 < n_tiles) stC = issue_tile(c, mC, lane < TR && (t + 2) * TR + lane < c.n, b, tma_ok, lane);
+                if (t + 2 < n_tiles) stC = issue_tile(c, mC, lane < TR && (t + 2) * TR + lane < c.ws->n, b, tma_ok, lane);
                 if (ws->wcnt >= 32u) flush_entries(c, lane);
                 mA = mB; cwA = cwB; stA = stB;
                 mB = mC; stB = stC;
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
             const uint32_t nr = warp_sum(c.n_reads), nb = warp_sum(c.n_bases);
             __syncwarp();
             if (lane == 0) {
-                X.cnt[item] = make_uint4(ws->ovf ? kCntOverflow : c.n_ent, c.n_obs, nr, nb);
+                X.cnt[item] = make_uint4(ws->ovf ? kCntOverflow : ws->n_ent, ws->n_obs, nr, nb);
                 ws->ovf = 0u;
             }
             __syncwarp();
