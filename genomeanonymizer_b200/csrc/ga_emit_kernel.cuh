@@ -298,4 +298,32 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
             }
         }
     }
+// Records of kind 5: indel-masked reads with more than two germline indels (rare; the one-CTA resolve kernel lists
+// them and stores their edit lists in E.many).  One warp per record, general element-wise emission.
+__global__ void __launch_bounds__(kThreads) emit_many_kernel(BatchView B, ResultView O, EmitScratch2 E) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_x = min(*E.n_many_recs, E.cap_many);
+    const uint32_t warps_total = gridDim.x * (kThreads / 32);
+    for (uint32_t j = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); j < n_x; j += warps_total) {   // warp-uniform
+        const uint4* dp = E.sdesc + 4ull * E.many_recs[j];
+        const uint4 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
+        const int s = (int)d0.w;
+        const int64_t r = (int64_t)d1.x;
+        const uint64_t qual16 = d1.w;
+        GermList germ; germ.e = E.germ + (size_t)s * kGermStride + 4; germ.n = __ldg(E.germ + (size_t)s * kGermStride);
+        const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);   // write_many_aux
+        const uint4 x0 = ap[0], x1 = ap[1];
+        const uint8_t* qrec = nullptr;
+        if (B.qual && !B.qual_reads) qrec = B.qual + 32ull * d0.x;
+        else if (B.qual) {
+            const int64_t qi = (int64_t)x1.w;
+            if (qi < B.n_qual && __ldg(B.qual_reads + qi) == (int32_t)r) qrec = B.qual + 32ull * __ldg(B.qual_off16 + qi);
+            else qrec = qual_record_in(B, r, (int64_t)d3.x, (int64_t)d3.y);
+        }
+        __syncwarp();                                                 // every lane has read the aux before it is overwritten
+        emit_many_group<32>(B, O.totals, O, true, E.many + x0.x, (int)(x1.z & 0xffu), (int)((x1.z >> 8) & 0xffu), r, (int)d0.y, (int)(d0.z & 0xffffu), d0.x,
+                            d2.x, d2.y, ((d0.z >> 20) & 1u) != 0u, (int)d2.z, qrec, (uint64_t)d1.z, qual16, (int)d1.y, lane, germ);
+    }
+}
+
 }  // namespace ga

@@ -113,7 +113,7 @@ __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* ti
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         memset(totals, 0, sizeof(ga_totals));
         *n_big = 0; tickets[0] = 0; tickets[1] = 0; *maxspan = given_span;
-        for (int k = 4; k < 15; ++k) n_big[k] = 0;                    // fallback reasons, n_large, n_special, second fallback ticket
+        for (int k = 4; k < 32; ++k) n_big[k] = 0;                    // fallback reasons, n_large, n_special, second fallback ticket, n_many, n_many_recs
     }
 }
 
@@ -161,7 +161,7 @@ int ga_engine_create(int device, ga_engine** out) {
     e->n_sm = prop.multiProcessorCount;
     if (cudaSetDevice(device) != cudaSuccess) { delete e; return GA_ERR_CUDA; }
     for (int l = 0; l < kLanes; ++l) {
-        if (cudaMalloc(&e->lanes[l].d_small, 64) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
+        if (cudaMalloc(&e->lanes[l].d_small, 128) != cudaSuccess) { ga_engine_destroy(e); return GA_ERR_CUDA; }
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) cudaEventCreate(&e->lanes[l].ev[j][k]);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -201,7 +201,7 @@ void ga_engine_destroy(ga_engine* e) {
         if (L.side) cudaStreamDestroy(L.side);
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_join) cudaEventDestroy(L.ev_join);
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_many); cudaFree(L.d_many_recs); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) if (L.ev[j][k]) cudaEventDestroy(L.ev[j][k]);
     }
     delete e;
@@ -256,6 +256,11 @@ static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int
         GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
         GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
         GA_CUDA(cudaMalloc(&L.d_special, (size_t)cap * 4 * sizeof(uint4)));
+        cudaFree(L.d_many); cudaFree(L.d_many_recs); L.d_many = nullptr; L.d_many_recs = nullptr; L.cap_many = 0;
+        const int64_t cap_many = std::min<int64_t>(std::max<int64_t>(1 << 16, cap / 4), 1 << 26);   // edit lists of reads with more than two germline indels
+        GA_CUDA(cudaMalloc(&L.d_many, (size_t)cap_many * sizeof(uint4)));
+        GA_CUDA(cudaMalloc(&L.d_many_recs, (size_t)cap_many * sizeof(uint32_t)));
+        L.cap_many = cap_many;
         L.cap_kind = cap;
     }
     if (n_sessions > L.cap_germ) {
@@ -378,6 +383,8 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     ga::ScanScratch X; X.ent = L.d_ent; X.obs = reinterpret_cast<ga::ObsRec*>(L.d_obs); X.cnt = reinterpret_cast<uint4*>(L.d_cnt);
     ga::EmitScratch2 E; E.kind = L.d_kind; E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
     E.sdesc = reinterpret_cast<uint4*>(L.d_special); E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
+    E.many = reinterpret_cast<uint4*>(L.d_many); E.n_many = reinterpret_cast<uint32_t*>(L.d_small + 15); E.cap_many = (uint32_t)L.cap_many;
+    E.many_recs = L.d_many_recs; E.n_many_recs = reinterpret_cast<uint32_t*>(L.d_small + 16);
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;
@@ -406,10 +413,11 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     // stage 3: record bodies
     ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
     ga::emit_special_kernel<<<e->n_sm * 4, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
+    ga::emit_many_kernel<<<e->n_sm * 4, ga::kThreads, 0, st>>>(B, O, E);   // reads with more than two germline indels (usually none)
     GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
     GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
-    e->launches += 7;
+    e->launches += 8;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

@@ -11,12 +11,12 @@ struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
 // Scratch of one in-flight ga_run: three lanes let the host pipeline overlap consecutive chunks.
 struct Lane {
     ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int32_t* d_large_list = nullptr; int64_t cap_sessions = 0;
-    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special
+    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special, [14] second fallback ticket, [15] n_many, [16] n_many_recs
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the fallback kernel runs beside the emission kernel
     uint8_t* d_big_scratch = nullptr;
     // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)
     uint32_t* d_ent = nullptr; void* d_obs = nullptr; void* d_cnt = nullptr; int64_t cap_items = 0;
-    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; void* d_special = nullptr; int64_t cap_kind = 0;
+    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; void* d_special = nullptr; void* d_many = nullptr; uint32_t* d_many_recs = nullptr; int64_t cap_many = 0; int64_t cap_kind = 0;
     uint32_t* d_germ = nullptr; int64_t cap_germ = 0;
     // CUDA events between the stages of the most recent kTimedRuns runs (ring), recorded on the launching stream so
     // bench.py can read per-launch durations after its timed region without syncing inside it:

@@ -319,6 +319,115 @@ __device__ void emit_indel_group_t(const BatchView& B, ga_totals* totals, const 
     }
 }
 
+// ------------------------------------------------------------------ more than two edits (rare): the edit list
+// travels through a global side buffer, one uint4 {p_eff, e_eff, length, reference position} per edit in application
+// order, and every output element is mapped back through it.  Code size over speed: these are out-of-line.
+constexpr int kManyEdits = 16;         // germline indels of one read handled by the streaming pipeline (more: fallback kernel)
+
+// The germline indel edits of modified read k (any number up to kManyEdits) in application order with the Python-slice
+// clamping of anonymizer_methods.py:186-195 (same rules as clamp_edits2).  Returns the number of edits (0: too many),
+// writes them to dst when dst is not null.
+template <class SM> __device__ __noinline__ int collect_many(const SessCtx& c, const SM* sm, int k, int L, uint4* dst, int* new_len, int* n_del_out) {
+    int slots[kManyEdits];
+    int ne = 0;
+    for (int o = sm->mhead[k]; o >= 0; o = sm->o_rnext[o]) {
+        if (ne == kManyEdits) return 0;
+        int a = ne++;
+        while (a > 0 && slots[a - 1] > o) { slots[a] = slots[a - 1]; --a; }    // CIGAR order = slot order
+        slots[a] = o;
+    }
+    int cur = L, q = 0, n_del = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass)                                      // all DELs, then all INSs (AM.py:264)
+#pragma unroll 1
+        for (int j = 0; j < ne; ++j) {
+            const uint32_t m = sm->o_meta[slots[j]];
+            if (((m & kMetaIns) != 0u) != (pass == 1)) continue;
+            const int irp = sm->o_irp[slots[j]], len = (int)(m & kMetaLenMask);
+            int p, e;
+            if (pass == 0) { p = irp < cur ? irp : cur; e = p + len; cur += len; ++n_del; }
+            else {
+                p = irp < cur ? irp : cur;
+                const int ee = irp + len < cur ? irp + len : cur;
+                e = ee > p ? ee : p; cur -= e - p;
+            }
+            if (dst) dst[q] = make_uint4((uint32_t)p, (uint32_t)e, (uint32_t)len, (uint32_t)(sm->o_col[slots[j]] + c.d.col_begin));
+            ++q;
+        }
+    *new_len = cur; *n_del_out = n_del;
+    return ne;
+}
+
+// Final index -> original index (>= 0), or -1 - q when DEL edit q inserted the element (*kin = offset in it).
+__device__ __forceinline__ int map_back_many(const uint4* ed, int n_del, int ne, int j, int* kin) {
+#pragma unroll 1
+    for (int q = ne - 1; q >= n_del; --q) { const uint4 e = __ldg(ed + q); if (j >= (int)e.x) j += (int)e.y - (int)e.x; }
+#pragma unroll 1
+    for (int q = n_del - 1; q >= 0; --q) {
+        const uint4 e = __ldg(ed + q);
+        if (j >= (int)e.y) j -= (int)e.z;
+        else if (j >= (int)e.x) { *kin = j - (int)e.x; return -1 - q; }
+    }
+    return j;
+}
+
+// One indel-masked record with more than two edits per group of G lanes (G = 8, 16 or 32); every lane of the warp
+// calls it (act = false for groups without such a record).  Same rules as emit_indel_group_t: SNV masking first
+// (anonymizer_methods.py:170-176), deleted reference bases come back with quality floor(mean(current qualities))
+// (:193), inserted bases and their qualities go (:186-187), qualities are edited in forward orientation and printed
+// in BAM order (:95, 213).
+template <int G, class Germ>
+__device__ __noinline__ void emit_many_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const uint4* ed, int ne, int n_del,
+                                             int64_t r, int pos, int L, uint32_t src_unit, uint32_t c0, uint32_t c1, bool reverse, int col_begin,
+                                             const uint8_t* qrec, uint64_t seq16, uint64_t qual16, int new_len, int glane, Germ germ) {
+    if (act && !qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
+    uint32_t part = 0;
+    if (act) {
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
+        for (int q = glane; q < ((L + 3) >> 2); q += G) {
+            uint32_t v = __ldg(qw + q);
+            if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
+            part += __vsadu4(v, 0u);
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (!act) return;
+    auto mean_of = [&](int q) -> uint32_t {                               // recomputed after each DEL (AM.py:193)
+        uint32_t sum = part, n = (uint32_t)L, m = 0u;
+        for (int t = 0; t <= q; ++t) { m = n ? sum / n : 0u; const uint32_t len = __ldg(ed + t).z; sum += m * len; n += len; }
+        return m;
+    };
+    if (glane == 0)
+        for (int q = 0; q < n_del; ++q) { const uint4 e = __ldg(ed + q); if ((int64_t)(int)e.w + (int)e.z > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r); }
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * src_unit);
+    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+    for (int w = glane; w < units * 4; w += G) {
+        uint32_t v = 0u;
+        for (int n = 0; n < 8 && 8 * w + n < new_len; ++n) {
+            int kin = 0;
+            const int src = map_back_many(ed, n_del, ne, 8 * w + n, &kin);
+            const uint32_t code = src >= 0 ? masked_base_g(B, rec, c0, c1, pos, col_begin, src, germ)
+                                           : ref_code(B.ref4, (int64_t)(int)__ldg(ed + (-1 - src)).w + kin);
+            v |= code << (n * 4);
+        }
+        oseq[w] = v;
+    }
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    for (int w = glane; w < units * 8; w += G) {
+        uint32_t v = 0u;
+        for (int n = 0; n < 4 && 4 * w + n < new_len; ++n) {
+            const int f = reverse ? new_len - 1 - (4 * w + n) : 4 * w + n;
+            int kin = 0;
+            const int src = map_back_many(ed, n_del, ne, f, &kin);
+            const uint32_t qv = src >= 0 ? (uint32_t)qrec[reverse ? L - 1 - src : src] : mean_of(-1 - src);
+            v |= qv << (n * 8);
+        }
+        oq[w] = v;
+    }
+}
+
 // In-kernel form: the germline test is the session's shared-memory table.
 
 }  // namespace ga

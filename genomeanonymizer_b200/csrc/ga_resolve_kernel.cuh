@@ -40,7 +40,34 @@ struct EmitScratch2 {
                          //   {first CIGAR word, one past the last, col_begin, -}   {quality-index slice begin, end, -, -}
                          // kind 0 marks a slot whose session did not fit the caller's capacities
     uint32_t* n_special;
+    uint4* many;         // [cap_many] edit lists of the records with more than two germline indels (collect_many)
+    uint32_t* n_many;
+    uint32_t cap_many;
+    uint32_t* many_recs; // [cap_many] special-record slots of those records (emit_many_kernel walks them)
+    uint32_t* n_many_recs;
 };
+
+// Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked
+// in mpatch[k] (unused by indel-masked reads).  False: more than kManyEdits edits or no room - the fallback kernel
+// takes the session.
+template <class SM> __device__ __noinline__ bool reserve_many(const EmitScratch2& E, const SessCtx& c, SM* sm, int k, int L, int* new_len) {
+    int nd = 0;
+    const int ne = collect_many(c, sm, k, L, (uint4*)nullptr, new_len, &nd);
+    if (!ne) return false;
+    const uint32_t off = atomicAdd(E.n_many, (uint32_t)ne);
+    if (off + (uint32_t)ne > E.cap_many) return false;
+    collect_many(c, sm, k, L, E.many + off, new_len, &nd);
+    sm->mpatch[k] = off;
+    return true;
+}
+
+// The hand-over of such a record (EditAux layout; ne > 2 says that irp0 is the offset of the edit list).
+template <class SM> __device__ __noinline__ void write_many_aux(const SessCtx& c, const SM* sm, int k, int L, uint32_t qidx, uint4* dst) {
+    int nl = 0, nd = 0;
+    const int ne = collect_many(c, sm, k, L, (uint4*)nullptr, &nl, &nd);
+    dst[0] = make_uint4(sm->mpatch[k], 0u, 0u, 0u);
+    dst[1] = make_uint4(0u, 0u, (uint32_t)ne | ((uint32_t)nd << 8), qidx);
+}
 
 __device__ __forceinline__ void write_special(const EmitScratch2& E, const BatchView& B, const SessionDesc& d, uint32_t slot, uint32_t kind,
                                               uint32_t so, int pos, uint32_t lf, int s, int64_t r, uint32_t new_len, uint64_t seq16, uint32_t qual16) {
@@ -317,7 +344,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
                 Ed2 E2;
                 int new_len = L0;
-                if (!collect2(c, sm, k, L0, E2, &new_len)) s_overflow = 1u;   // more than two edits: the fallback kernel takes the session
+                if (!collect2(c, sm, k, L0, E2, &new_len) && !reserve_many(E, c, sm, k, L0, &new_len)) s_overflow = 1u;   // the fallback kernel takes the session
                 m = kModFlag | kQualFlag | ((uint32_t)new_len & kLen2);
                 ++n_q;
             } else {
@@ -381,11 +408,20 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             if (kind == 1) E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
             else {
                 const uint32_t slot = atomicAdd(E.n_special, 1u);
-                if ((int64_t)slot < O.cap_records) write_special(E, B, c.d, slot, kind, __ldg(B.seq_off16 + r), pos, lf, s, r, m & kLen2, s_base[1] + sm->mseq[k], qual16);
+                uint32_t skind = kind;
+                if (kind == 3) {                                      // more than two edits: emit_many_kernel writes the body (kind 5)
+                    const int oa = sm->mhead[k];
+                    const int ob = oa >= 0 ? (int)sm->o_rnext[oa] : -1;
+                    if (ob >= 0 && sm->o_rnext[ob] >= 0) skind = 5;
+                }
+                if ((int64_t)slot < O.cap_records) {
+                    write_special(E, B, c.d, slot, skind, __ldg(B.seq_off16 + r), pos, lf, s, r, m & kLen2, s_base[1] + sm->mseq[k], qual16);
+                    if (skind == 5) { const uint32_t at = atomicAdd(E.n_many_recs, 1u); if (at < E.cap_many) E.many_recs[at] = slot; }
+                }
             }
             if (kind == 3) {                                          // the edits travel in the record's (still unused) quality slot
                 Ed2 E2; int nl = 0;
-                collect2(c, sm, k, (int)(lf & 0xffffu), E2, &nl);
+                const bool two = collect2(c, sm, k, (int)(lf & 0xffffu), E2, &nl);
                 EditAux a;
                 a.irp0 = E2.irp[0]; a.pos0 = E2.pos[0]; a.len0 = (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u);
                 a.irp1 = E2.irp[1]; a.pos1 = E2.pos[1]; a.len1 = (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u);
@@ -398,7 +434,8 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
                 }
                 uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
                 const uint4* src = reinterpret_cast<const uint4*>(&a);
-                dst[0] = src[0]; dst[1] = src[1];
+                if (two) { dst[0] = src[0]; dst[1] = src[1]; }
+                else write_many_aux(c, sm, k, (int)(lf & 0xffffu), a.qidx, dst);
             }
         }
         __syncthreads();                                              // tables and flags are reused by the next session
@@ -701,7 +738,7 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
             uint32_t kind;
             if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
                 Ed2 E2;
-                if (!lean_collect(c, sm, (int)k, L0, E2, &new_len)) slow = true;   // more than two edits: the fallback kernel takes the session
+                if (!lean_collect(c, sm, (int)k, L0, E2, &new_len)) slow = true;   // more than two edits: the one-CTA kernel takes the session
                 kind = 3u; ++n_q;
             } else {
                 kind = ((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2u : (sm->mpc[k] <= 2 ? 1u : 4u);
@@ -711,8 +748,8 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
             tot_seq += units; if (kind == 3u) tot_qual += units;
             sm->rnew[k] = ((uint32_t)new_len & kLen2) | (kind << 24);
         }
-        if (__any_sync(0xffffffffu, slow)) {
-            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 4, 1); }
+        if (__any_sync(0xffffffffu, slow)) {                          // nothing is reserved yet: hand the session over
+            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
         tot_seq = warp_sum(tot_seq); tot_qual = warp_sum(tot_qual); n_q = warp_sum(n_q); n_spec = warp_sum(n_spec);

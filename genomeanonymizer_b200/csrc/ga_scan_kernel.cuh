@@ -179,10 +179,13 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                 const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
                 const int irp = ccl + rcb;                                // variation_classifier.py:82
                 const int alen = allele_len(meta, irp, L);                // Python-slice clamped (variation_classifier.py:87-88)
-                uint32_t s0 = 0u, s1 = 0u;
-                for (int j = 0; j < alen && j < 16; ++j) {
-                    const uint32_t code = (rec[(irp + j) >> 3] >> (((irp + j) & 7) * 4)) & 15u;
-                    if (j < 8) s0 |= code << (4 * j); else s1 |= code << (4 * (j - 8));
+                uint32_t s0 = 0u, s1 = 0u;                                 // signature: the first 16 allele bases
+                if (alen > 0) {
+                    const int w0 = irp >> 3;
+                    const uint32_t sh = (uint32_t)(irp & 7) * 4u;
+                    const uint32_t a0 = rec[w0], a1 = 8 * (w0 + 1) < L ? rec[w0 + 1] : 0u, a2 = 8 * (w0 + 2) < L ? rec[w0 + 2] : 0u;
+                    s0 = __funnelshift_r(a0, a1, sh) & tail_mask(alen, 0);
+                    s1 = __funnelshift_r(a1, a2, sh) & tail_mask(alen, 1);
                 }
                 uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.ws->item * kObsHalf + n_obs);
                 dst[0] = make_uint4((uint32_t)(rc - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);

@@ -187,3 +187,26 @@ def test_engine_read_past_reference_end_is_index_error(engine):
     batch = B.pack_reads(H.ordered_reads(case))
     with pytest.raises(IndexError):
         engine.run(batch, B.pack_sessions(case["windows"]))
+
+
+@pytest.mark.parametrize("kw", [dict(seed=501, contig_len=5000, n_pairs=(30, 30), read_len=250, indel_rate=1.2e-2, max_indel=6),
+                                dict(seed=502, contig_len=5000, n_pairs=(40, 25), read_len=150, indel_rate=2.5e-2, max_indel=3, clip_frac=0.3),
+                                dict(seed=503, contig_len=6000, n_pairs=(25, 40), read_len=300, indel_rate=1.5e-2, max_indel=12, snp_rate=4e-3)],
+                         ids=["many-250", "many-150-clips", "many-300-snps"])
+@pytest.mark.parametrize("sparse_qual", [False, True], ids=["dense-qual", "sparse-qual"])
+def test_reads_with_many_germline_indels_stay_in_the_streaming_pipeline(engine, kw, sparse_qual):
+    """Reads with three and more germline indels (edit lists in the side buffer: collect_many / emit_many_group)
+    against the oracle; none of these sessions may need the fallback kernel for that reason."""
+    from oracle import oracle
+    case = synth.make_case(**kw)
+    batch = B.pack_reads(H.ordered_reads(case), sparse_qual=sparse_qual)
+    sessions = B.pack_sessions(case["windows"])
+    exp, st = oracle.run(batch, sessions, case["reference"])
+    assert st == 0
+    engine.upload_reference(0, case["reference"])
+    got = engine.run(batch, sessions)
+    assert_same_result(got, exp, kw["seed"])
+    n_many = sum(1 for r in H.ordered_reads(case) if sum(c in "ID" for c in r["cigar"]) > 2)
+    assert n_many > 10 and got.totals["masked"][1] + got.totals["masked"][2] > 10, (n_many, got.totals)
+    n, reasons = engine.fallback_sessions()
+    assert reasons[4] == 0, reasons
