@@ -403,9 +403,11 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
     GA_CUDA(cudaEventRecord(L.ev[2][tslot], st));
     // oversize sessions and whatever the tables of stages 1-2 could not hold: global-scratch kernel, complete records;
-    // it runs on a side stream beside stage 3 (it only appends records, which the emission kernel skips)
+    // it runs on a side stream beside stage 3 (it only appends records, which the emission kernel skips), behind the
+    // emission of the few records whose edit lists travel in the side buffer
     GA_CUDA(cudaEventRecord(L.ev_fork, st));
     GA_CUDA(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
+    ga::emit_many_kernel<<<e->n_sm * 4, ga::kThreads, 0, L.side>>>(B, O, E);   // records of reads with more than two germline indels (usually few)
     ga::session_kernel<false><<<e->n_sm * 2, ga::kThreads, sizeof(ga::SmemLayout), L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr,
                                                                                                reinterpret_cast<unsigned int*>(L.d_small + 14));
     ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
@@ -413,7 +415,6 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     // stage 3: record bodies
     ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
     ga::emit_special_kernel<<<e->n_sm * 4, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
-    ga::emit_many_kernel<<<e->n_sm * 4, ga::kThreads, 0, st>>>(B, O, E);   // reads with more than two germline indels (usually none)
     GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
     GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
