@@ -226,7 +226,10 @@ __device__ __forceinline__ uint32_t issue_tile(const ItemCtx& c, const TileMeta&
 }
 
 // Compare + discover one tile (lane = read).
-__device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, bool staged, int b, int lane) {
+// `prefetch` is called once, between the comparison and the mismatch handling: the kernel loads the meta words of
+// the tiles ahead there, away from the first use of this tile's own prefetched words.
+template <class Prefetch>
+__device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, bool staged, int b, int lane, Prefetch&& prefetch) {
     const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);                // first record unit of the tile (what issue_tile copied from)
     const int idx = t * TR + lane;
     const bool valid = lane < TR && idx < c.ws->n;
@@ -285,6 +288,7 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
             wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * u);
         }
     }
+    prefetch();
     // ---- mismatching words: SNV candidates (variation_classifier.py:147-150), resolved from the staged bytes
     while (wm) {
         const int k = __ffs(wm) - 1; wm &= wm - 1;
@@ -374,14 +378,16 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
             for (int t = 0; t < n_tiles; ++t) {
                 const int b = t & 1;
                 uint32_t cwB = 0u;
-                const uint32_t opsB = meta_ops(mB);
-                if (opsB && lane < TR && (t + 1) * TR + lane < c.ws->n) {
-                    cwB = __ldg(B.cigar + mB.c0);
-                    if (opsB > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
-                }
-                TileMeta mC = load_tile_meta(c, t + 2, TR, lane);
+                TileMeta mC = {0, 0u, 0u, 0u};
                 if (stA) { mbar_wait(&ws->bar[b], (parity >> b) & 1u); parity ^= 1u << b; }
-                scan_tile_w(c, t, TR, mA, cwA, stA != 0u, b, lane);
+                scan_tile_w(c, t, TR, mA, cwA, stA != 0u, b, lane, [&]() {
+                    const uint32_t opsB = meta_ops(mB);
+                    if (opsB && lane < TR && (t + 1) * TR + lane < c.ws->n) {
+                        cwB = __ldg(B.cigar + mB.c0);
+                        if (opsB > 1u) prefetch_l1(B.cigar + mB.c0 + 1);
+                    }
+                    mC = load_tile_meta(c, t + 2, TR, lane);
+                });
                 __syncwarp();                                             // every lane is done with ring stage b
                 uint32_t stC = 0u;
                 if (t + 2 < n_tiles) stC = issue_tile(c, mC, lane < TR && (t + 2) * TR + lane < c.ws->n, b, tma_ok, lane);
