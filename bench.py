@@ -420,7 +420,7 @@ def main():
     # DRAM bytes of one pass from the committed ncu --set full capture (profiles/), when it is of this workload
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_stream_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")) as f:
             tj = json.load(f)
         if tj["workload"] == cfg.name and tj["windows"] == n_w:
             traffic, traffic_src = tj["dram_bytes_per_pass"], tj["source"]
@@ -429,7 +429,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "kernel": "masking pass = scan_kernel + resolve_lean_kernel + resolve_kernel + emit_kernel (|| session_kernel<fallback>)", "kernel_ms": pass_ms,
+                "kernel": "masking pass = scan_kernel + resolve_lean_kernel + resolve_kernel + emit_kernel + emit_special_kernel (|| emit_many_kernel, session_kernel<fallback>)", "kernel_ms": pass_ms,
                 "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernels": stage_ms[1], "emit_kernel": stage_ms[2],
                              "fallback_kernel_tail": stage_ms[3]},
                 "scan_kernel_gbs": scan_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else None,
