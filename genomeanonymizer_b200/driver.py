@@ -164,14 +164,37 @@ def plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int)
     """reads: every read of the sample on this contig, each {"name", "flag", "dataset", "pos", "end"} with `end` the
     exclusive reference end, tumor and normal each in file (coordinate) order; windows: [{"first", "last", "keep"}]
     sorted as the reference sorts them."""
+    import gc
+    # The plan allocates a few small containers per read and keeps them alive; the cyclic collector then re-walks the
+    # whole (acyclic) heap again and again - five times the cost of the planning itself.  Off for the duration.
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        return _plan_sample(reads, windows, contig_len)
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
+def _plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int) -> Plan:
     plan = Plan()
     t_all = [i for i, r in enumerate(reads) if r["dataset"] == 0]
     n_all = [i for i, r in enumerate(reads) if r["dataset"] == 1]
     to_pair: Dict[str, list] = {}                                 # name -> [(read, version) or None] * 2
     written = set()
 
-    def overlapping(idx, start, stop):                            # AlignmentFile.fetch / pileup read selection
-        return [i for i in idx if reads[i]["pos"] < stop and reads[i]["end"] > start]
+    # AlignmentFile.fetch / pileup read selection: reads with pos < stop and end > start.  Each dataset is in coordinate
+    # order, so the candidates are a bisected slice of it (pos in [start - longest span, stop)), not the whole list.
+    pos_of = {id(t_all): [reads[i]["pos"] for i in t_all], id(n_all): [reads[i]["pos"] for i in n_all]}
+    span = max((r["end"] - r["pos"] for r in reads), default=0)
+    for idx in (t_all, n_all):
+        if any(a > b for a, b in zip(pos_of[id(idx)], pos_of[id(idx)][1:])):
+            raise ValueError("reads of a dataset must be in coordinate order")
+
+    def overlapping(idx, start, stop):
+        ps = pos_of[id(idx)]
+        lo, hi = bisect.bisect_left(ps, start - span), bisect.bisect_left(ps, stop)
+        return [i for i in idx[lo:hi] if reads[i]["end"] > start]
 
     def write_pair(name, s1, s2, sink=None):                      # write_pair, :134-165
         if name in written:
@@ -293,18 +316,32 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     engine.run_device(db, ds, dres)
     torch.cuda.synchronize(engine.device)
     n = int(engine.check_device_status(dres).n_modified)
-    rec_of = {(int(s), int(r)): k for k, (s, r) in enumerate(zip(dres.mod_session[:n].cpu().numpy(), dres.mod_read[:n].cpu().numpy()))}
-    order = [(r1, v1) for _, r1, v1, _, _ in plan.pairs] + [(r2, v2) for _, _, _, r2, v2 in plan.pairs] + [(r, v) for _, r, v in plan.singles]
-    text, off = engine.render_fastq(db, names, [i for i, _ in order], [rec_of.get((v, i), -1) for i, v in order], dres, n)
-    piece = lambda k: text[off[k]:off[k + 1]].decode("ascii")
-    files = {f"{p}.{s}": [] for p in "TN" for s in ("1", "2", "single_end")}
-    np_ = len(plan.pairs)
-    for k, (d, _, _, _, _) in enumerate(plan.pairs):
-        files[f"{'TN'[d]}.1"].append(piece(k))
-        files[f"{'TN'[d]}.2"].append(piece(np_ + k))
-    for k, (d, _, _) in enumerate(plan.singles):
-        files[f"{'TN'[d]}.single_end"].append(piece(2 * np_ + k))
-    out = {k: "".join(v) for k, v in files.items()}
+    # which modified record (if any) each planned read prints: (session, read) keys, sorted once and searched
+    mod_key = (dres.mod_session[:n].cpu().numpy().astype(np.int64) << 32) | dres.mod_read[:n].cpu().numpy().astype(np.int64)
+    by_key = np.argsort(mod_key, kind="stable")
+    sorted_key = mod_key[by_key]
+    P = np.asarray(plan.pairs, np.int64).reshape(-1, 5)
+    S = np.asarray(plan.singles, np.int64).reshape(-1, 3)
+    # items in file order: T.1, T.2, N.1, N.2, T.single_end, N.single_end - each file is one slice of the rendered text
+    groups = []
+    for d in (0, 1):
+        rows = P[P[:, 0] == d]
+        groups += [(f"{'TN'[d]}.1", rows[:, 1], rows[:, 2]), (f"{'TN'[d]}.2", rows[:, 3], rows[:, 4])]
+    for d in (0, 1):
+        rows = S[S[:, 0] == d]
+        groups.append((f"{'TN'[d]}.single_end", rows[:, 1], rows[:, 2]))
+    item_read = np.concatenate([g[1] for g in groups]) if groups else np.zeros(0, np.int64)
+    item_ver = np.concatenate([g[2] for g in groups]) if groups else np.zeros(0, np.int64)
+    want = (item_ver << 32) | item_read
+    at = np.searchsorted(sorted_key, want)
+    hit = (item_ver >= 0) & (at < n)
+    hit[hit] = sorted_key[at[hit]] == want[hit]
+    item_rec = np.where(hit, by_key[np.minimum(at, max(n - 1, 0))] if n else 0, -1).astype(np.int32)
+    text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n)
+    out, k0 = {}, 0
+    for name, rd, _ in groups:
+        out[name] = text[int(off[k0]):int(off[k0 + len(rd)])].decode("ascii")
+        k0 += len(rd)
     counts = dres.sess_counts.view(-1, 4)[:sessions.n_sessions].cpu().numpy()
     out["statistics"] = statistics_text(contig, plan, counts)
     out["_plan"] = plan

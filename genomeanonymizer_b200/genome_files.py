@@ -162,13 +162,21 @@ class ContigBatch:
 
     def read_table(self) -> List[dict]:
         """(name, flag, dataset, pos, end) rows for driver.plan_sample."""
+        import gc
         b = self.batch
         blob = self.name_blob.tobytes()
-        off = self.name_off
-        flags = (b.len_flag >> 16).astype(np.int64)
+        off = self.name_off.tolist()
+        flags = (b.len_flag >> 16).tolist()
+        pos, end = b.pos.tolist(), self.ref_end.tolist()
         nt = b.n_tumor
-        return [{"name": blob[off[k]:off[k + 1]].decode("ascii"), "flag": int(flags[k]), "dataset": 0 if k < nt else 1,
-                 "pos": int(b.pos[k]), "end": int(self.ref_end[k])} for k in range(b.n_reads)]
+        was_enabled = gc.isenabled()
+        gc.disable()                                               # one dict per read: see driver.plan_sample
+        try:
+            return [{"name": blob[off[k]:off[k + 1]].decode("ascii"), "flag": flags[k], "dataset": 0 if k < nt else 1,
+                     "pos": pos[k], "end": end[k]} for k in range(b.n_reads)]
+        finally:
+            if was_enabled:
+                gc.enable()
 
 
 def _aligned(n_bytes: int, align: int = 64) -> np.ndarray:
