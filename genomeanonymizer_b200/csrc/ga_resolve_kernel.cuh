@@ -733,7 +733,13 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
 #pragma unroll 2
         for (uint32_t k = lane; k < n_mod; k += 32) {
             const int i = (int)sm->clist[k];
-            const int L0 = (int)(__ldg(B.len_flag + read_of(c, i)) & 0xffffu);
+            const int64_t r3 = read_of(c, i);
+            const uint32_t so3 = __ldg(B.seq_off16 + r3);             // travels with the length; only used to ask the record
+            const int L0 = (int)(__ldg(B.len_flag + r3) & 0xffffu);
+            // the header loop below reads pos and the record body of this read: ask them into L2 now
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.pos + r3));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.seq4 + 16ull * so3));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.seq4 + 16ull * so3 + 64));
             int new_len = L0;
             uint32_t kind;
             if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
