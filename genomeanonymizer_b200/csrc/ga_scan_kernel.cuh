@@ -24,7 +24,7 @@
 namespace ga {
 
 constexpr int kEntHalf = 768;            // SNV candidate entries per item (tumor or normal half of a session)
-constexpr int kObsHalf = 192;            // indel observations per item
+constexpr int kObsHalf = 384;            // indel observations per item
 constexpr int kTileUnits = 156;          // 16-byte units staged per tile (31 reads of 150 bp and room to spare)
 constexpr int kWbuf = 168;                // entries buffered per warp between flushes
 constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean single-op read
