@@ -62,15 +62,29 @@ __device__ __forceinline__ int32_t lower_bound_pos(const int32_t* __restrict__ p
 // (replaces the index fetch inside pileup(), pileup_io.pyx:12-17).
 __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* __restrict__ maxspan_p, SessionDesc* __restrict__ descs,
                                        int32_t* __restrict__ big_list, int32_t* __restrict__ n_big) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S.n_sessions) return;
+    // Four lanes per session: the four searches of the read positions run side by side, then the four searches of the
+    // sparse quality index (the chain of dependent loads is the cost of this kernel); lane 0 of the group does the rest.
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s_raw = gid >> 2, q4 = gid & 3, lane = threadIdx.x & 31, g0 = lane & ~3;
+    const bool active = s_raw < S.n_sessions;
+    const int s = active ? s_raw : S.n_sessions - 1;
     const int maxspan = max(1, *maxspan_p);
     const int64_t first = S.first[s], last = S.last[s];
     SessionDesc d;
-    d.t_begin = lower_bound_pos(B.pos, 0, B.n_tumor, first - maxspan + 1);
-    d.t_end = lower_bound_pos(B.pos, 0, B.n_tumor, last);
-    d.n_begin = lower_bound_pos(B.pos, B.n_tumor, B.n_reads, first - maxspan + 1);
-    d.n_end = lower_bound_pos(B.pos, B.n_tumor, B.n_reads, last);
+    {
+        const bool normal = q4 >= 2;
+        const int mine = lower_bound_pos(B.pos, normal ? B.n_tumor : 0, normal ? B.n_reads : B.n_tumor, (q4 & 1) ? last : first - maxspan + 1);
+        d.t_begin = __shfl_sync(0xffffffffu, mine, g0); d.t_end = __shfl_sync(0xffffffffu, mine, g0 + 1);
+        d.n_begin = __shfl_sync(0xffffffffu, mine, g0 + 2); d.n_end = __shfl_sync(0xffffffffu, mine, g0 + 3);
+    }
+    d.qt_begin = d.qt_end = d.qn_begin = d.qn_end = 0;
+    if (B.qual_reads) {                                               // warp-uniform
+        const int target = q4 == 0 ? d.t_begin : q4 == 1 ? d.t_end : q4 == 2 ? d.n_begin : d.n_end;
+        const int mine = lower_bound_pos(B.qual_reads, 0, B.n_qual, target);
+        d.qt_begin = __shfl_sync(0xffffffffu, mine, g0); d.qt_end = __shfl_sync(0xffffffffu, mine, g0 + 1);
+        d.qn_begin = __shfl_sync(0xffffffffu, mine, g0 + 2); d.qn_end = __shfl_sync(0xffffffffu, mine, g0 + 3);
+    }
+    if (!active || q4 != 0) return;
     int64_t lo = last;
     if (d.t_end > d.t_begin) lo = min(lo, (int64_t)B.pos[d.t_begin]);
     if (d.n_end > d.n_begin) lo = min(lo, (int64_t)B.pos[d.n_begin]);
@@ -99,11 +113,6 @@ __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* _
         const uint32_t hi = B.seq_off16[d.n_end - 1] + (L ? (L + 31u) / 32u : 1u);
         d.n_seq_n = hi > d.n_seq_lo ? hi - d.n_seq_lo : 0u;
         d.n_cig_lo = B.cigar_off[d.n_begin]; d.n_cig_n = B.cigar_off[d.n_end] - d.n_cig_lo;
-    }
-    d.qt_begin = d.qt_end = d.qn_begin = d.qn_end = 0;
-    if (B.qual_reads) {
-        d.qt_begin = lower_bound_pos(B.qual_reads, 0, B.n_qual, d.t_begin); d.qt_end = lower_bound_pos(B.qual_reads, d.qt_begin, B.n_qual, d.t_end);
-        d.qn_begin = lower_bound_pos(B.qual_reads, d.qt_end, B.n_qual, d.n_begin); d.qn_end = lower_bound_pos(B.qual_reads, d.qn_begin, B.n_qual, d.n_end);
     }
     descs[s] = d;
     if (d.big) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4, 1); }
@@ -374,7 +383,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
         ga::max_span_kernel<<<e->n_sm * 4, 256, 0, st>>>(R->cigar_off, R->cigar, R->n_reads, d_maxspan);
         e->launches++;
     }
-    ga::assign_sessions_kernel<<<(S->n_sessions + 127) / 128, 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
+    ga::assign_sessions_kernel<<<(int)((4 * (int64_t)S->n_sessions + 127) / 128), 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
     e->launches++;
     ga::BigScratch scr;
     scr.base = L.d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
