@@ -320,6 +320,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the masking path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from genomeanonymizer_b200.sharding import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)                            # host batches local to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -509,6 +511,7 @@ def main():
                            "modified_records_per_gpu": int(tot.n_modified),
                            "fallback_sessions_per_gpu": n_fallback, "fallback_reasons": fallback_reasons, "masked_snv_del_ins": [int(x) for x in tot.masked],
                            "sharding": "one contig-sized region per GPU, no data-path collective" if world > 1 else "single GPU",
+                           "host_numa_binding": numa,
                            "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
                 "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "bam_decode": bam, "gpu_launches": total_launches,

@@ -77,3 +77,31 @@ def merge_shard_results(shards: Sequence[Tuple[MaskResult, int, np.ndarray]]) ->
     out.sess_counts = np.concatenate(counts) if counts else np.zeros((0, 4), np.uint32)
     out.totals = totals
     return out
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pins the calling process (one process per GPU) to the CPUs of the NUMA node its GPU hangs on, so that the
+    pinned host batches it allocates afterwards are local to that GPU's PCIe root (first-touch placement): with
+    several ranks uploading at once the uploads then stop crossing the socket interconnect.  Returns
+    {"node": n, "cpus": count} or None when the topology cannot be read (single-node hosts, containers without /sys)."""
+    import os
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except (OSError, ValueError, AttributeError):
+        return None
