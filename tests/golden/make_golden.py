@@ -189,6 +189,16 @@ def kat_cases():
                             R("n1", R2, 40, "8M", "ACGTACGT", q(8), 1),
                             R("t2", F1, 4, "4M2I2D6M", "ACGTGGGTACGT", q(12), 0), R("n2", F1, 4, "4M2I2D6M", "ACGTGGGTACGT", q(12, 3), 1),
                             R("t2", R2, 44, "8M", "ACGTACGT", q(8), 0), R("n2", R2, 44, "8M", "ACGTACGT", q(8), 1)]})
+    # the same on the reverse strand, plus a forward mate with five indels: edits index the forward-orientation
+    # quality array while the bases stay in alignment order (quirks Q1/Q2 with more than two edits per read)
+    cases.append({"name": "K-multi-indel-rev", "contig": "c", "reference": "ACGT" * 20,
+                  "windows": [{"first": 0, "last": 80, "keep": None}],
+                  "reads": [R("t1", F1, 2, "3M1I3M2D4M1D3M2I3M1D2M", "GTATCGTGTACTACTTGTAGT", [3, 40, 5, 38, 7, 36, 9, 34, 11, 32, 13, 30, 15, 28, 17, 26, 19, 24, 21, 22, 2], 0),
+                            R("t1", R2, 38, "4M2D4M1I4M3D4M", "GTACACGTTACGTCGTA", [40, 2, 30, 4, 25, 6, 20, 8, 15, 10, 12, 33, 14, 3, 16, 37, 18], 0),
+                            R("n1", F1, 2, "3M1I3M2D4M1D3M2I3M1D2M", "GTATCGTGTACTACTTGTAGT", q(21, 4), 1),
+                            R("n1", R2, 38, "4M2D4M1I4M3D4M", "GTACACGTTACGTCGTA", q(17, 7), 1),
+                            R("t2", F1, 60, "8M", "ACGTACGT", q(8), 0), R("n2", F1, 60, "8M", "ACGTACGT", q(8), 1),
+                            R("t2", R2, 66, "8M", "GTACGTAC", q(8), 0), R("n2", R2, 66, "8M", "GTACGTAC", q(8), 1)]})
     # indel keep-variant that matches a discovered indel key exactly
     cases.append({"name": "K-keep-indel", "contig": "c", "reference": ref,
                   "windows": [{"first": 0, "last": 44,
@@ -211,6 +221,8 @@ def random_cases():
     cases.append(synth.make_case(14, contig_len=2400, n_pairs=(220, 200), read_len=40, name="rand-14-short-nokeep",
                                  snp_rate=5e-3, indel_rate=4e-3, keep_somatic=False, max_indel=12, clip_frac=0.4))
     cases.append(synth.make_case(15, contig_len=3000, n_pairs=(120, 0), read_len=50, name="rand-15-no-normal"))
+    cases.append(synth.make_case(16, contig_len=2600, n_pairs=(45, 40), read_len=150, name="rand-16-many-indels",
+                                 snp_rate=3e-3, indel_rate=2e-2, max_indel=4, clip_frac=0.2))
     return cases
 
 
