@@ -7,8 +7,8 @@ The reference opens its inputs through pysam / htslib and variant-extractor, nei
 Here a whole contig of a BAM file is decoded by the C++ reader (all host threads, zlib only) straight into the
 structure-of-arrays batch the engine takes; no per-read object is built.  The VCF reader restates what the path
 needs from variant-extractor ^4.0.6 (not in /root/reference, not installed - unpinned): contig, 1-based pos, end,
-length, REF, ALT and the variant type of plain SNV / DEL / INS / MNV records; symbolic and breakend records are
-rejected loudly rather than guessed.
+length, REF, ALT and the variant type of plain SNV / DEL / INS / MNV records and of symbolic <DEL> <INS> <DUP> <INV>
+<CNV> records (END / SVLEN as the VCF states them); breakend records are rejected loudly rather than guessed.
 """
 import ctypes as C
 import gzip
@@ -287,12 +287,34 @@ class VcfVariant:
     variant_type: str
 
 
-def classify_vcf_alleles(pos: int, ref: str, alt: str) -> Tuple[int, int, str]:
-    """(end, length, type) of a plain REF/ALT pair.  SNV: end = pos, length 1.  DEL: length = len(REF) - len(ALT),
-    end = pos + length.  INS: length = len(ALT) - len(REF), end = pos + 1.  Same-length multi-base records are kept as
-    SNV-typed records of that length (window geometry only; they can never equal a pileup SNV key, variants.py:83-96)."""
-    if alt.startswith("<") or "[" in alt or "]" in alt or alt == "*" or alt == ".":
-        raise ValueError(f"symbolic / breakend ALT allele {alt!r} at position {pos} is not supported by this reader")
+_SYMBOLIC_TYPES = {"DEL": "DEL", "INS": "INS", "DUP": "DUP", "INV": "INV", "CNV": "CNV"}
+
+
+def classify_vcf_alleles(pos: int, ref: str, alt: str, info: Optional[Dict[str, str]] = None) -> Tuple[int, int, str]:
+    """(end, length, type) of one REF/ALT pair.
+    Plain alleles - SNV: end = pos, length 1.  DEL: length = len(REF) - len(ALT), end = pos + length.  INS: length =
+    len(ALT) - len(REF), end = pos + 1.  Same-length multi-base records are kept as SNV-typed records of that length
+    (window geometry only; they can never equal a pileup SNV key, variants.py:83-96).
+    Symbolic alleles <DEL> <INS> <DUP> <INV> <CNV> (with :subtype) - end = INFO END (INS: pos + 1 when absent), length =
+    |INFO SVLEN| or end - pos.  Breakend (BND) and '*' alleles are not supported: variant-extractor pairs breakends into
+    TRA / INV / DEL / DUP records by rules this reader does not restate."""
+    info = info or {}
+    if alt.startswith("<") and alt.endswith(">"):
+        vt = _SYMBOLIC_TYPES.get(alt[1:-1].split(":")[0])
+        if vt is None:
+            raise ValueError(f"symbolic ALT allele {alt!r} at position {pos} is not supported by this reader")
+        svlen = abs(int(info["SVLEN"].split(",")[0])) if "SVLEN" in info else None
+        if "END" in info:
+            end = int(info["END"])
+        elif vt == "INS":
+            end = pos + 1
+        elif svlen is not None:
+            end = pos + svlen
+        else:
+            raise ValueError(f"{alt} record at position {pos} has neither END nor SVLEN")
+        return end, (svlen if svlen is not None else end - pos), vt
+    if "[" in alt or "]" in alt or alt == "*" or alt == "." or alt.startswith("."):
+        raise ValueError(f"breakend / missing ALT allele {alt!r} at position {pos} is not supported by this reader")
     if len(ref) == len(alt):
         return (pos, 1, "SNV") if len(ref) == 1 else (pos + len(ref) - 1, len(ref), "SNV")
     if len(ref) > len(alt):
@@ -315,26 +337,34 @@ def read_vcf(path: str) -> List[VcfVariant]:
             if len(f) < 5:
                 raise ValueError(f"{path}: malformed VCF record: {line!r}")
             pos = int(f[1])
+            info = dict(kv.partition("=")[::2] for kv in f[7].split(";")) if len(f) > 7 and f[7] not in (".", "") else {}
             for alt in f[4].split(","):
-                end, length, vt = classify_vcf_alleles(pos, f[3], alt)
+                end, length, vt = classify_vcf_alleles(pos, f[3], alt, info)
                 out.append(VcfVariant(f[0], pos, end, length, f[3], alt, vt))
     return out
 
 
 def windows_by_contig(variants: List[VcfVariant], contig_order: Dict[str, int]) -> Dict[str, List[dict]]:
-    """get_windows (short_read_tumor_normal_anonymizer.py:71-131) for SNV / DEL / INS records: one window
-    [pos - 1000, end + 1001) around each variant (SNV: [pos - 1000, pos + 1001)), sorted by (contig, first, last), with
-    the 0-based key of the variant to keep (variants.py:59-62)."""
-    from .driver import window_of_variant
-    vt_value = {"SNV": 1, "DEL": 2, "INS": 3}
+    """get_windows (short_read_tumor_normal_anonymizer.py:71-131) without the breakend branches: SNV -> one window
+    [pos - 1000, pos + 1001); INV -> one window around both ends when they are closer than a window, else one around
+    each end; every other type -> [pos - 1000, end + 1001) below 100 kb, else one window around each end.  Sorted by
+    (contig, first, last), each with the 0-based key of the variant to keep (variants.py:59-62)."""
+    from .driver import WINDOW_HALF, window_of_variant
     rows = []
     for v in variants:
         if v.contig not in contig_order:
             raise KeyError(f"VCF contig {v.contig!r} is not in the reference genome")
-        if v.length >= 100_000:
-            raise ValueError("variants of 100 kb and more (two-window records) are not supported by this reader")
-        first, last = window_of_variant(v.pos, v.pos if v.variant_type == "SNV" else v.end)
-        rows.append((contig_order[v.contig], first, last, v))
+        if v.variant_type == "SNV":
+            spans = [window_of_variant(v.pos, v.pos)]
+        elif v.variant_type == "INV":
+            near = v.pos + WINDOW_HALF > v.end - WINDOW_HALF
+            spans = [window_of_variant(v.pos, v.end)] if near else [window_of_variant(v.pos, v.pos), window_of_variant(v.end, v.end)]
+        elif v.length < 100_000:
+            spans = [window_of_variant(v.pos, v.end)]
+        else:
+            spans = [window_of_variant(v.pos, v.pos), window_of_variant(v.end, v.end)]
+        for first, last in spans:
+            rows.append((contig_order[v.contig], first, last, v))
     rows.sort(key=lambda t: t[:3])
     out: Dict[str, List[dict]] = {}
     for _, first, last, v in rows:

@@ -308,6 +308,26 @@ def window_kats():
             "sections": [[s.sequence, s.first, s.last, s.variant is not None] for s in secs]}
 
 
+def sv_window_kats():
+    """Window arithmetic of SR.get_windows for structural records: INV (one or two windows), DUP / CNV / symbolic DEL
+    (one window, or two from 100 kb on).  The records are built by hand (variant-extractor is not installed); what is
+    pinned here is the reference's geometry given pos / end / length / type."""
+    pysam.register_fasta("sv.fa", {"c1": "A" * 600000, "c2": "A" * 5000})
+    fasta = pysam.FastaFile("sv.fa")
+    recs = [VariantRecord("c1", 10000, 15000, 5000, "A", "<DEL>", VariantType.DEL),
+            VariantRecord("c1", 20000, 22000, 2000, "A", "<DUP>", VariantType.DUP),
+            VariantRecord("c1", 40000, 40500, 500, "A", "<INV>", VariantType.INV),
+            VariantRecord("c1", 200000, 260000, 60000, "A", "<INV>", VariantType.INV),
+            VariantRecord("c1", 300000, 450000, 150000, "A", "<DEL>", VariantType.DEL),
+            VariantRecord("c1", 500000, 503000, 3000, "A", "<CNV>", VariantType.CNV),
+            VariantRecord("c1", 550000, 550001, 300, "A", "<INS>", VariantType.INS)]
+    ws = SR.get_windows(recs, SR.get_ref_idxs(fasta))
+    return {"contigs": {"c1": 600000, "c2": 5000},
+            "vcf": [[v.contig, v.pos, v.end, v.length, v.ref, v.alt, v.variant_type.name] for v in recs],
+            "windows": [[w.sequence, w.first, w.last, w.variant.pos, w.variant.end, w.variant.variant_type.name,
+                         w.variant.length, w.variant.allele] for w in ws]}
+
+
 def main():
     import logging
     logging.disable(logging.CRITICAL)
@@ -324,7 +344,8 @@ def main():
     for g in gen:
         print(g["case"]["name"], {k: (len(v) if v else v) for k, v in g["expected"]["files"].items()})
     with open(os.path.join(HERE, "genome_cases.json"), "w") as f:
-        json.dump({"generator": "tests/golden/make_golden.py", "cases": gen, "windows_kat": window_kats()}, f,
+        json.dump({"generator": "tests/golden/make_golden.py", "cases": gen, "windows_kat": window_kats(),
+                   "sv_windows_kat": sv_window_kats()}, f,
                   separators=(",", ":"))
 
 

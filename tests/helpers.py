@@ -158,8 +158,9 @@ def write_vcf(path, records):
     """records: [contig, pos, end, length, ref, alt, type] rows (the layout of genome_cases.json's "vcf")."""
     with open(path, "w") as fh:
         fh.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
-        for c, pos, _end, _len, ref, alt, _t in records:
-            fh.write(f"{c}\t{pos}\t.\t{ref}\t{alt}\t.\tPASS\t.\n")
+        for c, pos, end, length, ref, alt, _t in records:
+            info = f"END={end};SVLEN={length}" if alt.startswith("<") else "."
+            fh.write(f"{c}\t{pos}\t.\t{ref}\t{alt}\t.\tPASS\t{info}\n")
 
 
 def write_sample_files(tmp, case, vcf, contig_len=None):

@@ -70,9 +70,26 @@ def test_windows_of_indel_records_match_the_reference_geometry(tmp_path):
     with gzip.open(gz, "wt") as fh:
         fh.write(open(vc).read())
     assert GF.read_vcf(gz) == GF.read_vcf(vc)
-    H.write_vcf(vc, [["c1", 10, 10, 1, "A", "<DEL>", "DEL"]])
-    with pytest.raises(ValueError):
+    open(vc, "w").write("##fileformat=VCFv4.2\nc1\t10\t.\tA\tA[c2:77[\t.\tPASS\tSVTYPE=BND\n")
+    with pytest.raises(ValueError):                                  # breakends are not restated: loud, not guessed
         GF.read_vcf(vc)
+    open(vc, "w").write("c1\t10\t.\tA\t<DEL>\t.\tPASS\t.\n")
+    with pytest.raises(ValueError):                                  # a symbolic allele needs END or SVLEN
+        GF.read_vcf(vc)
+
+
+def test_windows_of_structural_records_match_the_reference_geometry(tmp_path):
+    """tests/golden: the reference's get_windows on DEL / DUP / INV (near and far ends) / 150 kb DEL / CNV / INS records."""
+    kat = GOLD["sv_windows_kat"]
+    vc = str(tmp_path / "sv.vcf")
+    H.write_vcf(vc, kat["vcf"])
+    got = GF.windows_by_contig(GF.read_vcf(vc), {c: k for k, c in enumerate(kat["contigs"])})
+    rows = [[c, w["first"], w["last"], w["keep"]["pos"], w["keep"]["end"], w["keep"]["type"], w["keep"]["length"], w["keep"]["allele"]]
+            for c, ws in got.items() for w in ws]
+    assert rows == kat["windows"]
+    from genomeanonymizer_b200 import batch as B2
+    t = B2.pack_sessions(got["c1"])                                  # structural keep types never equal a called allele
+    assert set(int(x) for x in t.keep_type) <= {2, 3, 99}
 
 
 def test_multi_contig_bam_flag_filter_small_blocks_and_sort_check(tmp_path):
