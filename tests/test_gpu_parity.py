@@ -210,3 +210,36 @@ def test_reads_with_many_germline_indels_stay_in_the_streaming_pipeline(engine, 
     assert n_many > 10 and got.totals["masked"][1] + got.totals["masked"][2] > 10, (n_many, got.totals)
     n, reasons = engine.fallback_sessions()
     assert reasons[4] == 0, reasons
+
+
+def test_records_that_are_not_contiguous_in_seq4_take_the_unstaged_path(engine):
+    """The scan kernel stages a tile with one TMA bulk copy only when its records are contiguous and ascending in
+    seq4; any other layout the C ABI allows (here: records in reverse order with gaps between them) goes read by read
+    through the whole-warp walk.  Same results either way."""
+    from oracle import oracle
+    case = synth.make_case(seed=601, contig_len=7000, n_pairs=(300, 280), read_len=150, indel_rate=1e-3, clip_frac=0.2,
+                           somatic_positions=[2500, 4600])
+    batch = B.pack_reads(H.ordered_reads(case))
+    n = batch.n_reads
+    units = np.maximum(1, ((batch.len_flag & 0xFFFF).astype(np.int64) + 31) // 32)
+    new_off = np.zeros(n, np.int64)
+    cur = 3
+    for r in range(n - 1, -1, -1):                                    # last read first, one spare unit between records
+        new_off[r] = cur
+        cur += int(units[r]) + 1
+    seq4 = np.zeros(16 * cur, np.uint8)
+    qual = np.zeros(32 * cur, np.uint8)
+    for r in range(n):
+        o, u, s = int(batch.seq_off16[r]), int(units[r]), int(new_off[r])
+        seq4[16 * s:16 * (s + u)] = batch.seq4[16 * o:16 * (o + u)]
+        qual[32 * s:32 * (s + u)] = batch.qual[32 * o:32 * (o + u)]
+    scattered = B.ReadBatch(n_tumor=batch.n_tumor, pos=batch.pos, len_flag=batch.len_flag, seq_off16=new_off.astype(np.uint32),
+                            cigar_off=batch.cigar_off, cigar=batch.cigar, seq4=seq4, qual=qual, max_ref_span=batch.max_ref_span,
+                            contig_id=0, names=batch.names)
+    sessions = B.pack_sessions(case["windows"])
+    exp, st = oracle.run(batch, sessions, case["reference"])
+    assert st == 0
+    engine.upload_reference(0, case["reference"])
+    got = engine.run(scattered, sessions)
+    assert_same_result(got, exp, "scattered records")
+    assert got.totals["n_modified"] > 0
