@@ -93,12 +93,17 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
 //      index the forward-orientation quality array, printed order = BAM order (anonymizer_methods.py:95, 213).
 __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r,
                                                    int pos, int L, uint32_t src_unit, uint32_t c0, uint32_t c1, bool reverse, int col_begin, const GermList& germ, const uint8_t* qrec,
-                                                   uint32_t* stage, uint64_t seq16, uint64_t qual16, int new_len, int glane) {
-    const int nw = (L + 7) >> 3;
+                                                   uint32_t* stage, uint32_t* qstage, uint64_t seq16, uint64_t qual16, int new_len, int glane) {
+    const int nw = (L + 7) >> 3, nqw = (L + 3) >> 2;
     if (act) {
         const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * src_unit);
         for (int w = glane; w < nw; w += kGroup) stage[w] = __ldg(rec + w) & tail_mask(L, w);
         if (glane == 0) stage[nw] = 0u;                                // the funnel shift may touch one word past the end
+        if (E.ne == 1 && qrec) {                                       // the quality record too: it is summed and shifted below
+            const uint32_t* qg = reinterpret_cast<const uint32_t*>(qrec);
+            for (int q = glane; q < nqw; q += kGroup) qstage[q] = __ldg(qg + q);
+            if (glane == 0) qstage[nqw] = 0u;
+        }
     }
     __syncwarp();
     if (act) {
@@ -138,9 +143,8 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     if (__any_sync(0xffffffffu, ok && is_del)) {                      // quality of re-inserted bases (anonymizer_methods.py:193)
         uint32_t part = 0;
         if (ok && is_del) {
-            const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
-            for (int q = glane; q < ((L + 3) >> 2); q += kGroup) {
-                uint32_t v = __ldg(qw + q);
+            for (int q = glane; q < nqw; q += kGroup) {
+                uint32_t v = qstage[q];
                 if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
                 part += __vsadu4(v, 0u);
             }
@@ -175,11 +179,9 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     // 187, 195: quirk Q2), so for a reverse read the pieces come in the opposite order: printed [0, b1) = BAM bytes as
     // they are, [b1, b2) = the mean, [b2, new_len) = BAM bytes shifted by d3.
     const int b1 = reverse ? new_len - ins_end : p, b2 = reverse ? new_len - p : ins_end, d3 = reverse ? L - new_len : shift;
-    const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrec);
-    auto qual_at = [&](int bidx) -> uint32_t {                         // 4 quality bytes from BAM byte bidx (>= -3)
-        if (bidx < 0) return __ldg(qw) << ((-bidx) * 8);
-        const uint32_t lo = __ldg(qw + (bidx >> 2)), hi = (bidx & 3) ? __ldg(qw + (bidx >> 2) + 1) : 0u;
-        return __funnelshift_r(lo, hi, (uint32_t)(bidx & 3) * 8u);
+    auto qual_at = [&](int bidx) -> uint32_t {                         // 4 staged quality bytes from BAM byte bidx (>= -3)
+        if (bidx < 0) return qstage[0] << ((-bidx) * 8);
+        return __funnelshift_r(qstage[bidx >> 2], qstage[(bidx >> 2) + 1], (uint32_t)(bidx & 3) * 8u);
     };
     uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
     for (int w = glane; w < units * 8; w += kGroup) {
@@ -200,6 +202,7 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
 // kernels packed: four records per warp step, one group of 8 lanes each.
 __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
     __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
+    __shared__ uint32_t qstage[kThreads / kGroup][2 * kGroupStage];      // quality bytes of the same reads (4 per word)
     const int tid = threadIdx.x, group = tid / kGroup, glane = tid % kGroup;
     const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
     const uint32_t groups_total = gridDim.x * (kThreads / kGroup);
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
                 // the common shapes take the staged path; two edits or very long reads take the general one
                 const bool fast = (r_kind == 2u || (indel && Ed.ne == 1)) && ((L + 7) >> 3) <= kGroupStage - 1;
                 if (__any_sync(0xffffffffu, fast))
-                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, c0, c1, reverse, col_begin, germ, qrec, stage[group], seq16, qual16, new_len, glane);
+                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, c0, c1, reverse, col_begin, germ, qrec, stage[group], qstage[group], seq16, qual16, new_len, glane);
                 if (r_kind == 2u && !fast) {
                     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
                     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
