@@ -45,6 +45,7 @@ struct EmitScratch2 {
     uint32_t cap_many;
     uint32_t* many_recs; // [cap_many] special-record slots of those records (emit_many_kernel walks them)
     uint32_t* n_many_recs;
+    uint32_t* n_kind1;   // records left to emit_kernel (long clean reads); zero lets that kernel return at once
 };
 
 // Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked
@@ -77,6 +78,38 @@ __device__ __forceinline__ void write_special(const EmitScratch2& E, const Batch
     dp[1] = make_uint4((uint32_t)r, new_len, (uint32_t)seq16, qual16);
     dp[2] = make_uint4(__ldg(B.cigar_off + r), __ldg(B.cigar_off + r + 1), (uint32_t)d.col_begin, 0u);
     dp[3] = make_uint4((uint32_t)(tumor ? d.qt_begin : d.qn_begin), (uint32_t)(tumor ? d.qt_end : d.qn_end), 0u, 0u);
+}
+
+// The body of a common record - clean read, at most two germline hits, at most 160 bases (five 16-byte units) - written
+// by the resolve kernels themselves: copy, base <- reference base at the hits (anonymizer_methods.py:170-176).  hits =
+// two (column << 4 | reference code) half-words, rel0 = pos - col_begin.  The loads of the records a warp handles in one
+// step are in flight together.
+__device__ __forceinline__ void write_common_body(const BatchView& B, const ResultView& O, uint32_t so, uint64_t dst_unit, uint32_t L0,
+                                                  uint32_t hits, uint32_t n_hits, int rel0) {
+    const uint4* src = reinterpret_cast<const uint4*>(B.seq4 + 16ull * so);
+    uint4* dst = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * dst_unit);
+    const int nu = (int)((L0 + 31u) >> 5);
+    uint4 v[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) v[u] = u < nu ? ldg128(src + u) : make_uint4(0u, 0u, 0u, 0u);
+    const int q0 = (int)((hits >> 4) & 0xfffu) - rel0, q1 = n_hits > 1u ? (int)(hits >> 20) - rel0 : -1;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+        if (u >= nu) break;
+        uint4 w = v[u];
+        if (32 * u + 32 > (int)L0) { w.x &= tail_mask((int)L0, 4 * u); w.y &= tail_mask((int)L0, 4 * u + 1); w.z &= tail_mask((int)L0, 4 * u + 2); w.w &= tail_mask((int)L0, 4 * u + 3); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = h ? q1 : q0;
+            if (q >= 0 && (q >> 5) == u) {
+                const uint32_t sh = (uint32_t)(q & 7) * 4u, keepm = ~(0xfu << sh), ins = ((h ? hits >> 16 : hits) & 15u) << sh;
+                const int ww = (q >> 3) & 3;
+                if (ww == 0) w.x = (w.x & keepm) | ins; else if (ww == 1) w.y = (w.y & keepm) | ins;
+                else if (ww == 2) w.z = (w.z & keepm) | ins; else w.w = (w.w & keepm) | ins;
+            }
+        }
+        dst[u] = w;
+    }
 }
 
 struct SmemR {
@@ -403,10 +436,14 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             write_record_meta(O, rec_idx, s, r, (int)(m & kLen2), s_base[1] + sm->mseq[k], qual16);
             const uint32_t lf = __ldg(B.len_flag + r);
             const uint8_t kind = q ? 3 : (((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2 : (sm->mpc[k] <= 2 ? 1 : 4));
-            E.kind[rec_idx] = kind;
             const int pos = __ldg(B.pos + r);
-            if (kind == 1) E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
-            else {
+            if (kind == 1 && (lf & 0xffffu) <= 160u) {              // the common record: written here, nothing left for the emission kernels
+                write_common_body(B, O, __ldg(B.seq_off16 + r), s_base[1] + sm->mseq[k], lf & 0xffffu, sm->mpatch[k], sm->mpc[k], pos - c.d.col_begin);
+            } else if (kind == 1) {                                   // a long clean read: the copy kernel takes it
+                E.kind[rec_idx] = 1;
+                E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
+                atomicAdd(E.n_kind1, 1u);
+            } else {
                 const uint32_t slot = atomicAdd(E.n_special, 1u);
                 uint32_t skind = kind;
                 if (kind == 3) {                                      // more than two edits: emit_many_kernel writes the body (kind 5)
@@ -805,40 +842,14 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
             write_record_meta(O, rec_idx, s, r, (int)new_len, base_seq + so_rel, qual16);
             const uint32_t L0 = lf & 0xffffu;
             if (kind == 1u && L0 <= 160u) {
-                // clean read, at most two germline hits, up to five 16-byte units (the common record): the lane writes
-                // the body itself - copy, base <- reference base at the hits (anonymizer_methods.py:170-176).  The
-                // loads of the 32 records of this step are in flight together; the emission kernel skips kind 0.
-                const uint4* src = reinterpret_cast<const uint4*>(B.seq4 + 16ull * so);
-                uint4* dst = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * (base_seq + so_rel));
-                const int nu = (int)((L0 + 31u) >> 5);
-                uint4 v[5];
-#pragma unroll
-                for (int u = 0; u < 5; ++u) v[u] = u < nu ? ldg128(src + u) : make_uint4(0u, 0u, 0u, 0u);
-                const uint32_t hits = sm->mpatch[k];
-                const int rel0 = pos - c.d.col_begin;
-                const int q0 = (int)((hits >> 4) & 0xfffu) - rel0, q1 = sm->mpc[k] > 1 ? (int)(hits >> 20) - rel0 : -1;
-#pragma unroll
-                for (int u = 0; u < 5; ++u) {
-                    if (u >= nu) break;
-                    uint4 w = v[u];
-                    if (32 * u + 32 > (int)L0) { w.x &= tail_mask((int)L0, 4 * u); w.y &= tail_mask((int)L0, 4 * u + 1); w.z &= tail_mask((int)L0, 4 * u + 2); w.w &= tail_mask((int)L0, 4 * u + 3); }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int q = h ? q1 : q0;
-                        if (q >= 0 && (q >> 5) == u) {
-                            const uint32_t sh = (uint32_t)(q & 7) * 4u, keepm = ~(0xfu << sh), ins = ((h ? hits >> 16 : hits) & 15u) << sh;
-                            const int ww = (q >> 3) & 3;
-                            if (ww == 0) w.x = (w.x & keepm) | ins; else if (ww == 1) w.y = (w.y & keepm) | ins;
-                            else if (ww == 2) w.z = (w.z & keepm) | ins; else w.w = (w.w & keepm) | ins;
-                        }
-                    }
-                    dst[u] = w;
-                }
+                // the common record: the lane writes the body itself; the emission kernel skips kind 0
+                write_common_body(B, O, so, base_seq + so_rel, L0, sm->mpatch[k], sm->mpc[k], pos - c.d.col_begin);
                 continue;                                             // E.kind stays 0: nothing left for the emission kernels
             }
             if (kind == 1u) {                                         // a long clean read: the copy kernel takes it
                 E.kind[rec_idx] = 1;
                 E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
+                atomicAdd(E.n_kind1, 1u);
             } else if ((int64_t)my_slot < O.cap_records) {
                 write_special(E, B, c.d, my_slot, kind, so, pos, lf, s, r, new_len, base_seq + so_rel, qual16);
             }
