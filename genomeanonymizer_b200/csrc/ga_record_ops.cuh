@@ -11,7 +11,7 @@ namespace ga {
 
 constexpr int kCols2 = 2688;           // allele-table columns per session (shared-memory paths)
 constexpr int kReads2 = 4096;          // candidate reads per session
-constexpr int kMod2 = 512;             // modified reads per session
+constexpr int kMod2 = 1024;            // modified reads per session
 constexpr uint32_t kLen2 = (1u << 24) - 1;   // msize: length bits (flags above: kModFlag, kQualFlag)
 constexpr int kGermCap = 32;           // germline SNV alleles per session handed to the emission kernels
 constexpr int kGroup = 8;              // lanes that cooperate on one non-trivial output record
