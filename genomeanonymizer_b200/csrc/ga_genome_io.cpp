@@ -268,6 +268,8 @@ int ga_bam_pack_contig(const ga_bam* b, int ref_id, uint32_t flag_exclude, const
     for (int64_t k = 0; k < n; ++k) {
         const RecView v = view_of(b->data.data() + recs[k]);
         if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
+        if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > le32(b->data.data() + recs[k] - 4))
+            return fail(GA_IO_ERR_FORMAT, "alignment record fields exceed its block size");
         dst->seq_off16[k] = (uint32_t)u;
         dst->cigar_off[k] = (uint32_t)c;
         if (dst->name_off) dst->name_off[k] = nm;
