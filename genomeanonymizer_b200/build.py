@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libga_b200.so")
-SOURCES = ["ga_engine.cu", "ga_host_pipeline.cu", "ga_synth.cu", "ga_fastq.cu", "ga_genome_io.cpp"]
+SOURCES = ["ga_engine.cu", "ga_host_pipeline.cu", "ga_synth.cu", "ga_fastq.cu", "ga_genome_io.cpp", "ga_plan.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

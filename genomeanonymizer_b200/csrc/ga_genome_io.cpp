@@ -141,6 +141,7 @@ struct ga_fasta {
 extern "C" {
 
 const char* ga_io_last_error(void) { return g_err.c_str(); }
+int ga_io_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 
 int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
     if (!path || !out) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_open: NULL argument");

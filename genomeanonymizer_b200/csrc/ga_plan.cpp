@@ -1,0 +1,303 @@
+// ga_plan.cpp - the host-side plan of one contig of a tumor-normal sample behind include/ga_plan.h
+// (SURVEY.md 8(f) N2 + N3): sections, island sessions, yield order inside a session, mate pairing, first write wins.
+// Same algorithm as genomeanonymizer_b200/driver.py: plan_sample (which stays as its checker); the reference code each
+// step restates is cited there and below.
+#include "../../include/ga_plan.h"
+#include "../../include/ga_genome_io.h"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+extern "C" int ga_io_set_error(int code, const char* msg);   // ga_genome_io.cpp
+
+struct ga_plan {
+    std::vector<int32_t> s_first, s_last, s_window;
+    std::vector<int32_t> pairs;      // 5 per row
+    std::vector<int32_t> singles;    // 3 per row
+};
+
+namespace {
+
+constexpr int64_t kNone = INT64_MIN;                       // an empty mate slot
+inline int64_t slot_of(int32_t read, int32_t version) { return ((int64_t)read << 32) | (uint32_t)version; }
+inline int32_t slot_read(int64_t v) { return (int32_t)(v >> 32); }
+inline int32_t slot_version(int64_t v) { return (int32_t)(uint32_t)v; }
+
+struct Planner {
+    int64_t n, n_tumor;
+    const int32_t *pos, *end;
+    const uint32_t* lf;
+    std::vector<int32_t> name_id;                          // dense id of every read's name
+    int32_t n_names = 0;
+    int span = 0;
+    ga_plan* plan;
+
+    // to_pair_anonymized_reads: insertion-ordered map name -> [mate 1, mate 2] (a popped name re-enters at the end)
+    struct Entry { int32_t name; int64_t slot[2]; bool alive; };
+    std::vector<Entry> entries;
+    std::vector<int32_t> entry_of;                         // name id -> index into entries, -1 when absent
+    std::vector<uint8_t> written;                          // written_read_ids
+
+    // per-session scratch, indexed by name id through a stamp
+    std::vector<int32_t> stamp, local_of;
+    int32_t cur_stamp = 0;
+
+    int dataset(int32_t i) const { return i < n_tumor ? 0 : 1; }
+    int mate(int32_t i) const { return ((lf[i] >> 16) & 0x40u) ? 0 : 1; }
+
+    // AlignmentFile.fetch / pileup read selection: reads of one dataset with pos < stop and end > start
+    void overlapping(int ds, int64_t start, int64_t stop, std::vector<int32_t>& out) const {
+        out.clear();
+        const int32_t* b = pos + (ds ? n_tumor : 0);
+        const int32_t* e = pos + (ds ? n : n_tumor);
+        const int32_t* lo = std::lower_bound(b, e, start - span, [](int32_t p, int64_t v) { return (int64_t)p < v; });
+        const int32_t* hi = std::lower_bound(b, e, stop, [](int32_t p, int64_t v) { return (int64_t)p < v; });
+        for (const int32_t* p = lo; p < hi; ++p) {
+            const int32_t i = (int32_t)(p - pos);
+            if ((int64_t)end[i] > start) out.push_back(i);
+        }
+    }
+
+    int64_t* store(int32_t name, int m, int64_t value) {   // add_*_to_collection: an occupied slot keeps its read
+        int32_t k = entry_of[name];
+        if (k < 0) { k = (int32_t)entries.size(); entries.push_back({name, {kNone, kNone}, true}); entry_of[name] = k; }
+        if (entries[k].slot[m] == kNone) entries[k].slot[m] = value;
+        return entries[k].slot;
+    }
+    void pop(int32_t name) {
+        const int32_t k = entry_of[name];
+        if (k >= 0) { entries[k].alive = false; entry_of[name] = -1; }
+    }
+    void write_pair(int32_t name, int64_t s1, int64_t s2, std::vector<int32_t>& sink) {   // write_pair, SR.py:134-165
+        if (written[name]) return;
+        written[name] = 1;
+        const int32_t row[5] = {dataset(slot_read(s1)), slot_read(s1), slot_version(s1), slot_read(s2), slot_version(s2)};
+        sink.insert(sink.end(), row, row + 5);
+    }
+
+    // Pairs of one session in the order CompleteGermlineAnonymizer.anonymize yields them (AM.py:472-476, 489-512,
+    // 521-532): a pair whose two mates are in the session leaves at the first normal pileup column right of both
+    // mates, pairs in first-appearance order; everything else at the end, in registry order.
+    struct Yield { int32_t name, m1, m2; };
+    void session_yield_order(const std::vector<int32_t>& t_idx, const std::vector<int32_t>& n_idx, std::vector<Yield>& out) {
+        out.clear();
+        ++cur_stamp;
+        struct Local { int32_t name, slot[2]; int32_t max_end; };
+        std::vector<Local> loc;
+        size_t a = 0, b = 0;
+        while (a < t_idx.size() || b < n_idx.size()) {      // reads appear at their own start, tumor column before normal column
+            int32_t i;
+            if (b >= n_idx.size() || (a < t_idx.size() && pos[t_idx[a]] <= pos[n_idx[b]])) i = t_idx[a++]; else i = n_idx[b++];
+            const int32_t nm = name_id[i];
+            if (stamp[nm] != cur_stamp) { stamp[nm] = cur_stamp; local_of[nm] = (int32_t)loc.size(); loc.push_back({nm, {-1, -1}, -1}); }
+            Local& L = loc[local_of[nm]];
+            const int m = mate(i);
+            if (L.slot[m] < 0) L.slot[m] = i;                // the first alignment of a (name, mate) is the read
+            L.max_end = std::max(L.max_end, end[i]);
+        }
+        // normal pileup columns = positions covered by a normal read of the session
+        std::vector<std::pair<int32_t, int32_t>> merged;
+        for (const int32_t i : n_idx) {
+            if (!merged.empty() && pos[i] <= merged.back().second) merged.back().second = std::max(merged.back().second, end[i]);
+            else merged.push_back({pos[i], end[i]});
+        }
+        auto first_normal_column_after = [&](int32_t p, int32_t* col) -> bool {   // smallest covered position > p
+            int64_t k = (int64_t)(std::upper_bound(merged.begin(), merged.end(), p + 1,
+                                                   [](int32_t v, const std::pair<int32_t, int32_t>& m) { return v < m.first; }) - merged.begin()) - 1;
+            if (k >= 0 && merged[k].second > p + 1) { *col = p + 1; return true; }
+            ++k;
+            if (k < (int64_t)merged.size()) { *col = merged[k].first; return true; }
+            return false;
+        };
+        struct Early { int32_t col, order; };
+        std::vector<Early> early;
+        std::vector<int32_t> late;
+        for (int32_t o = 0; o < (int32_t)loc.size(); ++o) {
+            int32_t col;
+            if (loc[o].slot[0] >= 0 && loc[o].slot[1] >= 0 && first_normal_column_after(loc[o].max_end, &col)) early.push_back({col, o});
+            else late.push_back(o);
+        }
+        std::sort(early.begin(), early.end(), [](const Early& x, const Early& y) { return x.col != y.col ? x.col < y.col : x.order < y.order; });
+        for (const Early& e : early) out.push_back({loc[e.order].name, loc[e.order].slot[0], loc[e.order].slot[1]});
+        for (const int32_t o : late) out.push_back({loc[o].name, loc[o].slot[0], loc[o].slot[1]});
+    }
+
+    void run_session(int32_t first, int32_t last, int32_t window) {
+        const int32_t s = (int32_t)plan->s_first.size();
+        plan->s_first.push_back(first); plan->s_last.push_back(last); plan->s_window.push_back(window);
+        std::vector<int32_t> t_idx, n_idx;
+        overlapping(0, first, last, t_idx);
+        overlapping(1, first, last, n_idx);
+        std::vector<Yield> ys;
+        session_yield_order(t_idx, n_idx, ys);
+        for (const Yield& y : ys) {
+            if (y.m1 >= 0 && y.m2 >= 0) { write_pair(y.name, slot_of(y.m1, s), slot_of(y.m2, s), plan->pairs); continue; }   // SR.py:310-312
+            int64_t* slot = nullptr;
+            if (y.m1 >= 0) slot = store(y.name, 0, slot_of(y.m1, s));                                                        // SR.py:320-333
+            if (y.m2 >= 0) slot = store(y.name, 1, slot_of(y.m2, s));
+            if (slot && slot[0] != kNone && slot[1] != kNone) {                                                              // SR.py:348-359
+                const int64_t s0 = slot[0], s1 = slot[1];
+                write_pair(y.name, s0, s1, plan->pairs);
+                pop(y.name);
+            }
+        }
+    }
+
+    // Chains of reads in which every read overlaps (or touches, or ends with) the one before it
+    // (collect_intersecting_reads, pileup_io.pyx:78-106 with compare, :44-59).
+    struct Island { size_t begin, end_; int32_t first_pos, max_end; };   // [begin, end_) into the index list
+    void islands(const std::vector<int32_t>& idx, std::vector<Island>& out) const {
+        out.clear();
+        for (size_t k = 0; k < idx.size(); ++k) {
+            const int32_t i = idx[k];
+            if (!out.empty()) {
+                const int32_t l = idx[k - 1];
+                if ((pos[i] <= end[l] && end[i] >= pos[l]) || end[i] == end[l]) {
+                    out.back().end_ = k + 1; out.back().max_end = std::max(out.back().max_end, end[i]);
+                    continue;
+                }
+            }
+            out.push_back({k, k + 1, pos[i], end[i]});
+        }
+    }
+    static int cmp_islands(const Island& a, const Island& b) {   // compare() of pileup_io.pyx:44-59
+        const int32_t f1 = a.first_pos, l1 = a.max_end, f2 = b.first_pos, l2 = b.max_end;
+        const bool overlap = f2 <= l1 && l2 >= f1;
+        if (l1 < l2) return overlap ? -1 : -2;
+        if (l2 < l1) return overlap ? 1 : 2;
+        return f1 < f2 ? -1 : (f2 < f1 ? 1 : 0);
+    }
+
+    // pair_unmapped_or_non_pileup_pairs_and_write (SR.py:375-406) for one island that is yielded singly
+    void pass_through(const std::vector<int32_t>& idx, const Island* isl, std::vector<int32_t>& deferred) {
+        if (!isl) return;
+        for (size_t k = isl->begin; k < isl->end_; ++k) {
+            const int32_t i = idx[k];
+            int64_t* slot = store(name_id[i], mate(i), slot_of(i, -1));
+            if (slot[0] != kNone && slot[1] != kNone) write_pair(name_id[i], slot[0], slot[1], deferred);   // stays in the collection until the end (SR.py:737-741)
+        }
+    }
+
+    // What iter_fetch_pair (pileup_io.pyx:124-298) yields for the fetched reads of one inter-window region.
+    void region(int64_t start, int64_t stop) {
+        std::vector<int32_t> t_idx, n_idx, deferred;
+        overlapping(0, start, stop, t_idx);
+        overlapping(1, start, stop, n_idx);
+        if (t_idx.empty() && n_idx.empty()) return;
+        std::vector<Island> ti, ni;
+        islands(t_idx, ti);
+        islands(n_idx, ni);
+        size_t a = 0, b = 0;
+        for (;;) {
+            const bool more_t = a + 1 < ti.size(), more_n = b + 1 < ni.size();
+            if (!more_t && !more_n) {                          // the last island of each dataset is always yielded singly
+                pass_through(t_idx, a < ti.size() ? &ti[a] : nullptr, deferred);
+                pass_through(n_idx, b < ni.size() ? &ni[b] : nullptr, deferred);
+                break;
+            }
+            if (more_t && more_n) {
+                const int c = cmp_islands(ti[a], ni[b]);
+                if (c < -1) { pass_through(t_idx, &ti[a], deferred); ++a; }
+                else if (c > 1) { pass_through(n_idx, &ni[b], deferred); ++b; }
+                else {                                         // an island session has no variant to keep (SR.py:523-534)
+                    run_session(std::min(ti[a].first_pos, ni[b].first_pos), std::max(ti[a].max_end, ni[b].max_end), -1);
+                    ++a; ++b;
+                }
+            } else {
+                if (more_t) { pass_through(t_idx, &ti[a], deferred); ++a; }
+                if (more_n) { pass_through(n_idx, &ni[b], deferred); ++b; }
+            }
+        }
+        // the region's own records reach the files behind those of its island sessions (stream buffering)
+        plan->pairs.insert(plan->pairs.end(), deferred.begin(), deferred.end());
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ga_plan_sample(int64_t n_reads, int64_t n_tumor, const int32_t* pos, const int32_t* ref_end, const uint32_t* len_flag,
+                   const int64_t* name_off, const uint8_t* names, int32_t n_windows, const int32_t* win_first,
+                   const int32_t* win_last, int64_t contig_len, ga_plan** out) {
+    if (!out || n_reads < 0 || n_tumor < 0 || n_tumor > n_reads || n_windows < 0 ||
+        (n_reads && (!pos || !ref_end || !len_flag || !name_off || !names)) || (n_windows && (!win_first || !win_last)))
+        return ga_io_set_error(GA_IO_ERR_ARGUMENT, "ga_plan_sample: bad argument");
+    *out = nullptr;
+    for (int64_t i = 1; i < n_reads; ++i)
+        if (i != n_tumor && pos[i] < pos[i - 1]) return ga_io_set_error(GA_IO_ERR_ARGUMENT, "reads of a dataset must be in coordinate order");
+    Planner P;
+    P.n = n_reads; P.n_tumor = n_tumor; P.pos = pos; P.end = ref_end; P.lf = len_flag;
+    P.name_id.resize((size_t)n_reads);
+    {
+        std::unordered_map<std::string_view, int32_t> ids;
+        ids.reserve((size_t)n_reads);
+        for (int64_t i = 0; i < n_reads; ++i) {
+            const std::string_view nm(reinterpret_cast<const char*>(names) + name_off[i], (size_t)(name_off[i + 1] - name_off[i]));
+            const auto it = ids.emplace(nm, (int32_t)ids.size()).first;
+            P.name_id[(size_t)i] = it->second;
+            P.span = std::max(P.span, ref_end[i] - pos[i]);
+        }
+        P.n_names = (int32_t)ids.size();
+    }
+    P.entry_of.assign((size_t)P.n_names, -1);
+    P.written.assign((size_t)P.n_names, 0);
+    P.stamp.assign((size_t)P.n_names, 0);
+    P.local_of.assign((size_t)P.n_names, 0);
+    ga_plan* plan = new ga_plan();
+    P.plan = plan;
+    // get_genome_sections (SR.py:245-276): window k, the regions between windows, stably sorted by (first, last)
+    struct Section { int64_t first, last; int32_t window; };
+    std::vector<Section> secs;
+    if (n_windows == 0) secs.push_back({0, 0, -1});
+    else {
+        int64_t nxt = 1;
+        for (int32_t k = 0; k < n_windows; ++k) {
+            secs.push_back({nxt, (int64_t)win_first[k] - 1, -1});
+            secs.push_back({win_first[k], win_last[k], k});
+            nxt = (int64_t)win_last[k] + 1;
+        }
+        secs.push_back({nxt, contig_len - 1, -1});
+        std::stable_sort(secs.begin(), secs.end(), [](const Section& x, const Section& y) { return x.first != y.first ? x.first < y.first : x.last < y.last; });
+    }
+    for (const Section& sc : secs) {
+        if (sc.window >= 0) { P.run_session((int32_t)sc.first, (int32_t)sc.last, sc.window); continue; }
+        int64_t start, stop;
+        if (sc.first + sc.last == 0) { start = 0; stop = contig_len; }
+        else {
+            if (sc.first < 0 || sc.first > sc.last) {          // pysam rejects these coordinates
+                delete plan;
+                return ga_io_set_error(GA_IO_ERR_ARGUMENT, ("inter-window region (" + std::to_string(sc.first) + ", " + std::to_string(sc.last) +
+                                                            ") is not fetchable: variants closer than a window").c_str());
+            }
+            start = sc.first; stop = sc.last;
+        }
+        P.region(start, stop);
+    }
+    for (const Planner::Entry& e : P.entries) {                // write_single_end_reads (SR.py:603-622), insertion order
+        if (!e.alive || P.written[e.name]) continue;
+        const int64_t v = e.slot[0] != kNone ? e.slot[0] : e.slot[1];
+        const int32_t row[3] = {P.dataset(slot_read(v)), slot_read(v), slot_version(v)};
+        plan->singles.insert(plan->singles.end(), row, row + 3);
+    }
+    *out = plan;
+    return GA_IO_OK;
+}
+
+void ga_plan_free(ga_plan* p) { delete p; }
+int64_t ga_plan_n_sessions(const ga_plan* p) { return p ? (int64_t)p->s_first.size() : 0; }
+int64_t ga_plan_n_pairs(const ga_plan* p) { return p ? (int64_t)p->pairs.size() / 5 : 0; }
+int64_t ga_plan_n_singles(const ga_plan* p) { return p ? (int64_t)p->singles.size() / 3 : 0; }
+void ga_plan_sessions(const ga_plan* p, int32_t* first, int32_t* last, int32_t* window) {
+    if (!p) return;
+    const size_t n = p->s_first.size();
+    if (n) { std::memcpy(first, p->s_first.data(), 4 * n); std::memcpy(last, p->s_last.data(), 4 * n); std::memcpy(window, p->s_window.data(), 4 * n); }
+}
+void ga_plan_pairs(const ga_plan* p, int32_t* rows) { if (p && !p->pairs.empty()) std::memcpy(rows, p->pairs.data(), 4 * p->pairs.size()); }
+void ga_plan_singles(const ga_plan* p, int32_t* rows) { if (p && !p->singles.empty()) std::memcpy(rows, p->singles.data(), 4 * p->singles.size()); }
+
+}  // extern "C"

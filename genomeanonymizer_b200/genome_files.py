@@ -37,7 +37,7 @@ class _BamDest(C.Structure):
                 ("name_base", C.c_uint64)]
 
 
-IO_EXPORTS = ["ga_io_last_error", "ga_bam_open", "ga_bam_close", "ga_bam_n_references", "ga_bam_reference_name",
+IO_EXPORTS = ["ga_io_last_error", "ga_io_set_error", "ga_bam_open", "ga_bam_close", "ga_bam_n_references", "ga_bam_reference_name",
               "ga_bam_reference_length", "ga_bam_n_records", "ga_bam_inflated_bytes", "ga_bam_contig_sizes",
               "ga_bam_pack_contig", "ga_fasta_open", "ga_fasta_close", "ga_fasta_n_references", "ga_fasta_reference_name",
               "ga_fasta_reference_length", "ga_fasta_fetch"]
@@ -83,8 +83,58 @@ def _io():
     L.ga_fasta_reference_length.argtypes = [vp, C.c_int]
     L.ga_fasta_fetch.restype = C.c_int64
     L.ga_fasta_fetch.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, vp]
+    L.ga_plan_sample.restype = C.c_int
+    L.ga_plan_sample.argtypes = [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int64, C.POINTER(vp)]
+    L.ga_plan_free.restype = None
+    L.ga_plan_free.argtypes = [vp]
+    for fn in ("ga_plan_n_sessions", "ga_plan_n_pairs", "ga_plan_n_singles"):
+        getattr(L, fn).restype = C.c_int64
+        getattr(L, fn).argtypes = [vp]
+    L.ga_plan_sessions.restype = None
+    L.ga_plan_sessions.argtypes = [vp, vp, vp, vp]
+    L.ga_plan_pairs.restype = None
+    L.ga_plan_pairs.argtypes = [vp, vp]
+    L.ga_plan_singles.restype = None
+    L.ga_plan_singles.argtypes = [vp, vp]
     _BOUND = True
     return L
+
+
+PLAN_EXPORTS = ["ga_plan_sample", "ga_plan_free", "ga_plan_n_sessions", "ga_plan_n_pairs", "ga_plan_n_singles", "ga_plan_sessions",
+                "ga_plan_pairs", "ga_plan_singles"]
+
+
+def plan_contig(cb: "ContigBatch", windows, contig_len: int):
+    """driver.plan_sample in native code (include/ga_plan.h) over the packed arrays of one contig: no per-read Python
+    object.  Returns a driver.Plan whose pairs / singles are int32 arrays of 5 / 3 columns."""
+    from .driver import Plan
+    L = _io()
+    b = cb.batch
+    pos = np.ascontiguousarray(b.pos, np.int32)
+    end = np.ascontiguousarray(cb.ref_end, np.int32)
+    lf = np.ascontiguousarray(b.len_flag, np.uint32)
+    noff = np.ascontiguousarray(cb.name_off, np.int64)
+    blob = np.ascontiguousarray(cb.name_blob, np.uint8) if cb.name_blob.size else np.zeros(1, np.uint8)
+    wf = np.asarray([w["first"] for w in windows], np.int32)
+    wl = np.asarray([w["last"] for w in windows], np.int32)
+    h = C.c_void_p()
+    _check(L, L.ga_plan_sample(b.n_reads, b.n_tumor, pos.ctypes.data, end.ctypes.data, lf.ctypes.data, noff.ctypes.data, blob.ctypes.data,
+                               len(windows), wf.ctypes.data if len(windows) else None, wl.ctypes.data if len(windows) else None,
+                               int(contig_len), C.byref(h)))
+    try:
+        ns, npairs, nsing = int(L.ga_plan_n_sessions(h)), int(L.ga_plan_n_pairs(h)), int(L.ga_plan_n_singles(h))
+        first, last, win = np.zeros(ns, np.int32), np.zeros(ns, np.int32), np.zeros(ns, np.int32)
+        pairs, singles = np.zeros((npairs, 5), np.int32), np.zeros((nsing, 3), np.int32)
+        L.ga_plan_sessions(h, first.ctypes.data, last.ctypes.data, win.ctypes.data)
+        L.ga_plan_pairs(h, pairs.ctypes.data)
+        L.ga_plan_singles(h, singles.ctypes.data)
+    finally:
+        L.ga_plan_free(h)
+    plan = Plan()
+    plan.sessions = [{"first": int(f), "last": int(l), "keep": windows[int(k)].get("keep") if k >= 0 else None,
+                      "window": int(k) if k >= 0 else None} for f, l, k in zip(first, last, win)]
+    plan.pairs, plan.singles = pairs, singles
+    return plan
 
 
 def _check(L, rc):

@@ -4,8 +4,9 @@ FASTQ files and statistics file out (SURVEY.md 8(b) "Python entry point", 8(f) N
 Mirrors `run_short_read_tumor_normal_anonymizer` (short_read_tumor_normal_anonymizer.py:889-893: same name, same
 positional arguments) and `name_output` (:55-58).  Per sample the reference runs `anonymize_genome` (:625-760), which
 walks the genome section by section through pysam; here every contig of the sample is decoded by the C++ readers
-(genome_files.py -> csrc/ga_genome_io.cpp), planned on the host (driver.plan_sample: sections, island sessions,
-mate pairing, first write wins), masked by ONE engine pass over all of its sessions and printed by the device
+(genome_files.py -> csrc/ga_genome_io.cpp), planned on the host in native code (include/ga_plan.h: sections, island
+sessions, mate pairing, first write wins; driver.plan_sample is the same algorithm in Python and its checker),
+masked by ONE engine pass over all of its sessions and printed by the device
 FASTQ renderer.  Outputs, named as the reference names them:
     <tumor_output>.1.fastq / .2.fastq, <normal_output>.1.fastq / .2.fastq       (:652-655)
     <tumor_output>.single_end.fastq, <normal_output>.single_end.fastq             (:603-622; only when a read stayed unpaired)
@@ -24,7 +25,7 @@ import re
 from typing import List, Optional, Tuple
 
 from . import genome_files as GF
-from .driver import anonymize_packed, plan_sample, statistics_text
+from .driver import anonymize_packed, statistics_text
 
 DATASET_IDX_TUMORAL = 0      # variation_classifier.py:13
 DATASET_IDX_NORMAL = 1       # variation_classifier.py:14
@@ -53,12 +54,11 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
                 if cb.batch.n_reads == 0 and not windows:
                     continue
                 reference = fasta.fetch_bytes(contig)
-                table = cb.read_table()
-                plan = plan_sample(table, windows, len(reference))
+                plan = GF.plan_contig(cb, windows, len(reference))          # include/ga_plan.h: no per-read Python object
                 if cb.batch.n_reads == 0:
                     stats_parts.append((contig, plan, [[0, 0, 0, 0]] * len(plan.sessions)))
                     continue
-                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), table, windows, reference, contig, plan=plan)
+                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan)
                 for p in "TN":
                     handles[(p, "1")].write(got[f"{p}.1"])
                     handles[(p, "2")].write(got[f"{p}.2"])

@@ -35,6 +35,9 @@ typedef enum ga_io_status {
 } ga_io_status;
 
 const char* ga_io_last_error(void);
+/* Records an error text for ga_io_last_error() and returns `code`: used by the other host-side sources of the library
+ * (ga_plan.h) so that there is one error channel. */
+int ga_io_set_error(int code, const char* msg);
 
 /* ------------------------------------------------------------------ BAM */
 typedef struct ga_bam ga_bam;
