@@ -10,12 +10,17 @@
 // (short_read_tumor_normal_anonymizer.py:661-664, pileup_io.pyx:12-17, 138-139).
 #include "../../include/ga_genome_io.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,6 +56,27 @@ template <class F> void parallel_for(int64_t n, int threads, int64_t grain, F&& 
     for (auto& th : pool) th.join();
 }
 
+// Read-only view of a whole file (mmap: the compressed BAM is consumed straight from the page cache).
+struct FileView {
+    const uint8_t* p = nullptr; size_t n = 0; int fd = -1;
+    bool open(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+        n = (size_t)st.st_size;
+        if (n == 0) return true;
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        madvise(m, n, MADV_SEQUENTIAL);
+        p = static_cast<const uint8_t*>(m);
+        return true;
+    }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+    ~FileView() { if (p) munmap(const_cast<uint8_t*>(p), n); if (fd >= 0) ::close(fd); }
+};
+
 bool read_file(const char* path, std::vector<uint8_t>& out) {
     FILE* f = std::fopen(path, "rb");
     if (!f) return false;
@@ -70,7 +96,7 @@ inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 struct Block { uint64_t in_off; uint32_t in_size; uint64_t out_off; uint32_t out_size; };
 
 // Walks the gzip members of a BGZF file; false when the container is malformed.
-bool index_bgzf(const std::vector<uint8_t>& file, std::vector<Block>& blocks, uint64_t* total, std::string* why) {
+bool index_bgzf(const FileView& file, std::vector<Block>& blocks, uint64_t* total, std::string* why) {
     uint64_t off = 0, out = 0;
     const uint64_t n = file.size();
     while (off < n) {
@@ -126,7 +152,14 @@ inline int ref_span_of(const uint8_t* cigar, uint32_t n_ops) {
 }  // namespace
 
 struct ga_bam {
-    std::vector<uint8_t> data;                    // the inflated BAM stream
+    // the inflated BAM stream; not zero-initialised - its pages are first touched by the inflating threads
+    struct Bytes {
+        std::unique_ptr<uint8_t[]> p; uint64_t n = 0;
+        void resize(uint64_t k) { p.reset(new uint8_t[k ? k : 1]); n = k; }
+        uint8_t* data() { return p.get(); }
+        const uint8_t* data() const { return p.get(); }
+        uint64_t size() const { return n; }
+    } data;
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     std::vector<std::vector<uint64_t>> by_ref;    // per reference: offsets (of refID, i.e. past block_size) in file order
@@ -146,8 +179,8 @@ int ga_io_set_error(int code, const char* msg) { return fail(code, msg ? msg : "
 int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
     if (!path || !out) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_open: NULL argument");
     *out = nullptr;
-    std::vector<uint8_t> file;
-    if (!read_file(path, file)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
+    FileView file;
+    if (!file.open(path)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
     std::vector<Block> blocks;
     uint64_t total = 0;
     std::string why;
@@ -163,7 +196,6 @@ int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
         }
     });
     if (bad.load()) { delete b; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": a BGZF block failed to inflate or its CRC32 does not match"); }
-    file.clear(); file.shrink_to_fit();
     // ---- header
     const uint8_t* d = b->data.data();
     const uint64_t n = b->data.size();

@@ -298,10 +298,11 @@ def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], ref
 
 
 def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: Sequence[dict], reference,
-                     contig: str = "c", plan: Optional[Plan] = None) -> Dict[str, str]:
+                     contig: str = "c", plan: Optional[Plan] = None, as_bytes: bool = False) -> Dict[str, str]:
     """Same for an already packed batch (batch.ReadBatch with dense qualities, e.g. from
     genome_files.pack_tumor_normal): names = list of str or (uint8 blob, int64 offsets); read_table = rows with name /
-    flag / dataset / pos / end for the planner; reference = str / bytes / uint8 array of the contig."""
+    flag / dataset / pos / end for the planner (not needed when `plan` is given); reference = str / bytes / uint8 array
+    of the contig; as_bytes leaves the six FASTQ texts as bytes (the file writer appends them as they are)."""
     import numpy as np
     import torch
     from . import batch as B
@@ -340,7 +341,8 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n)
     out, k0 = {}, 0
     for name, rd, _ in groups:
-        out[name] = text[int(off[k0]):int(off[k0 + len(rd)])].decode("ascii")
+        piece = text[int(off[k0]):int(off[k0 + len(rd)])]
+        out[name] = piece if as_bytes else piece.decode("ascii")
         k0 += len(rd)
     counts = dres.sess_counts.view(-1, 4)[:sessions.n_sessions].cpu().numpy()
     out["statistics"] = statistics_text(contig, plan, counts)

@@ -42,7 +42,7 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
     fasta = GF.FastaFile(ref_genome_file)
     outs = {("T", "1"): tumor_output_fastq + ".1.fastq", ("T", "2"): tumor_output_fastq + ".2.fastq",
             ("N", "1"): normal_output_fastq + ".1.fastq", ("N", "2"): normal_output_fastq + ".2.fastq"}
-    handles = {k: open(p, "w") for k, p in outs.items()}       # truncated first, as the reference does (:652-655)
+    handles = {k: open(p, "wb") for k, p in outs.items()}      # truncated first, as the reference does (:652-655)
     singles = {"T": [], "N": []}
     stats_parts = []
     n_reads = n_sessions = 0
@@ -58,7 +58,7 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
                 if cb.batch.n_reads == 0:
                     stats_parts.append((contig, plan, [[0, 0, 0, 0]] * len(plan.sessions)))
                     continue
-                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan)
+                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan, as_bytes=True)
                 for p in "TN":
                     handles[(p, "1")].write(got[f"{p}.1"])
                     handles[(p, "2")].write(got[f"{p}.2"])
@@ -70,10 +70,10 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
         for h in handles.values():
             h.close()
         fasta.close()
-    if any("".join(v) for v in singles.values()):                  # write_single_end_reads opens both files (:603-605)
-        with open(tumor_output_fastq + ".single_end.fastq", "w") as t, open(normal_output_fastq + ".single_end.fastq", "w") as n:
-            t.write("".join(singles["T"]))
-            n.write("".join(singles["N"]))
+    if any(b"".join(v) for v in singles.values()):                 # write_single_end_reads opens both files (:603-605)
+        with open(tumor_output_fastq + ".single_end.fastq", "wb") as t, open(normal_output_fastq + ".single_end.fastq", "wb") as n:
+            t.write(b"".join(singles["T"]))
+            n.write(b"".join(singles["N"]))
     if record_statistics:
         with open(f"{normal_bam_file}.statistics.txt", "w") as fh:
             fh.write(statistics_text(stats_parts))
