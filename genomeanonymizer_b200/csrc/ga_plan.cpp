@@ -17,7 +17,7 @@ extern "C" int ga_io_set_error(int code, const char* msg);   // ga_genome_io.cpp
 struct ga_plan {
     std::vector<int32_t> s_first, s_last, s_window;
     std::vector<int32_t> pairs;      // 5 per row
-    std::vector<int32_t> singles;    // 3 per row
+    std::vector<int32_t> singles;    // 4 per row: dataset, read, version, pairs written before it was stored
 };
 
 namespace {
@@ -37,7 +37,9 @@ struct Planner {
     ga_plan* plan;
 
     // to_pair_anonymized_reads: insertion-ordered map name -> [mate 1, mate 2] (a popped name re-enters at the end)
-    struct Entry { int32_t name; int64_t slot[2]; bool alive; };
+    struct Entry { int32_t name; int64_t slot[2]; bool alive; int64_t ins_at; };
+    // ins_at: number of pairs that were (or, for a region's deferred records, will be) in the file before a pair completed by
+    // this entry's read would be written - where a mate carried over from an earlier contig joins it
     std::vector<Entry> entries;
     std::vector<int32_t> entry_of;                         // name id -> index into entries, -1 when absent
     std::vector<uint8_t> written;                          // written_read_ids
@@ -62,10 +64,11 @@ struct Planner {
         }
     }
 
-    int64_t* store(int32_t name, int m, int64_t value) {   // add_*_to_collection: an occupied slot keeps its read
+    int64_t* store(int32_t name, int m, int64_t value, int64_t ins_at, int32_t* entry = nullptr) {   // add_*_to_collection: an occupied slot keeps its read
         int32_t k = entry_of[name];
-        if (k < 0) { k = (int32_t)entries.size(); entries.push_back({name, {kNone, kNone}, true}); entry_of[name] = k; }
+        if (k < 0) { k = (int32_t)entries.size(); entries.push_back({name, {kNone, kNone}, true, ins_at}); entry_of[name] = k; }
         if (entries[k].slot[m] == kNone) entries[k].slot[m] = value;
+        if (entry) *entry = k;
         return entries[k].slot;
     }
     void pop(int32_t name) {
@@ -137,8 +140,9 @@ struct Planner {
         for (const Yield& y : ys) {
             if (y.m1 >= 0 && y.m2 >= 0) { write_pair(y.name, slot_of(y.m1, s), slot_of(y.m2, s), plan->pairs); continue; }   // SR.py:310-312
             int64_t* slot = nullptr;
-            if (y.m1 >= 0) slot = store(y.name, 0, slot_of(y.m1, s));                                                        // SR.py:320-333
-            if (y.m2 >= 0) slot = store(y.name, 1, slot_of(y.m2, s));
+            const int64_t at = (int64_t)plan->pairs.size() / 5;
+            if (y.m1 >= 0) slot = store(y.name, 0, slot_of(y.m1, s), at);                                                    // SR.py:320-333
+            if (y.m2 >= 0) slot = store(y.name, 1, slot_of(y.m2, s), at);
             if (slot && slot[0] != kNone && slot[1] != kNone) {                                                              // SR.py:348-359
                 const int64_t s0 = slot[0], s1 = slot[1];
                 write_pair(y.name, s0, s1, plan->pairs);
@@ -173,11 +177,15 @@ struct Planner {
     }
 
     // pair_unmapped_or_non_pileup_pairs_and_write (SR.py:375-406) for one island that is yielded singly
+    std::vector<int32_t> region_entries;                   // entries first stored by the current region: ins_at still relative
     void pass_through(const std::vector<int32_t>& idx, const Island* isl, std::vector<int32_t>& deferred) {
         if (!isl) return;
         for (size_t k = isl->begin; k < isl->end_; ++k) {
             const int32_t i = idx[k];
-            int64_t* slot = store(name_id[i], mate(i), slot_of(i, -1));
+            const size_t n_before = entries.size();
+            int32_t ent = -1;
+            int64_t* slot = store(name_id[i], mate(i), slot_of(i, -1), (int64_t)deferred.size() / 5, &ent);
+            if (entries.size() != n_before) region_entries.push_back(ent);
             if (slot[0] != kNone && slot[1] != kNone) write_pair(name_id[i], slot[0], slot[1], deferred);   // stays in the collection until the end (SR.py:737-741)
         }
     }
@@ -188,6 +196,7 @@ struct Planner {
         overlapping(0, start, stop, t_idx);
         overlapping(1, start, stop, n_idx);
         if (t_idx.empty() && n_idx.empty()) return;
+        region_entries.clear();
         std::vector<Island> ti, ni;
         islands(t_idx, ti);
         islands(n_idx, ni);
@@ -213,6 +222,8 @@ struct Planner {
             }
         }
         // the region's own records reach the files behind those of its island sessions (stream buffering)
+        const int64_t base = (int64_t)plan->pairs.size() / 5;
+        for (const int32_t k : region_entries) entries[k].ins_at += base;
         plan->pairs.insert(plan->pairs.end(), deferred.begin(), deferred.end());
     }
 };
@@ -281,8 +292,8 @@ int ga_plan_sample(int64_t n_reads, int64_t n_tumor, const int32_t* pos, const i
     for (const Planner::Entry& e : P.entries) {                // write_single_end_reads (SR.py:603-622), insertion order
         if (!e.alive || P.written[e.name]) continue;
         const int64_t v = e.slot[0] != kNone ? e.slot[0] : e.slot[1];
-        const int32_t row[3] = {P.dataset(slot_read(v)), slot_read(v), slot_version(v)};
-        plan->singles.insert(plan->singles.end(), row, row + 3);
+        const int32_t row[4] = {P.dataset(slot_read(v)), slot_read(v), slot_version(v), (int32_t)e.ins_at};
+        plan->singles.insert(plan->singles.end(), row, row + 4);
     }
     *out = plan;
     return GA_IO_OK;
@@ -291,7 +302,7 @@ int ga_plan_sample(int64_t n_reads, int64_t n_tumor, const int32_t* pos, const i
 void ga_plan_free(ga_plan* p) { delete p; }
 int64_t ga_plan_n_sessions(const ga_plan* p) { return p ? (int64_t)p->s_first.size() : 0; }
 int64_t ga_plan_n_pairs(const ga_plan* p) { return p ? (int64_t)p->pairs.size() / 5 : 0; }
-int64_t ga_plan_n_singles(const ga_plan* p) { return p ? (int64_t)p->singles.size() / 3 : 0; }
+int64_t ga_plan_n_singles(const ga_plan* p) { return p ? (int64_t)p->singles.size() / 4 : 0; }
 void ga_plan_sessions(const ga_plan* p, int32_t* first, int32_t* last, int32_t* window) {
     if (!p) return;
     const size_t n = p->s_first.size();

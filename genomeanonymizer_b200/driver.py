@@ -298,11 +298,16 @@ def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], ref
 
 
 def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: Sequence[dict], reference,
-                     contig: str = "c", plan: Optional[Plan] = None, as_bytes: bool = False) -> Dict[str, str]:
+                     contig: str = "c", plan: Optional[Plan] = None, as_bytes: bool = False, carry: Optional[dict] = None) -> Dict[str, str]:
     """Same for an already packed batch (batch.ReadBatch with dense qualities, e.g. from
     genome_files.pack_tumor_normal): names = list of str or (uint8 blob, int64 offsets); read_table = rows with name /
     flag / dataset / pos / end for the planner (not needed when `plan` is given); reference = str / bytes / uint8 array
-    of the contig; as_bytes leaves the six FASTQ texts as bytes (the file writer appends them as they are)."""
+    of the contig; as_bytes leaves the six FASTQ texts as bytes (the file writer appends them as they are).
+    carry: the sample's unpaired reads so far, {name bytes: (mate, dataset, FASTQ record)} in insertion order - the
+    reference keeps them across contigs (to_pair_anonymized_reads, short_read_tumor_normal_anonymizer.py:646) and writes a
+    pair the moment its second mate is processed.  With carry given (names must be the (blob, offsets) form and the plan
+    a native one, whose singles say where such a pair goes) the unpaired reads of this contig join it instead of being
+    returned as single-end text, and pairs completed by a carried mate are spliced into the pair files."""
     import numpy as np
     import torch
     from . import batch as B
@@ -322,7 +327,8 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     by_key = np.argsort(mod_key, kind="stable")
     sorted_key = mod_key[by_key]
     P = np.asarray(plan.pairs, np.int64).reshape(-1, 5)
-    S = np.asarray(plan.singles, np.int64).reshape(-1, 3)
+    S = np.asarray(plan.singles, np.int64)
+    S = S.reshape(-1, S.shape[1] if S.ndim == 2 and S.shape[0] else 3)
     # items in file order: T.1, T.2, N.1, N.2, T.single_end, N.single_end - each file is one slice of the rendered text
     groups = []
     for d in (0, 1):
@@ -339,11 +345,46 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     hit[hit] = sorted_key[at[hit]] == want[hit]
     item_rec = np.where(hit, by_key[np.minimum(at, max(n - 1, 0))] if n else 0, -1).astype(np.int32)
     text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n)
-    out, k0 = {}, 0
-    for name, rd, _ in groups:
-        piece = text[int(off[k0]):int(off[k0 + len(rd)])]
-        out[name] = piece if as_bytes else piece.decode("ascii")
-        k0 += len(rd)
+    starts = np.concatenate([[0], np.cumsum([len(g[1]) for g in groups])]).astype(np.int64)
+    piece = lambda a, b: text[int(off[a]):int(off[b])]                # records [a, b) of the item list
+    out = {}
+    if carry is None:
+        for g, (name, rd, _) in enumerate(groups):
+            out[name] = piece(starts[g], starts[g + 1])
+    else:
+        blob, noff = names
+        flags = np.asarray(batch.len_flag) >> 16
+        splice = {0: [], 1: []}                                       # dataset -> [(pairs of the contig before it, mate-1 text, mate-2 text)]
+        for d in (0, 1):
+            g = 4 + d                                                 # this dataset's unpaired reads, in spill order
+            rows = S[S[:, 0] == d]
+            for k in range(len(rows)):
+                r = int(rows[k, 1])
+                nm = bytes(blob[int(noff[r]):int(noff[r + 1])])
+                m = 0 if int(flags[r]) & 0x40 else 1
+                rec = piece(starts[g] + k, starts[g] + k + 1)
+                held = carry.get(nm)
+                if held is None:
+                    carry[nm] = (m, d, rec)
+                elif held[0] != m and held[1] == d:                   # the second mate of a pair whose first mate came earlier
+                    del carry[nm]
+                    at = int(rows[k, 3]) if rows.shape[1] > 3 else len(P)
+                    splice[d].append((at, held[2] if held[0] == 0 else rec, rec if held[0] == 0 else held[2]))
+        for d in (0, 1):
+            before = np.concatenate([[0], np.cumsum(P[:, 0] == d)]) if len(P) else np.zeros(1, np.int64)   # pairs of d among the first k pairs
+            for m in (0, 1):
+                g = 2 * d + m
+                parts, cur = [], 0
+                for at, t1, t2 in sorted(splice[d], key=lambda t: t[0]):   # stable: equal positions keep their order
+                    k = int(before[min(at, len(P))])
+                    parts.append(piece(starts[g] + cur, starts[g] + k))
+                    parts.append(t1 if m == 0 else t2)
+                    cur = k
+                parts.append(piece(starts[g] + cur, starts[g + 1]))
+                out[groups[g][0]] = b"".join(parts)
+            out[groups[4 + d][0]] = b""
+    if not as_bytes:
+        out = {k: v.decode("ascii") for k, v in out.items()}
     counts = dres.sess_counts.view(-1, 4)[:sessions.n_sessions].cpu().numpy()
     out["statistics"] = statistics_text(contig, plan, counts)
     out["_plan"] = plan

@@ -124,7 +124,7 @@ def plan_contig(cb: "ContigBatch", windows, contig_len: int):
     try:
         ns, npairs, nsing = int(L.ga_plan_n_sessions(h)), int(L.ga_plan_n_pairs(h)), int(L.ga_plan_n_singles(h))
         first, last, win = np.zeros(ns, np.int32), np.zeros(ns, np.int32), np.zeros(ns, np.int32)
-        pairs, singles = np.zeros((npairs, 5), np.int32), np.zeros((nsing, 3), np.int32)
+        pairs, singles = np.zeros((npairs, 5), np.int32), np.zeros((nsing, 4), np.int32)
         L.ga_plan_sessions(h, first.ctypes.data, last.ctypes.data, win.ctypes.data)
         L.ga_plan_pairs(h, pairs.ctypes.data)
         L.ga_plan_singles(h, singles.ctypes.data)

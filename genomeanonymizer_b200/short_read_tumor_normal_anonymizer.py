@@ -15,9 +15,9 @@ FASTQ renderer.  Outputs, named as the reference names them:
 Differences that are stated rather than hidden: `cpus` is the number of host threads of the file decoders (the
 reference forks one process per sample); `enhance_parallelization` (the reference splits a sample's BAMs into
 per-region files for its process pool, :795-885) has no counterpart - one GPU pass needs no such split - and is
-accepted and ignored; mates aligned to different contigs are planned per contig and therefore reach the
-single-end files (the reference pairs them when the second mate is fetched); VCF records other than plain SNV /
-DEL / INS / MNV are rejected (genome_files.read_vcf).  There is no CPU fallback: without a CUDA device the engine
+accepted and ignored; breakend VCF records are rejected (genome_files.read_vcf).  Mates aligned to different contigs
+are paired as the reference pairs them: unpaired reads are carried from contig to contig and a pair is written where
+its second mate is processed.  There is no CPU fallback: without a CUDA device the engine
 constructor raises.
 """
 import logging
@@ -43,7 +43,7 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
     outs = {("T", "1"): tumor_output_fastq + ".1.fastq", ("T", "2"): tumor_output_fastq + ".2.fastq",
             ("N", "1"): normal_output_fastq + ".1.fastq", ("N", "2"): normal_output_fastq + ".2.fastq"}
     handles = {k: open(p, "wb") for k, p in outs.items()}      # truncated first, as the reference does (:652-655)
-    singles = {"T": [], "N": []}
+    carry = {}                                                 # to_pair_anonymized_reads (:646): unpaired reads, kept across contigs
     stats_parts = []
     n_reads = n_sessions = 0
     try:
@@ -58,11 +58,10 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
                 if cb.batch.n_reads == 0:
                     stats_parts.append((contig, plan, [[0, 0, 0, 0]] * len(plan.sessions)))
                     continue
-                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan, as_bytes=True)
+                got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan, as_bytes=True, carry=carry)
                 for p in "TN":
                     handles[(p, "1")].write(got[f"{p}.1"])
                     handles[(p, "2")].write(got[f"{p}.2"])
-                    singles[p].append(got[f"{p}.single_end"])
                 stats_parts.append((contig, plan, got["_counts"]))
                 n_reads += cb.batch.n_reads
                 n_sessions += len(plan.sessions)
@@ -70,10 +69,10 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
         for h in handles.values():
             h.close()
         fasta.close()
-    if any(b"".join(v) for v in singles.values()):                 # write_single_end_reads opens both files (:603-605)
+    if carry:                                                      # write_single_end_reads opens both files (:603-605)
         with open(tumor_output_fastq + ".single_end.fastq", "wb") as t, open(normal_output_fastq + ".single_end.fastq", "wb") as n:
-            t.write(b"".join(singles["T"]))
-            n.write(b"".join(singles["N"]))
+            for _, d, rec in carry.values():                       # insertion order of the collection (:606-622)
+                (t if d == 0 else n).write(rec)
     if record_statistics:
         with open(f"{normal_bam_file}.statistics.txt", "w") as fh:
             fh.write(statistics_text(stats_parts))

@@ -40,7 +40,10 @@ int64_t ga_plan_n_singles(const ga_plan* p);
 /* sessions: first / last / window index (-1: island session between windows), each [n_sessions]. */
 void ga_plan_sessions(const ga_plan* p, int32_t* first, int32_t* last, int32_t* window);
 /* pairs: rows of 5 - dataset, read of mate 1, its session version, read of mate 2, its session version - in write order;
- * singles: rows of 3 - dataset, read, version - in the order the reference spills them to the single-end files. */
+ * singles: rows of 4 - dataset, read, version, and the number of pairs of this contig that precede the place where a pair
+ * completed by this read is written (the reference keeps unpaired reads across contigs, to_pair_anonymized_reads, and
+ * writes such a pair the moment the second mate is processed) - in the order the reference spills them to the
+ * single-end files. */
 void ga_plan_pairs(const ga_plan* p, int32_t* rows);
 void ga_plan_singles(const ga_plan* p, int32_t* rows);
 

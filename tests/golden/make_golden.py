@@ -226,14 +226,15 @@ def random_cases():
     return cases
 
 
-def run_genome(case, vcf_records):
-    """Whole-sample orchestration of the reference (anonymize_genome) under functional fakes."""
-    contig = case["contig"]
-    t = [seg(r, contig) for r in case["reads"] if r["dataset"] == 0]
-    n = [seg(r, contig) for r in case["reads"] if r["dataset"] == 1]
-    pysam.register_alignment_file("T.bam", t, [contig])
-    pysam.register_alignment_file("N.bam", n, [contig])
-    pysam.register_fasta("ref.fa", {contig: case["reference"]})
+def run_genome(case, vcf_records, more_cases=()):
+    """Whole-sample orchestration of the reference (anonymize_genome) under functional fakes; more_cases = further
+    contigs of the same sample (each a case with its own contig name), in genome order."""
+    cases = [case] + list(more_cases)
+    t = [seg(r, c["contig"]) for c in cases for r in c["reads"] if r["dataset"] == 0]
+    n = [seg(r, c["contig"]) for c in cases for r in c["reads"] if r["dataset"] == 1]
+    pysam.register_alignment_file("T.bam", t, [c["contig"] for c in cases])
+    pysam.register_alignment_file("N.bam", n, [c["contig"] for c in cases])
+    pysam.register_fasta("ref.fa", {c["contig"]: c["reference"] for c in cases})
     variant_extractor.register_vcf("s.vcf", vcf_records)
     fasta = pysam.FastaFile("ref.fa")
     windows = SR.get_windows(variant_extractor.VariantExtractor("s.vcf"), SR.get_ref_idxs(fasta))
@@ -288,6 +289,40 @@ def genome_cases():
         out.append({"case": case, "vcf": [[v.contig, v.pos, v.end, v.length, v.ref, v.alt, v.variant_type.name] for v in vcf],
                     "expected": res})
     return out
+
+
+def two_contig_case():
+    """One sample over two contigs with pairs whose mates lie on different contigs (mate 1 on c1, mate 2 on c2): the
+    reference keeps unpaired reads across contigs and writes such a pair when the second mate is processed."""
+    a = synth.make_case(31, name="genome-two-contigs-c1", contig_len=9000, n_pairs=(260, 240), read_len=70,
+                        somatic_positions=[2500, 6000], snp_rate=4e-3, indel_rate=1e-3)
+    b = synth.make_case(32, name="genome-two-contigs-c2", contig_len=8000, n_pairs=(240, 230), read_len=70,
+                        somatic_positions=[3200], snp_rate=4e-3, indel_rate=1e-3)
+    a["contig"], b["contig"] = "c1", "c2"
+    b["reads"] = [dict(r, name=r["name"] + "b") for r in b["reads"]]      # read names are unique within a sample
+    for ds in (0, 1):
+        # every 9th pair of c1 keeps only its first mate, every 9th pair of c2 only its second, renamed to the c1 pair
+        names_a = sorted({r["name"] for r in a["reads"] if r["dataset"] == ds})[::9]
+        names_b = sorted({r["name"] for r in b["reads"] if r["dataset"] == ds})[::9]
+        pairs = list(zip(names_a, names_b))
+        ren = {nb: na for na, nb in pairs}
+        keep_a = {na for na, _ in pairs}
+        a["reads"] = [r for r in a["reads"] if not (r["dataset"] == ds and r["name"] in keep_a and not (r["flag"] & 0x40))]
+        out = []
+        for r in b["reads"]:
+            if r["dataset"] == ds and r["name"] in ren:
+                if r["flag"] & 0x40:
+                    continue                                     # its first mate goes
+                r = dict(r, name=ren[r["name"]])
+            out.append(r)
+        b["reads"] = out
+    vcf = []
+    for c in (a, b):
+        for w in c["windows"]:
+            k = w["keep"]
+            vcf.append(VariantRecord(c["contig"], k["pos"] + 1, k["pos"] + 1, 1, c["reference"][k["pos"]].upper(), k["allele"], VariantType.SNV))
+    res = run_genome(a, vcf, [b])
+    return {"cases": [a, b], "vcf": [[v.contig, v.pos, v.end, v.length, v.ref, v.alt, v.variant_type.name] for v in vcf], "expected": res}
 
 
 def window_kats():
@@ -345,7 +380,7 @@ def main():
         print(g["case"]["name"], {k: (len(v) if v else v) for k, v in g["expected"]["files"].items()})
     with open(os.path.join(HERE, "genome_cases.json"), "w") as f:
         json.dump({"generator": "tests/golden/make_golden.py", "cases": gen, "windows_kat": window_kats(),
-                   "sv_windows_kat": sv_window_kats()}, f,
+                   "sv_windows_kat": sv_window_kats(), "two_contigs": two_contig_case()}, f,
                   separators=(",", ":"))
 
 

@@ -205,3 +205,33 @@ def test_entry_point_with_the_method_object_two_contigs_and_two_samples(tmp_path
     rows = lambda text: [ln for ln in text.split("\n") if ln and ln[0] != "#" and not ln.startswith("outside")]
     stats = open(n + ".statistics.txt").read()
     assert rows(stats) == rows(g0["N.bam.statistics.txt"]) + [ln.replace("c\t", "d\t", 1) for ln in rows(g1["N.bam.statistics.txt"])]
+
+
+@pytest.mark.gpu
+def test_pairs_split_over_two_contigs_are_written_where_the_reference_writes_them(tmp_path):
+    """tests/golden "two_contigs": the reference's anonymize_genome on a two-contig sample in which every ninth pair has
+    its first mate on c1 and its second on c2.  The reference keeps unpaired reads across contigs and writes the pair
+    when the second mate is processed; the entry point (per-contig plans + carried reads) must write the same files."""
+    from genomeanonymizer_b200.engine import Engine
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import name_output, run_short_read_tumor_normal_anonymizer
+    two = GOLD["two_contigs"]
+    a, b = two["cases"]
+    contigs = [(a["contig"], len(a["reference"])), (b["contig"], len(b["reference"]))]
+    reads = [dict(r, contig=a["contig"]) for r in a["reads"]] + [dict(r, contig=b["contig"]) for r in b["reads"]]
+    t, n = str(tmp_path / "T.bam"), str(tmp_path / "N.bam")
+    H.write_bam(t, contigs, [r for r in reads if r["dataset"] == 0])
+    H.write_bam(n, contigs, [r for r in reads if r["dataset"] == 1])
+    fa, vc = str(tmp_path / "ref.fa"), str(tmp_path / "s.vcf")
+    H.write_fasta(fa, [(a["contig"], a["reference"]), (b["contig"], b["reference"])])
+    H.write_vcf(vc, two["vcf"])
+    eng = Engine(0)
+    try:
+        run_short_read_tumor_normal_anonymizer([vc], [(t, n)], fa, eng, [(name_output(t), name_output(n))], True, 2, False)
+    finally:
+        eng.close()
+    for name, text in two["expected"]["files"].items():
+        path = os.path.join(str(tmp_path), name)
+        if text is None:
+            assert not os.path.exists(path), name
+        else:
+            assert open(path).read() == text, name
