@@ -211,6 +211,37 @@ def bench_bam_decode(n_reads=400_000, read_len=150):
             "reads_per_s": n_reads / (best_open + best_pack), "inflated_gbs": len(stream) / (best_open + best_pack) / 1e9}
 
 
+def bench_file_path(device_index, n_pairs=20000):
+    """Level (iii) of SURVEY.md 8(d): tumor / normal BAM + VCF + FASTA -> the reference's FASTQ and statistics files through
+    run_short_read_tumor_normal_anonymizer (C++ readers, native plan, one masking pass, device FASTQ text).  The sample is
+    a seeded synthetic one written by the test-side BAM / FASTA / VCF writers; the second of two runs is reported."""
+    import shutil, tempfile
+    from genomeanonymizer_b200 import synth
+    from genomeanonymizer_b200.engine import Engine
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import run_short_read_tumor_normal_anonymizer
+    from tests import helpers as H
+    eng = Engine(device_index)                                           # its own engine: the sample brings its own reference
+    contig_len = 150 * 2 * n_pairs // 30                                 # ~30x per dataset
+    case = synth.make_case(seed=9, contig_len=contig_len, n_pairs=(n_pairs, n_pairs), read_len=150,
+                           somatic_positions=list(range(3000, contig_len - 3000, 4000)))
+    tmp = tempfile.mkdtemp(prefix="ga_files_")
+    try:
+        vcf = [[case["contig"], w["keep"]["pos"] + 1, w["keep"]["pos"] + 1, 1, "N", w["keep"]["allele"], "SNV"] for w in case["windows"]]
+        t, n, fa, vc = H.write_sample_files(tmp, case, vcf)
+        best = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            res = run_short_read_tumor_normal_anonymizer([vc], [(t, n)], fa, eng, [(os.path.join(tmp, "T.out"), os.path.join(tmp, "N.out"))], True, 0, False)
+            best = min(best, time.perf_counter() - t0)
+        out_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.endswith(".fastq"))
+        return {"api": "run_short_read_tumor_normal_anonymizer (BAM + VCF + FASTA -> FASTQ + statistics files)", "reads": res[0]["reads"],
+                "sessions": res[0]["sessions"], "ms": best * 1e3, "reads_per_s": res[0]["reads"] / best, "fastq_bytes": out_bytes,
+                "host_threads": os.cpu_count()}
+    finally:
+        eng.close()
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def bench_fastq(eng, cfg, dev, n_w, peak):
     """ga_fastq_layout + ga_fastq_render over every read of the first n_w windows: masked where a session modified
     the read (lowest record index wins), as it came in otherwise.  Dense synthetic qualities, 10-character names."""
@@ -477,6 +508,12 @@ def main():
     bam = None
     if rank == 0 and world == 1 and not args.no_bam:
         bam = bench_bam_decode()
+    files = None
+    if rank == 0 and world == 1 and not args.no_bam:
+        try:
+            files = bench_file_path(local)
+        except Exception as exc:                                          # a side measurement must not take the bench line down
+            files = {"error": repr(exc)}
     fastq = None
     if rank == 0 and world == 1 and not args.no_fastq:
         fastq = bench_fastq(eng, cfg, dev, min(n_w, args.fastq_windows), peak)
@@ -514,7 +551,7 @@ def main():
                            "host_numa_binding": numa,
                            "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
                 "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "bam_decode": bam, "gpu_launches": total_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "bam_decode": bam, "file_path": files, "gpu_launches": total_launches,
                 "clocks": sampler.summary(), "parity_vs_oracle_on_sample": parity}
         print(json.dumps(line))
     if world > 1:
