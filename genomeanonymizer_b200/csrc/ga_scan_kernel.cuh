@@ -31,6 +31,19 @@ constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean 
 constexpr uint32_t kCntOverflow = 0xffffffffu;
 constexpr int kScanThreads = 256;
 
+// Nibble masks of a partial 32-base unit: row nv = the four 8-base words of a unit of which only the first nv bases exist.
+struct UnitMasks { uint32_t m[32][4]; };
+constexpr UnitMasks make_unit_masks() {
+    UnitMasks t{};
+    for (int nv = 0; nv < 32; ++nv)
+        for (int k = 0; k < 4; ++k) {
+            const int left = nv - 8 * k;
+            t.m[nv][k] = left >= 8 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> ((8 - left) * 4)));
+        }
+    return t;
+}
+__constant__ UnitMasks c_unit_masks = make_unit_masks();
+
 struct ObsRec { int32_t col; uint32_t meta; uint32_t read_alen; int32_t irp; uint32_t sig0, sig1, qord, pad1; };   // qord: the read's ordinal among the item's reads with an I/D op
 static_assert(sizeof(ObsRec) == 32, "ObsRec is two 16-byte stores");
 
@@ -214,10 +227,10 @@ __device__ __forceinline__ uint32_t issue_tile(const ItemCtx& c, const TileMeta&
     const uint32_t L = meta_len(m);
     const uint32_t units = valid ? (L + 31u) >> 5 : 0u;
     const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);
-    const bool ok = !valid || (m.so >= sof && m.so - sof + units <= (uint32_t)kTileUnits);
-    const uint32_t end = valid ? m.so - sof + units : 0u;
-    const uint32_t total = __reduce_max_sync(0xffffffffu, ok ? end : 0u);
-    const uint32_t staged = (tma_ok && total > 0u && __all_sync(0xffffffffu, ok)) ? 1u : 0u;
+    const uint32_t rel = m.so - sof;                                  // huge when the record lies before the tile's first one
+    const uint32_t end = valid ? (rel <= (uint32_t)kTileUnits ? rel + units : 0xffffffffu) : 0u;
+    const uint32_t total = __reduce_max_sync(0xffffffffu, end);       // units from the first record to the end of the last
+    const uint32_t staged = (tma_ok && total > 0u && total <= (uint32_t)kTileUnits) ? 1u : 0u;
     if (staged && lane == 0) {
         mbar_expect_tx(&c.ws->bar[b], total * 16u);
         bulk_g2s(c.ws->ring[b], c.B.seq4 + 16ull * sof, total * 16u, &c.ws->bar[b]);
@@ -281,10 +294,9 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
             const int u = full, nv = L & 31;                             // nv valid nibbles in this unit
             const uint4 v = rec4[u];
             const uint32_t r1 = rp[4 * u + 1], r2 = rp[4 * u + 2], r3 = rp[4 * u + 3], r4 = rp[4 * u + 4];
-            const unsigned long long lo = nv >= 16 ? ~0ull : ((1ull << (4 * nv)) - 1ull);
-            const unsigned long long hi = nv <= 16 ? 0ull : ((1ull << (4 * (nv - 16))) - 1ull);
-            const uint32_t x0 = (v.x ^ __funnelshift_r(prev, r1, sh)) & (uint32_t)lo, x1 = (v.y ^ __funnelshift_r(r1, r2, sh)) & (uint32_t)(lo >> 32);
-            const uint32_t x2 = (v.z ^ __funnelshift_r(r2, r3, sh)) & (uint32_t)hi, x3 = (v.w ^ __funnelshift_r(r3, r4, sh)) & (uint32_t)(hi >> 32);
+            const uint32_t* um = c_unit_masks.m[nv];                     // usually the same row for the whole warp
+            const uint32_t x0 = (v.x ^ __funnelshift_r(prev, r1, sh)) & um[0], x1 = (v.y ^ __funnelshift_r(r1, r2, sh)) & um[1];
+            const uint32_t x2 = (v.z ^ __funnelshift_r(r2, r3, sh)) & um[2], x3 = (v.w ^ __funnelshift_r(r3, r4, sh)) & um[3];
             wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * u);
         }
     }
@@ -295,7 +307,8 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
         const uint32_t rw = rec[k];
         const int nib = rel + 8 * k;
         const uint32_t fw = __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u);
-        uint32_t x = (rw ^ fw) & tail_mask(L, k);
+        uint32_t x = rw ^ fw;
+        if (8 * k + 8 > L) x &= tail_mask(L, k);                        // only the read's last word has padding nibbles
         const int colb = pos - c.col_begin + 8 * k;
         while (x) {
             const int n = (__ffs(x) - 1) >> 2;
