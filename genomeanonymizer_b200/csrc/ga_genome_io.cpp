@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -162,9 +163,72 @@ struct ga_bam {
     } data;
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
-    std::vector<std::vector<uint64_t>> by_ref;    // per reference: offsets (of refID, i.e. past block_size) in file order
+    std::vector<std::vector<uint64_t>> by_ref;    // per reference: offsets (of refID, i.e. past block_size) into data, in file order
     int64_t n_records = 0;
+    // Large files whose records are grouped by reference (every sorted BAM) are not kept inflated: open() only walks
+    // them once, window by window, to find each reference's span of the uncompressed stream, and the records of ONE
+    // reference at a time are inflated when they are asked for (memory = one contig, not the file).
+    bool lazy = false;
+    FileView file;                                // stays mapped in lazy mode
+    std::vector<Block> blocks;
+    uint64_t total = 0;                           // size of the uncompressed stream
+    int threads = 0;
+    struct Span { uint64_t u_begin = 0, u_end = 0; int64_t n = 0; };
+    std::vector<Span> spans;                      // per reference, lazy mode
+    int loaded_ref = -1;
 };
+
+namespace {
+
+// Inflates the blocks that hold bytes [u_lo, u_hi) of the uncompressed stream; *base = stream offset of out[0].
+bool inflate_range(const FileView& file, const std::vector<Block>& blocks, uint64_t u_lo, uint64_t u_hi, int threads, ga_bam::Bytes& out, uint64_t* base) {
+    if (u_hi <= u_lo || blocks.empty()) { out.resize(0); *base = u_lo; return true; }
+    size_t lo = (size_t)(std::upper_bound(blocks.begin(), blocks.end(), u_lo, [](uint64_t v, const Block& b) { return v < b.out_off; }) - blocks.begin());
+    lo = lo ? lo - 1 : 0;
+    size_t hi = (size_t)(std::lower_bound(blocks.begin(), blocks.end(), u_hi, [](const Block& b, uint64_t v) { return b.out_off < v; }) - blocks.begin());
+    *base = blocks[lo].out_off;
+    const uint64_t end = hi < blocks.size() ? blocks[hi].out_off : blocks.back().out_off + blocks.back().out_size;
+    out.resize(end - *base);
+    std::atomic<int> bad(0);
+    parallel_for((int64_t)(hi - lo), n_workers(threads), 64, [&](int64_t a, int64_t z) {
+        for (int64_t k = a; k < z; ++k) {
+            const Block& bl = blocks[lo + (size_t)k];
+            if (bl.out_size == 0) continue;                               // the EOF marker block
+            if (!inflate_block(file.data() + bl.in_off, bl.in_size, out.data() + (bl.out_off - *base), bl.out_size)) bad.store(1);
+        }
+    });
+    return !bad.load();
+}
+
+// Parses "BAM\1", the header text and the reference dictionary from the head of the stream; returns the offset of the
+// first alignment record, 0 when the buffer does not hold the whole header yet, -1 when it is not a BAM header.
+int64_t parse_header(const uint8_t* d, uint64_t n, std::vector<std::string>& names, std::vector<int64_t>& lens) {
+    names.clear(); lens.clear();
+    if (n < 12) return 0;
+    if (std::memcmp(d, "BAM\1", 4) != 0) return -1;
+    uint64_t off = 4;
+    const uint32_t l_text = le32(d + off); off += 4;
+    if (off + l_text + 4 > n) return 0;
+    off += l_text;
+    const uint32_t n_ref = le32(d + off); off += 4;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (off + 4 > n) return 0;
+        const uint32_t l_name = le32(d + off); off += 4;
+        if (l_name == 0) return -1;
+        if (off + l_name + 4 > n) return 0;
+        names.emplace_back(reinterpret_cast<const char*>(d + off), l_name - 1);
+        off += l_name;
+        lens.push_back((int64_t)le32(d + off)); off += 4;
+    }
+    return (int64_t)off;
+}
+
+uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::strtoull(v, nullptr, 10) : dflt;
+}
+
+}  // namespace
 
 struct ga_fasta {
     std::vector<std::string> names;
@@ -176,57 +240,146 @@ extern "C" {
 const char* ga_io_last_error(void) { return g_err.c_str(); }
 int ga_io_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 
+// Indexes the records in data[from, data.size()) per reference (one hop per record); data_base = stream offset of data[0].
+static int index_records(ga_bam* b, uint64_t from, const std::string& path) {
+    const uint8_t* d = b->data.data();
+    const uint64_t n = b->data.size();
+    const uint32_t n_ref = (uint32_t)b->ref_names.size();
+    uint64_t off = from;
+    while (off < n) {
+        if (off + 4 > n) return fail(GA_IO_ERR_FORMAT, path + ": truncated alignment record");
+        const uint32_t block_size = le32(d + off);
+        if (block_size < 32 || off + 4 + block_size > n) return fail(GA_IO_ERR_FORMAT, path + ": alignment record runs past the end of the stream");
+        const int32_t ref_id = (int32_t)le32(d + off + 4);
+        if (ref_id >= 0 && (uint32_t)ref_id < n_ref) b->by_ref[ref_id].push_back(off + 4);
+        else if (ref_id != -1) return fail(GA_IO_ERR_FORMAT, path + ": alignment record names a reference that is not in the header");
+        off += 4 + (uint64_t)block_size;
+    }
+    return GA_IO_OK;
+}
+
+// Lazy mode: one walk over the file, window by window, that finds the header and each reference's span of the
+// uncompressed stream.  *grouped = false when a reference's records come in more than one run (unsorted file).
+static int scan_spans(ga_bam* b, const std::string& path, bool* grouped) {
+    uint64_t window = std::max<uint64_t>(env_u64("GA_BAM_WINDOW_BYTES", 256ull << 20), 1u << 16);
+    ga_bam::Bytes buf;
+    uint64_t base = 0;
+    int64_t hdr = 0;
+    for (uint64_t want = window;; want *= 2) {                             // the header: grow until it is whole
+        if (!inflate_range(b->file, b->blocks, 0, std::min(b->total, want), b->threads, buf, &base))
+            return fail(GA_IO_ERR_FORMAT, path + ": a BGZF block failed to inflate or its CRC32 does not match");
+        hdr = parse_header(buf.data(), buf.size(), b->ref_names, b->ref_lens);
+        if (hdr < 0) return fail(GA_IO_ERR_FORMAT, path + ": BAM magic missing");
+        if (hdr > 0) break;
+        if (want >= b->total) return fail(GA_IO_ERR_FORMAT, path + ": truncated header");
+    }
+    const int32_t n_ref = (int32_t)b->ref_names.size();
+    b->spans.assign((size_t)n_ref, ga_bam::Span());
+    std::vector<uint8_t> seen((size_t)n_ref, 0);
+    *grouped = true;
+    int32_t last = -2;
+    uint64_t cur = (uint64_t)hdr;
+    while (cur < b->total) {
+        if (!inflate_range(b->file, b->blocks, cur, std::min(b->total, cur + window), b->threads, buf, &base))
+            return fail(GA_IO_ERR_FORMAT, path + ": a BGZF block failed to inflate or its CRC32 does not match");
+        const uint8_t* d = buf.data();
+        const uint64_t n = buf.size();
+        uint64_t p = cur - base;
+        bool progressed = false;
+        while (p + 4 <= n) {
+            const uint32_t bs = le32(d + p);
+            if (bs < 32) return fail(GA_IO_ERR_FORMAT, path + ": alignment record shorter than its fixed fields");
+            if (p + 4 + bs > n) break;                                   // continues in the next window
+            const int32_t ref = (int32_t)le32(d + p + 4);
+            if (ref < -1 || ref >= n_ref) return fail(GA_IO_ERR_FORMAT, path + ": alignment record names a reference that is not in the header");
+            if (ref != last) {
+                if (last >= 0) b->spans[last].u_end = base + p;
+                if (ref >= 0) {
+                    if (seen[ref]) *grouped = false;
+                    seen[ref] = 1;
+                    b->spans[ref].u_begin = base + p;
+                }
+                last = ref;
+            }
+            if (ref >= 0) b->spans[ref].n++;
+            b->n_records++;
+            p += 4 + (uint64_t)bs;
+            progressed = true;
+        }
+        if (!progressed) {
+            if (base + n >= b->total) return fail(GA_IO_ERR_FORMAT, path + ": alignment record runs past the end of the stream");
+            window *= 2;                                                 // a record longer than the window
+            continue;
+        }
+        cur = base + p;
+    }
+    if (last >= 0) b->spans[last].u_end = cur;
+    return GA_IO_OK;
+}
+
+// Lazy mode: makes the records of reference ref_id the loaded ones.
+static int ensure_loaded(const ga_bam* cb, int ref_id) {
+    ga_bam* b = const_cast<ga_bam*>(cb);                                 // the handle caches one contig; single-threaded use
+    if (!b->lazy || b->loaded_ref == ref_id) return GA_IO_OK;
+    for (auto& v : b->by_ref) { v.clear(); v.shrink_to_fit(); }
+    b->loaded_ref = -1;
+    const ga_bam::Span& sp = b->spans[(size_t)ref_id];
+    uint64_t base = 0;
+    if (!inflate_range(b->file, b->blocks, sp.u_begin, sp.u_end, b->threads, b->data, &base))
+        return fail(GA_IO_ERR_FORMAT, "a BGZF block failed to inflate or its CRC32 does not match");
+    if (sp.n) {
+        // only this reference's records: the span ends where the next reference begins
+        const uint64_t from = sp.u_begin - base, to = sp.u_end - base;
+        const uint8_t* d = b->data.data();
+        b->by_ref[(size_t)ref_id].reserve((size_t)sp.n);
+        for (uint64_t off = from; off < to;) {
+            const uint32_t bs = le32(d + off);
+            b->by_ref[(size_t)ref_id].push_back(off + 4);
+            off += 4 + (uint64_t)bs;
+        }
+    }
+    b->loaded_ref = ref_id;
+    return GA_IO_OK;
+}
+
 int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
     if (!path || !out) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_open: NULL argument");
     *out = nullptr;
-    FileView file;
-    if (!file.open(path)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
-    std::vector<Block> blocks;
-    uint64_t total = 0;
+    std::unique_ptr<ga_bam> b(new ga_bam());
+    b->threads = n_threads;
+    if (!b->file.open(path)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
     std::string why;
-    if (!index_bgzf(file, blocks, &total, &why)) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + why);
-    ga_bam* b = new ga_bam();
-    b->data.resize(total);
-    std::atomic<int> bad(0);
-    parallel_for((int64_t)blocks.size(), n_workers(n_threads), 64, [&](int64_t lo, int64_t hi) {
-        for (int64_t k = lo; k < hi; ++k) {
-            const Block& bl = blocks[k];
-            if (bl.out_size == 0) continue;                               // the EOF marker block
-            if (!inflate_block(file.data() + bl.in_off, bl.in_size, b->data.data() + bl.out_off, bl.out_size)) bad.store(1);
+    if (!index_bgzf(b->file, b->blocks, &b->total, &why)) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + why);
+    // Files above the threshold are opened lazily when their records are grouped by reference
+    if (b->total > env_u64("GA_BAM_EAGER_BYTES", 2ull << 30)) {
+        bool grouped = false;
+        const int rc = scan_spans(b.get(), path, &grouped);
+        if (rc != GA_IO_OK) return rc;
+        if (grouped) {
+            b->lazy = true;
+            b->by_ref.resize(b->ref_names.size());
+            *out = b.release();
+            return GA_IO_OK;
         }
-    });
-    if (bad.load()) { delete b; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": a BGZF block failed to inflate or its CRC32 does not match"); }
-    // ---- header
-    const uint8_t* d = b->data.data();
-    const uint64_t n = b->data.size();
-    auto corrupt = [&](const char* what) { delete b; return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + what); };
-    if (n < 12 || std::memcmp(d, "BAM\1", 4) != 0) return corrupt("BAM magic missing");
-    uint64_t off = 4;
-    const uint32_t l_text = le32(d + off); off += 4;
-    if (off + l_text + 4 > n) return corrupt("truncated header text");
-    off += l_text;
-    const uint32_t n_ref = le32(d + off); off += 4;
-    for (uint32_t r = 0; r < n_ref; ++r) {
-        if (off + 4 > n) return corrupt("truncated reference dictionary");
-        const uint32_t l_name = le32(d + off); off += 4;
-        if (off + l_name + 4 > n || l_name == 0) return corrupt("truncated reference dictionary");
-        b->ref_names.emplace_back(reinterpret_cast<const char*>(d + off), l_name - 1);
-        off += l_name;
-        b->ref_lens.push_back((int64_t)le32(d + off)); off += 4;
+        b->n_records = 0; b->spans.clear();                                // interleaved references: keep the whole stream
     }
-    b->by_ref.resize(n_ref);
-    // ---- record index (one hop per record)
-    while (off < n) {
-        if (off + 4 > n) return corrupt("truncated alignment record");
-        const uint32_t block_size = le32(d + off);
-        if (block_size < 32 || off + 4 + block_size > n) return corrupt("alignment record runs past the end of the stream");
-        const int32_t ref_id = (int32_t)le32(d + off + 4);
-        if (ref_id >= 0 && (uint32_t)ref_id < n_ref) b->by_ref[ref_id].push_back(off + 4);
-        else if (ref_id != -1) return corrupt("alignment record names a reference that is not in the header");
-        b->n_records++;
-        off += 4 + (uint64_t)block_size;
+    uint64_t base = 0;
+    if (!inflate_range(b->file, b->blocks, 0, b->total, n_threads, b->data, &base))
+        return fail(GA_IO_ERR_FORMAT, std::string(path) + ": a BGZF block failed to inflate or its CRC32 does not match");
+    const int64_t hdr = parse_header(b->data.data(), b->data.size(), b->ref_names, b->ref_lens);
+    if (hdr < 0) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": BAM magic missing");
+    if (hdr == 0) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": truncated header");
+    b->by_ref.resize(b->ref_names.size());
+    const int rc = index_records(b.get(), (uint64_t)hdr, path);
+    if (rc != GA_IO_OK) return rc;
+    for (const auto& v : b->by_ref) b->n_records += (int64_t)v.size();
+    {   // records without a reference count too
+        const uint8_t* d = b->data.data();
+        int64_t all = 0;
+        for (uint64_t off = (uint64_t)hdr; off < b->data.size(); off += 4 + (uint64_t)le32(d + off)) ++all;
+        b->n_records = all;
     }
-    *out = b;
+    *out = b.release();
     return GA_IO_OK;
 }
 
@@ -239,7 +392,7 @@ int64_t ga_bam_reference_length(const ga_bam* b, int ref_id) {
     return (b && ref_id >= 0 && ref_id < (int)b->ref_lens.size()) ? b->ref_lens[ref_id] : -1;
 }
 int64_t ga_bam_n_records(const ga_bam* b) { return b ? b->n_records : 0; }
-int64_t ga_bam_inflated_bytes(const ga_bam* b) { return b ? (int64_t)b->data.size() : 0; }
+int64_t ga_bam_inflated_bytes(const ga_bam* b) { return b ? (int64_t)b->total : 0; }
 
 // Fixed part of an alignment record, p = address of refID.
 struct RecView {
@@ -263,6 +416,7 @@ static inline uint32_t units_of(uint32_t l_seq) { const uint32_t u = (l_seq + 31
 
 int ga_bam_contig_sizes(const ga_bam* b, int ref_id, uint32_t flag_exclude, ga_bam_sizes* out) {
     if (!b || !out || ref_id < 0 || ref_id >= (int)b->by_ref.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_contig_sizes: bad argument");
+    { const int rc = ensure_loaded(b, ref_id); if (rc != GA_IO_OK) return rc; }
     ga_bam_sizes s;
     std::memset(&s, 0, sizeof(s));
     s.sorted = 1;
@@ -291,6 +445,7 @@ int ga_bam_pack_contig(const ga_bam* b, int ref_id, uint32_t flag_exclude, const
     if (!b || !dst || ref_id < 0 || ref_id >= (int)b->by_ref.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_pack_contig: bad argument");
     if (!dst->pos || !dst->len_flag || !dst->seq_off16 || !dst->cigar_off || !dst->seq4 || !dst->cigar)
         return fail(GA_IO_ERR_ARGUMENT, "ga_bam_pack_contig: NULL destination array");
+    { const int rc = ensure_loaded(b, ref_id); if (rc != GA_IO_OK) return rc; }
     // ---- pass 1 (sequential, one hop per record): which records, and where each one goes
     std::vector<uint64_t> recs;
     recs.reserve(b->by_ref[ref_id].size());

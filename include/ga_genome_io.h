@@ -43,7 +43,11 @@ int ga_io_set_error(int code, const char* msg);
 typedef struct ga_bam ga_bam;
 
 /* Opens a BAM file: inflates every BGZF block (n_threads host threads, 0 = all), checks the block CRCs, parses
- * the header and indexes the alignment records per reference (file order is kept; no .bai is needed). */
+ * the header and indexes the alignment records per reference (file order is kept; no .bai is needed).
+ * A file whose uncompressed stream exceeds GA_BAM_EAGER_BYTES (environment, default 2 GiB) and whose records are
+ * grouped by reference is walked once, window by window, and then kept mapped: the records of one reference at a time
+ * are inflated when ga_bam_contig_sizes / ga_bam_pack_contig ask for them (the handle caches one reference, so it is
+ * for one thread at a time). */
 int  ga_bam_open(const char* path, int n_threads, ga_bam** out);
 void ga_bam_close(ga_bam* b);
 int  ga_bam_n_references(const ga_bam* b);

@@ -235,3 +235,33 @@ def test_pairs_split_over_two_contigs_are_written_where_the_reference_writes_the
             assert not os.path.exists(path), name
         else:
             assert open(path).read() == text, name
+
+
+def test_large_files_are_read_one_contig_at_a_time(tmp_path, monkeypatch):
+    """Above GA_BAM_EAGER_BYTES the reader keeps the file mapped and inflates the records of one reference when they
+    are asked for (found by one windowed walk at open time); here the threshold is 0 and the window smaller than the
+    file, with records straddling both BGZF blocks and windows.  Same arrays as the eager reader; a file whose
+    references are interleaved falls back to the eager mode."""
+    case = GENOME[1]["case"]
+    reads = [r for r in case["reads"] if r["dataset"] == 0]
+    three = [dict(r, contig="a") for r in reads[:220]] + [dict(r, contig="b") for r in reads[220:300]] + [dict(r, contig="d") for r in reads[300:420]]
+    p = str(tmp_path / "three.bam")
+    H.write_bam(p, [("a", 9000), ("b", 9000), ("empty", 10), ("d", 9000)], three, block_bytes=3001)
+    with GF.BamFile(p) as f:
+        eager = {c: GF.pack_tumor_normal(f, f, c) for c in ("a", "b", "empty", "d")}
+        n_all = f.n_records
+    monkeypatch.setenv("GA_BAM_EAGER_BYTES", "0")
+    monkeypatch.setenv("GA_BAM_WINDOW_BYTES", "65536")
+    with GF.BamFile(p, 2) as f:
+        assert f.references == ("a", "b", "empty", "d") and f.n_records == n_all
+        assert [int(f.contig_sizes(c).n_reads) for c in f.references] == [220, 80, 0, 120]
+        for c in ("d", "a", "empty", "b", "a"):                      # any order, twice
+            lazy = GF.pack_tumor_normal(f, f, c)
+            for k in ARRAYS:
+                assert np.array_equal(getattr(lazy.batch, k), getattr(eager[c].batch, k)), (c, k)
+            assert np.array_equal(lazy.name_blob, eager[c].name_blob) and np.array_equal(lazy.ref_end, eager[c].ref_end)
+    mixed = [dict(r, contig="a") for r in reads[:50]] + [dict(r, contig="b") for r in reads[50:90]] + [dict(r, contig="a") for r in reads[90:120]]
+    H.write_bam(p, [("a", 9000), ("b", 9000)], mixed, block_bytes=3001)
+    with GF.BamFile(p) as f:                                         # references interleaved: the whole stream is kept
+        assert [int(f.contig_sizes(c).n_reads) for c in f.references] == [80, 40]
+        assert GF.pack_tumor_normal(f, f, "b").batch.n_reads == 80
