@@ -46,6 +46,7 @@ struct EmitScratch2 {
     uint32_t* many_recs; // [cap_many] special-record slots of those records (emit_many_kernel walks them)
     uint32_t* n_many_recs;
     uint32_t* n_kind1;   // records left to emit_kernel (long clean reads); zero lets that kernel return at once
+    unsigned int* ticket_large;   // next entry of large_list for the one-CTA resolve kernel
 };
 
 // Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked
@@ -181,7 +182,13 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
     uint32_t round = 0;
 
     const int n_list = *n_large;                                      // sessions the lean kernel handed over
-    for (int li = blockIdx.x; li < n_list; li += gridDim.x, ++round) {
+    __shared__ int s_li;
+    for (;; ++round) {                                                // sessions differ in cost: a ticket, not a stride
+        if (tid == 0) s_li = (int)atomicAdd(E.ticket_large, 1u);
+        __syncthreads();
+        const int li = s_li;
+        __syncthreads();
+        if (li >= n_list) break;
         const int s = large_list[li];
         c.d = descs[s];
         if (c.d.big) continue;                                        // listed by the assignment kernel
