@@ -393,7 +393,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     ga::EmitScratch2 E; E.kind = L.d_kind; E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
     E.sdesc = reinterpret_cast<uint4*>(L.d_special); E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
     E.many = reinterpret_cast<uint4*>(L.d_many); E.n_many = reinterpret_cast<uint32_t*>(L.d_small + 15); E.cap_many = (uint32_t)L.cap_many;
-    E.many_recs = L.d_many_recs; E.n_many_recs = reinterpret_cast<uint32_t*>(L.d_small + 16); E.n_kind1 = reinterpret_cast<uint32_t*>(L.d_small + 17); E.ticket_large = reinterpret_cast<unsigned int*>(L.d_small + 18);
+    E.many_recs = L.d_many_recs; E.n_many_recs = reinterpret_cast<uint32_t*>(L.d_small + 16); E.n_kind1 = reinterpret_cast<uint32_t*>(L.d_small + 17); E.ticket_large = reinterpret_cast<unsigned int*>(L.d_small + 18); E.ticket_lean = reinterpret_cast<unsigned int*>(L.d_small + 19);
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;

@@ -11,7 +11,7 @@ struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
 // Scratch of one in-flight ga_run: three lanes let the host pipeline overlap consecutive chunks.
 struct Lane {
     ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int32_t* d_large_list = nullptr; int64_t cap_sessions = 0;
-    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special, [14] second fallback ticket, [15] n_many, [16] n_many_recs, [17] n_kind1, [18] ticket of the one-CTA resolve kernel
+    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special, [14] second fallback ticket, [15] n_many, [16] n_many_recs, [17] n_kind1, [18] / [19] tickets of the one-CTA / one-warp resolve kernels
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the fallback kernel runs beside the emission kernel
     uint8_t* d_big_scratch = nullptr;
     // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)

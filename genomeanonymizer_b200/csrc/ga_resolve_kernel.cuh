@@ -47,6 +47,7 @@ struct EmitScratch2 {
     uint32_t* n_many_recs;
     uint32_t* n_kind1;   // records left to emit_kernel (long clean reads); zero lets that kernel return at once
     unsigned int* ticket_large;   // next entry of large_list for the one-CTA resolve kernel
+    unsigned int* ticket_lean;    // next session of the one-warp resolve kernel
 };
 
 // Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked
@@ -553,7 +554,13 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
     uint32_t acc_snv = 0u, acc_del = 0u, acc_ins = 0u, acc_q = 0u;
 
 #pragma unroll 1
-    for (int s = blockIdx.x * kLeanWarps + warp; s < S.n_sessions; s += n_warps) {
+    // sessions differ in cost: a warp takes the next one from a ticket counter (the ticket after that travels while the
+    // session is processed), so that no warp is left with a long tail of expensive sessions
+    uint32_t ticket = lane == 0 ? atomicAdd(E.ticket_lean, 1u) : 0u, next_ticket = 0u;
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    for (; ticket < (uint32_t)S.n_sessions; ticket = __shfl_sync(0xffffffffu, next_ticket, 0)) {
+        const int s = (int)ticket;
+        next_ticket = lane == 0 ? atomicAdd(E.ticket_lean, 1u) : 0u;
         // ---- round trip 1: descriptor, scan counts, variant_to_keep
         uint32_t w1 = 0u, w2 = 0u;
         if (lane < 20) w1 = __ldg(reinterpret_cast<const uint32_t*>(descs + s) + lane);
