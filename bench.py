@@ -109,7 +109,7 @@ def host_sample(cfg, n_windows, device=None):
     b, s, _ = SD.generate_host(cfg, 0, n_windows, with_reference=False)
     buf = np.zeros(prefix, np.uint8)
     p = cfg.params(0, 0)
-    _lib.lib().ga_synth_reference_host(C.byref(p), buf.ctypes.data, 0, prefix)
+    _lib.synth_lib().ga_synth_reference_host(C.byref(p), buf.ctypes.data, 0, prefix)
     return b, s, buf.tobytes()
 
 

@@ -43,6 +43,11 @@ class GaFastqItems(C.Structure):
     _fields_ = [("n_items", C.c_int64), ("read", _vp), ("record", _vp), ("names", _vp), ("name_off", _vp)]
 
 
+class GaDigestIds(C.Structure):
+    _fields_ = [("session_base", C.c_int64), ("tumor_base", C.c_int64), ("normal_base", C.c_int64), ("n_tumor", C.c_int64),
+                ("contig", C.c_int64)]
+
+
 class GaSynthParams(C.Structure):
     _fields_ = [("contig_len", C.c_int64), ("seed", C.c_uint64), ("read_len", C.c_int32),
                 ("total_windows", C.c_int32), ("window_begin", C.c_int32), ("n_windows", C.c_int32),

@@ -10,9 +10,12 @@ _LIB = None
 
 # every entry point declared in include/ga_b200.h
 EXPORTS = ["ga_abi_version", "ga_status_string", "ga_engine_create", "ga_engine_destroy", "ga_last_error",
-           "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions", "ga_fastq_layout", "ga_fastq_render",
-           "ga_synth_plan_sizes", "ga_synth_reference", "ga_synth_sessions", "ga_synth_reads_count", "ga_synth_reads_fill",
-           "ga_synth_reference_host", "ga_synth_sessions_host", "ga_synth_reads_count_host", "ga_synth_reads_fill_host"]
+           "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions", "ga_fastq_layout", "ga_fastq_render", "ga_result_digest"]
+# include/ga_synth.h - the synthetic-input generator lives in its own library (never needed by the masking path)
+SYNTH_LIB_PATH = os.path.join(_HERE, "libga_synth.so")
+SYNTH_EXPORTS = ["ga_synth_plan_sizes", "ga_synth_reference", "ga_synth_sessions", "ga_synth_reads_count", "ga_synth_reads_fill",
+                 "ga_synth_reference_host", "ga_synth_sessions_host", "ga_synth_reads_count_host", "ga_synth_reads_fill_host"]
+_SYNTH = None
 
 
 def lib():
@@ -58,6 +61,21 @@ def lib():
     L.ga_run_host.argtypes = [C.c_void_p, C.POINTER(_abi.GaReads), C.POINTER(_abi.GaSessions), C.POINTER(_abi.GaResult), C.c_int64]
     L.ga_last_host_traffic.restype = None
     L.ga_last_host_traffic.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.ga_result_digest.restype = C.c_int
+    L.ga_result_digest.argtypes = [C.c_void_p, C.POINTER(_abi.GaResult), C.c_int64, C.POINTER(_abi.GaDigestIds), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    _LIB = L
+    return L
+
+
+def synth_lib():
+    """libga_synth.so: benchmark / test input generator (include/ga_synth.h).  Loading it does not map the engine."""
+    global _SYNTH
+    if _SYNTH is not None:
+        return _SYNTH
+    if not os.path.exists(SYNTH_LIB_PATH):
+        raise RuntimeError(f"{SYNTH_LIB_PATH} is missing - build it with `python -m genomeanonymizer_b200.build`")
+    L = C.CDLL(SYNTH_LIB_PATH)
     P = C.POINTER(_abi.GaSynthParams)
     vp = C.c_void_p
     L.ga_synth_plan_sizes.restype = C.c_int
@@ -78,5 +96,5 @@ def lib():
     L.ga_synth_reads_count_host.argtypes = [P, vp, vp, vp]
     L.ga_synth_reads_fill_host.restype = C.c_int
     L.ga_synth_reads_fill_host.argtypes = [P, C.POINTER(_abi.GaReads), vp]
-    _LIB = L
+    _SYNTH = L
     return L

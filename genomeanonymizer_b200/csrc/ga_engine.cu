@@ -228,21 +228,30 @@ int ga_upload_reference(ga_engine* e, int contig_id, const uint8_t* bases, int64
     uint8_t* tmp = nullptr;
     bool is_dev = (cudaPointerGetAttributes(&attr, bases) == cudaSuccess) && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
     cudaGetLastError();
+    // every failure path releases the staging copy and leaves the entry consistent (no pointer without its length)
+#define GA_UP(call) do { cudaError_t _ce = (call); if (_ce != cudaSuccess) { if (tmp) cudaFree(tmp); return ga_fail(e, GA_ERR_CUDA, #call, _ce); } } while (0)
     if (!is_dev) {
-        GA_CUDA(cudaMalloc(&tmp, (size_t)n_bases + 16));
-        GA_CUDA(cudaMemcpyAsync(tmp, bases, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+        GA_UP(cudaMalloc(&tmp, (size_t)n_bases + 16));
+        GA_UP(cudaMemcpyAsync(tmp, bases, (size_t)n_bases, cudaMemcpyHostToDevice, st));
         d_asc = tmp;
     }
     RefEntry& re = e->refs[contig_id];
-    if (re.d_ref4) { cudaFree(re.d_ref4); re.d_ref4 = nullptr; }
     const int64_t n_words = (n_bases + 7) / 8 + 1 + 8;          // 1 pad word in front, 8 behind
-    GA_CUDA(cudaMalloc(&re.d_ref4, (size_t)n_words * 4));
+    if (n_words > re.cap_words) {                               // the resident copy only grows (one session per call re-uploads often)
+        if (re.d_ref4) { cudaFree(re.d_ref4); re.d_ref4 = nullptr; }
+        re.n = 0; re.cap_words = 0;
+        const int64_t want = n_words + n_words / 4;
+        GA_UP(cudaMalloc(&re.d_ref4, (size_t)want * 4));
+        re.cap_words = want;
+    }
     re.n = n_bases;
     const int threads = 256;
     ga::pack_reference_kernel<<<(unsigned)((n_words + threads - 1) / threads), threads, 0, st>>>(d_asc, n_bases, re.d_ref4, n_words);
     e->launches++;
-    GA_CUDA(cudaGetLastError());
-    if (tmp) { GA_CUDA(cudaStreamSynchronize(st)); cudaFree(tmp); }
+    GA_UP(cudaGetLastError());
+    if (tmp) GA_UP(cudaStreamSynchronize(st));
+#undef GA_UP
+    if (tmp) cudaFree(tmp);
     return GA_OK;
 }
 

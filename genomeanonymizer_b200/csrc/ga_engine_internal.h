@@ -6,7 +6,7 @@
 #include <string>
 #include "ga_device.cuh"
 
-struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; };
+struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; int64_t cap_words = 0; };
 
 // Scratch of one in-flight ga_run: three lanes let the host pipeline overlap consecutive chunks.
 struct Lane {

@@ -31,6 +31,25 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// ga_run_host's precondition (include/ga_b200.h): inside each dataset the seq4 records - and the sparse quality records -
+// lie in read order without overlap, so a chunk's records are one contiguous slice.  Checked on the uploaded slice.
+__global__ void check_layout_kernel(const uint32_t* __restrict__ seq_off16, const uint32_t* __restrict__ len_flag, int64_t n_t, int64_t n_all,
+                                    const int32_t* __restrict__ qual_reads, const uint32_t* __restrict__ qual_off16, int64_t nq_t, int64_t nq_all,
+                                    int32_t qr_sub_t, int32_t qr_sub_n, int32_t qr_add_n, uint32_t* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_all; r += stride) {
+        if (r > 0 && r != n_t) {
+            const uint32_t L = len_flag[r - 1] & 0xffffu, units = L ? (L + 31u) / 32u : 1u;
+            if (seq_off16[r] < seq_off16[r - 1] + units) atomicOr(bad, 1u);
+        }
+        if (r < nq_all && r > 0 && r != nq_t) {
+            const int32_t prev = r - 1 < nq_t ? qual_reads[r - 1] - qr_sub_t : qual_reads[r - 1] - qr_sub_n + qr_add_n;   // chunk-local read index
+            const uint32_t L = (prev >= 0 && prev < n_all) ? (len_flag[prev] & 0xffffu) : 0u, units = L ? (L + 31u) / 32u : 1u;
+            if (qual_off16[r] < qual_off16[r - 1] + units) atomicOr(bad, 2u);
+        }
+    }
+}
+
 // chunk-local offsets -> consistent offsets of the concatenated (tumor slice | normal slice) mini batch
 __global__ void rebase_kernel(uint32_t* seq_off16, uint32_t* cigar_off, int32_t* qual_reads, uint32_t* qual_off16,
                               int64_t n_t, int64_t n_all, uint32_t seq_sub_t, uint32_t seq_sub_n, uint32_t seq_add_n,
@@ -69,6 +88,7 @@ struct HostSlot {
     ga::DevBuf s_first, s_last, s_kt, s_kp, s_ke, s_kl, s_koff, s_kall;
     ga::DevBuf o_sess, o_read, o_len, o_soff, o_qoff, o_seq, o_qual, o_counts, o_totals;
     ga_totals* h_totals = nullptr;       // pinned
+    uint32_t* d_bad = nullptr; uint32_t* h_bad = nullptr;   // layout check of the uploaded slice (device flag, pinned copy)
     uint32_t* h_koff = nullptr; size_t cap_koff = 0;   // pinned staging of the rebased keep_allele_off slice
     // description of the chunk in flight
     bool busy = false;
@@ -86,6 +106,8 @@ void ga_host_slots_destroy(ga_engine* e) {
                              &h.o_sess, &h.o_read, &h.o_len, &h.o_soff, &h.o_qoff, &h.o_seq, &h.o_qual, &h.o_counts, &h.o_totals};
         for (ga::DevBuf* b : all) b->release();
         if (h.h_totals) cudaFreeHost(h.h_totals);
+        if (h.h_bad) cudaFreeHost(h.h_bad);
+        if (h.d_bad) cudaFree(h.d_bad);
         if (h.h_koff) cudaFreeHost(h.h_koff);
         if (h.st) cudaStreamDestroy(h.st);
         if (h.done) cudaEventDestroy(h.done);
@@ -101,6 +123,8 @@ static int ensure_slots(ga_engine* e) {
         GA_CUDA(cudaStreamCreateWithFlags(&e->slots[k].st, cudaStreamNonBlocking));
         GA_CUDA(cudaEventCreateWithFlags(&e->slots[k].done, cudaEventDisableTiming));
         GA_CUDA(cudaHostAlloc(&e->slots[k].h_totals, sizeof(ga_totals), cudaHostAllocDefault));
+        GA_CUDA(cudaHostAlloc(&e->slots[k].h_bad, sizeof(uint32_t), cudaHostAllocDefault));
+        GA_CUDA(cudaMalloc(&e->slots[k].d_bad, sizeof(uint32_t)));
     }
     return GA_OK;
 }
@@ -140,6 +164,8 @@ static int submit_chunk(ga_engine* e, int lane, const ga_reads* R, const ga_sess
     };
     const uint32_t su_t0 = n_t ? R->seq_off16[h.t_lo] : 0u, su_t1 = n_t ? seq_end(h.t_hi, h.t_lo) : 0u;
     const uint32_t su_n0 = n_n ? R->seq_off16[h.n_lo] : 0u, su_n1 = n_n ? seq_end(h.n_hi, h.n_lo) : 0u;
+    if (su_t1 < su_t0 || su_n1 < su_n0 || 16ll * su_t1 > R->seq4_bytes || 16ll * su_n1 > R->seq4_bytes)
+        return ga_fail(e, GA_ERR_BAD_ARGUMENT, "ga_run_host: seq_off16 must ascend with the read index inside each dataset (records of a chunk are one slice)");
     const uint32_t units_t = su_t1 - su_t0, units_n = su_n1 - su_n0;
     const uint32_t cg_t0 = R->cigar_off[h.t_lo], cg_t1 = R->cigar_off[h.t_hi];
     const uint32_t cg_n0 = R->cigar_off[h.n_lo], cg_n1 = R->cigar_off[h.n_hi];
@@ -172,11 +198,18 @@ static int submit_chunk(ga_engine* e, int lane, const ga_reads* R, const ga_sess
         auto q_end = [&](int64_t qb) -> uint32_t { return R->qual_off16[qb - 1] + units_of(R->len_flag[R->qual_reads[qb - 1]]); };
         qo_t0 = nq_t ? R->qual_off16[qa_t] : 0u; qu_t = nq_t ? q_end(qb_t) - qo_t0 : 0u;
         qo_n0 = nq_n ? R->qual_off16[qa_n] : 0u; const uint32_t qu_n = nq_n ? q_end(qb_n) - qo_n0 : 0u;
+        if ((nq_t && q_end(qb_t) < qo_t0) || (nq_n && q_end(qb_n) < qo_n0))
+            return ga_fail(e, GA_ERR_BAD_ARGUMENT, "ga_run_host: qual_off16 must ascend with qual_reads inside each dataset");
         NEED(h.qual, 32ll * (qu_t + qu_n)); NEED(h.qual_reads, 4 * (nq_t + nq_n)); NEED(h.qual_off16, 4 * (nq_t + nq_n));
         H2D(h.qual_reads.as<int32_t>(), R->qual_reads + qa_t, 4 * nq_t);     H2D(h.qual_reads.as<int32_t>() + nq_t, R->qual_reads + qa_n, 4 * nq_n);
         H2D(h.qual_off16.as<uint32_t>(), R->qual_off16 + qa_t, 4 * nq_t);    H2D(h.qual_off16.as<uint32_t>() + nq_t, R->qual_off16 + qa_n, 4 * nq_n);
         H2D(h.qual.p, R->qual + 32ull * qo_t0, 32ll * qu_t);                 H2D(h.qual.p + 32ull * qu_t, R->qual + 32ull * qo_n0, 32ll * qu_n);
     }
+    GA_CUDA(cudaMemsetAsync(h.d_bad, 0, sizeof(uint32_t), h.st));
+    ga::check_layout_kernel<<<e->n_sm * 2, 256, 0, h.st>>>(h.seq_off16.as<uint32_t>(), h.len_flag.as<uint32_t>(), n_t, n_all,
+        sparse ? h.qual_reads.as<int32_t>() : nullptr, sparse ? h.qual_off16.as<uint32_t>() : nullptr, nq_t, sparse ? nq_t + nq_n : 0,
+        (int32_t)h.t_lo, (int32_t)h.n_lo, (int32_t)n_t, h.d_bad);
+    e->launches++;
     ga::rebase_kernel<<<e->n_sm * 2, 256, 0, h.st>>>(h.seq_off16.as<uint32_t>(), h.cigar_off.as<uint32_t>(),
         sparse ? h.qual_reads.as<int32_t>() : nullptr, sparse ? h.qual_off16.as<uint32_t>() : nullptr,
         n_t, n_all, su_t0, su_n0, units_t, cg_t0, cg_n0, ops_t,
@@ -230,6 +263,7 @@ static int submit_chunk(ga_engine* e, int lane, const ga_reads* R, const ga_sess
     int rc = ga_run_lane(e, lane, &h.R, &h.S, &h.O, h.st);
     if (rc) return rc;
     D2H(h.h_totals, h.o_totals.p, sizeof(ga_totals));
+    D2H(h.h_bad, h.d_bad, sizeof(uint32_t));
     GA_CUDA(cudaEventRecord(h.done, h.st));
     h.busy = true;
     return GA_OK;
@@ -244,6 +278,11 @@ static int collect_chunk(ga_engine* e, int lane, ga_result* out, ga_totals* acc,
     GA_CUDA(cudaEventSynchronize(h.done));
     h.busy = false;
     const ga_totals t = *h.h_totals;
+    if (*h.h_bad) {
+        if (!acc->error) { acc->error = GA_ERR_BAD_ARGUMENT; acc->error_detail = (uint32_t)h.s0; }
+        return ga_fail(e, GA_ERR_BAD_ARGUMENT, (*h.h_bad & 1u) ? "ga_run_host: seq4 records are not in read order inside a dataset (seq_off16 must ascend without overlap)"
+                                                             : "ga_run_host: sparse quality records are not in read order (qual_off16 must ascend without overlap)");
+    }
     if (t.error == GA_ERR_CAPACITY && t.error_detail == 0xffffffffu) { *retry = true; return GA_OK; }
     if (t.error) {
         if (!acc->error) { acc->error = t.error; acc->error_detail = t.error_detail; }

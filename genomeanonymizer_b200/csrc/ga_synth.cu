@@ -15,7 +15,7 @@
 #include <stdint.h>
 #include <string.h>
 
-#include "../../include/ga_b200.h"
+#include "../../include/ga_synth.h"
 
 namespace gs {
 

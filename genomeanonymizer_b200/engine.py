@@ -366,3 +366,28 @@ def _host_traffic(self):
 
 Engine.run_host = _run_host
 Engine.host_traffic = _host_traffic
+
+
+def _digest(self, dres: DeviceResult, n_records: int, session_base: int = 0, tumor_base: int = 0, normal_base: int = 0,
+            n_tumor: int = 0, contig: int = 0, records: bool = False, accumulate: "torch.Tensor" = None):
+    """ga_result_digest over a device-resident result (include/ga_digest.h).  Returns the int64[4] digest tensor
+    {sum lo, sum hi, records, sum of new lengths} (accumulated into `accumulate` when given) and, with records=True,
+    the per-record (keys[n,2], hashes[n,2]) int64 tensors."""
+    with torch.cuda.device(self.device):
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        dig = accumulate if accumulate is not None else torch.zeros(4, dtype=torch.int64, device=self.device)
+        keys = hashes = None
+        if records:
+            keys = torch.empty((max(1, n_records), 2), dtype=torch.int64, device=self.device)
+            hashes = torch.empty((max(1, n_records), 2), dtype=torch.int64, device=self.device)
+        ids = _abi.GaDigestIds(int(session_base), int(tumor_base), int(normal_base), int(n_tumor), int(contig))
+        O = dres.as_struct()
+        self._check(self._L.ga_result_digest(self._h, C.byref(O), int(n_records), C.byref(ids),
+                                             keys.data_ptr() if records else None, hashes.data_ptr() if records else None,
+                                             dig.data_ptr(), st))
+        if records:
+            return dig, keys[:n_records], hashes[:n_records]
+        return dig
+
+
+Engine.digest = _digest

@@ -49,7 +49,7 @@ class SynthConfig:
     def plan(self, window_begin: int = 0, n_windows: Optional[int] = None) -> _abi.GaSynthPlan:
         pl = _abi.GaSynthPlan()
         p = self.params(window_begin, n_windows)
-        st = _lib.lib().ga_synth_plan_sizes(C.byref(p), C.byref(pl))
+        st = _lib.synth_lib().ga_synth_plan_sizes(C.byref(p), C.byref(pl))
         if st != _abi.GA_OK:
             raise ValueError(f"invalid synthetic configuration {self.name}: windows do not fit the contig")
         return pl
@@ -89,7 +89,7 @@ def shard_windows(total_windows: int, world_size: int, rank: int) -> Tuple[int, 
 
 def generate_host(cfg: SynthConfig, window_begin: int = 0, n_windows: Optional[int] = None, with_reference: bool = True):
     """(ReadBatch, SessionTable, reference bytes | None) on the host; small shapes only (single thread)."""
-    L = _lib.lib()
+    L = _lib.synth_lib()
     p = cfg.params(window_begin, n_windows)
     pl = cfg.plan(window_begin, n_windows)
     n, nw = int(pl.n_reads), int(p.n_windows)
@@ -134,7 +134,7 @@ def generate_device(cfg: SynthConfig, device, window_begin: int = 0, n_windows: 
     """(DeviceBatch, DeviceSessions) of a window shard, generated in HBM on `device`."""
     import torch
     from .engine import DeviceBatch, DeviceSessions
-    L = _lib.lib()
+    L = _lib.synth_lib()
     p = cfg.params(window_begin, n_windows)
     pl = cfg.plan(window_begin, n_windows)
     n, nw, units = int(pl.n_reads), int(p.n_windows), int(pl.units_per_read)
@@ -191,7 +191,7 @@ def reference_device(cfg: SynthConfig, device, begin: int = 0, n: Optional[int] 
     with torch.cuda.device(device):
         out = torch.empty(n, dtype=torch.uint8, device=device)
         p = cfg.params(0, 0)
-        _check(_lib.lib().ga_synth_reference(C.byref(p), out.data_ptr(), begin, n, torch.cuda.current_stream().cuda_stream),
+        _check(_lib.synth_lib().ga_synth_reference(C.byref(p), out.data_ptr(), begin, n, torch.cuda.current_stream().cuda_stream),
                "reference")
         torch.cuda.current_stream().synchronize()
     return out

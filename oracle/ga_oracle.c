@@ -34,6 +34,7 @@
 #include <pthread.h>
 #include <unistd.h>
 #include "../include/ga_b200.h"
+#include "../include/ga_digest.h"
 
 /* ASCII -> BAM 4-bit code ("=ACMGRSVTWYHKDBN"), case-insensitive; anything else -> 15 (N). */
 static uint8_t g_asc2code[256];
@@ -437,5 +438,47 @@ int ga_oracle_run(const ga_reads* R, const ga_sessions* S, const uint8_t* ref_as
     free(res); free(refc);
     if (status != GA_OK) return status;
     if (overflow) { T->error = GA_ERR_CAPACITY; return GA_ERR_CAPACITY; }
+    return GA_OK;
+}
+
+/* Host twin of ga_result_digest (include/ga_digest.h) over a HOST result - written separately from the device kernel:
+ * per record the key (global session, read gid) and the two 64-bit hashes; digest[0..3] += {sum lo, sum hi, records,
+ * sum of new lengths}.  rec_keys / rec_hash may be NULL. */
+int ga_oracle_digest(const ga_result* out, int64_t n_records, const ga_digest_ids* ids, uint64_t* rec_keys, uint64_t* rec_hash,
+                     uint64_t* digest) {
+    if (!out || !ids || !digest || n_records < 0 || n_records > out->cap_records) return GA_ERR_BAD_ARGUMENT;
+    for (int64_t k = 0; k < n_records; ++k) {
+        const uint64_t s = (uint64_t)((int64_t)out->mod_session[k] + ids->session_base);
+        const int64_t r = out->mod_read[k];
+        const uint64_t gid = r < ids->n_tumor ? (uint64_t)(ids->tumor_base + r) : ((1ull << 40) | (uint64_t)(ids->normal_base + r - ids->n_tumor));
+        const uint32_t len = out->mod_len[k];
+        const int has_q = out->mod_qual_off16[k] != 0xffffffffu;
+        uint64_t h[2] = {GA_DIGEST_SEED_LO, GA_DIGEST_SEED_HI};
+        const uint64_t mul[2] = {GA_DIGEST_MUL_LO, GA_DIGEST_MUL_HI};
+        const uint8_t* sq = out->out_seq4 + 16ull * out->mod_seq_off16[k];
+        const uint8_t* qq = has_q ? out->out_qual + 32ull * out->mod_qual_off16[k] : NULL;
+        for (int j = 0; j < 2; ++j) {
+            uint64_t v = h[j];
+            v = ga_digest_mix(v, (uint64_t)ids->contig, mul[j]);
+            v = ga_digest_mix(v, s, mul[j]);
+            v = ga_digest_mix(v, gid, mul[j]);
+            v = ga_digest_mix(v, (uint64_t)len | ((uint64_t)has_q << 32), mul[j]);
+            for (uint32_t b = 0; b < len; b += 8) {                 /* eight bases per word, absent nibbles are zero */
+                uint32_t w = 0;
+                for (uint32_t i = b; i < b + 8 && i < len; ++i) w |= (uint32_t)nib_at(sq, (int)i) << (4 * (i - b));
+                v = ga_digest_mix(v, w, mul[j]);
+            }
+            if (has_q)
+                for (uint32_t b = 0; b < len; b += 4) {             /* four qualities per word, absent bytes are zero */
+                    uint32_t w = 0;
+                    for (uint32_t i = b; i < b + 4 && i < len; ++i) w |= (uint32_t)qq[i] << (8 * (i - b));
+                    v = ga_digest_mix(v, w, mul[j]);
+                }
+            h[j] = ga_digest_fin(v);
+        }
+        if (rec_keys) { rec_keys[2 * k] = s; rec_keys[2 * k + 1] = gid; }
+        if (rec_hash) { rec_hash[2 * k] = h[0]; rec_hash[2 * k + 1] = h[1]; }
+        digest[0] += h[0]; digest[1] += h[1]; digest[2] += 1; digest[3] += len;
+    }
     return GA_OK;
 }

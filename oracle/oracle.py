@@ -18,8 +18,8 @@ _LIB = None
 def build(force=False):
     so = os.path.join(_HERE, "libga_oracle.so")
     src = os.path.join(_HERE, "ga_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "ga_b200.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("ga_b200.h", "ga_digest.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libga_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -35,6 +35,8 @@ def lib():
         _LIB.ga_oracle_run.argtypes = [C.POINTER(_abi.GaReads), C.POINTER(_abi.GaSessions), C.c_void_p, C.c_int64,
                                        C.POINTER(_abi.GaResult), C.c_int]
         _LIB.ga_oracle_threads.restype = C.c_int
+        _LIB.ga_oracle_digest.restype = C.c_int
+        _LIB.ga_oracle_digest.argtypes = [C.POINTER(_abi.GaResult), C.c_int64, C.POINTER(_abi.GaDigestIds), C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
 
@@ -68,8 +70,42 @@ def run(batch: ReadBatch, sessions: SessionTable, reference: bytes, threads: int
     refb = np.frombuffer(reference if isinstance(reference, (bytes, bytearray)) else reference.encode("ascii"), dtype=np.uint8)
     st = lib().ga_oracle_run(C.byref(R), C.byref(S), refb.ctypes.data, len(refb), C.byref(res), int(threads))
     if not decode:
-        return {"totals": totals, "counts": counts.reshape(-1, 4)}, st
+        return {"totals": totals, "counts": counts.reshape(-1, 4), "result": res,
+                "arrays": (mod_sess, mod_read, mod_len, mod_so, mod_qo, out_seq, out_qual, counts)}, st
     if st != _abi.GA_OK:
         return None, st
     return decode_result(sessions.n_sessions, totals, mod_sess, mod_read, mod_len, mod_so, mod_qo, out_seq, out_qual,
                          counts[:sessions.n_sessions * 4]), st
+
+
+def digest(result_struct, n_records, session_base=0, tumor_base=0, normal_base=0, n_tumor=0, contig=0, records=False, accumulate=None):
+    """Host twin of ga_result_digest over a HOST ga_result (an _abi.GaResult whose arrays the caller keeps alive):
+    uint64[4] digest {sum lo, sum hi, records, sum of new lengths} and, with records=True, (keys[n,2], hashes[n,2])."""
+    dig = accumulate if accumulate is not None else np.zeros(4, np.uint64)
+    keys = np.zeros((max(1, n_records), 2), np.uint64) if records else None
+    hashes = np.zeros((max(1, n_records), 2), np.uint64) if records else None
+    ids = _abi.GaDigestIds(int(session_base), int(tumor_base), int(normal_base), int(n_tumor), int(contig))
+    st = lib().ga_oracle_digest(C.byref(result_struct), int(n_records), C.byref(ids), keys.ctypes.data if records else None,
+                                hashes.ctypes.data if records else None, dig.ctypes.data)
+    if st != _abi.GA_OK:
+        raise ValueError(f"ga_oracle_digest failed with status {st}")
+    if records:
+        return dig, keys[:n_records], hashes[:n_records]
+    return dig
+
+
+def compare_records(keys_a, hash_a, keys_b, hash_b):
+    """Number of records that differ between two (keys, hashes) sets: records present on one side only, plus records
+    with the same key and different hashes.  Inputs are [n,2] integer arrays (any 64-bit dtype)."""
+    def canon(k, h):
+        k = np.ascontiguousarray(k).view(np.uint64).reshape(-1, 2)
+        h = np.ascontiguousarray(h).view(np.uint64).reshape(-1, 2)
+        o = np.lexsort((k[:, 1], k[:, 0]))
+        return k[o], h[o]
+    ka, ha = canon(keys_a, hash_a)
+    kb, hb = canon(keys_b, hash_b)
+    if len(ka) == len(kb) and np.array_equal(ka, kb):
+        return int(np.count_nonzero((ha != hb).any(axis=1)))
+    sa = {(int(a), int(b)): (int(c), int(d)) for (a, b), (c, d) in zip(ka, ha)}
+    sb = {(int(a), int(b)): (int(c), int(d)) for (a, b), (c, d) in zip(kb, hb)}
+    return sum(1 for k in sa.keys() | sb.keys() if sa.get(k) != sb.get(k))

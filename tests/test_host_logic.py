@@ -17,8 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "ga_b200.h")
 
 
-def declared_functions():
-    text = open(HEADER).read()
+SYNTH_HEADER = os.path.join(ROOT, "include", "ga_synth.h")
+
+
+def declared_functions(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ga_[a-z0-9_]+)\s*\(", text)))
 
@@ -26,10 +29,21 @@ def declared_functions():
 def test_library_exports_every_declared_symbol():
     L = C.CDLL(_lib.LIB_PATH)                                    # loads without a GPU; no compute call is made
     names = declared_functions()
-    assert len(names) >= 18
+    assert len(names) >= 17
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert sorted(_lib.EXPORTS) == names                         # the loader binds exactly the declared surface
+
+
+def test_synth_library_is_separate_and_exports_its_header():
+    """The input generator lives in libga_synth.so (include/ga_synth.h): a process that only needs input data never
+    maps the masking engine, and the engine library carries no generator symbol."""
+    L = C.CDLL(_lib.SYNTH_LIB_PATH)
+    names = declared_functions(SYNTH_HEADER)
+    assert len(names) == 9 and sorted(_lib.SYNTH_EXPORTS) == names
+    assert not [n for n in names if not hasattr(L, n)]
+    E = C.CDLL(_lib.LIB_PATH)
+    assert not [n for n in names if hasattr(E, n)]
 
 
 def test_abi_version_and_status_strings():
@@ -41,7 +55,7 @@ def test_abi_version_and_status_strings():
 
 def test_ctypes_mirrors_match_the_c_structs(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "ga_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ga_reads),'
+    src.write_text('#include <stdio.h>\n#include "ga_synth.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ga_reads),'
                    ' sizeof(ga_sessions), sizeof(ga_totals), sizeof(ga_result), sizeof(ga_synth_params), sizeof(ga_synth_plan));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
