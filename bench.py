@@ -10,8 +10,13 @@ records in host memory out, H2D/D2H inside the timed region.  `roofline` is the 
 the measured HBM copy peak; `cpu_baseline` is the CPU oracle (a C restatement of the reference's
 algorithm, all host threads) on a bounded sample of the same sessions.
 
-N > 1 (torchrun): each rank owns one contig-sized shard of the genome (region sharding),
-no data-path collective; the masking counters are all-reduced once per step over NCCL.  Weak scaling.
+N > 1 (torchrun): region sharding of ONE synthetic whole genome, "wgs-30x" (24 contigs, 30x / 30x,
+one somatic SNV per 4,979 bp; contig 0 is the N=1 workload chr1-30x-50k).  `value` is weak scaling: rank r masks
+sessions [50,000 r, 50,000 (r+1)) of the genome-ordered session list; `strong` cuts the WHOLE genome's session list
+across the N ranks with sharding.shard_sessions (total work fixed).  No data-path collective; the masking counters
+and the record digest are all-reduced over NCCL.  At every N the digest of all modified records (include/ga_digest.h)
+is compared with the oracle's digest of the same sessions (tests/golden/workload_digests.json, written by
+tools/make_workload_digests.py), so the merged output is proven identical for N = 1, 2, 4, 8.
 """
 import argparse
 import json
@@ -317,32 +322,174 @@ def _has_cuda():
         return False
 
 
+REGION = 50_000          # sessions per rank of the weak-scaling line (= the N=1 workload's session count)
+DIGESTS = os.path.join(ROOT, "tests", "golden", "workload_digests.json")
+
+
+def committed_digest(name, s_begin=None, s_end=None):
+    """Oracle digest of sessions [s_begin, s_end) of workload `name` (whole workload by default) from the committed
+    table, or None when the table has no entry or the range does not fall on block boundaries."""
+    try:
+        with open(DIGESTS) as f:
+            t = json.load(f)[name]
+    except Exception:
+        return None
+    if s_begin is None:
+        return [int(x) for x in t["total"]]
+    acc, lo_ok, hi_ok = [0, 0, 0, 0], s_begin == s_end, s_begin == s_end
+    for b in t["blocks"]:
+        if b[0] >= s_begin and b[1] <= s_end:
+            acc = [(a + x) & ((1 << 64) - 1) for a, x in zip(acc, b[2:6])]
+            lo_ok |= b[0] == s_begin
+            hi_ok |= b[1] == s_end
+        elif b[0] < s_end and b[1] > s_begin:
+            return None
+    return acc if lo_ok and hi_ok else None
+
+
+class Piece:
+    """Sessions [w0, w0 + nw) of one contig, resident in HBM, with their caller-owned result buffers."""
+    pass
+
+
+class ShardRun:
+    """This rank's share of a workload: per-contig pieces (device batch, session table, result buffers)."""
+
+    def __init__(self, eng, dev, contigs, pieces):
+        import torch
+        from genomeanonymizer_b200 import synthdev as SD
+        from genomeanonymizer_b200.engine import DeviceResult
+        self.eng, self.dev, self.contigs, self.pieces = eng, dev, contigs, []
+        done_refs = set()
+        for k, w0, nw, g in pieces:
+            cfg = contigs[k]
+            if k not in done_refs:
+                ref = SD.reference_device(cfg, dev)
+                eng.upload_reference(k, ref)
+                del ref
+                done_refs.add(k)
+            p = Piece()
+            p.k, p.w0, p.nw, p.g, p.cfg = k, w0, nw, g, cfg
+            p.db, p.ds = SD.generate_device(cfg, dev, w0, nw)
+            p.db.contig_id = k
+            pl = cfg.plan(0, 0)
+            p.ids = dict(session_base=g, tumor_base=w0 * int(pl.reads_per_window[0]), normal_base=w0 * int(pl.reads_per_window[1]),
+                         n_tumor=p.db.n_tumor, contig=k)
+            # size the caller-owned result once: a trial run reports what the piece needs
+            units = p.db.seq4_bytes // 16
+            upr = max(1, units // max(1, p.db.n_reads))
+            cap = p.db.n_reads // 3 + 1024
+            trial = DeviceResult(nw, cap, cap * (upr + 1), cap * (upr + 1) // 2 + 1024, dev)
+            eng.run_device(p.db, p.ds, trial)
+            torch.cuda.synchronize()
+            t0 = trial.read_totals()
+            if int(t0.error) not in (0, 5):
+                eng.check_device_status(trial)
+            del trial
+            p.dres = DeviceResult(nw, int(t0.n_modified * 1.02) + 1024, int(t0.seq16_used * 1.02) + 1024, int(t0.qual16_used * 1.02) + 1024, dev)
+            self.pieces.append(p)
+        torch.cuda.empty_cache()
+        self.sessions = sum(p.nw for p in self.pieces)
+
+    def step(self):
+        for p in self.pieces:
+            self.eng.run_device(p.db, p.ds, p.dres)
+
+    def totals(self):
+        """Checks every piece's device status; sums of the totals over the pieces."""
+        out = {"session_reads": 0, "session_bases": 0, "n_modified": 0, "indel_records": 0, "seq16_used": 0, "qual16_used": 0,
+               "masked": [0, 0, 0]}
+        for p in self.pieces:
+            t = self.eng.check_device_status(p.dres)
+            p.tot = t
+            for f in ("session_reads", "session_bases", "n_modified", "indel_records", "seq16_used", "qual16_used"):
+                out[f] += int(getattr(t, f))
+            out["masked"] = [a + int(b) for a, b in zip(out["masked"], t.masked)]
+        return out
+
+    def counters(self, out):
+        """Masking counters of this shard (SR.py:198-204) into the int64[8] device tensor `out`."""
+        out.zero_()
+        for p in self.pieces:
+            out[:3] += p.dres.sess_counts.view(-1, 4)[:p.nw, :3].sum(0)
+
+    def digest(self):
+        import torch
+        acc = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        for p in self.pieces:
+            self.eng.digest(p.dres, int(p.tot.n_modified), accumulate=acc, **p.ids)
+        return acc
+
+    def fallbacks(self):
+        """(sessions that took the global-scratch fallback kernel, per-reason counts) summed over the pieces (one more run each)."""
+        n, why = 0, [0] * 9
+        for p in self.pieces:
+            self.eng.run_device(p.db, p.ds, p.dres)
+            a, b = self.eng.fallback_sessions()
+            n, why = n + a, [x + y for x, y in zip(why, b)]
+        return n, why
+
+    def free(self):
+        import torch
+        self.pieces = []
+        torch.cuda.empty_cache()
+
+
+def timed_steps(fn, steps, warmup, barrier, sampler=None):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    if sampler:
+        sampler.stop()
+    return ev0.elapsed_time(ev1)
+
+
+def u64(t):
+    return [int(x) & ((1 << 64) - 1) for x in t.tolist()]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chr1-30x-50k")
+    ap.add_argument("--workload", default="", help="default: chr1-30x-50k at N=1, 50,000-session regions of wgs-30x at N>1")
     ap.add_argument("--windows", type=int, default=0, help="debug: use only the first WINDOWS windows per rank")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--chunk-sessions", type=int, default=4096)
-    ap.add_argument("--sample-windows", type=int, default=0, help="CPU baseline sample (0 = auto, ~10 s)")
+    ap.add_argument("--sample-windows", type=int, default=0, help="CPU baseline sample (0 = the whole N=1 workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fastq", action="store_true")
     ap.add_argument("--no-bam", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling run of the whole wgs-30x genome")
+    ap.add_argument("--strong-workload", default="wgs-30x")
+    ap.add_argument("--others", default="auto", help="comma list of other workloads run for 3 steps each (auto: per GPU count; none)")
     ap.add_argument("--fastq-windows", type=int, default=10000, help="windows rendered by the FASTQ measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
+        args.workload = args.workload or "chr1-30x-50k"
         return run_reference_arm(args)
 
     import numpy as np
     import torch
     import torch.distributed as dist
+    from genomeanonymizer_b200 import sharding
     from genomeanonymizer_b200 import synthdev as SD
-    from genomeanonymizer_b200.engine import DeviceResult, Engine, HostBatch, HostResult
+    from genomeanonymizer_b200.engine import Engine, HostBatch, HostResult
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -351,8 +498,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the masking path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    from genomeanonymizer_b200.sharding import bind_to_gpu_numa_node
-    numa = bind_to_gpu_numa_node(local)                            # host batches local to this rank's GPU
+    numa = sharding.bind_to_gpu_numa_node(local)                   # host batches local to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -362,82 +508,86 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    base = SD.WORKLOADS[args.workload]
-    # region sharding: rank r owns contig r of the synthetic genome (same shape, its own seed)
-    from dataclasses import replace
-    cfg = replace(base, seed=base.seed + 7919 * rank, name=base.name)
-    n_w = args.windows or cfg.total_windows
+    def allsum(t):
+        if world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def allmax(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
     eng = Engine(local)
-    db, ds = SD.generate_device(cfg, dev, 0, n_w)
-    ref_dev = SD.reference_device(cfg, dev)
-    eng.upload_reference(0, ref_dev)
-    del ref_dev
-    torch.cuda.empty_cache()
-    units = db.seq4_bytes // 16
-    cap_rec = db.n_reads // 3 + 1024
-    upr = max(1, units // max(1, db.n_reads))
-    dres = DeviceResult(n_w, cap_rec, cap_rec * (upr + 1), cap_rec * (upr + 1) // 2 + 1024, dev)
-    # size the caller-owned result once: a trial run reports what the workload needs (ga_totals holds the need
-    # when the capacities are exceeded)
-    eng.run_device(db, ds, dres)
-    torch.cuda.synchronize()
-    t0 = dres.read_totals()
-    if int(t0.error) == 5:                                    # GA_ERR_CAPACITY
-        cap_rec = int(t0.n_modified * 1.05) + 1024
-        del dres
-        torch.cuda.empty_cache()
-        dres = DeviceResult(n_w, cap_rec, int(t0.seq16_used * 1.05) + 1024, int(t0.qual16_used * 1.05) + 1024, dev)
     counters = torch.zeros(8, dtype=torch.int64, device=dev)
 
+    # ---- the workload of `value`
+    if args.workload:
+        wname = args.workload
+        contigs = SD.genome_contigs(wname)
+        total_sessions = sum(c.total_windows for c in contigs)
+        spans = sharding.shard_sessions(SD.genome_session_weights(contigs), world)
+        s_lo, s_hi = spans[rank]
+        scaling, span_all = "strong", (0, total_sessions)
+        sharding_note = f"{wname}: genome-ordered session list cut into {world} contiguous ranges balanced by session reads"
+    elif world == 1:
+        wname = "chr1-30x-50k"
+        contigs = SD.genome_contigs(wname)
+        s_lo, s_hi = 0, contigs[0].total_windows
+        scaling, span_all = "weak", (0, s_hi)
+        sharding_note = "single GPU"
+    else:
+        wname = "wgs-30x"
+        contigs = SD.genome_contigs(wname)
+        s_lo, s_hi = REGION * rank, REGION * (rank + 1)
+        scaling, span_all = "weak", (0, REGION * world)
+        sharding_note = (f"wgs-30x: rank r masks sessions [{REGION} r, {REGION} (r+1)) of the genome-ordered session list "
+                         f"(rank 0 = chr1-30x-50k); no data-path collective")
+    if args.windows:
+        s_hi = min(s_hi, s_lo + args.windows)
+    pieces = SD.genome_pieces(contigs, s_lo, s_hi)
+    run = ShardRun(eng, dev, contigs, pieces)
+    cfg = run.pieces[0].cfg
+    n_w = run.sessions
+
     def step():
-        eng.run_device(db, ds, dres)
+        run.step()
         if world > 1:
             # the only collective of the path: masking counters (SR.py:198-204) summed over the shards
-            counters.zero_()
-            counters[:3] = dres.sess_counts.view(-1, 4)[:, :3].sum(0)
+            run.counters(counters)
             dist.all_reduce(counters)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    tot = eng.check_device_status(dres)
-    session_reads, session_bases = int(tot.session_reads), int(tot.session_bases)
 
     sampler = ClockSampler(local)
     launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.start()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    torch.cuda.synchronize()
-    barrier()
-    sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = timed_steps(step, args.steps, args.warmup, barrier, sampler)
     launches = eng.launch_count - launches0
-    kernel_ms = [x for x in eng.kernel_ms_history(min(args.steps, 32)) if x > 0]
+    tot = run.totals()
+    session_reads, session_bases = tot["session_reads"], tot["session_bases"]
+    n_hist = min(args.steps * len(run.pieces), 32)
+    kernel_ms = [x for x in eng.kernel_ms_history(n_hist) if x > 0]
     stage_ms = []
     for st in range(4):
-        h = [x for x in eng.stage_ms_history(st, min(args.steps, 32)) if x >= 0]
-        stage_ms.append(sum(h) / len(h) if h else float("nan"))
-    eng.check_device_status(dres)
-    n_fallback, fallback_reasons = eng.fallback_sessions()
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    work = torch.tensor([session_reads, session_bases, launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work)
-    ms_max = float(t_ms.item())
-    total_reads, total_bases, total_launches = (int(x) for x in work.tolist())
+        h = [x for x in eng.stage_ms_history(st, n_hist) if x >= 0]
+        stage_ms.append(sum(h) / len(h) * len(run.pieces) if h else float("nan"))
+    n_fallback, fallback_reasons = run.fallbacks()
+    ms_max = float(allmax(torch.tensor([ms], dtype=torch.float64, device=dev)).item())
+    work = allsum(torch.tensor([session_reads, session_bases, launches, tot["n_modified"]], dtype=torch.int64, device=dev))
+    total_reads, total_bases, total_launches, total_modified = (int(x) for x in work.tolist())
     value = total_reads * args.steps / (ms_max * 1e-3)
 
-    # ---- roofline of the session kernel (rank 0's shard)
-    n_cigar = int(db.cigar_off[-1].item())
+    # ---- parity of EVERY modified record against the oracle's digest of the same sessions, all ranks together
+    dig = u64(allsum(run.digest()))
+    want = None if args.windows else committed_digest(wname, *span_all)
+    parity_digest = {"digest": dig, "oracle_digest": want,
+                     "records": "unchecked (no committed oracle digest for these sessions)" if want is None else ("ok" if dig == want else "MISMATCH"),
+                     "sessions": list(span_all), "source": "tests/golden/workload_digests.json (oracle on every session)"}
+
+    # ---- roofline of the masking pass (rank 0's shard)
+    p0 = run.pieces[0]
+    n_cigar = sum(int(p.db.cigar_off[-1].item()) for p in run.pieces)
     n_cols = 2 * cfg.window_half + 1 + 2 * (cfg.read_len - 1)
-    single, survey = algorithmic_bytes(cfg.read_len, session_reads, n_cigar, n_w, n_cols, int(tot.n_modified),
-                                       int(tot.indel_records), int(tot.seq16_used), int(tot.qual16_used))
+    single, two_pass = algorithmic_bytes(cfg.read_len, session_reads, n_cigar, n_w, n_cols, tot["n_modified"],
+                                         tot["indel_records"], tot["seq16_used"], tot["qual16_used"])
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -447,25 +597,26 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # the algorithmic bytes cover the whole masking pass (scan -> resolve -> [fallback] -> emission kernels, back to
     # back on one stream), so the duration is that of the pass; the per-kernel durations are listed beside it
-    pass_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else float("nan")
+    pass_ms = sum(kernel_ms) / len(kernel_ms) * len(run.pieces) if kernel_ms else float("nan")
     ach = single / (pass_ms * 1e-3) / 1e9
-    scan_bytes = single - (int(tot.n_modified) * 20 + 2 * 16 * int(tot.seq16_used) + 2 * 32 * int(tot.qual16_used))
+    scan_bytes = single - (tot["n_modified"] * 20 + 2 * 16 * tot["seq16_used"] + 2 * 32 * tot["qual16_used"])
     # DRAM bytes of one pass from the committed ncu --set full capture (profiles/), when it is of this workload
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")) as f:
-            tj = json.load(f)
-        if tj["workload"] == cfg.name and tj["windows"] == n_w:
-            traffic, traffic_src = tj["dram_bytes_per_pass"], tj["source"]
-    except Exception:
-        pass
+    traffic, traffic_src, tj = None, None, None
+    for tf in ("r02_final_traffic.json", "r01_final_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                tj = json.load(f)
+            if tj["workload"] == cfg.name and tj["windows"] == n_w:
+                traffic, traffic_src = tj["dram_bytes_per_pass"], tj["source"]
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "masking pass = scan_kernel + resolve_lean_kernel + resolve_kernel + emit_kernel + emit_special_kernel (|| emit_many_kernel, session_kernel<fallback>)", "kernel_ms": pass_ms,
                 "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernels": stage_ms[1], "emit_kernel": stage_ms[2],
                              "fallback_kernel_tail": stage_ms[3]},
-                "scan_kernel_gbs": scan_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else None,
                 # the dominant kernel on its own: its algorithmic bytes are the inputs, read once
                 "dominant_kernel": {"name": "scan_kernel", "ms": stage_ms[0], "algorithmic_bytes": scan_bytes,
                                     "achieved": scan_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else None,
@@ -473,86 +624,201 @@ def main():
                                     "traffic": (tj["per_kernel"]["scan_kernel"][0] + tj["per_kernel"]["scan_kernel"][1]) if traffic else None},
                 "kernel_share_of_step": pass_ms / (ms / args.steps),
                 "algorithmic_bytes_per_launch": single, "bytes_per_session_read": single / max(1, session_reads),
-                "survey_8d_bytes_per_launch": survey, "survey_8d_achieved": survey / (pass_ms * 1e-3) / 1e9,
-                "survey_8d_frac": survey / (pass_ms * 1e-3) / 1e9 / peak}
+                "two_pass_reference_traffic": {"note": "SURVEY 8(d) counts the read arrays twice (discover, then mask); not a roofline fraction of this single-pass design",
+                                               "bytes_per_launch": two_pass}}
 
-    # ---- end to end through the host entry (pinned host SoA in, host records out)
+    # ---- end to end through the host entry (pinned host SoA in, host records out), every rank on its own shard
     e2e = None
+    parity_e2e = None
+    host_pieces = None
     if not args.no_e2e:
-        hb = HostBatch(db.to_host(), ds.to_host())
-        hres = HostResult(n_w, dres.cap_records, dres.cap_seq16, dres.cap_qual16)
-        eng.run_host(hb, hres, args.chunk_sessions)            # warm-up: allocates the lane buffers
+        host_pieces = []
+        for p in run.pieces:
+            hb = HostBatch(p.db.to_host(), p.ds.to_host())
+            hres = HostResult(p.nw, p.dres.cap_records, p.dres.cap_seq16, p.dres.cap_qual16)
+            host_pieces.append((p, hb, hres))
+
+        traffic_now = [0, 0]
+
+        def e2e_step():
+            traffic_now[0] = traffic_now[1] = 0
+            for p, hb, hres in host_pieces:
+                eng.run_host(hb, hres, args.chunk_sessions)
+                a, b = eng.host_traffic()
+                traffic_now[0] += a
+                traffic_now[1] += b
+        e2e_step()                                             # warm-up: allocates the lane buffers
         barrier()
         sampler.start()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            th = eng.run_host(hb, hres, args.chunk_sessions)
+            e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
         sampler.stop()
-        h2d, d2h = eng.host_traffic()
-        assert int(th.session_reads) == session_reads and int(th.n_modified) == int(tot.n_modified), "host path disagrees with device path"
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        io = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-            dist.all_reduce(io)
-        e2e = {"value": total_reads * args.e2e_steps / float(t_e.item()), "unit": UNIT,
+        h2d, d2h = traffic_now
+        for p, hb, hres in host_pieces:
+            assert int(hres.totals.session_reads) == int(p.tot.session_reads) and int(hres.totals.n_modified) == int(p.tot.n_modified), "host path disagrees with device path"
+        t_e = float(allmax(torch.tensor([dt], dtype=torch.float64, device=dev)).item())
+        io = allsum(torch.tensor([h2d, d2h], dtype=torch.int64, device=dev))
+        e2e = {"value": total_reads * args.e2e_steps / t_e, "unit": UNIT,
                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * float(t_e.item()) / args.e2e_steps,
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * t_e / args.e2e_steps,
+               "h2d_bytes_per_session_read": int(io[0].item()) / max(1, total_reads),
                "api": "ga_run_host (C ABI), pinned host SoA in / host records out", "chunk_sessions": args.chunk_sessions}
-        del hb, hres
 
-    # ---- next row of the scope table: FASTQ rendering of the masked reads, device resident
-    bam = None
+    # ---- CPU baseline = the oracle on the whole N=1 workload, and record-by-record parity against it (rank 0, N=1);
+    #      at N>1 every rank checks a 1,500-session sample of its shard against the oracle, live
+    cpu = None
+    parity_records = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        threads = oracle.n_threads()
+        if world == 1 and len(run.pieces) == 1:
+            if host_pieces is not None:
+                hb_np, hs_np = host_pieces[0][1].batch, host_pieces[0][1].sessions
+            else:
+                hb_np, hs_np = p0.db.to_host(), p0.ds.to_host()
+            ref_host = SD.reference_device(cfg, dev).cpu().numpy().tobytes()
+            if args.sample_windows:
+                sb, ss, sref = host_sample(cfg, min(n_w, args.sample_windows), dev)
+                dt, raw = time_oracle(sb, ss, sref, threads)
+                sample = f"first {min(n_w, args.sample_windows)} of {n_w} windows"
+            else:
+                time_oracle(*host_sample(cfg, min(n_w, 64), dev), threads)         # pages the library in
+                t0 = time.perf_counter()
+                raw, st = oracle.run(hb_np, hs_np, ref_host, threads=threads, decode=False, cap_frac=0.25)
+                dt = time.perf_counter() - t0
+                if st != 0:
+                    raise RuntimeError(f"oracle failed with status {st}")
+                sample = f"all {n_w} windows of the workload"
+            cpu_reads = int(raw["totals"].session_reads)
+            cpu = {"value": cpu_reads / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{sample} ({cpu_reads} session reads), one pass, {dt:.2f} s"}
+            if not args.sample_windows:
+                n_exp = int(raw["totals"].n_modified)
+                edig, ekeys, ehash = oracle.digest(raw["result"], n_exp, records=True, **p0.ids)
+                _, gkeys, ghash = eng.digest(p0.dres, int(p0.tot.n_modified), records=True, **p0.ids)
+                bad = oracle.compare_records(gkeys.cpu().numpy(), ghash.cpu().numpy(), ekeys, ehash)
+                counts_ok = np.array_equal(p0.dres.sess_counts.view(-1, 4)[:n_w].cpu().numpy().view(np.uint32), raw["counts"][:n_w])
+                parity_records = {"ga_run": "ok" if bad == 0 and counts_ok else f"MISMATCH({bad} records, counters {'ok' if counts_ok else 'differ'})",
+                                  "records_compared": n_exp, "sessions_compared": n_w,
+                                  "how": "every modified record: (session, read) key, new length, bases and printed qualities as a 128-bit hash (include/ga_digest.h), engine vs oracle run live on the same sessions"}
+                if host_pieces is not None:
+                    hres = host_pieces[0][2]
+                    _, hkeys, hhash = oracle.digest(hres.as_struct(), int(hres.totals.n_modified), records=True, **p0.ids)
+                    bad_h = oracle.compare_records(hkeys, hhash, ekeys, ehash)
+                    hc_ok = np.array_equal(hres.sess_counts.numpy().view(np.uint32)[:4 * n_w].reshape(-1, 4), raw["counts"][:n_w])
+                    parity_records["ga_run_host"] = "ok" if bad_h == 0 and hc_ok else f"MISMATCH({bad_h} records, counters {'ok' if hc_ok else 'differ'})"
+                del ekeys, ehash, gkeys, ghash
+            del raw
+        else:
+            n_s = min(1500, p0.nw)
+            sb, ss = SD.generate_device(p0.cfg, dev, p0.w0, n_s)
+            hb_s, hs_s = sb.to_host(), ss.to_host()
+            del sb, ss
+            ref_host = SD.reference_device(p0.cfg, dev).cpu().numpy().tobytes()
+            raw, st = oracle.run(hb_s, hs_s, ref_host, threads=max(1, threads // world), decode=False)
+            ids = dict(p0.ids)
+            ids["n_tumor"] = hb_s.n_tumor
+            _, ekeys, ehash = oracle.digest(raw["result"], int(raw["totals"].n_modified), records=True, **ids)
+            _, gkeys, ghash = eng.digest(p0.dres, int(p0.tot.n_modified), records=True, **p0.ids)
+            # the piece's tumor reads of the sampled sessions keep their ids; normal ordinals are counted per dataset too
+            sel = (gkeys[:, 0] >= p0.g) & (gkeys[:, 0] < p0.g + n_s)
+            bad = oracle.compare_records(gkeys[sel].cpu().numpy(), ghash[sel].cpu().numpy(), ekeys, ehash) if st == 0 else -1
+            bad_all = allsum(torch.tensor([bad if bad >= 0 else 1 << 40, int(raw["totals"].n_modified)], dtype=torch.int64, device=dev))
+            parity_records = {"every_rank_sample_vs_live_oracle": "ok" if int(bad_all[0].item()) == 0 else f"MISMATCH({int(bad_all[0].item())})",
+                              "records_compared": int(bad_all[1].item()), "sessions_per_rank": n_s}
+            del raw
+    if host_pieces is not None:
+        del host_pieces
+    torch.cuda.empty_cache()
+
+    # ---- next rows of the scope table: BAM decode, file path, FASTQ rendering (rank 0, N=1)
+    bam = files = fastq = None
     if rank == 0 and world == 1 and not args.no_bam:
         bam = bench_bam_decode()
-    files = None
-    if rank == 0 and world == 1 and not args.no_bam:
         try:
             files = bench_file_path(local)
         except Exception as exc:                                          # a side measurement must not take the bench line down
             files = {"error": repr(exc)}
-    fastq = None
     if rank == 0 and world == 1 and not args.no_fastq:
         fastq = bench_fastq(eng, cfg, dev, min(n_w, args.fastq_windows), peak)
+    main_cfg = {"workload": wname if world == 1 or args.workload else f"{wname} sessions [0, {REGION * world})", "windows_per_gpu": n_w, "read_len": cfg.read_len,
+                "coverage": [cfg.cov_tumor, cfg.cov_normal], "session_reads_per_gpu": session_reads,
+                "modified_records_per_gpu": tot["n_modified"], "modified_records": total_modified,
+                "fallback_sessions_per_gpu": n_fallback, "fallback_reasons": fallback_reasons, "masked_snv_del_ins": tot["masked"],
+                "sharding": sharding_note, "host_numa_binding": numa,
+                "l2_policy": f"inputs ({sum(p.db.seq4_bytes + 20 * p.db.n_reads for p in run.pieces) / 1e9:.2f} GB per step) exceed the 126 MB L2"}
+    run.free()
+    del run
 
-    # ---- CPU baseline on a bounded sample + parity of the sampled sessions (rank 0, N=1)
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        oracle.build()
-        threads = oracle.n_threads()
-        n_s = args.sample_windows
-        if not n_s:
-            pb, ps, pref = host_sample(cfg, min(n_w, 64), dev)
-            dt, _ = time_oracle(pb, ps, pref, threads)
-            dt, _ = time_oracle(pb, ps, pref, threads)
-            n_s = int(min(n_w, max(64, 12.0 / max(dt / min(n_w, 64), 1e-6))))
-        sb, ss, sref = host_sample(cfg, n_s, dev)
-        dt, raw = time_oracle(sb, ss, sref, threads)
-        cpu_reads = int(raw["totals"].session_reads)
-        cpu = {"value": cpu_reads / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {n_s} of {n_w} windows ({cpu_reads} session reads), one pass, {dt:.2f} s"}
-        got = dres.sess_counts.view(-1, 4)[:n_s].cpu().numpy().view(np.uint32)
-        parity = "ok" if np.array_equal(got, raw["counts"][:n_s]) else "MISMATCH"
+    # ---- strong scaling: the WHOLE wgs-30x genome cut across the ranks, and the other BASELINE workloads
+    def side_run(name, steps=3):
+        cs = SD.genome_contigs(name)
+        spans = sharding.shard_sessions(SD.genome_session_weights(cs), world)
+        r = ShardRun(eng, dev, cs, SD.genome_pieces(cs, *spans[rank]))
+
+        def st():
+            r.step()
+            if world > 1:
+                r.counters(counters)
+                dist.all_reduce(counters)
+        t_ms = timed_steps(st, steps, 3, barrier)
+        tt = r.totals()
+        hist = min(steps * len(r.pieces), 32)
+        km = [x for x in eng.kernel_ms_history(hist) if x > 0]
+        stg = []
+        for s_i in range(4):
+            h = [x for x in eng.stage_ms_history(s_i, hist) if x >= 0]
+            stg.append(sum(h) / len(h) * len(r.pieces) if h else None)
+        nfb, why = r.fallbacks()
+        t_max = float(allmax(torch.tensor([t_ms], dtype=torch.float64, device=dev)).item())
+        w = allsum(torch.tensor([tt["session_reads"], tt["session_bases"], tt["n_modified"], nfb, why[8]] + tt["masked"], dtype=torch.int64, device=dev)).tolist()
+        d = u64(allsum(r.digest()))
+        wd = committed_digest(name)
+        out = {"workload": name, "contigs": len(cs), "sessions": int(sum(c.total_windows for c in cs)), "session_reads": int(w[0]),
+               "modified_records": int(w[2]), "masked_snv_del_ins": [int(x) for x in w[5:8]], "steps": steps, "ms_per_step": t_max / steps,
+               "value": w[0] * steps / (t_max * 1e-3), "unit": UNIT, "bases_per_s": w[1] * steps / (t_max * 1e-3),
+               "sessions_per_rank": [b - a for a, b in spans], "pieces_this_rank": len(r.pieces),
+               "pass_ms_rank0": sum(km) / len(km) * len(r.pieces) if km else None,
+               "stage_ms_rank0": {"scan_kernel": stg[0], "resolve_kernels": stg[1], "emit_kernel": stg[2], "fallback_kernel_tail": stg[3]},
+               "fallback_sessions": int(w[3]), "sessions_resolved_by_the_one_cta_kernel": int(w[4]),
+               "digest": d, "oracle_digest": wd,
+               "parity_records": "unchecked (no committed oracle digest)" if wd is None else ("ok" if d == wd else "MISMATCH")}
+        r.free()
+        return out
+
+    strong = None
+    if not args.no_strong and not args.windows and not args.workload:
+        strong = side_run(args.strong_workload)
+        strong["scaling"] = "strong"
+        strong["parity_across_n"] = strong["parity_records"] + " (every GPU count is compared with the same oracle digest of the whole genome)"
+    others = {}
+    if args.others == "auto":
+        names = ["cigar-stress", "dense-60x30x", "chr22-1k"] if world == 1 else ["dense-60x30x", "cigar-stress"] + (["wgs-60x30x"] if world >= 4 else [])
+    else:
+        names = [x for x in args.others.split(",") if x and x != "none"]
+    if not args.windows:
+        for nm in names:
+            others[nm] = side_run(nm)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": cfg.name, "windows_per_gpu": n_w, "read_len": cfg.read_len,
-                           "coverage": [cfg.cov_tumor, cfg.cov_normal], "session_reads_per_gpu": session_reads,
-                           "modified_records_per_gpu": int(tot.n_modified),
-                           "fallback_sessions_per_gpu": n_fallback, "fallback_reasons": fallback_reasons, "masked_snv_del_ins": [int(x) for x in tot.masked],
-                           "sharding": "one contig-sized region per GPU, no data-path collective" if world > 1 else "single GPU",
-                           "host_numa_binding": numa,
-                           "l2_policy": f"inputs ({(db.seq4_bytes + 20 * db.n_reads) / 1e9:.2f} GB per step) exceed the 126 MB L2"},
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": main_cfg,
                 "bases_per_s": total_bases * args.steps / (ms_max * 1e-3),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq": fastq, "bam_decode": bam, "file_path": files, "gpu_launches": total_launches,
-                "clocks": sampler.summary(), "parity_vs_oracle_on_sample": parity}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_records": parity_records, "parity_digest": parity_digest,
+                "strong": strong, "other_workloads": others,
+                "fastq": fastq, "bam_decode": bam, "file_path": files, "gpu_launches": total_launches,
+                "clocks": sampler.summary()}
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "ref_timing.json")) as f:
+                line["cpu_baseline_reference_python"] = json.load(f)
+        except Exception:
+            pass
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -74,6 +74,58 @@ WORKLOADS = {
 }
 
 
+# GRCh38 primary assembly lengths: the contigs of the whole-genome workloads
+HUMAN_CONTIGS = (("chr1", 248_956_422), ("chr2", 242_193_529), ("chr3", 198_295_559), ("chr4", 190_214_555), ("chr5", 181_538_259),
+                 ("chr6", 170_805_979), ("chr7", 159_345_973), ("chr8", 145_138_636), ("chr9", 138_394_717), ("chr10", 133_797_422),
+                 ("chr11", 135_086_622), ("chr12", 133_275_309), ("chr13", 114_364_328), ("chr14", 107_043_718), ("chr15", 101_991_189),
+                 ("chr16", 90_338_345), ("chr17", 83_257_441), ("chr18", 80_373_285), ("chr19", 58_617_616), ("chr20", 64_444_167),
+                 ("chr21", 46_709_983), ("chr22", 50_818_468), ("chrX", 156_040_895), ("chrY", 57_227_415))
+GENOME_LEN = sum(n for _, n in HUMAN_CONTIGS)
+
+# Whole-genome workloads: (per-contig template, somatic variants over the whole genome).  Contig k gets the template's
+# densities on its own length, round(total * len / genome) windows and seed + 7919 k, so contig 0 of "wgs-30x" IS the
+# workload "chr1-30x-50k" (BASELINE config 2) and the genome is the north star's "synthetic 30x WGS tumor-normal pair";
+# "wgs-60x30x" is BASELINE configs 4 / 5 at full scale: 1,000,000 somatic variants, 60x tumor / 30x normal.
+GENOMES = {
+    "wgs-30x": ("chr1-30x-50k", round(50_000 * GENOME_LEN / 248_956_422)),
+    "wgs-60x30x": ("dense-60x30x", 1_000_000),
+}
+
+
+def genome_contigs(name: str):
+    """The per-contig SynthConfigs of workload `name`, in genome order; a single-contig workload is a genome of one."""
+    if name in WORKLOADS:
+        return [WORKLOADS[name]]
+    base_name, total = GENOMES[name]
+    base = WORKLOADS[base_name]
+    out = []
+    for k, (cname, clen) in enumerate(HUMAN_CONTIGS):
+        nw = base.total_windows if (clen == base.contig_len and name == "wgs-30x") else max(1, round(total * clen / GENOME_LEN))
+        out.append(replace(base, name=f"{name}:{cname}", contig_len=clen, total_windows=nw, seed=base.seed + 7919 * k))
+    return out
+
+
+def genome_session_weights(contigs) -> np.ndarray:
+    """Session reads of every session of the genome-ordered session list (what shard_sessions balances by)."""
+    parts = []
+    for c in contigs:
+        pl = c.plan(0, 0)
+        parts.append(np.full(c.total_windows, int(pl.reads_per_window[0]) + int(pl.reads_per_window[1]), np.int64))
+    return np.concatenate(parts)
+
+
+def genome_pieces(contigs, s_begin: int, s_end: int):
+    """Sessions [s_begin, s_end) of the genome-ordered session list as per-contig pieces
+    [(contig index, first window, windows, global index of the piece's first session)]."""
+    out, base = [], 0
+    for k, c in enumerate(contigs):
+        lo, hi = max(s_begin, base), min(s_end, base + c.total_windows)
+        if hi > lo:
+            out.append((k, lo - base, hi - lo, lo))
+        base += c.total_windows
+    return out
+
+
 def _check(st, what):
     if st != _abi.GA_OK:
         raise RuntimeError(f"{what} failed with ga status {st}")

@@ -265,3 +265,27 @@ def test_large_files_are_read_one_contig_at_a_time(tmp_path, monkeypatch):
     with GF.BamFile(p) as f:                                         # references interleaved: the whole stream is kept
         assert [int(f.contig_sizes(c).n_reads) for c in f.references] == [80, 40]
         assert GF.pack_tumor_normal(f, f, "b").batch.n_reads == 80
+
+
+@pytest.mark.parametrize("flag", [0x800, 0x4])
+def test_entry_point_refuses_supplementary_and_unmapped_records(tmp_path, flag):
+    """The reference's supplementary / unmapped-mate bookkeeping (anonymizer_methods.py:98-149, SR.py:561-600) is not
+    implemented: the entry point says so instead of treating such records as ordinary alignments (no engine is needed
+    to find out - the check runs on the packed flags before any device work)."""
+    from genomeanonymizer_b200 import genome_files as GF
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import anonymize_genome
+    case = dict(GENOME[0]["case"])
+    reads = [dict(r) for r in case["reads"]]
+    reads[5]["flag"] |= flag
+    case["reads"] = reads
+    t, n, fa, vc = H.write_sample_files(str(tmp_path), case, GENOME[0]["vcf"])
+    f = GF.FastaFile(fa)
+    order = {name: k for k, name in enumerate(f.references)}
+    f.close()
+    windows = GF.windows_by_contig(GF.read_vcf(vc), order)
+    with pytest.raises(ValueError, match="supplementary"):
+        anonymize_genome(windows, t, n, fa, None, str(tmp_path / "T.out"), str(tmp_path / "N.out"))
+    # secondary records are first-wins in the reference too: not refused by the flag check
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import _refuse_unsupported_records
+    import numpy as np
+    _refuse_unsupported_records(np.array([(0x100 | 0x1 | 0x40) << 16 | 150], np.uint32), "c")
