@@ -390,10 +390,28 @@ class ShardRun:
             self.pieces.append(p)
         torch.cuda.empty_cache()
         self.sessions = sum(p.nw for p in self.pieces)
+        # several pieces (the contigs of a genome): one stream each, up to the engine's three lanes, so that the
+        # persistent kernels of one contig fill the SMs the tail of another leaves idle (ga_run: a lane per stream)
+        self.streams = [torch.cuda.Stream(dev) for _ in range(min(3, len(self.pieces)))] if len(self.pieces) > 1 else []
+        self.ev_fork = torch.cuda.Event()
+        self.ev_join = [torch.cuda.Event() for _ in self.streams]
 
     def step(self):
-        for p in self.pieces:
-            self.eng.run_device(p.db, p.ds, p.dres)
+        import torch
+        if not self.streams:
+            for p in self.pieces:
+                self.eng.run_device(p.db, p.ds, p.dres)
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        self.ev_fork.record(cur)
+        for i, p in enumerate(self.pieces):
+            st = self.streams[i % len(self.streams)]
+            if i < len(self.streams):
+                st.wait_event(self.ev_fork)
+            self.eng.run_device(p.db, p.ds, p.dres, stream=st)
+        for st, ev in zip(self.streams, self.ev_join):
+            ev.record(st)
+            cur.wait_event(ev)
 
     def totals(self):
         """Checks every piece's device status; sums of the totals over the pieces."""
@@ -409,9 +427,10 @@ class ShardRun:
 
     def counters(self, out):
         """Masking counters of this shard (SR.py:198-204) into the int64[8] device tensor `out`."""
+        import torch
         out.zero_()
         for p in self.pieces:
-            out[:3] += p.dres.sess_counts.view(-1, 4)[:p.nw, :3].sum(0)
+            out[:3] += p.dres.totals.view(torch.int64)[6:9]          # ga_totals.masked = sum of the sessions' counters
 
     def digest(self):
         import torch

@@ -177,6 +177,7 @@ int ga_engine_create(int device, ga_engine** out) {
         cudaStreamCreateWithPriority(&e->lanes[l].side, cudaStreamNonBlocking, hi);
         cudaEventCreateWithFlags(&e->lanes[l].ev_fork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->lanes[l].ev_join, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->lanes[l].ev_done, cudaEventDisableTiming);
     }
     cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::WarpSmem) * (ga::kScanThreads / 32)));
     cudaFuncSetAttribute(ga::scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -210,6 +211,7 @@ void ga_engine_destroy(ga_engine* e) {
         if (L.side) cudaStreamDestroy(L.side);
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_join) cudaEventDestroy(L.ev_join);
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
         cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_many); cudaFree(L.d_many_recs); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) if (L.ev[j][k]) cudaEventDestroy(L.ev[j][k]);
     }
@@ -307,14 +309,25 @@ static int ensure_big_scratch(ga_engine* e, Lane& L) {
     return GA_OK;
 }
 
+// A run uses one lane (scratch + side stream).  Runs launched on ONE stream share a lane - stream order keeps them
+// apart; a run on another stream takes another lane, so that up to kLanes runs (e.g. the contigs of a genome, one
+// stream each) overlap: the persistent kernels of one run fill the SMs that the tail of another leaves idle.  With
+// more streams than lanes a lane is reused and the new run waits for the lane's previous one.
 int ga_run(ga_engine* e, const ga_reads* R, const ga_sessions* S, ga_result* out, void* stream_) {
-    return ga_run_lane(e, 0, R, S, out, (cudaStream_t)stream_);
+    if (!e) return GA_ERR_BAD_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream_;
+    int lane = -1;
+    for (int l = 0; l < kLanes && lane < 0; ++l) if (e->lanes[l].used && e->lanes[l].last_stream == st) lane = l;
+    for (int l = 0; l < kLanes && lane < 0; ++l) if (!e->lanes[l].used) lane = l;
+    if (lane < 0) { lane = e->next_lane; e->next_lane = (e->next_lane + 1) % kLanes; }
+    e->last_lane = lane;
+    return ga_run_lane(e, lane, R, S, out, st);
 }
 
 // Duration (ms) between events ev[a] and ev[b] of the most recent runs, out[0] = latest.
 static int stage_history(ga_engine* e, int a, int b, float* out, int n) {
     if (!e || !out || n < 0) return 0;
-    Lane& L = e->lanes[0];
+    Lane& L = e->lanes[e->last_lane];
     const int have = (int)std::min<int64_t>(std::min<int64_t>(L.runs, kTimedRuns), n);
     for (int k = 0; k < have; ++k) {
         const int slot = (int)((L.runs - 1 - k) % kTimedRuns);
@@ -336,7 +349,7 @@ int ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons) {
     if (!e) return -1;
     int32_t h[16] = {0};
     if (cudaSetDevice(e->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
-        cudaMemcpy(h, e->lanes[0].d_small, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        cudaMemcpy(h, e->lanes[e->last_lane].d_small, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     for (int k = 0; reasons && k < n_reasons && k < 9; ++k) reasons[k] = h[4 + k];
     return h[0];
 }
@@ -361,6 +374,9 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     if (it == e->refs.end()) return fail(e, GA_ERR_BAD_ARGUMENT, "ga_run: reference contig was not uploaded");
     Lane& L = e->lanes[lane];
     GA_CUDA(cudaSetDevice(e->device));
+    if (L.used && L.last_stream != st) GA_CUDA(cudaStreamWaitEvent(st, L.ev_done, 0));   // the lane's scratch is still the previous run's
+    L.used = true; L.last_stream = st;
+    struct DoneMark { Lane& L; cudaStream_t st; ~DoneMark() { cudaEventRecord(L.ev_done, st); } } done_mark{L, st};
     int rc = ensure_session_scratch(e, L, S->n_sessions); if (rc) return rc;
     rc = ensure_big_scratch(e, L); if (rc) return rc;
 

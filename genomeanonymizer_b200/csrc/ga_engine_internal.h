@@ -23,6 +23,8 @@ struct Lane {
     // ev[0] start | scan | ev[1] | resolve (lean + large) | ev[2] | emission | ev[3] | wait for the fallback kernel | ev[4]
     cudaEvent_t ev[5][32] = {};
     int64_t runs = 0;
+    // the stream the lane's most recent run was launched on and the end of that run: a run on another stream waits for it
+    cudaStream_t last_stream = nullptr; bool used = false; cudaEvent_t ev_done = nullptr;
 };
 constexpr int kTimedRuns = 32;
 
@@ -39,6 +41,7 @@ struct ga_engine {
     int64_t big_bytes_per_cta = 0; int big_ctas = 0;
     int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
     int64_t launches = 0;
+    int last_lane = 0, next_lane = 0;        // ga_run: lane of the most recent run; round-robin cursor when every lane is taken
     int occ_scan = 4, occ_lean = 9, occ_res = 6;   // resident CTAs per SM of the persistent kernels
     HostSlot* slots = nullptr;           // lazily created by ga_run_host
     int64_t last_h2d = 0, last_d2h = 0;

@@ -215,3 +215,43 @@ def test_device_digest_accumulates_over_shards(engine):
         engine.digest(dres, int(tot.n_modified), session_base=w0, tumor_base=w0 * per_t, normal_base=w0 * per_n, n_tumor=db.n_tumor,
                       accumulate=acc)
     assert np.array_equal(acc.cpu().numpy(), full)
+
+
+@pytest.mark.gpu
+def test_runs_on_several_streams_overlap_on_the_engine_lanes_and_stay_correct(engine):
+    """ga_run gives every stream its own lane (scratch + side stream); with more streams than lanes a lane is reused
+    behind the run that held it.  Five shards on five streams, three rounds, in flight together: every round's
+    records must equal the one-stream result."""
+    import torch
+    from genomeanonymizer_b200.engine import DeviceResult
+    cfg = SD.WORKLOADS["tiny-stress"]
+    dev = torch.device("cuda", 0)
+    engine.upload_reference(0, SD.reference_device(cfg, dev))
+    pl = cfg.plan()
+    per_t, per_n = pl.reads_per_window
+    cuts = [(0, 5), (5, 4), (9, 6), (15, 2), (17, 7)]
+    shards = []
+    for w0, nw in cuts:
+        db, ds = SD.generate_device(cfg, dev, w0, nw)
+        units = db.seq4_bytes // 16
+        shards.append((db, ds, DeviceResult(nw, db.n_reads + 16, 2 * units + 64, 2 * units + 64, dev), w0))
+    want = torch.zeros(4, dtype=torch.int64, device=dev)
+    for db, ds, dres, w0 in shards:
+        engine.run_device(db, ds, dres)
+        torch.cuda.synchronize()
+        t = engine.check_device_status(dres)
+        engine.digest(dres, int(t.n_modified), session_base=w0, tumor_base=w0 * per_t, normal_base=w0 * per_n, n_tumor=db.n_tumor, accumulate=want)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev) for _ in shards]
+    for _ in range(3):
+        for (db, ds, dres, w0), st in zip(shards, streams):
+            dres.out_seq4.zero_(); dres.mod_len.zero_()
+        torch.cuda.synchronize()
+        for (db, ds, dres, w0), st in zip(shards, streams):
+            engine.run_device(db, ds, dres, stream=st)
+        torch.cuda.synchronize()
+        got = torch.zeros(4, dtype=torch.int64, device=dev)
+        for db, ds, dres, w0 in shards:
+            t = engine.check_device_status(dres)
+            engine.digest(dres, int(t.n_modified), session_base=w0, tumor_base=w0 * per_t, normal_base=w0 * per_n, n_tumor=db.n_tumor, accumulate=got)
+        assert np.array_equal(got.cpu().numpy(), want.cpu().numpy()) and int(want[2]) > 100
