@@ -646,46 +646,63 @@ def main():
                 "two_pass_reference_traffic": {"note": "SURVEY 8(d) counts the read arrays twice (discover, then mask); not a roofline fraction of this single-pass design",
                                                "bytes_per_launch": two_pass}}
 
-    # ---- end to end through the host entry (pinned host SoA in, host records out), every rank on its own shard
+    # ---- end to end through the host entries, every rank on its own shard: host buffers in pinned memory in, compacted
+    #      records in host memory out.  `e2e` = ga_run_wire (include/ga_wire.h: ~44 bytes per read over PCIe, expanded on
+    #      the device); `e2e.soa` = ga_run_host over the plain structure of arrays (~100 bytes per read).
     e2e = None
-    parity_e2e = None
     host_pieces = None
     if not args.no_e2e:
+        from genomeanonymizer_b200.engine import HostWire
+        from genomeanonymizer_b200.wire import pack_wire
         host_pieces = []
+        t_pack = 0.0
         for p in run.pieces:
             hb = HostBatch(p.db.to_host(), p.ds.to_host())
+            t0 = time.perf_counter()
+            wb = pack_wire(hb.batch)
+            t_pack += time.perf_counter() - t0
+            hw = HostWire(wb, hb.sessions)
             hres = HostResult(p.nw, p.dres.cap_records, p.dres.cap_seq16, p.dres.cap_qual16)
-            host_pieces.append((p, hb, hres))
-
+            host_pieces.append((p, hb, hres, hw))
         traffic_now = [0, 0]
 
-        def e2e_step():
+        def e2e_step(wire=True):
             traffic_now[0] = traffic_now[1] = 0
-            for p, hb, hres in host_pieces:
-                eng.run_host(hb, hres, args.chunk_sessions)
+            for p, hb, hres, hw in host_pieces:
+                if wire:
+                    eng.run_wire(hw, hres, args.chunk_sessions)
+                else:
+                    eng.run_host(hb, hres, args.chunk_sessions)
                 a, b = eng.host_traffic()
                 traffic_now[0] += a
                 traffic_now[1] += b
-        e2e_step()                                             # warm-up: allocates the lane buffers
-        barrier()
-        sampler.start()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        barrier()
-        sampler.stop()
-        h2d, d2h = traffic_now
-        for p, hb, hres in host_pieces:
-            assert int(hres.totals.session_reads) == int(p.tot.session_reads) and int(hres.totals.n_modified) == int(p.tot.n_modified), "host path disagrees with device path"
-        t_e = float(allmax(torch.tensor([dt], dtype=torch.float64, device=dev)).item())
-        io = allsum(torch.tensor([h2d, d2h], dtype=torch.int64, device=dev))
-        e2e = {"value": total_reads * args.e2e_steps / t_e, "unit": UNIT,
-               "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * t_e / args.e2e_steps,
-               "h2d_bytes_per_session_read": int(io[0].item()) / max(1, total_reads),
-               "api": "ga_run_host (C ABI), pinned host SoA in / host records out", "chunk_sessions": args.chunk_sessions}
+
+        def timed_e2e(wire, steps):
+            e2e_step(wire)                                         # warm-up: allocates the lane buffers
+            barrier()
+            sampler.start()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step(wire)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            sampler.stop()
+            for p, hb, hres, hw in host_pieces:
+                assert int(hres.totals.session_reads) == int(p.tot.session_reads) and int(hres.totals.n_modified) == int(p.tot.n_modified), "host path disagrees with device path"
+            t_e = float(allmax(torch.tensor([dt], dtype=torch.float64, device=dev)).item())
+            io = allsum(torch.tensor(traffic_now, dtype=torch.int64, device=dev))
+            return {"value": total_reads * steps / t_e, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+                    "steps": steps, "ms_per_step": 1e3 * t_e / steps, "h2d_bytes_per_session_read": int(io[0].item()) / max(1, total_reads)}
+        soa = timed_e2e(False, max(1, args.e2e_steps - 1))
+        soa["api"] = "ga_run_host (C ABI), pinned host structure of arrays in / host records out"
+        soa_digest = None
+        if world == 1 and len(host_pieces) == 1:
+            from oracle import oracle as _o
+            soa_digest = _o.digest(host_pieces[0][2].as_struct(), int(host_pieces[0][2].totals.n_modified), records=True, **run.pieces[0].ids)
+        e2e = timed_e2e(True, args.e2e_steps)
+        e2e.update({"api": "ga_run_wire (C ABI, include/ga_wire.h), pinned host wire form in / host records out", "chunk_sessions": args.chunk_sessions,
+                    "wire_pack_ms_outside_the_timed_region": 1e3 * t_pack, "wire_bytes_per_gpu": sum(x[3].bytes for x in host_pieces), "soa": soa})
 
     # ---- CPU baseline = the oracle on the whole N=1 workload, and record-by-record parity against it (rank 0, N=1);
     #      at N>1 every rank checks a 1,500-session sample of its shard against the oracle, live
@@ -726,11 +743,14 @@ def main():
                                   "records_compared": n_exp, "sessions_compared": n_w,
                                   "how": "every modified record: (session, read) key, new length, bases and printed qualities as a 128-bit hash (include/ga_digest.h), engine vs oracle run live on the same sessions"}
                 if host_pieces is not None:
-                    hres = host_pieces[0][2]
+                    hres = host_pieces[0][2]                       # holds the result of the last ga_run_wire call
                     _, hkeys, hhash = oracle.digest(hres.as_struct(), int(hres.totals.n_modified), records=True, **p0.ids)
                     bad_h = oracle.compare_records(hkeys, hhash, ekeys, ehash)
                     hc_ok = np.array_equal(hres.sess_counts.numpy().view(np.uint32)[:4 * n_w].reshape(-1, 4), raw["counts"][:n_w])
-                    parity_records["ga_run_host"] = "ok" if bad_h == 0 and hc_ok else f"MISMATCH({bad_h} records, counters {'ok' if hc_ok else 'differ'})"
+                    parity_records["ga_run_wire"] = "ok" if bad_h == 0 and hc_ok else f"MISMATCH({bad_h} records, counters {'ok' if hc_ok else 'differ'})"
+                    if soa_digest is not None:
+                        bad_s = oracle.compare_records(soa_digest[1], soa_digest[2], ekeys, ehash)
+                        parity_records["ga_run_host"] = "ok" if bad_s == 0 else f"MISMATCH({bad_s} records)"
                 del ekeys, ehash, gkeys, ghash
             del raw
         else:

@@ -43,6 +43,18 @@ class GaFastqItems(C.Structure):
     _fields_ = [("n_items", C.c_int64), ("read", _vp), ("record", _vp), ("names", _vp), ("name_off", _vp)]
 
 
+class GaWireDir(C.Structure):
+    _fields_ = [("byte", C.c_uint64), ("read", C.c_uint32), ("unit", C.c_uint32), ("ops", C.c_uint32), ("pos", C.c_int32),
+                ("reserved", C.c_uint32 * 2)]
+
+
+class GaReadsWire(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_tumor", C.c_int64), ("n_blocks", C.c_int64), ("n_tumor_blocks", C.c_int64),
+                ("blob", _vp), ("blob_bytes", C.c_int64), ("dir", _vp),
+                ("qual", _vp), ("n_qual", C.c_int64), ("qual_reads", _vp), ("qual_off16", _vp), ("qual_units", C.c_int64),
+                ("max_ref_span", C.c_int32), ("contig_id", C.c_int32)]
+
+
 class GaDigestIds(C.Structure):
     _fields_ = [("session_base", C.c_int64), ("tumor_base", C.c_int64), ("normal_base", C.c_int64), ("n_tumor", C.c_int64),
                 ("contig", C.c_int64)]

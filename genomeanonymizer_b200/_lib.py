@@ -11,6 +11,8 @@ _LIB = None
 # every entry point declared in include/ga_b200.h
 EXPORTS = ["ga_abi_version", "ga_status_string", "ga_engine_create", "ga_engine_destroy", "ga_last_error",
            "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions", "ga_fastq_layout", "ga_fastq_render", "ga_result_digest"]
+# include/ga_wire.h
+WIRE_EXPORTS = ["ga_wire_pack_sizes", "ga_wire_pack", "ga_run_wire"]
 # include/ga_synth.h - the synthetic-input generator lives in its own library (never needed by the masking path)
 SYNTH_LIB_PATH = os.path.join(_HERE, "libga_synth.so")
 SYNTH_EXPORTS = ["ga_synth_plan_sizes", "ga_synth_reference", "ga_synth_sessions", "ga_synth_reads_count", "ga_synth_reads_fill",
@@ -64,6 +66,12 @@ def lib():
     L.ga_result_digest.restype = C.c_int
     L.ga_result_digest.argtypes = [C.c_void_p, C.POINTER(_abi.GaResult), C.c_int64, C.POINTER(_abi.GaDigestIds), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
+    L.ga_wire_pack_sizes.restype = C.c_int
+    L.ga_wire_pack_sizes.argtypes = [C.POINTER(_abi.GaReads), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.ga_wire_pack.restype = C.c_int
+    L.ga_wire_pack.argtypes = [C.POINTER(_abi.GaReads), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]
+    L.ga_run_wire.restype = C.c_int
+    L.ga_run_wire.argtypes = [C.c_void_p, C.POINTER(_abi.GaReadsWire), C.POINTER(_abi.GaSessions), C.POINTER(_abi.GaResult), C.c_int64]
     _LIB = L
     return L
 

@@ -75,3 +75,284 @@ extern "C" int ga_result_digest(ga_engine* e, const ga_result* out, int64_t n_re
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }
+
+// =====================================================================================================================
+// Wire form (include/ga_wire.h): host packer and device expansion.
+#include <string.h>
+#include <thread>
+#include <vector>
+#include "../../include/ga_wire.h"
+
+namespace {
+
+inline size_t align4(size_t n) { return (n + 3) & ~(size_t)3; }
+
+struct BlockPlan { int64_t r0; uint32_t n, n_words, n_gen, n_gen_ops, n_exc, units, ops; uint64_t bytes; };
+
+inline bool is_generic(const ga_reads* R, int64_t r, uint32_t L) {
+    const uint32_t c0 = R->cigar_off[r], c1 = R->cigar_off[r + 1];
+    return !(c1 - c0 == 1u && (R->cigar[c0] & 15u) == 0u && (R->cigar[c0] >> 4) == L);
+}
+inline uint32_t units_of_len(uint32_t L) { return L ? (L + 31u) / 32u : 1u; }
+inline bool plain_code(uint32_t c) { return c == 1u || c == 2u || c == 4u || c == 8u; }
+
+// Block boundaries of one dataset: at most GA_WIRE_BLOCK_READS reads, position differences below 65,536.
+bool cut_blocks(const ga_reads* R, int64_t lo, int64_t hi, std::vector<BlockPlan>& out) {
+    int64_t r = lo;
+    while (r < hi) {
+        BlockPlan b; memset(&b, 0, sizeof b);
+        b.r0 = r;
+        int64_t k = r + 1;
+        while (k < hi && k - r < GA_WIRE_BLOCK_READS) {
+            const int64_t d = (int64_t)R->pos[k] - R->pos[k - 1];
+            if (d < 0) return false;
+            if (d > 65535) break;
+            ++k;
+        }
+        b.n = (uint32_t)(k - r);
+        out.push_back(b);
+        r = k;
+    }
+    return true;
+}
+
+void size_block(const ga_reads* R, BlockPlan& b) {
+    b.n_words = b.n_gen = b.n_gen_ops = b.n_exc = b.units = b.ops = 0;
+    for (int64_t r = b.r0; r < b.r0 + b.n; ++r) {
+        const uint32_t L = R->len_flag[r] & 0xffffu;
+        b.n_words += (L + 15u) / 16u;
+        b.units += units_of_len(L);
+        const uint32_t nops = R->cigar_off[r + 1] - R->cigar_off[r];
+        b.ops += nops;
+        if (is_generic(R, r, L)) { ++b.n_gen; b.n_gen_ops += nops; }
+        const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
+        for (uint32_t q = 0; q < L; ++q) { const uint32_t c = (rec[q >> 1] >> (4 * (q & 1))) & 15u; if (!plain_code(c)) ++b.n_exc; }
+    }
+    size_t bytes = 32 + 4 * (size_t)b.n + align4(2 * (size_t)b.n) + align4(2 * (size_t)b.n_gen) + 4 * ((size_t)b.n_gen + 1) + 4 * (size_t)b.n_gen_ops +
+                   4 * (size_t)b.n_exc + 4 * (size_t)b.n_words;
+    b.bytes = (bytes + 15) & ~(size_t)15;
+}
+
+void write_block(const ga_reads* R, const BlockPlan& b, uint8_t* dst) {
+    memset(dst, 0, b.bytes);
+    uint32_t* hd = reinterpret_cast<uint32_t*>(dst);
+    hd[0] = b.n; hd[1] = b.n_words; hd[2] = b.n_gen; hd[3] = b.n_gen_ops; hd[4] = b.n_exc;
+    uint32_t* lf = reinterpret_cast<uint32_t*>(dst + 32);
+    uint16_t* dpos = reinterpret_cast<uint16_t*>(dst + 32 + 4 * (size_t)b.n);
+    uint16_t* gen_idx = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(dpos) + align4(2 * (size_t)b.n));
+    uint32_t* gen_off = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(gen_idx) + align4(2 * (size_t)b.n_gen));
+    uint32_t* gen_cig = gen_off + b.n_gen + 1;
+    uint32_t* exc = gen_cig + b.n_gen_ops;
+    uint32_t* bases = exc + b.n_exc;
+    uint32_t ng = 0, ngo = 0, ne = 0, nw = 0;
+    for (uint32_t i = 0; i < b.n; ++i) {
+        const int64_t r = b.r0 + i;
+        const uint32_t L = R->len_flag[r] & 0xffffu;
+        lf[i] = R->len_flag[r];
+        dpos[i] = i ? (uint16_t)(R->pos[r] - R->pos[r - 1]) : (uint16_t)0;
+        if (is_generic(R, r, L)) {
+            gen_idx[ng] = (uint16_t)i; gen_off[ng] = ngo; ++ng;
+            for (uint32_t c = R->cigar_off[r]; c < R->cigar_off[r + 1]; ++c) gen_cig[ngo++] = R->cigar[c];
+        }
+        const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
+        for (uint32_t q = 0; q < L; ++q) {
+            const uint32_t c = (rec[q >> 1] >> (4 * (q & 1))) & 15u;
+            uint32_t two = 0;
+            if (c == 2u) two = 1; else if (c == 4u) two = 2; else if (c == 8u) two = 3;
+            else if (c != 1u) exc[ne++] = (i << 20) | (q << 4) | c;
+            bases[nw + (q >> 4)] |= two << (2 * (q & 15));
+        }
+        nw += (L + 15u) / 16u;
+    }
+    gen_off[ng] = ngo;
+}
+
+template <class F> void parallel_blocks(size_t n, int n_threads, F&& f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = n_threads > 0 ? (size_t)n_threads : (hw ? hw : 1);
+    nt = std::min(nt, std::max<size_t>(1, n));
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; ++t) th.emplace_back([&, t]() { for (size_t i = t; i < n; i += nt) f(i); });
+    for (auto& x : th) x.join();
+}
+
+int plan_wire(const ga_reads* R, int n_threads, std::vector<BlockPlan>& blocks, int64_t* n_tumor_blocks, int32_t* maxspan) {
+    if (!R || R->n_reads < 0 || R->n_tumor < 0 || R->n_tumor > R->n_reads || R->n_reads > 0x7fffffffll) return GA_ERR_BAD_ARGUMENT;
+    if (R->n_reads && (!R->pos || !R->len_flag || !R->seq_off16 || !R->cigar_off || !R->cigar || !R->seq4)) return GA_ERR_BAD_ARGUMENT;
+    if (!cut_blocks(R, 0, R->n_tumor, blocks)) return GA_ERR_BAD_ARGUMENT;
+    *n_tumor_blocks = (int64_t)blocks.size();
+    if (!cut_blocks(R, R->n_tumor, R->n_reads, blocks)) return GA_ERR_BAD_ARGUMENT;
+    parallel_blocks(blocks.size(), n_threads, [&](size_t i) { size_block(R, blocks[i]); });
+    if (maxspan) {
+        int32_t m = R->max_ref_span;
+        if (m <= 0) {
+            m = 1;
+            for (int64_t r = 0; r < R->n_reads; ++r) {
+                int32_t sp = 0;
+                for (uint32_t c = R->cigar_off[r]; c < R->cigar_off[r + 1]; ++c) {
+                    const uint32_t op = R->cigar[c] & 15u;
+                    if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) sp += (int32_t)(R->cigar[c] >> 4);
+                }
+                m = std::max(m, sp);
+            }
+        }
+        *maxspan = m;
+    }
+    return GA_OK;
+}
+
+}  // namespace
+
+extern "C" int ga_wire_pack_sizes(const ga_reads* R, int64_t* n_blocks, int64_t* n_tumor_blocks, int64_t* blob_bytes, int32_t* max_ref_span) {
+    if (!n_blocks || !n_tumor_blocks || !blob_bytes) return GA_ERR_BAD_ARGUMENT;
+    std::vector<BlockPlan> blocks;
+    const int rc = plan_wire(R, 0, blocks, n_tumor_blocks, max_ref_span);
+    if (rc) return rc;
+    uint64_t bytes = 0;
+    for (const BlockPlan& b : blocks) bytes += b.bytes;
+    *n_blocks = (int64_t)blocks.size(); *blob_bytes = (int64_t)bytes;
+    return GA_OK;
+}
+
+extern "C" int ga_wire_pack(const ga_reads* R, uint8_t* blob, int64_t blob_bytes, ga_wire_dir* dir, int64_t n_blocks, int n_threads) {
+    if (!blob && blob_bytes > 0) return GA_ERR_BAD_ARGUMENT;
+    if (!dir || (reinterpret_cast<uintptr_t>(blob) & 15u)) return GA_ERR_BAD_ARGUMENT;
+    std::vector<BlockPlan> blocks;
+    int64_t ntb = 0;
+    const int rc = plan_wire(R, n_threads, blocks, &ntb, nullptr);
+    if (rc) return rc;
+    if ((int64_t)blocks.size() != n_blocks) return GA_ERR_BAD_ARGUMENT;
+    uint64_t byte = 0, unit = 0, ops = 0;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        memset(&dir[i], 0, sizeof dir[i]);
+        dir[i].byte = byte; dir[i].read = (uint32_t)blocks[i].r0; dir[i].unit = (uint32_t)unit; dir[i].ops = (uint32_t)ops; dir[i].pos = R->pos[blocks[i].r0];
+        byte += blocks[i].bytes; unit += blocks[i].units; ops += blocks[i].ops;
+    }
+    if ((int64_t)byte != blob_bytes || unit > 0xffffffffull || ops > 0xffffffffull) return GA_ERR_BAD_ARGUMENT;
+    memset(&dir[n_blocks], 0, sizeof dir[0]);
+    dir[n_blocks].byte = byte; dir[n_blocks].read = (uint32_t)R->n_reads; dir[n_blocks].unit = (uint32_t)unit; dir[n_blocks].ops = (uint32_t)ops;
+    dir[n_blocks].pos = 0x7fffffff;
+    parallel_blocks(blocks.size(), n_threads, [&](size_t i) { write_block(R, blocks[i], blob + dir[i].byte); });
+    return GA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- device expansion
+namespace ga {
+
+__device__ __forceinline__ uint32_t wire_nibbles(uint32_t h16) {         // 8 two-bit codes -> 8 one-hot BAM nibbles
+    uint32_t t = h16 & 0xffffu;
+    t = (t | (t << 8)) & 0x00ff00ffu; t = (t | (t << 4)) & 0x0f0f0f0fu; t = (t | (t << 2)) & 0x33333333u;
+    const uint32_t b0 = t & 0x11111111u, b1 = (t >> 1) & 0x11111111u;
+    return (~(b0 | b1) & 0x11111111u) | ((b0 & ~b1) << 1) | ((b1 & ~b0) << 2) | ((b0 & b1) << 3);
+}
+__device__ __forceinline__ uint32_t keep_nibbles(uint32_t w, int n) {   // the first n nibbles of w (n may be <= 0 or >= 8)
+    return n >= 8 ? w : (n <= 0 ? 0u : (w & (0xffffffffu >> ((8 - n) * 4))));
+}
+
+constexpr int kWireThreads = 256;
+constexpr int kWirePer = GA_WIRE_BLOCK_READS / kWireThreads;             // reads per thread
+
+// One CTA expands one block into the chunk's ga_reads arrays (chunk-local offsets; tumor slice then normal slice).
+__global__ void __launch_bounds__(kWireThreads) wire_expand_kernel(const uint8_t* __restrict__ blob, const ga_wire_dir* __restrict__ dir, int nb_t, int nb_all,
+        uint64_t byte0_t, uint64_t byte0_n, uint64_t place_n, uint32_t read0_t, uint32_t read0_n, uint32_t n_t, uint32_t unit0_t, uint32_t unit0_n, uint32_t units_t,
+        uint32_t ops0_t, uint32_t ops0_n, uint32_t ops_t, uint32_t n_all, uint32_t ops_all,
+        int32_t* __restrict__ pos, uint32_t* __restrict__ len_flag, uint32_t* __restrict__ seq_off16, uint32_t* __restrict__ cigar_off,
+        uint32_t* __restrict__ cigar, uint8_t* __restrict__ seq4) {
+    __shared__ int16_t s_gen[GA_WIRE_BLOCK_READS];
+    __shared__ uint32_t s_seqoff[GA_WIRE_BLOCK_READS];
+    __shared__ uint32_t s_part[4][kWireThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ds = b >= nb_t;
+    const ga_wire_dir d = dir[b];
+    const uint8_t* blk = blob + (ds ? place_n + (d.byte - byte0_n) : d.byte - byte0_t);
+    const uint32_t r_base = ds ? n_t + (d.read - read0_n) : d.read - read0_t;
+    const uint32_t u_base = ds ? units_t + (d.unit - unit0_n) : d.unit - unit0_t;
+    const uint32_t o_base = ds ? ops_t + (d.ops - ops0_n) : d.ops - ops0_t;
+    const uint32_t* hd = reinterpret_cast<const uint32_t*>(blk);
+    const uint32_t n = hd[0], n_gen = hd[2], n_gen_ops = hd[3], n_exc = hd[4];
+    const uint32_t* lf = reinterpret_cast<const uint32_t*>(blk + 32);
+    const uint16_t* dpos = reinterpret_cast<const uint16_t*>(blk + 32 + 4ull * n);
+    const uint16_t* gen_idx = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(dpos) + ((2ull * n + 3) & ~3ull));
+    const uint32_t* gen_off = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(gen_idx) + ((2ull * n_gen + 3) & ~3ull));
+    const uint32_t* gen_cig = gen_off + n_gen + 1;
+    const uint32_t* exc = gen_cig + n_gen_ops;
+    const uint32_t* bases = exc + n_exc;
+
+    for (uint32_t i = tid; i < n; i += kWireThreads) s_gen[i] = (int16_t)-1;
+    __syncthreads();
+    for (uint32_t j = tid; j < n_gen; j += kWireThreads) s_gen[gen_idx[j]] = (int16_t)j;
+    __syncthreads();
+
+    // per-thread: kWirePer consecutive reads
+    uint32_t Lk[kWirePer], lfk[kWirePer], nops[kWirePer], dp[kWirePer];
+    uint32_t su = 0, so = 0, sw = 0, sp = 0;
+#pragma unroll
+    for (int k = 0; k < kWirePer; ++k) {
+        const uint32_t i = (uint32_t)tid * kWirePer + k;
+        lfk[k] = i < n ? lf[i] : 0u; Lk[k] = lfk[k] & 0xffffu; dp[k] = i < n ? (uint32_t)dpos[i] : 0u;
+        nops[k] = 0u;
+        if (i < n) { const int j = s_gen[i]; nops[k] = j >= 0 ? gen_off[j + 1] - gen_off[j] : 1u; }
+        su += i < n ? (Lk[k] ? (Lk[k] + 31u) >> 5 : 1u) : 0u; so += nops[k]; sw += i < n ? (Lk[k] + 15u) >> 4 : 0u; sp += dp[k];
+    }
+    // block-wide exclusive scans of the four per-thread sums
+    uint32_t v[4] = {su, so, sw, sp}, ex[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t inc = v[q];
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
+        if (lane == 31) s_part[q][warp] = inc;
+        ex[q] = inc - v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { uint32_t before = 0u; for (int w = 0; w < warp; ++w) before += s_part[q][w]; ex[q] += before; }
+
+    uint32_t u = u_base + ex[0], o = o_base + ex[1], w = ex[2], p = (uint32_t)d.pos + ex[3];
+#pragma unroll
+    for (int k = 0; k < kWirePer; ++k) {
+        const uint32_t i = (uint32_t)tid * kWirePer + k;
+        if (i >= n) break;
+        const uint32_t L = Lk[k], r = r_base + i;
+        p += dp[k];
+        pos[r] = (int32_t)p; len_flag[r] = lfk[k]; seq_off16[r] = u; cigar_off[r] = o;
+        s_seqoff[i] = u;
+        const int j = s_gen[i];
+        if (j < 0) cigar[o] = L << 4;                                    // one M op spanning the read
+        else { const uint32_t g0 = gen_off[j]; for (uint32_t c = 0; c < nops[k]; ++c) cigar[o + c] = gen_cig[g0 + c]; }
+        const uint32_t nu = L ? (L + 31u) >> 5 : 1u, nw = (L + 15u) >> 4;
+        uint4* dst = reinterpret_cast<uint4*>(seq4 + 16ull * u);
+        for (uint32_t q = 0; q < nu; ++q) {
+            const uint32_t w0 = 2 * q < nw ? bases[w + 2 * q] : 0u, w1 = 2 * q + 1 < nw ? bases[w + 2 * q + 1] : 0u;
+            const int left = (int)L - 32 * (int)q;
+            dst[q] = make_uint4(keep_nibbles(wire_nibbles(w0), left), keep_nibbles(wire_nibbles(w0 >> 16), left - 8),
+                                keep_nibbles(wire_nibbles(w1), left - 16), keep_nibbles(wire_nibbles(w1 >> 16), left - 24));
+        }
+        u += nu; o += nops[k]; w += nw;
+    }
+    if (b == nb_all - 1 && tid == 0) cigar_off[n_all] = ops_all;
+    __syncthreads();                                                      // the records of this block are written
+    // base codes other than A C G T
+    for (uint32_t x = tid; x < n_exc; x += kWireThreads) {
+        const uint32_t e = exc[x], i = e >> 20, q = (e >> 4) & 0xffffu, code = e & 15u;
+        uint32_t* word = reinterpret_cast<uint32_t*>(seq4 + 16ull * s_seqoff[i]) + (q >> 3);
+        const uint32_t sh = (q & 7u) * 4u;
+        atomicAnd(word, ~(0xfu << sh));
+        atomicOr(word, code << sh);
+    }
+}
+
+}  // namespace ga
+
+int ga_wire_expand(ga_engine* e, cudaStream_t st, const uint8_t* d_blob, const ga_wire_dir* d_dir, int n_blocks_t, int n_blocks_all,
+                   uint64_t byte0_t, uint64_t byte0_n, uint64_t place_n, uint32_t read0_t, uint32_t read0_n, uint32_t n_t,
+                   uint32_t unit0_t, uint32_t unit0_n, uint32_t units_t, uint32_t ops0_t, uint32_t ops0_n, uint32_t ops_t, uint32_t n_all, uint32_t ops_all,
+                   int32_t* pos, uint32_t* len_flag, uint32_t* seq_off16, uint32_t* cigar_off, uint32_t* cigar, uint8_t* seq4) {
+    if (n_blocks_all <= 0) return GA_OK;
+    ga::wire_expand_kernel<<<n_blocks_all, ga::kWireThreads, 0, st>>>(d_blob, d_dir, n_blocks_t, n_blocks_all, byte0_t, byte0_n, place_n, read0_t, read0_n, n_t,
+        unit0_t, unit0_n, units_t, ops0_t, ops0_n, ops_t, n_all, ops_all, pos, len_flag, seq_off16, cigar_off, cigar, seq4);
+    e->launches++;
+    GA_CUDA(cudaGetLastError());
+    return GA_OK;
+}

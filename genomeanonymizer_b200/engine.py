@@ -347,6 +347,51 @@ class HostResult:
                              v(self.sess_counts, np.uint32, self.n_sessions * 4))
 
 
+class HostWire:
+    """A WireBatch (include/ga_wire.h) + SessionTable in pinned host memory: what the plugin hands to ga_run_wire."""
+
+    def __init__(self, wire, sessions: SessionTable, pin: bool = True):
+        def pin_arr(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+            if pin and torch.cuda.is_available():
+                t = t.pin_memory()
+            return t
+        self.wire, self.sessions = wire, sessions
+        self._t = {k: pin_arr(getattr(wire, k)) for k in ("blob", "dir", "qual", "qual_reads", "qual_off16")}
+        if self._t["blob"] is not None and self._t["blob"].data_ptr() % 16:
+            raise ValueError("the wire blob must be 16-byte aligned")
+        s = sessions
+        self._s = {k: pin_arr(getattr(s, k)) for k in ("first", "last", "keep_type", "keep_pos", "keep_end", "keep_len", "keep_allele_off", "keep_alleles")}
+        self.bytes = sum(t.numel() for t in self._t.values() if t is not None) + sum(t.numel() for t in self._s.values())
+
+    def reads_struct(self) -> _abi.GaReadsWire:
+        p = lambda k: self._t[k].data_ptr() if self._t[k] is not None and self._t[k].numel() else None
+        w = self.wire
+        r = _abi.GaReadsWire()
+        r.n_reads, r.n_tumor, r.n_blocks, r.n_tumor_blocks = w.n_reads, w.n_tumor, w.n_blocks, w.n_tumor_blocks
+        r.blob, r.blob_bytes, r.dir = p("blob"), int(w.blob.nbytes), p("dir")
+        r.qual, r.qual_reads, r.qual_off16 = p("qual"), p("qual_reads"), p("qual_off16")
+        r.n_qual = 0 if w.qual_reads is None else int(len(w.qual_reads))
+        r.qual_units = int(w.qual_units)
+        r.max_ref_span, r.contig_id = int(w.max_ref_span), int(w.contig_id)
+        return r
+
+    sessions_struct = HostBatch.sessions_struct
+
+
+def _run_wire(self, hw: HostWire, hres: HostResult, chunk_sessions: int = 0) -> _abi.GaTotals:
+    """Wire form in, host records out (ga_run_wire): the end-to-end call with ~44 instead of ~100 bytes per read on PCIe."""
+    R, S, O = hw.reads_struct(), hw.sessions_struct(), hres.as_struct()
+    st = self._L.ga_run_wire(self._h, C.byref(R), C.byref(S), C.byref(O), int(chunk_sessions))
+    if st != _abi.GA_OK:
+        t = hres.totals
+        _abi.raise_for_status(st, f"{self._L.ga_last_error(self._h).decode()} (device status {t.error} at {t.error_detail}; "
+                                  f"needs records={t.n_modified} seq16={t.seq16_used} qual16={t.qual16_used})")
+    return hres.totals
+
+
 def _run_host(self, hb: HostBatch, hres: HostResult, chunk_sessions: int = 0) -> _abi.GaTotals:
     """Host buffers in, host buffers out: chunked H2D / kernels / D2H inside the C library (ga_run_host)."""
     R, S, O = hb.reads_struct(), hb.sessions_struct(), hres.as_struct()
@@ -365,6 +410,7 @@ def _host_traffic(self):
 
 
 Engine.run_host = _run_host
+Engine.run_wire = _run_wire
 Engine.host_traffic = _host_traffic
 
 

@@ -199,6 +199,16 @@ def test_engine_records_equal_oracle_records_at_scale(engine, name, w0, nw):
     assert oracle.compare_records(hkeys, hhashes, ekeys, ehashes) == 0
     assert np.array_equal(hdig, edig)
     assert np.array_equal(out.sess_counts.numpy().view(np.uint32)[:4 * nw].reshape(-1, 4), raw["counts"][:nw])
+    # the wire entry (include/ga_wire.h): same records from ~44 bytes per read
+    from genomeanonymizer_b200.engine import HostWire
+    from genomeanonymizer_b200.wire import pack_wire
+    out2 = HostResult(nw, n + 64, int(tot.seq16_used) + 64, int(tot.qual16_used) + 64)
+    tw = engine.run_wire(HostWire(pack_wire(hb), hs), out2, max(1, nw // 4))
+    assert int(tw.n_modified) == n
+    wdig, wkeys, whashes = oracle.digest(out2.as_struct(), n, records=True, **ids)
+    assert oracle.compare_records(wkeys, whashes, ekeys, ehashes) == 0
+    assert np.array_equal(wdig, edig)
+    assert np.array_equal(out2.sess_counts.numpy().view(np.uint32)[:4 * nw].reshape(-1, 4), raw["counts"][:nw])
 
 
 @pytest.mark.gpu

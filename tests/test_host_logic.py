@@ -30,6 +30,8 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(_lib.LIB_PATH)                                    # loads without a GPU; no compute call is made
     names = declared_functions()
     assert len(names) >= 17
+    wire = declared_functions(os.path.join(ROOT, "include", "ga_wire.h"))
+    assert sorted(_lib.WIRE_EXPORTS) == wire and not [n for n in wire if not hasattr(L, n)]
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert sorted(_lib.EXPORTS) == names                         # the loader binds exactly the declared surface
