@@ -441,7 +441,7 @@ class ShardRun:
 
     def fallbacks(self):
         """(sessions that took the global-scratch fallback kernel, per-reason counts) summed over the pieces (one more run each)."""
-        n, why = 0, [0] * 9
+        n, why = 0, [0] * 10
         for p in self.pieces:
             self.eng.run_device(p.db, p.ds, p.dres)
             a, b = self.eng.fallback_sessions()
@@ -815,16 +815,16 @@ def main():
             stg.append(sum(h) / len(h) * len(r.pieces) if h else None)
         nfb, why = r.fallbacks()
         t_max = float(allmax(torch.tensor([t_ms], dtype=torch.float64, device=dev)).item())
-        w = allsum(torch.tensor([tt["session_reads"], tt["session_bases"], tt["n_modified"], nfb, why[8]] + tt["masked"], dtype=torch.int64, device=dev)).tolist()
+        w = allsum(torch.tensor([tt["session_reads"], tt["session_bases"], tt["n_modified"], nfb, why[8], why[9]] + tt["masked"], dtype=torch.int64, device=dev)).tolist()
         d = u64(allsum(r.digest()))
         wd = committed_digest(name)
         out = {"workload": name, "contigs": len(cs), "sessions": int(sum(c.total_windows for c in cs)), "session_reads": int(w[0]),
-               "modified_records": int(w[2]), "masked_snv_del_ins": [int(x) for x in w[5:8]], "steps": steps, "ms_per_step": t_max / steps,
+               "modified_records": int(w[2]), "masked_snv_del_ins": [int(x) for x in w[6:9]], "steps": steps, "ms_per_step": t_max / steps,
                "value": w[0] * steps / (t_max * 1e-3), "unit": UNIT, "bases_per_s": w[1] * steps / (t_max * 1e-3),
                "sessions_per_rank": [b - a for a, b in spans], "pieces_this_rank": len(r.pieces),
                "pass_ms_rank0": sum(km) / len(km) * len(r.pieces) if km else None,
                "stage_ms_rank0": {"scan_kernel": stg[0], "resolve_kernels": stg[1], "emit_kernel": stg[2], "fallback_kernel_tail": stg[3]},
-               "fallback_sessions": int(w[3]), "sessions_resolved_by_the_one_cta_kernel": int(w[4]),
+               "fallback_sessions": int(w[3]), "sessions_resolved_by_the_one_cta_kernel": int(w[4]), "sessions_resolved_by_the_mid_one_warp_kernel": int(w[5]) - int(w[4]),
                "digest": d, "oracle_digest": wd,
                "parity_records": "unchecked (no committed oracle digest)" if wd is None else ("ok" if d == wd else "MISMATCH")}
         r.free()

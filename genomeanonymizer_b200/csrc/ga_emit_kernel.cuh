@@ -83,6 +83,137 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
     }
 }
 
+// ------------------------------------------------------------------ two edits as runs
+// After its (at most two) edits a read is a handful of RUNS: pieces of the SNV-masked source and, per masked DEL, the
+// deleted reference bases that come back (anonymizer_methods.py:188-195; all DELs, then all INSs, each at its original,
+// clamped offset: :254-270).  The leader lane of a group builds the run list in shared memory by applying the edits to
+// the list [whole read]; every output word is then merged from the runs it overlaps - no per-element loop.
+constexpr int kMaxRuns = 6;
+struct RunList { int f[kMaxRuns], len[kMaxRuns], a[kMaxRuns], kind[kMaxRuns]; int n; };   // kind 0: source from offset a; 1 + q: reference from position a, re-inserted by DEL q
+
+__device__ __noinline__ void build_runs(const Ed2& E, int L, RunList* R) {
+    int n = 1;
+    R->len[0] = L; R->a[0] = 0; R->kind[0] = 0;
+    for (int q = 0; q < E.ne; ++q) {
+        const int p = E.p[q];
+        if (q < E.n_del) {                                              // insert E.len[q] reference bases at p
+            int k = 0, acc = 0;
+            while (k < n && acc + R->len[k] < p) { acc += R->len[k]; ++k; }
+            if (k >= n) { R->len[n] = E.len[q]; R->a[n] = E.pos[q]; R->kind[n] = 1 + q; ++n; continue; }
+            const int off = p - acc;
+            for (int t = n - 1; t > k; --t) { R->len[t + 2] = R->len[t]; R->a[t + 2] = R->a[t]; R->kind[t + 2] = R->kind[t]; }
+            R->len[k + 2] = R->len[k] - off; R->a[k + 2] = R->a[k] + off; R->kind[k + 2] = R->kind[k];
+            R->len[k + 1] = E.len[q]; R->a[k + 1] = E.pos[q]; R->kind[k + 1] = 1 + q;
+            R->len[k] = off;
+            n += 2;
+        } else {                                                        // remove [p, e)
+            const int e = E.e[q];
+            int acc = 0;
+            for (int k = 0; k < n; ++k) {
+                const int ln = R->len[k], lo = max(acc, p), hi = min(acc + ln, e);
+                if (lo < hi) {
+                    if (lo == acc) { R->a[k] += hi - acc; R->len[k] = acc + ln - hi; }           // a prefix (or all) of the run goes
+                    else if (hi == acc + ln) R->len[k] = lo - acc;                                // a suffix goes
+                    else {                                                                         // the middle goes: the run splits
+                        for (int t = n - 1; t > k; --t) { R->len[t + 1] = R->len[t]; R->a[t + 1] = R->a[t]; R->kind[t + 1] = R->kind[t]; }
+                        R->len[k + 1] = acc + ln - hi; R->a[k + 1] = R->a[k] + (hi - acc); R->kind[k + 1] = R->kind[k];
+                        R->len[k] = lo - acc;
+                        ++n;
+                        acc += ln;
+                        ++k;                                                                       // the new right part lies behind e
+                        continue;
+                    }
+                }
+                acc += ln;
+            }
+        }
+    }
+    int f = 0;
+    for (int k = 0; k < n; ++k) { R->f[k] = f; f += R->len[k]; }
+    R->n = n;
+}
+
+// The body of an indel-masked record with two edits from the staged (SNV-masked) words and quality bytes.
+__device__ __noinline__ void emit_runs_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r, int L, bool reverse,
+                                             const uint8_t* qrec, const uint32_t* stage, const uint32_t* qstage, RunList* R, uint64_t seq16, uint64_t qual16,
+                                             int new_len, int glane) {
+    const int nqw = (L + 3) >> 2;
+    if (act && !qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
+    uint32_t part = 0;
+    if (act) {
+        for (int q = glane; q < nqw; q += kGroup) {
+            uint32_t v = qstage[q];
+            if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
+            part += __vsadu4(v, 0u);
+        }
+        if (glane == 0) {
+            build_runs(E, L, R);
+            for (int q = 0; q < E.n_del; ++q)
+                if ((int64_t)E.pos[q] + E.len[q] > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
+        }
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
+    __syncwarp();                                                         // the run list is visible to the group
+    if (!act) return;
+    // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (anonymizer_methods.py:193)
+    uint32_t mean0 = 0u, mean1 = 0u;
+    {
+        uint32_t sum = part, n = (uint32_t)L;
+        if (E.n_del >= 1) { mean0 = n ? sum / n : 0u; sum += mean0 * (uint32_t)E.len[0]; n += (uint32_t)E.len[0]; }
+        if (E.n_del >= 2) mean1 = n ? sum / n : 0u;
+    }
+    auto low_nibbles = [](int cnt) -> uint32_t { return cnt >= 8 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((8 - cnt) * 4))); };
+    auto low_bytes = [](int cnt) -> uint32_t { return cnt >= 4 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((4 - cnt) * 8))); };
+    const int n_runs = R->n;
+    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
+    for (int w = glane; w < units * 4; w += kGroup) {
+        const int j0 = w << 3;
+        uint32_t v = 0u;
+        if (j0 < new_len) {
+#pragma unroll 1
+            for (int k = 0; k < n_runs; ++k) {
+                const int f = R->f[k], lo = max(f, j0), hi = min(f + R->len[k], j0 + 8);
+                if (lo >= hi) continue;
+                const uint32_t m = low_nibbles(hi - j0) & ~low_nibbles(lo - j0);
+                const int at = R->a[k] + (j0 - f);                       // >= -7
+                uint32_t val;
+                if (R->kind[k]) val = ref_word(B.ref4, (int64_t)at);
+                else if (at < 0) val = stage[0] << ((-at) * 4);
+                else val = __funnelshift_r(stage[at >> 3], stage[(at >> 3) + 1], (uint32_t)(at & 7) * 4u);
+                v |= val & m;
+            }
+        }
+        oseq[w] = v;
+    }
+    // qualities in printed (= BAM) order; the runs index the forward-orientation array (anonymizer_methods.py:95, 187,
+    // 195: quirk Q2), so for a reverse read a run [f, f + len) is printed at [new_len - f - len, new_len - f) and its BAM
+    // bytes ascend with the printed index
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    for (int w = glane; w < units * 8; w += kGroup) {
+        const int p0 = w << 2;
+        uint32_t v = 0u;
+        if (p0 < new_len) {
+#pragma unroll 1
+            for (int k = 0; k < n_runs; ++k) {
+                const int ln = R->len[k], f = reverse ? new_len - R->f[k] - ln : R->f[k];
+                const int lo = max(f, p0), hi = min(f + ln, p0 + 4);
+                if (lo >= hi) continue;
+                const uint32_t m = low_bytes(hi - p0) & ~low_bytes(lo - p0);
+                uint32_t val;
+                const int kind = R->kind[k];
+                if (kind) val = (kind == 1 ? mean0 : mean1) * 0x01010101u;
+                else {
+                    const int at = p0 + (reverse ? L - new_len - R->a[k] + R->f[k] : R->a[k] - R->f[k]);   // BAM byte of printed byte p0 (>= -3)
+                    val = at < 0 ? qstage[0] << ((-at) * 8) : __funnelshift_r(qstage[at >> 2], qstage[(at >> 2) + 1], (uint32_t)(at & 3) * 8u);
+                }
+                v |= val & m;
+            }
+        }
+        oq[w] = v;
+    }
+}
+
 // Reads with other CIGARs, the common shapes: SNV-only (kind 2, E.ne == 0) and one germline indel (kind 3,
 // E.ne == 1), reads of at most 8 * (kGroupStage - 1) bases.  One group of 8 lanes per record; every lane of the warp
 // calls this (act = false for groups without such a record).
@@ -100,7 +231,7 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
         const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * src_unit);
         for (int w = glane; w < nw; w += kGroup) stage[w] = __ldg(rec + w) & tail_mask(L, w);
         if (glane == 0) stage[nw] = 0u;                                // the funnel shift may touch one word past the end
-        if (E.ne == 1 && qrec) {                                       // the quality record too: it is summed and shifted below
+        if (E.ne >= 1 && qrec) {                                       // the quality record too: it is summed and shifted below
             const uint32_t* qg = reinterpret_cast<const uint32_t*>(qrec);
             for (int q = glane; q < nqw; q += kGroup) qstage[q] = __ldg(qg + q);
             if (glane == 0) qstage[nqw] = 0u;
@@ -132,7 +263,7 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     __syncwarp();
     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-    const bool indel = act && E.ne == 1;
+    const bool indel = act && E.ne == 1;                              // two edits: the caller continues with emit_runs_group
     if (act && E.ne == 0) for (int w = glane; w < units * 4; w += kGroup) oseq[w] = w < nw ? stage[w] : 0u;
     // ---- one edit
     const bool is_del = E.n_del == 1;
@@ -204,6 +335,7 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
 __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
     __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
     __shared__ uint32_t qstage[kThreads / kGroup][2 * kGroupStage];      // quality bytes of the same reads (4 per word)
+    __shared__ RunList runs[kThreads / kGroup];                           // two-edit records: the runs the output is merged from
     const int tid = threadIdx.x, group = tid / kGroup, glane = tid % kGroup;
     const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
     const uint32_t groups_total = gridDim.x * (kThreads / kGroup);
@@ -286,9 +418,14 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
                 }
                 __syncwarp();                                         // every lane of the group has read the aux before it is overwritten
                 // the common shapes take the staged path; two edits or very long reads take the general one
-                const bool fast = (r_kind == 2u || (indel && Ed.ne == 1)) && ((L + 7) >> 3) <= kGroupStage - 1;
+                const bool fast = (r_kind == 2u || (indel && (Ed.ne == 1 || Ed.ne == 2))) && ((L + 7) >> 3) <= kGroupStage - 1;
                 if (__any_sync(0xffffffffu, fast))
                     emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, c0, c1, reverse, col_begin, germ, qrec, stage[group], qstage[group], seq16, qual16, new_len, glane);
+                const bool two = fast && indel && Ed.ne == 2;
+                if (__any_sync(0xffffffffu, two)) {
+                    __syncwarp();                                     // staged words are SNV-masked
+                    emit_runs_group(B, O.totals, O, two, Ed, r, L, reverse, qrec, stage[group], qstage[group], &runs[group], seq16, qual16, new_len, glane);
+                }
                 if (r_kind == 2u && !fast) {
                     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
                     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);

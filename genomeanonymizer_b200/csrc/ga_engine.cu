@@ -130,6 +130,10 @@ __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* ti
 
 // ------------------------------------------------------------------ engine
 
+// the two instantiations of the one-warp resolve kernel (ga_resolve_kernel.cuh)
+static const auto kResolveLean = ga::resolve_warp_kernel<ga::kReadsL, ga::kModL, ga::kObsL, ga::kEntL, ga::kLeanWarps, 11, false>;
+static const auto kResolveMid = ga::resolve_warp_kernel<ga::kReadsL, ga::kModM, ga::kObsM, ga::kEntM, ga::kMidWarps, 6, true>;
+
 int ga_fail(ga_engine* e, int code, const char* what, cudaError_t ce) {
     if (e) {
         e->err = what;
@@ -184,11 +188,15 @@ int ga_engine_create(int device, ga_engine** out) {
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemR));
     cudaFuncSetAttribute(ga::resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(ga::session_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemLayout));
-    cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemL) * ga::kLeanWarps));
-    cudaFuncSetAttribute(ga::resolve_lean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kResolveLean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemL) * ga::kLeanWarps));
+    cudaFuncSetAttribute(kResolveLean, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kResolveMid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemM) * ga::kMidWarps));
+    cudaFuncSetAttribute(kResolveMid, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // persistent kernels: exactly one wave of resident CTAs (a partial second wave would wait for the first to drain)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_scan, ga::scan_kernel, ga::kScanThreads, sizeof(ga::WarpSmem) * (ga::kScanThreads / 32));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_lean, ga::resolve_lean_kernel, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_lean, kResolveLean, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_mid, kResolveMid, 32 * ga::kMidWarps, sizeof(ga::SmemM) * ga::kMidWarps);
+    if (e->occ_mid < 1) e->occ_mid = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_res, ga::resolve_kernel, ga::kResThreads, sizeof(ga::SmemR));
     if (const char* v = getenv("GA_OCC_SCAN")) e->occ_scan = std::min(e->occ_scan, std::max(1, atoi(v)));   // tuning knob: CTAs per SM of the scan kernel
     if (e->occ_scan < 1) e->occ_scan = 1;
@@ -207,7 +215,7 @@ void ga_engine_destroy(ga_engine* e) {
     cudaFree(e->d_fastq_sums);
     for (int l = 0; l < kLanes; ++l) {
         Lane& L = e->lanes[l];
-        cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
+        cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list); cudaFree(L.d_large2_list); cudaFree(L.d_small); cudaFree(L.d_big_scratch);
         if (L.side) cudaStreamDestroy(L.side);
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_join) cudaEventDestroy(L.ev_join);
@@ -259,12 +267,13 @@ int ga_upload_reference(ga_engine* e, int contig_id, const uint8_t* bases, int64
 
 static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
     if (n_sessions <= L.cap_sessions) return GA_OK;
-    cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list);
-    L.d_descs = nullptr; L.d_big_list = nullptr; L.d_large_list = nullptr; L.cap_sessions = 0;
+    cudaFree(L.d_descs); cudaFree(L.d_big_list); cudaFree(L.d_large_list); cudaFree(L.d_large2_list);
+    L.d_descs = nullptr; L.d_big_list = nullptr; L.d_large_list = nullptr; L.d_large2_list = nullptr; L.cap_sessions = 0;
     const int64_t cap = n_sessions + n_sessions / 4 + 1024;
     GA_CUDA(cudaMalloc(&L.d_descs, (size_t)cap * sizeof(ga::SessionDesc)));
     GA_CUDA(cudaMalloc(&L.d_big_list, (size_t)cap * sizeof(int32_t)));
     GA_CUDA(cudaMalloc(&L.d_large_list, (size_t)cap * sizeof(int32_t)));
+    GA_CUDA(cudaMalloc(&L.d_large2_list, (size_t)cap * sizeof(int32_t)));
     L.cap_sessions = cap;
     return GA_OK;
 }
@@ -347,10 +356,12 @@ int ga_stage_ms_history(ga_engine* e, int stage, float* out, int n) {
 
 int ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons) {
     if (!e) return -1;
-    int32_t h[16] = {0};
+    int32_t h[24] = {0};
     if (cudaSetDevice(e->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
         cudaMemcpy(h, e->lanes[e->last_lane].d_small, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    for (int k = 0; reasons && k < n_reasons && k < 9; ++k) reasons[k] = h[4 + k];
+    for (int k = 0; reasons && k < n_reasons && k < 8; ++k) reasons[k] = h[4 + k];
+    if (reasons && n_reasons > 8) reasons[8] = h[20];      // mid one-warp kernel -> one-CTA kernel
+    if (reasons && n_reasons > 9) reasons[9] = h[12];      // lean one-warp kernel -> mid one-warp kernel
     return h[0];
 }
 
@@ -432,9 +443,15 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     // session for those whose tables did not fit the lean capacities
     int32_t* d_nlarge = L.d_small + 12;
     const int lean_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_lean, (S->n_sessions + ga::kLeanWarps - 1) / ga::kLeanWarps);
-    ga::resolve_lean_kernel<<<lean_ctas, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
+    int32_t* d_nlarge2 = L.d_small + 20;
+    kResolveLean<<<lean_ctas, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, nullptr, nullptr, E.ticket_lean,
+                                                                                           L.d_large_list, d_nlarge, O, X, E);
+    // sessions beyond the lean capacities (indel-dense ones): the same kernel with larger tables, then the one-CTA kernel
+    const int mid_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_mid, (S->n_sessions + ga::kMidWarps - 1) / ga::kMidWarps);
+    kResolveMid<<<mid_ctas, 32 * ga::kMidWarps, sizeof(ga::SmemM) * ga::kMidWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge,
+                                                                                        reinterpret_cast<unsigned int*>(L.d_small + 21), L.d_large2_list, d_nlarge2, O, X, E);
     const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_res, S->n_sessions);
-    ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge, O, X, E);
+    ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large2_list, d_nlarge2, O, X, E);
     GA_CUDA(cudaEventRecord(L.ev[2][tslot], st));
     // oversize sessions and whatever the tables of stages 1-2 could not hold: global-scratch kernel, complete records;
     // it runs on a side stream beside stage 3 (it only appends records, which the emission kernel skips), behind the
@@ -452,7 +469,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
     GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
-    e->launches += 8;
+    e->launches += 9;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

@@ -10,8 +10,8 @@ struct RefEntry { uint32_t* d_ref4 = nullptr; int64_t n = 0; int64_t cap_words =
 
 // Scratch of one in-flight ga_run: three lanes let the host pipeline overlap consecutive chunks.
 struct Lane {
-    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int32_t* d_large_list = nullptr; int64_t cap_sessions = 0;
-    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special, [14] second fallback ticket, [15] n_many, [16] n_many_recs, [17] n_kind1, [18] / [19] tickets of the one-CTA / one-warp resolve kernels
+    ga::SessionDesc* d_descs = nullptr; int32_t* d_big_list = nullptr; int32_t* d_large_list = nullptr; int32_t* d_large2_list = nullptr; int64_t cap_sessions = 0;
+    int32_t* d_small = nullptr;          // [0] n_big, [1] maxspan, [2..3] tickets, [4..11] fallback reasons, [12] n_large, [13] n_special, [14] second fallback ticket, [15] n_many, [16] n_many_recs, [17] n_kind1, [18] / [19] tickets of the one-CTA / one-warp resolve kernels, [20] sessions the mid one-warp kernel handed to the one-CTA kernel, [21] its ticket
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the fallback kernel runs beside the emission kernel
     uint8_t* d_big_scratch = nullptr;
     // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)
@@ -42,7 +42,7 @@ struct ga_engine {
     int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
     int64_t launches = 0;
     int last_lane = 0, next_lane = 0;        // ga_run: lane of the most recent run; round-robin cursor when every lane is taken
-    int occ_scan = 4, occ_lean = 9, occ_res = 6;   // resident CTAs per SM of the persistent kernels
+    int occ_scan = 4, occ_lean = 9, occ_mid = 6, occ_res = 6;   // resident CTAs per SM of the persistent kernels
     HostSlot* slots = nullptr;           // lazily created by ga_run_host
     int64_t last_h2d = 0, last_d2h = 0;
     int64_t* d_fastq_sums = nullptr; int64_t cap_fastq_blocks = 0;   // ga_fastq_layout scratch

@@ -504,14 +504,23 @@ constexpr int kReadsL = 1536;            // candidate reads per session
 constexpr int kModL = 256;               // modified reads per session
 constexpr int kObsL = 64;                // indel observations per session
 constexpr int kEntL = 512;               // candidate entries per session
+// "Mid" instantiation of the same kernel: the sessions of an indel-dense workload (hundreds of indel observations and
+// modified reads per session) stay with the one-warp formulation instead of the barrier-bound one-CTA kernel; it walks
+// the list the lean instantiation handed over and lists what it cannot hold for the one-CTA kernel.
+constexpr int kMidWarps = 1;
+constexpr int kModM = 512;
+constexpr int kObsM = 512;
+constexpr int kEntM = 768;
 
-struct SmemL {
+template <int kReadsL, int kModL, int kObsL, int kEntL>
+struct SmemLT {
     uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
     uint32_t modbits[kReadsL / 32], indelbits[kReadsL / 32], genbits[kReadsL / 32], woff[kReadsL / 32];
     uint32_t mpatch[kModL];              // two germline hits of a clean read: (column << 4) | reference code, 16 bits each
     int32_t mhead[kModL];                // per modified read: chain of its germline indel observations
     uint8_t mpc[kModL];                  // germline SNV hits per modified read
     uint32_t o_meta[kObsL], o_ra[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
+    uint32_t o_key[kObsL];               // hash of (column, type, length, allele): one compare rejects almost every pair
     union {                              // the allele signatures are dead once the observations are compared,
         struct { uint32_t o_s0[kObsL], o_s1[kObsL]; };
         uint16_t clist[kModL];           // ... which is before the list of modified reads is built
@@ -521,12 +530,24 @@ struct SmemL {
         uint32_t rnew[kModL];            // ... which is before the new lengths are known: new length | kind << 24
     };
     uint32_t ngerm, pad[3];
+    static_assert(sizeof(uint16_t) * kModL <= 2 * sizeof(uint32_t) * kObsL && kModL <= kEntL, "aliases fit");
 };
-static_assert(sizeof(uint16_t) * kModL <= 2 * sizeof(uint32_t) * kObsL && kModL <= kEntL, "aliases fit");
-static_assert(sizeof(SmemL) % 16 == 0, "per-warp slices stay 16-byte aligned");
+using SmemL = SmemLT<kReadsL, kModL, kObsL, kEntL>;
+using SmemM = SmemLT<kReadsL, kModM, kObsM, kEntM>;
+static_assert(sizeof(SmemL) % 16 == 0 && sizeof(SmemM) % 16 == 0, "per-warp slices stay 16-byte aligned");
+
+// Alleles longer than the 16-base signature (rare): the bases behind it are compared from the records.
+__device__ __noinline__ bool long_allele_tail_equal(const SessCtx& c, uint32_t ra_a, int irp_a, uint32_t ra_b, int irp_b) {
+    const uint32_t* pa = rec_of(c, read_of(c, (int)(ra_a & 0xffffu)));
+    const uint32_t* pb = rec_of(c, read_of(c, (int)(ra_b & 0xffffu)));
+    const int na = (int)(ra_a >> 16);
+    for (int j = 16; j < na; ++j)
+        if (read_code(pa, irp_a + j) != read_code(pb, irp_b + j)) return false;
+    return true;
+}
 
 // collect2 behind a call: the lean kernel needs it twice and must stay small enough for the instruction cache
-__device__ __noinline__ bool lean_collect(const SessCtx& c, const SmemL* sm, int k, int L, Ed2& E, int* new_len) { return collect2(c, sm, k, L, E, new_len); }
+template <class SM> __device__ __noinline__ bool lean_collect(const SessCtx& c, const SM* sm, int k, int L, Ed2& E, int* new_len) { return collect2(c, sm, k, L, E, new_len); }
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
     uint32_t inc = v;
@@ -536,10 +557,14 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return inc - v;
 }
 
-__global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
+// kFromList: the sessions are the entries of in_list (what the lean instantiation handed over) instead of 0 .. n_sessions - 1.
+template <int kReadsL, int kModL, int kObsL, int kEntL, int kWarps, int kMinBlocks, bool kFromList>
+__global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                             int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
+                                                                            const int32_t* __restrict__ in_list, const int32_t* __restrict__ n_in, unsigned int* __restrict__ ticket_p,
                                                                             int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
                                                                             ResultView O, ScanScratch X, EmitScratch2 E) {
+    using SmemL = SmemLT<kReadsL, kModL, kObsL, kEntL>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SmemL* sm = reinterpret_cast<SmemL*>(smem_raw) + warp;
@@ -547,7 +572,6 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
     c.B = B;
     c.totals = O.totals;
     memset(&c.T, 0, sizeof c.T);
-    const int n_warps = gridDim.x * kLeanWarps;
     // statistics counters are summed per warp and added to ga_totals once, at the end: every session already sends
     // three atomics to that one cache line for its output slots, and same-address atomics serialise in L2
     unsigned long long acc_reads = 0ull, acc_bases = 0ull;
@@ -556,11 +580,12 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
 #pragma unroll 1
     // sessions differ in cost: a warp takes the next one from a ticket counter (the ticket after that travels while the
     // session is processed), so that no warp is left with a long tail of expensive sessions
-    uint32_t ticket = lane == 0 ? atomicAdd(E.ticket_lean, 1u) : 0u, next_ticket = 0u;
+    const uint32_t n_work = kFromList ? (uint32_t)*n_in : (uint32_t)S.n_sessions;
+    uint32_t ticket = lane == 0 ? atomicAdd(ticket_p, 1u) : 0u, next_ticket = 0u;
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    for (; ticket < (uint32_t)S.n_sessions; ticket = __shfl_sync(0xffffffffu, next_ticket, 0)) {
-        const int s = (int)ticket;
-        next_ticket = lane == 0 ? atomicAdd(E.ticket_lean, 1u) : 0u;
+    for (; ticket < n_work; ticket = __shfl_sync(0xffffffffu, next_ticket, 0)) {
+        const int s = kFromList ? in_list[ticket] : (int)ticket;
+        next_ticket = lane == 0 ? atomicAdd(ticket_p, 1u) : 0u;
         // ---- round trip 1: descriptor, scan counts, variant_to_keep
         uint32_t w1 = 0u, w2 = 0u;
         if (lane < 20) w1 = __ldg(reinterpret_cast<const uint32_t*>(descs + s) + lane);
@@ -611,6 +636,8 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
             const uint4* src = reinterpret_cast<const uint4*>(o < (int)n_obs0 ? op + o : op + kObsHalf + (o - (int)n_obs0));
             const uint4 a = __ldg(src), b = __ldg(src + 1);
             sm->o_col[o] = (int)a.x; sm->o_meta[o] = a.y; sm->o_ra[o] = a.z; sm->o_irp[o] = (int)a.w; sm->o_s0[o] = b.x; sm->o_s1[o] = b.y;
+            uint32_t kh = a.x * 0x9E3779B1u ^ ((a.y & (kMetaIns | kMetaLenMask)) * 0x85EBCA77u) ^ ((a.z >> 16) * 0xC2B2AE3Du) ^ (b.x * 0x27D4EB2Fu) ^ (b.y * 0x165667B1u);
+            sm->o_key[o] = kh ^ (kh >> 15);
         }
         {
             uint4* t4 = reinterpret_cast<uint4*>(sm->tab);
@@ -641,13 +668,6 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
         }
         if (__any_sync(0xffffffffu, bad)) {
             if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 2, 1); }
-            continue;
-        }
-        bool long_allele = false;
-#pragma unroll 1
-        for (int o = lane; o < n_obs; o += 32) long_allele |= (sm->o_ra[o] >> 16) > 16u;
-        if (__any_sync(0xffffffffu, long_allele)) {                  // allele longer than the signature: compared by the large variant
-            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
         __syncwarp();
@@ -688,13 +708,15 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
 #pragma unroll 1
         for (int o = lane; o < n_obs; o += 32) {
             const int o_col = sm->o_col[o];
-            const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o];
+            const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o], o_key = sm->o_key[o];
             bool germ = false, rep = true;
-#pragma unroll 1
+#pragma unroll 4
             for (int j = 0; j < n_obs; ++j) {
+                if (sm->o_key[j] != o_key) continue;                   // one broadcast load and a compare for almost every pair
                 if (j == o || sm->o_col[j] != o_col) continue;
                 const uint32_t j_meta = sm->o_meta[j];
                 if (((j_meta ^ o_meta) & (kMetaIns | kMetaLenMask)) != 0u || (sm->o_ra[j] >> 16) != (o_ra >> 16) || sm->o_s0[j] != o_s0 || sm->o_s1[j] != o_s1) continue;
+                if ((o_ra >> 16) > 16u && !long_allele_tail_equal(c, o_ra, sm->o_irp[o], sm->o_ra[j], sm->o_irp[j])) continue;   // bases behind the 16-base signature
                 if ((j_meta ^ o_meta) & kMetaDs) germ = true;
                 if (j < o) rep = false;
             }
@@ -708,7 +730,8 @@ __global__ void __launch_bounds__(32 * kLeanWarps, 11) resolve_lean_kernel(Batch
                     bool same = true;
 #pragma unroll 1
                     for (int j = 0; j < na; ++j) {
-                        const uint32_t code = ((j < 8 ? o_s0 : o_s1) >> (4 * (j & 7))) & 15u;
+                        const uint32_t code = j < 16 ? (((j < 8 ? o_s0 : o_s1) >> (4 * (j & 7))) & 15u)
+                                                     : read_code(rec_of(c, read_of(c, (int)(o_ra & 0xffffu))), sm->o_irp[o] + j);
                         if (c.keep_allele[j] != (uint8_t)code2asc[code]) same = false;
                     }
                     if (same) germ = false;

@@ -126,27 +126,12 @@ __device__ __forceinline__ void flush_entries(ItemCtx& c, int lane) {
     __syncwarp();
 }
 
-// One read with any CIGAR, walked by the whole warp (all arguments warp-uniform).  Lane w owns query words
-// w, w+32, ...: it compares the part of every aligned segment that overlaps its 8 bases with the reference;
-// lane 0 records the I/D observations (variation_classifier.py:52-107: pos, in_read_pos with the H/N quirk,
-// Python-slice clamped allele).
-__device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, int pos, int L, uint32_t c0, uint32_t c1, const uint32_t* rec, int lane) {
+// One read with a CIGAR of more than eight ops, walked by the whole warp (all arguments warp-uniform; rare).  Lane w
+// owns query words w, w+32, ...: it compares the part of every aligned segment that overlaps its 8 bases with the
+// reference; lane 0 records the I/D observations (variation_classifier.py:52-107: pos, in_read_pos with the H/N quirk,
+// Python-slice clamped allele).  The caller has counted the read, checked its span and knows its quality ordinal.
+__device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, int pos, int L, uint32_t c0, uint32_t c1, const uint32_t* rec, uint32_t qord, int lane) {
     const BatchView& B = c.B;
-    int span = 0;
-    bool has_id = false;
-    for (uint32_t ci = c0; ci < c1; ++ci) {
-        const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
-        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
-        has_id |= (op == 1u || op == 2u);
-    }
-    uint32_t qord = 0u;                                                  // counted before any early exit: the quality index lists every such read
-    if (lane == 0) { qord = c.ws->n_qord; if (has_id) c.ws->n_qord = qord + 1u; }
-    if (pos + span <= c.ws->first) return;                                   // fetched by range, does not reach the region
-    if (lane == 0) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
-    if ((int64_t)pos + span > B.ref_len || pos < 0 || pos < c.col_begin || pos + span - c.col_begin >= c.n_cols) {
-        if (lane == 0) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)r);
-        return;
-    }
     // ---- SNV candidates, one 8-base word per lane
     for (int w = lane; w < ((L + 7) >> 3); w += 32) {
         const int qb = w << 3;
@@ -210,6 +195,107 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
             else if (op == 5u) { rcb += ln; }
         }
         c.ws->n_obs = n_obs;
+    }
+}
+
+// Reads with a CIGAR of at most eight ops, FOUR AT A TIME: a group of 8 lanes per read (north_star job (2)).
+//   * one lane per op: the reference- and query-consumed lengths and the in_read_pos terms are turned into each op's
+//     start offsets by a warp-shuffle inclusive scan over the 8 lanes of the group (variation_classifier.py:69-82 sums
+//     them op by op; htslib's query_position is the same sum);
+//   * every I / D lane writes its observation in parallel (slots ascend in CIGAR order, reads in tile order);
+//   * lane k of the group then owns 8-base words k, k+8, ...: each aligned segment (broadcast from its op lane by
+//     shuffle) is compared against the session's staged reference window where it overlaps the word.
+// sel: the four source lanes (one byte each, 0xff = none).  Per-lane inputs describe the read the LANE holds.
+__device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int i_lane, int pos, int L, uint32_t c0, uint32_t n_ops, uint32_t so, uint32_t qord,
+                                                  bool staged, int b, uint32_t sof, int lane) {
+    const BatchView& B = c.B;
+    const int gl = lane & 7, gbase = lane & ~7;
+    const uint32_t src = (sel >> (8 * (lane >> 3))) & 0xffu;
+    const bool act = src != 0xffu;
+    const int sl = act ? (int)src : 0;
+    const int g_pos = __shfl_sync(0xffffffffu, pos, sl), g_L = __shfl_sync(0xffffffffu, L, sl), g_i = __shfl_sync(0xffffffffu, i_lane, sl);
+    const uint32_t g_c0 = __shfl_sync(0xffffffffu, c0, sl), g_nops = __shfl_sync(0xffffffffu, n_ops, sl);
+    const uint32_t g_so = __shfl_sync(0xffffffffu, so, sl), g_qord = __shfl_sync(0xffffffffu, qord, sl);
+    const uint32_t* rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - sof))
+                                 : reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * g_so);
+    // ---- K2: one lane per op, inclusive scans over the group
+    const bool has_op = act && (uint32_t)gl < g_nops;
+    const uint32_t cw = has_op ? __ldg(B.cigar + g_c0 + gl) : 0u;
+    const uint32_t op = has_op ? (cw & 15u) : 15u;
+    const int ln = has_op ? (int)(cw >> 4) : 0;
+    const bool aligned = op == 0u || op == 7u || op == 8u;
+    int sq = (aligned || op == 1u || op == 4u) ? ln : 0;                   // query consumed: M = X I S
+    int sr = (aligned || op == 2u || op == 3u) ? ln : 0;                   // reference consumed: M = X D N (= the reference's cigar-consumed length)
+    int sb = (op == 1u || op == 4u || op == 5u) ? ln : (op == 2u ? -ln : 0);   // read-consuming bases: +I +S +H -D (quirk Q7)
+    const int q_own = sq, r_own = sr, b_own = sb;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const int tq = __shfl_up_sync(0xffffffffu, sq, d, 8), tr = __shfl_up_sync(0xffffffffu, sr, d, 8), tb = __shfl_up_sync(0xffffffffu, sb, d, 8);
+        if (gl >= d) { sq += tq; sr += tr; sb += tb; }
+    }
+    const int q0 = sq - q_own, r0 = sr - r_own, b0 = sb - b_own;          // offsets at which this op starts
+    if (aligned && q0 + ln > g_L) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + (g_i - c.ws->i_base)));   // IndexError in variation_classifier.py:148
+    // ---- indel observations
+    const bool is_id = op == 1u || op == 2u;
+    const uint32_t idm = __ballot_sync(0xffffffffu, is_id);
+    if (idm) {
+        const uint32_t n_obs0 = c.ws->n_obs;
+        const uint32_t slot = n_obs0 + __popc(idm & ((1u << lane) - 1u));
+        if (is_id) {
+            if (slot >= (uint32_t)kObsHalf) c.ws->ovf = 1u;
+            else {
+                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+                const int irp = r0 + b0;                                  // variation_classifier.py:82
+                const int alen = allele_len(meta, irp, g_L);              // Python-slice clamped (variation_classifier.py:87-88)
+                uint32_t s0 = 0u, s1 = 0u;                                 // signature: the first 16 allele bases
+                if (alen > 0) {
+                    const int w0 = irp >> 3;
+                    const uint32_t sh = (uint32_t)(irp & 7) * 4u;
+                    const uint32_t a0 = rec[w0], a1 = 8 * (w0 + 1) < g_L ? rec[w0 + 1] : 0u, a2 = 8 * (w0 + 2) < g_L ? rec[w0 + 2] : 0u;
+                    s0 = __funnelshift_r(a0, a1, sh) & tail_mask(alen, 0);
+                    s1 = __funnelshift_r(a1, a2, sh) & tail_mask(alen, 1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.ws->item * kObsHalf + slot);
+                dst[0] = make_uint4((uint32_t)(g_pos + r0 - c.col_begin), meta, (uint32_t)g_i | ((uint32_t)alen << 16), (uint32_t)irp);
+                dst[1] = make_uint4(s0, s1, g_qord, 0u);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) c.ws->n_obs = min(n_obs0 + (uint32_t)__popc(idm), (uint32_t)kObsHalf);
+        __syncwarp();
+    }
+    // ---- SNV candidates (variation_classifier.py:147-150)
+    const int nw = act ? (g_L + 7) >> 3 : 0;
+    const int nw_max = __reduce_max_sync(0xffffffffu, nw);
+    const int ops_max = (int)__reduce_max_sync(0xffffffffu, act ? g_nops : 0u);
+    const int relbase = c.ws->relbase;
+    for (int wb = 0; wb < nw_max; wb += 8) {
+        const int w = wb + gl;
+        const bool mine = w < nw;
+        const int qb = w << 3;
+        const uint32_t v = mine ? rec[w] : 0u;
+#pragma unroll 1
+        for (int j = 0; j < ops_max; ++j) {
+            const uint32_t o_op = __shfl_sync(0xffffffffu, op, gbase + j);
+            const int o_q0 = __shfl_sync(0xffffffffu, q0, gbase + j), o_r0 = __shfl_sync(0xffffffffu, r0, gbase + j), o_ln = __shfl_sync(0xffffffffu, ln, gbase + j);
+            if (!mine || !(o_op == 0u || o_op == 7u || o_op == 8u)) continue;
+            const int lo = max(o_q0, qb), hi = min(min(o_q0 + o_ln, qb + 8), g_L);
+            if (lo >= hi) continue;
+            const int p0 = g_pos + o_r0 - o_q0 + qb;                      // reference position of query base qb under this segment (>= pos - 7)
+            const int nib = p0 + 8 - relbase;                             // nibble offset in the staged window (>= -7)
+            const uint32_t fw = nib >= 0 ? __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u)
+                                         : (c.ws->sref[0] << ((uint32_t)(-nib) * 4u));
+            uint32_t mask = 0xffffffffu;
+            if (lo > qb) mask &= 0xffffffffu << ((lo - qb) * 4);
+            if (hi < qb + 8) mask &= 0xffffffffu >> ((qb + 8 - hi) * 4);
+            uint32_t x = (v ^ fw) & mask;
+            while (x) {
+                const int n = (__ffs(x) - 1) >> 2;
+                x &= ~(0xfu << (n * 4));
+                const uint32_t bb = (v >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+                if (bb != 15u && is_acgt(rf)) push_entry_w(c, g_i, p0 + n - c.col_begin, bb, rf, kEntGen);
+            }
+        }
     }
 }
 
@@ -317,16 +403,51 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
             if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, rf, 0u);
         }
     }
-    // ---- reads with any other CIGAR (or an error case): the whole warp walks them one by one
-    uint32_t gm = __ballot_sync(0xffffffffu, valid && !clean);
-    while (gm) {
-        const int src = __ffs(gm) - 1; gm &= gm - 1;
-        const int g_pos = __shfl_sync(0xffffffffu, pos, src), g_L = __shfl_sync(0xffffffffu, L, src);
-        const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = g_c0 + __shfl_sync(0xffffffffu, n_ops, src);
-        const uint32_t g_so = __shfl_sync(0xffffffffu, m.so, src);
-        const uint32_t* g_rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - sof))
-                                          : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * g_so);
-        scan_generic_read(c, c.ws->i_base + t * TR + src, (int64_t)c.ws->begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, lane);
+    // ---- reads with any other CIGAR (and every read of a tile that could not be staged)
+    const bool gen = valid && !clean;
+    if (__any_sync(0xffffffffu, gen)) {
+        // lane = read: reference span and I/D presence of its ops, then the checks the reference's walk implies
+        int span = 0;
+        bool has_id = false;
+        if (gen) {
+            for (uint32_t ci = 0; ci < n_ops; ++ci) {
+                const uint32_t w = ci ? __ldg(c.B.cigar + m.c0 + ci) : cw0, op = w & 15u;
+                if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
+                has_id |= (op == 1u || op == 2u);
+            }
+        }
+        // the read's ordinal among the item's reads with an I/D op = its slot in the sparse quality index; counted
+        // before any exit: the index lists every such read
+        const uint32_t idm = __ballot_sync(0xffffffffu, gen && has_id);
+        const uint32_t qord = c.ws->n_qord + __popc(idm & ((1u << lane) - 1u));
+        __syncwarp();
+        if (lane == 0 && idm) c.ws->n_qord += __popc(idm);
+        bool work = gen && pos + span > c.ws->first;                     // fetched by range but not reaching the region: skipped
+        if (work) { c.n_reads += 1u; c.n_bases += (uint32_t)L; }
+        if (work && ((int64_t)pos + span > c.B.ref_len || pos < 0 || pos < c.col_begin || pos + span - c.col_begin >= c.n_cols)) {
+            raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + idx));
+            work = false;
+        }
+        uint32_t m_short = __ballot_sync(0xffffffffu, work && n_ops <= 8u), m_long = __ballot_sync(0xffffffffu, work && n_ops > 8u);
+        while (m_short) {                                                // four reads per step, 8 lanes each
+            uint32_t sel = 0u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t s1 = m_short ? (uint32_t)(__ffs(m_short) - 1) : 0xffu;
+                m_short &= m_short - 1u;
+                sel |= s1 << (8 * g);
+            }
+            scan_generic_quad(c, sel, i, pos, L, m.c0, n_ops, m.so, qord, staged, b, sof, lane);
+        }
+        while (m_long) {
+            const int src = __ffs(m_long) - 1; m_long &= m_long - 1;
+            const int g_pos = __shfl_sync(0xffffffffu, pos, src), g_L = __shfl_sync(0xffffffffu, L, src);
+            const uint32_t g_c0 = __shfl_sync(0xffffffffu, m.c0, src), g_c1 = g_c0 + __shfl_sync(0xffffffffu, n_ops, src);
+            const uint32_t g_so = __shfl_sync(0xffffffffu, m.so, src), g_qord = __shfl_sync(0xffffffffu, qord, src);
+            const uint32_t* g_rec = staged ? reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (g_so - sof))
+                                              : reinterpret_cast<const uint32_t*>(c.B.seq4 + 16ull * g_so);
+            scan_generic_read(c, c.ws->i_base + t * TR + src, (int64_t)c.ws->begin + t * TR + src, g_pos, g_L, g_c0, g_c1, g_rec, g_qord, lane);
+        }
     }
 }
 

@@ -160,8 +160,8 @@ class Engine:
 
     def fallback_sessions(self):
         """(sessions of the last run that took the fallback kernel, per-reason counts) - see ga_last_fallback_sessions."""
-        buf = (C.c_int32 * 9)()
-        n = int(self._L.ga_last_fallback_sessions(self._h, buf, 9))
+        buf = (C.c_int32 * 10)()
+        n = int(self._L.ga_last_fallback_sessions(self._h, buf, 10))
         return n, [int(x) for x in buf]
 
     def stage_ms_history(self, stage: int, n: int = 32):

@@ -196,7 +196,8 @@ int   ga_stage_ms_history(ga_engine* e, int stage, float* out, int n);
 /* Sessions of the most recent ga_run() that took the global-scratch fallback kernel (-1 on error), and why:
  * reasons[0] oversize session, [1] scan-kernel table overflow, [2] IUPAC read base, [3] more modified reads or
  * germline alleles than the shared-memory tables hold, [4] a read with more than two germline indels;
- * reasons[8] = sessions the one-warp resolve kernel handed to the one-CTA resolve kernel (not a fallback).
+ * reasons[8] = sessions resolved by the one-CTA resolve kernel, reasons[9] = sessions the lean one-warp resolve kernel
+ * handed to its larger instantiation (neither is a fallback).
  * Synchronises the device. */
 int   ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons);
 
