@@ -160,10 +160,12 @@ class B200GermlineAnonymizer:
     """`CompleteGermlineAnonymizer` on the B200 engine.  Picklable (the engine handle is created lazily per
     process, as the reference pickles its anonymizer into pool workers, SR.py:953-959)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, engine=None):
+        """engine: an engine.Engine that already exists (e.g. one shared by several samples of a process); by default
+        the engine is created on first use, on CUDA device `device`."""
         self.device = device
         self.anonymized_reads: Dict[str, list] = dict()
-        self._engine = None
+        self._engine = engine
 
     def __getstate__(self):
         return {"device": self.device}

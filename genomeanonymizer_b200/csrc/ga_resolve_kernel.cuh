@@ -521,6 +521,7 @@ struct SmemLT {
     uint8_t mpc[kModL];                  // germline SNV hits per modified read
     uint32_t o_meta[kObsL], o_ra[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
     uint32_t o_key[kObsL];               // hash of (column, type, length, allele): one compare rejects almost every pair
+    uint32_t o_cls[kObsL];               // low 16 bits: the first observation with the same key; bits 16 / 17 (on that one): tumor / normal saw the key
     union {                              // the allele signatures are dead once the observations are compared,
         struct { uint32_t o_s0[kObsL], o_s1[kObsL]; };
         uint16_t clist[kModL];           // ... which is before the list of modified reads is built
@@ -638,6 +639,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             sm->o_col[o] = (int)a.x; sm->o_meta[o] = a.y; sm->o_ra[o] = a.z; sm->o_irp[o] = (int)a.w; sm->o_s0[o] = b.x; sm->o_s1[o] = b.y;
             uint32_t kh = a.x * 0x9E3779B1u ^ ((a.y & (kMetaIns | kMetaLenMask)) * 0x85EBCA77u) ^ ((a.z >> 16) * 0xC2B2AE3Du) ^ (b.x * 0x27D4EB2Fu) ^ (b.y * 0x165667B1u);
             sm->o_key[o] = kh ^ (kh >> 15);
+            sm->o_cls[o] = 0u;
         }
         {
             uint4* t4 = reinterpret_cast<uint4*>(sm->tab);
@@ -703,30 +705,45 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             }
             cnt_snv = warp_sum(cnt_snv);
         }
-        // indels: exact key equality (variants.py:83-96), every observation against all the others
+        // indels: exact key equality (variants.py:83-96).  Every observation looks for the FIRST observation equal to it
+        // (the representative of its key: equality is an equivalence, so that is the smallest member of the class) - one
+        // hashed compare per candidate, a full compare only where the hash agrees - and tells the representative which
+        // dataset saw the key; an observation is germline when its representative was told by both.
         uint32_t cnt_del = 0, cnt_ins = 0;
 #pragma unroll 1
         for (int o = lane; o < n_obs; o += 32) {
             const int o_col = sm->o_col[o];
             const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o], o_key = sm->o_key[o];
-            bool germ = false, rep = true;
-#pragma unroll 4
-            for (int j = 0; j < n_obs; ++j) {
-                if (sm->o_key[j] != o_key) continue;                   // one broadcast load and a compare for almost every pair
-                if (j == o || sm->o_col[j] != o_col) continue;
+            int rep = o;
+#pragma unroll 1
+            for (int j = 0; j < o; ++j) {
+                if (sm->o_key[j] != o_key) continue;
+                if (sm->o_col[j] != o_col) continue;
                 const uint32_t j_meta = sm->o_meta[j];
                 if (((j_meta ^ o_meta) & (kMetaIns | kMetaLenMask)) != 0u || (sm->o_ra[j] >> 16) != (o_ra >> 16) || sm->o_s0[j] != o_s0 || sm->o_s1[j] != o_s1) continue;
                 if ((o_ra >> 16) > 16u && !long_allele_tail_equal(c, o_ra, sm->o_irp[o], sm->o_ra[j], sm->o_irp[j])) continue;   // bases behind the 16-base signature
-                if ((j_meta ^ o_meta) & kMetaDs) germ = true;
-                if (j < o) rep = false;
+                rep = j;
+                break;
             }
+            atomicOr(&sm->o_cls[o], (uint32_t)rep);                   // the entry was zeroed; others may be adding their dataset bits to it
+            atomicOr(&sm->o_cls[rep], (o_meta & kMetaDs) ? 0x20000u : 0x10000u);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int o = lane; o < n_obs; o += 32) {
+            const uint32_t cls = sm->o_cls[o];
+            const int rep = (int)(cls & 0xffffu);
+            bool germ = (sm->o_cls[rep] >> 16) == 3u;
+            const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o];
             if (germ) {                                               // variant_to_keep may be this indel
+                const int o_col = sm->o_col[o];
                 const int type = (o_meta & kMetaIns) ? GA_VT_INS : GA_VT_DEL;
                 const int len = (int)(o_meta & kMetaLenMask), pos = o_col + c.d.col_begin;
                 const int end = (type == GA_VT_INS) ? pos + 1 : pos + len - 1;       // variation_classifier.py:86
                 const int na = (int)(o_ra >> 16);
                 if (c.keep_type == type && c.keep_pos == pos && c.keep_len == len && c.keep_end == end && c.keep_alen == na) {
                     const char* code2asc = "=ACMGRSVTWYHKDBN";
+                    const uint32_t o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o];
                     bool same = true;
 #pragma unroll 1
                     for (int j = 0; j < na; ++j) {
@@ -741,8 +758,8 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 const uint32_t i = o_ra & 0xffffu;
                 atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
                 atomicOr(&sm->indelbits[i >> 5], 1u << (i & 31));
-                sm->o_meta[o] = o_meta | kMetaGerm;                  // own slot; the other lanes only compare the type / length / dataset bits
-                if (rep) { if (o_meta & kMetaIns) ++cnt_ins; else ++cnt_del; }
+                sm->o_meta[o] = o_meta | kMetaGerm;
+                if (rep == o) { if (o_meta & kMetaIns) ++cnt_ins; else ++cnt_del; }
             }
         }
         if (n_obs > 0) { cnt_del = warp_sum(cnt_del); cnt_ins = warp_sum(cnt_ins); }

@@ -1,0 +1,105 @@
+"""Boundary proof inside the reference's OWN driver: the reference's unmodified `anonymize_genome`
+(short_read_tumor_normal_anonymizer.py:625-760) - its window / section loop, `anonymize_window`, pairing, first-write-wins
+and the FASTQ / statistics writers - is executed with `B200GermlineAnonymizer` passed as its `anonymizer`, and must write
+the same seven files it wrote with its own `CompleteGermlineAnonymizer` (tests/golden/genome_cases.json).
+
+This needs the reference sources, which exist in the build container only (no GPU there) and cannot travel to the GPU box
+(the package's build backend, poetry-core, and pysam are absent, so it cannot be installed into baseline/_ref).  The proof
+is therefore split: HERE the plugin's host side (pileup collection, packing, object reconstruction, yield order, counter
+calls) runs inside the reference's driver with the CPU oracle standing in for the device behind the engine's two calls;
+on the GPU box tests/test_gpu_plugin.py runs the same plugin class on the CUDA engine against the reference's sessions.
+"""
+import json
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("GA_REFERENCE_ROOT", "/root/reference")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "src", "GenomeAnonymizer", "pileup_io.pyx")),
+                                reason="the reference sources are only mounted in the build container")
+
+
+class OracleEngine:
+    """The two engine calls the plugin makes, answered by the CPU oracle (test infrastructure)."""
+
+    def __init__(self):
+        self.reference = None
+        self.runs = 0
+
+    def upload_reference(self, contig_id, bases):
+        self.reference = bases if isinstance(bases, (bytes, bytearray)) else str(bases).encode("ascii")
+
+    def run(self, batch, sessions):
+        from oracle import oracle
+        res, st = oracle.run(batch, sessions, self.reference)
+        assert st == 0
+        self.runs += 1
+        return res
+
+
+@pytest.fixture(scope="module")
+def ref_modules():
+    saved_path, saved_mods = list(sys.path), {k: sys.modules.get(k) for k in ("pysam", "pileup_io", "variant_extractor", "variant_extractor.variants")}
+    sys.path[:0] = [os.path.join(HERE, "ref_stub"), REF]
+    for k in saved_mods:
+        sys.modules.pop(k, None)
+    import pysam, variant_extractor                                                     # noqa: E401  (the stubs)
+    from variant_extractor.variants import VariantRecord, VariantType
+    from src.GenomeAnonymizer import short_read_tumor_normal_anonymizer as SR
+    yield {"pysam": pysam, "vx": variant_extractor, "VariantRecord": VariantRecord, "VariantType": VariantType, "SR": SR}
+    sys.path[:] = saved_path
+    for k, v in saved_mods.items():
+        sys.modules.pop(k, None)
+        if v is not None:
+            sys.modules[k] = v
+    for k in [m for m in sys.modules if m.startswith("src.GenomeAnonymizer") or m == "src"]:
+        sys.modules.pop(k, None)
+
+
+GENOME = json.load(open(os.path.join(HERE, "golden", "genome_cases.json")))
+
+
+def run_reference_driver(mods, cases, vcf_rows, anonymizer, tmp):
+    pysam, vx, SR = mods["pysam"], mods["vx"], mods["SR"]
+    seg = lambda r, contig: pysam.AlignedSegment(r["name"], r["flag"], contig, r["pos"], r["cigar"], r["seq"], r["qual"])
+    t = [seg(r, c["contig"]) for c in cases for r in c["reads"] if r["dataset"] == 0]
+    n = [seg(r, c["contig"]) for c in cases for r in c["reads"] if r["dataset"] == 1]
+    pysam.register_alignment_file("T.bam", t, [c["contig"] for c in cases])
+    pysam.register_alignment_file("N.bam", n, [c["contig"] for c in cases])
+    pysam.register_fasta("ref.fa", {c["contig"]: c["reference"] for c in cases})
+    vcf = [mods["VariantRecord"](v[0], v[1], v[2], v[3], v[4], v[5], mods["VariantType"][v[6]]) for v in vcf_rows]
+    vx.register_vcf("s.vcf", vcf)
+    fasta = pysam.FastaFile("ref.fa")
+    windows = SR.get_windows(vx.VariantExtractor("s.vcf"), SR.get_ref_idxs(fasta))
+    cwd = os.getcwd()
+    os.chdir(tmp)                                                                        # the driver writes <T>_<N>.mem_debug into the cwd (SR.py:633)
+    try:
+        SR.anonymize_genome(windows, "T.bam", "N.bam", "ref.fa", anonymizer, os.path.join(tmp, "T.anonymized"), os.path.join(tmp, "N.anonymized"),
+                            None, None, True, 1)
+    finally:
+        os.chdir(cwd)
+    names = ("T.anonymized.1.fastq", "T.anonymized.2.fastq", "N.anonymized.1.fastq", "N.anonymized.2.fastq",
+             "T.anonymized.single_end.fastq", "N.anonymized.single_end.fastq", "N.bam.statistics.txt")
+    return {nm: (open(os.path.join(tmp, nm)).read() if os.path.exists(os.path.join(tmp, nm)) else None) for nm in names}
+
+
+@pytest.mark.parametrize("entry", GENOME["cases"], ids=[e["case"]["name"] for e in GENOME["cases"]])
+def test_reference_driver_with_the_plugin_writes_the_reference_files(ref_modules, entry, tmp_path):
+    from genomeanonymizer_b200.anonymizer_methods import B200GermlineAnonymizer
+    eng = OracleEngine()
+    files = run_reference_driver(ref_modules, [entry["case"]], entry["vcf"], B200GermlineAnonymizer(engine=eng), str(tmp_path))
+    assert eng.runs >= len(entry["expected"]["windows"])                                 # one engine call per pileup region
+    for name, text in entry["expected"]["files"].items():
+        assert files[name] == text, (entry["case"]["name"], name)
+
+
+def test_reference_driver_with_the_plugin_on_two_contigs(ref_modules, tmp_path):
+    from genomeanonymizer_b200.anonymizer_methods import B200GermlineAnonymizer
+    two = GENOME["two_contigs"]
+    files = run_reference_driver(ref_modules, two["cases"], two["vcf"], B200GermlineAnonymizer(engine=OracleEngine()), str(tmp_path))
+    for name, text in two["expected"]["files"].items():
+        assert files[name] == text, name
