@@ -298,7 +298,9 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     for (int w = glane; w < units * 4; w += kGroup) {
         const int j0 = w << 3;
         uint32_t v = 0u;
-        if (j0 < new_len) {
+        if (j0 + 8 <= p) v = stage_at(j0);                               // wholly in front of the edit (the usual word)
+        else if (j0 >= ins_end && j0 + 8 <= new_len) v = stage_at(j0 + shift);   // wholly behind it
+        else if (j0 < new_len) {
             const uint32_t mA = low_nibbles(p - j0), mAB = low_nibbles(ins_end - j0);
             if (mA) v = stage_at(j0) & mA;
             if (mAB & ~mA) v |= ref_word(B.ref4, (int64_t)E.pos[0] + (j0 - p)) & (mAB & ~mA);
@@ -319,7 +321,9 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
     for (int w = glane; w < units * 8; w += kGroup) {
         const int p0 = w << 2;
         uint32_t v = 0u;
-        if (p0 < new_len) {
+        if (p0 + 4 <= b1) v = qual_at(p0);                               // wholly in front of the edit (the usual word)
+        else if (p0 >= b2 && p0 + 4 <= new_len) v = qual_at(p0 + d3);    // wholly behind it
+        else if (p0 < new_len) {
             const uint32_t m1 = low_bytes(b1 - p0), m12 = low_bytes(b2 - p0);
             if (m1) v = qual_at(p0) & m1;
             if (m12 & ~m1) v |= (mean * 0x01010101u) & (m12 & ~m1);

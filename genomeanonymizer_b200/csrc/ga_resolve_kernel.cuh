@@ -710,20 +710,36 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         // hashed compare per candidate, a full compare only where the hash agrees - and tells the representative which
         // dataset saw the key; an observation is germline when its representative was told by both.
         uint32_t cnt_del = 0, cnt_ins = 0;
+        // the smallest observation of every hash bucket (mpatch is not in use yet): equal keys share a bucket, so the
+        // bucket's smallest member is the representative unless two different keys met in the bucket
+        uint32_t* kt = sm->mpatch;
+        static_assert((kModL & (kModL - 1)) == 0, "bucket count is a power of two");
+        if (n_obs > 0) {
+#pragma unroll 1
+            for (int k = lane; k < kModL; k += 32) kt[k] = 0xffffffffu;
+            __syncwarp();
+#pragma unroll 1
+            for (int o = lane; o < n_obs; o += 32) atomicMin(&kt[sm->o_key[o] & (kModL - 1)], (uint32_t)o);
+            __syncwarp();
+        }
 #pragma unroll 1
         for (int o = lane; o < n_obs; o += 32) {
             const int o_col = sm->o_col[o];
             const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o], o_key = sm->o_key[o];
             int rep = o;
-#pragma unroll 1
-            for (int j = 0; j < o; ++j) {
-                if (sm->o_key[j] != o_key) continue;
-                if (sm->o_col[j] != o_col) continue;
+            const int cand = (int)kt[o_key & (kModL - 1)];
+            auto same_key = [&](int j) -> bool {
+                if (sm->o_key[j] != o_key || sm->o_col[j] != o_col) return false;
                 const uint32_t j_meta = sm->o_meta[j];
-                if (((j_meta ^ o_meta) & (kMetaIns | kMetaLenMask)) != 0u || (sm->o_ra[j] >> 16) != (o_ra >> 16) || sm->o_s0[j] != o_s0 || sm->o_s1[j] != o_s1) continue;
-                if ((o_ra >> 16) > 16u && !long_allele_tail_equal(c, o_ra, sm->o_irp[o], sm->o_ra[j], sm->o_irp[j])) continue;   // bases behind the 16-base signature
-                rep = j;
-                break;
+                if (((j_meta ^ o_meta) & (kMetaIns | kMetaLenMask)) != 0u || (sm->o_ra[j] >> 16) != (o_ra >> 16) || sm->o_s0[j] != o_s0 || sm->o_s1[j] != o_s1) return false;
+                return !((o_ra >> 16) > 16u && !long_allele_tail_equal(c, o_ra, sm->o_irp[o], sm->o_ra[j], sm->o_irp[j]));   // bases behind the 16-base signature
+            };
+            if (cand != o) {
+                if (same_key(cand)) rep = cand;
+                else {                                                    // two keys in one bucket (rare): look for the first equal one
+#pragma unroll 1
+                    for (int j = 0; j < o; ++j) if (same_key(j)) { rep = j; break; }
+                }
             }
             atomicOr(&sm->o_cls[o], (uint32_t)rep);                   // the entry was zeroed; others may be adding their dataset bits to it
             atomicOr(&sm->o_cls[rep], (o_meta & kMetaDs) ? 0x20000u : 0x10000u);

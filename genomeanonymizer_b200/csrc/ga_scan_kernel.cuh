@@ -265,29 +265,35 @@ __device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int 
         __syncwarp();
     }
     // ---- SNV candidates (variation_classifier.py:147-150)
+    // an aligned op travels as two words: (query start | length << 16) and the diagonal (reference minus query
+    // offset); every other op travels with length 0 and drops out of the overlap test by itself
+    const uint32_t seg_ql = aligned ? ((uint32_t)q0 | ((uint32_t)ln << 16)) : 0u;
+    const int seg_diag = r0 - q0;
+    const uint32_t al_mask = __ballot_sync(0xffffffffu, aligned);
     const int nw = act ? (g_L + 7) >> 3 : 0;
     const int nw_max = __reduce_max_sync(0xffffffffu, nw);
-    const int ops_max = (int)__reduce_max_sync(0xffffffffu, act ? g_nops : 0u);
     const int relbase = c.ws->relbase;
+    // op slots that hold an aligned op in at least one of the four groups
+    const uint32_t slots = (al_mask | (al_mask >> 8) | (al_mask >> 16) | (al_mask >> 24)) & 0xffu;
     for (int wb = 0; wb < nw_max; wb += 8) {
         const int w = wb + gl;
         const bool mine = w < nw;
         const int qb = w << 3;
         const uint32_t v = mine ? rec[w] : 0u;
+        uint32_t todo = slots;
 #pragma unroll 1
-        for (int j = 0; j < ops_max; ++j) {
-            const uint32_t o_op = __shfl_sync(0xffffffffu, op, gbase + j);
-            const int o_q0 = __shfl_sync(0xffffffffu, q0, gbase + j), o_r0 = __shfl_sync(0xffffffffu, r0, gbase + j), o_ln = __shfl_sync(0xffffffffu, ln, gbase + j);
-            if (!mine || !(o_op == 0u || o_op == 7u || o_op == 8u)) continue;
-            const int lo = max(o_q0, qb), hi = min(min(o_q0 + o_ln, qb + 8), g_L);
-            if (lo >= hi) continue;
-            const int p0 = g_pos + o_r0 - o_q0 + qb;                      // reference position of query base qb under this segment (>= pos - 7)
+        while (todo) {
+            const int j = __ffs(todo) - 1; todo &= todo - 1u;
+            const uint32_t o_ql = __shfl_sync(0xffffffffu, seg_ql, gbase + j);
+            const int o_diag = __shfl_sync(0xffffffffu, seg_diag, gbase + j);
+            const int o_q0 = (int)(o_ql & 0xffffu), o_end = o_q0 + (int)(o_ql >> 16);
+            const int lo = max(o_q0, qb), hi = min(min(o_end, qb + 8), g_L);
+            if (!mine || lo >= hi) continue;
+            const int p0 = g_pos + o_diag + qb;                           // reference position of query base qb under this segment (>= pos - 7)
             const int nib = p0 + 8 - relbase;                             // nibble offset in the staged window (>= -7)
             const uint32_t fw = nib >= 0 ? __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u)
                                          : (c.ws->sref[0] << ((uint32_t)(-nib) * 4u));
-            uint32_t mask = 0xffffffffu;
-            if (lo > qb) mask &= 0xffffffffu << ((lo - qb) * 4);
-            if (hi < qb + 8) mask &= 0xffffffffu >> ((qb + 8 - hi) * 4);
+            const uint32_t mask = (0xffffffffu << ((lo - qb) * 4)) & (0xffffffffu >> ((qb + 8 - hi) * 4));
             uint32_t x = (v ^ fw) & mask;
             while (x) {
                 const int n = (__ffs(x) - 1) >> 2;
