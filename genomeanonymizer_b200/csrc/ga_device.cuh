@@ -22,7 +22,9 @@ constexpr uint32_t kMetaIns = 1u << 31;
 constexpr uint32_t kMetaDs = 1u << 30;
 constexpr uint32_t kMetaGerm = 1u << 29;
 constexpr uint32_t kMetaRep = 1u << 28;
-constexpr uint32_t kMetaLenMask = (1u << 28) - 1;
+constexpr uint32_t kMetaSeenT = 1u << 24;   // on a key's representative observation: a tumor / normal read showed the key
+constexpr uint32_t kMetaSeenN = 1u << 25;
+constexpr uint32_t kMetaLenMask = (1u << 24) - 1;   // op lengths are below 65,536 (the read length is 16 bits)
 
 // msize word (per candidate read, after analysis)
 constexpr uint32_t kModFlag = 1u << 30;

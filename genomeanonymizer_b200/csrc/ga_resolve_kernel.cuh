@@ -20,7 +20,7 @@ namespace ga {
 constexpr int kResThreads = 128;
 constexpr int kEntR = 2 * kEntHalf;
 constexpr int kObsR = 2 * kObsHalf;
-constexpr int kHashR = 512;
+constexpr int kHashR = 256;
 constexpr int kGermStride = kGermCap + 4;   // per session: [0] germline SNV alleles, [1] col_begin, [4..] (column << 4) | base code
 static_assert(kReads2 / 32 <= kResThreads, "phase L gives every bitmap word its own thread");
 
@@ -126,8 +126,8 @@ struct SmemR {
     uint32_t o_read[kObsR];              // session-relative read (low 16) | allele length (high 16)
     int32_t o_irp[kObsR];
     uint32_t o_sig0[kObsR], o_sig1[kObsR];
-    int16_t o_next[kObsR], o_rnext[kObsR];
-    int16_t ihash[kHashR];               // heads of the observation chains, hashed by column
+    int16_t o_rep[kObsR], o_rnext[kObsR]; // o_rep: the first observation with the same key (its representative)
+    uint32_t kt[kHashR];                 // per hash bucket of the key: the smallest observation in it
     uint32_t mpatch[kMod2];              // two germline hits of a clean read: (column << 4) | reference code, 16 bits each
     uint8_t mpc[kMod2];                  // germline SNV hits per modified read
 };
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
         // ---- stage the session: zeroed tables, entries and observations from the scan kernel's regions
         for (int k = tid; k < ((n_cols + 3) >> 2); k += T) sm->tab[k] = 0u;
         for (int k = tid; k < n_cw; k += T) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
-        if (n_obs > 0) for (int k = tid; k < kHashR; k += T) sm->ihash[k] = (int16_t)-1;
+        if (n_obs > 0) for (int k = tid; k < kHashR; k += T) sm->kt[k] = 0xffffffffu;
         if (tid == 0) { s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u; s_ngerm = 0u; s_overflow = 0u; }
         {
             const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
@@ -250,19 +250,12 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             if (idx < 0) { s_overflow = 1u; continue; }                // IUPAC read base: the fallback kernel keeps all 16 codes
             atomicOr(&sm->tab[col >> 2], 1u << (idx + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
         }
-        for (int o = tid; o < n_obs; o += T) {
-            // push on the column's chain: 16-bit heads are updated with a CAS on the containing word
-            const int h = sm->o_col[o] & (kHashR - 1);
-            uint32_t* hw = reinterpret_cast<uint32_t*>(sm->ihash) + (h >> 1);
-            const int shift = (h & 1) * 16;
-            uint32_t old = *hw, assumed;
-            do {
-                assumed = old;
-                sm->o_next[o] = (int16_t)((assumed >> shift) & 0xffffu);
-                __threadfence_block();
-                old = atomicCAS(hw, assumed, (assumed & ~(0xffffu << shift)) | (((uint32_t)o & 0xffffu) << shift));
-            } while (old != assumed);
-        }
+        auto obs_hash = [&](int o) -> uint32_t {                         // equal keys (variants.py:83-96) hash alike
+            uint32_t kh = (uint32_t)sm->o_col[o] * 0x9E3779B1u ^ ((sm->o_meta[o] & (kMetaIns | kMetaLenMask)) * 0x85EBCA77u) ^ ((sm->o_read[o] >> 16) * 0xC2B2AE3Du) ^
+                          (sm->o_sig0[o] * 0x27D4EB2Fu) ^ (sm->o_sig1[o] * 0x165667B1u);
+            return (kh ^ (kh >> 15)) & (kHashR - 1);
+        };
+        for (int o = tid; o < n_obs; o += T) atomicMin(&sm->kt[obs_hash(o)], (uint32_t)o);
         __syncthreads();
         if (s_overflow) {
             __syncthreads();
@@ -299,20 +292,29 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             cnt = warp_sum(cnt);
             if (lane == 0 && cnt) atomicAdd(&s_cnt[0], cnt);
         }
-        for (int o = tid; o < n_obs; o += T) {                        // indels: exact key equality (variants.py:83-96)
-            const uint32_t m = sm->o_meta[o];
+        // indels: exact key equality (variants.py:83-96).  Equal keys share a hash bucket, so an observation's
+        // representative (the first observation equal to it) is the bucket's smallest member unless two keys met in the
+        // bucket; the representative collects which datasets showed the key.
+        for (int o = tid; o < n_obs; o += T) {
             const int col = sm->o_col[o];
-            bool germ = false, rep = true;
-            for (int o2 = sm->ihash[col & (kHashR - 1)]; o2 >= 0; o2 = sm->o_next[o2]) {
-                if (o2 == o || sm->o_col[o2] != col) continue;
-                if (!obs_equal2(c, sm, o, o2)) continue;
-                if ((sm->o_meta[o2] ^ m) & kMetaDs) germ = true;
-                if (o2 < o) rep = false;
+            const int cand = (int)sm->kt[obs_hash(o)];
+            int rep = o;
+            if (cand != o) {
+                if (sm->o_col[cand] == col && obs_equal2(c, sm, o, cand)) rep = cand;
+                else for (int j = 0; j < o; ++j) if (sm->o_col[j] == col && obs_equal2(c, sm, o, j)) { rep = j; break; }
             }
+            sm->o_rep[o] = (int16_t)rep;
+            atomicOr(&sm->o_meta[rep], (sm->o_meta[o] & kMetaDs) ? kMetaSeenN : kMetaSeenT);
+        }
+        __syncthreads();
+        for (int o = tid; o < n_obs; o += T) {
+            const uint32_t m = sm->o_meta[o];
+            const int rep = sm->o_rep[o];
+            bool germ = (sm->o_meta[rep] & (kMetaSeenT | kMetaSeenN)) == (kMetaSeenT | kMetaSeenN);
             if (germ && obs_equals_keep2(c, sm, o)) germ = false;
             if (germ) {
-                atomicOr(&sm->o_meta[o], kMetaGerm | (rep ? kMetaRep : 0u));
-                if (rep) atomicAdd(&s_cnt[(m & kMetaIns) ? 2 : 1], 1u);
+                atomicOr(&sm->o_meta[o], kMetaGerm | (rep == o ? kMetaRep : 0u));
+                if (rep == o) atomicAdd(&s_cnt[(m & kMetaIns) ? 2 : 1], 1u);
                 const uint32_t i = (uint32_t)obs_read(sm, o);
                 atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
                 atomicOr(&sm->indelbits[i >> 5], 1u << (i & 31));
