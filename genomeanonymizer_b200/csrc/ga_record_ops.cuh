@@ -13,7 +13,7 @@ constexpr int kCols2 = 2688;           // allele-table columns per session (shar
 constexpr int kReads2 = 4096;          // candidate reads per session
 constexpr int kMod2 = 1024;            // modified reads per session
 constexpr uint32_t kLen2 = (1u << 24) - 1;   // msize: length bits (flags above: kModFlag, kQualFlag)
-constexpr int kGermCap = 32;           // germline SNV alleles per session handed to the emission kernels
+constexpr int kGermCap = 252;          // germline SNV alleles per session handed to the emission kernels (below 256: per-read hit counters are bytes)
 constexpr int kGroup = 8;              // lanes that cooperate on one non-trivial output record
 
 struct EditAux { int32_t irp0, pos0; uint32_t len0; int32_t irp1, pos1; uint32_t len1; uint32_t ne_ndel, qidx; };   // len bit 31 = INS; ne | n_del << 8;

@@ -18,7 +18,7 @@
 namespace ga {
 
 constexpr int kResThreads = 128;
-constexpr int kEntR = 2 * kEntHalf;
+constexpr int kEntR = 1536;              // entries staged in shared memory; sessions with more stream them from the scan kernel's regions
 constexpr int kObsR = 2 * kObsHalf;
 constexpr int kHashR = 256;
 constexpr int kGermStride = kGermCap + 4;   // per session: [0] germline SNV alleles, [1] col_begin, [4..] (column << 4) | base code
@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             continue;
         }
         const int n_ent0 = (int)cnt0.x, n_ent = n_ent0 + (int)cnt1.x;
+        // staged in shared memory when they fit, streamed from the scan kernel's regions otherwise
+        const uint32_t* ent0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
+        const bool ent_staged = n_ent <= kEntR;
+        auto ent_at = [&](int k) -> uint32_t { return ent_staged ? sm->ent[k] : (k < n_ent0 ? __ldg(ent0 + k) : __ldg(ent0 + kEntHalf + (k - n_ent0))); };
         const int n_obs0 = (int)cnt0.y, n_obs = n_obs0 + (int)cnt1.y;
         const uint32_t sess_reads = cnt0.z + cnt1.z, sess_bases = cnt0.w + cnt1.w;
         c.first = S.first[s];
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
         {
             const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
             const uint32_t* e1 = e0 + kEntHalf;
-            for (int k = tid; k < n_ent; k += T) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+            if (n_ent <= kEntR) for (int k = tid; k < n_ent; k += T) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
             const ObsRec* o0 = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
             const ObsRec* o1 = o0 + kObsHalf;
             for (int o = tid; o < n_obs; o += T) {
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
 
         // ---- build: allele table and observation chains
         for (int k = tid; k < n_ent; k += T) {
-            const uint32_t e = sm->ent[k];
+            const uint32_t e = ent_at(k);
             const uint32_t col = (e >> 4) & 0xfffu;
             const int idx = acgt_index(e & 15u);
             if (idx < 0) { s_overflow = 1u; continue; }                // IUPAC read base: the fallback kernel keeps all 16 codes
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
 
         // ---- resolve + mark: germline = seen in tumor AND normal, minus variant_to_keep
         for (int k = tid; k < n_ent; k += T) {
-            const uint32_t e = sm->ent[k];
+            const uint32_t e = ent_at(k);
             const uint32_t col = (e >> 4) & 0xfffu;
             const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
             const int idx = acgt_index(e & 15u);
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
 
         // ---- the germline hits of every clean modified read (they travel in the emission descriptor)
         for (int k = tid; k < n_ent; k += T) {
-            const uint32_t e = sm->ent[k];
+            const uint32_t e = ent_at(k);
             if (e & kEntGen) continue;
             const uint32_t col = (e >> 4) & 0xfffu;
             const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
@@ -622,14 +626,18 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         }
         const int n_obs = (int)(n_obs0 + n_obs1);
         const uint32_t n_ent = n_ent0 + n_ent1;
-        if (c.n_range > kReadsL || n_obs > kObsL || n_ent > (uint32_t)kEntL) {
+        if (c.n_range > kReadsL || n_obs > kObsL) {
             if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
         // ---- round trip 2: entries, observations, keep allele; tables zeroed meanwhile
-        {
-            const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
-            const uint32_t* e1 = e0 + kEntHalf;
+        // the entries are staged in shared memory when they fit (the usual session) and streamed from the scan kernel's
+        // regions - three passes over L2 - when they do not (noisy reads: one candidate per mismatch)
+        const uint32_t* e0 = X.ent + (size_t)(2 * (size_t)s) * kEntHalf;
+        const uint32_t* e1 = e0 + kEntHalf;
+        const bool ent_staged = n_ent <= (uint32_t)kEntL;
+        auto ent_at = [&](uint32_t k) -> uint32_t { return ent_staged ? sm->ent[k] : (k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0))); };
+        if (ent_staged) {
 #pragma unroll 2
             for (uint32_t k = lane; k < n_ent; k += 32) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
         }
@@ -665,7 +673,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         bool bad = false;
 #pragma unroll 1
         for (uint32_t k = lane; k < n_ent; k += 32) {
-            const uint32_t e = sm->ent[k], b = e & 15u;
+            const uint32_t e = ent_at(k), b = e & 15u;
             if (b == 0u || (b & (b - 1u))) { bad = true; continue; }   // IUPAC read base: the fallback kernel keeps all 16 codes
             const uint32_t col = (e >> 4) & 0xfffu;
             atomicOr(&sm->tab[col >> 2], 1u << ((__ffs(b) - 1) + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
@@ -679,14 +687,14 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         // Bit 31 of an entry remembers that it is a germline hit (pass 3 needs only those).
 #pragma unroll 1
         for (uint32_t k = lane; k < n_ent; k += 32) {
-            const uint32_t e = sm->ent[k];
+            const uint32_t e = ent_at(k);
             const uint32_t col = (e >> 4) & 0xfffu;
             const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
             if ((((byte & (byte >> 4)) >> (__ffs(e & 15u) - 1)) & 1u) && (e & 0xffffu) != keep_key) {
                 const uint32_t i = (e >> 16) & 0xfffu;
                 atomicOr(&sm->modbits[i >> 5], 1u << (i & 31));
                 if (e & kEntGen) atomicOr(&sm->genbits[i >> 5], 1u << (i & 31));
-                sm->ent[k] = e | 0x80000000u;
+                if (ent_staged) sm->ent[k] = e | 0x80000000u;
             }
         }
         uint32_t cnt_snv = 0;
@@ -827,8 +835,13 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         // ---- pass 3: the germline hits of every clean modified read
 #pragma unroll 1
         for (uint32_t k = lane; k < n_ent; k += 32) {
-            const uint32_t e = sm->ent[k];
-            if ((e & (0x80000000u | kEntGen)) != 0x80000000u) continue;
+            const uint32_t e = ent_at(k);
+            if (ent_staged) { if ((e & (0x80000000u | kEntGen)) != 0x80000000u) continue; }
+            else {                                                    // streamed: the germline test of pass 2 again
+                if (e & kEntGen) continue;
+                const uint32_t c2 = (e >> 4) & 0xfffu, byte = (sm->tab[c2 >> 2] >> (8 * (c2 & 3u))) & 0xffu;
+                if (!((((byte & (byte >> 4)) >> (__ffs(e & 15u) - 1)) & 1u) && (e & 0xffffu) != keep_key)) continue;
+            }
             const uint32_t col = (e >> 4) & 0xfffu, i = (e >> 16) & 0xfffu;
             const uint32_t m = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
             uint32_t* cw = reinterpret_cast<uint32_t*>(sm->mpc) + (m >> 2);

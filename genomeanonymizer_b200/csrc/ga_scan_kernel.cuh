@@ -23,7 +23,7 @@
 
 namespace ga {
 
-constexpr int kEntHalf = 768;            // SNV candidate entries per item (tumor or normal half of a session)
+constexpr int kEntHalf = 2560;           // SNV candidate entries per item (tumor or normal half of a session): room for a 1 % mismatch rate at 60x
 constexpr int kObsHalf = 384;            // indel observations per item
 constexpr int kTileUnits = 156;          // 16-byte units staged per tile (31 reads of 150 bp and room to spare)
 constexpr int kWbuf = 168;                // entries buffered per warp between flushes

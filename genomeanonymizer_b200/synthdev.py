@@ -67,6 +67,9 @@ WORKLOADS = {
                                 max_indel=20),
     # configs[3] at 1/10 scale: high variant density, 60x tumor / 30x normal
     "dense-60x30x": SynthConfig("dense-60x30x", 310_000_000, 100_000, 60.0, 30.0),
+    # capacity check: a realistic 1 % mismatch rate at 60x / 30x - an order of magnitude more SNV
+    # candidates per window than the error model of the other workloads
+    "noisy-60x30x": SynthConfig("noisy-60x30x", 62_000_000, 20_000, 60.0, 30.0, err_rate=1e-2),
     # small shapes for tests
     "tiny": SynthConfig("tiny", 400_000, 40, 30.0, 30.0, indel_rate=4e-4, clip_frac=0.1),
     "tiny-stress": SynthConfig("tiny-stress", 300_000, 24, 20.0, 25.0, read_len=100, indel_rate=3e-3, clip_frac=0.3,
