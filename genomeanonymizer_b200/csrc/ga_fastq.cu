@@ -93,7 +93,8 @@ __device__ __forceinline__ uint8_t base_char(uint32_t code) {
     return (uint8_t)(((code & 8u) ? w1 : w0) >> (8u * (code & 7u)));
 }
 
-constexpr int kStageBytes = 1024;        // staged text per warp (records of up to ~500 bases)
+constexpr int kStageBytes = 544;         // staged text per group of 8 lanes (records of up to ~250 bases)
+constexpr int kRenderGroup = 8;          // lanes that render one record
 
 struct FastqItem {                       // everything one record needs, gathered lane-per-record and broadcast by shuffle
     const uint32_t* seqw; const uint8_t* q; const uint8_t* name; int64_t off; int nl, L; uint32_t flag; int ok;
@@ -110,12 +111,27 @@ __device__ __forceinline__ FastqItem shfl_item(const FastqItem& it, int src) {
     return o;
 }
 
+// eight base codes (one 32-bit word of seq4) -> eight characters, six byte permutes
+__device__ __forceinline__ void base_chars8(uint32_t cw, uint32_t* ch) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t n16 = (cw >> (16 * h)) & 0xffffu;
+        const uint32_t sel = n16 & 0x7777u;
+        const uint32_t lo = __byte_perm(0x4d43413du, 0x56535247u, sel);      // "=ACM" "GRSV"
+        const uint32_t hi = __byte_perm(0x48595754u, 0x4e42444bu, sel);      // "TWYH" "KDBN"
+        ch[h] = __byte_perm(lo, hi, 0x3210u + ((n16 & 0x8888u) >> 1));
+    }
+}
+
 // A warp takes 32 records at a time: their indices, lengths, offsets and source pointers are gathered lane-per-record
-// (three dependent round trips for the whole batch), then the records are rendered one after the other.
+// (three dependent round trips for the whole batch).  Then FOUR records are rendered at a time, a group of 8 lanes
+// each: every lane first issues all of its loads (at most four sequence words, eight quality words), so that the
+// loads of four records are in flight together, then the characters are produced into the group's shared-memory
+// slice with the alignment of their destination and leave with aligned 128-bit stores.
 __global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const int64_t* __restrict__ text_off, uint8_t* __restrict__ text,
                                                            int64_t text_cap, ga_totals* totals) {
-    __shared__ __align__(16) uint8_t stage[8][kStageBytes];
-    const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint8_t stage[8][32 / kRenderGroup][kStageBytes];
+    const int lane = threadIdx.x & 31, g = lane / kRenderGroup, gl = lane % kRenderGroup;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t k0 = warp0 * 32; k0 < V.n_items; k0 += n_warps * 32) {
@@ -148,66 +164,86 @@ __global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const in
             }
         }
         const int n_here = (int)min((int64_t)32, V.n_items - k0);
-        // ---- one record after the other, all lanes
-        for (int j = 0; j < n_here; ++j) {
-            const FastqItem it = shfl_item(me, j);
-            if (!it.ok) continue;
+        // does the record fit a group's slice?  (destination alignment pad + text; at most 32 words of bases, 64 of qualities)
+        const int my_pad = (int)(reinterpret_cast<uintptr_t>(text + me.off) & 15u);
+        const bool my_fit = me.ok && my_pad + me.nl + 2ll * me.L + 8 <= (int64_t)kStageBytes && me.L <= 256 && me.nl <= 200;
+        uint32_t slow_mask = __ballot_sync(0xffffffffu, me.ok && !my_fit);
+        const uint32_t fit_mask = __ballot_sync(0xffffffffu, my_fit);
+        // ---- four records per step, 8 lanes each
+        for (int step = 0; step < 32 / (32 / kRenderGroup); ++step) {
+            if (!((fit_mask >> (4 * step)) & 0xfu)) continue;           // warp-uniform
+            const int src = 4 * step + g;
+            const FastqItem it = shfl_item(me, src);
+            const bool act = src < n_here && ((fit_mask >> src) & 1u);
             const int nl = it.nl, L = it.L;
             const bool reverse = (it.flag & 0x10u) != 0u;
             const uint8_t mate = (it.flag & 0x40u) ? '1' : '2';           // anonymizer_methods.py:218
-            const int64_t total = (int64_t)nl + 2ll * L + 8;
+            const int total = nl + 2 * L + 8;
             uint8_t* out = text + it.off;
             const int pad = (int)(reinterpret_cast<uintptr_t>(out) & 15u);   // the staged copy has the alignment of its destination
-            if (pad + total <= (int64_t)kStageBytes) {
-                // ---- staged path: characters are produced into the warp's shared-memory slice (8 bases / 4 qualities
-                // per lane and step), then written out with aligned 128-bit stores
-                uint8_t* sg = stage[threadIdx.x >> 5] + pad;
-                for (int c = lane; c < nl + 4; c += 32)
+            uint8_t* sb = stage[threadIdx.x >> 5][g];
+            uint8_t* sg = sb + pad;
+            // every load first
+            uint32_t sw[4], qv[8];
+            const int nw = act ? (L + 7) >> 3 : 0, nq = act ? (L + 3) >> 2 : 0;
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(it.q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int w = gl + kRenderGroup * t; sw[t] = w < nw ? __ldg(it.seqw + w) : 0u; }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { const int w = gl + kRenderGroup * t; qv[t] = w < nq ? __ldg(qw + w) : 0u; }
+            if (act) {
+                for (int c = gl; c < nl + 4; c += kRenderGroup)
                     sg[c] = c == 0 ? (uint8_t)'@' : c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
                 uint8_t* ss = sg + nl + 4;
-                for (int w = lane; w < ((L + 7) >> 3); w += 32) {
-                    uint32_t cw = it.seqw[w];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int w = gl + kRenderGroup * t;
+                    if (w >= nw) break;
+                    uint32_t cw = sw[t];
                     int j0 = 8 * w;                                       // output position of the word's first character
                     if (reverse) {                                        // reversed nibble order + complemented codes = the word bit-reversed
                         cw = __brev(cw);
                         j0 = L - 8 - 8 * w;
                     }
                     uint32_t ch[2];
+                    base_chars8(cw, ch);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {                         // four codes -> four characters with three byte permutes
-                        const uint32_t n16 = (cw >> (16 * h)) & 0xffffu;
-                        const uint32_t sel = n16 & 0x7777u;
-                        const uint32_t lo = __byte_perm(0x4d43413du, 0x56535247u, sel);      // "=ACM" "GRSV"
-                        const uint32_t hi = __byte_perm(0x48595754u, 0x4e42444bu, sel);      // "TWYH" "KDBN"
-                        ch[h] = __byte_perm(lo, hi, 0x3210u + ((n16 & 0x8888u) >> 1));
-                    }
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int jj = j0 + t;
-                        if (jj >= 0 && jj < L) ss[jj] = (uint8_t)(ch[t >> 2] >> (8 * (t & 3)));
+                    for (int u = 0; u < 8; ++u) {
+                        const int jj = j0 + u;
+                        if (jj >= 0 && jj < L) ss[jj] = (uint8_t)(ch[u >> 2] >> (8 * (u & 3)));
                     }
                 }
-                if (lane < 3) ss[L + lane] = lane == 1 ? (uint8_t)'+' : (uint8_t)'\n';
+                if (gl < 3) ss[L + gl] = gl == 1 ? (uint8_t)'+' : (uint8_t)'\n';
                 uint8_t* sq = ss + L + 3;
-                const uint32_t* qw = reinterpret_cast<const uint32_t*>(it.q);
-                for (int w = lane; w < ((L + 3) >> 2); w += 32) {
-                    const uint32_t v = qw[w] + 0x21212121u;               // anonymizer_methods.py:232 (phred <= 93: no carry between bytes)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) if (4 * w + t < L) sq[4 * w + t] = (uint8_t)(v >> (8 * t));
+                for (int t = 0; t < 8; ++t) {
+                    const int w = gl + kRenderGroup * t;
+                    if (w >= nq) break;
+                    const uint32_t v = qv[t] + 0x21212121u;               // anonymizer_methods.py:232 (phred <= 93: no carry between bytes)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (4 * w + u < L) sq[4 * w + u] = (uint8_t)(v >> (8 * u));
                 }
-                if (lane == 0) sq[L] = (uint8_t)'\n';
-                __syncwarp();
-                const uint8_t* sb = stage[threadIdx.x >> 5];
+                if (gl == 0) sq[L] = (uint8_t)'\n';
+            }
+            __syncwarp();
+            if (act) {
                 uint8_t* gb = out - pad;                                  // 16-byte aligned
-                const int end = pad + (int)total;
-                for (int c16 = lane * 16; c16 < end; c16 += 32 * 16) {
+                const int end = pad + total;
+                for (int c16 = gl * 16; c16 < end; c16 += kRenderGroup * 16) {
                     if (c16 >= pad && c16 + 16 <= end) *reinterpret_cast<uint4*>(gb + c16) = *reinterpret_cast<const uint4*>(sb + c16);
                     else for (int t = max(c16, pad); t < min(c16 + 16, end); ++t) gb[t] = sb[t];   // the neighbours' bytes share these chunks
                 }
-                __syncwarp();
-                continue;
             }
-            // ---- general path (records longer than the staging slice): one character per lane and step
+            __syncwarp();
+        }
+        // ---- general path (records longer than a slice; rare): one record after the other, one character per lane and step
+        while (slow_mask) {
+            const int j = __ffs(slow_mask) - 1; slow_mask &= slow_mask - 1u;
+            const FastqItem it = shfl_item(me, j);
+            const int nl = it.nl, L = it.L;
+            const bool reverse = (it.flag & 0x10u) != 0u;
+            const uint8_t mate = (it.flag & 0x40u) ? '1' : '2';
+            uint8_t* out = text + it.off;
             for (int c = lane; c < nl + 4; c += 32)
                 out[c] = c == 0 ? (uint8_t)'@' : c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
             uint8_t* os = out + nl + 4;
