@@ -162,7 +162,7 @@ def pack_reads(reads: Sequence[dict], contig_id: int = 0, sparse_qual: bool = Fa
             raise ValueError("Length of the qualities does not match the length of the sequence")
         cw = parse_cigar(r["cigar"])
         qlen = int((cw >> 4)[np.isin(cw & 15, (0, 1, 4, 7, 8))].sum())
-        if qlen != L:
+        if qlen != L and not (len(cw) == 0 and int(r["flag"]) & 0x4):      # an unmapped read has no CIGAR
             raise ValueError(f"CIGAR {r['cigar']} consumes {qlen} query bases, sequence has {L}")
         cap = max(32, (L + 31) // 32 * 32)
         pos[k] = r["pos"]

@@ -50,17 +50,20 @@ struct Planner {
 
     int dataset(int32_t i) const { return i < n_tumor ? 0 : 1; }
     int mate(int32_t i) const { return ((lf[i] >> 16) & 0x40u) ? 0 : 1; }
+    bool unmapped(int32_t i) const { return ((lf[i] >> 16) & 0x4u) != 0u; }   // a mate placed at its partner's position
 
-    // AlignmentFile.fetch / pileup read selection: reads of one dataset with pos < stop and end > start
-    void overlapping(int ds, int64_t start, int64_t stop, std::vector<int32_t>& out) const {
+    // Read selection of one dataset: pileup() takes mapped reads with pos < stop and end > start (htslib drops unmapped
+    // records); fetch() also returns unmapped reads, as intervals of length one at their position.
+    void overlapping(int ds, int64_t start, int64_t stop, std::vector<int32_t>& out, bool fetch = false) const {
         out.clear();
         const int32_t* b = pos + (ds ? n_tumor : 0);
         const int32_t* e = pos + (ds ? n : n_tumor);
-        const int32_t* lo = std::lower_bound(b, e, start - span, [](int32_t p, int64_t v) { return (int64_t)p < v; });
+        const int32_t* lo = std::lower_bound(b, e, start - std::max(span, 1), [](int32_t p, int64_t v) { return (int64_t)p < v; });
         const int32_t* hi = std::lower_bound(b, e, stop, [](int32_t p, int64_t v) { return (int64_t)p < v; });
         for (const int32_t* p = lo; p < hi; ++p) {
             const int32_t i = (int32_t)(p - pos);
-            if ((int64_t)end[i] > start) out.push_back(i);
+            if (unmapped(i)) { if (fetch && (int64_t)pos[i] + 1 > start) out.push_back(i); }
+            else if ((int64_t)end[i] > start) out.push_back(i);
         }
     }
 
@@ -154,19 +157,33 @@ struct Planner {
     // Chains of reads in which every read overlaps (or touches, or ends with) the one before it
     // (collect_intersecting_reads, pileup_io.pyx:78-106 with compare, :44-59).
     struct Island { size_t begin, end_; int32_t first_pos, max_end; };   // [begin, end_) into the index list
+    // idx: the fetched reads without the unmapped ones that iter_fetch_pair sets aside (only the first fetched read can
+    // be unmapped here: it seeds an island as a read of length zero, pileup_io.pyx:72-73); max_end counts mapped reads
+    // only and is 0 without any (get_righmost_pos, :109-121).
     void islands(const std::vector<int32_t>& idx, std::vector<Island>& out) const {
         out.clear();
         for (size_t k = 0; k < idx.size(); ++k) {
             const int32_t i = idx[k];
             if (!out.empty()) {
                 const int32_t l = idx[k - 1];
-                if ((pos[i] <= end[l] && end[i] >= pos[l]) || end[i] == end[l]) {
+                const int32_t l_end = unmapped(l) ? pos[l] : end[l];
+                if ((pos[i] <= l_end && end[i] >= pos[l]) || end[i] == l_end) {
                     out.back().end_ = k + 1; out.back().max_end = std::max(out.back().max_end, end[i]);
                     continue;
                 }
             }
-            out.push_back({k, k + 1, pos[i], end[i]});
+            out.push_back({k, k + 1, pos[i], unmapped(i) ? 0 : end[i]});
         }
+    }
+    // the unmapped reads behind the first fetched read leave the list (pileup_io.pyx:93-96)
+    void set_unmapped_aside(std::vector<int32_t>& idx, std::vector<int32_t>& aside) const {
+        aside.clear();
+        size_t w = 0;
+        for (size_t k = 0; k < idx.size(); ++k) {
+            if (k > 0 && unmapped(idx[k])) aside.push_back(idx[k]);
+            else idx[w++] = idx[k];
+        }
+        idx.resize(w);
     }
     static int cmp_islands(const Island& a, const Island& b) {   // compare() of pileup_io.pyx:44-59
         const int32_t f1 = a.first_pos, l1 = a.max_end, f2 = b.first_pos, l2 = b.max_end;
@@ -180,7 +197,10 @@ struct Planner {
     std::vector<int32_t> region_entries;                   // entries first stored by the current region: ins_at still relative
     void pass_through(const std::vector<int32_t>& idx, const Island* isl, std::vector<int32_t>& deferred) {
         if (!isl) return;
-        for (size_t k = isl->begin; k < isl->end_; ++k) {
+        pass_reads(idx, isl->begin, isl->end_, deferred);
+    }
+    void pass_reads(const std::vector<int32_t>& idx, size_t begin, size_t end_, std::vector<int32_t>& deferred) {
+        for (size_t k = begin; k < end_; ++k) {
             const int32_t i = idx[k];
             const size_t n_before = entries.size();
             int32_t ent = -1;
@@ -192,10 +212,12 @@ struct Planner {
 
     // What iter_fetch_pair (pileup_io.pyx:124-298) yields for the fetched reads of one inter-window region.
     void region(int64_t start, int64_t stop) {
-        std::vector<int32_t> t_idx, n_idx, deferred;
-        overlapping(0, start, stop, t_idx);
-        overlapping(1, start, stop, n_idx);
+        std::vector<int32_t> t_idx, n_idx, deferred, t_um, n_um;
+        overlapping(0, start, stop, t_idx, true);
+        overlapping(1, start, stop, n_idx, true);
         if (t_idx.empty() && n_idx.empty()) return;
+        set_unmapped_aside(t_idx, t_um);
+        set_unmapped_aside(n_idx, n_um);
         region_entries.clear();
         std::vector<Island> ti, ni;
         islands(t_idx, ti);
@@ -221,6 +243,9 @@ struct Planner {
                 if (more_n) { pass_through(n_idx, &ni[b], deferred); ++b; }
             }
         }
+        // the unmapped reads that were set aside come last (pileup_io.pyx:298 -> SR.py:536-545), tumor then normal
+        pass_reads(t_um, 0, t_um.size(), deferred);
+        pass_reads(n_um, 0, n_um.size(), deferred);
         // the region's own records reach the files behind those of its island sessions (stream buffering)
         const int64_t base = (int64_t)plan->pairs.size() / 5;
         for (const int32_t k : region_entries) entries[k].ins_at += base;
@@ -288,6 +313,22 @@ int ga_plan_sample(int64_t n_reads, int64_t n_tumor, const int32_t* pos, const i
             start = sc.first; stop = sc.last;
         }
         P.region(start, stop);
+    }
+    // pair_unmapped_mates (SR.py:561-600, called at :725-732 when the collection is not empty): every window is fetched
+    // again (start = first - 1), tumor then normal, and an unmapped read whose name waits in the collection joins it
+    bool waiting = false;
+    for (const Planner::Entry& e : P.entries) waiting |= e.alive;
+    if (waiting) {
+        std::vector<int32_t> idx;
+        for (int32_t k = 0; k < n_windows; ++k)
+            for (int ds = 0; ds < 2; ++ds) {
+                P.overlapping(ds, std::max<int64_t>((int64_t)win_first[k] - 1, 0), win_last[k], idx, true);
+                for (const int32_t i : idx) {
+                    if (!P.unmapped(i) || P.entry_of[P.name_id[i]] < 0) continue;
+                    int64_t* slot = P.store(P.name_id[i], P.mate(i), slot_of(i, -1), (int64_t)plan->pairs.size() / 5);
+                    if (slot[0] != kNone && slot[1] != kNone) P.write_pair(P.name_id[i], slot[0], slot[1], plan->pairs);
+                }
+            }
     }
     for (const Planner::Entry& e : P.entries) {                // write_single_end_reads (SR.py:603-622), insertion order
         if (!e.alive || P.written[e.name]) continue;

@@ -337,7 +337,8 @@ template <class Prefetch>
 __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const TileMeta& m, uint32_t cw0, bool staged, int b, int lane, Prefetch&& prefetch) {
     const uint32_t sof = __shfl_sync(0xffffffffu, m.so, 0);                // first record unit of the tile (what issue_tile copied from)
     const int idx = t * TR + lane;
-    const bool valid = lane < TR && idx < c.ws->n;
+    // a placed-unmapped mate (flag 0x4) is in no session: htslib's pileup drops BAM_FUNMAP records
+    const bool valid = lane < TR && idx < c.ws->n && !((m.lf >> 16) & 0x4u);
     const int i = c.ws->i_base + idx;
     const int pos = m.pos;
     const int L = (int)meta_len(m);

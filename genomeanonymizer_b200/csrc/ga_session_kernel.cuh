@@ -109,6 +109,7 @@ __device__ void discover_read(const SessCtx& c, int i, uint32_t* n_obs, uint32_t
     const int span = ref_span_of(c.B.cigar, c0, c1);
     if (pos + span <= c.first) return;                                   // fetched by range, does not reach the region
     const uint32_t lf = __ldg(c.B.len_flag + r);
+    if ((lf >> 16) & 0x4u) return;                                        // a placed-unmapped mate: htslib's pileup drops BAM_FUNMAP records
     const int L = (int)(lf & 0xffffu);
     atomicAdd(sess_reads, 1u);
     atomicAdd(sess_bases, (uint32_t)L);

@@ -14,8 +14,9 @@ None of this needs the bases: `plan_sample` works on (name, flag, dataset, start
 The engine then masks all sessions in one `ga_run`, and `ga_fastq_render` prints the planned records.
 `tests/test_genome_files.py` checks the four files byte for byte against what the reference itself wrote.
 
-Scope: one contig per call, mapped primary alignments (no unmapped / supplementary / secondary records - SURVEY.md
-Appendix B), windows as `get_windows` makes them for SNVs and short indels.
+Scope: one contig per call, primary alignments and placed-unmapped mates (flag 0x4 at the mate's position: pileups never
+see them, regions collect them for their end, what is left is paired after the last section); no supplementary /
+secondary records; windows as `get_windows` makes them for SNVs and short indels.
 """
 from __future__ import annotations
 
@@ -101,25 +102,41 @@ def _session_yield_order(reads, t_idx: List[int], n_idx: List[int]):
     return [(n, slots[n][0], slots[n][1]) for _, _, n in sorted(early)] + [(n, slots[n][0], slots[n][1]) for _, n in sorted(late)]
 
 
-def _islands(reads, idx: List[int]) -> List[List[int]]:
+def _is_unmapped(r) -> bool:
+    return bool(r["flag"] & 0x4)
+
+
+def _islands(reads, idx: List[int], unmapped: Optional[List[int]] = None) -> List[List[int]]:
     """Chains of reads in which every read overlaps (or touches, or ends with) the one before it
-    (collect_intersecting_reads, pileup_io.pyx:78-106 with compare, :44-59)."""
+    (collect_intersecting_reads, pileup_io.pyx:78-106 with compare, :44-59).  Unmapped reads behind the first fetched
+    read are set aside in `unmapped` (:93-96); an unmapped FIRST read seeds an island like any read, as a read of
+    length zero (compare_read_alignments_intersection uses its start as its end, :72-73)."""
     out: List[List[int]] = []
     for i in idx:
+        r = reads[i]
         if out:
+            if _is_unmapped(r):
+                if unmapped is not None:
+                    unmapped.append(i)
+                continue
             last = reads[out[-1][-1]]
-            r = reads[i]
-            if (r["pos"] <= last["end"] and r["end"] >= last["pos"]) or r["end"] == last["end"]:
+            last_end = last["pos"] if _is_unmapped(last) else last["end"]
+            if (r["pos"] <= last_end and r["end"] >= last["pos"]) or r["end"] == last_end:
                 out[-1].append(i)
                 continue
         out.append([i])
     return out
 
 
+def _island_right(reads, a: List[int]) -> int:
+    """get_righmost_pos (pileup_io.pyx:109-121): the largest end of the island's mapped reads, 0 when there is none."""
+    return max((reads[i]["end"] for i in a if not _is_unmapped(reads[i])), default=0)
+
+
 def _cmp_islands(reads, a: List[int], b: List[int]) -> int:
     """compare() of pileup_io.pyx:44-59 on (first read's start, rightmost end) of two islands of one contig."""
-    f1, l1 = reads[a[0]]["pos"], max(reads[i]["end"] for i in a)
-    f2, l2 = reads[b[0]]["pos"], max(reads[i]["end"] for i in b)
+    f1, l1 = reads[a[0]]["pos"], _island_right(reads, a)
+    f2, l2 = reads[b[0]]["pos"], _island_right(reads, b)
     overlap = f2 <= l1 and l2 >= f1
     if l1 < l2:
         return -1 if overlap else -2
@@ -130,11 +147,19 @@ def _cmp_islands(reads, a: List[int], b: List[int]) -> int:
 
 def _fetch_pair_events(reads, t_idx: List[int], n_idx: List[int]):
     """What iter_fetch_pair (pileup_io.pyx:124-298) yields for the fetched tumor / normal reads of one region:
-    ("single", dataset, [reads]) or ("both", (left, right)).  The last island of each dataset is always yielded
-    singly, and when one dataset runs out the other's remaining islands are yielded singly too."""
+    ("single", dataset, [reads]) or ("both", (left, right)), and last ("unmapped", dataset, [reads]) for the unmapped
+    reads it set aside (:298).  The last island of each dataset is always yielded singly, and when one dataset runs out
+    the other's remaining islands are yielded singly too."""
     if not t_idx and not n_idx:
         return
-    ti, ni = _islands(reads, t_idx), _islands(reads, n_idx)
+    um: List[List[int]] = [[], []]
+    ti, ni = _islands(reads, t_idx, um[0]), _islands(reads, n_idx, um[1])
+    yield from _fetch_pair_island_events(reads, ti, ni)
+    yield ("unmapped", 0, um[0])
+    yield ("unmapped", 1, um[1])
+
+
+def _fetch_pair_island_events(reads, ti, ni):
     a = b = 0                                                     # current island of each dataset
     # "r is not None" in the reference = there is another island after the current one
     while True:
@@ -151,7 +176,7 @@ def _fetch_pair_events(reads, t_idx: List[int], n_idx: List[int]):
                 yield ("single", 1, ni[b]); b += 1
             else:
                 left = min(reads[ti[a][0]]["pos"], reads[ni[b][0]]["pos"])
-                right = max(max(reads[i]["end"] for i in ti[a]), max(reads[i]["end"] for i in ni[b]))
+                right = max(_island_right(reads, ti[a]), _island_right(reads, ni[b]))
                 yield ("both", (left, right)); a += 1; b += 1
         else:
             if more_t:
@@ -191,10 +216,14 @@ def _plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int
         if any(a > b for a, b in zip(pos_of[id(idx)], pos_of[id(idx)][1:])):
             raise ValueError("reads of a dataset must be in coordinate order")
 
-    def overlapping(idx, start, stop):
+    def overlapping(idx, start, stop, fetch=False):
+        """pileup(): mapped reads with pos < stop and end > start (htslib drops unmapped reads); fetch(): unmapped reads
+        too, as intervals of length one at their position."""
         ps = pos_of[id(idx)]
-        lo, hi = bisect.bisect_left(ps, start - span), bisect.bisect_left(ps, stop)
-        return [i for i in idx[lo:hi] if reads[i]["end"] > start]
+        lo, hi = bisect.bisect_left(ps, start - max(span, 1)), bisect.bisect_left(ps, stop)
+        if fetch:
+            return [i for i in idx[lo:hi] if (reads[i]["pos"] + 1 if _is_unmapped(reads[i]) else reads[i]["end"]) > start]
+        return [i for i in idx[lo:hi] if reads[i]["end"] > start and not _is_unmapped(reads[i])]
 
     def write_pair(name, s1, s2, sink=None):                      # write_pair, :134-165
         if name in written:
@@ -238,7 +267,7 @@ def _plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int
         # buffers and reach the files when the region ends, behind the records of its island sessions.  (Exact while a
         # region's pass-through text per file stays below the platform's stream buffer; see DESIGN.md.)
         deferred: List[Tuple[int, int, int, int, int]] = []
-        for ev in _fetch_pair_events(reads, overlapping(t_all, start, stop), overlapping(n_all, start, stop)):
+        for ev in _fetch_pair_events(reads, overlapping(t_all, start, stop, fetch=True), overlapping(n_all, start, stop, fetch=True)):
             if ev[0] == "both":
                 run_session(ev[1][0], ev[1][1], None, None)       # an island session has no variant to keep (:523-534)
                 continue
@@ -248,6 +277,17 @@ def _plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int
                 if slot[0] is not None and slot[1] is not None:
                     write_pair(r["name"], slot[0], slot[1], deferred)   # (stays in the collection until the end, :737-741)
         plan.pairs.extend(deferred)
+    # pair_unmapped_mates (:561-600, called at :725-732 when the collection is not empty): every window is fetched again
+    # (start = first - 1), tumor then normal, and an unmapped read whose name waits in the collection joins it
+    if to_pair:
+        for w in windows:
+            for idx in (t_all, n_all):
+                for i in overlapping(idx, max(w["first"] - 1, 0), w["last"], fetch=True):
+                    r = reads[i]
+                    if _is_unmapped(r) and r["name"] in to_pair:
+                        slot = store(r["name"], 0 if r["flag"] & 0x40 else 1, (i, -1))
+                        if slot[0] is not None and slot[1] is not None:
+                            write_pair(r["name"], slot[0], slot[1])
     for name in written:
         to_pair.pop(name, None)
     for name, slot in to_pair.items():                            # write_single_end_reads, :603-622

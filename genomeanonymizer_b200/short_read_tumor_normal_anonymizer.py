@@ -36,23 +36,21 @@ def name_output(sample: str) -> str:
     return re.sub('.bam|.sam|.cram', '.anonymized', sample)
 
 
-UNSUPPORTED_FLAGS = 0x800 | 0x4      # supplementary alignments, placed-unmapped mates
+UNSUPPORTED_FLAGS = 0x800            # supplementary alignments
 
 
 def _refuse_unsupported_records(len_flag, contig):
     """The reference keeps separate bookkeeping for supplementary alignments (primary replaces supplementary, SA tags,
-    left-over variants: anonymizer_methods.py:98-149, 245-288) and pairs placed-unmapped mates in a pass of its own
-    (short_read_tumor_normal_anonymizer.py:561-600).  Neither exists here yet, and treating such records as ordinary
-    alignments would print truncated or unmasked reads, so the entry point refuses them instead of guessing.
-    Secondary records (0x100) are first-wins in the reference as well and are accepted."""
+    left-over variants: anonymizer_methods.py:98-149, 245-288).  It does not exist here, and treating such records as
+    ordinary alignments would print truncated or unmasked reads, so the entry point refuses them instead of guessing.
+    Secondary records (0x100) are first-wins in the reference as well and are accepted; placed-unmapped mates (0x4) are
+    handled as the reference handles them (driver.plan_sample / ga_plan_sample)."""
     import numpy as np
     flags = np.asarray(len_flag) >> 16
     bad = flags & UNSUPPORTED_FLAGS
     if bad.any():
-        n_sup, n_unm = int(np.count_nonzero(bad & 0x800)), int(np.count_nonzero(bad & 0x4))
-        raise ValueError(f"contig {contig}: {n_sup} supplementary (0x800) and {n_unm} unmapped (0x4) records - this engine does not "
-                         f"implement the reference's supplementary / unmapped-mate bookkeeping; filter them first "
-                         f"(samtools view -F 0x804)")
+        raise ValueError(f"contig {contig}: {int(np.count_nonzero(bad))} supplementary (0x800) records - this engine does not implement the "
+                         f"reference's supplementary-alignment bookkeeping; filter them first (samtools view -F 0x800)")
 
 
 def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: str, ref_genome_file: str, engine,

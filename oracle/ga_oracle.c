@@ -100,6 +100,9 @@ static int ref_end_of(const ga_reads* R, int64_t r) {
     return e;
 }
 
+/* htslib's pileup drops BAM_FUNMAP records: a placed-unmapped mate is in no session */
+static int is_unmapped(const ga_reads* R, int64_t r) { return (int)((R->len_flag[r] >> 16) & 0x4u); }
+
 static int64_t lower_bound_pos(const int32_t* pos, int64_t b, int64_t e, int64_t v) {
     while (b < e) { int64_t m = (b + e) >> 1; if ((int64_t)pos[m] < v) b = m + 1; else e = m; }
     return b;
@@ -152,7 +155,7 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
     for (int d = 0; d < 2; ++d)
         for (int64_t r = rng[d][0]; r < rng[d][1]; ++r) {
             int e = ref_end_of(R, r);
-            if (e <= first) continue;
+            if (e <= first || is_unmapped(R, r)) continue;
             if (R->pos[r] < col_lo) col_lo = R->pos[r];
             if (e > col_hi) col_hi = e;
         }
@@ -172,7 +175,7 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
     uint32_t n_sess_reads = 0;
     for (int d = 0; d < 2; ++d)
         for (int64_t r = rng[d][0]; r < rng[d][1]; ++r) {
-            if (ref_end_of(R, r) <= first) continue;
+            if (ref_end_of(R, r) <= first || is_unmapped(R, r)) continue;
             ++n_sess_reads;
             const int L = (int)(R->len_flag[r] & 0xffff);
             *tot_bases += (uint64_t)L;
@@ -250,7 +253,7 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
     int oi = 0;   /* observations were appended in the same read/op order we now replay */
     for (int d = 0; d < 2; ++d)
         for (int64_t r = rng[d][0]; r < rng[d][1]; ++r) {
-            if (ref_end_of(R, r) <= first) continue;
+            if (ref_end_of(R, r) <= first || is_unmapped(R, r)) continue;
             int n_ops_indel = 0;
             for (uint32_t c = R->cigar_off[r]; c < R->cigar_off[r + 1]; ++c) { int op = R->cigar[c] & 15; n_ops_indel += (op == 1 || op == 2); }
             const int my_obs0 = oi; oi += n_ops_indel;

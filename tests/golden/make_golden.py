@@ -259,6 +259,31 @@ def run_genome(case, vcf_records, more_cases=()):
             "files": files}
 
 
+def unmap_mates(case, every):
+    """Every `every`-th pair of each dataset: one mate (alternating) becomes an unmapped read placed at its mate's
+    position, as aligners write it: flag 0x4, no CIGAR, RNAME / POS of the mate, stored sequence as read; the mapped mate
+    gets 0x8 and loses 0x2.  File order: by position, the unmapped read behind mapped reads of the same position."""
+    reads = case["reads"]
+    by_name = {}
+    for k, r in enumerate(reads):
+        by_name.setdefault((r["dataset"], r["name"]), []).append(k)
+    n = 0
+    for key in sorted(by_name):
+        idx = by_name[key]
+        if len(idx) != 2:
+            continue
+        n += 1
+        if n % every:
+            continue
+        keep, unm = (idx[0], idx[1]) if (n // every) % 2 else (idx[1], idx[0])
+        rk, ru = reads[keep], reads[unm]
+        ru["pos"], ru["cigar"] = rk["pos"], "*"
+        ru["flag"] = (ru["flag"] & (0x40 | 0x80)) | 0x1 | 0x4 | (0x20 if rk["flag"] & 0x10 else 0)
+        rk["flag"] = (rk["flag"] & ~0x2 & ~0x20) | 0x8
+    order = sorted(range(len(reads)), key=lambda k: (reads[k]["dataset"], reads[k]["pos"], 1 if reads[k]["flag"] & 4 else 0))
+    case["reads"] = [reads[k] for k in order]
+
+
 def genome_cases():
     out = []
     specs = [
@@ -275,10 +300,17 @@ def genome_cases():
                   indel_rate=8e-4, clip_frac=0.1), "orphans-three-windows", 7),
         # no somatic variant at all: the whole contig is one inter-window region
         (25, dict(contig_len=5000, n_pairs=(40, 35), read_len=70, somatic_positions=[], snp_rate=4e-3, indel_rate=1e-3), "no-variants", None),
+        # placed-unmapped mates (flag 0x4 at the mate's position, mate flagged 0x8), inside windows and between them:
+        # pileups never see them (htslib), regions collect them for their end (pileup_io.pyx:93-96, 298), and what is
+        # left is paired after the last section (pair_unmapped_mates, short_read_tumor_normal_anonymizer.py:561-600)
+        (41, dict(contig_len=9000, n_pairs=(120, 110), read_len=80, somatic_positions=[2500, 6000], snp_rate=3e-3, indel_rate=8e-4,
+                  clip_frac=0.1), "unmapped-mates", -6),
     ]
     for seed, kw, label, drop in specs:
         case = synth.make_case(seed, name=f"genome-{label}", **kw)
-        if drop:                                                  # deterministic orphans: every `drop`-th read disappears
+        if drop and drop < 0:
+            unmap_mates(case, -drop)
+        elif drop:                                                # deterministic orphans: every `drop`-th read disappears
             case["reads"] = [r for k, r in enumerate(case["reads"]) if k % drop != 3]
         vcf = []
         for w in case["windows"]:

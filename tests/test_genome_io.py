@@ -267,11 +267,11 @@ def test_large_files_are_read_one_contig_at_a_time(tmp_path, monkeypatch):
         assert GF.pack_tumor_normal(f, f, "b").batch.n_reads == 80
 
 
-@pytest.mark.parametrize("flag", [0x800, 0x4])
-def test_entry_point_refuses_supplementary_and_unmapped_records(tmp_path, flag):
-    """The reference's supplementary / unmapped-mate bookkeeping (anonymizer_methods.py:98-149, SR.py:561-600) is not
-    implemented: the entry point says so instead of treating such records as ordinary alignments (no engine is needed
-    to find out - the check runs on the packed flags before any device work)."""
+@pytest.mark.parametrize("flag", [0x800])
+def test_entry_point_refuses_supplementary_records(tmp_path, flag):
+    """The reference's supplementary-alignment bookkeeping (anonymizer_methods.py:98-149) is not implemented: the entry
+    point says so instead of treating such records as ordinary alignments (no engine is needed to find out - the check
+    runs on the packed flags before any device work)."""
     from genomeanonymizer_b200 import genome_files as GF
     from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import anonymize_genome
     case = dict(GENOME[0]["case"])
@@ -288,4 +288,4 @@ def test_entry_point_refuses_supplementary_and_unmapped_records(tmp_path, flag):
     # secondary records are first-wins in the reference too: not refused by the flag check
     from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import _refuse_unsupported_records
     import numpy as np
-    _refuse_unsupported_records(np.array([(0x100 | 0x1 | 0x40) << 16 | 150], np.uint32), "c")
+    _refuse_unsupported_records(np.array([(0x100 | 0x1 | 0x40) << 16 | 150, (0x4 | 0x1 | 0x80) << 16 | 150], np.uint32), "c")

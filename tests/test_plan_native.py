@@ -57,11 +57,38 @@ RANDOM = [
 ]
 
 
+def unmap_some(reads, every):
+    """Every `every`-th pair: one mate becomes an unmapped read placed at its mate's position - behind it in the file,
+    or (every other time) in front of it, which can make it the first read a region fetches."""
+    by_name = {}
+    for k, r in enumerate(reads):
+        by_name.setdefault((r["dataset"], r["name"]), []).append(k)
+    front = set()
+    n = 0
+    for key in sorted(by_name):
+        idx = by_name[key]
+        if len(idx) != 2:
+            continue
+        n += 1
+        if n % every:
+            continue
+        keep, unm = (idx[0], idx[1]) if (n // every) % 2 else (idx[1], idx[0])
+        reads[unm] = dict(reads[unm], pos=reads[keep]["pos"], cigar="*", flag=(reads[unm]["flag"] & 0xC0) | 0x5)
+        reads[keep] = dict(reads[keep], flag=(reads[keep]["flag"] & ~0x22) | 0x8)
+        if (n // every) % 3 == 0:
+            front.add(unm)
+    order = sorted(range(len(reads)), key=lambda k: (reads[k]["dataset"], reads[k]["pos"], 0 if k in front else (2 if reads[k]["flag"] & 4 else 1)))
+    return [reads[k] for k in order]
+
+
 @pytest.mark.parametrize("kw", RANDOM, ids=[f"seed{k['seed']}" for k in RANDOM])
 @pytest.mark.parametrize("drop", [0, 5, 2])
-def test_native_plan_equals_python_plan_on_random_samples(kw, drop):
+@pytest.mark.parametrize("unmap", [0, 4])
+def test_native_plan_equals_python_plan_on_random_samples(kw, drop, unmap):
     case = synth.make_case(**kw)
-    reads = case["reads"]
+    reads = [dict(r) for r in case["reads"]]
+    if unmap:
+        reads = unmap_some(reads, unmap)
     if drop:                                                         # orphans: every `drop`-th read disappears
         reads = [r for k, r in enumerate(reads) if k % drop != 1]
     if kw["seed"] == 705:                                            # a duplicated alignment of the same (name, mate)

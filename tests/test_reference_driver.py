@@ -103,3 +103,42 @@ def test_reference_driver_with_the_plugin_on_two_contigs(ref_modules, tmp_path):
     files = run_reference_driver(ref_modules, two["cases"], two["vcf"], B200GermlineAnonymizer(engine=OracleEngine()), str(tmp_path))
     for name, text in two["expected"]["files"].items():
         assert files[name] == text, name
+
+
+@pytest.mark.parametrize("seed,unmap", [(811, 3), (812, 5), (813, 2)])
+def test_plan_matches_the_reference_on_samples_with_unmapped_mates(ref_modules, seed, unmap, tmp_path):
+    """Live golden: seeded samples whose placed-unmapped mates sit behind OR in front of their mapped partner (an unmapped
+    read can then be the first read a region fetches and seeds an island, pileup_io.pyx:150-158) run through the
+    reference's own anonymize_genome with its own CompleteGermlineAnonymizer; driver.plan_sample + oracle must write the
+    same files."""
+    from genomeanonymizer_b200 import batch as B
+    from genomeanonymizer_b200 import driver as D
+    from genomeanonymizer_b200 import synth
+    from oracle import fastq as OF
+    from oracle import oracle
+    from src.GenomeAnonymizer.anonymizer_methods import CompleteGermlineAnonymizer
+    from tests import helpers as H
+    from tests.test_genome_files import assemble, with_ends
+    from tests.test_plan_native import unmap_some
+    case = synth.make_case(seed, name=f"live-{seed}", contig_len=9000, n_pairs=(90, 80), read_len=80, somatic_positions=[2400, 6100],
+                           snp_rate=3e-3, indel_rate=8e-4, clip_frac=0.1)
+    case["reads"] = unmap_some([dict(r) for r in case["reads"]], unmap)
+    vcf = [["c", w["keep"]["pos"] + 1, w["keep"]["pos"] + 1, 1, case["reference"][w["keep"]["pos"]].upper(), w["keep"]["allele"], "SNV"] for w in case["windows"]]
+    gold = run_reference_driver(ref_modules, [case], vcf, CompleteGermlineAnonymizer(), str(tmp_path))
+    reads = with_ends(H.ordered_reads(case))
+    plan = D.plan_sample(reads, case["windows"], len(case["reference"]))
+    batch = B.pack_reads(reads)
+    res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"])
+    assert st == 0
+
+    def text_of(i, version):
+        if version >= 0 and (version, i) in res.records:
+            seq, qual = H.final_read(batch, res, i, session=version)
+        else:
+            seq, qual = B.decode_bases(batch.sequence_codes(i)), [int(x) for x in batch.qualities(i)]
+        return OF.render(reads[i]["name"], reads[i]["flag"], seq, qual)
+    mine = assemble(plan, reads, text_of)
+    assert sum(1 for r in reads if r["flag"] & 4) > 5
+    for name, text in mine.items():
+        assert text == (gold.get(name) or ""), name
+    assert D.statistics_text(case["contig"], plan, res.sess_counts) == gold["N.bam.statistics.txt"]
