@@ -83,6 +83,33 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const Sessi
     }
 }
 
+// ------------------------------------------------------------------ staged records of a lane group
+// A group of 8 lanes stages its record (SNV-masked below) and, for an indel-masked read, the quality record in shared
+// memory.  Data starts at word 4 (16-byte aligned for 128-bit stores); word 3 is a zero pad so that source index -1 .. -8
+// is addressable, and four words behind the data are addressable too: every piece of an output word is fetched without
+// a branch and cut to size by masks.
+constexpr int kStageW = 4 + kGroupStage + 4;
+constexpr int kQStageW = 4 + 2 * kGroupStage + 4;
+
+__device__ __forceinline__ uint32_t low_nibbles_bf(int cnt) {            // the low min(max(cnt, 0), 8) nibbles
+    return __funnelshift_rc(0xffffffffu, 0u, (uint32_t)(32 - 4 * min(max(cnt, 0), 8)));
+}
+__device__ __forceinline__ uint32_t low_bytes_bf(int cnt) {              // the low min(max(cnt, 0), 4) bytes
+    return __funnelshift_rc(0xffffffffu, 0u, (uint32_t)(32 - 8 * min(max(cnt, 0), 4)));
+}
+// 8 staged bases from source index sidx (any value: clamped to the addressable range, the caller masks what lies outside the read)
+__device__ __forceinline__ uint32_t stage_at(const uint32_t* sg, int sidx) {
+    const int s = min(max(sidx, -8), 8 * kGroupStage + 8);
+    const int wi = (s >> 3) + 4;
+    return __funnelshift_r(sg[wi], sg[wi + 1], (uint32_t)(s & 7) * 4u);
+}
+// 4 staged quality bytes from BAM byte bidx (same rules)
+__device__ __forceinline__ uint32_t qual_at(const uint32_t* qs, int bidx) {
+    const int s = min(max(bidx, -4), 8 * kGroupStage + 4);
+    const int wi = (s >> 2) + 4;
+    return __funnelshift_r(qs[wi], qs[wi + 1], (uint32_t)(s & 3) * 8u);
+}
+
 // ------------------------------------------------------------------ two edits as runs
 // After its (at most two) edits a read is a handful of RUNS: pieces of the SNV-masked source and, per masked DEL, the
 // deleted reference bases that come back (anonymizer_methods.py:188-195; all DELs, then all INSs, each at its original,
@@ -133,125 +160,67 @@ __device__ __noinline__ void build_runs(const Ed2& E, int L, RunList* R) {
     R->n = n;
 }
 
-// The body of an indel-masked record with two edits from the staged (SNV-masked) words and quality bytes.
-__device__ __noinline__ void emit_runs_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r, int L, bool reverse,
-                                             const uint8_t* qrec, const uint32_t* stage, const uint32_t* qstage, RunList* R, uint64_t seq16, uint64_t qual16,
-                                             int new_len, int glane) {
-    const int nqw = (L + 3) >> 2;
-    if (act && !qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); act = false; }
-    uint32_t part = 0;
-    if (act) {
-        for (int q = glane; q < nqw; q += kGroup) {
-            uint32_t v = qstage[q];
-            if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
-            part += __vsadu4(v, 0u);
-        }
-        if (glane == 0) {
-            build_runs(E, L, R);
-            for (int q = 0; q < E.n_del; ++q)
-                if ((int64_t)E.pos[q] + E.len[q] > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
-        }
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
-    __syncwarp();                                                         // the run list is visible to the group
-    if (!act) return;
-    // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (anonymizer_methods.py:193)
-    uint32_t mean0 = 0u, mean1 = 0u;
-    {
-        uint32_t sum = part, n = (uint32_t)L;
-        if (E.n_del >= 1) { mean0 = n ? sum / n : 0u; sum += mean0 * (uint32_t)E.len[0]; n += (uint32_t)E.len[0]; }
-        if (E.n_del >= 2) mean1 = n ? sum / n : 0u;
-    }
-    auto low_nibbles = [](int cnt) -> uint32_t { return cnt >= 8 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((8 - cnt) * 4))); };
-    auto low_bytes = [](int cnt) -> uint32_t { return cnt >= 4 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((4 - cnt) * 8))); };
-    const int n_runs = R->n;
-    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
-    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-    for (int w = glane; w < units * 4; w += kGroup) {
-        const int j0 = w << 3;
-        uint32_t v = 0u;
-        if (j0 < new_len) {
-#pragma unroll 1
-            for (int k = 0; k < n_runs; ++k) {
-                const int f = R->f[k], lo = max(f, j0), hi = min(f + R->len[k], j0 + 8);
-                if (lo >= hi) continue;
-                const uint32_t m = low_nibbles(hi - j0) & ~low_nibbles(lo - j0);
-                const int at = R->a[k] + (j0 - f);                       // >= -7
-                uint32_t val;
-                if (R->kind[k]) val = ref_word(B.ref4, (int64_t)at);
-                else if (at < 0) val = stage[0] << ((-at) * 4);
-                else val = __funnelshift_r(stage[at >> 3], stage[(at >> 3) + 1], (uint32_t)(at & 7) * 4u);
-                v |= val & m;
-            }
-        }
-        oseq[w] = v;
-    }
-    // qualities in printed (= BAM) order; the runs index the forward-orientation array (anonymizer_methods.py:95, 187,
-    // 195: quirk Q2), so for a reverse read a run [f, f + len) is printed at [new_len - f - len, new_len - f) and its BAM
-    // bytes ascend with the printed index
-    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
-    for (int w = glane; w < units * 8; w += kGroup) {
-        const int p0 = w << 2;
-        uint32_t v = 0u;
-        if (p0 < new_len) {
-#pragma unroll 1
-            for (int k = 0; k < n_runs; ++k) {
-                const int ln = R->len[k], f = reverse ? new_len - R->f[k] - ln : R->f[k];
-                const int lo = max(f, p0), hi = min(f + ln, p0 + 4);
-                if (lo >= hi) continue;
-                const uint32_t m = low_bytes(hi - p0) & ~low_bytes(lo - p0);
-                uint32_t val;
-                const int kind = R->kind[k];
-                if (kind) val = (kind == 1 ? mean0 : mean1) * 0x01010101u;
-                else {
-                    const int at = p0 + (reverse ? L - new_len - R->a[k] + R->f[k] : R->a[k] - R->f[k]);   // BAM byte of printed byte p0 (>= -3)
-                    val = at < 0 ? qstage[0] << ((-at) * 8) : __funnelshift_r(qstage[at >> 2], qstage[(at >> 2) + 1], (uint32_t)(at & 3) * 8u);
-                }
-                v |= val & m;
-            }
-        }
-        oq[w] = v;
-    }
-}
+// What a group knows about its record (read from the warp's descriptor table, see emit_special_kernel).
+struct SpecRec {
+    uint32_t src_unit, c0, c1, germ_n, qunit;
+    int pos, L, s, new_len, col_begin;
+    int64_t r;
+    uint64_t seq16, qual16;
+    bool reverse;
+};
 
-// Reads with other CIGARs, the common shapes: SNV-only (kind 2, E.ne == 0) and one germline indel (kind 3,
-// E.ne == 1), reads of at most 8 * (kGroupStage - 1) bases.  One group of 8 lanes per record; every lane of the warp
-// calls this (act = false for groups without such a record).
-//   1. the record is staged in shared memory, coalesced;
-//   2. SNV masking (anonymizer_methods.py:170-176): every germline allele of the session is carried through the
-//      CIGAR to its query offset and, when the read shows it, replaced by the reference base;
-//   3. the one edit is applied while copying: DEL -> the deleted reference bases come back with quality
-//      floor(mean(qualities)), INS -> the inserted bases and qualities go (anonymizer_methods.py:178-203); edits
-//      index the forward-orientation quality array, printed order = BAM order (anonymizer_methods.py:95, 213).
-__device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals* totals, const ResultView& O, bool act, const Ed2& E, int64_t r,
-                                                   int pos, int L, uint32_t src_unit, uint32_t c0, uint32_t c1, bool reverse, int col_begin, const GermList& germ, const uint8_t* qrec,
-                                                   uint32_t* stage, uint32_t* qstage, uint64_t seq16, uint64_t qual16, int new_len, int glane) {
-    const int nw = (L + 7) >> 3, nqw = (L + 3) >> 2;
+// Steps shared by the staged kinds: (1) the record - and for an indel-masked read its quality record - goes to shared
+// memory with 128-bit loads; (2) SNV masking (anonymizer_methods.py:170-176): every germline allele of the session is
+// carried through the CIGAR to its query offset and, when the read shows it, replaced by the reference base.  Returns
+// the sum of the read's qualities (kQual) to every lane of the group.
+template <bool kQual>
+__device__ __forceinline__ uint32_t stage_and_mask(const BatchView& B, const EmitScratch2& E, bool act, const SpecRec& R, uint32_t* sg, uint32_t* qs, int glane) {
+    uint32_t part = 0u;
     if (act) {
-        const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * src_unit);
-        for (int w = glane; w < nw; w += kGroup) stage[w] = __ldg(rec + w) & tail_mask(L, w);
-        if (glane == 0) stage[nw] = 0u;                                // the funnel shift may touch one word past the end
-        if (E.ne >= 1 && qrec) {                                       // the quality record too: it is summed and shifted below
-            const uint32_t* qg = reinterpret_cast<const uint32_t*>(qrec);
-            for (int q = glane; q < nqw; q += kGroup) qstage[q] = __ldg(qg + q);
-            if (glane == 0) qstage[nqw] = 0u;
+        const int L = R.L;
+        const uint4* rec = reinterpret_cast<const uint4*>(B.seq4 + 16ull * R.src_unit);
+        uint4* sg4 = reinterpret_cast<uint4*>(sg) + 1;
+        const int nu = (L + 31) >> 5;                                    // at most kGroupStage / 4 = 8 units
+        if (glane < nu) {
+            uint4 v = ldg128(rec + glane);
+            v.x &= tail_mask(L, 4 * glane); v.y &= tail_mask(L, 4 * glane + 1); v.z &= tail_mask(L, 4 * glane + 2); v.w &= tail_mask(L, 4 * glane + 3);
+            sg4[glane] = v;
+        }
+        if (glane == 7) { sg[3] = 0u; sg[4 + 4 * nu] = 0u; }            // pad in front; the word behind the last unit
+        if (kQual) {
+            const uint4* qrec = reinterpret_cast<const uint4*>(B.qual + 32ull * R.qunit);
+            uint4* qs4 = reinterpret_cast<uint4*>(qs) + 1;
+            const int nq = (L + 15) >> 4;                                // at most 16
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int u = glane + 8 * h;
+                if (u < nq) {
+                    uint4 v = ldg128(qrec + u);
+                    v.x &= low_bytes_bf(L - 16 * u); v.y &= low_bytes_bf(L - 16 * u - 4); v.z &= low_bytes_bf(L - 16 * u - 8); v.w &= low_bytes_bf(L - 16 * u - 12);
+                    part += __vsadu4(v.x, 0u) + __vsadu4(v.y, 0u) + __vsadu4(v.z, 0u) + __vsadu4(v.w, 0u);
+                    qs4[u] = v;
+                }
+            }
+            if (glane == 7) { qs[3] = 0u; qs[4 + 4 * nq] = 0u; }
         }
     }
+    if (kQual) { part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4); }
     __syncwarp();
     if (act) {
-        for (uint32_t a = glane; a < germ.n; a += kGroup) {
-            const uint32_t key = __ldg(germ.e + a), code = key & 15u;
-            const int at = col_begin + (int)(key >> 4);
-            int rc = pos, q = 0;
-            for (uint32_t ci = c0; ci < c1; ++ci) {
+        const uint32_t* ge = E.germ + (size_t)R.s * kGermStride + 4;
+        for (uint32_t a = glane; a < R.germ_n; a += kGroup) {
+            const uint32_t key = __ldg(ge + a), code = key & 15u;
+            const int at = R.col_begin + (int)(key >> 4);
+            int rc = R.pos, q = 0;
+            for (uint32_t ci = R.c0; ci < R.c1; ++ci) {
+                if (at < rc) break;                                    // the column lies before what is left of the read
                 const uint32_t cw = __ldg(B.cigar + ci), op = cw & 15u;
                 const int ln = (int)(cw >> 4);
-                if (at < rc) break;                                    // the column lies before what is left of the read
                 if (op == 0u || op == 7u || op == 8u) {
                     if (at < rc + ln) {
                         const int qq = q + (at - rc);
-                        if (qq < L && ((stage[qq >> 3] >> ((qq & 7) * 4)) & 15u) == code)
-                            atomicXor(&stage[qq >> 3], (code ^ ref_code(B.ref4, at)) << ((qq & 7) * 4));
+                        if (qq < R.L && ((sg[4 + (qq >> 3)] >> ((qq & 7) * 4)) & 15u) == code)
+                            atomicXor(&sg[4 + (qq >> 3)], (code ^ ref_code(B.ref4, at)) << ((qq & 7) * 4));
                         break;
                     }
                     q += ln; rc += ln;
@@ -261,188 +230,270 @@ __device__ __forceinline__ void emit_special_group(const BatchView& B, ga_totals
         }
     }
     __syncwarp();
+    return part;
+}
+
+// kind 2: another CIGAR, SNV-only - the staged, masked record is the output.
+__device__ __forceinline__ void emit_snv_only_quad(const BatchView& B, const ResultView& O, const EmitScratch2& E, bool act, const SpecRec& R, uint32_t* sg, int glane) {
+    stage_and_mask<false>(B, E, act, R, sg, nullptr, glane);
+    if (!act) return;
+    const int nu = (R.L + 31) >> 5;
+    int units = (R.new_len + 31) >> 5; if (units < 1) units = 1;
+    uint4* out = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * R.seq16);
+    const uint4* sg4 = reinterpret_cast<const uint4*>(sg) + 1;
+    for (int u = glane; u < units; u += kGroup) out[u] = u < nu ? sg4[u] : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// kind 3, one germline indel: DEL -> the deleted reference bases come back with quality floor(mean(qualities)), INS ->
+// the inserted bases and qualities go (anonymizer_methods.py:178-203); edits index the forward-orientation quality
+// array, printed order = BAM order (anonymizer_methods.py:95, 213).  The final array is three pieces: [0, p) = source as
+// is, [p, ins_end) = re-inserted reference bases (DEL only), [ins_end, new_len) = source shifted by `shift`; every output
+// word is merged from the pieces with nibble / byte masks, without a branch (the lanes of a warp sit in different pieces).
+__device__ __forceinline__ void emit_one_edit_quad(const BatchView& B, const ResultView& O, const EmitScratch2& E, bool act, const SpecRec& R, const Ed2& Ed,
+                                                   uint32_t* sg, uint32_t* qs, int glane) {
+    const uint32_t sum = stage_and_mask<true>(B, E, act, R, sg, qs, glane);
+    if (!act) return;
+    const int L = R.L, new_len = R.new_len;
+    const bool is_del = Ed.n_del == 1;
+    const int p = Ed.p[0], len = Ed.len[0], shift = is_del ? -len : Ed.e[0] - Ed.p[0];       // source = final + shift behind the edit
+    const int ins_end = is_del ? p + len : p;                                                 // [p, ins_end): re-inserted elements
+    const uint32_t mean4 = (is_del && L ? sum / (uint32_t)L : 0u) * 0x01010101u;              // anonymizer_methods.py:193
+    if (is_del && glane == 0 && (int64_t)Ed.pos[0] + len > B.ref_len) raise_error(O.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)R.r);
     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
-    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-    const bool indel = act && E.ne == 1;                              // two edits: the caller continues with emit_runs_group
-    if (act && E.ne == 0) for (int w = glane; w < units * 4; w += kGroup) oseq[w] = w < nw ? stage[w] : 0u;
-    // ---- one edit
-    const bool is_del = E.n_del == 1;
-    const int p = E.p[0], len = E.len[0], shift = is_del ? -len : E.e[0] - E.p[0];      // source = final + shift behind the edit
-    const int ins_end = is_del ? p + len : p;                                             // [p, ins_end): re-inserted elements
-    bool ok = indel;
-    if (indel && !qrec) { if (glane == 0) raise_error(totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); ok = false; }
-    uint32_t mean = 0u;
-    if (__any_sync(0xffffffffu, ok && is_del)) {                      // quality of re-inserted bases (anonymizer_methods.py:193)
-        uint32_t part = 0;
-        if (ok && is_del) {
-            for (int q = glane; q < nqw; q += kGroup) {
-                uint32_t v = qstage[q];
-                if (4 * q + 4 > L) v &= 0xffffffffu >> ((4 * q + 4 - L) * 8);
-                part += __vsadu4(v, 0u);
-            }
-        }
-        part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
-        mean = L ? part / (uint32_t)L : 0u;
-        if (ok && is_del && glane == 0 && (int64_t)E.pos[0] + len > B.ref_len) raise_error(totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)r);
-    }
-    if (!ok) return;
-    // The final array is three pieces: [0, p) = source as is, [p, ins_end) = re-inserted reference bases (DEL only),
-    // [ins_end, new_len) = source shifted by `shift`.  Every output word is merged from the (at most three) pieces it
-    // overlaps with nibble / byte masks - no per-element loop.
-    auto low_nibbles = [](int cnt) -> uint32_t { return cnt >= 8 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((8 - cnt) * 4))); };
-    auto low_bytes = [](int cnt) -> uint32_t { return cnt >= 4 ? 0xffffffffu : (cnt <= 0 ? 0u : (0xffffffffu >> ((4 - cnt) * 8))); };
-    auto stage_at = [&](int sidx) -> uint32_t {                        // 8 staged bases from source index sidx (>= -7; nibbles outside the read are masked by the caller)
-        if (sidx < 0) return stage[0] << ((-sidx) * 4);
-        return __funnelshift_r(stage[sidx >> 3], stage[(sidx >> 3) + 1], (uint32_t)(sidx & 7) * 4u);
-    };
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * R.seq16);
     for (int w = glane; w < units * 4; w += kGroup) {
         const int j0 = w << 3;
-        uint32_t v = 0u;
-        if (j0 + 8 <= p) v = stage_at(j0);                               // wholly in front of the edit (the usual word)
-        else if (j0 >= ins_end && j0 + 8 <= new_len) v = stage_at(j0 + shift);   // wholly behind it
-        else if (j0 < new_len) {
-            const uint32_t mA = low_nibbles(p - j0), mAB = low_nibbles(ins_end - j0);
-            if (mA) v = stage_at(j0) & mA;
-            if (mAB & ~mA) v |= ref_word(B.ref4, (int64_t)E.pos[0] + (j0 - p)) & (mAB & ~mA);
-            if (~mAB) v |= stage_at(j0 + shift) & ~mAB;
-            v &= low_nibbles(new_len - j0);
-        }
-        oseq[w] = v;
+        const uint32_t mA = low_nibbles_bf(p - j0), mAB = low_nibbles_bf(ins_end - j0);
+        uint32_t v = (stage_at(sg, j0) & mA) | (stage_at(sg, j0 + shift) & ~mAB);
+        const uint32_t mR = mAB & ~mA;
+        if (mR) v |= ref_word(B.ref4, (int64_t)Ed.pos[0] + (j0 - p)) & mR;
+        oseq[w] = v & low_nibbles_bf(new_len - j0);
     }
-    // qualities in printed (= BAM) order.  The edit indexes the forward-orientation array (anonymizer_methods.py:95,
-    // 187, 195: quirk Q2), so for a reverse read the pieces come in the opposite order: printed [0, b1) = BAM bytes as
-    // they are, [b1, b2) = the mean, [b2, new_len) = BAM bytes shifted by d3.
-    const int b1 = reverse ? new_len - ins_end : p, b2 = reverse ? new_len - p : ins_end, d3 = reverse ? L - new_len : shift;
-    auto qual_at = [&](int bidx) -> uint32_t {                         // 4 staged quality bytes from BAM byte bidx (>= -3)
-        if (bidx < 0) return qstage[0] << ((-bidx) * 8);
-        return __funnelshift_r(qstage[bidx >> 2], qstage[(bidx >> 2) + 1], (uint32_t)(bidx & 3) * 8u);
-    };
-    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * qual16);
+    // qualities in printed (= BAM) order.  The edit indexes the forward-orientation array (quirk Q2), so for a reverse
+    // read the pieces come in the opposite order: printed [0, b1) = BAM bytes as they are, [b1, b2) = the mean,
+    // [b2, new_len) = BAM bytes shifted by d3.
+    const int b1 = R.reverse ? new_len - ins_end : p, b2 = R.reverse ? new_len - p : ins_end, d3 = R.reverse ? L - new_len : shift;
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * R.qual16);
     for (int w = glane; w < units * 8; w += kGroup) {
         const int p0 = w << 2;
-        uint32_t v = 0u;
-        if (p0 + 4 <= b1) v = qual_at(p0);                               // wholly in front of the edit (the usual word)
-        else if (p0 >= b2 && p0 + 4 <= new_len) v = qual_at(p0 + d3);    // wholly behind it
-        else if (p0 < new_len) {
-            const uint32_t m1 = low_bytes(b1 - p0), m12 = low_bytes(b2 - p0);
-            if (m1) v = qual_at(p0) & m1;
-            if (m12 & ~m1) v |= (mean * 0x01010101u) & (m12 & ~m1);
-            if (~m12) v |= qual_at(p0 + d3) & ~m12;
-            v &= low_bytes(new_len - p0);
-        }
-        oq[w] = v;
+        const uint32_t m1 = low_bytes_bf(b1 - p0), m12 = low_bytes_bf(b2 - p0);
+        const uint32_t v = (qual_at(qs, p0) & m1) | (mean4 & m12 & ~m1) | (qual_at(qs, p0 + d3) & ~m12);
+        oq[w] = v & low_bytes_bf(new_len - p0);
     }
 }
 
-// Records of kind >= 2 (reads with other CIGARs, reads with many hits), taken densely from the list the resolve
-// kernels packed: four records per warp step, one group of 8 lanes each.
-__global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
-    __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
-    __shared__ uint32_t qstage[kThreads / kGroup][2 * kGroupStage];      // quality bytes of the same reads (4 per word)
-    __shared__ RunList runs[kThreads / kGroup];                           // two-edit records: the runs the output is merged from
-    const int tid = threadIdx.x, group = tid / kGroup, glane = tid % kGroup;
-    const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
-    const uint32_t groups_total = gridDim.x * (kThreads / kGroup);
-    for (uint32_t jb = blockIdx.x * (kThreads / kGroup) + (tid >> 5) * 4; jb < n_x; jb += groups_total) {   // warp-uniform
-        const uint32_t j = jb + ((tid & 31) >> 3);
-        const bool have = j < n_x;
-        // ---- the record's 64-byte descriptor: one round trip, one 16-byte part per lane of the group
-        uint4 part = make_uint4(0u, 0u, 0u, 0u);
-        if (have && glane < 4) part = E.sdesc[4ull * j + glane];
-        const int gbase = (tid & 31) & ~7;
-        uint4 d0, d1, d2, d3;
-        d0.x = __shfl_sync(0xffffffffu, part.x, gbase);     d0.y = __shfl_sync(0xffffffffu, part.y, gbase);
-        d0.z = __shfl_sync(0xffffffffu, part.z, gbase);     d0.w = __shfl_sync(0xffffffffu, part.w, gbase);
-        d1.x = __shfl_sync(0xffffffffu, part.x, gbase + 1); d1.y = __shfl_sync(0xffffffffu, part.y, gbase + 1);
-        d1.z = __shfl_sync(0xffffffffu, part.z, gbase + 1); d1.w = __shfl_sync(0xffffffffu, part.w, gbase + 1);
-        d2.x = __shfl_sync(0xffffffffu, part.x, gbase + 2); d2.y = __shfl_sync(0xffffffffu, part.y, gbase + 2);
-        d2.z = __shfl_sync(0xffffffffu, part.z, gbase + 2);
-        d3.x = __shfl_sync(0xffffffffu, part.x, gbase + 3); d3.y = __shfl_sync(0xffffffffu, part.y, gbase + 3);
-        const uint32_t r_kind = (d0.z >> 16) & 15u;                      // 0: the slot of a session that did not fit
-        const uint32_t r_src = d0.x; const int r_pos = (int)d0.y; const int s = (int)d0.w;
-        const int64_t r = (int64_t)d1.x; const int new_len = (int)d1.y; const uint64_t seq16 = d1.z, qual16 = d1.w;
-        const uint32_t c0 = d2.x, c1 = d2.y; const int col_begin = (int)d2.z;
-        const bool reverse = ((d0.z >> 20) & 1u) != 0u;
-        GermList germ; germ.e = E.germ + (size_t)s * kGermStride + 4; germ.n = 0u;
-        if (r_kind) germ.n = __ldg(E.germ + (size_t)s * kGermStride);
-        {
-                if (r_kind == 4u) {
-                    const int L = new_len;
-                    const uint4* rec = reinterpret_cast<const uint4*>(B.seq4 + 16ull * r_src);
-                    uint4* out = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * seq16);
-                    const int units = (L + 31) >> 5;
-                    for (int u = glane; u < units; u += kGroup) {
-                        const uint4 vv = ldg128(rec + u);
-                        const int64_t ni = (int64_t)r_pos + 32 * u + 8;
-                        const uint32_t* rp = B.ref4 + (ni >> 3);
-                        const uint32_t sh = (uint32_t)(ni & 7) * 4u;
-                        const uint32_t r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3), r4 = __ldg(rp + 4);
-                        uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
-                        const uint32_t f[4] = {__funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh), __funnelshift_r(r2, r3, sh), __funnelshift_r(r3, r4, sh)};
+// kind 3, two germline indels: the body from the staged (SNV-masked) words and quality bytes through the run list.
+__device__ __forceinline__ void emit_two_edit_quad(const BatchView& B, const ResultView& O, const EmitScratch2& E, bool act, const SpecRec& R, const Ed2& Ed,
+                                                   uint32_t* sg, uint32_t* qs, RunList* RL, int glane) {
+    const uint32_t sum0 = stage_and_mask<true>(B, E, act, R, sg, qs, glane);
+    if (act && glane == 0) {
+        build_runs(Ed, R.L, RL);
+        for (int q = 0; q < Ed.n_del; ++q)
+            if ((int64_t)Ed.pos[q] + Ed.len[q] > B.ref_len) raise_error(O.totals, GA_ERR_LENGTH_MISMATCH, (uint32_t)R.r);
+    }
+    __syncwarp();                                                         // the run list is visible to the group
+    if (!act) return;
+    const int L = R.L, new_len = R.new_len;
+    // quality of re-inserted bases: floor(mean(current qualities)), recomputed after each DEL (anonymizer_methods.py:193)
+    uint32_t mean0 = 0u, mean1 = 0u;
+    {
+        uint32_t sum = sum0, n = (uint32_t)L;
+        if (Ed.n_del >= 1) { mean0 = n ? sum / n : 0u; sum += mean0 * (uint32_t)Ed.len[0]; n += (uint32_t)Ed.len[0]; }
+        if (Ed.n_del >= 2) mean1 = n ? sum / n : 0u;
+    }
+    const int n_runs = RL->n;
+    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
+    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * R.seq16);
+    for (int w = glane; w < units * 4; w += kGroup) {
+        const int j0 = w << 3;
+        uint32_t v = 0u;
+#pragma unroll 1
+        for (int k = 0; k < n_runs; ++k) {
+            const int f = RL->f[k];
+            const uint32_t m = low_nibbles_bf(f + RL->len[k] - j0) & ~low_nibbles_bf(f - j0);
+            if (!m) continue;
+            const int at = RL->a[k] + (j0 - f);                          // >= -7 where the mask is set
+            v |= (RL->kind[k] ? ref_word(B.ref4, (int64_t)max(at, -8)) : stage_at(sg, at)) & m;
+        }
+        oseq[w] = v & low_nibbles_bf(new_len - j0);
+    }
+    // qualities in printed (= BAM) order; the runs index the forward-orientation array (anonymizer_methods.py:95, 187,
+    // 195: quirk Q2), so for a reverse read a run [f, f + len) is printed at [new_len - f - len, new_len - f) and its BAM
+    // bytes ascend with the printed index
+    uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * R.qual16);
+    for (int w = glane; w < units * 8; w += kGroup) {
+        const int p0 = w << 2;
+        uint32_t v = 0u;
+#pragma unroll 1
+        for (int k = 0; k < n_runs; ++k) {
+            const int ln = RL->len[k], f = R.reverse ? new_len - RL->f[k] - ln : RL->f[k];
+            const uint32_t m = low_bytes_bf(f + ln - p0) & ~low_bytes_bf(f - p0);
+            if (!m) continue;
+            const int kind = RL->kind[k];
+            uint32_t val;
+            if (kind) val = (kind == 1 ? mean0 : mean1) * 0x01010101u;
+            else val = qual_at(qs, p0 + (R.reverse ? L - new_len - RL->a[k] + RL->f[k] : RL->a[k] - RL->f[k]));   // BAM byte of printed byte p0
+            v |= val & m;
+        }
+        oq[w] = v & low_bytes_bf(new_len - p0);
+    }
+}
+
+// kind 4: a clean read with more than two germline hits - copy, looking every mismatch up in the session's germline list.
+__device__ __forceinline__ void emit_many_hits_quad(const BatchView& B, const ResultView& O, const GermList& germ, const SpecRec& R, int glane) {
+    const int L = R.new_len;
+    const uint4* rec = reinterpret_cast<const uint4*>(B.seq4 + 16ull * R.src_unit);
+    uint4* out = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * R.seq16);
+    const int units = (L + 31) >> 5;
+    for (int u = glane; u < units; u += kGroup) {
+        const uint4 vv = ldg128(rec + u);
+        const int64_t ni = (int64_t)R.pos + 32 * u + 8;
+        const uint32_t* rp = B.ref4 + (ni >> 3);
+        const uint32_t sh = (uint32_t)(ni & 7) * 4u;
+        const uint32_t r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3), r4 = __ldg(rp + 4);
+        uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+        const uint32_t f[4] = {__funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh), __funnelshift_r(r2, r3, sh), __funnelshift_r(r3, r4, sh)};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int wi = 4 * u + q;
-                            const uint32_t tm = tail_mask(L, wi);
-                            uint32_t v = w[q] & tm;
-                            uint32_t x = (v ^ f[q]) & tm;
-                            while (x) {
-                                const int nb = (__ffs(x) - 1) >> 2;
-                                x &= ~(0xfu << (nb * 4));
-                                const uint32_t b = (v >> (nb * 4)) & 15u;
-                                if (b != 15u && germ(r_pos + 8 * wi + nb - col_begin, b)) v = (v & ~(0xfu << (nb * 4))) | (((f[q] >> (nb * 4)) & 15u) << (nb * 4));
-                            }
-                            w[q] = v;
-                        }
-                        out[u] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int q = 0; q < 4; ++q) {
+            const int wi = 4 * u + q;
+            const uint32_t tm = tail_mask(L, wi);
+            uint32_t v = w[q] & tm;
+            uint32_t x = (v ^ f[q]) & tm;
+            while (x) {
+                const int nb = (__ffs(x) - 1) >> 2;
+                x &= ~(0xfu << (nb * 4));
+                const uint32_t b = (v >> (nb * 4)) & 15u;
+                if (b != 15u && germ(R.pos + 8 * wi + nb - R.col_begin, b)) v = (v & ~(0xfu << (nb * 4))) | (((f[q] >> (nb * 4)) & 15u) << (nb * 4));
+            }
+            w[q] = v;
+        }
+        out[u] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// Records of kind >= 2 (reads with other CIGARs, reads with many hits), taken densely from the list the resolve kernels
+// packed.  A warp takes 32 records at a time, LANE = RECORD: descriptor, edit description (EditAux, parked by the
+// resolve kernel in the record's quality slot), the germline-list length and the place of the quality record arrive
+// with coalesced loads - one chain of dependent round trips per 32 records instead of one per record - and go to the
+// warp's table in shared memory.  The records are then regrouped BY KIND and taken four at a time, 8 lanes each, so
+// that a warp step runs one code path: SNV-only / one edit / two edits / many hits / (reads beyond 248 bases: the
+// general forms of ga_record_ops.cuh).
+constexpr int kSpecFields = 23;
+enum { SF_SO, SF_POS, SF_LZ, SF_S, SF_R, SF_NEWLEN, SF_SEQ16, SF_QUAL16, SF_C0, SF_C1, SF_COLB, SF_QLO, SF_QHI, SF_AUX0, SF_QUNIT = SF_AUX0 + 8, SF_GERMN };
+static_assert(SF_GERMN + 1 == kSpecFields, "field count");
+constexpr int kSpecClasses = 5;         // 0 SNV-only, 1 one edit, 2 two edits, 3 many hits, 4 long reads
+struct SpecWarp { uint32_t f[kSpecFields][32]; uint8_t order[kSpecClasses][32]; };
+
+__global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
+    extern __shared__ __align__(16) uint8_t emit_smem[];
+    SpecWarp* tabs = reinterpret_cast<SpecWarp*>(emit_smem);
+    uint32_t* stage_all = reinterpret_cast<uint32_t*>(tabs + kThreads / 32);
+    uint32_t* qstage_all = stage_all + (kThreads / kGroup) * kStageW;
+    RunList* runs_all = reinterpret_cast<RunList*>(qstage_all + (kThreads / kGroup) * kQStageW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, group = tid / kGroup, glane = tid % kGroup, gw = lane >> 3;
+    SpecWarp& T = tabs[warp];
+    uint32_t* sg = stage_all + group * kStageW;
+    uint32_t* qs = qstage_all + group * kQStageW;
+    RunList* RL = runs_all + group;
+    const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
+    const uint32_t stride = gridDim.x * (kThreads / 32) * 32;
+    for (uint32_t jb = (blockIdx.x * (kThreads / 32) + warp) * 32; jb < n_x; jb += stride) {      // warp-uniform
+        // ---- lane = record
+        const uint32_t j = jb + lane;
+        int cls = -1;
+        if (j < n_x) {
+            const uint4* dp = E.sdesc + 4ull * j;
+            const uint4 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
+            const uint32_t kind = (d0.z >> 16) & 15u;                    // 0: the slot of a session that did not fit
+            const int L = (int)(d0.z & 0xffffu);
+            T.f[SF_SO][lane] = d0.x; T.f[SF_POS][lane] = d0.y; T.f[SF_LZ][lane] = d0.z; T.f[SF_S][lane] = d0.w;
+            T.f[SF_R][lane] = d1.x; T.f[SF_NEWLEN][lane] = d1.y; T.f[SF_SEQ16][lane] = d1.z; T.f[SF_QUAL16][lane] = d1.w;
+            T.f[SF_C0][lane] = d2.x; T.f[SF_C1][lane] = d2.y; T.f[SF_COLB][lane] = d2.z; T.f[SF_QLO][lane] = d3.x; T.f[SF_QHI][lane] = d3.y;
+            const bool is_long = ((L + 7) >> 3) > kGroupStage - 1;
+            if (kind >= 2u && kind <= 4u) T.f[SF_GERMN][lane] = __ldg(E.germ + (size_t)d0.w * kGermStride);
+            if (kind == 2u) cls = is_long ? 4 : 0;
+            else if (kind == 4u) cls = 3;
+            else if (kind == 3u) {
+                const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * d1.w);
+                const uint4 x0 = ap[0], x1 = ap[1];                      // EditAux written by the resolve kernel
+                T.f[SF_AUX0 + 0][lane] = x0.x; T.f[SF_AUX0 + 1][lane] = x0.y; T.f[SF_AUX0 + 2][lane] = x0.z; T.f[SF_AUX0 + 3][lane] = x0.w;
+                T.f[SF_AUX0 + 4][lane] = x1.x; T.f[SF_AUX0 + 5][lane] = x1.y; T.f[SF_AUX0 + 6][lane] = x1.z; T.f[SF_AUX0 + 7][lane] = x1.w;
+                // the read's quality record: dense upload, or the slot the resolve kernel predicted in the sparse index
+                // (verified; a caller may list more reads than those with I/D ops), or a search of the slice
+                uint32_t qunit = 0xffffffffu;
+                if (B.qual && !B.qual_reads) qunit = d0.x;
+                else if (B.qual) {
+                    const int64_t qi = (int64_t)x1.w;
+                    if (qi < B.n_qual && __ldg(B.qual_reads + qi) == (int32_t)d1.x) qunit = __ldg(B.qual_off16 + qi);
+                    else {
+                        const uint8_t* qp = qual_record_in(B, (int64_t)d1.x, (int64_t)d3.x, (int64_t)d3.y);
+                        if (qp) qunit = (uint32_t)((qp - B.qual) >> 5);
                     }
                 }
-                const bool indel = r_kind == 3u;
+                T.f[SF_QUNIT][lane] = qunit;
+                if (qunit == 0xffffffffu) raise_error(O.totals, GA_ERR_BAD_ARGUMENT, d1.x);   // no quality record for an indel-masked read
+                else cls = is_long ? 4 : ((x1.z & 0xffu) == 1u ? 1 : 2);
+            }
+        }
+        unsigned long long n_cls = 0ull;                                  // records per kind, 8 bits each
+#pragma unroll
+        for (int k = 0; k < kSpecClasses; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
+            n_cls |= (unsigned long long)__popc(m) << (8 * k);
+            if (cls == k) T.order[k][__popc(m & ((1u << lane) - 1u))] = (uint8_t)lane;
+        }
+        __syncwarp();
+        // ---- four records of one kind per step, 8 lanes each
+#pragma unroll 1
+        for (int k = 0; k < kSpecClasses; ++k) {
+            const uint32_t n_k = (uint32_t)(n_cls >> (8 * k)) & 0xffu;
+#pragma unroll 1
+            for (uint32_t q0 = 0; q0 < n_k; q0 += 4) {
+                const bool act = q0 + gw < n_k;
+                const int t = act ? (int)T.order[k][q0 + gw] : 0;
+                SpecRec R;
+                const uint32_t lz = T.f[SF_LZ][t];
+                R.src_unit = T.f[SF_SO][t]; R.pos = (int)T.f[SF_POS][t]; R.L = (int)(lz & 0xffffu); R.reverse = ((lz >> 20) & 1u) != 0u; R.s = (int)T.f[SF_S][t];
+                R.r = (int64_t)T.f[SF_R][t]; R.new_len = (int)T.f[SF_NEWLEN][t]; R.seq16 = T.f[SF_SEQ16][t]; R.qual16 = T.f[SF_QUAL16][t];
+                R.c0 = T.f[SF_C0][t]; R.c1 = T.f[SF_C1][t]; R.col_begin = (int)T.f[SF_COLB][t]; R.germ_n = T.f[SF_GERMN][t]; R.qunit = T.f[SF_QUNIT][t];
                 Ed2 Ed; Ed.ne = 0; Ed.n_del = 0;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) { Ed.irp[q] = 0; Ed.len[q] = 0; Ed.pos[q] = 0; Ed.mean[q] = 0u; Ed.p[q] = 0; Ed.e[q] = 0; }
-                int64_t q_lo = 0, q_hi = 0;
-                const uint8_t* qrec = nullptr;
-                const int L = (int)(d0.z & 0xffffu);
-                if (indel) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
-                    const uint4 x0 = ap[0], x1 = ap[1];              // EditAux written by the resolve kernel
-                    Ed.irp[0] = (int)x0.x; Ed.pos[0] = (int)x0.y; Ed.len[0] = (int)(x0.z & 0x7fffffffu);
-                    Ed.irp[1] = (int)x0.w; Ed.pos[1] = (int)x1.x; Ed.len[1] = (int)(x1.y & 0x7fffffffu);
-                    Ed.ne = (int)(x1.z & 0xffu); Ed.n_del = (int)((x1.z >> 8) & 0xffu);
-                    clamp_edits2(Ed, L);
-                    q_lo = (int64_t)d3.x; q_hi = (int64_t)d3.y;
-                    // the read's quality record: dense upload, or the slot the resolve kernel predicted in the sparse
-                    // index (verified; a caller may list more reads than those with I/D ops), or a search of the slice
-                    if (B.qual && !B.qual_reads) qrec = B.qual + 32ull * r_src;
-                    else if (B.qual) {
-                        const int64_t qi = (int64_t)x1.w;
-                        if (qi < B.n_qual && __ldg(B.qual_reads + qi) == (int32_t)r) qrec = B.qual + 32ull * __ldg(B.qual_off16 + qi);
-                        else qrec = qual_record_in(B, r, q_lo, q_hi);
+                if (k == 1 || k == 2 || k == 4) {
+                    const uint32_t kind = (lz >> 16) & 15u;
+                    if (act && kind == 3u) {
+                        Ed.irp[0] = (int)T.f[SF_AUX0][t]; Ed.pos[0] = (int)T.f[SF_AUX0 + 1][t]; Ed.len[0] = (int)(T.f[SF_AUX0 + 2][t] & 0x7fffffffu);
+                        Ed.irp[1] = (int)T.f[SF_AUX0 + 3][t]; Ed.pos[1] = (int)T.f[SF_AUX0 + 4][t]; Ed.len[1] = (int)(T.f[SF_AUX0 + 5][t] & 0x7fffffffu);
+                        const uint32_t nn = T.f[SF_AUX0 + 6][t];
+                        Ed.ne = (int)(nn & 0xffu); Ed.n_del = (int)((nn >> 8) & 0xffu);
+                        clamp_edits2(Ed, R.L);
                     }
                 }
-                __syncwarp();                                         // every lane of the group has read the aux before it is overwritten
-                // the common shapes take the staged path; two edits or very long reads take the general one
-                const bool fast = (r_kind == 2u || (indel && (Ed.ne == 1 || Ed.ne == 2))) && ((L + 7) >> 3) <= kGroupStage - 1;
-                if (__any_sync(0xffffffffu, fast))
-                    emit_special_group(B, O.totals, O, fast, Ed, r, r_pos, L, r_src, c0, c1, reverse, col_begin, germ, qrec, stage[group], qstage[group], seq16, qual16, new_len, glane);
-                const bool two = fast && indel && Ed.ne == 2;
-                if (__any_sync(0xffffffffu, two)) {
-                    __syncwarp();                                     // staged words are SNV-masked
-                    emit_runs_group(B, O.totals, O, two, Ed, r, L, reverse, qrec, stage[group], qstage[group], &runs[group], seq16, qual16, new_len, glane);
+                if (k == 0) emit_snv_only_quad(B, O, E, act, R, sg, glane);
+                else if (k == 1) emit_one_edit_quad(B, O, E, act, R, Ed, sg, qs, glane);
+                else if (k == 2) emit_two_edit_quad(B, O, E, act, R, Ed, sg, qs, RL, glane);
+                else {
+                    GermList germ; germ.e = E.germ + (size_t)R.s * kGermStride + 4; germ.n = act ? R.germ_n : 0u;
+                    if (k == 3) { if (act) emit_many_hits_quad(B, O, germ, R, glane); }
+                    else {                                                // reads beyond the staging area: the general forms
+                        const bool indel = act && ((lz >> 16) & 15u) == 3u;
+                        if (act && !indel) {
+                            int units = (R.new_len + 31) >> 5; if (units < 1) units = 1;
+                            uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * R.seq16);
+                            masked_words_g(B, R.r, R.pos, R.new_len, R.c0, R.c1, R.col_begin, units * 4, glane, kGroup, germ, [&](int wd, uint32_t v) { oseq[wd] = v; });
+                        }
+                        if (__any_sync(0xffffffffu, indel))
+                            emit_indel_group_t(B, O.totals, O, indel, Ed, R.r, R.col_begin, (int64_t)T.f[SF_QLO][t], (int64_t)T.f[SF_QHI][t], sg, R.seq16, R.qual16, R.new_len, glane, germ);
+                    }
                 }
-                if (r_kind == 2u && !fast) {
-                    int units = (new_len + 31) >> 5; if (units < 1) units = 1;
-                    uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * seq16);
-                    masked_words_g(B, r, r_pos, new_len, c0, c1, col_begin, units * 4, glane, kGroup, germ, [&](int wd, uint32_t v) { oseq[wd] = v; });
-                }
-                const bool slow = indel && !fast;
-                if (__any_sync(0xffffffffu, slow)) {
-                    __syncwarp();
-                    emit_indel_group_t(B, O.totals, O, slow, Ed, r, col_begin, q_lo, q_hi, stage[group], seq16, qual16, new_len, glane, germ);
-                }
+                __syncwarp();                                             // the staging areas are reused by the next step
             }
         }
+        __syncwarp();                                                     // the table is rewritten by the next 32 records
     }
+}
+constexpr size_t kEmitSpecialSmem = sizeof(SpecWarp) * (kThreads / 32) + sizeof(uint32_t) * (kThreads / kGroup) * (kStageW + kQStageW) + sizeof(RunList) * (kThreads / kGroup);
+
 // Records of kind 5: indel-masked reads with more than two germline indels (rare; the one-CTA resolve kernel lists
 // them and stores their edit lists in E.many).  One warp per record, general element-wise emission.
 __global__ void __launch_bounds__(kThreads) emit_many_kernel(BatchView B, ResultView O, EmitScratch2 E) {

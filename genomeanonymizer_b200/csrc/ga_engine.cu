@@ -131,8 +131,8 @@ __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* ti
 // ------------------------------------------------------------------ engine
 
 // the two instantiations of the one-warp resolve kernel (ga_resolve_kernel.cuh)
-static const auto kResolveLean = ga::resolve_warp_kernel<ga::kReadsL, ga::kModL, ga::kObsL, ga::kEntL, ga::kLeanWarps, 11, false>;
-static const auto kResolveMid = ga::resolve_warp_kernel<ga::kReadsL, ga::kModM, ga::kObsM, ga::kEntM, ga::kMidWarps, 6, true>;
+static const auto kResolveLean = ga::resolve_warp_kernel<ga::kReadsL, ga::kModL, ga::kObsL, ga::kEntL, ga::kLeanWarps, 11, false, 1>;
+static const auto kResolveMid = ga::resolve_warp_kernel<ga::kReadsL, ga::kModM, ga::kObsM, ga::kEntM, ga::kMidTeam, 6, true, ga::kMidTeam>;
 
 int ga_fail(ga_engine* e, int code, const char* what, cudaError_t ce) {
     if (e) {
@@ -190,12 +190,12 @@ int ga_engine_create(int device, ga_engine** out) {
     cudaFuncSetAttribute(ga::session_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemLayout));
     cudaFuncSetAttribute(kResolveLean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemL) * ga::kLeanWarps));
     cudaFuncSetAttribute(kResolveLean, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(kResolveMid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::SmemM) * ga::kMidWarps));
+    cudaFuncSetAttribute(kResolveMid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ga::SmemM));
     cudaFuncSetAttribute(kResolveMid, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // persistent kernels: exactly one wave of resident CTAs (a partial second wave would wait for the first to drain)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_scan, ga::scan_kernel, ga::kScanThreads, sizeof(ga::WarpSmem) * (ga::kScanThreads / 32));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_lean, kResolveLean, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_mid, kResolveMid, 32 * ga::kMidWarps, sizeof(ga::SmemM) * ga::kMidWarps);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_mid, kResolveMid, 32 * ga::kMidTeam, sizeof(ga::SmemM));
     if (e->occ_mid < 1) e->occ_mid = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_res, ga::resolve_kernel, ga::kResThreads, sizeof(ga::SmemR));
     if (const char* v = getenv("GA_OCC_SCAN")) e->occ_scan = std::min(e->occ_scan, std::max(1, atoi(v)));   // tuning knob: CTAs per SM of the scan kernel
@@ -447,8 +447,8 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     kResolveLean<<<lean_ctas, 32 * ga::kLeanWarps, sizeof(ga::SmemL) * ga::kLeanWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, nullptr, nullptr, E.ticket_lean,
                                                                                            L.d_large_list, d_nlarge, O, X, E);
     // sessions beyond the lean capacities (indel-dense ones): the same kernel with larger tables, then the one-CTA kernel
-    const int mid_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_mid, (S->n_sessions + ga::kMidWarps - 1) / ga::kMidWarps);
-    kResolveMid<<<mid_ctas, 32 * ga::kMidWarps, sizeof(ga::SmemM) * ga::kMidWarps, st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge,
+    const int mid_ctas = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_mid, (int64_t)S->n_sessions);
+    kResolveMid<<<mid_ctas, 32 * ga::kMidTeam, sizeof(ga::SmemM), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large_list, d_nlarge,
                                                                                         reinterpret_cast<unsigned int*>(L.d_small + 21), L.d_large2_list, d_nlarge2, O, X, E);
     const int grid_res = (int)std::min<int64_t>((int64_t)e->n_sm * e->occ_res, S->n_sessions);
     ga::resolve_kernel<<<grid_res, ga::kResThreads, sizeof(ga::SmemR), st>>>(B, V, L.d_descs, L.d_big_list, d_nbig, L.d_large2_list, d_nlarge2, O, X, E);
@@ -465,7 +465,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     GA_CUDA(cudaEventRecord(L.ev_join, L.side));
     // stage 3: record bodies
     ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
-    ga::emit_special_kernel<<<e->n_sm * 4, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
+    ga::emit_special_kernel<<<e->n_sm * 4, ga::kThreads, ga::kEmitSpecialSmem, st>>>(B, L.d_descs, O, E);
     GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
     GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));

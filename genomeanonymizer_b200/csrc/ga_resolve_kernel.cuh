@@ -513,12 +513,11 @@ constexpr int kEntL = 512;               // candidate entries per session
 // "Mid" instantiation of the same kernel: the sessions of an indel-dense workload (hundreds of indel observations and
 // modified reads per session) stay with the one-warp formulation instead of the barrier-bound one-CTA kernel; it walks
 // the list the lean instantiation handed over and lists what it cannot hold for the one-CTA kernel.
-constexpr int kMidWarps = 1;
 constexpr int kModM = 512;
 constexpr int kObsM = 512;
 constexpr int kEntM = 768;
 
-template <int kReadsL, int kModL, int kObsL, int kEntL>
+template <int kReadsL, int kModL, int kObsL, int kEntL, int kChunks>
 struct SmemLT {
     uint32_t tab[kCols2 / 4];            // one byte per column: bits 0-3 tumor saw A,C,G,T, bits 4-7 normal
     uint32_t modbits[kReadsL / 32], indelbits[kReadsL / 32], genbits[kReadsL / 32], woff[kReadsL / 32];
@@ -536,11 +535,15 @@ struct SmemLT {
         uint32_t ent[kEntL];             // candidate entries (tumor item, then normal item); bit 31: germline hit
         uint32_t rnew[kModL];            // ... which is before the new lengths are known: new length | kind << 24
     };
-    uint32_t ngerm, pad[3];
+    // what the warps of a team tell each other (a one-warp team keeps most of it in registers)
+    unsigned long long base[3];
+    uint32_t ngerm, flag, cnt_del, cnt_ins, tot_seq, tot_qual, n_q, n_spec, n_mod, ticket, spec_base, pad[3];
+    uint32_t chunk_s[kChunks], chunk_q[kChunks], chunk_p[kChunks];   // per chunk of 32 modified reads: sequence units, quality units, special records
     static_assert(sizeof(uint16_t) * kModL <= 2 * sizeof(uint32_t) * kObsL && kModL <= kEntL, "aliases fit");
 };
-using SmemL = SmemLT<kReadsL, kModL, kObsL, kEntL>;
-using SmemM = SmemLT<kReadsL, kModM, kObsM, kEntM>;
+constexpr int kMidTeam = 4;              // warps that share one session in the mid instantiation
+using SmemL = SmemLT<kReadsL, kModL, kObsL, kEntL, 4>;
+using SmemM = SmemLT<kReadsL, kModM, kObsM, kEntM, kModM / 32>;
 static_assert(sizeof(SmemL) % 16 == 0 && sizeof(SmemM) % 16 == 0, "per-warp slices stay 16-byte aligned");
 
 // Alleles longer than the 16-base signature (rare): the bases behind it are compared from the records.
@@ -565,35 +568,55 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
 }
 
 // kFromList: the sessions are the entries of in_list (what the lean instantiation handed over) instead of 0 .. n_sessions - 1.
-template <int kReadsL, int kModL, int kObsL, int kEntL, int kWarps, int kMinBlocks, bool kFromList>
+// kTeam: warps that work on one session together.  1 = every warp of the CTA has its own session and its own tables
+// (no block barrier); kTeam = kWarps = the CTA is one team: loops are strided over the team, the phases are separated by
+// block barriers and sums travel through shared memory - for sessions with hundreds of observations and modified reads,
+// whose tables leave room for few sessions per SM: a team keeps four times as many warps (and memory requests) in
+// flight per table.
+template <int kReadsL, int kModL, int kObsL, int kEntL, int kWarps, int kMinBlocks, bool kFromList, int kTeam>
 __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                                             int32_t* __restrict__ big_list, int32_t* __restrict__ n_big,
                                                                             const int32_t* __restrict__ in_list, const int32_t* __restrict__ n_in, unsigned int* __restrict__ ticket_p,
                                                                             int32_t* __restrict__ large_list, int32_t* __restrict__ n_large,
                                                                             ResultView O, ScanScratch X, EmitScratch2 E) {
-    using SmemL = SmemLT<kReadsL, kModL, kObsL, kEntL>;
+    static_assert(kTeam == 1 || kTeam == kWarps, "a team is one warp or the whole CTA");
+    constexpr bool kSolo = kTeam == 1;
+    constexpr int TS = 32 * kTeam;                                     // threads of a team
+    using SmemT = SmemLT<kReadsL, kModL, kObsL, kEntL, kSolo ? 4 : kModL / 32>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SmemL* sm = reinterpret_cast<SmemL*>(smem_raw) + warp;
+    const int tw = kSolo ? 0 : warp;                                   // warp within the team
+    const int tl = kSolo ? lane : (int)threadIdx.x;                    // lane within the team
+    SmemT* sm = reinterpret_cast<SmemT*>(smem_raw) + (kSolo ? warp : 0);
+    auto tsync = [] { if constexpr (kSolo) __syncwarp(); else __syncthreads(); };
     SessCtx c;
     c.B = B;
     c.totals = O.totals;
     memset(&c.T, 0, sizeof c.T);
-    // statistics counters are summed per warp and added to ga_totals once, at the end: every session already sends
+    // statistics counters are summed per team and added to ga_totals once, at the end: every session already sends
     // three atomics to that one cache line for its output slots, and same-address atomics serialise in L2
     unsigned long long acc_reads = 0ull, acc_bases = 0ull;
     uint32_t acc_snv = 0u, acc_del = 0u, acc_ins = 0u, acc_q = 0u;
 
-#pragma unroll 1
-    // sessions differ in cost: a warp takes the next one from a ticket counter (the ticket after that travels while the
-    // session is processed), so that no warp is left with a long tail of expensive sessions
+    // sessions differ in cost: a team takes the next one from a ticket counter (the ticket after that travels while the
+    // session is processed), so that no team is left with a long tail of expensive sessions
     const uint32_t n_work = kFromList ? (uint32_t)*n_in : (uint32_t)S.n_sessions;
-    uint32_t ticket = lane == 0 ? atomicAdd(ticket_p, 1u) : 0u, next_ticket = 0u;
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    for (; ticket < n_work; ticket = __shfl_sync(0xffffffffu, next_ticket, 0)) {
+    uint32_t next_ticket = 0u;
+    auto take = [&](uint32_t mine) -> uint32_t {                       // the team's thread 0 holds the ticket
+        if constexpr (kSolo) return __shfl_sync(0xffffffffu, mine, 0);
+        else {
+            __syncthreads();                                          // everybody is done with the previous session's tables
+            if (tl == 0) sm->ticket = mine;
+            __syncthreads();
+            return sm->ticket;
+        }
+    };
+    uint32_t ticket = take(tl == 0 ? atomicAdd(ticket_p, 1u) : 0u);
+#pragma unroll 1
+    for (; ticket < n_work; ticket = take(next_ticket)) {
         const int s = kFromList ? in_list[ticket] : (int)ticket;
-        next_ticket = lane == 0 ? atomicAdd(ticket_p, 1u) : 0u;
-        // ---- round trip 1: descriptor, scan counts, variant_to_keep
+        next_ticket = tl == 0 ? atomicAdd(ticket_p, 1u) : 0u;
+        // ---- round trip 1: descriptor, scan counts, variant_to_keep (every warp of a team for itself: same lines)
         uint32_t w1 = 0u, w2 = 0u;
         if (lane < 20) w1 = __ldg(reinterpret_cast<const uint32_t*>(descs + s) + lane);
         else if (lane < 28) w1 = __ldg(reinterpret_cast<const uint32_t*>(X.cnt + 2 * (size_t)s) + (lane - 20));
@@ -621,13 +644,13 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         const int n_cols = c.d.n_cols;
         const int n_cw = (c.n_range + 31) >> 5;
         if (n_ent0 == kCntOverflow || n_ent1 == kCntOverflow) {       // the scan kernel could not hold the session
-            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 1, 1); }
+            if (tl == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 1, 1); }
             continue;
         }
         const int n_obs = (int)(n_obs0 + n_obs1);
         const uint32_t n_ent = n_ent0 + n_ent1;
         if (c.n_range > kReadsL || n_obs > kObsL) {
-            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+            if (tl == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
         // ---- round trip 2: entries, observations, keep allele; tables zeroed meanwhile
@@ -639,10 +662,10 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         auto ent_at = [&](uint32_t k) -> uint32_t { return ent_staged ? sm->ent[k] : (k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0))); };
         if (ent_staged) {
 #pragma unroll 2
-            for (uint32_t k = lane; k < n_ent; k += 32) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
+            for (uint32_t k = tl; k < n_ent; k += TS) sm->ent[k] = k < n_ent0 ? __ldg(e0 + k) : __ldg(e1 + (k - n_ent0));
         }
 #pragma unroll 1
-        for (int o = lane; o < n_obs; o += 32) {
+        for (int o = tl; o < n_obs; o += TS) {
             const ObsRec* op = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
             const uint4* src = reinterpret_cast<const uint4*>(o < (int)n_obs0 ? op + o : op + kObsHalf + (o - (int)n_obs0));
             const uint4 a = __ldg(src), b = __ldg(src + 1);
@@ -654,10 +677,10 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         {
             uint4* t4 = reinterpret_cast<uint4*>(sm->tab);
 #pragma unroll 1
-            for (int k = lane; k < ((n_cols + 15) >> 4); k += 32) t4[k] = make_uint4(0u, 0u, 0u, 0u);
+            for (int k = tl; k < ((n_cols + 15) >> 4); k += TS) t4[k] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
-            for (int k = lane; k < n_cw; k += 32) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
-            if (lane == 0) sm->ngerm = 0u;
+            for (int k = tl; k < n_cw; k += TS) { sm->modbits[k] = 0u; sm->indelbits[k] = 0u; sm->genbits[k] = 0u; }
+            if (tl == 0) { sm->ngerm = 0u; sm->flag = 0u; sm->cnt_del = 0u; sm->cnt_ins = 0u; sm->tot_seq = 0u; sm->tot_qual = 0u; sm->n_q = 0u; sm->n_spec = 0u; }
         }
         uint32_t keep_key = 0xffffffffu;                              // variant_to_keep as an SNV entry key
         if (c.keep_type == GA_VT_SNV && c.keep_end == c.keep_pos && c.keep_len == 1 && c.keep_alen == 1) {
@@ -668,25 +691,27 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 if (code) keep_key = ((uint32_t)kc << 4) | code;
             }
         }
-        __syncwarp();
+        tsync();
         // ---- pass 1: allele table
         bool bad = false;
 #pragma unroll 1
-        for (uint32_t k = lane; k < n_ent; k += 32) {
+        for (uint32_t k = tl; k < n_ent; k += TS) {
             const uint32_t e = ent_at(k), b = e & 15u;
             if (b == 0u || (b & (b - 1u))) { bad = true; continue; }   // IUPAC read base: the fallback kernel keeps all 16 codes
             const uint32_t col = (e >> 4) & 0xfffu;
             atomicOr(&sm->tab[col >> 2], 1u << ((__ffs(b) - 1) + (k >= n_ent0 ? 4 : 0) + 8 * (int)(col & 3u)));
         }
-        if (__any_sync(0xffffffffu, bad)) {
-            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 2, 1); }
+        if constexpr (kSolo) bad = __any_sync(0xffffffffu, bad);
+        else { if (bad) sm->flag = 1u; __syncthreads(); bad = sm->flag != 0u; }
+        if (bad) {
+            if (tl == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 2, 1); }
             continue;
         }
-        __syncwarp();
+        if constexpr (kSolo) __syncwarp();
         // ---- pass 2: germline = seen in tumor AND normal, minus variant_to_keep; mark the reads that carry one.
         // Bit 31 of an entry remembers that it is a germline hit (pass 3 needs only those).
 #pragma unroll 1
-        for (uint32_t k = lane; k < n_ent; k += 32) {
+        for (uint32_t k = tl; k < n_ent; k += TS) {
             const uint32_t e = ent_at(k);
             const uint32_t col = (e >> 4) & 0xfffu;
             const uint32_t byte = (sm->tab[col >> 2] >> (8 * (col & 3u))) & 0xffu;
@@ -697,10 +722,9 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 if (ent_staged) sm->ent[k] = e | 0x80000000u;
             }
         }
-        uint32_t cnt_snv = 0;
-        {   // distinct germline SNV alleles: the per-session counter and the emission kernel's list
+        {   // distinct germline SNV alleles: the per-session counter (= the list's length) and the emission kernel's list
 #pragma unroll 1
-            for (int kw = lane; kw < ((n_cols + 3) >> 2); kw += 32) {
+            for (int kw = tl; kw < ((n_cols + 3) >> 2); kw += TS) {
                 const uint32_t w = sm->tab[kw];
                 uint32_t g = w & (w >> 4) & 0x0f0f0f0fu;
 #pragma unroll 1
@@ -708,12 +732,10 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                     const int bit = __ffs(g) - 1; g &= g - 1;
                     const uint32_t key = ((uint32_t)(4 * kw + (bit >> 3)) << 4) | (1u << (bit & 7));
                     if (key == keep_key) continue;
-                    ++cnt_snv;
                     const uint32_t slot = atomicAdd(&sm->ngerm, 1u);
                     if (slot < (uint32_t)kGermCap) E.germ[(size_t)s * kGermStride + 4 + slot] = key;
                 }
             }
-            cnt_snv = warp_sum(cnt_snv);
         }
         // indels: exact key equality (variants.py:83-96).  Every observation looks for the FIRST observation equal to it
         // (the representative of its key: equality is an equivalence, so that is the smallest member of the class) - one
@@ -726,14 +748,14 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         static_assert((kModL & (kModL - 1)) == 0, "bucket count is a power of two");
         if (n_obs > 0) {
 #pragma unroll 1
-            for (int k = lane; k < kModL; k += 32) kt[k] = 0xffffffffu;
-            __syncwarp();
+            for (int k = tl; k < kModL; k += TS) kt[k] = 0xffffffffu;
+            tsync();
 #pragma unroll 1
-            for (int o = lane; o < n_obs; o += 32) atomicMin(&kt[sm->o_key[o] & (kModL - 1)], (uint32_t)o);
-            __syncwarp();
+            for (int o = tl; o < n_obs; o += TS) atomicMin(&kt[sm->o_key[o] & (kModL - 1)], (uint32_t)o);
+            tsync();
         }
 #pragma unroll 1
-        for (int o = lane; o < n_obs; o += 32) {
+        for (int o = tl; o < n_obs; o += TS) {
             const int o_col = sm->o_col[o];
             const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o], o_s0 = sm->o_s0[o], o_s1 = sm->o_s1[o], o_key = sm->o_key[o];
             int rep = o;
@@ -754,9 +776,9 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             atomicOr(&sm->o_cls[o], (uint32_t)rep);                   // the entry was zeroed; others may be adding their dataset bits to it
             atomicOr(&sm->o_cls[rep], (o_meta & kMetaDs) ? 0x20000u : 0x10000u);
         }
-        __syncwarp();
+        tsync();
 #pragma unroll 1
-        for (int o = lane; o < n_obs; o += 32) {
+        for (int o = tl; o < n_obs; o += TS) {
             const uint32_t cls = sm->o_cls[o];
             const int rep = (int)(cls & 0xffffu);
             bool germ = (sm->o_cls[rep] >> 16) == 3u;
@@ -788,12 +810,16 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 if (rep == o) { if (o_meta & kMetaIns) ++cnt_ins; else ++cnt_del; }
             }
         }
-        if (n_obs > 0) { cnt_del = warp_sum(cnt_del); cnt_ins = warp_sum(cnt_ins); }
-        __syncwarp();
-        const uint32_t ngerm = sm->ngerm;
-        // ---- ordered list of the modified reads (two bitmap words per lane)
-        uint32_t n_mod;
-        {
+        if (n_obs > 0) {
+            cnt_del = warp_sum(cnt_del); cnt_ins = warp_sum(cnt_ins);
+            if constexpr (!kSolo) { if (lane == 0) { if (cnt_del) atomicAdd(&sm->cnt_del, cnt_del); if (cnt_ins) atomicAdd(&sm->cnt_ins, cnt_ins); } }
+        }
+        tsync();
+        if constexpr (!kSolo) { cnt_del = sm->cnt_del; cnt_ins = sm->cnt_ins; }
+        const uint32_t ngerm = sm->ngerm, cnt_snv = ngerm;
+        // ---- ordered list of the modified reads (two bitmap words per lane of the team's first warp)
+        uint32_t n_mod = 0u;
+        if (tw == 0) {
             const uint32_t b0 = lane < n_cw ? sm->modbits[lane] : 0u, b1 = lane + 32 < n_cw ? sm->modbits[lane + 32] : 0u;
             uint32_t t0, t1;
             uint32_t off0 = warp_excl_scan(__popc(b0), lane, &t0);
@@ -809,24 +835,26 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
 #pragma unroll 1
                 while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off1++] = (uint16_t)((lane + 32) * 32 + k); }
             }
+            if constexpr (!kSolo) { if (lane == 0) sm->n_mod = n_mod; }
         }
+        if constexpr (!kSolo) { __syncthreads(); n_mod = sm->n_mod; }
         if (n_mod > (uint32_t)kModL) {
-            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+            if (tl == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
         if (ngerm > (uint32_t)kGermCap) {
-            if (lane == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 3, 1); }
+            if (tl == 0) { big_list[atomicAdd(n_big, 1)] = s; atomicAdd(n_big + 4 + 3, 1); }
             continue;
         }
         {
             uint32_t* pc4 = reinterpret_cast<uint32_t*>(sm->mpc);
 #pragma unroll 1
-            for (int k = lane; k < (int)((n_mod + 3) >> 2); k += 32) pc4[k] = 0u;
-            if (n_obs > 0) for (int k = lane; k < (int)n_mod; k += 32) sm->mhead[k] = -1;
+            for (int k = tl; k < (int)((n_mod + 3) >> 2); k += TS) pc4[k] = 0u;
+            if (n_obs > 0) for (int k = tl; k < (int)n_mod; k += TS) sm->mhead[k] = -1;
         }
-        __syncwarp();
+        tsync();
 #pragma unroll 1
-        for (int o = lane; o < n_obs; o += 32) {                      // hang every germline observation on its modified read
+        for (int o = tl; o < n_obs; o += TS) {                      // hang every germline observation on its modified read
             if (!(sm->o_meta[o] & kMetaGerm)) continue;
             const uint32_t i = sm->o_ra[o] & 0xffffu;
             const uint32_t k = sm->woff[i >> 5] + __popc(sm->modbits[i >> 5] & ((1u << (i & 31)) - 1u));
@@ -834,7 +862,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         }
         // ---- pass 3: the germline hits of every clean modified read
 #pragma unroll 1
-        for (uint32_t k = lane; k < n_ent; k += 32) {
+        for (uint32_t k = tl; k < n_ent; k += TS) {
             const uint32_t e = ent_at(k);
             if (ent_staged) { if ((e & (0x80000000u | kEntGen)) != 0x80000000u) continue; }
             else {                                                    // streamed: the germline test of pass 2 again
@@ -848,66 +876,106 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             const uint32_t have = (atomicAdd(cw, 1u << (8 * (m & 3u))) >> (8 * (m & 3u))) & 0xffu;   // at most kGermCap hits per read: no carry
             if (have < 2u) reinterpret_cast<uint16_t*>(sm->mpatch)[2 * m + have] = (uint16_t)((col << 4) | (1u << ((e >> 29) & 3u)));
         }
-        __syncwarp();
-        // ---- round trip 3: new length of every modified read (indel-masked reads need the edit analysis), output sizes
+        tsync();
+        // ---- round trip 3: new length of every modified read (indel-masked reads need the edit analysis), output sizes.
+        // A warp takes chunks of 32 consecutive modified reads; a team notes every chunk's sums for the header loop.
         uint32_t tot_seq = 0, tot_qual = 0, n_q = 0, n_spec = 0;
         bool slow = false;
-#pragma unroll 2
-        for (uint32_t k = lane; k < n_mod; k += 32) {
-            const int i = (int)sm->clist[k];
-            const int64_t r3 = read_of(c, i);
-            const uint32_t so3 = __ldg(B.seq_off16 + r3);             // travels with the length; only used to ask the record
-            const int L0 = (int)(__ldg(B.len_flag + r3) & 0xffffu);
-            // the header loop below reads pos and the record body of this read: ask them into L2 now
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.pos + r3));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.seq4 + 16ull * so3));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.seq4 + 16ull * so3 + 64));
-            int new_len = L0;
-            uint32_t kind;
-            if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
-                Ed2 E2;
-                if (!lean_collect(c, sm, (int)k, L0, E2, &new_len)) slow = true;   // more than two edits: the one-CTA kernel takes the session
-                kind = 3u; ++n_q;
-            } else {
-                kind = ((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2u : (sm->mpc[k] <= 2 ? 1u : 4u);
+#pragma unroll 1
+        for (uint32_t kb = 32u * tw; kb < n_mod; kb += TS) {
+            const uint32_t k = kb + lane;
+            uint32_t units = 0u, qunits = 0u, spec = 0u;
+            if (k < n_mod) {
+                const int i = (int)sm->clist[k];
+                const int64_t r3 = read_of(c, i);
+                const uint32_t so3 = __ldg(B.seq_off16 + r3);         // travels with the length; only used to ask the record
+                const int L0 = (int)(__ldg(B.len_flag + r3) & 0xffffu);
+                // the header loop below reads pos and the record body of this read: ask them into L2 now
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(B.pos + r3));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(B.seq4 + 16ull * so3));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(B.seq4 + 16ull * so3 + 64));
+                int new_len = L0;
+                uint32_t kind;
+                if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
+                    Ed2 E2;
+                    kind = 3u;
+                    if (!lean_collect(c, sm, (int)k, L0, E2, &new_len)) {  // more than two edits: the edit list travels in the side buffer (kind 5)
+                        kind = 5u;
+                        if (!reserve_many(E, c, sm, (int)k, L0, &new_len)) slow = true;   // no room, or more edits than the pipeline takes
+                    }
+                    ++n_q;
+                } else {
+                    kind = ((sm->genbits[i >> 5] >> (i & 31)) & 1u) ? 2u : (sm->mpc[k] <= 2 ? 1u : 4u);
+                }
+                if (kind != 1u) spec = 1u;
+                units = ((uint32_t)new_len + 31u) / 32u; if (units < 1u) units = 1u;
+                if (kind == 3u || kind == 5u) qunits = units;
+                sm->rnew[k] = ((uint32_t)new_len & kLen2) | (kind << 24);
             }
-            if (kind != 1u) ++n_spec;
-            uint32_t units = ((uint32_t)new_len + 31u) / 32u; if (units < 1u) units = 1u;
-            tot_seq += units; if (kind == 3u) tot_qual += units;
-            sm->rnew[k] = ((uint32_t)new_len & kLen2) | (kind << 24);
+            if constexpr (kSolo) { tot_seq += units; tot_qual += qunits; n_spec += spec; }
+            else {
+                const uint32_t cs = warp_sum(units), cq = warp_sum(qunits), cp = warp_sum(spec);
+                if (lane == 0) { sm->chunk_s[kb >> 5] = cs; sm->chunk_q[kb >> 5] = cq; sm->chunk_p[kb >> 5] = cp; }
+                tot_seq += cs; tot_qual += cq; n_spec += cp;
+            }
         }
-        if (__any_sync(0xffffffffu, slow)) {                          // nothing is reserved yet: hand the session over
-            if (lane == 0) large_list[atomicAdd(n_large, 1)] = s;
+        if constexpr (kSolo) {
+            slow = __any_sync(0xffffffffu, slow);
+            tot_seq = warp_sum(tot_seq); tot_qual = warp_sum(tot_qual); n_q = warp_sum(n_q); n_spec = warp_sum(n_spec);
+        } else {
+            n_q = warp_sum(n_q);
+            if (slow) sm->flag = 1u;
+            if (lane == 0) { atomicAdd(&sm->tot_seq, tot_seq); atomicAdd(&sm->tot_qual, tot_qual); atomicAdd(&sm->n_q, n_q); atomicAdd(&sm->n_spec, n_spec); }
+            __syncthreads();
+            slow = sm->flag != 0u; tot_seq = sm->tot_seq; tot_qual = sm->tot_qual; n_q = sm->n_q; n_spec = sm->n_spec;
+        }
+        if (slow) {                                                   // nothing is reserved yet: hand the session over
+            if (tl == 0) large_list[atomicAdd(n_large, 1)] = s;
             continue;
         }
-        tot_seq = warp_sum(tot_seq); tot_qual = warp_sum(tot_qual); n_q = warp_sum(n_q); n_spec = warp_sum(n_spec);
         // ---- output slots: one atomicAdd per cursor per session (north_star job (4): compaction)
         unsigned long long base = 0ull;
         uint32_t spec_base = 0u;
-        if (lane == 0) base = atomicAdd((unsigned long long*)&O.totals->n_modified, (unsigned long long)n_mod);
-        else if (lane == 1) base = atomicAdd((unsigned long long*)&O.totals->seq16_used, (unsigned long long)tot_seq);
-        else if (lane == 2) base = atomicAdd((unsigned long long*)&O.totals->qual16_used, (unsigned long long)tot_qual);
-        else if (lane >= 5 && lane < 9) O.sess_counts[4 * (size_t)s + (lane - 5)] = lane == 5 ? cnt_snv : lane == 6 ? cnt_del : lane == 7 ? cnt_ins : sess_reads;
-        else if (lane == 9) { E.germ[(size_t)s * kGermStride] = ngerm; E.germ[(size_t)s * kGermStride + 1] = (uint32_t)c.d.col_begin; }
-        else if (lane == 11) { if (n_spec) spec_base = atomicAdd(E.n_special, n_spec); }
-        acc_reads += sess_reads; acc_bases += sess_bases; acc_snv += cnt_snv; acc_del += cnt_del; acc_ins += cnt_ins; acc_q += n_q;
-        spec_base = __shfl_sync(0xffffffffu, spec_base, 11);
-        const unsigned long long base_rec = __shfl_sync(0xffffffffu, base, 0), base_seq = __shfl_sync(0xffffffffu, base, 1), base_qual = __shfl_sync(0xffffffffu, base, 2);
+        if (tw == 0) {
+            if (lane == 0) base = atomicAdd((unsigned long long*)&O.totals->n_modified, (unsigned long long)n_mod);
+            else if (lane == 1) base = atomicAdd((unsigned long long*)&O.totals->seq16_used, (unsigned long long)tot_seq);
+            else if (lane == 2) base = atomicAdd((unsigned long long*)&O.totals->qual16_used, (unsigned long long)tot_qual);
+            else if (lane >= 5 && lane < 9) O.sess_counts[4 * (size_t)s + (lane - 5)] = lane == 5 ? cnt_snv : lane == 6 ? cnt_del : lane == 7 ? cnt_ins : sess_reads;
+            else if (lane == 9) { E.germ[(size_t)s * kGermStride] = ngerm; E.germ[(size_t)s * kGermStride + 1] = (uint32_t)c.d.col_begin; }
+            else if (lane == 11) { if (n_spec) spec_base = atomicAdd(E.n_special, n_spec); }
+            acc_reads += sess_reads; acc_bases += sess_bases; acc_snv += cnt_snv; acc_del += cnt_del; acc_ins += cnt_ins; acc_q += n_q;
+            if constexpr (!kSolo) { if (lane < 3) sm->base[lane] = base; else if (lane == 11) sm->spec_base = spec_base; }
+        }
+        unsigned long long base_rec, base_seq, base_qual;
+        if constexpr (kSolo) {
+            spec_base = __shfl_sync(0xffffffffu, spec_base, 11);
+            base_rec = __shfl_sync(0xffffffffu, base, 0); base_seq = __shfl_sync(0xffffffffu, base, 1); base_qual = __shfl_sync(0xffffffffu, base, 2);
+        } else {
+            __syncthreads();
+            spec_base = sm->spec_base; base_rec = sm->base[0]; base_seq = sm->base[1]; base_qual = sm->base[2];
+        }
         const bool fits = (int64_t)(base_rec + n_mod) <= O.cap_records && (int64_t)(base_seq + tot_seq) <= O.cap_seq16 &&
                           (int64_t)(base_qual + tot_qual) <= O.cap_qual16;
         if (!fits) {                                                  // the reserved special slots must not stay undefined
-            for (uint32_t t = lane; t < n_spec; t += 32) if ((int64_t)(spec_base + t) < O.cap_records) E.sdesc[4ull * (spec_base + t)] = make_uint4(0u, 0u, 0u, 0u);
-            if (lane == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu);
+            for (uint32_t t = tl; t < n_spec; t += TS) if ((int64_t)(spec_base + t) < O.cap_records) E.sdesc[4ull * (spec_base + t)] = make_uint4(0u, 0u, 0u, 0u);
+            if (tl == 0) raise_error(O.totals, GA_ERR_CAPACITY, 0xffffffffu);
             continue;
         }
         // ---- record headers and the hand-over to the emission kernels
         uint32_t run_seq = 0u, run_qual = 0u;
 #pragma unroll 1
-        for (uint32_t kb = 0; kb < n_mod; kb += 32) {
+        for (uint32_t kb = 32u * tw; kb < n_mod; kb += TS) {
+            if constexpr (!kSolo) {                                    // where the chunk starts: the sums of the chunks in front of it
+                const uint32_t ch = kb >> 5;
+                const bool in_front = (uint32_t)lane < ch;
+                run_seq = warp_sum(in_front ? sm->chunk_s[lane] : 0u); run_qual = warp_sum(in_front ? sm->chunk_q[lane] : 0u);
+                spec_base = sm->spec_base + warp_sum(in_front ? sm->chunk_p[lane] : 0u);
+            }
             const uint32_t k = kb + lane;
             const bool have_k = k < n_mod;
             const uint32_t rn = have_k ? sm->rnew[k] : 0u;
             const uint32_t kind = rn >> 24, new_len = rn & kLen2;
+            const bool has_qual = kind == 3u || kind == 5u;
             const int i = have_k ? (int)sm->clist[k] : 0;
             const int64_t r = read_of(c, i);
             uint32_t lf = 0u, so = 0u; int pos = 0;
@@ -915,7 +983,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             uint32_t units = have_k ? (new_len + 31u) / 32u : 0u; if (have_k && units < 1u) units = 1u;
             uint32_t ts, tq;
             const uint32_t so_rel = run_seq + warp_excl_scan(units, lane, &ts);
-            const uint32_t qo_rel = run_qual + warp_excl_scan(kind == 3u ? units : 0u, lane, &tq);
+            const uint32_t qo_rel = run_qual + warp_excl_scan(has_qual ? units : 0u, lane, &tq);
             run_seq += ts; run_qual += tq;
             const bool is_spec = have_k && kind != 1u;
             const uint32_t sb = __ballot_sync(0xffffffffu, is_spec);
@@ -923,7 +991,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             spec_base += __popc(sb);
             if (!have_k) continue;
             const uint64_t rec_idx = base_rec + k;
-            const uint32_t qual16 = kind == 3u ? (uint32_t)(base_qual + qo_rel) : 0xffffffffu;
+            const uint32_t qual16 = has_qual ? (uint32_t)(base_qual + qo_rel) : 0xffffffffu;
             write_record_meta(O, rec_idx, s, r, (int)new_len, base_seq + so_rel, qual16);
             const uint32_t L0 = lf & 0xffffu;
             if (kind == 1u && L0 <= 160u) {
@@ -937,28 +1005,32 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 atomicAdd(E.n_kind1, 1u);
             } else if ((int64_t)my_slot < O.cap_records) {
                 write_special(E, B, c.d, my_slot, kind, so, pos, lf, s, r, new_len, base_seq + so_rel, qual16);
+                if (kind == 5u) { const uint32_t at = atomicAdd(E.n_many_recs, 1u); if (at < E.cap_many) E.many_recs[at] = my_slot; }
             }
-            if (kind == 3u) {                                         // the edits travel in the record's (still unused) quality slot
-                Ed2 E2; int nl = 0;
-                lean_collect(c, sm, (int)k, (int)L0, E2, &nl);
+            if (has_qual) {                                           // the edits travel in the record's (still unused) quality slot
                 uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
-                dst[0] = make_uint4((uint32_t)E2.irp[0], (uint32_t)E2.pos[0], (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u), (uint32_t)E2.irp[1]);
                 const int o = sm->mhead[k];                           // any germline observation of the read knows its ordinal
                 const ObsRec* ob = X.obs + (size_t)(2 * (size_t)s) * kObsHalf;
                 const uint32_t qord = __ldg(&(o < (int)n_obs0 ? ob + o : ob + kObsHalf + (o - (int)n_obs0))->qord);
                 const uint32_t qidx = (uint32_t)(i < c.nt ? c.d.qt_begin : c.d.qn_begin) + qord;
-                dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u),
-                                    (uint32_t)E2.ne | ((uint32_t)E2.n_del << 8), qidx);
+                if (kind == 3u) {
+                    Ed2 E2; int nl = 0;
+                    lean_collect(c, sm, (int)k, (int)L0, E2, &nl);
+                    dst[0] = make_uint4((uint32_t)E2.irp[0], (uint32_t)E2.pos[0], (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u), (uint32_t)E2.irp[1]);
+                    dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u),
+                                        (uint32_t)E2.ne | ((uint32_t)E2.n_del << 8), qidx);
+                } else write_many_aux(c, sm, (int)k, (int)L0, qidx, dst);
             }
         }
-        __syncwarp();                                                 // tables are reused by the next session
     }
-    if (lane == 3 && acc_reads) atomicAdd((unsigned long long*)&O.totals->session_reads, acc_reads);
-    else if (lane == 4 && acc_bases) atomicAdd((unsigned long long*)&O.totals->session_bases, acc_bases);
-    else if (lane == 5 && acc_snv) atomicAdd((unsigned long long*)&O.totals->masked[0], (unsigned long long)acc_snv);
-    else if (lane == 6 && acc_del) atomicAdd((unsigned long long*)&O.totals->masked[1], (unsigned long long)acc_del);
-    else if (lane == 7 && acc_ins) atomicAdd((unsigned long long*)&O.totals->masked[2], (unsigned long long)acc_ins);
-    else if (lane == 10 && acc_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)acc_q);
+    if (tw == 0) {
+        if (lane == 3 && acc_reads) atomicAdd((unsigned long long*)&O.totals->session_reads, acc_reads);
+        else if (lane == 4 && acc_bases) atomicAdd((unsigned long long*)&O.totals->session_bases, acc_bases);
+        else if (lane == 5 && acc_snv) atomicAdd((unsigned long long*)&O.totals->masked[0], (unsigned long long)acc_snv);
+        else if (lane == 6 && acc_del) atomicAdd((unsigned long long*)&O.totals->masked[1], (unsigned long long)acc_del);
+        else if (lane == 7 && acc_ins) atomicAdd((unsigned long long*)&O.totals->masked[2], (unsigned long long)acc_ins);
+        else if (lane == 10 && acc_q) atomicAdd((unsigned long long*)&O.totals->indel_records, (unsigned long long)acc_q);
+    }
 }
 
 }  // namespace ga

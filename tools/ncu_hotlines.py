@@ -4,6 +4,7 @@
 usage: tools/ncu_hotlines.py REPORT.ncu-rep [N] [KERNEL_REGEX] [samples|inst]
 """
 import csv
+import os
 import subprocess
 import sys
 
@@ -19,8 +20,14 @@ def main():
     out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     fname, hdr, data = None, None, []
+    want = os.environ.get("FUNC_SUBSTR")                  # e.g. "(int)768": one template instantiation (ncu matches base names only)
+    take = True
     for r in rows:
         if not r:
+            continue
+        if r[0] == "Function Name":
+            take = want is None or want in r[1]
+        if not take:
             continue
         if r[0] == "File Path":
             fname = r[1].split("/")[-1]

@@ -42,13 +42,16 @@ def main():
     per = {}
     for r in rows[2:]:
         name = re.match(r"(?:void )?(?:ga::)?(\w+)", r[ix["Kernel Name"]]).group(1)
+        tm = re.search(r"<([^>]*)>", r[ix["Kernel Name"]])
+        if tm:                                                          # template instantiations are different kernels
+            name += "<" + tm.group(1).replace(" ", "") + ">"
         per[name] = [float(r[ix[k]]) * UNIT[u[ix[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
-        print(f"{name:26s} {float(r[ix['gpu__time_duration.sum']]) * 1e3:8.1f} us  read {per[name][0] / 1e9:6.3f} GB  write {per[name][1] / 1e9:6.3f} GB  "
+        print(f"{name[:44]:44s} {float(r[ix['gpu__time_duration.sum']]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}[u[ix['gpu__time_duration.sum']]]:8.1f} us  read {per[name][0] / 1e9:6.3f} GB  write {per[name][1] / 1e9:6.3f} GB  "
               f"inst {float(r[ix['smsp__inst_executed.sum']]) / 1e6:7.1f} M  issue {float(r[ix['sm__issue_active.avg.pct_of_peak_sustained_elapsed']]):5.1f} %  "
               f"warps {float(r[ix['sm__warps_active.avg.pct_of_peak_sustained_active']]):5.1f} %  regs {r[ix['launch__registers_per_thread']]}  "
               f"grid {r[ix['launch__grid_size']]} x {r[ix['launch__block_size']]}")
     total = sum(a + b for a, b in per.values())
-    json.dump({"workload": "chr1-30x-50k", "windows": 50000,
+    json.dump({"workload": sys.argv[4] if len(sys.argv) > 4 else "chr1-30x-50k", "windows": 50000,
                "source": prefix.split("/")[-1] + "_kernels_raw.csv under profiles/ (ncu --set full, one launch per kernel)",
                "dram_bytes_per_pass": int(total), "per_kernel": per}, open(prefix + "_traffic.json", "w"), indent=1)
     print(f"DRAM bytes per pass: {total / 1e9:.3f} GB")

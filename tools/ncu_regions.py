@@ -4,6 +4,7 @@
 usage: tools/ncu_regions.py REPORT.ncu-rep file:lo-hi=name [...]   (lines not covered are grouped by file)
 """
 import csv
+import os
 import subprocess
 import sys
 from collections import defaultdict
@@ -17,8 +18,10 @@ def main():
         f, rng = loc.split(":")
         lo, hi = rng.split("-")
         regions.append((f, int(lo), int(hi), name))
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"],
-                         capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"]
+    if os.environ.get("KERNEL"):                                          # base-name regex of the kernel to look at
+        cmd += ["--kernel-name", "regex:" + os.environ["KERNEL"]]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     fname, hdr = None, None
     inst, thr, smp = defaultdict(int), defaultdict(int), defaultdict(int)
     for r in csv.reader(out.splitlines()):
