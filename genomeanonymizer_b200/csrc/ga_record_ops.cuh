@@ -34,6 +34,14 @@ __device__ __forceinline__ uint32_t tail_mask(int L, int word) {           // va
     return nv >= 8 ? 0xffffffffu : (nv <= 0 ? 0u : (0xffffffffu >> ((8 - nv) * 4)));
 }
 
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);

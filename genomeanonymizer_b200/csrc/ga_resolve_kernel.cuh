@@ -559,14 +559,6 @@ __device__ __noinline__ bool long_allele_tail_equal(const SessCtx& c, uint32_t r
 // collect2 behind a call: the lean kernel needs it twice and must stay small enough for the instruction cache
 template <class SM> __device__ __noinline__ bool lean_collect(const SessCtx& c, const SM* sm, int k, int L, Ed2& E, int* new_len) { return collect2(c, sm, k, L, E, new_len); }
 
-__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t* total) {
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
-    *total = __shfl_sync(0xffffffffu, inc, 31);
-    return inc - v;
-}
-
 // kFromList: the sessions are the entries of in_list (what the lean instantiation handed over) instead of 0 .. n_sessions - 1.
 // kTeam: warps that work on one session together.  1 = every warp of the CTA has its own session and its own tables
 // (no block barrier); kTeam = kWarps = the CTA is one team: loops are strided over the team, the phases are separated by

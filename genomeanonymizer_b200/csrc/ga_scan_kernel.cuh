@@ -30,6 +30,8 @@ constexpr int kWbuf = 168;                // entries buffered per warp between f
 constexpr uint32_t kEntGen = 1u << 28;   // entry flag: the read is not a clean single-op read
 constexpr uint32_t kCntOverflow = 0xffffffffu;
 constexpr int kScanThreads = 256;
+constexpr int kSrefPad = 8;              // words of reference staged in front of the session's first column
+constexpr int kLaneOps = 12;             // CIGAR ops of a read that the lane-per-read walk takes (more: the whole warp walks the read)
 
 // Nibble masks of a partial 32-base unit: row nv = the four 8-base words of a unit of which only the first nv bases exist.
 struct UnitMasks { uint32_t m[32][4]; };
@@ -55,7 +57,8 @@ struct ScanScratch {
 
 struct WarpSmem {
     uint4 ring[2][kTileUnits];           // record bytes of the tile in flight and the tile being compared
-    uint32_t sref[kCols2 / 8 + 8];       // 4-bit reference of the session's columns (word 0 = ref4 word of column col_begin)
+    uint32_t sref[kCols2 / 8 + 16];      // 4-bit reference of the session's columns: word kSrefPad = the ref4 word of column col_begin, 64 bases of
+                                         // padding in front (a segment's first 32-base unit may start before the window) and 64 behind
     uint32_t wbuf[kWbuf];                // entries waiting for the next coalesced flush
     uint64_t bar[2];                     // mbarriers of the two ring stages
     uint32_t wcnt, ovf;
@@ -66,7 +69,7 @@ struct WarpSmem {
     int n;                               // reads of the item
     int i_base;                          // session-relative id of read `begin`
     int first;                           // region start of the session
-    int relbase;                         // (col_begin + 8) & ~7: reference nibble index of sref word 0
+    int relbase;                         // ((col_begin + 8) & ~7) - 8 * kSrefPad: reference nibble index of sref word 0
     uint32_t item;                       // 2 * session + dataset; the ent / obs regions are derived from it
     uint32_t pad;
 };
@@ -305,6 +308,112 @@ __device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int 
     }
 }
 
+// Reads with another CIGAR, LANE = READ (the records of the tile are staged in the ring).  Every lane walks the ops of its
+// own read, the warp in lockstep over the op index (north_star job (2): the running sums below are the reference's
+// cigar-consumed lengths, variation_classifier.py:69-82):
+//   * an I / D op: the lane writes the observation (slots were handed out by a warp scan of the reads' I / D counts, so
+//     they ascend in read order and, inside a read, in CIGAR order - the emission relies on it);
+//   * an aligned op: the segment's 32-base units are compared against the staged reference window exactly like a clean
+//     read's (128-bit shared-memory loads, one funnel shift per word) on the segment's own diagonal; words outside the
+//     segment are dropped from the mismatch mask, the boundary words are cut to the segment nibble by nibble.
+// A soft-clipped read costs one compare round, a read with one indel two: tens of warp instructions per tile instead of
+// hundreds per read (the 8-lanes-per-read walk, kept for tiles that could not be staged).
+__device__ __forceinline__ void scan_generic_lanes(ItemCtx& c, bool act, int i, int idx, int pos, int L, uint32_t c0, uint32_t n_ops, uint32_t n_id, uint32_t cw0,
+                                                   const uint32_t* rec, uint32_t qord, int lane) {
+    const BatchView& B = c.B;
+    uint32_t tot_id;
+    const uint32_t n_obs0 = c.ws->n_obs;
+    uint32_t slot = n_obs0 + warp_excl_scan(act ? n_id : 0u, lane, &tot_id);
+    const int max_ops = (int)__reduce_max_sync(0xffffffffu, act ? n_ops : 0u);
+    const int relbase = c.ws->relbase;
+    const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
+    int q = 0, rr = 0, bsum = 0;                                         // query consumed, reference consumed, +I +S +H -D (quirk Q7)
+#pragma unroll 1
+    for (int ci = 0; ci < max_ops; ++ci) {
+        const bool has = act && (uint32_t)ci < n_ops;
+        const uint32_t cw = has ? (ci ? __ldg(B.cigar + c0 + ci) : cw0) : 0xfu;
+        const uint32_t op = cw & 15u;
+        const int ln = (int)(cw >> 4);
+        bool aligned = op == 0u || op == 7u || op == 8u;
+        if (op == 1u || op == 2u) {                                      // indel observation (variation_classifier.py:52-107)
+            if (slot >= (uint32_t)kObsHalf) c.ws->ovf = 1u;
+            else {
+                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+                const int irp = rr + bsum;                               // variation_classifier.py:82
+                const int alen = allele_len(meta, irp, L);               // Python-slice clamped (variation_classifier.py:87-88)
+                uint32_t s0 = 0u, s1 = 0u;                                // signature: the first 16 allele bases
+                if (alen > 0) {
+                    const int w0 = irp >> 3;
+                    const uint32_t sh = (uint32_t)(irp & 7) * 4u;
+                    const uint32_t a0 = rec[w0], a1 = 8 * (w0 + 1) < L ? rec[w0 + 1] : 0u, a2 = 8 * (w0 + 2) < L ? rec[w0 + 2] : 0u;
+                    s0 = __funnelshift_r(a0, a1, sh) & tail_mask(alen, 0);
+                    s1 = __funnelshift_r(a1, a2, sh) & tail_mask(alen, 1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.ws->item * kObsHalf + slot);
+                dst[0] = make_uint4((uint32_t)(pos + rr - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
+                dst[1] = make_uint4(s0, s1, qord, 0u);
+            }
+            ++slot;
+        }
+        if (aligned && q + ln > L) {                                     // IndexError in variation_classifier.py:148
+            raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + idx));
+            aligned = false;
+        }
+        if (__any_sync(0xffffffffu, aligned && ln > 0)) {
+            const bool seg = aligned && ln > 0;
+            const int qs = q, qe = q + ln;                               // the segment's query range; its diagonal: reference = pos + rr - q + query
+            const int u_lo = qs >> 5, n_u = seg ? ((qe - 1) >> 5) - u_lo + 1 : 0;
+            const int rel = pos + rr - q + 32 * u_lo + 8 - relbase;      // nibble offset of query base 32 * u_lo in the staged window (>= 0: kSrefPad)
+            const int n_max = __reduce_max_sync(0xffffffffu, n_u);
+            uint32_t wm = 0u;                                            // bit k: 8-base word 4 * u_lo + k differs from the reference
+            {
+                const uint32_t* rp = c.ws->sref + (seg ? (rel >> 3) : 0);
+                const uint32_t sh = (uint32_t)(rel & 7) * 4u;
+                uint32_t prev = rp[0];
+#pragma unroll 1
+                for (int uu = 0; uu < n_max; ++uu) {
+                    if (uu < n_u) {
+                        const uint4 v = rec4[u_lo + uu];
+                        const uint32_t r1 = rp[4 * uu + 1], r2 = rp[4 * uu + 2], r3 = rp[4 * uu + 3], r4 = rp[4 * uu + 4];
+                        const uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
+                        const uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
+                        prev = r4;
+                        wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * uu);
+                    }
+                }
+            }
+            if (seg) {                                                   // only the words that hold bases of the segment
+                const int lo_w = (qs >> 3) - 4 * u_lo, hi_w = ((qe - 1) >> 3) - 4 * u_lo;
+                wm &= (0xffffffffu << lo_w) & (0xffffffffu >> (31 - hi_w));
+            } else wm = 0u;
+            while (wm) {                                                 // SNV candidates (variation_classifier.py:147-150)
+                const int k = __ffs(wm) - 1; wm &= wm - 1;
+                const int kw = 4 * u_lo + k, qb = kw << 3;
+                const uint32_t rw = rec[kw];
+                const int nib = rel + 8 * k;
+                const uint32_t fw = __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u);
+                const int lo = max(qs, qb), hi = min(qe, qb + 8);
+                uint32_t x = (rw ^ fw) & (0xffffffffu << ((lo - qb) * 4)) & (0xffffffffu >> ((qb + 8 - hi) * 4));
+                const int colb = pos + rr - q + qb - c.col_begin;
+                while (x) {
+                    const int n = (__ffs(x) - 1) >> 2;
+                    x &= ~(0xfu << (n * 4));
+                    const uint32_t bb = (rw >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+                    if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, rf, kEntGen);
+                }
+            }
+        }
+        if (aligned) { q += ln; rr += ln; }
+        else if (op == 1u || op == 4u) { q += ln; bsum += ln; }
+        else if (op == 2u) { rr += ln; bsum -= ln; }
+        else if (op == 3u) rr += ln;
+        else if (op == 5u) bsum += ln;
+    }
+    __syncwarp();
+    if (lane == 0 && tot_id) c.ws->n_obs = min(n_obs0 + tot_id, (uint32_t)kObsHalf);
+    __syncwarp();
+}
+
 __device__ __forceinline__ TileMeta load_tile_meta(const ItemCtx& c, int t, int TR, int lane) {
     TileMeta m = {0, 0u, 0u, 0u};
     const int i = t * TR + lane;
@@ -415,14 +524,15 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
     if (__any_sync(0xffffffffu, gen)) {
         // lane = read: reference span and I/D presence of its ops, then the checks the reference's walk implies
         int span = 0;
-        bool has_id = false;
+        uint32_t n_id = 0u;
         if (gen) {
             for (uint32_t ci = 0; ci < n_ops; ++ci) {
                 const uint32_t w = ci ? __ldg(c.B.cigar + m.c0 + ci) : cw0, op = w & 15u;
                 if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int)(w >> 4);
-                has_id |= (op == 1u || op == 2u);
+                n_id += (op == 1u || op == 2u) ? 1u : 0u;
             }
         }
+        const bool has_id = n_id != 0u;
         // the read's ordinal among the item's reads with an I/D op = its slot in the sparse quality index; counted
         // before any exit: the index lists every such read
         const uint32_t idm = __ballot_sync(0xffffffffu, gen && has_id);
@@ -435,7 +545,11 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
             raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + idx));
             work = false;
         }
-        uint32_t m_short = __ballot_sync(0xffffffffu, work && n_ops <= 8u), m_long = __ballot_sync(0xffffffffu, work && n_ops > 8u);
+        // staged tiles: lane = read; tiles that could not be staged (and very long CIGARs / reads): the group and whole-warp walks
+        const bool by_lane = work && staged && n_ops <= (uint32_t)kLaneOps && L <= 256;
+        if (__any_sync(0xffffffffu, by_lane))
+            scan_generic_lanes(c, by_lane, i, idx, pos, L, m.c0, n_ops, n_id, cw0, reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (by_lane ? m.so - sof : 0u)), qord, lane);
+        uint32_t m_short = __ballot_sync(0xffffffffu, work && !by_lane && n_ops <= 8u), m_long = __ballot_sync(0xffffffffu, work && !by_lane && n_ops > 8u);
         while (m_short) {                                                // four reads per step, 8 lanes each
             uint32_t sel = 0u;
 #pragma unroll
@@ -492,7 +606,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
         c.ws->begin = ds ? n_begin : t_begin;
         c.ws->n = ds ? n_end - n_begin : t_end - t_begin;
         c.ws->i_base = ds ? t_end - t_begin : 0;
-        c.ws->relbase = (c.col_begin + 8) & ~7;
+        c.ws->relbase = ((c.col_begin + 8) & ~7) - 8 * kSrefPad;
         c.table_in_ref = c.col_begin >= 0 && (int64_t)c.col_begin + c.n_cols <= B.ref_len;
         c.ws->item = item;
         c.n_reads = 0u; c.n_bases = 0u;
@@ -501,9 +615,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_kernel(BatchView B, Sess
         if (!big && c.ws->n > 0) {
             // ---- the session's reference window (+ record padding, + funnel-shift lookahead)
             {
-                const int64_t w0 = (int64_t)((c.col_begin + 8) >> 3);
-                const int nw = (c.n_cols >> 3) + 8;
-                for (int k = lane; k < nw; k += 32) ws->sref[k] = (w0 + k < ref_words) ? __ldg(B.ref4 + w0 + k) : 0xffffffffu;
+                const int64_t w0 = (int64_t)((c.col_begin + 8) >> 3) - kSrefPad;
+                const int nw = (c.n_cols >> 3) + 8 + kSrefPad;
+                for (int k = lane; k < nw; k += 32) ws->sref[k] = (w0 + k >= 0 && w0 + k < ref_words) ? __ldg(B.ref4 + w0 + k) : 0xffffffffu;
             }
             const uint32_t avg_units = max(1u, (seq_n + (uint32_t)c.ws->n - 1u) / (uint32_t)c.ws->n);
             const int TR = (int)max(1u, min(31u, (uint32_t)kTileUnits / avg_units));     // reads per tile (31: see TileMeta)
