@@ -309,8 +309,8 @@ __device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int 
 }
 
 // Reads with another CIGAR, LANE = READ (the records of the tile are staged in the ring).  Every lane walks the ops of its
-// own read, the warp in lockstep over the op index (north_star job (2): the running sums below are the reference's
-// cigar-consumed lengths, variation_classifier.py:69-82):
+// own read; the warp moves in ROUNDS, one aligned segment per lane and round (north_star job (2): the running sums below
+// are the reference's cigar-consumed lengths, variation_classifier.py:69-82):
 //   * an I / D op: the lane writes the observation (slots were handed out by a warp scan of the reads' I / D counts, so
 //     they ascend in read order and, inside a read, in CIGAR order - the emission relies on it);
 //   * an aligned op: the segment's 32-base units are compared against the staged reference window exactly like a clean
@@ -324,90 +324,94 @@ __device__ __forceinline__ void scan_generic_lanes(ItemCtx& c, bool act, int i, 
     uint32_t tot_id;
     const uint32_t n_obs0 = c.ws->n_obs;
     uint32_t slot = n_obs0 + warp_excl_scan(act ? n_id : 0u, lane, &tot_id);
-    const int max_ops = (int)__reduce_max_sync(0xffffffffu, act ? n_ops : 0u);
     const int relbase = c.ws->relbase;
     const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
     int q = 0, rr = 0, bsum = 0;                                         // query consumed, reference consumed, +I +S +H -D (quirk Q7)
+    uint32_t ci = 0u;                                                    // the lane's next op
 #pragma unroll 1
-    for (int ci = 0; ci < max_ops; ++ci) {
-        const bool has = act && (uint32_t)ci < n_ops;
-        const uint32_t cw = has ? (ci ? __ldg(B.cigar + c0 + ci) : cw0) : 0xfu;
-        const uint32_t op = cw & 15u;
-        const int ln = (int)(cw >> 4);
-        bool aligned = op == 0u || op == 7u || op == 8u;
-        if (op == 1u || op == 2u) {                                      // indel observation (variation_classifier.py:52-107)
-            if (slot >= (uint32_t)kObsHalf) c.ws->ovf = 1u;
-            else {
-                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
-                const int irp = rr + bsum;                               // variation_classifier.py:82
-                const int alen = allele_len(meta, irp, L);               // Python-slice clamped (variation_classifier.py:87-88)
-                uint32_t s0 = 0u, s1 = 0u;                                // signature: the first 16 allele bases
-                if (alen > 0) {
-                    const int w0 = irp >> 3;
-                    const uint32_t sh = (uint32_t)(irp & 7) * 4u;
-                    const uint32_t a0 = rec[w0], a1 = 8 * (w0 + 1) < L ? rec[w0 + 1] : 0u, a2 = 8 * (w0 + 2) < L ? rec[w0 + 2] : 0u;
-                    s0 = __funnelshift_r(a0, a1, sh) & tail_mask(alen, 0);
-                    s1 = __funnelshift_r(a1, a2, sh) & tail_mask(alen, 1);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.ws->item * kObsHalf + slot);
-                dst[0] = make_uint4((uint32_t)(pos + rr - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
-                dst[1] = make_uint4(s0, s1, qord, 0u);
-            }
-            ++slot;
-        }
-        if (aligned && q + ln > L) {                                     // IndexError in variation_classifier.py:148
-            raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + idx));
-            aligned = false;
-        }
-        if (__any_sync(0xffffffffu, aligned && ln > 0)) {
-            const bool seg = aligned && ln > 0;
-            const int qs = q, qe = q + ln;                               // the segment's query range; its diagonal: reference = pos + rr - q + query
-            const int u_lo = qs >> 5, n_u = seg ? ((qe - 1) >> 5) - u_lo + 1 : 0;
-            const int rel = pos + rr - q + 32 * u_lo + 8 - relbase;      // nibble offset of query base 32 * u_lo in the staged window (>= 0: kSrefPad)
-            const int n_max = __reduce_max_sync(0xffffffffu, n_u);
-            uint32_t wm = 0u;                                            // bit k: 8-base word 4 * u_lo + k differs from the reference
-            {
-                const uint32_t* rp = c.ws->sref + (seg ? (rel >> 3) : 0);
-                const uint32_t sh = (uint32_t)(rel & 7) * 4u;
-                uint32_t prev = rp[0];
+    for (;;) {
+        // ---- every lane moves on to its next aligned op; what lies in front of it is handled on the way
+        bool seg = false;
+        int ln = 0;
 #pragma unroll 1
-                for (int uu = 0; uu < n_max; ++uu) {
-                    if (uu < n_u) {
-                        const uint4 v = rec4[u_lo + uu];
-                        const uint32_t r1 = rp[4 * uu + 1], r2 = rp[4 * uu + 2], r3 = rp[4 * uu + 3], r4 = rp[4 * uu + 4];
-                        const uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
-                        const uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
-                        prev = r4;
-                        wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * uu);
+        while (__any_sync(0xffffffffu, act && !seg && ci < n_ops)) {
+            if (act && !seg && ci < n_ops) {
+                const uint32_t cw = ci ? __ldg(B.cigar + c0 + ci) : cw0;
+                const uint32_t op = cw & 15u;
+                const int l = (int)(cw >> 4);
+                ++ci;
+                if (op == 0u || op == 7u || op == 8u) {
+                    if (q + l > L) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + idx));   // IndexError in variation_classifier.py:148
+                    else if (l > 0) { seg = true; ln = l; }
+                } else if (op == 1u || op == 2u) {                       // indel observation (variation_classifier.py:52-107)
+                    if (slot >= (uint32_t)kObsHalf) c.ws->ovf = 1u;
+                    else {
+                        const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)l & kMetaLenMask);
+                        const int irp = rr + bsum;                       // variation_classifier.py:82
+                        const int alen = allele_len(meta, irp, L);       // Python-slice clamped (variation_classifier.py:87-88)
+                        uint32_t s0 = 0u, s1 = 0u;                        // signature: the first 16 allele bases
+                        if (alen > 0) {
+                            const int w0 = irp >> 3;
+                            const uint32_t sh = (uint32_t)(irp & 7) * 4u;
+                            const uint32_t a0 = rec[w0], a1 = 8 * (w0 + 1) < L ? rec[w0 + 1] : 0u, a2 = 8 * (w0 + 2) < L ? rec[w0 + 2] : 0u;
+                            s0 = __funnelshift_r(a0, a1, sh) & tail_mask(alen, 0);
+                            s1 = __funnelshift_r(a1, a2, sh) & tail_mask(alen, 1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(c.X.obs + (size_t)c.ws->item * kObsHalf + slot);
+                        dst[0] = make_uint4((uint32_t)(pos + rr - c.col_begin), meta, (uint32_t)i | ((uint32_t)alen << 16), (uint32_t)irp);
+                        dst[1] = make_uint4(s0, s1, qord, 0u);
                     }
-                }
+                    ++slot;
+                    if (op == 1u) { q += l; bsum += l; } else { rr += l; bsum -= l; }
+                } else if (op == 4u) { q += l; bsum += l; }
+                else if (op == 3u) rr += l;
+                else if (op == 5u) bsum += l;
             }
-            if (seg) {                                                   // only the words that hold bases of the segment
-                const int lo_w = (qs >> 3) - 4 * u_lo, hi_w = ((qe - 1) >> 3) - 4 * u_lo;
-                wm &= (0xffffffffu << lo_w) & (0xffffffffu >> (31 - hi_w));
-            } else wm = 0u;
-            while (wm) {                                                 // SNV candidates (variation_classifier.py:147-150)
-                const int k = __ffs(wm) - 1; wm &= wm - 1;
-                const int kw = 4 * u_lo + k, qb = kw << 3;
-                const uint32_t rw = rec[kw];
-                const int nib = rel + 8 * k;
-                const uint32_t fw = __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u);
-                const int lo = max(qs, qb), hi = min(qe, qb + 8);
-                uint32_t x = (rw ^ fw) & (0xffffffffu << ((lo - qb) * 4)) & (0xffffffffu >> ((qb + 8 - hi) * 4));
-                const int colb = pos + rr - q + qb - c.col_begin;
-                while (x) {
-                    const int n = (__ffs(x) - 1) >> 2;
-                    x &= ~(0xfu << (n * 4));
-                    const uint32_t bb = (rw >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
-                    if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, rf, kEntGen);
+        }
+        if (!__any_sync(0xffffffffu, seg)) break;
+        // ---- one compare round: the lanes' segments on their own diagonals (reference = pos + rr - q + query)
+        const int qs = q, qe = q + ln;
+        const int u_lo = qs >> 5, n_u = seg ? ((qe - 1) >> 5) - u_lo + 1 : 0;
+        const int rel = pos + rr - q + 32 * u_lo + 8 - relbase;          // nibble offset of query base 32 * u_lo in the staged window (>= 0: kSrefPad)
+        const int n_max = __reduce_max_sync(0xffffffffu, n_u);
+        uint32_t wm = 0u;                                                // bit k: 8-base word 4 * u_lo + k differs from the reference
+        {
+            const uint32_t* rp = c.ws->sref + (seg ? (rel >> 3) : 0);
+            const uint32_t sh = (uint32_t)(rel & 7) * 4u;
+            uint32_t prev = rp[0];
+#pragma unroll 1
+            for (int uu = 0; uu < n_max; ++uu) {
+                if (uu < n_u) {
+                    const uint4 v = rec4[u_lo + uu];
+                    const uint32_t r1 = rp[4 * uu + 1], r2 = rp[4 * uu + 2], r3 = rp[4 * uu + 3], r4 = rp[4 * uu + 4];
+                    const uint32_t x0 = v.x ^ __funnelshift_r(prev, r1, sh), x1 = v.y ^ __funnelshift_r(r1, r2, sh);
+                    const uint32_t x2 = v.z ^ __funnelshift_r(r2, r3, sh), x3 = v.w ^ __funnelshift_r(r3, r4, sh);
+                    prev = r4;
+                    wm |= ((x0 ? 1u : 0u) | (x1 ? 2u : 0u) | (x2 ? 4u : 0u) | (x3 ? 8u : 0u)) << (4 * uu);
                 }
             }
         }
-        if (aligned) { q += ln; rr += ln; }
-        else if (op == 1u || op == 4u) { q += ln; bsum += ln; }
-        else if (op == 2u) { rr += ln; bsum -= ln; }
-        else if (op == 3u) rr += ln;
-        else if (op == 5u) bsum += ln;
+        if (seg) {                                                       // only the words that hold bases of the segment
+            const int lo_w = (qs >> 3) - 4 * u_lo, hi_w = ((qe - 1) >> 3) - 4 * u_lo;
+            wm &= (0xffffffffu << lo_w) & (0xffffffffu >> (31 - hi_w));
+        } else wm = 0u;
+        while (wm) {                                                     // SNV candidates (variation_classifier.py:147-150)
+            const int k = __ffs(wm) - 1; wm &= wm - 1;
+            const int kw = 4 * u_lo + k, qb = kw << 3;
+            const uint32_t rw = rec[kw];
+            const int nib = rel + 8 * k;
+            const uint32_t fw = __funnelshift_r(c.ws->sref[nib >> 3], c.ws->sref[(nib >> 3) + 1], (uint32_t)(nib & 7) * 4u);
+            const int lo = max(qs, qb), hi = min(qe, qb + 8);
+            uint32_t x = (rw ^ fw) & (0xffffffffu << ((lo - qb) * 4)) & (0xffffffffu >> ((qb + 8 - hi) * 4));
+            const int colb = pos + rr - q + qb - c.col_begin;
+            while (x) {
+                const int n = (__ffs(x) - 1) >> 2;
+                x &= ~(0xfu << (n * 4));
+                const uint32_t bb = (rw >> (n * 4)) & 15u, rf = (fw >> (n * 4)) & 15u;
+                if (bb != 15u && is_acgt(rf)) push_entry_w(c, i, colb + n, bb, rf, kEntGen);
+            }
+        }
+        if (seg) { q += ln; rr += ln; }
     }
     __syncwarp();
     if (lane == 0 && tot_id) c.ws->n_obs = min(n_obs0 + tot_id, (uint32_t)kObsHalf);
