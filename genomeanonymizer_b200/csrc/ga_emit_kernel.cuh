@@ -339,6 +339,276 @@ __device__ __forceinline__ void emit_two_edit_quad(const BatchView& B, const Res
     }
 }
 
+// ------------------------------------------------------------------ LANE = RECORD
+// emit_records_kernel writes the common special records - reads up to 160 bases with another CIGAR and SNV hits only
+// (kind 2) or with ONE germline indel (kind 3) - with ONE LANE PER RECORD.  Eight lanes per record (emit_special_kernel,
+// round 1) repeat every scalar step of a record eight times and leave a third of the lanes idle in the word loops; a
+// lane of its own runs the whole record as straight-line arithmetic, and the 32 records of a warp step differ only in
+// data, never in control flow.  What a lane cannot do efficiently is touch global memory (32 lanes = 32 cache lines per
+// instruction), so a warp step is:
+//   1. lane = record: descriptor, edit description, quality-record slot (coalesced: the descriptors are dense); what
+//      this kernel does not take (two edits, many hits, longer reads) is listed for emit_special_kernel;
+//   2. the WARP copies the 32 source records (and quality records) into shared memory with asynchronous 4-byte copies
+//      (cp.async, zero fill for the padding words), one record per step with consecutive lanes on consecutive words, all
+//      in flight together - a lane's record lands in a private row of odd stride (no bank conflicts);
+//   3. lane = record: SNV masking (anonymizer_methods.py:170-176) in the row; then the final array is three pieces -
+//      [0, p) = source as is, [p, ins_end) = re-inserted reference bases with quality floor(mean) (DEL only),
+//      [ins_end, new_len) = source shifted (anonymizer_methods.py:178-203; no edit: one piece) - and every output word is
+//      merged from them by masks, four words per 128-bit store; qualities in printed (= BAM) order (quirks Q1, Q2).
+constexpr int kRecMaxL = 160;            // bases of a read handled here (longer: emit_special_kernel)
+constexpr int kRecSeqW = 23;             // row: [0] zero pad (source index -8 .. -1), [1, 21) record words, [21, 23) zero
+constexpr int kRecQualW = 43;            // row: [0] zero pad, [1, 41) quality words, [41, 43) zero
+constexpr int kRecWarps = 4;
+struct RecWarp { uint32_t guard0[8]; uint32_t seq[32][kRecSeqW]; uint32_t guard1[8]; uint32_t qual[32][kRecQualW]; uint32_t guard2[8]; };   // guards: a shifted row pointer may reach a few words outside its row (values unused)
+static_assert(kRecSeqW % 2 == 1 && kRecQualW % 2 == 1, "rows of odd word stride");
+
+__device__ __forceinline__ uint32_t rec_stage_at(const uint32_t* row, int sidx) {      // 8 staged bases from source index sidx (any value)
+    const int s = min(max(sidx, -8), 8 * (kRecSeqW - 2) - 1);
+    const int wi = (s >> 3) + 1;
+    return __funnelshift_r(row[wi], row[wi + 1], (uint32_t)(s & 7) * 4u);
+}
+__device__ __forceinline__ uint32_t rec_qual_at(const uint32_t* row, int bidx) {       // 4 staged quality bytes from BAM byte bidx (any value)
+    const int s = min(max(bidx, -4), 4 * (kRecQualW - 2) - 1);
+    const int wi = (s >> 2) + 1;
+    return __funnelshift_r(row[wi], row[wi + 1], (uint32_t)(s & 3) * 8u);
+}
+// asynchronous 4-byte copy global -> shared; n_src = 0 writes zeros instead (SASS: LDGSTS)
+__device__ __forceinline__ void cp_async4(uint32_t* dst, const uint32_t* src, uint32_t n_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(n_src) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kRecWarps) emit_records_kernel(BatchView B, ResultView O, EmitScratch2 E) {
+    extern __shared__ __align__(16) uint8_t emit_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RecWarp& W = reinterpret_cast<RecWarp*>(emit_smem)[warp];
+    uint32_t* sq = W.seq[lane];
+    uint32_t* qq = W.qual[lane];
+    const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
+    const uint32_t stride = gridDim.x * kRecWarps * 32;
+    for (uint32_t jb = (blockIdx.x * kRecWarps + warp) * 32; jb < n_x; jb += stride) {      // warp-uniform
+        // ---- 1. lane = record
+        const uint32_t j = jb + lane;
+        int cls = -1;                                                    // 0: SNV-only, 1: one germline indel
+        bool rare = false;
+        uint32_t so = 0u, c0 = 0u, c1 = 0u, germ_n = 0u, qunit = 0u, seq16 = 0u, qual16 = 0u, rd = 0u;
+        int pos = 0, L = 0, s = 0, new_len = 0, col_begin = 0;
+        bool reverse = false;
+        int ed_pos = 0, ed_len = 0, p = 0, ins_end = 0, shift = 0;        // the edit: [p, ins_end) re-inserted elements, source = final + shift behind them
+        bool is_del = false;
+        if (j < n_x) {
+            const uint4* dp = E.sdesc + 4ull * j;
+            const uint4 d0 = dp[0], d1 = dp[1], d2 = dp[2];
+            const uint32_t kind = (d0.z >> 16) & 15u;                    // 0: the slot of a session that did not fit
+            so = d0.x; pos = (int)d0.y; L = (int)(d0.z & 0xffffu); reverse = ((d0.z >> 20) & 1u) != 0u; s = (int)d0.w;
+            rd = d1.x; new_len = (int)d1.y; seq16 = d1.z; qual16 = d1.w;
+            c0 = d2.x; c1 = d2.y; col_begin = (int)d2.z;
+            p = ins_end = new_len;
+            if (kind == 4u || ((kind == 2u || kind == 3u) && L > kRecMaxL)) rare = true;
+            else if (kind == 2u) cls = 0;
+            else if (kind == 3u) {
+                const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
+                const uint4 x0 = ap[0], x1 = ap[1];                      // EditAux written by the resolve kernel
+                if ((x1.z & 0xffu) != 1u) rare = true;                   // two edits: the run-list form of emit_special_kernel
+                else {
+                    Ed2 Ed; Ed.ne = 1; Ed.n_del = (int)((x1.z >> 8) & 0xffu);
+                    Ed.irp[0] = (int)x0.x; Ed.pos[0] = (int)x0.y; Ed.len[0] = (int)(x0.z & 0x7fffffffu);
+                    Ed.irp[1] = 0; Ed.pos[1] = 0; Ed.len[1] = 0; Ed.mean[0] = Ed.mean[1] = 0u;
+                    clamp_edits2(Ed, L);
+                    is_del = Ed.n_del == 1; ed_pos = Ed.pos[0]; ed_len = Ed.len[0];
+                    p = Ed.p[0]; shift = is_del ? -ed_len : Ed.e[0] - Ed.p[0]; ins_end = is_del ? p + ed_len : p;
+                    if (is_del && (int64_t)ed_pos + ed_len > B.ref_len) raise_error(O.totals, GA_ERR_LENGTH_MISMATCH, rd);
+                    // the read's quality record: dense upload, or the slot the resolve kernel predicted in the sparse index
+                    // (verified; a caller may list more reads than those with I/D ops), or a search of the slice
+                    qunit = 0xffffffffu;
+                    if (B.qual && !B.qual_reads) qunit = so;
+                    else if (B.qual) {
+                        const int64_t qi = (int64_t)x1.w;
+                        if (qi < B.n_qual && __ldg(B.qual_reads + qi) == (int32_t)rd) qunit = __ldg(B.qual_off16 + qi);
+                        else {
+                            const uint4 d3 = dp[3];
+                            const uint8_t* qp = qual_record_in(B, (int64_t)rd, (int64_t)d3.x, (int64_t)d3.y);
+                            if (qp) qunit = (uint32_t)((qp - B.qual) >> 5);
+                        }
+                    }
+                    if (qunit == 0xffffffffu) raise_error(O.totals, GA_ERR_BAD_ARGUMENT, rd);   // no quality record for an indel-masked read
+                    else cls = 1;
+                }
+            }
+            if (cls >= 0) germ_n = __ldg(E.germ + (size_t)s * kGermStride);
+        }
+        {   // what is left for emit_special_kernel
+            const uint32_t rm = __ballot_sync(0xffffffffu, rare);
+            if (rm) {
+                uint32_t at = 0u;
+                if (lane == 0) at = atomicAdd(E.n_rare, (uint32_t)__popc(rm));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (rare) E.rare_list[at + __popc(rm & ((1u << lane) - 1u))] = j;
+            }
+        }
+        const uint32_t live = __ballot_sync(0xffffffffu, cls >= 0);
+        if (!live) continue;
+        // ---- 2. the warp stages the records: one record per step, consecutive lanes on consecutive words, all copies in flight
+#pragma unroll 4
+        for (int t = 0; t < 32; ++t) {
+            if (!((live >> t) & 1u)) continue;
+            const uint32_t t_so = __shfl_sync(0xffffffffu, so, t), t_qu = __shfl_sync(0xffffffffu, qunit, t);
+            const int t_L = __shfl_sync(0xffffffffu, L, t), t_cls = __shfl_sync(0xffffffffu, cls, t);
+            {
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * t_so);
+                const int w = lane - 1;
+                const bool data = w >= 0 && 8 * w < t_L;
+                if (lane < kRecSeqW) cp_async4(&W.seq[t][lane], rec + (data ? w : 0), data ? 4u : 0u);
+            }
+            if (t_cls == 1) {
+                const uint32_t* qrec = reinterpret_cast<const uint32_t*>(B.qual + 32ull * t_qu);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jq = lane + 32 * h, w = jq - 1;
+                    const bool data = w >= 0 && 4 * w < t_L;
+                    if (jq < kRecQualW) cp_async4(&W.qual[t][jq], qrec + (data ? w : 0), data ? 4u : 0u);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        // ---- 3a. lane = record: SNV masking - every germline allele of the session is carried through the CIGAR to its
+        // query offset and, when the read shows it, replaced by the reference base
+        {
+            const uint32_t n_ops = c1 - c0;
+            uint32_t cg0 = 0u, cg1 = 0u, cg2 = 0u, cg3 = 0u;             // the first four ops travel in registers
+            if (cls >= 0) {
+                if (n_ops > 0u) cg0 = __ldg(B.cigar + c0);
+                if (n_ops > 1u) cg1 = __ldg(B.cigar + c0 + 1);
+                if (n_ops > 2u) cg2 = __ldg(B.cigar + c0 + 2);
+                if (n_ops > 3u) cg3 = __ldg(B.cigar + c0 + 3);
+                const uint32_t tm = tail_mask(L, (L - 1) >> 3);          // the padding nibbles of the last word are not part of the read
+                if (L > 0) sq[1 + ((L - 1) >> 3)] &= tm;
+            }
+            const uint32_t g_max = __reduce_max_sync(0xffffffffu, cls >= 0 ? germ_n : 0u);
+            const uint32_t* ge = E.germ + (size_t)s * kGermStride + 4;
+#pragma unroll 1
+            for (uint32_t a = 0; a < g_max; ++a) {
+                if (cls < 0 || a >= germ_n) continue;
+                const uint32_t key = __ldg(ge + a), code = key & 15u;
+                const int at = col_begin + (int)(key >> 4);
+                if (at < pos) continue;                                  // the column lies in front of the read
+                int rc = pos, q = 0;
+#pragma unroll 1
+                for (uint32_t ci = 0; ci < n_ops; ++ci) {
+                    if (at < rc) break;                                  // the column lies before what is left of the read
+                    const uint32_t cw = ci == 0u ? cg0 : ci == 1u ? cg1 : ci == 2u ? cg2 : ci == 3u ? cg3 : __ldg(B.cigar + c0 + ci);
+                    const uint32_t op = cw & 15u;
+                    const int ln = (int)(cw >> 4);
+                    if (op == 0u || op == 7u || op == 8u) {
+                        if (at < rc + ln) {
+                            const int x = q + (at - rc);
+                            if (x < L) {
+                                const uint32_t sh = (uint32_t)(x & 7) * 4u, w = sq[1 + (x >> 3)];
+                                if (((w >> sh) & 15u) == code) sq[1 + (x >> 3)] = w ^ ((code ^ ref_code(B.ref4, at)) << sh);
+                            }
+                            break;
+                        }
+                        q += ln; rc += ln;
+                    } else if (op == 1u || op == 4u) q += ln;
+                    else if (op == 2u || op == 3u) { if (at < rc + ln) break; rc += ln; }
+                }
+            }
+        }
+        // ---- 3b. quality of re-inserted bases: floor(mean(qualities)) (anonymizer_methods.py:193)
+        uint32_t mean4 = 0u;
+        if (__any_sync(0xffffffffu, is_del)) {
+            uint32_t sum = 0u;
+            if (is_del) {
+#pragma unroll 8
+                for (int w = 0; w < kRecQualW - 3; ++w) sum += __vsadu4(qq[1 + w] & low_bytes_bf(L - 4 * w), 0u);
+            }
+            mean4 = (is_del && L ? sum / (uint32_t)L : 0u) * 0x01010101u;
+        }
+        // ---- 3c. bases.  A word that lies wholly in front of the edit is the staged word, a word wholly behind it one funnel
+        // shift of two staged words (constant shift per record); only the words that straddle a piece boundary or hold
+        // re-inserted reference bases need the masked merge - they are rewritten afterwards, a handful per record.
+        const int units = cls >= 0 ? max(1, (new_len + 31) >> 5) : 0;
+        const int u_max = __reduce_max_sync(0xffffffffu, units);
+        {
+            uint4* out = reinterpret_cast<uint4*>(O.out_seq4 + 16ull * seq16);
+            const int wf = p >> 3, wz = (new_len + 7) >> 3;
+            const uint32_t* sb = sq + 1 + (shift >> 3);                  // may point a few words outside the row: guard words around the rows
+            const uint32_t sh = (uint32_t)(shift & 7) * 4u;
+#pragma unroll 1
+            for (int u = 0; u < u_max; ++u) {
+                if (u >= units) continue;
+                const uint32_t* a4 = sq + 1 + 4 * u;
+                const uint32_t* b4 = sb + 4 * u;
+                const uint32_t b0 = b4[0], b1w = b4[1], b2w = b4[2], b3w = b4[3], b4w = b4[4];
+                uint32_t o[4] = {__funnelshift_r(b0, b1w, sh), __funnelshift_r(b1w, b2w, sh), __funnelshift_r(b2w, b3w, sh), __funnelshift_r(b3w, b4w, sh)};
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int w = 4 * u + x;
+                    if (w < wf) o[x] = a4[x];
+                    if (w >= wz) o[x] = 0u;
+                }
+                out[u] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            // the words around the edit and the last word
+            uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+            auto merged = [&](int w) {
+                const int j0 = w << 3;
+                const uint32_t mA = low_nibbles_bf(p - j0), mAB = low_nibbles_bf(ins_end - j0);
+                uint32_t v = (rec_stage_at(sq, j0) & mA) | (rec_stage_at(sq, j0 + shift) & ~mAB);
+                const uint32_t mR = mAB & ~mA;
+                if (mR) v |= ref_word(B.ref4, (int64_t)ed_pos + (j0 - p)) & mR;
+                ow[w] = v & low_nibbles_bf(new_len - j0);
+            };
+            const int w_lo = p >> 3, w_hi = cls >= 0 ? min((max(ins_end, p + 1) - 1) >> 3, 4 * units - 1) : -1;
+            const int n_fix = __reduce_max_sync(0xffffffffu, cls >= 0 ? w_hi - w_lo + 1 : 0);
+#pragma unroll 1
+            for (int t = 0; t < n_fix; ++t) if (w_lo + t <= w_hi) merged(w_lo + t);
+            if (cls >= 0 && (new_len & 7) && (new_len >> 3) < 4 * units) merged(new_len >> 3);
+        }
+        // ---- 3d. qualities in printed (= BAM) order.  The edit indexes the forward-orientation array (quirk Q2), so for a
+        // reverse read the pieces come in the opposite order: printed [0, b1) = BAM bytes as they are, [b1, b2) = the mean,
+        // [b2, new_len) = BAM bytes shifted by d3.  Same scheme: whole words first, the straddling words afterwards.
+        if (__any_sync(0xffffffffu, cls == 1)) {
+            const int b1 = reverse ? new_len - ins_end : p, b2 = reverse ? new_len - p : ins_end, d3 = reverse ? L - new_len : shift;
+            const int qunits = cls == 1 ? 2 * units : 0;
+            const int q_max = __reduce_max_sync(0xffffffffu, qunits);
+            uint4* out = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
+            const int wf = b1 >> 2, wb = (b2 + 3) >> 2, wz = (new_len + 3) >> 2;
+            const uint32_t* qb = qq + 1 + (d3 >> 2);
+            const uint32_t sh = (uint32_t)(d3 & 3) * 8u;
+#pragma unroll 1
+            for (int u = 0; u < q_max; ++u) {
+                if (u >= qunits) continue;
+                const uint32_t* a4 = qq + 1 + 4 * u;
+                const uint32_t* b4 = qb + 4 * u;
+                const uint32_t b0 = b4[0], b1w = b4[1], b2w = b4[2], b3w = b4[3], b4w = b4[4];
+                uint32_t o[4] = {__funnelshift_r(b0, b1w, sh), __funnelshift_r(b1w, b2w, sh), __funnelshift_r(b2w, b3w, sh), __funnelshift_r(b3w, b4w, sh)};
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int w = 4 * u + x;
+                    if (w < wb) o[x] = mean4;
+                    if (w < wf) o[x] = a4[x];
+                    if (w >= wz) o[x] = 0u;
+                }
+                out[u] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+            auto merged = [&](int w) {
+                const int p0 = w << 2;
+                const uint32_t m1 = low_bytes_bf(b1 - p0), m12 = low_bytes_bf(b2 - p0);
+                const uint32_t v = (rec_qual_at(qq, p0) & m1) | (mean4 & m12 & ~m1) | (rec_qual_at(qq, p0 + d3) & ~m12);
+                ow[w] = v & low_bytes_bf(new_len - p0);
+            };
+            if (cls == 1) {
+                if ((b1 & 3) && (b1 >> 2) < 4 * qunits) merged(b1 >> 2);
+                if ((b2 & 3) && (b2 >> 2) < 4 * qunits) merged(b2 >> 2);
+                if ((new_len & 3) && (new_len >> 2) < 4 * qunits) merged(new_len >> 2);
+            }
+        }
+        __syncwarp();                                                     // the rows are rewritten by the next 32 records
+    }
+}
+
 // kind 4: a clean read with more than two germline hits - copy, looking every mismatch up in the session's germline list.
 __device__ __forceinline__ void emit_many_hits_quad(const BatchView& B, const ResultView& O, const GermList& germ, const SpecRec& R, int glane) {
     const int L = R.new_len;
@@ -395,14 +665,13 @@ __global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, con
     uint32_t* sg = stage_all + group * kStageW;
     uint32_t* qs = qstage_all + group * kQStageW;
     RunList* RL = runs_all + group;
-    const uint32_t n_x = (uint32_t)min((int64_t)*E.n_special, O.cap_records);   // slots past the capacity were never written
+    const uint32_t n_x = *E.n_rare;                                     // the records emit_records_kernel left (two edits, many hits, long reads)
     const uint32_t stride = gridDim.x * (kThreads / 32) * 32;
     for (uint32_t jb = (blockIdx.x * (kThreads / 32) + warp) * 32; jb < n_x; jb += stride) {      // warp-uniform
         // ---- lane = record
-        const uint32_t j = jb + lane;
         int cls = -1;
-        if (j < n_x) {
-            const uint4* dp = E.sdesc + 4ull * j;
+        if (jb + lane < n_x) {
+            const uint4* dp = E.sdesc + 4ull * E.rare_list[jb + lane];
             const uint4 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
             const uint32_t kind = (d0.z >> 16) & 15u;                    // 0: the slot of a session that did not fit
             const int L = (int)(d0.z & 0xffffu);

@@ -198,6 +198,10 @@ int ga_engine_create(int device, ga_engine** out) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_mid, kResolveMid, 32 * ga::kMidTeam, sizeof(ga::SmemM));
     if (e->occ_mid < 1) e->occ_mid = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_res, ga::resolve_kernel, ga::kResThreads, sizeof(ga::SmemR));
+    cudaFuncSetAttribute(ga::emit_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ga::RecWarp) * ga::kRecWarps));
+    cudaFuncSetAttribute(ga::emit_records_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_rec, ga::emit_records_kernel, 32 * ga::kRecWarps, sizeof(ga::RecWarp) * ga::kRecWarps);
+    if (e->occ_rec < 1) e->occ_rec = 1;
     if (const char* v = getenv("GA_OCC_SCAN")) e->occ_scan = std::min(e->occ_scan, std::max(1, atoi(v)));   // tuning knob: CTAs per SM of the scan kernel
     if (e->occ_scan < 1) e->occ_scan = 1;
     if (e->occ_lean < 1) e->occ_lean = 1;
@@ -220,7 +224,7 @@ void ga_engine_destroy(ga_engine* e) {
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_join) cudaEventDestroy(L.ev_join);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_many); cudaFree(L.d_many_recs); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); cudaFree(L.d_many); cudaFree(L.d_many_recs); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) if (L.ev[j][k]) cudaEventDestroy(L.ev[j][k]);
     }
     delete e;
@@ -280,11 +284,12 @@ static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
 
 static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int64_t n_sessions) {
     if (cap_records > L.cap_kind) {
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); L.d_kind = nullptr; L.d_edesc = nullptr; L.d_special = nullptr; L.cap_kind = 0;
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); L.d_kind = nullptr; L.d_edesc = nullptr; L.d_special = nullptr; L.d_rare_list = nullptr; L.cap_kind = 0;
         const int64_t cap = cap_records + cap_records / 8 + 1024;
         GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
         GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
         GA_CUDA(cudaMalloc(&L.d_special, (size_t)cap * 4 * sizeof(uint4)));
+        GA_CUDA(cudaMalloc(&L.d_rare_list, (size_t)cap * sizeof(uint32_t)));
         cudaFree(L.d_many); cudaFree(L.d_many_recs); L.d_many = nullptr; L.d_many_recs = nullptr; L.cap_many = 0;
         const int64_t cap_many = std::min<int64_t>(std::max<int64_t>(1 << 16, cap / 4), 1 << 26);   // edit lists of reads with more than two germline indels
         GA_CUDA(cudaMalloc(&L.d_many, (size_t)cap_many * sizeof(uint4)));
@@ -430,6 +435,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     E.sdesc = reinterpret_cast<uint4*>(L.d_special); E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
     E.many = reinterpret_cast<uint4*>(L.d_many); E.n_many = reinterpret_cast<uint32_t*>(L.d_small + 15); E.cap_many = (uint32_t)L.cap_many;
     E.many_recs = L.d_many_recs; E.n_many_recs = reinterpret_cast<uint32_t*>(L.d_small + 16); E.n_kind1 = reinterpret_cast<uint32_t*>(L.d_small + 17); E.ticket_large = reinterpret_cast<unsigned int*>(L.d_small + 18); E.ticket_lean = reinterpret_cast<unsigned int*>(L.d_small + 19);
+    E.n_rare = reinterpret_cast<uint32_t*>(L.d_small + 22); E.rare_list = L.d_rare_list;
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;
@@ -465,11 +471,12 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     GA_CUDA(cudaEventRecord(L.ev_join, L.side));
     // stage 3: record bodies
     ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);
+    ga::emit_records_kernel<<<e->n_sm * e->occ_rec, 32 * ga::kRecWarps, sizeof(ga::RecWarp) * ga::kRecWarps, st>>>(B, O, E);
     ga::emit_special_kernel<<<e->n_sm * 4, ga::kThreads, ga::kEmitSpecialSmem, st>>>(B, L.d_descs, O, E);
     GA_CUDA(cudaEventRecord(L.ev[3][tslot], st));
     GA_CUDA(cudaStreamWaitEvent(st, L.ev_join, 0));
     GA_CUDA(cudaEventRecord(L.ev[4][tslot], st));
-    e->launches += 9;
+    e->launches += 10;
     GA_CUDA(cudaGetLastError());
     return GA_OK;
 }

@@ -48,6 +48,8 @@ struct EmitScratch2 {
     uint32_t* n_kind1;   // records left to emit_kernel (long clean reads); zero lets that kernel return at once
     unsigned int* ticket_large;   // next entry of large_list for the one-CTA resolve kernel
     unsigned int* ticket_lean;    // next session of the one-warp resolve kernel
+    uint32_t* n_rare;             // special records that emit_records_kernel leaves to emit_special_kernel (two edits, many hits, reads beyond 160 bases)
+    uint32_t* rare_list;          // [cap_records] their slots in sdesc
 };
 
 // Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked
