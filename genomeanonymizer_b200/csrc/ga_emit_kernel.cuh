@@ -654,7 +654,7 @@ static_assert(SF_GERMN + 1 == kSpecFields, "field count");
 constexpr int kSpecClasses = 5;         // 0 SNV-only, 1 one edit, 2 two edits, 3 many hits, 4 long reads
 struct SpecWarp { uint32_t f[kSpecFields][32]; uint8_t order[kSpecClasses][32]; };
 
-__global__ void __launch_bounds__(kThreads) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
+__global__ void __launch_bounds__(kThreads, 4) emit_special_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
     extern __shared__ __align__(16) uint8_t emit_smem[];
     SpecWarp* tabs = reinterpret_cast<SpecWarp*>(emit_smem);
     uint32_t* stage_all = reinterpret_cast<uint32_t*>(tabs + kThreads / 32);
