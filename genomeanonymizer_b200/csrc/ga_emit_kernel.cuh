@@ -340,7 +340,7 @@ __device__ __forceinline__ void emit_two_edit_quad(const BatchView& B, const Res
 }
 
 // ------------------------------------------------------------------ LANE = RECORD
-// emit_records_kernel writes the common special records - reads up to 160 bases with another CIGAR and SNV hits only
+// emit_records_kernel writes the common special records - reads up to 156 bases with another CIGAR and SNV hits only
 // (kind 2) or with ONE germline indel (kind 3) - with ONE LANE PER RECORD.  Eight lanes per record (emit_special_kernel,
 // round 1) repeat every scalar step of a record eight times and leave a third of the lanes idle in the word loops; a
 // lane of its own runs the whole record as straight-line arithmetic, and the 32 records of a warp step differ only in
@@ -355,12 +355,13 @@ __device__ __forceinline__ void emit_two_edit_quad(const BatchView& B, const Res
 //      [0, p) = source as is, [p, ins_end) = re-inserted reference bases with quality floor(mean) (DEL only),
 //      [ins_end, new_len) = source shifted (anonymizer_methods.py:178-203; no edit: one piece) - and every output word is
 //      merged from them by masks, four words per 128-bit store; qualities in printed (= BAM) order (quirks Q1, Q2).
-constexpr int kRecMaxL = 160;            // bases of a read handled here (longer: emit_special_kernel)
+constexpr int kRecMaxL = 156;            // bases of a read handled here (longer: emit_special_kernel)
 constexpr int kRecSeqW = 23;             // row: [0] zero pad (source index -8 .. -1), [1, 21) record words, [21, 23) zero
-constexpr int kRecQualW = 43;            // row: [0] zero pad, [1, 41) quality words, [41, 43) zero
+constexpr int kRecQualW = 41;            // row: [0] zero pad, [1, 40) quality words, [40, 41) zero
 constexpr int kRecWarps = 4;
 struct RecWarp { uint32_t guard0[8]; uint32_t seq[32][kRecSeqW]; uint32_t guard1[8]; uint32_t qual[32][kRecQualW]; uint32_t guard2[8]; };   // guards: a shifted row pointer may reach a few words outside its row (values unused)
 static_assert(kRecSeqW % 2 == 1 && kRecQualW % 2 == 1, "rows of odd word stride");
+static_assert(kRecQualW == 32 + (32 - kRecSeqW) && 4 * (kRecQualW - 2) >= kRecMaxL && 8 * (kRecSeqW - 3) >= kRecMaxL, "two copies per lane stage a record");
 
 __device__ __forceinline__ uint32_t rec_stage_at(const uint32_t* row, int sidx) {      // 8 staged bases from source index sidx (any value)
     const int s = min(max(sidx, -8), 8 * (kRecSeqW - 2) - 1);
@@ -453,20 +454,22 @@ __global__ void __launch_bounds__(32 * kRecWarps) emit_records_kernel(BatchView 
             if (!((live >> t) & 1u)) continue;
             const uint32_t t_so = __shfl_sync(0xffffffffu, so, t), t_qu = __shfl_sync(0xffffffffu, qunit, t);
             const int t_L = __shfl_sync(0xffffffffu, L, t), t_cls = __shfl_sync(0xffffffffu, cls, t);
-            {
-                const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * t_so);
+            const uint32_t* rec = reinterpret_cast<const uint32_t*>(B.seq4 + 16ull * t_so);
+            const uint32_t* qrec = reinterpret_cast<const uint32_t*>(B.qual + 32ull * t_qu);
+            // two copies per lane: lanes 0-22 the sequence row and lanes 23-31 the tail of the quality row, then its first 32 words
+            if (lane < kRecSeqW) {
                 const int w = lane - 1;
                 const bool data = w >= 0 && 8 * w < t_L;
-                if (lane < kRecSeqW) cp_async4(&W.seq[t][lane], rec + (data ? w : 0), data ? 4u : 0u);
+                cp_async4(&W.seq[t][lane], rec + (data ? w : 0), data ? 4u : 0u);
+            } else if (t_cls == 1) {
+                const int jq = lane + (32 - kRecSeqW), w = jq - 1;        // 32 .. 40
+                const bool data = 4 * w < t_L;
+                cp_async4(&W.qual[t][jq], qrec + (data ? w : 0), data ? 4u : 0u);
             }
             if (t_cls == 1) {
-                const uint32_t* qrec = reinterpret_cast<const uint32_t*>(B.qual + 32ull * t_qu);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int jq = lane + 32 * h, w = jq - 1;
-                    const bool data = w >= 0 && 4 * w < t_L;
-                    if (jq < kRecQualW) cp_async4(&W.qual[t][jq], qrec + (data ? w : 0), data ? 4u : 0u);
-                }
+                const int w = lane - 1;
+                const bool data = w >= 0 && 4 * w < t_L;
+                cp_async4(&W.qual[t][lane], qrec + (data ? w : 0), data ? 4u : 0u);
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(32 * kRecWarps) emit_records_kernel(BatchView 
             uint32_t sum = 0u;
             if (is_del) {
 #pragma unroll 8
-                for (int w = 0; w < kRecQualW - 3; ++w) sum += __vsadu4(qq[1 + w] & low_bytes_bf(L - 4 * w), 0u);
+                for (int w = 0; w < kRecQualW - 2; ++w) sum += __vsadu4(qq[1 + w] & low_bytes_bf(L - 4 * w), 0u);
             }
             mean4 = (is_del && L ? sum / (uint32_t)L : 0u) * 0x01010101u;
         }

@@ -54,6 +54,10 @@ RANDOM_CASES = [
     dict(seed=106, contig_len=4000, n_pairs=(100, 0), read_len=100),                                   # no normal reads
     dict(seed=107, contig_len=12000, n_pairs=(900, 900), read_len=250, snp_rate=5e-3, indel_rate=1e-3,
          somatic_positions=[3000, 6000, 9000], max_indel=20),
+    # read lengths around the limits of the emission kernels (156 bases: lane per record; 248: staged by a lane group)
+    dict(seed=108, contig_len=7000, n_pairs=(300, 300), read_len=156, snp_rate=3e-3, indel_rate=3e-3, clip_frac=0.3),
+    dict(seed=109, contig_len=7000, n_pairs=(300, 300), read_len=158, snp_rate=3e-3, indel_rate=3e-3, clip_frac=0.3),
+    dict(seed=110, contig_len=8000, n_pairs=(250, 250), read_len=200, snp_rate=3e-3, indel_rate=3e-3, clip_frac=0.3, max_indel=12),
 ]
 
 
