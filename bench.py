@@ -633,7 +633,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "kernel": "masking pass = scan_kernel + resolve_lean_kernel + resolve_kernel + emit_kernel + emit_special_kernel (|| emit_many_kernel, session_kernel<fallback>)", "kernel_ms": pass_ms,
+                "kernel": "masking pass = scan_kernel + resolve_warp_kernel<lean> + resolve_warp_kernel<mid, four-warp teams> + resolve_kernel + emit_kernel + emit_records_kernel + emit_special_kernel (|| emit_many_kernel, session_kernel<fallback>)", "kernel_ms": pass_ms,
                 "stage_ms": {"scan_kernel": stage_ms[0], "resolve_kernels": stage_ms[1], "emit_kernel": stage_ms[2],
                              "fallback_kernel_tail": stage_ms[3]},
                 # the dominant kernel on its own: its algorithmic bytes are the inputs, read once
@@ -837,7 +837,7 @@ def main():
         strong["parity_across_n"] = strong["parity_records"] + " (every GPU count is compared with the same oracle digest of the whole genome)"
     others = {}
     if args.others == "auto":
-        names = ["cigar-stress", "dense-60x30x", "noisy-60x30x", "chr22-1k"] if world == 1 else ["dense-60x30x", "cigar-stress"] + (["wgs-60x30x"] if world >= 4 else [])
+        names = ["cigar-stress", "cigar-stress-100m", "dense-60x30x", "noisy-60x30x", "chr22-1k"] if world == 1 else ["dense-60x30x", "cigar-stress", "cigar-stress-100m"] + (["wgs-60x30x"] if world >= 4 else [])
     else:
         names = [x for x in args.others.split(",") if x and x != "none"]
     if not args.windows:

@@ -92,6 +92,8 @@ GENOME_LEN = sum(n for _, n in HUMAN_CONTIGS)
 GENOMES = {
     "wgs-30x": ("chr1-30x-50k", round(50_000 * GENOME_LEN / 248_956_422)),
     "wgs-60x30x": ("dense-60x30x", 1_000_000),
+    # BASELINE config 3 at its stated size: the CIGAR-stress read model, 100 M session reads (116,600 windows over the genome)
+    "cigar-stress-100m": ("cigar-stress", 116_600),
 }
 
 
