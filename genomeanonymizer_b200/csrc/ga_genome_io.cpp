@@ -413,6 +413,12 @@ static inline RecView view_of(const uint8_t* p) {
     return v;
 }
 static inline uint32_t units_of(uint32_t l_seq) { const uint32_t u = (l_seq + 31u) / 32u; return u ? u : 1u; }
+// A CIGAR of more than 65,535 ops lives in the CG:B,I tag; its place holds "<l_seq>S<reference span>N" (SAM v1.6 4.2.2).
+static inline bool cigar_in_cg_tag(const RecView& v) {
+    if (v.n_cigar != 2 || v.l_seq == 0) return false;
+    const uint32_t c0 = le32(v.cigar), c1 = le32(v.cigar + 4);
+    return (c0 & 15u) == 4u && (c0 >> 4) == v.l_seq && (c1 & 15u) == 3u;
+}
 
 int ga_bam_contig_sizes(const ga_bam* b, int ref_id, uint32_t flag_exclude, ga_bam_sizes* out) {
     if (!b || !out || ref_id < 0 || ref_id >= (int)b->by_ref.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_contig_sizes: bad argument");
@@ -427,6 +433,8 @@ int ga_bam_contig_sizes(const ga_bam* b, int ref_id, uint32_t flag_exclude, ga_b
         if (v.flag & flag_exclude) continue;
         if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
         const uint32_t block_size = le32(p - 4);
+        if (32ull + v.l_name + 4ull * v.n_cigar <= block_size && cigar_in_cg_tag(v))
+            return fail(GA_IO_ERR_UNSUPPORTED, "a record keeps its CIGAR in the CG tag (more than 65535 ops): not supported");
         if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > block_size)
             return fail(GA_IO_ERR_FORMAT, "alignment record fields exceed its block size");
         s.n_reads++;
@@ -458,6 +466,7 @@ int ga_bam_pack_contig(const ga_bam* b, int ref_id, uint32_t flag_exclude, const
         if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
         if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > le32(b->data.data() + recs[k] - 4))
             return fail(GA_IO_ERR_FORMAT, "alignment record fields exceed its block size");
+        if (cigar_in_cg_tag(v)) return fail(GA_IO_ERR_UNSUPPORTED, "a record keeps its CIGAR in the CG tag (more than 65535 ops): not supported");
         dst->seq_off16[k] = (uint32_t)u;
         dst->cigar_off[k] = (uint32_t)c;
         if (dst->name_off) dst->name_off[k] = nm;

@@ -289,3 +289,103 @@ def test_entry_point_refuses_supplementary_records(tmp_path, flag):
     from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import _refuse_unsupported_records
     import numpy as np
     _refuse_unsupported_records(np.array([(0x100 | 0x1 | 0x40) << 16 | 150, (0x4 | 0x1 | 0x80) << 16 | 150], np.uint32), "c")
+
+
+# ------------------------------------------------------------------------------------- format conformance (CPU)
+def _spec_bam_record(ref_id, pos, mapq, flag, name, cigar_ops, seq, qual, aux=b"", next_ref=-1, next_pos=-1, tlen=0, bin_=None):
+    """One BAM alignment record laid out field by field from SAM v1.6 section 4.2 (written separately from
+    tests/helpers.bam_record on purpose): block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq,
+    next_refID, next_pos, tlen, read_name, cigar, seq (high nibble first), qual, auxiliary fields."""
+    import struct
+    rn = name.encode() + b"\0"
+    cig = b"".join(struct.pack("<I", (n << 4) | "MIDNSHP=X".index(op)) for n, op in cigar_ops)
+    codes = ["=ACMGRSVTWYHKDBN".index(c) for c in seq]
+    sq = bytes(((codes[k] << 4) | (codes[k + 1] if k + 1 < len(codes) else 0)) for k in range(0, len(codes), 2))
+    span = sum(n for n, op in cigar_ops if op in "MDN=X")
+    if bin_ is None:
+        bin_ = H._reg2bin(pos, pos + max(span, 1))
+    body = struct.pack("<iiBBHHHIiii", ref_id, pos, len(rn), mapq, bin_, len(cigar_ops), flag, len(seq), next_ref, next_pos, tlen)
+    body += rn + cig + sq + bytes(qual) + aux
+    return struct.pack("<I", len(body)) + body
+
+
+def _gzip_member(data: bytes, level=6, extra_before=b"", extra_after=b"") -> bytes:
+    """A BGZF member: gzip header with FEXTRA, the BC subfield (total member size - 1) among other subfields."""
+    import struct, zlib
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    cdata = co.compress(data) + co.flush()
+    xlen = len(extra_before) + 6 + len(extra_after)
+    bsize = 12 + xlen + len(cdata) + 8
+    extra = extra_before + b"BC" + struct.pack("<HH", 2, bsize - 1) + extra_after
+    return (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", xlen) + extra + cdata +
+            struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+
+def test_bam_features_htslib_writes_are_read(tmp_path):
+    """Auxiliary fields of every type behind the qualities, mate fields, bin 0, '*' qualities (0xff), other gzip extra
+    subfields beside BC, an empty member in mid-file, stored (level 0) members, records and header cut anywhere by
+    member boundaries, @PG / @RG / @CO header lines: none of it may change what the reader hands to the engine."""
+    import struct
+    rng = np.random.default_rng(5)
+    reads = []
+    for k in range(60):
+        L = int(rng.integers(30, 120))
+        seq = "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, L))
+        shape = k % 4
+        if shape == 0: ops = [(L, "M")]
+        elif shape == 1: ops = [(5, "S"), (L - 5, "M")]
+        elif shape == 2: ops = [(10, "M"), (3, "I"), (L - 13, "M")]
+        else: ops = [(3, "H"), (12, "="), (4, "D"), (L - 12, "X"), (2, "H")]
+        reads.append(dict(name=f"r{k:03d}/x", flag=[99, 147, 83, 163, 1024 + 99][k % 5], pos=100 + 7 * k, ops=ops, seq=seq,
+                          qual=[0xff] * L if k % 7 == 3 else [int(q) for q in rng.integers(2, 41, L)]))
+    aux_all = (b"NMC\x03" + b"MDZ10A5^AC6\0" + b"RGZgrp1\0" + b"XSc\xfe" + b"XTs" + struct.pack("<h", -300) + b"XUS" + struct.pack("<H", 60000) +
+               b"XIi" + struct.pack("<i", -70000) + b"XVI" + struct.pack("<I", 4000000000) + b"XFf" + struct.pack("<f", 1.5) + b"XAA!" +
+               b"XHH1AE301\0" + b"XBBc" + struct.pack("<I", 3) + b"\x01\x02\xff" + b"XCBS" + struct.pack("<I", 2) + struct.pack("<HH", 1, 65535) +
+               b"XDBf" + struct.pack("<I", 1) + struct.pack("<f", 2.25) + b"XEBi" + struct.pack("<I", 0))
+    text = ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:ctgA\tLN:5000\tM5:abc\n@SQ\tSN:ctgB\tLN:300\n@RG\tID:grp1\tSM:s\n"
+            "@PG\tID:bwa\tPN:bwa\tCL:bwa mem -Y x y\n@CO\tfree text\twith tabs\n")
+    stream = bytearray(b"BAM\1" + struct.pack("<I", len(text)) + text.encode() + struct.pack("<I", 2))
+    for nm, ln in (("ctgA", 5000), ("ctgB", 300)):
+        stream += struct.pack("<I", len(nm) + 1) + nm.encode() + b"\0" + struct.pack("<I", ln)
+    for k, r in enumerate(reads):
+        stream += _spec_bam_record(0, r["pos"], 255 if k % 3 else 0, r["flag"], r["name"], r["ops"], r["seq"], r["qual"],
+                                   aux=aux_all if k % 2 else b"", next_ref=0 if k % 2 else -1, next_pos=r["pos"] + 200, tlen=(-1) ** k * 350,
+                                   bin_=0 if k % 4 == 0 else None)
+    p = str(tmp_path / "spec.bam")
+    with open(p, "wb") as fh:
+        cuts = [0, 7, 64, 65, 900, 901, 2500, 2501, 2502, len(stream) // 2, len(stream) - 3, len(stream)]   # header and records cut anywhere
+        for i, (a, b) in enumerate(zip(cuts, cuts[1:])):
+            fh.write(_gzip_member(bytes(stream[a:b]), level=0 if i % 3 == 0 else 9,
+                                  extra_before=b"RA\x04\x00abcd" if i % 2 else b"", extra_after=b"ZZ\x01\x00q" if i % 4 == 1 else b""))
+            if i == 4:
+                fh.write(_gzip_member(b""))                              # an empty member in mid-file is legal
+        fh.write(H._BAM_EOF)
+    with GF.BamFile(p, 2) as f:
+        assert f.references == ("ctgA", "ctgB") and f.lengths == (5000, 300)
+        assert f.n_records == len(reads)
+        cb = GF.pack_tumor_normal(f, f, "ctgA")
+    as_dict = [dict(name=r["name"], flag=r["flag"], pos=r["pos"], cigar="".join(f"{n}{op}" for n, op in r["ops"]), seq=r["seq"], qual=r["qual"], dataset=0)
+               for r in reads]
+    ref = B.pack_reads(as_dict + [dict(r, dataset=1) for r in as_dict])
+    for k in ARRAYS:
+        assert np.array_equal(getattr(cb.batch, k), getattr(ref, k)), k
+    assert [cb.name(k) for k in range(len(reads))] == [r["name"] for r in reads]
+
+
+def test_bam_without_sequence_and_long_cigar_records(tmp_path):
+    """A record without a stored sequence ('*': l_seq = 0, as secondary alignments have) is a read of length zero; a
+    CIGAR moved to the CG tag (more than 65,535 ops, SAM v1.6 4.2.2) is refused by name, not mis-read."""
+    import struct
+    hdr = bytearray(b"BAM\1" + struct.pack("<I", 0) + struct.pack("<I", 1) + struct.pack("<I", 2) + b"c\0" + struct.pack("<I", 100000))
+    ok = hdr + _spec_bam_record(0, 10, 30, 256, "nosq", [(50, "M")], "", []) + _spec_bam_record(0, 20, 30, 0, "plain", [(4, "M")], "ACGT", [30] * 4)
+    p = str(tmp_path / "nosq.bam")
+    open(p, "wb").write(_gzip_member(bytes(ok)) + H._BAM_EOF)
+    with GF.BamFile(p) as f:
+        rows = GF.pack_tumor_normal(f, f, "c").read_table()
+    assert [(r["name"], r["pos"], r["end"]) for r in rows[:2]] == [("nosq", 10, 60), ("plain", 20, 24)]
+    cg = hdr + _spec_bam_record(0, 10, 30, 0, "long", [(4, "S"), (70000, "N")], "ACGT", [30] * 4,
+                                aux=b"CGBI" + struct.pack("<I", 2) + struct.pack("<II", (2 << 4) | 0, (2 << 4) | 4))
+    open(p, "wb").write(_gzip_member(bytes(cg)) + H._BAM_EOF)
+    with pytest.raises((GF.GenomeFileError, ValueError)):
+        with GF.BamFile(p) as f:
+            GF.pack_tumor_normal(f, f, "c")
