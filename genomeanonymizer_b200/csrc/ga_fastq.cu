@@ -128,7 +128,7 @@ __device__ __forceinline__ void base_chars8(uint32_t cw, uint32_t* ch) {
 // each: every lane first issues all of its loads (at most four sequence words, eight quality words), so that the
 // loads of four records are in flight together, then the characters are produced into the group's shared-memory
 // slice with the alignment of their destination and leave with aligned 128-bit stores.
-__global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const int64_t* __restrict__ text_off, uint8_t* __restrict__ text,
+__global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const int64_t* __restrict__ text_off, uint8_t* __restrict__ text,
                                                            int64_t text_cap, ga_totals* totals) {
     __shared__ __align__(16) uint8_t stage[8][32 / kRenderGroup][kStageBytes];
     const int lane = threadIdx.x & 31, g = lane / kRenderGroup, gl = lane % kRenderGroup;
@@ -181,9 +181,21 @@ __global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const in
             const int total = nl + 2 * L + 8;
             uint8_t* out = text + it.off;
             const int pad = (int)(reinterpret_cast<uintptr_t>(out) & 15u);   // the staged copy has the alignment of its destination
+            // The records of a step usually lie back to back in the text (the layout is a running sum): then the four of
+            // them are staged as ONE span with the alignment of its destination, and only the span's first and last
+            // 16-byte chunk are shared with neighbours - not those of every record.
+            const int64_t off0 = __shfl_sync(0xffffffffu, (unsigned long long)it.off, 0);
+            const int64_t prev_end = __shfl_up_sync(0xffffffffu, (unsigned long long)(it.off + total), kRenderGroup);
+            const bool chained = act && (g == 0 || prev_end == it.off);
+            const bool span = __all_sync(0xffffffffu, chained);
+            const int pad0 = (int)(reinterpret_cast<uintptr_t>(text + off0) & 15u);
+            const int span_len = (int)(__shfl_sync(0xffffffffu, (unsigned long long)(it.off + total), 31) - off0);
             uint8_t* sb = stage[threadIdx.x >> 5][g];
-            uint8_t* sg = sb + pad;
+            uint8_t* sg = span ? stage[threadIdx.x >> 5][0] + pad0 + (int)(it.off - off0) : sb + pad;
             // every load first
+            uint8_t nm[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int c = gl + kRenderGroup * t; nm[t] = (act && c >= 1 && c <= nl) ? it.name[c - 1] : (uint8_t)0; }
             uint32_t sw[4], qv[8];
             const int nw = act ? (L + 7) >> 3 : 0, nq = act ? (L + 3) >> 2 : 0;
             const uint32_t* qw = reinterpret_cast<const uint32_t*>(it.q);
@@ -192,8 +204,13 @@ __global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const in
 #pragma unroll
             for (int t = 0; t < 8; ++t) { const int w = gl + kRenderGroup * t; qv[t] = w < nq ? __ldg(qw + w) : 0u; }
             if (act) {
-                for (int c = gl; c < nl + 4; c += kRenderGroup)
-                    sg[c] = c == 0 ? (uint8_t)'@' : c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int c = gl + kRenderGroup * t;
+                    if (c < nl + 4) sg[c] = c == 0 ? (uint8_t)'@' : c <= nl ? nm[t] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
+                }
+                for (int c = gl + 4 * kRenderGroup; c < nl + 4; c += kRenderGroup)
+                    sg[c] = c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
                 uint8_t* ss = sg + nl + 4;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -226,7 +243,15 @@ __global__ void __launch_bounds__(256) fastq_render_kernel(FastqView V, const in
                 if (gl == 0) sq[L] = (uint8_t)'\n';
             }
             __syncwarp();
-            if (act) {
+            if (span) {                                                   // warp-uniform: the whole warp copies the span
+                const uint8_t* ws = stage[threadIdx.x >> 5][0];
+                uint8_t* gb = text + off0 - pad0;                         // 16-byte aligned
+                const int end = pad0 + span_len;
+                for (int c16 = lane * 16; c16 < end; c16 += 32 * 16) {
+                    if (c16 >= pad0 && c16 + 16 <= end) *reinterpret_cast<uint4*>(gb + c16) = *reinterpret_cast<const uint4*>(ws + c16);
+                    else for (int t = max(c16, pad0); t < min(c16 + 16, end); ++t) gb[t] = ws[t];   // the neighbours' bytes share these chunks
+                }
+            } else if (act) {
                 uint8_t* gb = out - pad;                                  // 16-byte aligned
                 const int end = pad + total;
                 for (int c16 = gl * 16; c16 < end; c16 += kRenderGroup * 16) {
