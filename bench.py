@@ -216,7 +216,7 @@ def bench_bam_decode(n_reads=400_000, read_len=150):
             "reads_per_s": n_reads / (best_open + best_pack), "inflated_gbs": len(stream) / (best_open + best_pack) / 1e9}
 
 
-def bench_file_path(device_index, n_pairs=20000):
+def bench_file_path(device_index, n_pairs=100000):
     """Level (iii) of SURVEY.md 8(d): tumor / normal BAM + VCF + FASTA -> the reference's FASTQ and statistics files through
     run_short_read_tumor_normal_anonymizer (C++ readers, native plan, one masking pass, device FASTQ text).  The sample is
     a seeded synthetic one written by the test-side BAM / FASTA / VCF writers; the best of four runs is reported."""

@@ -384,7 +384,7 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     hit = (item_ver >= 0) & (at < n)
     hit[hit] = sorted_key[at[hit]] == want[hit]
     item_rec = np.where(hit, by_key[np.minimum(at, max(n - 1, 0))] if n else 0, -1).astype(np.int32)
-    text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n)
+    text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n, as_view=as_bytes)   # as_bytes: slices of the download buffer, no copies
     starts = np.concatenate([[0], np.cumsum([len(g[1]) for g in groups])]).astype(np.int64)
     piece = lambda a, b: text[int(off[a]):int(off[b])]                # records [a, b) of the item list
     out = {}
@@ -402,7 +402,7 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
                 r = int(rows[k, 1])
                 nm = bytes(blob[int(noff[r]):int(noff[r + 1])])
                 m = 0 if int(flags[r]) & 0x40 else 1
-                rec = piece(starts[g] + k, starts[g] + k + 1)
+                rec = bytes(piece(starts[g] + k, starts[g] + k + 1))  # outlives the download buffer
                 held = carry.get(nm)
                 if held is None:
                     carry[nm] = (m, d, rec)
@@ -421,10 +421,10 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
                     parts.append(t1 if m == 0 else t2)
                     cur = k
                 parts.append(piece(starts[g] + cur, starts[g + 1]))
-                out[groups[g][0]] = b"".join(parts)
+                out[groups[g][0]] = parts[0] if len(parts) == 1 else (parts if as_bytes else b"".join(parts))   # a list: written piece by piece
             out[groups[4 + d][0]] = b""
     if not as_bytes:
-        out = {k: v.decode("ascii") for k, v in out.items()}
+        out = {k: bytes(v).decode("ascii") for k, v in out.items()}
     counts = dres.sess_counts.view(-1, 4)[:sessions.n_sessions].cpu().numpy()
     out["statistics"] = statistics_text(contig, plan, counts)
     out["_plan"] = plan

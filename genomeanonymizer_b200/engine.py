@@ -189,13 +189,21 @@ class Engine:
         R, S, O = dbatch.as_struct(), dsess.as_struct(), dres.as_struct()
         self._check(self._L.ga_run(self._h, C.byref(R), C.byref(S), C.byref(O), s))
 
-    def render_fastq(self, dbatch: DeviceBatch, names, reads_idx, records_idx=None, dres: "DeviceResult" = None, n_records: int = 0):
+    def _pinned_text(self, n_bytes: int):
+        """A pinned host buffer of at least n_bytes for rendered text; it only grows (page-locking is slow)."""
+        buf = getattr(self, "_text_buf", None)
+        if buf is None or buf.numel() < n_bytes:
+            self._text_buf = buf = torch.empty(max(n_bytes + n_bytes // 4, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        return buf
+
+    def render_fastq(self, dbatch: DeviceBatch, names, reads_idx, records_idx=None, dres: "DeviceResult" = None, n_records: int = 0, as_view: bool = False):
         """FASTQ text of reads `reads_idx` (ga_fastq_layout + ga_fastq_render on the device).
 
         names: query name of every read of the batch (list of str).  records_idx[k] >= 0 renders read reads_idx[k]
         with the sequence / length / qualities of modified record records_idx[k] of `dres` (the reference prints the
         masked read, anonymizer_methods.py:205-243); -1 renders the read as it came in.
-        Returns (text: bytes, offsets: np.ndarray[int64] of n+1 entries)."""
+        Returns (text: bytes, offsets: np.ndarray[int64] of n+1 entries).  as_view: the text is a memoryview of the engine's
+        pinned download buffer instead (no copy; valid until the next call) - what the file writer appends to its files."""
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream(self.device).cuda_stream
             n = len(reads_idx)
@@ -229,6 +237,10 @@ class Engine:
             t = _abi.GaTotals.from_buffer_copy(status.cpu().numpy().tobytes())
             if t.error:
                 _abi.raise_for_status(int(t.error), f"ga_fastq_render failed at item {t.error_detail}")
+            if as_view:
+                host = self._pinned_text(total)
+                host[:total].copy_(t_text[:total])                    # synchronous for the host (pinned target, blocking copy)
+                return memoryview(host.numpy())[:total], t_off.cpu().numpy()
             return t_text[:total].cpu().numpy().tobytes(), t_off.cpu().numpy()
 
     def check_device_status(self, dres: DeviceResult) -> _abi.GaTotals:

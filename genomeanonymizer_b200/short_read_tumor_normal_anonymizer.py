@@ -59,33 +59,53 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
     fasta = GF.FastaFile(ref_genome_file)
     outs = {("T", "1"): tumor_output_fastq + ".1.fastq", ("T", "2"): tumor_output_fastq + ".2.fastq",
             ("N", "1"): normal_output_fastq + ".1.fastq", ("N", "2"): normal_output_fastq + ".2.fastq"}
-    handles = {k: open(p, "wb") for k, p in outs.items()}      # truncated first, as the reference does (:652-655)
+    handles = {k: open(p, "wb", buffering=0) for k, p in outs.items()}      # truncated first, as the reference does (:652-655); unbuffered: whole slices are written
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(5)                               # the four files are written side by side (write() releases the GIL); one thread prepares the next contig
+
+    def _append(handle, data):
+        for part in (data if isinstance(data, list) else [data]):
+            view = memoryview(part)
+            while len(view):                                   # a raw write may be short
+                view = view[handle.write(view):]
     carry = {}                                                 # to_pair_anonymized_reads (:646): unpaired reads, kept across contigs
     stats_parts = []
     n_reads = n_sessions = 0
     try:
-        with GF.BamFile(tumor_bam_file, cpus) as tumor, GF.BamFile(normal_bam_file, cpus) as normal:
-            for contig_id, contig in enumerate(fasta.references):
+        opened = list(pool.map(lambda f: GF.BamFile(f, cpus), (tumor_bam_file, normal_bam_file)))    # both files inflate side by side
+        with opened[0] as tumor, opened[1] as normal:
+            def prepare(contig_id):
+                """Decode, pack and plan one contig (native code, no GIL): runs one contig ahead of the masking."""
+                contig = fasta.references[contig_id]
                 windows = windows_by_contig.get(contig, [])
                 cb = GF.pack_tumor_normal(tumor, normal, contig, contig_id=contig_id)
                 if cb.batch.n_reads == 0 and not windows:
-                    continue
+                    return None
                 _refuse_unsupported_records(cb.batch.len_flag, contig)
                 reference = fasta.fetch_bytes(contig)
                 plan = GF.plan_contig(cb, windows, len(reference))          # include/ga_plan.h: no per-read Python object
+                return contig, windows, cb, reference, plan
+
+            n_contigs = len(fasta.references)
+            ahead = pool.submit(prepare, 0) if n_contigs else None
+            for contig_id in range(n_contigs):
+                ready = ahead.result()
+                ahead = pool.submit(prepare, contig_id + 1) if contig_id + 1 < n_contigs else None
+                if ready is None:
+                    continue
+                contig, windows, cb, reference, plan = ready
                 if cb.batch.n_reads == 0:
                     stats_parts.append((contig, plan, [[0, 0, 0, 0]] * len(plan.sessions)))
                     continue
                 got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan, as_bytes=True, carry=carry)
-                for p in "TN":
-                    handles[(p, "1")].write(got[f"{p}.1"])
-                    handles[(p, "2")].write(got[f"{p}.2"])
+                list(pool.map(lambda k: _append(handles[k], got[f"{k[0]}.{k[1]}"]), list(handles)))   # done before the next contig reuses the buffer
                 stats_parts.append((contig, plan, got["_counts"]))
                 n_reads += cb.batch.n_reads
                 n_sessions += len(plan.sessions)
     finally:
         for h in handles.values():
             h.close()
+        pool.shutdown()
         fasta.close()
     if carry:                                                      # write_single_end_reads opens both files (:603-605)
         with open(tumor_output_fastq + ".single_end.fastq", "wb") as t, open(normal_output_fastq + ".single_end.fastq", "wb") as n:
