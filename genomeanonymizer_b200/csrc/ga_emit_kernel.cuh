@@ -669,11 +669,15 @@ __global__ void __launch_bounds__(kThreads, 4) emit_special_kernel(BatchView B, 
     uint32_t* qs = qstage_all + group * kQStageW;
     RunList* RL = runs_all + group;
     const uint32_t n_x = *E.n_rare;                                     // the records emit_records_kernel left (two edits, many hits, long reads)
-    const uint32_t stride = gridDim.x * (kThreads / 32) * 32;
-    for (uint32_t jb = (blockIdx.x * (kThreads / 32) + warp) * 32; jb < n_x; jb += stride) {      // warp-uniform
+    // records per warp step: 32, or fewer when there are only a few records (then every warp takes one short step instead
+    // of a few warps walking eight groups of four one after the other)
+    const uint32_t warps_total = gridDim.x * (kThreads / 32);
+    const uint32_t per_warp = min(32u, max(4u, ((n_x + warps_total - 1u) / warps_total + 3u) & ~3u));
+    const uint32_t stride = warps_total * per_warp;
+    for (uint32_t jb = (blockIdx.x * (kThreads / 32) + warp) * per_warp; jb < n_x; jb += stride) {      // warp-uniform
         // ---- lane = record
         int cls = -1;
-        if (jb + lane < n_x) {
+        if ((uint32_t)lane < per_warp && jb + lane < n_x) {
             const uint4* dp = E.sdesc + 4ull * E.rare_list[jb + lane];
             const uint4 d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3];
             const uint32_t kind = (d0.z >> 16) & 15u;                    // 0: the slot of a session that did not fit
