@@ -130,7 +130,12 @@ __device__ __forceinline__ int clamp_edits2(Ed2& E, int L) {
 
 // Germline indel edits of modified read k when there are at most two; false otherwise.  Same ordering and
 // clamping rules as collect_edits.
+template <class SM> __device__ __forceinline__ bool collect2_at(int col_begin, const SM* sm, int k, int L, Ed2& E, int* new_len);
 template <class SM> __device__ __forceinline__ bool collect2(const SessCtx& c, const SM* sm, int k, int L, Ed2& E, int* new_len) {
+    return collect2_at(c.d.col_begin, sm, k, L, E, new_len);
+}
+// (the session context stays out of the signature: a caller that reaches this through a call does not have to keep it in memory)
+template <class SM> __device__ __forceinline__ bool collect2_at(int col_begin, const SM* sm, int k, int L, Ed2& E, int* new_len) {
     const int oa = sm->mhead[k];
     const int ob = oa >= 0 ? (int)sm->o_rnext[oa] : -1;
     if (ob >= 0 && sm->o_rnext[ob] >= 0) return false;
@@ -146,7 +151,7 @@ template <class SM> __device__ __forceinline__ bool collect2(const SessCtx& c, c
         const bool has = o[q] >= 0;
         const uint32_t m = has ? sm->o_meta[o[q]] : kMetaIns;
         E.irp[q] = has ? sm->o_irp[o[q]] : 0; E.len[q] = has ? (int)(m & kMetaLenMask) : 0;
-        E.pos[q] = has ? sm->o_col[o[q]] + c.d.col_begin : 0; E.mean[q] = 0u;
+        E.pos[q] = has ? sm->o_col[o[q]] + col_begin : 0; E.mean[q] = 0u;
         if (has && !(m & kMetaIns)) ++E.n_del;
     }
     const int cur = clamp_edits2(E, L);

@@ -559,7 +559,7 @@ __device__ __noinline__ bool long_allele_tail_equal(const SessCtx& c, uint32_t r
 }
 
 // collect2 behind a call: the lean kernel needs it twice and must stay small enough for the instruction cache
-template <class SM> __device__ __noinline__ bool lean_collect(const SessCtx& c, const SM* sm, int k, int L, Ed2& E, int* new_len) { return collect2(c, sm, k, L, E, new_len); }
+template <class SM> __device__ __noinline__ bool lean_collect(int col_begin, const SM* sm, int k, int L, Ed2& E, int* new_len) { return collect2_at(col_begin, sm, k, L, E, new_len); }
 
 // kFromList: the sessions are the entries of in_list (what the lean instantiation handed over) instead of 0 .. n_sessions - 1.
 // kTeam: warps that work on one session together.  1 = every warp of the CTA has its own session and its own tables
@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 if ((sm->indelbits[i >> 5] >> (i & 31)) & 1u) {
                     Ed2 E2;
                     kind = 3u;
-                    if (!lean_collect(c, sm, (int)k, L0, E2, &new_len)) {  // more than two edits: the edit list travels in the side buffer (kind 5)
+                    if (!lean_collect(c.d.col_begin, sm, (int)k, L0, E2, &new_len)) {  // more than two edits: the edit list travels in the side buffer (kind 5)
                         kind = 5u;
                         if (!reserve_many(E, c, sm, (int)k, L0, &new_len)) slow = true;   // no room, or more edits than the pipeline takes
                     }
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 const uint32_t qidx = (uint32_t)(i < c.nt ? c.d.qt_begin : c.d.qn_begin) + qord;
                 if (kind == 3u) {
                     Ed2 E2; int nl = 0;
-                    lean_collect(c, sm, (int)k, (int)L0, E2, &nl);
+                    lean_collect(c.d.col_begin, sm, (int)k, (int)L0, E2, &nl);
                     dst[0] = make_uint4((uint32_t)E2.irp[0], (uint32_t)E2.pos[0], (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u), (uint32_t)E2.irp[1]);
                     dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u),
                                         (uint32_t)E2.ne | ((uint32_t)E2.n_del << 8), qidx);
