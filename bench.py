@@ -218,33 +218,59 @@ def bench_bam_decode(n_reads=400_000, read_len=150):
 
 def bench_file_path(device_index, n_pairs=100000):
     """Level (iii) of SURVEY.md 8(d): tumor / normal BAM + VCF + FASTA -> the reference's FASTQ and statistics files through
-    run_short_read_tumor_normal_anonymizer (C++ readers, native plan, one masking pass, device FASTQ text).  The sample is
-    a seeded synthetic one written by the test-side BAM / FASTA / VCF writers; the best of four runs is reported."""
+    run_short_read_tumor_normal_anonymizer (C++ readers, native plan, one masking pass per contig, device FASTQ text).  The
+    samples are seeded synthetic ones written by the test-side BAM / FASTA / VCF writers: one contig with all the reads,
+    and the same number of reads over four contigs (the entry point prepares contig k+1 while contig k is masked and
+    written); the best of four runs each is reported."""
     import shutil, tempfile
     from genomeanonymizer_b200 import synth
     from genomeanonymizer_b200.engine import Engine
     from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import run_short_read_tumor_normal_anonymizer
     from tests import helpers as H
     eng = Engine(device_index)                                           # its own engine: the sample brings its own reference
-    contig_len = 150 * 2 * n_pairs // 30                                 # ~30x per dataset
-    case = synth.make_case(seed=9, contig_len=contig_len, n_pairs=(n_pairs, n_pairs), read_len=150,
-                           somatic_positions=list(range(3000, contig_len - 3000, 4000)))
-    tmp = tempfile.mkdtemp(prefix="ga_files_")
-    try:
-        vcf = [[case["contig"], w["keep"]["pos"] + 1, w["keep"]["pos"] + 1, 1, "N", w["keep"]["allele"], "SNV"] for w in case["windows"]]
-        t, n, fa, vc = H.write_sample_files(tmp, case, vcf)
-        best = 1e9
+
+    def case_of(seed, pairs):
+        contig_len = 150 * 2 * pairs // 30                               # ~30x per dataset
+        return synth.make_case(seed=seed, contig_len=contig_len, n_pairs=(pairs, pairs), read_len=150,
+                               somatic_positions=list(range(3000, contig_len - 3000, 4000)))
+
+    def timed(tmp, t, n, fa, vc):
+        best, res = 1e9, None
         for _ in range(4):
             t0 = time.perf_counter()
             res = run_short_read_tumor_normal_anonymizer([vc], [(t, n)], fa, eng, [(os.path.join(tmp, "T.out"), os.path.join(tmp, "N.out"))], True, 0, False)
             best = min(best, time.perf_counter() - t0)
         out_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.endswith(".fastq"))
-        return {"api": "run_short_read_tumor_normal_anonymizer (BAM + VCF + FASTA -> FASTQ + statistics files)", "reads": res[0]["reads"],
-                "sessions": res[0]["sessions"], "ms": best * 1e3, "reads_per_s": res[0]["reads"] / best, "fastq_bytes": out_bytes,
-                "host_threads": os.cpu_count()}
+        return {"reads": res[0]["reads"], "sessions": res[0]["sessions"], "ms": best * 1e3, "reads_per_s": res[0]["reads"] / best, "fastq_bytes": out_bytes}
+
+    tmp = tempfile.mkdtemp(prefix="ga_files_")
+    tmp4 = tempfile.mkdtemp(prefix="ga_files4_")
+    try:
+        case = case_of(9, n_pairs)
+        vcf = [[case["contig"], w["keep"]["pos"] + 1, w["keep"]["pos"] + 1, 1, "N", w["keep"]["allele"], "SNV"] for w in case["windows"]]
+        one = timed(tmp, *H.write_sample_files(tmp, case, vcf))
+        del case
+        # four contigs, a quarter of the reads each
+        cases = [case_of(11 + k, n_pairs // 4) for k in range(4)]
+        names = [f"ctg{k}" for k in range(4)]
+        contigs = [(names[k], len(c["reference"])) for k, c in enumerate(cases)]
+        reads = [dict(r, contig=names[k], name=f"k{k}_{r['name']}") for k, c in enumerate(cases) for r in c["reads"]]
+        t, n = os.path.join(tmp4, "T.bam"), os.path.join(tmp4, "N.bam")
+        H.write_bam(t, contigs, [r for r in reads if r["dataset"] == 0])
+        H.write_bam(n, contigs, [r for r in reads if r["dataset"] == 1])
+        fa, vc = os.path.join(tmp4, "ref.fa"), os.path.join(tmp4, "somatic.vcf")
+        H.write_fasta(fa, [(names[k], c["reference"]) for k, c in enumerate(cases)])
+        H.write_vcf(vc, [[names[k], w["keep"]["pos"] + 1, w["keep"]["pos"] + 1, 1, "N", w["keep"]["allele"], "SNV"] for k, c in enumerate(cases) for w in c["windows"]])
+        del reads
+        four = timed(tmp4, t, n, fa, vc)
+        out = {"api": "run_short_read_tumor_normal_anonymizer (BAM + VCF + FASTA -> FASTQ + statistics files)"}
+        out.update(one)
+        out.update({"host_threads": os.cpu_count(), "sample": "one contig", "four_contigs": four})
+        return out
     finally:
         eng.close()
         shutil.rmtree(tmp, ignore_errors=True)
+        shutil.rmtree(tmp4, ignore_errors=True)
 
 
 def bench_fastq(eng, cfg, dev, n_w, peak):
