@@ -359,7 +359,13 @@ constexpr int kRecMaxL = 156;            // bases of a read handled here (longer
 constexpr int kRecSeqW = 23;             // row: [0] zero pad (source index -8 .. -1), [1, 21) record words, [21, 23) zero
 constexpr int kRecQualW = 41;            // row: [0] zero pad, [1, 40) quality words, [40, 41) zero
 constexpr int kRecWarps = 4;
-struct RecWarp { uint32_t guard0[8]; uint32_t seq[32][kRecSeqW]; uint32_t guard1[8]; uint32_t qual[32][kRecQualW]; uint32_t guard2[8]; };   // guards: a shifted row pointer may reach a few words outside its row (values unused)
+constexpr int kRecMaxEdit = 32;          // longest germline indel handled here: bounds how far a shifted row pointer reaches outside its row
+constexpr int kRecMaxNew = 188;          // longest record written here (six 32-base units)
+// guards: a shifted row pointer reaches at most 4 (bases) / 8 (qualities) words in front of its row and, in the last unit of
+// the longest record, 6 / 16 words behind it; the values read there are never used, the addresses must exist
+struct RecWarp { uint32_t guard0[16]; uint32_t seq[32][kRecSeqW]; uint32_t guard1[16]; uint32_t qual[32][kRecQualW]; uint32_t guard2[24]; };
+static_assert(kRecMaxEdit / 8 <= 16 && 1 + kRecMaxEdit / 8 + 4 * ((kRecMaxNew + 31) / 32) + 1 - kRecSeqW <= 16, "sequence rows: reach of a shifted pointer");
+static_assert(kRecMaxEdit / 4 <= 16 && 1 + kRecMaxEdit / 4 + 8 * ((kRecMaxNew + 31) / 32) + 1 - kRecQualW <= 24, "quality rows: reach of a shifted pointer");
 static_assert(kRecSeqW % 2 == 1 && kRecQualW % 2 == 1, "rows of odd word stride");
 static_assert(kRecQualW == 32 + (32 - kRecSeqW) && 4 * (kRecQualW - 2) >= kRecMaxL && 8 * (kRecSeqW - 3) >= kRecMaxL, "two copies per lane stage a record");
 
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(32 * kRecWarps) emit_records_kernel(BatchView 
             else if (kind == 3u) {
                 const uint4* ap = reinterpret_cast<const uint4*>(O.out_qual + 32ull * qual16);
                 const uint4 x0 = ap[0], x1 = ap[1];                      // EditAux written by the resolve kernel
-                if ((x1.z & 0xffu) != 1u) rare = true;                   // two edits: the run-list form of emit_special_kernel
+                if ((x1.z & 0xffu) != 1u || (x0.z & 0x7fffffffu) > (uint32_t)kRecMaxEdit || new_len > kRecMaxNew) rare = true;   // two edits, or an edit beyond the rows' guards: emit_special_kernel
                 else {
                     Ed2 Ed; Ed.ne = 1; Ed.n_del = (int)((x1.z >> 8) & 0xffu);
                     Ed.irp[0] = (int)x0.x; Ed.pos[0] = (int)x0.y; Ed.len[0] = (int)(x0.z & 0x7fffffffu);

@@ -58,6 +58,8 @@ RANDOM_CASES = [
     dict(seed=108, contig_len=7000, n_pairs=(300, 300), read_len=156, snp_rate=3e-3, indel_rate=3e-3, clip_frac=0.3),
     dict(seed=109, contig_len=7000, n_pairs=(300, 300), read_len=158, snp_rate=3e-3, indel_rate=3e-3, clip_frac=0.3),
     dict(seed=110, contig_len=8000, n_pairs=(250, 250), read_len=200, snp_rate=3e-3, indel_rate=3e-3, clip_frac=0.3, max_indel=12),
+    # germline indels longer than the lane-per-record kernel takes (32 bases) and records longer than its rows (188)
+    dict(seed=111, contig_len=7000, n_pairs=(300, 300), read_len=150, snp_rate=2e-3, indel_rate=2e-3, clip_frac=0.2, max_indel=60),
 ]
 
 
