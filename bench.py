@@ -866,7 +866,7 @@ def main():
         strong["parity_across_n"] = strong["parity_records"] + " (every GPU count is compared with the same oracle digest of the whole genome)"
     others = {}
     if args.others == "auto":
-        names = ["cigar-stress", "cigar-stress-100m", "dense-60x30x", "noisy-60x30x", "chr22-1k"] if world == 1 else ["dense-60x30x", "cigar-stress", "cigar-stress-100m"] + (["wgs-60x30x"] if world >= 4 else [])
+        names = ["cigar-stress", "cigar-stress-100m", "dense-60x30x", "noisy-60x30x", "varied-depth", "chr22-1k"] if world == 1 else ["dense-60x30x", "cigar-stress", "cigar-stress-100m"] + (["wgs-60x30x"] if world >= 4 else [])
     else:
         names = [x for x in args.others.split(",") if x and x != "none"]
     if not args.windows:

@@ -63,7 +63,7 @@ class GaDigestIds(C.Structure):
 class GaSynthParams(C.Structure):
     _fields_ = [("contig_len", C.c_int64), ("seed", C.c_uint64), ("read_len", C.c_int32),
                 ("total_windows", C.c_int32), ("window_begin", C.c_int32), ("n_windows", C.c_int32),
-                ("window_half", C.c_int32), ("max_indel", C.c_int32), ("max_clip", C.c_int32), ("reserved", C.c_int32),
+                ("window_half", C.c_int32), ("max_indel", C.c_int32), ("max_clip", C.c_int32), ("depth_var_pct", C.c_int32),
                 ("cov_tumor", C.c_float), ("cov_normal", C.c_float),
                 ("snp_rate", C.c_float), ("indel_rate", C.c_float), ("err_rate", C.c_float),
                 ("n_rate", C.c_float), ("somatic_vaf", C.c_float), ("clip_frac", C.c_float)]

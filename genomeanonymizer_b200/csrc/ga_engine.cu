@@ -132,7 +132,7 @@ __global__ void clear_kernel(ga_totals* totals, int32_t* n_big, unsigned int* ti
 
 // the two instantiations of the one-warp resolve kernel (ga_resolve_kernel.cuh)
 static const auto kResolveLean = ga::resolve_warp_kernel<ga::kReadsL, ga::kModL, ga::kObsL, ga::kEntL, ga::kLeanWarps, 11, false, 1>;
-static const auto kResolveMid = ga::resolve_warp_kernel<ga::kReadsL, ga::kModM, ga::kObsM, ga::kEntM, ga::kMidTeam, 6, true, ga::kMidTeam>;
+static const auto kResolveMid = ga::resolve_warp_kernel<ga::kReadsM, ga::kModM, ga::kObsM, ga::kEntM, ga::kMidTeam, 7, true, ga::kMidTeam>;
 
 int ga_fail(ga_engine* e, int code, const char* what, cudaError_t ce) {
     if (e) {

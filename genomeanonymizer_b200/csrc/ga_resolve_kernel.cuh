@@ -515,6 +515,7 @@ constexpr int kEntL = 512;               // candidate entries per session
 // "Mid" instantiation of the same kernel: the sessions of an indel-dense workload (hundreds of indel observations and
 // modified reads per session) stay with the one-warp formulation instead of the barrier-bound one-CTA kernel; it walks
 // the list the lean instantiation handed over and lists what it cannot hold for the one-CTA kernel.
+constexpr int kReadsM = 4096;             // candidate reads per session in the mid instantiation (12 bits of an entry)
 constexpr int kModM = 512;
 constexpr int kObsM = 512;
 constexpr int kEntM = 768;
@@ -545,7 +546,7 @@ struct SmemLT {
 };
 constexpr int kMidTeam = 4;              // warps that share one session in the mid instantiation
 using SmemL = SmemLT<kReadsL, kModL, kObsL, kEntL, 4>;
-using SmemM = SmemLT<kReadsL, kModM, kObsM, kEntM, kModM / 32>;
+using SmemM = SmemLT<kReadsM, kModM, kObsM, kEntM, kModM / 32>;
 static_assert(sizeof(SmemL) % 16 == 0 && sizeof(SmemM) % 16 == 0, "per-warp slices stay 16-byte aligned");
 
 // Alleles longer than the 16-base signature (rare): the bases behind it are compared from the records.
@@ -811,23 +812,27 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
         tsync();
         if constexpr (!kSolo) { cnt_del = sm->cnt_del; cnt_ins = sm->cnt_ins; }
         const uint32_t ngerm = sm->ngerm, cnt_snv = ngerm;
-        // ---- ordered list of the modified reads (two bitmap words per lane of the team's first warp)
+        // ---- ordered list of the modified reads (the bitmap words are scanned by the team's first warp)
         uint32_t n_mod = 0u;
         if (tw == 0) {
-            const uint32_t b0 = lane < n_cw ? sm->modbits[lane] : 0u, b1 = lane + 32 < n_cw ? sm->modbits[lane + 32] : 0u;
-            uint32_t t0, t1;
-            uint32_t off0 = warp_excl_scan(__popc(b0), lane, &t0);
-            uint32_t off1 = t0 + warp_excl_scan(__popc(b1), lane, &t1);
-            n_mod = t0 + t1;
-            if (lane < n_cw) sm->woff[lane] = off0;
-            if (lane + 32 < n_cw) sm->woff[lane + 32] = off1;
+            constexpr int kWPL = (kReadsL / 32 + 31) / 32;                // bitmap words per lane: word lane + 32 j
+            uint32_t bw[kWPL], offw[kWPL];
+#pragma unroll
+            for (int j = 0; j < kWPL; ++j) {
+                const int idx = lane + 32 * j;
+                bw[j] = idx < n_cw ? sm->modbits[idx] : 0u;
+                uint32_t t;
+                offw[j] = n_mod + warp_excl_scan(__popc(bw[j]), lane, &t);
+                n_mod += t;
+                if (idx < n_cw) sm->woff[idx] = offw[j];
+            }
             if (n_mod <= (uint32_t)kModL) {
-                uint32_t b = b0;
+#pragma unroll
+                for (int j = 0; j < kWPL; ++j) {
+                    uint32_t b = bw[j], o = offw[j];
 #pragma unroll 1
-                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off0++] = (uint16_t)(lane * 32 + k); }
-                b = b1;
-#pragma unroll 1
-                while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[off1++] = (uint16_t)((lane + 32) * 32 + k); }
+                    while (b) { const int k = __ffs(b) - 1; b &= b - 1; sm->clist[o++] = (uint16_t)((lane + 32 * j) * 32 + k); }
+                }
             }
             if constexpr (!kSolo) { if (lane == 0) sm->n_mod = n_mod; }
         }

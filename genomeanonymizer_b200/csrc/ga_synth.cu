@@ -31,7 +31,7 @@ GS_HD uint64_t h2(uint64_t seed, uint64_t a) { return mix(seed ^ mix(a)); }
 GS_HD uint64_t h3(uint64_t seed, uint64_t a, uint64_t b) { return mix(mix(seed ^ mix(a)) ^ (b * 0xd6e8feb86659fd93ull)); }
 GS_HD float unif(uint64_t h) { return (float)(h >> 40) * (1.0f / 16777216.0f); }
 
-constexpr uint64_t kRef = 0x1001, kGerm = 0x1002, kSom = 0x1003, kWin = 0x1004, kRead = 0x2001, kIns = 0x1005;
+constexpr uint64_t kRef = 0x1001, kGerm = 0x1002, kSom = 0x1003, kWin = 0x1004, kRead = 0x2001, kIns = 0x1005, kDepth = 0x1006;
 
 // base index 0..3 = A C G T
 GS_HD int ref_idx(const ga_synth_params& P, int64_t p) { return (int)(h2(P.seed ^ kRef, (uint64_t)p) & 3u); }
@@ -148,6 +148,10 @@ __host__ __device__ inline int32_t build_read(const ga_synth_params& P, const Ge
     const bool reverse = ((hf >> 1) & 1u) != 0;
     const bool is_r1 = ((hf >> 2) & 1u) != 0;
     *flag_out = 0x1u | 0x2u | (reverse ? 0x10u : 0x20u) | (is_r1 ? 0x40u : 0x80u);
+    if (P.depth_var_pct > 0) {                                           // depth varies from window to window: the reads a window loses stay in the
+        const float keep = 1.0f - 0.01f * (float)P.depth_var_pct * unif(h2(P.seed ^ kDepth, (uint64_t)w * 2u + (uint64_t)ds));   // batch as placed-unmapped records
+        if (unif(h2(rid, 7)) >= keep) *flag_out |= 0x4u;
+    }
     int clip = 0; bool clip_head = false;
     if (unif(h2(rid, 3)) < P.clip_frac) {
         int mc = P.max_clip < L / 3 ? P.max_clip : L / 3;

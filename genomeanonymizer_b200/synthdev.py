@@ -34,13 +34,14 @@ class SynthConfig:
     clip_frac: float = 0.0
     max_indel: int = 10
     max_clip: int = 50
+    depth_var_pct: int = 0          # > 0: every window keeps a uniformly drawn fraction in [1 - v/100, 1] of its reads (the others are flagged 0x4)
 
     def params(self, window_begin: int = 0, n_windows: Optional[int] = None) -> _abi.GaSynthParams:
         p = _abi.GaSynthParams()
         p.contig_len, p.seed, p.read_len = self.contig_len, self.seed, self.read_len
         p.total_windows, p.window_begin = self.total_windows, window_begin
         p.n_windows = self.total_windows - window_begin if n_windows is None else n_windows
-        p.window_half, p.max_indel, p.max_clip, p.reserved = self.window_half, self.max_indel, self.max_clip, 0
+        p.window_half, p.max_indel, p.max_clip, p.depth_var_pct = self.window_half, self.max_indel, self.max_clip, self.depth_var_pct
         p.cov_tumor, p.cov_normal = self.cov_tumor, self.cov_normal
         p.snp_rate, p.indel_rate, p.err_rate, p.n_rate = self.snp_rate, self.indel_rate, self.err_rate, self.n_rate
         p.somatic_vaf, p.clip_frac = self.somatic_vaf, self.clip_frac
@@ -70,10 +71,13 @@ WORKLOADS = {
     # capacity check: a realistic 1 % mismatch rate at 60x / 30x - an order of magnitude more SNV
     # candidates per window than the error model of the other workloads
     "noisy-60x30x": SynthConfig("noisy-60x30x", 62_000_000, 20_000, 60.0, 30.0, err_rate=1e-2),
+    # load imbalance: the depth of a window varies between 6x and 60x per dataset, window by window
+    "varied-depth": SynthConfig("varied-depth", 124_000_000, 40_000, 60.0, 60.0, depth_var_pct=90),
     # small shapes for tests
     "tiny": SynthConfig("tiny", 400_000, 40, 30.0, 30.0, indel_rate=4e-4, clip_frac=0.1),
     "tiny-stress": SynthConfig("tiny-stress", 300_000, 24, 20.0, 25.0, read_len=100, indel_rate=3e-3, clip_frac=0.3,
                                max_indel=16, snp_rate=3e-3),
+    "tiny-varied": SynthConfig("tiny-varied", 400_000, 40, 40.0, 40.0, indel_rate=1e-3, clip_frac=0.1, depth_var_pct=90),
 }
 
 

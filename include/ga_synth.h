@@ -34,7 +34,8 @@ typedef struct ga_synth_params {
     int32_t window_half;        /* 1000 (get_windows window_size/2, SR.py:71)                          */
     int32_t max_indel;          /* germline indel length 1..max_indel                                  */
     int32_t max_clip;           /* soft clip length 1..max_clip                                        */
-    int32_t reserved;
+    int32_t depth_var_pct;      /* 0 = every window at full depth; v > 0: window w of dataset d keeps a fraction drawn uniformly from
+                                 * [1 - v/100, 1] of its reads, the others are flagged unmapped (0x4: placed reads, in no session) */
     float   cov_tumor, cov_normal;
     float   snp_rate, indel_rate, err_rate, n_rate, somatic_vaf;
     float   clip_frac;          /* fraction of reads with a soft clip                                  */

@@ -161,7 +161,7 @@ def _device_run(engine, cfg, w0, nw):
 
 
 SCALE_SLICES = [("tiny", 0, 40), ("tiny-stress", 0, 24), ("chr1-30x-50k", 21000, 2200), ("cigar-stress", 4000, 2000),
-                ("dense-60x30x", 50000, 2048)]
+                ("dense-60x30x", 50000, 2048), ("varied-depth", 17000, 2000)]
 
 
 @pytest.mark.gpu

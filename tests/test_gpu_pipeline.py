@@ -17,7 +17,7 @@ def engine():
     e.close()
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny-stress"])
+@pytest.mark.parametrize("name", ["tiny", "tiny-stress", "tiny-varied"])
 def test_device_generator_equals_host_twin(name):
     import torch
     cfg = SD.WORKLOADS[name]
@@ -35,7 +35,7 @@ def test_device_generator_equals_host_twin(name):
     assert dref == ref
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny-stress"])
+@pytest.mark.parametrize("name", ["tiny", "tiny-stress", "tiny-varied"])
 def test_device_entry_matches_oracle_on_synthetic_workload(engine, name):
     from oracle import oracle
     cfg = SD.WORKLOADS[name]
@@ -47,7 +47,7 @@ def test_device_entry_matches_oracle_on_synthetic_workload(engine, name):
     assert_same_result(got, exp, name)
 
 
-@pytest.mark.parametrize("name,chunk", [("tiny", 0), ("tiny", 1), ("tiny", 7), ("tiny-stress", 5), ("tiny-stress", 24)])
+@pytest.mark.parametrize("name,chunk", [("tiny", 0), ("tiny", 1), ("tiny", 7), ("tiny-stress", 5), ("tiny-stress", 24), ("tiny-varied", 9)])
 def test_host_entry_matches_oracle_for_every_chunking(engine, name, chunk):
     from genomeanonymizer_b200.engine import HostBatch, HostResult
     from oracle import oracle

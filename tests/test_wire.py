@@ -120,7 +120,7 @@ def engine():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,chunk", [("tiny", 0), ("tiny", 1), ("tiny", 7), ("tiny-stress", 5), ("tiny-stress", 24)])
+@pytest.mark.parametrize("name,chunk", [("tiny", 0), ("tiny", 1), ("tiny", 7), ("tiny-stress", 5), ("tiny-stress", 24), ("tiny-varied", 6)])
 def test_wire_entry_matches_oracle_for_every_chunking(engine, name, chunk):
     from genomeanonymizer_b200.engine import HostResult, HostWire
     from oracle import oracle
