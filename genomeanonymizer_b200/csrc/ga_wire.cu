@@ -87,7 +87,7 @@ namespace {
 
 inline size_t align4(size_t n) { return (n + 3) & ~(size_t)3; }
 
-struct BlockPlan { int64_t r0; uint32_t n, n_words, n_gen, n_gen_ops, n_exc, units, ops; uint64_t bytes; };
+struct BlockPlan { int64_t r0; uint32_t n, n_words, n_gen, n_gen_ops, n_exc, units, ops, len_common, n_lenx, n_posx, n_flags; uint16_t fdict[16]; uint64_t bytes; };
 
 inline bool is_generic(const ga_reads* R, int64_t r, uint32_t L) {
     const uint32_t c0 = R->cigar_off[r], c1 = R->cigar_off[r + 1];
@@ -116,11 +116,30 @@ bool cut_blocks(const ga_reads* R, int64_t lo, int64_t hi, std::vector<BlockPlan
     return true;
 }
 
+// The length most reads of the block have (ties: the smaller one); the others are listed as exceptions.
+uint32_t common_length(const ga_reads* R, const BlockPlan& b) {
+    std::vector<uint16_t> ls(b.n);
+    for (uint32_t i = 0; i < b.n; ++i) ls[i] = (uint16_t)(R->len_flag[b.r0 + i] & 0xffffu);
+    std::sort(ls.begin(), ls.end());
+    uint32_t best = ls.empty() ? 0u : ls[0], best_n = 0;
+    for (size_t i = 0; i < ls.size();) {
+        size_t j = i;
+        while (j < ls.size() && ls[j] == ls[i]) ++j;
+        if (j - i > best_n) { best_n = (uint32_t)(j - i); best = ls[i]; }
+        i = j;
+    }
+    return best;
+}
+
 void size_block(const ga_reads* R, BlockPlan& b) {
     b.n_words = b.n_gen = b.n_gen_ops = b.n_exc = b.units = b.ops = 0;
+    b.len_common = common_length(R, b);
+    b.n_lenx = 0;
+    uint64_t n_bases = 0;
     for (int64_t r = b.r0; r < b.r0 + b.n; ++r) {
         const uint32_t L = R->len_flag[r] & 0xffffu;
-        b.n_words += (L + 15u) / 16u;
+        n_bases += L;
+        if (L != b.len_common) ++b.n_lenx;
         b.units += units_of_len(L);
         const uint32_t nops = R->cigar_off[r + 1] - R->cigar_off[r];
         b.ops += nops;
@@ -128,41 +147,66 @@ void size_block(const ga_reads* R, BlockPlan& b) {
         const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
         for (uint32_t q = 0; q < L; ++q) { const uint32_t c = (rec[q >> 1] >> (4 * (q & 1))) & 15u; if (!plain_code(c)) ++b.n_exc; }
     }
-    size_t bytes = 32 + 4 * (size_t)b.n + align4(2 * (size_t)b.n) + align4(2 * (size_t)b.n_gen) + 4 * ((size_t)b.n_gen + 1) + 4 * (size_t)b.n_gen_ops +
-                   4 * (size_t)b.n_exc + 4 * (size_t)b.n_words;
+    b.n_words = (uint32_t)((n_bases + 15) / 16) + 3;                      // three zero words behind: the expansion reads two words ahead of any base
+    // flags: a dictionary of up to 16 values and 4-bit indices when the block has no more distinct flags (the usual case), else 16 bits each
+    b.n_flags = 0; b.n_posx = 0;
+    memset(b.fdict, 0, sizeof b.fdict);
+    bool dict_ok = true;
+    for (int64_t r = b.r0; r < b.r0 + b.n; ++r) {
+        const uint16_t f = (uint16_t)(R->len_flag[r] >> 16);
+        uint32_t k = 0;
+        while (k < b.n_flags && b.fdict[k] != f) ++k;
+        if (k == b.n_flags && dict_ok) { if (b.n_flags < 16) b.fdict[b.n_flags++] = f; else dict_ok = false; }
+        if (r > b.r0 && (int64_t)R->pos[r] - R->pos[r - 1] >= 255) ++b.n_posx;
+    }
+    if (!dict_ok) b.n_flags = 0;
+    const size_t flag_bytes = b.n_flags ? 32 + align4(((size_t)b.n + 1) / 2) : align4(2 * (size_t)b.n);
+    size_t bytes = 32 + flag_bytes + align4((size_t)b.n) + 4 * (size_t)b.n_posx + 4 * (size_t)b.n_lenx + align4(2 * (size_t)b.n_gen) + 4 * ((size_t)b.n_gen + 1) +
+                   4 * (size_t)b.n_gen_ops + 4 * (size_t)b.n_exc + 4 * (size_t)b.n_words;
     b.bytes = (bytes + 15) & ~(size_t)15;
 }
 
 void write_block(const ga_reads* R, const BlockPlan& b, uint8_t* dst) {
     memset(dst, 0, b.bytes);
     uint32_t* hd = reinterpret_cast<uint32_t*>(dst);
-    hd[0] = b.n; hd[1] = b.n_words; hd[2] = b.n_gen; hd[3] = b.n_gen_ops; hd[4] = b.n_exc;
-    uint32_t* lf = reinterpret_cast<uint32_t*>(dst + 32);
-    uint16_t* dpos = reinterpret_cast<uint16_t*>(dst + 32 + 4 * (size_t)b.n);
-    uint16_t* gen_idx = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(dpos) + align4(2 * (size_t)b.n));
+    hd[0] = b.n; hd[1] = b.n_words; hd[2] = b.n_gen; hd[3] = b.n_gen_ops; hd[4] = b.n_exc; hd[5] = b.len_common | (b.n_flags << 16); hd[6] = b.n_lenx; hd[7] = b.n_posx;
+    uint8_t* at_p = dst + 32;
+    uint16_t* fdict = nullptr; uint8_t* fidx = nullptr; uint16_t* flag = nullptr;
+    if (b.n_flags) { fdict = reinterpret_cast<uint16_t*>(at_p); at_p += 32; fidx = at_p; at_p += align4(((size_t)b.n + 1) / 2); memcpy(fdict, b.fdict, 32); }
+    else { flag = reinterpret_cast<uint16_t*>(at_p); at_p += align4(2 * (size_t)b.n); }
+    uint8_t* dpos8 = at_p; at_p += align4((size_t)b.n);
+    uint32_t* posx = reinterpret_cast<uint32_t*>(at_p);
+    uint32_t* lenx = posx + b.n_posx;
+    uint16_t* gen_idx = reinterpret_cast<uint16_t*>(lenx + b.n_lenx);
     uint32_t* gen_off = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(gen_idx) + align4(2 * (size_t)b.n_gen));
     uint32_t* gen_cig = gen_off + b.n_gen + 1;
     uint32_t* exc = gen_cig + b.n_gen_ops;
     uint32_t* bases = exc + b.n_exc;
-    uint32_t ng = 0, ngo = 0, ne = 0, nw = 0;
+    uint32_t npx = 0;
+    uint32_t ng = 0, ngo = 0, ne = 0, nx = 0;
+    uint64_t at = 0;                                                      // bases of the block so far: the reads lie back to back
     for (uint32_t i = 0; i < b.n; ++i) {
         const int64_t r = b.r0 + i;
         const uint32_t L = R->len_flag[r] & 0xffffu;
-        lf[i] = R->len_flag[r];
-        dpos[i] = i ? (uint16_t)(R->pos[r] - R->pos[r - 1]) : (uint16_t)0;
+        const uint16_t f = (uint16_t)(R->len_flag[r] >> 16);
+        if (b.n_flags) { uint32_t k = 0; while (b.fdict[k] != f) ++k; fidx[i >> 1] |= (uint8_t)(k << (4 * (i & 1))); }
+        else flag[i] = f;
+        if (L != b.len_common) lenx[nx++] = (i << 16) | L;
+        const uint32_t dlt = i ? (uint32_t)(R->pos[r] - R->pos[r - 1]) : 0u;
+        dpos8[i] = (uint8_t)(dlt < 255u ? dlt : 255u);
+        if (dlt >= 255u) posx[npx++] = (i << 16) | dlt;
         if (is_generic(R, r, L)) {
             gen_idx[ng] = (uint16_t)i; gen_off[ng] = ngo; ++ng;
             for (uint32_t c = R->cigar_off[r]; c < R->cigar_off[r + 1]; ++c) gen_cig[ngo++] = R->cigar[c];
         }
         const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
-        for (uint32_t q = 0; q < L; ++q) {
+        for (uint32_t q = 0; q < L; ++q, ++at) {
             const uint32_t c = (rec[q >> 1] >> (4 * (q & 1))) & 15u;
             uint32_t two = 0;
             if (c == 2u) two = 1; else if (c == 4u) two = 2; else if (c == 8u) two = 3;
             else if (c != 1u) exc[ne++] = (i << 20) | (q << 4) | c;
-            bases[nw + (q >> 4)] |= two << (2 * (q & 15));
+            bases[at >> 4] |= two << (2 * (at & 15));
         }
-        nw += (L + 15u) / 16u;
     }
     gen_off[ng] = ngo;
 }
@@ -260,6 +304,8 @@ __global__ void __launch_bounds__(kWireThreads) wire_expand_kernel(const uint8_t
         int32_t* __restrict__ pos, uint32_t* __restrict__ len_flag, uint32_t* __restrict__ seq_off16, uint32_t* __restrict__ cigar_off,
         uint32_t* __restrict__ cigar, uint8_t* __restrict__ seq4) {
     __shared__ int16_t s_gen[GA_WIRE_BLOCK_READS];
+    __shared__ uint16_t s_len[GA_WIRE_BLOCK_READS];
+    __shared__ uint16_t s_dpos[GA_WIRE_BLOCK_READS];
     __shared__ uint32_t s_seqoff[GA_WIRE_BLOCK_READS];
     __shared__ uint32_t s_part[4][kWireThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -270,18 +316,25 @@ __global__ void __launch_bounds__(kWireThreads) wire_expand_kernel(const uint8_t
     const uint32_t u_base = ds ? units_t + (d.unit - unit0_n) : d.unit - unit0_t;
     const uint32_t o_base = ds ? ops_t + (d.ops - ops0_n) : d.ops - ops0_t;
     const uint32_t* hd = reinterpret_cast<const uint32_t*>(blk);
-    const uint32_t n = hd[0], n_gen = hd[2], n_gen_ops = hd[3], n_exc = hd[4];
-    const uint32_t* lf = reinterpret_cast<const uint32_t*>(blk + 32);
-    const uint16_t* dpos = reinterpret_cast<const uint16_t*>(blk + 32 + 4ull * n);
-    const uint16_t* gen_idx = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(dpos) + ((2ull * n + 3) & ~3ull));
+    const uint32_t n = hd[0], n_words = hd[1], n_gen = hd[2], n_gen_ops = hd[3], n_exc = hd[4], len_common = hd[5] & 0xffffu, n_flags = hd[5] >> 16, n_lenx = hd[6], n_posx = hd[7];
+    const uint8_t* at_p = blk + 32;
+    const uint16_t* fdict = nullptr; const uint8_t* fidx = nullptr; const uint16_t* flag = nullptr;
+    if (n_flags) { fdict = reinterpret_cast<const uint16_t*>(at_p); at_p += 32; fidx = at_p; at_p += (((size_t)n + 1) / 2 + 3) & ~(size_t)3; }
+    else { flag = reinterpret_cast<const uint16_t*>(at_p); at_p += (2ull * n + 3) & ~3ull; }
+    const uint8_t* dpos8 = at_p; at_p += ((size_t)n + 3) & ~(size_t)3;
+    const uint32_t* posx = reinterpret_cast<const uint32_t*>(at_p);
+    const uint32_t* lenx = posx + n_posx;
+    const uint16_t* gen_idx = reinterpret_cast<const uint16_t*>(lenx + n_lenx);
     const uint32_t* gen_off = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(gen_idx) + ((2ull * n_gen + 3) & ~3ull));
     const uint32_t* gen_cig = gen_off + n_gen + 1;
     const uint32_t* exc = gen_cig + n_gen_ops;
     const uint32_t* bases = exc + n_exc;
 
-    for (uint32_t i = tid; i < n; i += kWireThreads) s_gen[i] = (int16_t)-1;
+    for (uint32_t i = tid; i < n; i += kWireThreads) { s_gen[i] = (int16_t)-1; s_len[i] = (uint16_t)len_common; s_dpos[i] = (uint16_t)dpos8[i]; }
     __syncthreads();
     for (uint32_t j = tid; j < n_gen; j += kWireThreads) s_gen[gen_idx[j]] = (int16_t)j;
+    for (uint32_t j = tid; j < n_lenx; j += kWireThreads) { const uint32_t x = lenx[j]; s_len[x >> 16] = (uint16_t)(x & 0xffffu); }
+    for (uint32_t j = tid; j < n_posx; j += kWireThreads) { const uint32_t x = posx[j]; s_dpos[x >> 16] = (uint16_t)(x & 0xffffu); }
     __syncthreads();
 
     // per-thread: kWirePer consecutive reads
@@ -290,10 +343,12 @@ __global__ void __launch_bounds__(kWireThreads) wire_expand_kernel(const uint8_t
 #pragma unroll
     for (int k = 0; k < kWirePer; ++k) {
         const uint32_t i = (uint32_t)tid * kWirePer + k;
-        lfk[k] = i < n ? lf[i] : 0u; Lk[k] = lfk[k] & 0xffffu; dp[k] = i < n ? (uint32_t)dpos[i] : 0u;
+        Lk[k] = i < n ? (uint32_t)s_len[i] : 0u; dp[k] = i < n ? (uint32_t)s_dpos[i] : 0u;
+        lfk[k] = 0u;
+        if (i < n) lfk[k] = ((uint32_t)(n_flags ? fdict[(fidx[i >> 1] >> (4 * (i & 1))) & 15u] : flag[i]) << 16) | Lk[k];
         nops[k] = 0u;
         if (i < n) { const int j = s_gen[i]; nops[k] = j >= 0 ? gen_off[j + 1] - gen_off[j] : 1u; }
-        su += i < n ? (Lk[k] ? (Lk[k] + 31u) >> 5 : 1u) : 0u; so += nops[k]; sw += i < n ? (Lk[k] + 15u) >> 4 : 0u; sp += dp[k];
+        su += i < n ? (Lk[k] ? (Lk[k] + 31u) >> 5 : 1u) : 0u; so += nops[k]; sw += Lk[k]; sp += dp[k];     // sw: bases (the reads lie back to back in bases2)
     }
     // block-wide exclusive scans of the four per-thread sums
     uint32_t v[4] = {su, so, sw, sp}, ex[4];
@@ -321,15 +376,18 @@ __global__ void __launch_bounds__(kWireThreads) wire_expand_kernel(const uint8_t
         const int j = s_gen[i];
         if (j < 0) cigar[o] = L << 4;                                    // one M op spanning the read
         else { const uint32_t g0 = gen_off[j]; for (uint32_t c = 0; c < nops[k]; ++c) cigar[o + c] = gen_cig[g0 + c]; }
-        const uint32_t nu = L ? (L + 31u) >> 5 : 1u, nw = (L + 15u) >> 4;
+        const uint32_t nu = L ? (L + 31u) >> 5 : 1u;
         uint4* dst = reinterpret_cast<uint4*>(seq4 + 16ull * u);
+        const uint32_t sh = (w & 15u) * 2u;                              // the read starts anywhere in a word of 16 bases
         for (uint32_t q = 0; q < nu; ++q) {
-            const uint32_t w0 = 2 * q < nw ? bases[w + 2 * q] : 0u, w1 = 2 * q + 1 < nw ? bases[w + 2 * q + 1] : 0u;
-            const int left = (int)L - 32 * (int)q;
+            const uint32_t i0 = min((w + 32u * q) >> 4, n_words - 3u);    // (zero words close the stream)
+            const uint32_t a = bases[i0], b1 = bases[i0 + 1], c = bases[i0 + 2];
+            const uint32_t w0 = __funnelshift_r(a, b1, sh), w1 = __funnelshift_r(b1, c, sh);
+            const int left = (int)L - 32 * (int)q;                       // bases behind the read belong to the next one: cut
             dst[q] = make_uint4(keep_nibbles(wire_nibbles(w0), left), keep_nibbles(wire_nibbles(w0 >> 16), left - 8),
                                 keep_nibbles(wire_nibbles(w1), left - 16), keep_nibbles(wire_nibbles(w1 >> 16), left - 24));
         }
-        u += nu; o += nops[k]; w += nw;
+        u += nu; o += nops[k]; w += L;
     }
     if (b == nb_all - 1 && tid == 0) cigar_off[n_all] = ops_all;
     __syncthreads();                                                      // the records of this block are written

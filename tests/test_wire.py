@@ -18,34 +18,51 @@ def decode_wire(w: W.WireBatch):
     al4 = lambda n: (n + 3) & ~3
     for b in range(w.n_blocks):
         o = int(w.dir["byte"][b])
-        n, n_words, n_gen, n_gen_ops, n_exc = (int(x) for x in blob[o:o + 20].view("<u4"))
+        n, n_words, n_gen, n_gen_ops, n_exc, lc_nf, n_lenx, n_posx = (int(x) for x in blob[o:o + 32].view("<u4"))
+        len_common, n_flags = lc_nf & 0xFFFF, lc_nf >> 16
         assert int(w.dir["read"][b]) == len(out) and o % 16 == 0
         p = o + 32
-        lf = blob[p:p + 4 * n].view("<u4"); p += 4 * n
-        dpos = blob[p:p + 2 * n].view("<u2"); p += al4(2 * n)
+        if n_flags:
+            fdict = blob[p:p + 32].view("<u2"); p += 32
+            fidx = blob[p:p + (n + 1) // 2]; p += al4((n + 1) // 2)
+            flag = [int(fdict[(int(fidx[i >> 1]) >> (4 * (i & 1))) & 15]) for i in range(n)]
+            assert n_flags <= 16 and len(set(flag)) == n_flags
+        else:
+            flag = [int(x) for x in blob[p:p + 2 * n].view("<u2")]; p += al4(2 * n)
+            assert len(set(flag)) > 16
+        dpos = [int(x) for x in blob[p:p + n]]; p += al4(n)
+        posx = blob[p:p + 4 * n_posx].view("<u4"); p += 4 * n_posx
+        assert all(d < 255 or i in {int(x) >> 16 for x in posx} for i, d in enumerate(dpos))
+        for x in posx:
+            assert dpos[int(x) >> 16] == 255 and (int(x) & 0xFFFF) >= 255
+            dpos[int(x) >> 16] = int(x) & 0xFFFF
+        lenx = blob[p:p + 4 * n_lenx].view("<u4"); p += 4 * n_lenx
         gen_idx = blob[p:p + 2 * n_gen].view("<u2"); p += al4(2 * n_gen)
         gen_off = blob[p:p + 4 * (n_gen + 1)].view("<u4"); p += 4 * (n_gen + 1)
         gen_cig = blob[p:p + 4 * n_gen_ops].view("<u4"); p += 4 * n_gen_ops
         exc = blob[p:p + 4 * n_exc].view("<u4"); p += 4 * n_exc
         bases = blob[p:p + 4 * n_words].view("<u4"); p += 4 * n_words
-        assert (p + 15) // 16 * 16 == int(w.dir["byte"][b + 1]) - 0 or (p + 15) // 16 * 16 - o == int(w.dir["byte"][b + 1]) - o
+        assert (p + 15) // 16 * 16 - o == int(w.dir["byte"][b + 1]) - o
         gen = {int(i): gen_cig[int(gen_off[j]):int(gen_off[j + 1])] for j, i in enumerate(gen_idx)}
+        lengths = [len_common] * n
+        for x in lenx:
+            lengths[int(x) >> 16] = int(x) & 0xFFFF
+        assert all(int(a) < int(b2) for a, b2 in zip(lenx[:-1] >> 16, lenx[1:] >> 16)) and all(lengths[int(x) >> 16] != len_common for x in lenx)
         patches = {}
         for e in exc:
             patches.setdefault(int(e) >> 20, []).append(((int(e) >> 4) & 0xFFFF, int(e) & 15))
-        pos, wo = int(w.dir["pos"][b]), 0
+        two_all = (np.repeat(bases, 16) >> (2 * np.tile(np.arange(16, dtype=np.uint32), n_words))) & 3      # the block's bases, back to back
+        pos, at = int(w.dir["pos"][b]), 0
         for i in range(n):
-            L = int(lf[i]) & 0xFFFF
+            L = lengths[i]
             pos += int(dpos[i])
-            nw = (L + 15) // 16
-            two = np.repeat(bases[wo:wo + nw], 16) >> (2 * np.tile(np.arange(16, dtype=np.uint32), nw)) & 3
-            codes = (1 << two[:L]).astype(np.uint8)
+            codes = (1 << two_all[at:at + L]).astype(np.uint8)
             for q, c in patches.get(i, []):
                 codes[q] = c
-            wo += nw
+            at += L
             cig = gen[i] if i in gen else np.array([L << 4], np.uint32)
-            out.append((pos, int(lf[i]), cig, codes))
-        assert wo == n_words
+            out.append((pos, (int(flag[i]) << 16) | L, cig, codes))
+        assert n_words == (at + 15) // 16 + 3 and not two_all[at:].any()
     return out
 
 
@@ -65,7 +82,7 @@ def test_packer_round_trips_through_the_documented_format(name):
     b, s, ref = SD.generate_host(SD.WORKLOADS[name], 0, 6)
     w = W.pack_wire(b)
     assert_wire_equals_batch(w, b)
-    assert w.blob.nbytes < 0.6 * (b.seq4.nbytes + 16 * b.n_reads)        # about 41 instead of 100 bytes per 100-150 bp read
+    assert w.blob.nbytes < 0.6 * (b.seq4.nbytes + 16 * b.n_reads)        # about 36 instead of 100 bytes per 100-150 bp read
     assert w.max_ref_span == b.max_ref_span
 
 
@@ -100,6 +117,22 @@ def test_other_base_codes_generic_cigars_and_odd_lengths_survive():
     w = W.pack_wire(b)
     assert_wire_equals_batch(w, b)
     assert w.n_blocks == 2                                                # 500 -> 67000 does not fit 16 bits
+
+
+def test_more_than_sixteen_distinct_flags_and_every_position_step_survive():
+    rng = np.random.default_rng(3)
+    steps = np.concatenate([[0], rng.integers(0, 4, 300), [254, 255, 256, 1000, 65535], rng.integers(0, 600, 200)])
+    pos = np.cumsum(steps)
+    reads = _reads(len(pos), pos, L=37)
+    for k, r in enumerate(reads):
+        r["flag"] = 1 + 2 * (k % 23) + (0x10 if k % 3 else 0x20)          # 40-odd distinct values: the dictionary does not hold them
+    many = B.pack_reads(reads, sparse_qual=True)
+    w = W.pack_wire(many)
+    assert_wire_equals_batch(w, many)
+    for k, r in enumerate(reads):
+        r["flag"] = [99, 147, 83, 163, 1123, 65, 129, 73, 133, 89, 153, 97, 145, 81, 161, 1187][k % 16]      # exactly sixteen: the dictionary is full
+    w = W.pack_wire(B.pack_reads(reads, sparse_qual=True))
+    assert_wire_equals_batch(w, B.pack_reads(reads, sparse_qual=True))
 
 
 def test_unsorted_reads_are_refused():
