@@ -224,10 +224,16 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
                     }
                     uint32_t ch[2];
                     base_chars8(cw, ch);
+                    if (j0 >= 0 && j0 + 8 <= L) {                         // the whole word lies inside the read (all but the last word): no bound per character
+                        uint8_t* sp = ss + j0;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int jj = j0 + u;
-                        if (jj >= 0 && jj < L) ss[jj] = (uint8_t)(ch[u >> 2] >> (8 * (u & 3)));
+                        for (int u = 0; u < 8; ++u) sp[u] = (uint8_t)(ch[u >> 2] >> (8 * (u & 3)));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int jj = j0 + u;
+                            if (jj >= 0 && jj < L) ss[jj] = (uint8_t)(ch[u >> 2] >> (8 * (u & 3)));
+                        }
                     }
                 }
                 if (gl < 3) ss[L + gl] = gl == 1 ? (uint8_t)'+' : (uint8_t)'\n';
@@ -237,8 +243,14 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
                     const int w = gl + kRenderGroup * t;
                     if (w >= nq) break;
                     const uint32_t v = qv[t] + 0x21212121u;               // anonymizer_methods.py:232 (phred <= 93: no carry between bytes)
+                    if (4 * w + 4 <= L) {
+                        uint8_t* sp = sq + 4 * w;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (4 * w + u < L) sq[4 * w + u] = (uint8_t)(v >> (8 * u));
+                        for (int u = 0; u < 4; ++u) sp[u] = (uint8_t)(v >> (8 * u));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (4 * w + u < L) sq[4 * w + u] = (uint8_t)(v >> (8 * u));
+                    }
                 }
                 if (gl == 0) sq[L] = (uint8_t)'\n';
             }
