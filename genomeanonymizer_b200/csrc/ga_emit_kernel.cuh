@@ -304,16 +304,21 @@ __device__ __forceinline__ void emit_two_edit_quad(const BatchView& B, const Res
     const int n_runs = RL->n;
     int units = (new_len + 31) >> 5; if (units < 1) units = 1;
     uint32_t* oseq = reinterpret_cast<uint32_t*>(O.out_seq4 + 16ull * R.seq16);
+    // a lane's words ascend, so it walks the run list once: k = the first run that reaches beyond the word's start
+    int k = 0;
     for (int w = glane; w < units * 4; w += kGroup) {
         const int j0 = w << 3;
         uint32_t v = 0u;
+        while (k < n_runs - 1 && RL->f[k] + RL->len[k] <= j0) ++k;
 #pragma unroll 1
-        for (int k = 0; k < n_runs; ++k) {
-            const int f = RL->f[k];
-            const uint32_t m = low_nibbles_bf(f + RL->len[k] - j0) & ~low_nibbles_bf(f - j0);
-            if (!m) continue;
-            const int at = RL->a[k] + (j0 - f);                          // >= -7 where the mask is set
-            v |= (RL->kind[k] ? ref_word(B.ref4, (int64_t)max(at, -8)) : stage_at(sg, at)) & m;
+        for (int kk = k;; ++kk) {
+            const int f = RL->f[kk], e = f + RL->len[kk];
+            const uint32_t m = low_nibbles_bf(e - j0) & ~low_nibbles_bf(f - j0);
+            if (m) {
+                const int at = RL->a[kk] + (j0 - f);                     // >= -7 where the mask is set
+                v |= (RL->kind[kk] ? ref_word(B.ref4, (int64_t)max(at, -8)) : stage_at(sg, at)) & m;
+            }
+            if (e >= j0 + 8 || kk >= n_runs - 1) break;
         }
         oseq[w] = v & low_nibbles_bf(new_len - j0);
     }
@@ -321,19 +326,29 @@ __device__ __forceinline__ void emit_two_edit_quad(const BatchView& B, const Res
     // 195: quirk Q2), so for a reverse read a run [f, f + len) is printed at [new_len - f - len, new_len - f) and its BAM
     // bytes ascend with the printed index
     uint32_t* oq = reinterpret_cast<uint32_t*>(O.out_qual + 32ull * R.qual16);
+    int kq = 0;                                                           // position in printed order: run kq is run n_runs - 1 - kq of a reverse read
     for (int w = glane; w < units * 8; w += kGroup) {
         const int p0 = w << 2;
         uint32_t v = 0u;
+        auto printed = [&](int kp, int* kf, int* ln) -> int {             // printed start, forward index and length of the kp-th run in printed order
+            *kf = R.reverse ? n_runs - 1 - kp : kp;
+            *ln = RL->len[*kf];
+            return R.reverse ? new_len - RL->f[*kf] - *ln : RL->f[*kf];
+        };
+        int kf, ln;
+        while (kq < n_runs - 1 && printed(kq, &kf, &ln) + ln <= p0) ++kq;
 #pragma unroll 1
-        for (int k = 0; k < n_runs; ++k) {
-            const int ln = RL->len[k], f = R.reverse ? new_len - RL->f[k] - ln : RL->f[k];
-            const uint32_t m = low_bytes_bf(f + ln - p0) & ~low_bytes_bf(f - p0);
-            if (!m) continue;
-            const int kind = RL->kind[k];
-            uint32_t val;
-            if (kind) val = (kind == 1 ? mean0 : mean1) * 0x01010101u;
-            else val = qual_at(qs, p0 + (R.reverse ? L - new_len - RL->a[k] + RL->f[k] : RL->a[k] - RL->f[k]));   // BAM byte of printed byte p0
-            v |= val & m;
+        for (int kk = kq;; ++kk) {
+            const int f = printed(kk, &kf, &ln), e = f + ln;
+            const uint32_t m = low_bytes_bf(e - p0) & ~low_bytes_bf(f - p0);
+            if (m) {
+                const int kind = RL->kind[kf];
+                uint32_t val;
+                if (kind) val = (kind == 1 ? mean0 : mean1) * 0x01010101u;
+                else val = qual_at(qs, p0 + (R.reverse ? L - new_len - RL->a[kf] + RL->f[kf] : RL->a[kf] - RL->f[kf]));   // BAM byte of printed byte p0
+                v |= val & m;
+            }
+            if (e >= p0 + 4 || kk >= n_runs - 1) break;
         }
         oq[w] = v & low_bytes_bf(new_len - p0);
     }
