@@ -24,6 +24,9 @@ constexpr uint32_t kMetaGerm = 1u << 29;
 constexpr uint32_t kMetaRep = 1u << 28;
 constexpr uint32_t kMetaSeenT = 1u << 24;   // on a key's representative observation: a tumor / normal read showed the key
 constexpr uint32_t kMetaSeenN = 1u << 25;
+constexpr uint32_t kMetaCol = 1u << 26;     // on a key's representative: a normal read that shows the key also covers its position
+constexpr uint32_t kMetaTrail = 1u << 27;   // an insertion with no reference-consuming op behind it: it sits at its read's reference_end,
+                                            // a position the read itself does not cover (see normal_covers, ga_session_kernel.cuh)
 constexpr uint32_t kMetaLenMask = (1u << 24) - 1;   // op lengths are below 65,536 (the read length is 16 bits)
 
 // msize word (per candidate read, after analysis)

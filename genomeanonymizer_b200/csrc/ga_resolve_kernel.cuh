@@ -310,13 +310,17 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
                 else for (int j = 0; j < o; ++j) if (sm->o_col[j] == col && obs_equal2(c, sm, o, j)) { rep = j; break; }
             }
             sm->o_rep[o] = (int16_t)rep;
-            atomicOr(&sm->o_meta[rep], (sm->o_meta[o] & kMetaDs) ? kMetaSeenN : kMetaSeenT);
+            {
+                const uint32_t mo = sm->o_meta[o];                        // a normal read that shows the key and covers its position: the normal column exists
+                atomicOr(&sm->o_meta[rep], (mo & kMetaDs) ? (kMetaSeenN | ((mo & kMetaTrail) ? 0u : kMetaCol)) : kMetaSeenT);
+            }
         }
         __syncthreads();
         for (int o = tid; o < n_obs; o += T) {
             const uint32_t m = sm->o_meta[o];
             const int rep = sm->o_rep[o];
             bool germ = (sm->o_meta[rep] & (kMetaSeenT | kMetaSeenN)) == (kMetaSeenT | kMetaSeenN);
+            if (germ && !(sm->o_meta[rep] & kMetaCol)) germ = normal_covers(c, c.first, sm->o_col[o] + c.d.col_begin);   // anonymizer_methods.py:474-481
             if (germ && obs_equals_keep2(c, sm, o)) germ = false;
             if (germ) {
                 atomicOr(&sm->o_meta[o], kMetaGerm | (rep == o ? kMetaRep : 0u));
@@ -529,7 +533,8 @@ struct SmemLT {
     uint8_t mpc[kModL];                  // germline SNV hits per modified read
     uint32_t o_meta[kObsL], o_ra[kObsL]; int32_t o_irp[kObsL], o_col[kObsL], o_rnext[kObsL];
     uint32_t o_key[kObsL];               // hash of (column, type, length, allele): one compare rejects almost every pair
-    uint32_t o_cls[kObsL];               // low 16 bits: the first observation with the same key; bits 16 / 17 (on that one): tumor / normal saw the key
+    uint32_t o_cls[kObsL];               // low 16 bits: the first observation with the same key; bits 16 / 17 (on that one): tumor / normal saw the key;
+                                         // bit 18: a normal read that shows it covers its position
     union {                              // the allele signatures are dead once the observations are compared,
         struct { uint32_t o_s0[kObsL], o_s1[kObsL]; };
         uint16_t clist[kModL];           // ... which is before the list of modified reads is built
@@ -769,15 +774,17 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                 }
             }
             atomicOr(&sm->o_cls[o], (uint32_t)rep);                   // the entry was zeroed; others may be adding their dataset bits to it
-            atomicOr(&sm->o_cls[rep], (o_meta & kMetaDs) ? 0x20000u : 0x10000u);
+            atomicOr(&sm->o_cls[rep], (o_meta & kMetaDs) ? (0x20000u | ((o_meta & kMetaTrail) ? 0u : 0x40000u)) : 0x10000u);   // bit 18: the normal column of the key exists
         }
         tsync();
 #pragma unroll 1
         for (int o = tl; o < n_obs; o += TS) {
             const uint32_t cls = sm->o_cls[o];
             const int rep = (int)(cls & 0xffffu);
-            bool germ = (sm->o_cls[rep] >> 16) == 3u;
+            const uint32_t seen = sm->o_cls[rep] >> 16;
+            bool germ = (seen & 3u) == 3u;
             const uint32_t o_meta = sm->o_meta[o], o_ra = sm->o_ra[o];
+            if (germ && !(seen & 4u)) germ = normal_covers(c, __ldg(S.first + s), sm->o_col[o] + c.d.col_begin);   // only insertions that end their reads: anonymizer_methods.py:474-481
             if (germ) {                                               // variant_to_keep may be this indel
                 const int o_col = sm->o_col[o];
                 const int type = (o_meta & kMetaIns) ? GA_VT_INS : GA_VT_DEL;

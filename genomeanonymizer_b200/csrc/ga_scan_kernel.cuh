@@ -168,6 +168,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
     // ---- indel observations (lane 0; the count stays warp-uniform through the shuffle below)
     if (lane == 0) {
         uint32_t n_obs = c.ws->n_obs;
+        const int span_all = ref_span_of(B.cigar, c0, c1);               // an insertion behind the last aligned base is marked (kMetaTrail)
         int rc = pos, q = 0, ccl = 0, rcb = 0;
         for (uint32_t ci = c0; ci < c1; ++ci) {
             const uint32_t w = __ldg(B.cigar + ci), op = w & 15u;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void scan_generic_read(ItemCtx& c, int i, int64_t r, 
                 q += ln; rc += ln; ccl += ln;
             } else if (op == 1u || op == 2u) {
                 if (n_obs >= (uint32_t)kObsHalf) { c.ws->ovf = 1u; break; }
-                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+                const uint32_t meta = (op == 1u ? kMetaIns | (rc - pos == span_all ? kMetaTrail : 0u) : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
                 const int irp = ccl + rcb;                                // variation_classifier.py:82
                 const int alen = allele_len(meta, irp, L);                // Python-slice clamped (variation_classifier.py:87-88)
                 uint32_t s0 = 0u, s1 = 0u;                                 // signature: the first 16 allele bases
@@ -237,6 +238,7 @@ __device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int 
         if (gl >= d) { sq += tq; sr += tr; sb += tb; }
     }
     const int q0 = sq - q_own, r0 = sr - r_own, b0 = sb - b_own;          // offsets at which this op starts
+    const int g_span = __shfl_sync(0xffffffffu, sr, gbase + 7);          // the read's reference span: an insertion that starts there ends the alignment (kMetaTrail)
     if (aligned && q0 + ln > g_L) raise_error(c.totals, GA_ERR_OFFSET_RANGE, (uint32_t)(c.ws->begin + (g_i - c.ws->i_base)));   // IndexError in variation_classifier.py:148
     // ---- indel observations
     const bool is_id = op == 1u || op == 2u;
@@ -247,7 +249,7 @@ __device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int 
         if (is_id) {
             if (slot >= (uint32_t)kObsHalf) c.ws->ovf = 1u;
             else {
-                const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+                const uint32_t meta = (op == 1u ? kMetaIns | (r0 == g_span ? kMetaTrail : 0u) : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
                 const int irp = r0 + b0;                                  // variation_classifier.py:82
                 const int alen = allele_len(meta, irp, g_L);              // Python-slice clamped (variation_classifier.py:87-88)
                 uint32_t s0 = 0u, s1 = 0u;                                 // signature: the first 16 allele bases
@@ -318,7 +320,7 @@ __device__ __forceinline__ void scan_generic_quad(ItemCtx& c, uint32_t sel, int 
 //     segment are dropped from the mismatch mask, the boundary words are cut to the segment nibble by nibble.
 // A soft-clipped read costs one compare round, a read with one indel two: tens of warp instructions per tile instead of
 // hundreds per read (the 8-lanes-per-read walk, kept for tiles that could not be staged).
-__device__ __forceinline__ void scan_generic_lanes(ItemCtx& c, bool act, int i, int idx, int pos, int L, uint32_t c0, uint32_t n_ops, uint32_t n_id, uint32_t cw0,
+__device__ __forceinline__ void scan_generic_lanes(ItemCtx& c, bool act, int i, int idx, int pos, int L, int span, uint32_t c0, uint32_t n_ops, uint32_t n_id, uint32_t cw0,
                                                    const uint32_t* rec, uint32_t qord, int lane) {
     const BatchView& B = c.B;
     uint32_t tot_id;
@@ -346,7 +348,7 @@ __device__ __forceinline__ void scan_generic_lanes(ItemCtx& c, bool act, int i, 
                 } else if (op == 1u || op == 2u) {                       // indel observation (variation_classifier.py:52-107)
                     if (slot >= (uint32_t)kObsHalf) c.ws->ovf = 1u;
                     else {
-                        const uint32_t meta = (op == 1u ? kMetaIns : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)l & kMetaLenMask);
+                        const uint32_t meta = (op == 1u ? kMetaIns | (rr == span ? kMetaTrail : 0u) : 0u) | ((c.ws->item & 1u) ? kMetaDs : 0u) | ((uint32_t)l & kMetaLenMask);
                         const int irp = rr + bsum;                       // variation_classifier.py:82
                         const int alen = allele_len(meta, irp, L);       // Python-slice clamped (variation_classifier.py:87-88)
                         uint32_t s0 = 0u, s1 = 0u;                        // signature: the first 16 allele bases
@@ -552,7 +554,7 @@ __device__ __forceinline__ void scan_tile_w(ItemCtx& c, int t, int TR, const Til
         // staged tiles: lane = read; tiles that could not be staged (and very long CIGARs / reads): the group and whole-warp walks
         const bool by_lane = work && staged && n_ops <= (uint32_t)kLaneOps && L <= 256;
         if (__any_sync(0xffffffffu, by_lane))
-            scan_generic_lanes(c, by_lane, i, idx, pos, L, m.c0, n_ops, n_id, cw0, reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (by_lane ? m.so - sof : 0u)), qord, lane);
+            scan_generic_lanes(c, by_lane, i, idx, pos, L, span, m.c0, n_ops, n_id, cw0, reinterpret_cast<const uint32_t*>(c.ws->ring[b] + (by_lane ? m.so - sof : 0u)), qord, lane);
         uint32_t m_short = __ballot_sync(0xffffffffu, work && !by_lane && n_ops <= 8u), m_long = __ballot_sync(0xffffffffu, work && !by_lane && n_ops > 8u);
         while (m_short) {                                                // four reads per step, 8 lanes each
             uint32_t sel = 0u;

@@ -101,6 +101,23 @@ __device__ bool obs_equals_keep(const SessCtx& c, int a) {
     return true;
 }
 
+// The reference masks the variants of a position when it reaches the NORMAL pileup column of that position
+// (anonymizer_methods.py:474-481): a key seen in both datasets is masked only if some normal read of the session covers
+// its position.  A read that shows an SNV or a DEL covers it, and so does a read whose insertion is followed by aligned
+// bases; an insertion that ends its read's alignment sits at the read's reference_end, which the read does not cover -
+// then another normal read has to (kMetaTrail / kMetaCol).  This is that test: rare, one thread, the reads in position order.
+__device__ __noinline__ bool normal_covers(const SessCtx& c, int first, int p) {
+    for (int64_t r = c.d.n_begin; r < c.d.n_end; ++r) {
+        const int pos = __ldg(c.B.pos + r);
+        if (pos > p) break;
+        if ((__ldg(c.B.len_flag + r) >> 16) & 0x4u) continue;             // placed-unmapped: in no pileup
+        const int span = ref_span_of(c.B.cigar, __ldg(c.B.cigar_off + r), __ldg(c.B.cigar_off + r + 1));
+        if (pos + span <= first) continue;                                // fetched by range, does not reach the region
+        if (p < pos + span) return true;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------- phase A: one read
 __device__ void discover_read(const SessCtx& c, int i, uint32_t* n_obs, uint32_t* sess_reads, uint32_t* sess_bases) {
     const int64_t r = read_of(c, i);
@@ -136,7 +153,7 @@ __device__ void discover_read(const SessCtx& c, int i, uint32_t* n_obs, uint32_t
             if ((int)slot >= c.T.obs_cap) { raise_error(c.totals, GA_ERR_CAPACITY, (uint32_t)c.s); return; }
             const int col = rc - c.d.col_begin;
             c.T.o_col[slot] = col;
-            c.T.o_meta[slot] = (op == 1u ? kMetaIns : 0u) | (ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
+            c.T.o_meta[slot] = (op == 1u ? kMetaIns | (rc - pos == span ? kMetaTrail : 0u) : 0u) | (ds ? kMetaDs : 0u) | ((uint32_t)ln & kMetaLenMask);
             c.T.o_read[slot] = (uint32_t)i;
             c.T.o_irp[slot] = ccl + rcb;                                  // variation_classifier.py:82
             __threadfence_block();
@@ -491,12 +508,16 @@ __global__ void __launch_bounds__(kThreads) session_kernel(BatchView B, SessView
         for (int o = tid; o < n_obs; o += kThreads) {
             const uint32_t m = c.T.o_meta[o];
             bool germ = false, rep = true;
+            bool col = (m & kMetaDs) && !(m & kMetaTrail);               // a normal read that shows the key covers its position
             for (int o2 = c.T.ihead[c.T.o_col[o]]; o2 >= 0; o2 = c.T.o_next[o2]) {
                 if (o2 == o) continue;
                 if (!obs_equal(c, o, o2)) continue;
-                if ((c.T.o_meta[o2] ^ m) & kMetaDs) germ = true;
+                const uint32_t m2 = c.T.o_meta[o2];
+                if ((m2 ^ m) & kMetaDs) germ = true;
+                if ((m2 & kMetaDs) && !(m2 & kMetaTrail)) col = true;
                 if (o2 < o) rep = false;
             }
+            if (germ && !col) germ = normal_covers(c, c.first, c.T.o_col[o] + c.d.col_begin);   // the normal pileup must have a column there (anonymizer_methods.py:474-481)
             if (germ && obs_equals_keep(c, o)) germ = false;
             if (germ) {
                 atomicOr(&c.T.o_meta[o], kMetaGerm | (rep ? kMetaRep : 0u));

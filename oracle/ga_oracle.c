@@ -20,7 +20,9 @@
  *                variants.py:83-96); each key remembers which datasets showed it (the T/N state
  *                machine variation_classifier.py:163-182 collapses to "seen in T" | "seen in N").
  *   2. germline  keys seen in both datasets, minus the window's variant_to_keep
- *                (anonymizer_methods.py:546-547).
+ *                (anonymizer_methods.py:546-547), at positions the normal pileup has a column for
+ *                (the reference masks a position's variants when it reaches that column,
+ *                anonymizer_methods.py:474-481: matters for an insertion that ends its read).
  *   3. mask      SNV: base <- reference base, quality untouched (anonymizer_methods.py:170-176);
  *                indels: all DELs then all INSs at original, unadjusted offsets
  *                (anonymizer_methods.py:254-270, 178-203), edits literally simulated on arrays.
@@ -87,7 +89,7 @@ typedef struct { rres_t* v; int n, cap; } sres_t;   /* modified reads of one ses
 typedef struct {
     obs_t* obs; int n_obs, cap_obs;
     ikey_t* keys; int n_keys, cap_keys;
-    uint32_t* snv; int* khead; int cap_cols;
+    uint32_t* snv; int* khead; uint8_t* ncov; int cap_cols;   /* ncov[col]: a normal read of the session covers the column */
     uint8_t* sbuf; uint8_t* qbuf; int cap_buf;
 } scratch_t;
 
@@ -166,8 +168,10 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
         W->cap_cols = n_cols * 2;
         W->snv = (uint32_t*)realloc(W->snv, sizeof(uint32_t) * (size_t)W->cap_cols);
         W->khead = (int*)realloc(W->khead, sizeof(int) * (size_t)W->cap_cols);
+        W->ncov = (uint8_t*)realloc(W->ncov, (size_t)W->cap_cols);
     }
     memset(W->snv, 0, sizeof(uint32_t) * (size_t)n_cols);
+    memset(W->ncov, 0, (size_t)n_cols);
     for (int i = 0; i < n_cols; ++i) W->khead[i] = -1;
     W->n_obs = 0; W->n_keys = 0;
 
@@ -181,6 +185,8 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
             *tot_bases += (uint64_t)L;
             const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
             int rc = R->pos[r], q = 0, ccl = 0, rcb = 0;
+            if (d == 1)                                           /* the columns of the normal pileup: [reference_start, reference_end) */
+                for (int p = R->pos[r], e = ref_end_of(R, r); p < e; ++p) W->ncov[p - col_lo] = 1;
             for (uint32_t c = R->cigar_off[r]; c < R->cigar_off[r + 1]; ++c) {
                 int op = (int)(R->cigar[c] & 15), ln = (int)(R->cigar[c] >> 4);
                 if (op == 0 || op == 7 || op == 8) {              /* M = X */
@@ -243,7 +249,9 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
     }
     for (int k = 0; k < W->n_keys; ++k) {
         ikey_t* kk = &W->keys[k];
-        if (kk->mask == 3 && !key_equals_keep(R, S, s, kk, W->obs)) {
+        /* seen in both datasets, and masked when the reference reaches the NORMAL pileup column of the key's position
+         * (AM.py:474-481): only an insertion that ends its read's alignment can sit at a column no normal read covers */
+        if (kk->mask == 3 && W->ncov[kk->pos - col_lo] && !key_equals_keep(R, S, s, kk, W->obs)) {
             kk->germline = 1;
             counts[kk->type == GA_VT_DEL ? 1 : 2]++;
         }
@@ -331,7 +339,7 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
     return GA_OK;
 }
 
-static void free_scratch(scratch_t* W) { free(W->obs); free(W->keys); free(W->snv); free(W->khead); free(W->sbuf); free(W->qbuf); }
+static void free_scratch(scratch_t* W) { free(W->obs); free(W->keys); free(W->snv); free(W->khead); free(W->ncov); free(W->sbuf); free(W->qbuf); }
 
 int ga_oracle_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
