@@ -175,3 +175,33 @@ def write_sample_files(tmp, case, vcf, contig_len=None):
     write_fasta(fa, [(contig, case["reference"])])
     write_vcf(vc, vcf)
     return t, n, fa, vc
+
+
+_TWIST_OPS = _re.compile(r"(\d+)([MIDNSHP=X])")
+
+
+def twist_reads(reads):
+    """Edge shapes the generator never makes, chosen by reference coordinates so that tumor and normal reads agree on them:
+    an insertion as the last / first aligned op, hard clips around the read, a reference skip in the middle of a match."""
+    out = []
+    for r in reads:
+        ops = [(int(n), op) for n, op in _TWIST_OPS.findall(r["cigar"])]
+        seq, qual, pos = r["seq"], list(r["qual"]), r["pos"]
+        end = pos + sum(n for n, op in ops if op in "MDN=X")
+        if ops and ops[-1][1] == "M" and ops[-1][0] > 6 and end % 5 == 0:          # ... kM -> (k-j)M jI : the insertion sits at reference_end
+            j = 1 + end % 3
+            ops[-1:] = [(ops[-1][0] - j, "M"), (j, "I")]
+        elif ops and ops[0][1] == "M" and ops[0][0] > 6 and pos % 7 == 0:          # kM ... -> jI (k-j)M : at reference_start
+            j = 1 + pos % 2
+            ops[:1] = [(j, "I"), (ops[0][0] - j, "M")]
+            pos += j
+        elif len(ops) == 1 and ops[0][1] == "M" and ops[0][0] > 20 and pos % 11 == 0:   # aM bN cM : the bases under the skip leave the read
+            a, b = 8, 3 + pos % 4
+            c = ops[0][0] - a - b
+            ops = [(a, "M"), (b, "N"), (c, "M")]
+            seq, qual = seq[:a] + seq[a + b:], qual[:a] + qual[a + b:]
+        if pos % 3 == 0:
+            ops = [(2, "H")] + ops + [(1, "H")]
+        out.append(dict(r, pos=pos, cigar="".join(f"{n}{op}" for n, op in ops), seq=seq, qual=qual))
+    out.sort(key=lambda r: (r["dataset"], r["pos"]))
+    return out

@@ -249,3 +249,16 @@ def test_records_that_are_not_contiguous_in_seq4_take_the_unstaged_path(engine):
     got = engine.run(scattered, sessions)
     assert_same_result(got, exp, "scattered records")
     assert got.totals["n_modified"] > 0
+
+
+@pytest.mark.gpu
+def test_engine_equals_oracle_on_random_and_twisted_samples():
+    """A slice of tools/fuzz_parity.py (engine through the C ABI against the oracle, random shape parameters, dense and
+    sparse qualities), plain and with trailing / leading insertions, hard clips and reference skips (helpers.twist_reads)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--twist"]):
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "920000", "20"] + extra, capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0 and "20 cases, 0 mismatches" in res.stdout, res.stdout[-600:] + res.stderr[-600:]

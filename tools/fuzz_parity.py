@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised parity: engine (ga_run through the C ABI) against the CPU oracle on many small seeded samples whose shape
 parameters are drawn at random (read length 30-300, indel / clip / SNP / error rates, indel lengths up to 60, coverage,
-window count).  usage: tools/fuzz_parity.py [first seed] [cases]     exit code 1 on the first difference."""
+window count).  usage: tools/fuzz_parity.py [first seed] [cases] [--twist]     exit code 1 when anything differed."""
 import os
 import sys
 
@@ -12,11 +12,12 @@ from genomeanonymizer_b200 import batch as B           # noqa: E402
 from genomeanonymizer_b200 import synth                # noqa: E402
 from genomeanonymizer_b200.engine import Engine        # noqa: E402
 from oracle import oracle                              # noqa: E402
+from tests import helpers as H                         # noqa: E402
 
 
 def main():
     seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 100
     eng = Engine(0)
     bad = 0
     for seed in range(seed0, seed0 + n):
@@ -27,6 +28,8 @@ def main():
                   snp_rate=float(rng.choice([1e-3, 3e-3, 1e-2])), indel_rate=float(rng.choice([0, 1e-4, 1e-3, 4e-3, 1e-2])),
                   clip_frac=float(rng.choice([0, 0.1, 0.5])), max_indel=int(rng.choice([3, 10, 20, 40, 60])))
         case = synth.make_case(**kw)
+        if "--twist" in sys.argv:                                            # trailing / leading insertions, hard clips, reference skips
+            case["reads"] = H.twist_reads(case["reads"])
         reads = [r for r in case["reads"] if r["dataset"] == 0] + [r for r in case["reads"] if r["dataset"] == 1]
         for sparse in (False, True):
             batch = B.pack_reads(reads, sparse_qual=sparse)
