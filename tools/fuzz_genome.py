@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Randomised check of the per-sample orchestration (N2 / N3: sections, island sessions, mate pairing, write-once, placed-
+unmapped mates) against the REFERENCE'S OWN DRIVER (build container only): seeded samples with random coverage, window
+layout, orphans and unmapped mates go through the reference's unmodified anonymize_genome with its own
+CompleteGermlineAnonymizer (under tests/ref_stub) and through driver.plan_sample + the oracle; the seven files must be
+equal.  Two known quirks of the reference are reported separately and do not fail the run: a difference that is only the
+ORDER of the records of a file (Q11 of DESIGN.md: the reference's buffered streams; exact only while a region's pass-through
+text stays below the 8 KiB stream buffer) and bodies of reads whose left-over indels the reference applies twice (Q12).
+usage: tools/fuzz_genome.py [first seed] [cases]"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tests.test_reference_driver as TR             # noqa: E402
+
+
+def records(text):
+    ls = (text or "").split("\n")
+    return sorted("\n".join(ls[k:k + 4]) for k in range(0, len(ls) - 1, 4))
+
+
+def is_q12(mine, gold, reads, plan):
+    """The two files hold the same records in the same order and differ only in the bodies of reads that (a) carry an I / D
+    op, (b) lie in two or more sessions and (c) have a mate that is missing or elsewhere - the reads whose left-over indels
+    the reference applies a second time (quirk Q12 of DESIGN.md: AnonymizedRead.update_anonymized_read_from_other switches
+    has_left_overs_to_mask back on for a read that was masked, parked unpaired and met again in a later session)."""
+    a, b = (mine or "").split("\n"), (gold or "").split("\n")
+    if len(a) != len(b) or a[0::4] != b[0::4]:
+        return False
+    by_name = {}
+    for r in reads:
+        by_name.setdefault((r["name"], 1 if r["flag"] & 0x40 else 2), []).append(r)
+    for k in range(0, len(a) - 1, 4):
+        if a[k:k + 4] == b[k:k + 4]:
+            continue
+        name, mate = a[k][1:].rsplit("/", 1)
+        hit = False
+        for r in by_name.get((name, int(mate)), []):
+            n_sess = sum(1 for ses in plan.sessions if r["pos"] < ses["last"] and r["end"] > ses["first"])
+            if ("I" in r["cigar"] or "D" in r["cigar"]) and n_sess >= 2:
+                hit = True
+        if not hit:
+            return False
+    return True
+
+
+def main():
+    seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    gen = TR.ref_modules.__wrapped__() if hasattr(TR.ref_modules, "__wrapped__") else TR.ref_modules.__pytest_wrapped__.obj()
+    mods = next(gen)
+    from genomeanonymizer_b200 import batch as B
+    from genomeanonymizer_b200 import driver as D
+    from genomeanonymizer_b200 import synth
+    from oracle import fastq as OF
+    from oracle import oracle
+    from src.GenomeAnonymizer.anonymizer_methods import CompleteGermlineAnonymizer
+    from tests import helpers as H
+    from tests.test_genome_files import assemble, with_ends
+    from tests.test_plan_native import unmap_some
+    bad = order_only = q12 = 0
+    for seed in range(seed0, seed0 + n):
+        rng = np.random.default_rng(seed)
+        clen = int(rng.integers(5000, 12000))
+        nwin = int(rng.integers(0, 4))
+        som = sorted(int(x) for x in rng.choice(np.arange(1500, clen - 1500, 50), size=nwin, replace=False)) if nwin else []
+        kw = dict(contig_len=clen, n_pairs=(int(rng.integers(8, 160)), int(rng.integers(8, 160))), read_len=int(rng.choice([50, 80, 100])),
+                  somatic_positions=som, snp_rate=float(rng.choice([1e-3, 4e-3])), indel_rate=float(rng.choice([0, 8e-4, 3e-3])),
+                  clip_frac=float(rng.choice([0, 0.1, 0.4])))
+        case = synth.make_case(seed, name=f"fuzz-{seed}", **kw)
+        reads = [dict(r) for r in case["reads"]]
+        drop = int(rng.choice([0, 0, 5, 9]))
+        if drop:
+            reads = [r for k, r in enumerate(reads) if k % drop != 3]
+        unmap = int(rng.choice([0, 0, 3, 6]))
+        if unmap:
+            reads = unmap_some(reads, unmap)
+        case["reads"] = reads
+        vcf = [["c", w["keep"]["pos"] + 1, w["keep"]["pos"] + 1, 1, case["reference"][w["keep"]["pos"]].upper(), w["keep"]["allele"], "SNV"] for w in case["windows"]]
+        tmp = tempfile.mkdtemp(prefix="ga_fuzz_")
+        try:
+            gold = TR.run_reference_driver(mods, [case], vcf, CompleteGermlineAnonymizer(), tmp)
+        except Exception as exc:
+            print("reference raised", seed, repr(exc)[:160], flush=True)
+            shutil.rmtree(tmp, ignore_errors=True)
+            continue
+        shutil.rmtree(tmp, ignore_errors=True)
+        rs = with_ends(H.ordered_reads(case))
+        plan = D.plan_sample(rs, case["windows"], len(case["reference"]))
+        batch = B.pack_reads(rs)
+        res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"])
+        assert st == 0
+
+        def text_of(i, version):
+            if version >= 0 and (version, i) in res.records:
+                seq, qual = H.final_read(batch, res, i, session=version)
+            else:
+                seq, qual = B.decode_bases(batch.sequence_codes(i)), [int(x) for x in batch.qualities(i)]
+            return OF.render(rs[i]["name"], rs[i]["flag"], seq, qual)
+        mine = assemble(plan, rs, text_of)
+        diff = [nm for nm, text in mine.items() if text != (gold.get(nm) or "")]
+        stats_ok = D.statistics_text(case["contig"], plan, res.sess_counts) == gold["N.bam.statistics.txt"]
+        if os.environ.get("GA_FUZZ_DUMP") and (diff or not stats_ok):
+            import pickle
+            pickle.dump({"mine": mine, "gold": gold, "case": case, "reads": rs, "pairs": plan.pairs, "singles": plan.singles, "sessions": plan.sessions}, open(os.environ["GA_FUZZ_DUMP"], "wb"))
+        if diff or not stats_ok:
+            if stats_ok and all(records(mine[nm]) == records(gold.get(nm)) for nm in diff):
+                order_only += 1
+                print("ORDER-ONLY", seed, diff, kw, "drop", drop, "unmap", unmap, flush=True)
+            elif stats_ok and all(is_q12(mine[nm], gold.get(nm), rs, plan) for nm in diff):
+                q12 += 1
+                print("Q12", seed, diff, flush=True)
+            else:
+                bad += 1
+                print("MISMATCH", seed, diff, "stats" if not stats_ok else "", kw, "drop", drop, "unmap", unmap, flush=True)
+        if (seed - seed0) % 10 == 9:
+            print(f"{seed - seed0 + 1} cases, {bad} mismatches, {order_only} order-only, {q12} Q12", flush=True)
+    print(f"done: {n} cases, {bad} mismatches, {order_only} order-only, {q12} Q12")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
