@@ -10,7 +10,7 @@ _LIB = None
 
 # every entry point declared in include/ga_b200.h
 EXPORTS = ["ga_abi_version", "ga_status_string", "ga_engine_create", "ga_engine_destroy", "ga_last_error",
-           "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions", "ga_fastq_layout", "ga_fastq_render", "ga_result_digest"]
+           "ga_upload_reference", "ga_run", "ga_run_host", "ga_last_host_traffic", "ga_launch_count", "ga_last_kernel_ms", "ga_kernel_ms_history", "ga_stage_ms_history", "ga_last_fallback_sessions", "ga_engine_keep_edits", "ga_record_edits", "ga_fastq_layout", "ga_fastq_render", "ga_result_digest"]
 # include/ga_wire.h
 WIRE_EXPORTS = ["ga_wire_pack_sizes", "ga_wire_pack", "ga_run_wire"]
 # include/ga_synth.h - the synthetic-input generator lives in its own library (never needed by the masking path)
@@ -51,6 +51,10 @@ def lib():
     L.ga_kernel_ms_history.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
     L.ga_stage_ms_history.restype = C.c_int
     L.ga_stage_ms_history.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]
+    L.ga_engine_keep_edits.restype = C.c_int
+    L.ga_engine_keep_edits.argtypes = [C.c_void_p, C.c_int]
+    L.ga_record_edits.restype = C.c_int
+    L.ga_record_edits.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_uint32)]
     L.ga_last_fallback_sessions.restype = C.c_int
     L.ga_last_fallback_sessions.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
     L.ga_fastq_layout.restype = C.c_int

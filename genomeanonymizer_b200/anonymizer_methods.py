@@ -8,7 +8,11 @@ yielding two-element lists of `AnonymizedRead`-compatible objects in the referen
 
 What differs is where the work happens: the pileup stream is only used to collect the session's reads;
 discovery, germline resolution and masking run in the CUDA engine (libga_b200.so) on one packed batch.
-Nothing here masks on the CPU; without the CUDA library / a GPU the class raises.
+Nothing in `anonymize()` masks on the CPU; without the CUDA library / a GPU the class raises.  The one piece of the
+reference's read object that edits bases on the host is kept because the reference's DRIVER calls it after the path:
+`AnonymizedRead.mask_or_anonymize_left_over_variants`, which the driver's writers invoke a second time on a read that was
+parked unpaired and met again (quirk Q12 of DESIGN.md) - the engine hands over what it applied (ga_record_edits) and the
+object repeats it exactly as the reference's object would.
 """
 from __future__ import annotations
 
@@ -47,8 +51,10 @@ class VariantType(enum.Enum):
 class MaskedVariant:
     """What `stats_recorder.count_variant` receives: only `.variant_type` is read (SR.py:198-204)."""
 
-    def __init__(self, variant_type):
+    def __init__(self, variant_type, length: int = 0, ref_allele: str = ""):
         self.variant_type = variant_type
+        self.length = length
+        self.ref_allele = ref_allele
 
 
 def generate_anonymized_read(name: str, sequence: str, quality: str) -> str:
@@ -96,7 +102,28 @@ class AnonymizedRead:
         return generate_anonymized_read(name, seq, qual)
 
     def update_anonymized_read_from_other(self, other):
-        pass
+        """anonymizer_methods.py:281-287 - the list of an already masked read is never emptied, so meeting the read again
+        switches the flag back on and the next writer masks its indels a second time (quirk Q12)."""
+        if other.has_left_overs_to_mask:
+            self.left_over_variants_to_mask.extend(other.left_over_variants_to_mask)
+        if self.left_over_variants_to_mask:
+            self.has_left_overs_to_mask = True
+
+    def mask_or_anonymize_left_over_variants(self):
+        """anonymizer_methods.py:254-270 over mask_or_modify_indel (:178-203), for the writers of the reference's driver
+        (SR.py:354-357, 401-404, 615-616).  The first application happened on the device."""
+        self.left_over_variants_to_mask.sort(key=lambda e: e[1].variant_type.value)
+        seq = [int(x) for x in self.anonymized_sequence_array]
+        qual = [int(x) for x in self.anonymized_qualities_array]
+        for at, v in self.left_over_variants_to_mask:
+            if v.variant_type == VariantType.INS:                 # the inserted bases go
+                seq, qual = seq[:at] + seq[at + v.length:], qual[:at] + qual[at + v.length:]
+            elif v.variant_type == VariantType.DEL:               # the deleted reference bases come back, floor(mean quality)
+                fill = int(np.mean(qual))
+                seq, qual = seq[:at] + [ord(c) for c in v.ref_allele] + seq[at:], qual[:at] + [fill] * v.length + qual[at:]
+        self.anonymized_sequence_array = np.asarray(seq, dtype=np.uint8)
+        self.anonymized_qualities_array = array.array("B", qual)
+        self.has_left_overs_to_mask = False
 
 
 def anonymized_read_pair_is_writeable(r1, r2) -> bool:
@@ -210,7 +237,7 @@ class B200GermlineAnonymizer:
                                      "keep": keep_from_variant(validated_source_variant, lo)}])
         eng = self._get_engine()
         eng.upload_reference(0, ref)
-        result = eng.run(batch, sessions)
+        result = eng.run(batch, sessions, edits=True)
         if stats_recorder is not None:
             for col, vt in enumerate((VariantType.SNV, VariantType.DEL, VariantType.INS)):
                 for _ in range(int(result.sess_counts[0, col])):
@@ -232,6 +259,9 @@ class B200GermlineAnonymizer:
                     q = [int(x) for x in rec["qual"]]
                     fq = array.array("B", reversed(q) if a.is_reverse else q)
             ar = AnonymizedRead(a.query_name, a.is_read1, a.is_read2, a.is_reverse, ds, seq, fq)
+            for at, pos, ln, ins in (rec.get("edits") or ()) if rec is not None else ():
+                ar.left_over_variants_to_mask.append(
+                    (at, MaskedVariant(VariantType.INS if ins else VariantType.DEL, ln, "" if ins else ref[pos:pos + ln].upper())))
             slot = pairs.setdefault(a.query_name, [None, None])
             if slot[ar.get_pair_idx()] is None:                   # first alignment of (name, mate) wins (AM.py:331-335)
                 slot[ar.get_pair_idx()] = ar

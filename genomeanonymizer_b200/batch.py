@@ -231,8 +231,18 @@ class MaskResult:
         return out
 
 
+def parse_edits(aux) -> Optional[list]:
+    """The 8 words of ga_record_edits (include/ga_b200.h) as [(in_read_pos, reference position, length, is_insertion)] in
+    application order; None when the description was not kept."""
+    if int(aux[6]) == 0xFFFFFFFF:
+        return None
+    s32 = lambda w: int(w) - (1 << 32) if int(w) >> 31 else int(w)
+    return [(s32(aux[3 * k]), s32(aux[3 * k + 1]), int(aux[3 * k + 2]) & 0x7FFFFFFF, bool(int(aux[3 * k + 2]) >> 31)) for k in range(int(aux[6]) & 0xFF)]
+
+
 def decode_result(n_sessions, totals: _abi.GaTotals, mod_session, mod_read, mod_len, mod_seq_off16, mod_qual_off16,
-                  out_seq4, out_qual, sess_counts) -> MaskResult:
+                  out_seq4, out_qual, sess_counts, edits=None) -> MaskResult:
+    """edits: [n, 8] words of ga_record_edits - every indel-masked record then carries "edits" (parse_edits)."""
     res = MaskResult()
     n = int(totals.n_modified)
     for k in range(n):
@@ -246,6 +256,8 @@ def decode_result(n_sessions, totals: _abi.GaTotals, mod_session, mod_read, mod_
         if r in res.records:
             raise ValueError(f"(session, read) {r} emitted twice")
         res.records[r] = {"seq": codes, "qual": q}
+        if edits is not None and q is not None:
+            res.records[r]["edits"] = parse_edits(edits[k])
     res.sess_counts = np.asarray(sess_counts).reshape(n_sessions, 4).copy()
     res.totals = {"n_modified": n, "seq16_used": int(totals.seq16_used), "qual16_used": int(totals.qual16_used),
                   "session_reads": int(totals.session_reads), "session_bases": int(totals.session_bases),

@@ -224,7 +224,7 @@ void ga_engine_destroy(ga_engine* e) {
         if (L.ev_fork) cudaEventDestroy(L.ev_fork);
         if (L.ev_join) cudaEventDestroy(L.ev_join);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); cudaFree(L.d_many); cudaFree(L.d_many_recs); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); cudaFree(L.d_edit_keep); cudaFree(L.d_many); cudaFree(L.d_many_recs); cudaFree(L.d_germ); cudaFree(L.d_ent); cudaFree(L.d_obs); cudaFree(L.d_cnt);
         for (int j = 0; j < 5; ++j) for (int k = 0; k < kTimedRuns; ++k) if (L.ev[j][k]) cudaEventDestroy(L.ev[j][k]);
     }
     delete e;
@@ -284,7 +284,7 @@ static int ensure_session_scratch(ga_engine* e, Lane& L, int64_t n_sessions) {
 
 static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int64_t n_sessions) {
     if (cap_records > L.cap_kind) {
-        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); L.d_kind = nullptr; L.d_edesc = nullptr; L.d_special = nullptr; L.d_rare_list = nullptr; L.cap_kind = 0;
+        cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); cudaFree(L.d_edit_keep); L.d_edit_keep = nullptr; L.d_kind = nullptr; L.d_edesc = nullptr; L.d_special = nullptr; L.d_rare_list = nullptr; L.cap_kind = 0;
         const int64_t cap = cap_records + cap_records / 8 + 1024;
         GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
         GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
@@ -370,6 +370,28 @@ int ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons) {
     return h[0];
 }
 
+int ga_engine_keep_edits(ga_engine* e, int on) {
+    if (!e) return GA_ERR_BAD_ARGUMENT;
+    e->keep_edits = on != 0;
+    return GA_OK;
+}
+
+int ga_record_edits(ga_engine* e, const int64_t* rec_idx, int64_t n, uint32_t* out) {
+    if (!e || (n > 0 && (!rec_idx || !out)) || n < 0) return ga_fail(e, GA_ERR_BAD_ARGUMENT, "ga_record_edits: null argument");
+    Lane& L = e->lanes[e->last_lane];
+    if (!e->keep_edits || !L.d_edit_keep) return ga_fail(e, GA_ERR_BAD_ARGUMENT, "ga_record_edits: ga_engine_keep_edits was not switched on before the run");
+    GA_CUDA(cudaSetDevice(e->device));
+    GA_CUDA(cudaDeviceSynchronize());
+    for (int64_t k = 0; k < n;) {                                     // one copy per run of consecutive indices
+        if (rec_idx[k] < 0 || rec_idx[k] >= L.cap_kind) return ga_fail(e, GA_ERR_OFFSET_RANGE, "ga_record_edits: record index out of range");
+        int64_t m = 1;
+        while (k + m < n && rec_idx[k + m] == rec_idx[k] + m && rec_idx[k + m] < L.cap_kind) ++m;
+        GA_CUDA(cudaMemcpy(out + 8 * k, static_cast<const uint8_t*>(L.d_edit_keep) + 32 * rec_idx[k], (size_t)(32 * m), cudaMemcpyDeviceToHost));
+        k += m;
+    }
+    return GA_OK;
+}
+
 float ga_last_kernel_ms(ga_engine* e) {
     float ms = -1.f;
     return ga_kernel_ms_history(e, &ms, 1) == 1 ? ms : -1.f;
@@ -436,6 +458,12 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     E.many = reinterpret_cast<uint4*>(L.d_many); E.n_many = reinterpret_cast<uint32_t*>(L.d_small + 15); E.cap_many = (uint32_t)L.cap_many;
     E.many_recs = L.d_many_recs; E.n_many_recs = reinterpret_cast<uint32_t*>(L.d_small + 16); E.n_kind1 = reinterpret_cast<uint32_t*>(L.d_small + 17); E.ticket_large = reinterpret_cast<unsigned int*>(L.d_small + 18); E.ticket_lean = reinterpret_cast<unsigned int*>(L.d_small + 19);
     E.n_rare = reinterpret_cast<uint32_t*>(L.d_small + 22); E.rare_list = L.d_rare_list;
+    E.edit_keep = nullptr;
+    if (e->keep_edits) {                                              // asked for by the per-sample driver (quirk Q12 of DESIGN.md), small batches
+        if (!L.d_edit_keep) GA_CUDA(cudaMalloc(&L.d_edit_keep, (size_t)L.cap_kind * 32));
+        GA_CUDA(cudaMemsetAsync(L.d_edit_keep, 0xff, (size_t)std::max<int64_t>(out->cap_records, 1) * 32, st));
+        E.edit_keep = reinterpret_cast<uint4*>(L.d_edit_keep);
+    }
     GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;

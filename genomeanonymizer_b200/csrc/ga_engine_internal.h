@@ -16,7 +16,7 @@ struct Lane {
     uint8_t* d_big_scratch = nullptr;
     // streaming pipeline scratch: scan kernel -> resolve kernel (ga::ScanScratch), resolve -> emission (ga::EmitScratch2)
     uint32_t* d_ent = nullptr; void* d_obs = nullptr; void* d_cnt = nullptr; int64_t cap_items = 0;
-    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; void* d_special = nullptr; uint32_t* d_rare_list = nullptr; void* d_many = nullptr; uint32_t* d_many_recs = nullptr; int64_t cap_many = 0; int64_t cap_kind = 0;
+    uint8_t* d_kind = nullptr; void* d_edesc = nullptr; void* d_special = nullptr; uint32_t* d_rare_list = nullptr; void* d_edit_keep = nullptr; void* d_many = nullptr; uint32_t* d_many_recs = nullptr; int64_t cap_many = 0; int64_t cap_kind = 0;
     uint32_t* d_germ = nullptr; int64_t cap_germ = 0;
     // CUDA events between the stages of the most recent kTimedRuns runs (ring), recorded on the launching stream so
     // bench.py can read per-launch durations after its timed region without syncing inside it:
@@ -42,7 +42,8 @@ struct ga_engine {
     int32_t big_cols_cap = 1 << 18, big_reads_cap = 1 << 18, big_obs_cap = 1 << 17;
     int64_t launches = 0;
     int last_lane = 0, next_lane = 0;        // ga_run: lane of the most recent run; round-robin cursor when every lane is taken
-    int occ_scan = 4, occ_lean = 9, occ_mid = 6, occ_res = 6, occ_rec = 4;   // resident CTAs per SM of the persistent kernels
+    int occ_scan = 4, occ_lean = 9, occ_mid = 6, occ_res = 6, occ_rec = 4;
+    bool keep_edits = false;              // ga_engine_keep_edits: the resolve kernels keep a copy of every record's edit description   // resident CTAs per SM of the persistent kernels
     HostSlot* slots = nullptr;           // lazily created by ga_run_host
     int64_t last_h2d = 0, last_d2h = 0;
     int64_t* d_fastq_sums = nullptr; int64_t cap_fastq_blocks = 0;   // ga_fastq_layout scratch

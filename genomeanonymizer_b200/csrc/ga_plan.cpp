@@ -23,6 +23,7 @@ struct ga_plan {
 namespace {
 
 constexpr int64_t kNone = INT64_MIN;                       // an empty mate slot
+constexpr int32_t kReapply = 1 << 30;                      // flag on a version: the read's left-over indels are applied twice (GA_PLAN_REAPPLY)
 inline int64_t slot_of(int32_t read, int32_t version) { return ((int64_t)read << 32) | (uint32_t)version; }
 inline int32_t slot_read(int64_t v) { return (int32_t)(v >> 32); }
 inline int32_t slot_version(int64_t v) { return (int32_t)(uint32_t)v; }
@@ -144,8 +145,14 @@ struct Planner {
             if (y.m1 >= 0 && y.m2 >= 0) { write_pair(y.name, slot_of(y.m1, s), slot_of(y.m2, s), plan->pairs); continue; }   // SR.py:310-312
             int64_t* slot = nullptr;
             const int64_t at = (int64_t)plan->pairs.size() / 5;
-            if (y.m1 >= 0) slot = store(y.name, 0, slot_of(y.m1, s), at);                                                    // SR.py:320-333
-            if (y.m2 >= 0) slot = store(y.name, 1, slot_of(y.m2, s), at);
+            // quirk Q12: a read that waits unpaired with the masking of an earlier session and is met again has its left-over
+            // indels switched on again (anonymizer_methods.py:281-287) - whoever writes it applies them a second time
+            auto meet = [&](int m, int32_t read) {
+                slot = store(y.name, m, slot_of(read, s), at);
+                if (slot[m] != slot_of(read, s) && slot_version(slot[m]) >= 0) slot[m] = slot_of(slot_read(slot[m]), slot_version(slot[m]) | kReapply);
+            };
+            if (y.m1 >= 0) meet(0, y.m1);                                                                                    // SR.py:320-333
+            if (y.m2 >= 0) meet(1, y.m2);
             if (slot && slot[0] != kNone && slot[1] != kNone) {                                                              // SR.py:348-359
                 const int64_t s0 = slot[0], s1 = slot[1];
                 write_pair(y.name, s0, s1, plan->pairs);

@@ -50,6 +50,8 @@ struct EmitScratch2 {
     unsigned int* ticket_lean;    // next session of the one-warp resolve kernel
     uint32_t* n_rare;             // special records that emit_records_kernel leaves to emit_special_kernel (two edits, many hits, reads beyond 160 bases)
     uint32_t* rare_list;          // [cap_records] their slots in sdesc
+    uint4* edit_keep;             // null, or [cap_records][2]: a lasting copy of the EditAux of every indel-masked record, by record index
+                                  // (ga_record_edits; all bits set = not kept: more than two edits, or a record of the fallback kernel)
 };
 
 // Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
                 }
                 uint4* dst = reinterpret_cast<uint4*>(O.out_qual + 32ull * qual16);
                 const uint4* src = reinterpret_cast<const uint4*>(&a);
-                if (two) { dst[0] = src[0]; dst[1] = src[1]; }
+                if (two) { dst[0] = src[0]; dst[1] = src[1]; if (E.edit_keep) { E.edit_keep[2 * rec_idx] = src[0]; E.edit_keep[2 * rec_idx + 1] = src[1]; } }
                 else write_many_aux(c, sm, k, (int)(lf & 0xffffu), a.qidx, dst);
             }
         }
@@ -1025,6 +1027,7 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
                     dst[0] = make_uint4((uint32_t)E2.irp[0], (uint32_t)E2.pos[0], (uint32_t)E2.len[0] | ((E2.ne >= 1 && E2.n_del < 1) ? 0x80000000u : 0u), (uint32_t)E2.irp[1]);
                     dst[1] = make_uint4((uint32_t)E2.pos[1], (uint32_t)E2.len[1] | ((E2.ne >= 2 && E2.n_del < 2) ? 0x80000000u : 0u),
                                         (uint32_t)E2.ne | ((uint32_t)E2.n_del << 8), qidx);
+                    if (E.edit_keep) { E.edit_keep[2 * rec_idx] = dst[0]; E.edit_keep[2 * rec_idx + 1] = dst[1]; }
                 } else write_many_aux(c, sm, (int)k, (int)L0, qidx, dst);
             }
         }

@@ -159,6 +159,26 @@ def _fetch_pair_events(reads, t_idx: List[int], n_idx: List[int]):
     yield ("unmapped", 1, um[1])
 
 
+REAPPLY = 1 << 30          # flag on the version of a planned read: its left-over indels are applied twice (quirk Q12)
+
+
+def version_of(v: int) -> int:
+    """The session whose masking a planned read prints (-1: as it came in), without the REAPPLY flag."""
+    v = int(v)
+    return v if v < 0 else v & ~REAPPLY
+
+
+def reapply_pairs(plan) -> List[Tuple[int, int]]:
+    """(session, read) of every planned read that carries the REAPPLY flag."""
+    out = []
+    for row in plan.pairs:
+        out += [(version_of(v), int(r)) for r, v in ((row[1], row[2]), (row[3], row[4])) if int(v) >= 0 and int(v) & REAPPLY]
+    for row in plan.singles:
+        if int(row[2]) >= 0 and int(row[2]) & REAPPLY:
+            out.append((version_of(row[2]), int(row[1])))
+    return out
+
+
 def _fetch_pair_island_events(reads, ti, ni):
     a = b = 0                                                     # current island of each dataset
     # "r is not None" in the reference = there is another island after the current one
@@ -248,6 +268,11 @@ def _plan_sample(reads: Sequence[dict], windows: Sequence[dict], contig_len: int
             for mate, m in ((0, m1), (1, m2)):                    # :320-333
                 if m is not None:
                     slot = store(name, mate, (m, s))
+                    if slot[mate] != (m, s) and slot[mate][1] >= 0:
+                        # quirk Q12: the read waits unpaired with the masking of an earlier session and is met again:
+                        # update_anonymized_read_from_other (anonymizer_methods.py:281-287) switches its left-over indels on
+                        # again, and whoever writes it applies them a second time
+                        slot[mate] = (slot[mate][0], slot[mate][1] | REAPPLY)
             if slot[0] is not None and slot[1] is not None:       # :348-359
                 write_pair(name, slot[0], slot[1])
                 to_pair.pop(name)
@@ -337,6 +362,37 @@ def anonymize_sample(engine, reads: Sequence[dict], windows: Sequence[dict], ref
     return anonymize_packed(engine, batch, [r["name"] for r in rs], rs, windows, reference, contig)
 
 
+_CODE2ASC = "=ACMGRSVTWYHKDBN"
+_ASC2CODE = {c: k for k, c in enumerate(_CODE2ASC)}
+_COMPLEMENT = [int(f"{k:04b}"[::-1], 2) for k in range(16)]       # the complement of a 4-bit base code is its bit reversal
+
+
+def reapply_indel_edits(codes, printed_quals, reverse: bool, edits, reference) -> Tuple[List[int], List[int]]:
+    """Quirk Q12: the second application of a read's left-over indels, as the reference performs it
+    (anonymizer_methods.py:254-270 over the list that :281-287 switched on again; mask_or_modify_indel, :178-203).
+    codes: the record's 4-bit base codes in alignment orientation, printed_quals: its qualities in printed (BAM) order, both
+    as the first application left them; edits: batch.parse_edits of the record.  Returns (codes, printed qualities)."""
+    seq = [int(c) for c in codes]
+    q = [int(x) for x in (printed_quals[::-1] if reverse else printed_quals)]     # the reference edits the forward-orientation array (quirk Q1)
+    for at, pos, ln, ins in edits:                                 # application order: all DELs, then all INSs
+        if ins:                                                    # the inserted bases go (Python slices clamp)
+            seq, q = seq[:at] + seq[at + ln:], q[:at] + q[at + ln:]
+        else:                                                      # the deleted reference bases come back with floor(mean(qualities))
+            ref = reference[pos:pos + ln]
+            ref = ref.decode("ascii") if isinstance(ref, (bytes, bytearray)) else str(ref)
+            avg = int(sum(q) / len(q)) if q else 0
+            seq, q = seq[:at] + [_ASC2CODE.get(ch, 15) for ch in ref.upper()] + seq[at:], q[:at] + [avg] * ln + q[at:]
+    return seq, (q[::-1] if reverse else q)
+
+
+def fastq_text(name: bytes, flag: int, codes: Sequence[int], printed_quals: Sequence[int]) -> bytes:
+    """One FASTQ record as the reference prints it (anonymizer_methods.py:205-243): reverse reads reverse-complemented."""
+    if flag & 0x10:
+        codes = [_COMPLEMENT[c] for c in reversed(codes)]
+    return (b"@" + name + b"/" + (b"1" if flag & 0x40 else b"2") + b"\n" + "".join(_CODE2ASC[c] for c in codes).encode("ascii") + b"\n+\n" +
+            bytes(int(x) + 33 for x in printed_quals) + b"\n")
+
+
 def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: Sequence[dict], reference,
                      contig: str = "c", plan: Optional[Plan] = None, as_bytes: bool = False, carry: Optional[dict] = None) -> Dict[str, str]:
     """Same for an already packed batch (batch.ReadBatch with dense qualities, e.g. from
@@ -359,6 +415,12 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     db, ds = DeviceBatch(batch, engine.device), DeviceSessions(sessions, engine.device)
     units = batch.seq4.shape[0] // 16
     dres = DeviceResult(sessions.n_sessions, 2 * batch.n_reads + 16, 2 * units + 64, 2 * units + 64, engine.device)
+    P = np.asarray(plan.pairs, np.int64).reshape(-1, 5)
+    S = np.asarray(plan.singles, np.int64)
+    S = S.reshape(-1, S.shape[1] if S.ndim == 2 and S.shape[0] else 3)
+    any_reapply = bool(((P[:, [2, 4]] >= 0) & ((P[:, [2, 4]] & REAPPLY) != 0)).any() or ((S[:, 2] >= 0) & ((S[:, 2] & REAPPLY) != 0)).any())
+    if hasattr(engine, "keep_edits"):
+        engine.keep_edits(any_reapply)                                # quirk Q12: the edit descriptions of this run are needed on the host
     engine.run_device(db, ds, dres)
     torch.cuda.synchronize(engine.device)
     n = int(engine.check_device_status(dres).n_modified)
@@ -366,9 +428,6 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     mod_key = (dres.mod_session[:n].cpu().numpy().astype(np.int64) << 32) | dres.mod_read[:n].cpu().numpy().astype(np.int64)
     by_key = np.argsort(mod_key, kind="stable")
     sorted_key = mod_key[by_key]
-    P = np.asarray(plan.pairs, np.int64).reshape(-1, 5)
-    S = np.asarray(plan.singles, np.int64)
-    S = S.reshape(-1, S.shape[1] if S.ndim == 2 and S.shape[0] else 3)
     # items in file order: T.1, T.2, N.1, N.2, T.single_end, N.single_end - each file is one slice of the rendered text
     groups = []
     for d in (0, 1):
@@ -379,6 +438,8 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
         groups.append((f"{'TN'[d]}.single_end", rows[:, 1], rows[:, 2]))
     item_read = np.concatenate([g[1] for g in groups]) if groups else np.zeros(0, np.int64)
     item_ver = np.concatenate([g[2] for g in groups]) if groups else np.zeros(0, np.int64)
+    reapply = np.nonzero((item_ver >= 0) & ((item_ver & REAPPLY) != 0))[0]
+    item_ver = np.where(item_ver >= 0, item_ver & ~REAPPLY, item_ver)
     want = (item_ver << 32) | item_read
     at = np.searchsorted(sorted_key, want)
     hit = (item_ver >= 0) & (at < n)
@@ -386,7 +447,43 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     item_rec = np.where(hit, by_key[np.minimum(at, max(n - 1, 0))] if n else 0, -1).astype(np.int32)
     text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n, as_view=as_bytes)   # as_bytes: slices of the download buffer, no copies
     starts = np.concatenate([[0], np.cumsum([len(g[1]) for g in groups])]).astype(np.int64)
-    piece = lambda a, b: text[int(off[a]):int(off[b])]                # records [a, b) of the item list
+    # quirk Q12: the few planned reads whose left-over indels the reference applies twice are printed on the host
+    replaced: Dict[int, bytes] = {}
+    if len(reapply) and hasattr(engine, "record_edits"):
+        cand = [int(k) for k in reapply if item_rec[k] >= 0]
+        if cand:
+            recs = np.asarray([int(item_rec[k]) for k in cand], np.int64)
+            ridx = torch.as_tensor(recs, device=dres.mod_len.device)
+            qoff = dres.mod_qual_off16[ridx].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            soff = dres.mod_seq_off16[ridx].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            mlen = dres.mod_len[ridx].cpu().numpy().astype(np.int64)
+            aux = engine.record_edits(recs)
+            blob, noff = names if isinstance(names, tuple) else (None, None)
+            for k, q16, s16, L1, a in zip(cand, qoff, soff, mlen, aux):
+                edits = None if q16 == 0xFFFFFFFF else B.parse_edits(a)
+                if not edits:
+                    continue                                          # no indel edits (nothing to re-apply), or a description that was not kept
+                r = int(item_read[k])
+                packed = dres.out_seq4[16 * int(s16):16 * int(s16) + (int(L1) + 1) // 2].cpu().numpy()
+                codes = np.stack([packed & 15, packed >> 4], 1).reshape(-1)[:int(L1)]
+                quals = dres.out_qual[32 * int(q16):32 * int(q16) + int(L1)].cpu().numpy()
+                flag = int(batch.len_flag[r]) >> 16
+                codes2, quals2 = reapply_indel_edits(codes, quals, bool(flag & 0x10), edits, reference)
+                nm = bytes(blob[int(noff[r]):int(noff[r + 1])]) if blob is not None else names[r].encode("ascii")
+                replaced[k] = fastq_text(nm, flag, codes2, quals2)
+    rep_at = sorted(replaced)
+
+    def piece(a, b):                                                  # records [a, b) of the item list
+        a, b = int(a), int(b)
+        lo, hi = bisect.bisect_left(rep_at, a), bisect.bisect_left(rep_at, b)
+        if lo == hi:
+            return text[int(off[a]):int(off[b])]
+        parts, cur = [], a
+        for k in rep_at[lo:hi]:
+            parts += [bytes(text[int(off[cur]):int(off[k])]), replaced[k]]
+            cur = k + 1
+        parts.append(bytes(text[int(off[cur]):int(off[b])]))
+        return b"".join(parts)
     out = {}
     if carry is None:
         for g, (name, rd, _) in enumerate(groups):

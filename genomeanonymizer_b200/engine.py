@@ -105,7 +105,7 @@ class DeviceResult:
         raw = self.totals.cpu().numpy().tobytes()
         return _abi.GaTotals.from_buffer_copy(raw)
 
-    def to_host(self) -> MaskResult:
+    def to_host(self, edits=None) -> MaskResult:
         t = self.read_totals()
         n = int(t.n_modified)
         u32 = lambda x, k: x[:k].cpu().numpy().view(np.uint32)
@@ -113,7 +113,7 @@ class DeviceResult:
                              u32(self.mod_len, n), u32(self.mod_seq_off16, n), u32(self.mod_qual_off16, n),
                              self.out_seq4[:int(t.seq16_used) * 16].cpu().numpy(),
                              self.out_qual[:int(t.qual16_used) * 32].cpu().numpy(),
-                             self.sess_counts[:self.n_sessions * 4].cpu().numpy().view(np.uint32))
+                             self.sess_counts[:self.n_sessions * 4].cpu().numpy().view(np.uint32), edits=edits)
 
 
 class Engine:
@@ -183,6 +183,18 @@ class Engine:
         buf = np.frombuffer(bases, dtype=np.uint8)
         self._check(self._L.ga_upload_reference(self._h, contig_id, buf.ctypes.data, len(buf), stream))
 
+    def keep_edits(self, on: bool = True) -> None:
+        """The following runs keep every record's edit description (ga_engine_keep_edits; per-sample driver, quirk Q12)."""
+        self._check(self._L.ga_engine_keep_edits(self._h, 1 if on else 0))
+
+    def record_edits(self, rec_idx) -> np.ndarray:
+        """[n, 8] uint32: the edit descriptions of records `rec_idx` of the last run (ga_record_edits)."""
+        idx = np.ascontiguousarray(rec_idx, np.int64)
+        out = np.zeros((len(idx), 8), np.uint32)
+        if len(idx):
+            self._check(self._L.ga_record_edits(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), len(idx), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
     def run_device(self, dbatch: DeviceBatch, dsess: DeviceSessions, dres: DeviceResult, stream=None) -> None:
         """Asynchronous launch over device-resident buffers (the `value` path of bench.py)."""
         s = (stream or torch.cuda.current_stream(self.device)).cuda_stream
@@ -250,17 +262,19 @@ class Engine:
                                                 f"(needs records={t.n_modified} seq16={t.seq16_used} qual16={t.qual16_used})")
         return t
 
-    def run(self, batch: ReadBatch, sessions: SessionTable, cap_frac: float = 1.0) -> MaskResult:
-        """Synchronous convenience: upload, run, download, decode."""
+    def run(self, batch: ReadBatch, sessions: SessionTable, cap_frac: float = 1.0, edits: bool = False) -> MaskResult:
+        """Synchronous convenience: upload, run, download, decode.  edits: every indel-masked record also carries the
+        description of what was applied to it (ga_record_edits; the plugin hands it to the reference's driver, quirk Q12)."""
         with torch.cuda.device(self.device):
             db, ds = DeviceBatch(batch, self.device), DeviceSessions(sessions, self.device)
             units = batch.seq4.shape[0] // 16
             dres = DeviceResult(sessions.n_sessions, max(16, int(2 * batch.n_reads * cap_frac) + 16),
                                 int(2 * units * cap_frac) + 64, int(2 * units * cap_frac) + 64, self.device)
+            self.keep_edits(edits)
             self.run_device(db, ds, dres)
             torch.cuda.synchronize(self.device)
-            self.check_device_status(dres)
-            return dres.to_host()
+            n = int(self.check_device_status(dres).n_modified)
+            return dres.to_host(self.record_edits(np.arange(n)) if edits else None)
 
 
 def _to_host_batch(db: DeviceBatch) -> ReadBatch:

@@ -201,6 +201,16 @@ int   ga_stage_ms_history(ga_engine* e, int stage, float* out, int n);
  * Synchronises the device. */
 int   ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons);
 
+/* Edit descriptions of indel-masked records, for a host that has to reproduce quirk Q12 of the reference (a read
+ * that was masked, parked unpaired and met again by a later session has its left-over indels applied a second time,
+ * anonymizer_methods.py:254-287).  ga_engine_keep_edits(e, 1) makes the following runs keep, per modified record, what was
+ * applied to it; ga_record_edits then copies 8 words per requested record index (indices into the mod_* arrays of the last
+ * ga_run on this engine): { in_read_pos 0, reference position 0, length 0 | INS << 31, in_read_pos 1, reference position 1,
+ * length 1 | INS << 31, edits | DELs << 8, - } in application order (all DELs, then all INSs).  All bits set: nothing kept
+ * (a record without indel edits, one with more than two, or one written by the fallback kernel). */
+int   ga_engine_keep_edits(ga_engine* e, int on);
+int   ga_record_edits(ga_engine* e, const int64_t* rec_idx, int64_t n, uint32_t* out);
+
 /* ------------------------------------------------------------------ end-to-end host entry
  * ga_run_host: all pointers are HOST pointers (pinned for full speed).  Splits the session table into
  * chunks of about `chunk_sessions` sessions (<=0: engine default), slices the reads each chunk needs,

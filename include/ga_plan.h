@@ -19,6 +19,8 @@
 
 #include <stdint.h>
 
+#define GA_PLAN_REAPPLY (1 << 30)
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -39,7 +41,10 @@ int64_t ga_plan_n_pairs(const ga_plan* p);
 int64_t ga_plan_n_singles(const ga_plan* p);
 /* sessions: first / last / window index (-1: island session between windows), each [n_sessions]. */
 void ga_plan_sessions(const ga_plan* p, int32_t* first, int32_t* last, int32_t* window);
-/* pairs: rows of 5 - dataset, read of mate 1, its session version, read of mate 2, its session version - in write order;
+/* A version is the session whose masking the read prints, or -1 (as it came in); bit 30 (GA_PLAN_REAPPLY) on a version says
+ * that the reference applies the read's left-over indels a second time (quirk Q12 of DESIGN.md: the read waited unpaired with
+ * that masking and was met again by a later session).
+ * pairs: rows of 5 - dataset, read of mate 1, its session version, read of mate 2, its session version - in write order;
  * singles: rows of 4 - dataset, read, version, and the number of pairs of this contig that precede the place where a pair
  * completed by this read is written (the reference keeps unpaired reads across contigs, to_pair_anonymized_reads, and
  * writes such a pair the moment the second mate is processed) - in the order the reference spills them to the

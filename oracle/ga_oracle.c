@@ -82,6 +82,7 @@ typedef struct {
     int newlen;
     uint8_t* seq;         /* codes, one per byte, newlen                                        */
     uint8_t* qual;        /* printed order, newlen; NULL when qualities unchanged               */
+    uint32_t aux[8];     /* the record's edits in the form of ga_record_edits (include/ga_b200.h), all ones: none kept */
 } rres_t;
 
 typedef struct { rres_t* v; int n, cap; } sres_t;   /* modified reads of one session, ascending read index */
@@ -142,6 +143,24 @@ static int key_equals_keep(const ga_reads* R, const ga_sessions* S, int s, const
 }
 
 #define GROW(ptr, cap, need, T) do { if ((need) > (cap)) { (cap) = (need) * 2 + 16; (ptr) = (T*)realloc((ptr), sizeof(T) * (size_t)(cap)); } } while (0)
+
+/* Quirk Q12 of DESIGN.md (per-sample orchestration): (session << 32 | read) keys, ascending, of the reads whose left-over
+ * indels the reference applies a SECOND time (anonymizer_methods.py:254-287: the read was masked, parked unpaired and met again
+ * by a later session, which switches has_left_overs_to_mask on again over the list that was never cleared).  Set by the
+ * whole-sample checkers before ga_oracle_run; empty for everything else. */
+static const int64_t* g_reapply = NULL;
+static int64_t g_n_reapply = 0;
+void ga_oracle_set_reapply(const int64_t* keys, int64_t n) { g_reapply = keys; g_n_reapply = n; }
+/* Checker twin of ga_record_edits (include/ga_b200.h): 8 words per record of the next runs, in record order. */
+static uint32_t* g_edit_sink = NULL;
+static int64_t g_edit_cap = 0;
+void ga_oracle_set_edit_sink(uint32_t* out8, int64_t cap_records) { g_edit_sink = out8; g_edit_cap = cap_records; }
+static int reapply_twice(int s, int64_t r) {
+    const int64_t key = ((int64_t)s << 32) | (int64_t)r;
+    int64_t lo = 0, hi = g_n_reapply;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (g_reapply[m] < key) lo = m + 1; else hi = m; }
+    return lo < g_n_reapply && g_reapply[lo] == key;
+}
 
 static int process_session(const ga_reads* R, const ga_sessions* S, int s, const uint8_t* refc, int64_t ref_len,
                            int maxspan, scratch_t* W, sres_t* res, uint32_t* counts,
@@ -273,7 +292,8 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
                 const obs_t* o = &W->obs[my_obs0 + j];
                 if (W->keys[o->key].germline) { any_indel = 1; if (o->type == GA_VT_DEL) extra += o->len; }
             }
-            int need = L + extra + 1;
+            const int rounds = (any_indel && g_n_reapply && reapply_twice(s, r)) ? 2 : 1;
+            int need = L + rounds * extra + 1;
             if (need > W->cap_buf) { W->cap_buf = need * 2; W->sbuf = (uint8_t*)realloc(W->sbuf, (size_t)W->cap_buf); W->qbuf = (uint8_t*)realloc(W->qbuf, (size_t)W->cap_buf); }
             uint8_t* sq = W->sbuf;
             for (int k = 0; k < L; ++k) sq[k] = (uint8_t)nib_at(rec, k);
@@ -301,6 +321,7 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
                 ql = W->qbuf;
                 for (int k = 0; k < L; ++k) ql[k] = reverse ? qrec[L - 1 - k] : qrec[k];   /* get_forward_qualities(), AM.py:95 */
                 /* left-overs sorted by VariantType value: DEL (2) before INS (3), stable (AM.py:264) */
+                for (int round = 0; round < rounds; ++round)
                 for (int pass = 0; pass < 2; ++pass)
                     for (int j = 0; j < n_ops_indel; ++j) {
                         const obs_t* o = &W->obs[my_obs0 + j];
@@ -328,6 +349,19 @@ static int process_session(const ga_reads* R, const ga_sessions* S, int s, const
             GROW(res->v, res->cap, res->n + 1, rres_t);
             rres_t* o = &res->v[res->n++];
             o->read = (int)r; o->newlen = cur;
+            memset(o->aux, 0xff, sizeof o->aux);
+            if (any_indel) {                                         /* application order: DELs, then INSs */
+                int ne = 0, nd = 0;
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int j = 0; j < n_ops_indel; ++j) {
+                        const obs_t* e = &W->obs[my_obs0 + j];
+                        if (!W->keys[e->key].germline || (e->type == GA_VT_DEL) != (pass == 0)) continue;
+                        if (ne < 2) { o->aux[3 * ne] = (uint32_t)e->irp; o->aux[3 * ne + 1] = (uint32_t)e->pos; o->aux[3 * ne + 2] = (uint32_t)e->len | (pass ? 0x80000000u : 0u); }
+                        ++ne; nd += (pass == 0);
+                    }
+                if (ne <= 2) { o->aux[6] = (uint32_t)ne | ((uint32_t)nd << 8); o->aux[7] = 0; for (int k = 3 * ne; k < 6; ++k) o->aux[k] = 0; }
+                else memset(o->aux, 0xff, sizeof o->aux);
+            }
             o->seq = (uint8_t*)malloc((size_t)cur + 1);
             memcpy(o->seq, sq, (size_t)cur);
             o->qual = NULL;
@@ -440,6 +474,7 @@ int ga_oracle_run(const ga_reads* R, const ga_sessions* S, const uint8_t* ref_as
                 memset(qd, 0, 32ull * units);
                 memcpy(qd, o->qual, (size_t)o->newlen);
             } else out->mod_qual_off16[nrec] = 0xffffffffu;
+            if (g_edit_sink && (int64_t)nrec < g_edit_cap) memcpy(g_edit_sink + 8 * nrec, o->aux, sizeof o->aux);
         } else overflow = 1;
         ++nrec; s16 += units; if (o->qual) { q16 += units; ++nq; }
         free(o->seq); free(o->qual);

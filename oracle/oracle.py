@@ -35,6 +35,10 @@ def lib():
         _LIB.ga_oracle_run.argtypes = [C.POINTER(_abi.GaReads), C.POINTER(_abi.GaSessions), C.c_void_p, C.c_int64,
                                        C.POINTER(_abi.GaResult), C.c_int]
         _LIB.ga_oracle_threads.restype = C.c_int
+        _LIB.ga_oracle_set_reapply.restype = None
+        _LIB.ga_oracle_set_reapply.argtypes = [C.c_void_p, C.c_int64]
+        _LIB.ga_oracle_set_edit_sink.restype = None
+        _LIB.ga_oracle_set_edit_sink.argtypes = [C.c_void_p, C.c_int64]
         _LIB.ga_oracle_digest.restype = C.c_int
         _LIB.ga_oracle_digest.argtypes = [C.POINTER(_abi.GaResult), C.c_int64, C.POINTER(_abi.GaDigestIds), C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
@@ -45,8 +49,10 @@ def n_threads():
 
 
 def run(batch: ReadBatch, sessions: SessionTable, reference: bytes, threads: int = 0, decode: bool = True,
-        cap_frac: float = 1.0):
-    """Returns (MaskResult | raw dict, status)."""
+        cap_frac: float = 1.0, reapply=(), edits: bool = False):
+    """Returns (MaskResult | raw dict, status).  reapply: (session, read) pairs whose left-over indels the reference
+    applies twice (quirk Q12 of DESIGN.md; the whole-sample checkers pass the pairs the plan flags).  edits: records carry
+    "edits" as Engine.run(edits=True) returns them."""
     keep = []
     R = batch.as_struct(keep)
     S = sessions.as_struct(keep)
@@ -68,14 +74,22 @@ def run(batch: ReadBatch, sessions: SessionTable, reference: bytes, threads: int
     res.sess_counts = counts.ctypes.data
     res.totals = C.addressof(totals)
     refb = np.frombuffer(reference if isinstance(reference, (bytes, bytearray)) else reference.encode("ascii"), dtype=np.uint8)
-    st = lib().ga_oracle_run(C.byref(R), C.byref(S), refb.ctypes.data, len(refb), C.byref(res), int(threads))
+    keys = np.sort(np.asarray([(int(a) << 32) | int(b) for a, b in reapply], np.int64))
+    lib().ga_oracle_set_reapply(keys.ctypes.data if len(keys) else None, len(keys))
+    aux = np.full((cap_rec, 8), 0xFFFFFFFF, np.uint32) if edits else None
+    lib().ga_oracle_set_edit_sink(aux.ctypes.data if edits else None, cap_rec if edits else 0)
+    try:
+        st = lib().ga_oracle_run(C.byref(R), C.byref(S), refb.ctypes.data, len(refb), C.byref(res), int(threads))
+    finally:
+        lib().ga_oracle_set_reapply(None, 0)
+        lib().ga_oracle_set_edit_sink(None, 0)
     if not decode:
         return {"totals": totals, "counts": counts.reshape(-1, 4), "result": res,
                 "arrays": (mod_sess, mod_read, mod_len, mod_so, mod_qo, out_seq, out_qual, counts)}, st
     if st != _abi.GA_OK:
         return None, st
     return decode_result(sessions.n_sessions, totals, mod_sess, mod_read, mod_len, mod_so, mod_qo, out_seq, out_qual,
-                         counts[:sessions.n_sessions * 4]), st
+                         counts[:sessions.n_sessions * 4], edits=aux), st
 
 
 def digest(result_struct, n_records, session_base=0, tumor_base=0, normal_base=0, n_tumor=0, contig=0, records=False, accumulate=None):

@@ -318,6 +318,10 @@ def genome_cases():
         # left is paired after the last section (pair_unmapped_mates, short_read_tumor_normal_anonymizer.py:561-600)
         (41, dict(contig_len=9000, n_pairs=(120, 110), read_len=80, somatic_positions=[2500, 6000], snp_rate=3e-3, indel_rate=8e-4,
                   clip_frac=0.1), "unmapped-mates", -6),
+        # quirk Q12: thin coverage, orphans and many indels - reads that one session masks and parks unpaired are met again by
+        # an overlapping later session, and the reference applies their left-over indels a second time when it writes them
+        (54, dict(contig_len=9000, n_pairs=(70, 60), read_len=80, somatic_positions=[2500, 4650, 6800], snp_rate=4e-3, indel_rate=3e-3,
+                  clip_frac=0.1), "twice-masked", 5),
     ]
     for seed, kw, label, drop in specs:
         case = synth.make_case(seed, name=f"genome-{label}", **kw)

@@ -12,6 +12,7 @@ import pytest
 
 from genomeanonymizer_b200 import batch as B
 from genomeanonymizer_b200 import driver as D
+from genomeanonymizer_b200 import synth
 from oracle import fastq as OF
 from oracle import oracle
 from tests import helpers as H
@@ -39,7 +40,9 @@ def golden_counts(files):
 
 
 def assemble(plan, reads, text_of):
-    """The six output files from the write plan; text_of(read index, version) -> record text."""
+    """The six output files from the write plan; text_of(read index, version) -> record text.  The version reaches text_of
+    without the plan's REAPPLY flag (quirk Q12): the checker gets the flagged pairs through driver.reapply_pairs."""
+    text_of = (lambda f: lambda r, v: f(int(r), D.version_of(v)))(text_of)
     files = {f"{p}.anonymized.{s}.fastq": [] for p in "TN" for s in ("1", "2", "single_end")}
     for ds, r1, v1, r2, v2 in plan.pairs:
         p = "TN"[ds]
@@ -79,7 +82,7 @@ def test_oracle_writes_the_reference_files(entry):
     plan = D.plan_sample(reads, case["windows"], len(case["reference"]))
     assert [[s["first"], s["last"]] for s in plan.sessions if s["window"] is not None] == [w[1:] for w in entry["expected"]["windows"]]
     batch = B.pack_reads(reads)
-    res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"])
+    res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"], reapply=D.reapply_pairs(plan))
     assert st == 0
 
     def text_of(i, version):
@@ -109,3 +112,38 @@ def test_device_writes_the_reference_files(entry):
         for s in ("1", "2", "single_end"):
             assert got[f"{p}.{s}"] == (gold.get(f"{p}.anonymized.{s}.fastq") or ""), (case["name"], p, s)
     assert got["statistics"] == gold["N.bam.statistics.txt"], case["name"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [50, 54, 57])
+def test_device_applies_left_over_indels_twice_where_the_reference_does(seed):
+    """Quirk Q12 on the device path: thin, orphan-rich samples in which sessions meet reads that an earlier session parked
+    unpaired; driver.anonymize_sample must print what plan + oracle print with the flagged reads masked twice (the pair is
+    pinned to the reference's own files by the golden sample genome-twice-masked and by tools/fuzz_genome.py)."""
+    from genomeanonymizer_b200.engine import Engine
+    case = synth.make_case(seed, name=f"twice-{seed}", contig_len=9000, n_pairs=(70, 60), read_len=80, somatic_positions=[2500, 4650, 6800],
+                           snp_rate=4e-3, indel_rate=3e-3, clip_frac=0.1)
+    case["reads"] = [r for k, r in enumerate(case["reads"]) if k % 5 != 3]
+    reads = with_ends(H.ordered_reads(case))
+    plan = D.plan_sample(reads, case["windows"], len(case["reference"]))
+    flagged = D.reapply_pairs(plan)
+    assert flagged
+    batch = B.pack_reads(reads)
+    res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"], reapply=flagged)
+    assert st == 0
+
+    def text_of(i, version):
+        if version >= 0 and (version, i) in res.records:
+            seq, qual = H.final_read(batch, res, i, session=version)
+        else:
+            seq, qual = B.decode_bases(batch.sequence_codes(i)), [int(x) for x in batch.qualities(i)]
+        return OF.render(reads[i]["name"], reads[i]["flag"], seq, qual)
+    want = assemble(plan, reads, text_of)
+    eng = Engine(0)
+    try:
+        got = D.anonymize_sample(eng, H.ordered_reads(case), case["windows"], case["reference"], contig=case["contig"])
+    finally:
+        eng.close()
+    for p in "TN":
+        for s in ("1", "2", "single_end"):
+            assert got[f"{p}.{s}"] == want[f"{p}.anonymized.{s}.fastq"], (seed, p, s)

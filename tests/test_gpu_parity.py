@@ -78,6 +78,32 @@ def test_engine_matches_oracle_random(engine, kw, sparse_qual):
     assert got.totals["n_modified"] > 0 or kw["n_pairs"][1] == 0
 
 
+@pytest.mark.parametrize("kw", [k for k in RANDOM_CASES if k.get("indel_rate", 1e-3) > 0][:6] + [RANDOM_CASES[-1]], ids=lambda k: f"seed{k['seed']}")
+def test_engine_edit_descriptions_match_oracle(engine, kw):
+    """ga_record_edits (what the per-sample driver and the plugin's read objects need for quirk Q12): every indel-masked
+    record carries the edits the oracle applied, in application order; records and counters are unchanged by keeping them."""
+    from oracle import oracle
+    case = synth.make_case(**kw)
+    batch = B.pack_reads(H.ordered_reads(case))
+    sessions = B.pack_sessions(case["windows"])
+    exp, st = oracle.run(batch, sessions, case["reference"], edits=True)
+    assert st == 0
+    engine.upload_reference(0, case["reference"])
+    try:
+        got = engine.run(batch, sessions, edits=True)
+    finally:
+        engine.keep_edits(False)
+    assert_same_result(got, exp, kw["seed"])
+    n = 0
+    for key, rec in exp.records.items():
+        if rec["qual"] is None:
+            assert "edits" not in got.records[key]
+            continue
+        assert got.records[key]["edits"] == rec["edits"], (kw["seed"], key)
+        n += rec["edits"] is not None
+    assert n > 0
+
+
 def _trim_clean_reads(case, seed, keep_min):
     """Mixed read lengths (trimmed reads): every other clean read loses a random tail."""
     rng = np.random.default_rng(seed)

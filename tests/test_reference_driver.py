@@ -33,9 +33,9 @@ class OracleEngine:
     def upload_reference(self, contig_id, bases):
         self.reference = bases if isinstance(bases, (bytes, bytearray)) else str(bases).encode("ascii")
 
-    def run(self, batch, sessions):
+    def run(self, batch, sessions, edits=False):
         from oracle import oracle
-        res, st = oracle.run(batch, sessions, self.reference)
+        res, st = oracle.run(batch, sessions, self.reference, edits=edits)
         assert st == 0
         self.runs += 1
         return res
@@ -128,7 +128,7 @@ def test_plan_matches_the_reference_on_samples_with_unmapped_mates(ref_modules, 
     reads = with_ends(H.ordered_reads(case))
     plan = D.plan_sample(reads, case["windows"], len(case["reference"]))
     batch = B.pack_reads(reads)
-    res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"])
+    res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"], reapply=D.reapply_pairs(plan))
     assert st == 0
 
     def text_of(i, version):

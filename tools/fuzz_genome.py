@@ -93,7 +93,7 @@ def main():
         rs = with_ends(H.ordered_reads(case))
         plan = D.plan_sample(rs, case["windows"], len(case["reference"]))
         batch = B.pack_reads(rs)
-        res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"])
+        res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"], reapply=D.reapply_pairs(plan))
         assert st == 0
 
         def text_of(i, version):
