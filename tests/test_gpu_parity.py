@@ -78,7 +78,7 @@ def test_engine_matches_oracle_random(engine, kw, sparse_qual):
     assert got.totals["n_modified"] > 0 or kw["n_pairs"][1] == 0
 
 
-@pytest.mark.parametrize("kw", [k for k in RANDOM_CASES if k.get("indel_rate", 1e-3) > 0][:6] + [RANDOM_CASES[-1]], ids=lambda k: f"seed{k['seed']}")
+@pytest.mark.parametrize("kw", [k for k in RANDOM_CASES if k.get("indel_rate", 1e-3) > 0 and k["n_pairs"][1] > 0], ids=lambda k: f"seed{k['seed']}")
 def test_engine_edit_descriptions_match_oracle(engine, kw):
     """ga_record_edits (what the per-sample driver and the plugin's read objects need for quirk Q12): every indel-masked
     record carries the edits the oracle applied, in application order; records and counters are unchanged by keeping them."""
