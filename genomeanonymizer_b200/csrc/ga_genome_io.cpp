@@ -420,30 +420,71 @@ static inline bool cigar_in_cg_tag(const RecView& v) {
     return (c0 & 15u) == 4u && (c0 >> 4) == v.l_seq && (c1 & 15u) == 3u;
 }
 
+// What one slice of a contig's records adds to the totals (both passes over the records run slice by slice on all
+// host threads: one record is one hop through the inflated stream, i.e. one cache miss).
+struct SliceSums {
+    int64_t n_reads = 0, units = 0, n_cigar = 0, name_bytes = 0;
+    int32_t max_ref_span = 0, first_pos = 0, last_pos = 0;
+    bool sorted = true;
+    int err = GA_IO_OK;
+    const char* msg = nullptr;
+};
+constexpr int64_t kSliceRecords = 8192;
+
+static SliceSums sum_slice(const ga_bam* b, const std::vector<uint64_t>& offs, int64_t lo, int64_t hi, uint32_t flag_exclude) {
+    SliceSums s;
+    int32_t prev = INT32_MIN;
+    for (int64_t k = lo; k < hi; ++k) {
+        const uint8_t* p = b->data.data() + offs[(size_t)k];
+        const RecView v = view_of(p);
+        if (v.flag & flag_exclude) continue;
+        if (v.l_seq > 0xffffu) { s.err = GA_IO_ERR_UNSUPPORTED; s.msg = "reads longer than 65535 bases are not supported"; return s; }
+        const uint32_t block_size = le32(p - 4);
+        if (32ull + v.l_name + 4ull * v.n_cigar <= block_size && cigar_in_cg_tag(v)) {
+            s.err = GA_IO_ERR_UNSUPPORTED; s.msg = "a record keeps its CIGAR in the CG tag (more than 65535 ops): not supported"; return s;
+        }
+        if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > block_size) {
+            s.err = GA_IO_ERR_FORMAT; s.msg = "alignment record fields exceed its block size"; return s;
+        }
+        if (!s.n_reads) s.first_pos = v.pos;
+        s.n_reads++;
+        s.units += units_of(v.l_seq);
+        s.n_cigar += v.n_cigar;
+        s.name_bytes += v.l_name ? v.l_name - 1 : 0;
+        s.max_ref_span = std::max(s.max_ref_span, (int32_t)ref_span_of(v.cigar, v.n_cigar));
+        if (v.pos < prev) s.sorted = false;
+        prev = v.pos;
+        s.last_pos = v.pos;
+    }
+    return s;
+}
+
+static int sum_slices(const ga_bam* b, int ref_id, uint32_t flag_exclude, int n_threads, std::vector<SliceSums>& slices) {
+    const std::vector<uint64_t>& offs = b->by_ref[ref_id];
+    const int64_t n = (int64_t)offs.size();
+    slices.assign((size_t)((n + kSliceRecords - 1) / kSliceRecords), SliceSums());
+    parallel_for(n, n_workers(n_threads), kSliceRecords, [&](int64_t lo, int64_t hi) {
+        slices[(size_t)(lo / kSliceRecords)] = sum_slice(b, offs, lo, hi, flag_exclude);
+    });
+    for (const SliceSums& s : slices) if (s.err != GA_IO_OK) return fail(s.err, s.msg);
+    return GA_IO_OK;
+}
+
 int ga_bam_contig_sizes(const ga_bam* b, int ref_id, uint32_t flag_exclude, ga_bam_sizes* out) {
     if (!b || !out || ref_id < 0 || ref_id >= (int)b->by_ref.size()) return fail(GA_IO_ERR_ARGUMENT, "ga_bam_contig_sizes: bad argument");
     { const int rc = ensure_loaded(b, ref_id); if (rc != GA_IO_OK) return rc; }
+    std::vector<SliceSums> slices;
+    { const int rc = sum_slices(b, ref_id, flag_exclude, b->threads, slices); if (rc != GA_IO_OK) return rc; }
     ga_bam_sizes s;
     std::memset(&s, 0, sizeof(s));
     s.sorted = 1;
     int32_t prev = INT32_MIN;
-    for (const uint64_t off : b->by_ref[ref_id]) {
-        const uint8_t* p = b->data.data() + off;
-        const RecView v = view_of(p);
-        if (v.flag & flag_exclude) continue;
-        if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
-        const uint32_t block_size = le32(p - 4);
-        if (32ull + v.l_name + 4ull * v.n_cigar <= block_size && cigar_in_cg_tag(v))
-            return fail(GA_IO_ERR_UNSUPPORTED, "a record keeps its CIGAR in the CG tag (more than 65535 ops): not supported");
-        if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > block_size)
-            return fail(GA_IO_ERR_FORMAT, "alignment record fields exceed its block size");
-        s.n_reads++;
-        s.seq16_units += units_of(v.l_seq);
-        s.n_cigar += v.n_cigar;
-        s.name_bytes += v.l_name ? v.l_name - 1 : 0;
-        s.max_ref_span = std::max(s.max_ref_span, (int32_t)ref_span_of(v.cigar, v.n_cigar));
-        if (v.pos < prev) s.sorted = 0;
-        prev = v.pos;
+    for (const SliceSums& c : slices) {
+        if (!c.n_reads) continue;
+        s.n_reads += c.n_reads; s.seq16_units += c.units; s.n_cigar += c.n_cigar; s.name_bytes += c.name_bytes;
+        s.max_ref_span = std::max(s.max_ref_span, c.max_ref_span);
+        if (!c.sorted || c.first_pos < prev) s.sorted = 0;
+        prev = c.last_pos;
     }
     *out = s;
     return GA_IO_OK;
@@ -454,45 +495,46 @@ int ga_bam_pack_contig(const ga_bam* b, int ref_id, uint32_t flag_exclude, const
     if (!dst->pos || !dst->len_flag || !dst->seq_off16 || !dst->cigar_off || !dst->seq4 || !dst->cigar)
         return fail(GA_IO_ERR_ARGUMENT, "ga_bam_pack_contig: NULL destination array");
     { const int rc = ensure_loaded(b, ref_id); if (rc != GA_IO_OK) return rc; }
-    // ---- pass 1 (sequential, one hop per record): which records, and where each one goes
-    std::vector<uint64_t> recs;
-    recs.reserve(b->by_ref[ref_id].size());
-    for (const uint64_t off : b->by_ref[ref_id])
-        if (!(le16(b->data.data() + off + 14) & flag_exclude)) recs.push_back(off);
-    const int64_t n = (int64_t)recs.size();
-    uint64_t u = dst->seq16_base, c = dst->cigar_base, nm = dst->name_base;
-    for (int64_t k = 0; k < n; ++k) {
-        const RecView v = view_of(b->data.data() + recs[k]);
-        if (v.l_seq > 0xffffu) return fail(GA_IO_ERR_UNSUPPORTED, "reads longer than 65535 bases are not supported");
-        if (32ull + v.l_name + 4ull * v.n_cigar + (v.l_seq + 1) / 2 + v.l_seq > le32(b->data.data() + recs[k] - 4))
-            return fail(GA_IO_ERR_FORMAT, "alignment record fields exceed its block size");
-        if (cigar_in_cg_tag(v)) return fail(GA_IO_ERR_UNSUPPORTED, "a record keeps its CIGAR in the CG tag (more than 65535 ops): not supported");
-        dst->seq_off16[k] = (uint32_t)u;
-        dst->cigar_off[k] = (uint32_t)c;
-        if (dst->name_off) dst->name_off[k] = nm;
-        u += units_of(v.l_seq); c += v.n_cigar; nm += v.l_name ? v.l_name - 1 : 0;
-        if (u > 0xffffffffull || c > 0xffffffffull) return fail(GA_IO_ERR_UNSUPPORTED, "batch exceeds the 32-bit record offsets: pack the contig in chunks");
-    }
-    dst->cigar_off[n] = (uint32_t)c;
-    if (dst->name_off) dst->name_off[n] = nm;
-    // ---- pass 2 (parallel): the record bytes
-    parallel_for(n, n_workers(n_threads), 4096, [&](int64_t lo, int64_t hi) {
-        for (int64_t k = lo; k < hi; ++k) {
-            const RecView v = view_of(b->data.data() + recs[k]);
+    // ---- pass 1 (parallel, one hop per record): what every slice of records holds; a scan over the slices says where each starts
+    std::vector<SliceSums> slices;
+    { const int rc = sum_slices(b, ref_id, flag_exclude, n_threads, slices); if (rc != GA_IO_OK) return rc; }
+    struct Start { int64_t read; uint64_t unit, cigar, name; };
+    std::vector<Start> starts(slices.size() + 1);
+    starts[0] = Start{0, dst->seq16_base, dst->cigar_base, dst->name_base};
+    for (size_t c = 0; c < slices.size(); ++c)
+        starts[c + 1] = Start{starts[c].read + slices[c].n_reads, starts[c].unit + (uint64_t)slices[c].units, starts[c].cigar + (uint64_t)slices[c].n_cigar,
+                              starts[c].name + (uint64_t)slices[c].name_bytes};
+    const Start& total = starts.back();
+    if (total.unit > 0xffffffffull || total.cigar > 0xffffffffull) return fail(GA_IO_ERR_UNSUPPORTED, "batch exceeds the 32-bit record offsets: pack the contig in chunks");
+    const std::vector<uint64_t>& offs = b->by_ref[ref_id];
+    const int64_t n_all = (int64_t)offs.size();
+    dst->cigar_off[total.read] = (uint32_t)total.cigar;
+    if (dst->name_off) dst->name_off[total.read] = total.name;
+    // ---- pass 2 (parallel): offsets and record bytes of every slice
+    parallel_for(n_all, n_workers(n_threads), kSliceRecords, [&](int64_t lo, int64_t hi) {
+        Start at = starts[(size_t)(lo / kSliceRecords)];
+        for (int64_t r = lo; r < hi; ++r) {
+            const RecView v = view_of(b->data.data() + offs[(size_t)r]);
+            if (v.flag & flag_exclude) continue;
+            const int64_t k = at.read++;
+            dst->seq_off16[k] = (uint32_t)at.unit;
+            dst->cigar_off[k] = (uint32_t)at.cigar;
+            if (dst->name_off) dst->name_off[k] = at.name;
             dst->pos[k] = v.pos;
             dst->len_flag[k] = (v.flag << 16) | v.l_seq;
             if (dst->ref_end) dst->ref_end[k] = v.pos + ref_span_of(v.cigar, v.n_cigar);
-            std::memcpy(dst->cigar + dst->cigar_off[k], v.cigar, 4ull * v.n_cigar);       // BAM words are little endian, as is the host
+            std::memcpy(dst->cigar + at.cigar, v.cigar, 4ull * v.n_cigar);                // BAM words are little endian, as is the host
             const uint32_t cap = units_of(v.l_seq) * 16u, nb = (v.l_seq + 1) / 2;
-            uint8_t* s = dst->seq4 + 16ull * dst->seq_off16[k];
+            uint8_t* s = dst->seq4 + 16ull * at.unit;
             for (uint32_t j = 0; j < nb; ++j) s[j] = (uint8_t)((v.seq[j] >> 4) | (v.seq[j] << 4));   // HIGH-nibble-first -> LOW-nibble-first
             std::memset(s + nb, 0, cap - nb);
             if (dst->qual) {
-                uint8_t* q = dst->qual + 32ull * dst->seq_off16[k];
+                uint8_t* q = dst->qual + 32ull * at.unit;
                 std::memcpy(q, v.qual, v.l_seq);
                 std::memset(q + v.l_seq, 0, 2ull * cap - v.l_seq);
             }
-            if (dst->names && dst->name_off && v.l_name) std::memcpy(dst->names + dst->name_off[k], v.name, v.l_name - 1);
+            if (dst->names && dst->name_off && v.l_name) std::memcpy(dst->names + at.name, v.name, v.l_name - 1);
+            at.unit += units_of(v.l_seq); at.cigar += v.n_cigar; at.name += v.l_name ? v.l_name - 1 : 0;
         }
     });
     return GA_IO_OK;

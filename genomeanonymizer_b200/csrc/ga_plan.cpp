@@ -9,7 +9,6 @@
 #include <cstring>
 #include <string>
 #include <string_view>
-#include <unordered_map>
 #include <vector>
 
 extern "C" int ga_io_set_error(int code, const char* msg);   // ga_genome_io.cpp
@@ -277,15 +276,38 @@ int ga_plan_sample(int64_t n_reads, int64_t n_tumor, const int32_t* pos, const i
     P.n = n_reads; P.n_tumor = n_tumor; P.pos = pos; P.end = ref_end; P.lf = len_flag;
     P.name_id.resize((size_t)n_reads);
     {
-        std::unordered_map<std::string_view, int32_t> ids;
-        ids.reserve((size_t)n_reads);
+        // dense name ids through a flat open-addressing table keyed by a 64-bit hash of the name (one probe sequence per
+        // read, no node allocation); equal hashes are confirmed by comparing the bytes
+        size_t cap = 16;
+        while (cap < (size_t)n_reads * 2) cap <<= 1;
+        struct Cell { uint64_t hash; int32_t id, read; };
+        std::vector<Cell> table(cap, Cell{0, -1, -1});
+        const char* base = reinterpret_cast<const char*>(names);
+        auto hash_of = [](const char* p, size_t len) {
+            uint64_t h = 0x9E3779B97F4A7C15ull ^ (len * 0xFF51AFD7ED558CCDull);
+            while (len >= 8) { uint64_t w; std::memcpy(&w, p, 8); h = (h ^ w) * 0x9FB21C651E98DF25ull; h ^= h >> 29; p += 8; len -= 8; }
+            uint64_t w = 0;
+            std::memcpy(&w, p, len);
+            h = (h ^ w) * 0x9FB21C651E98DF25ull;
+            return h ^ (h >> 32);
+        };
+        std::vector<uint64_t> hashes((size_t)n_reads);
+        for (int64_t i = 0; i < n_reads; ++i) hashes[(size_t)i] = hash_of(base + name_off[i], (size_t)(name_off[i + 1] - name_off[i]));
+        constexpr int64_t kAhead = 24;                          // the table is far larger than the caches: cells are fetched ahead of their probe
         for (int64_t i = 0; i < n_reads; ++i) {
-            const std::string_view nm(reinterpret_cast<const char*>(names) + name_off[i], (size_t)(name_off[i + 1] - name_off[i]));
-            const auto it = ids.emplace(nm, (int32_t)ids.size()).first;
-            P.name_id[(size_t)i] = it->second;
+            if (i + kAhead < n_reads) __builtin_prefetch(&table[(size_t)hashes[(size_t)(i + kAhead)] & (cap - 1)]);
+            const char* nm = base + name_off[i];
+            const size_t len = (size_t)(name_off[i + 1] - name_off[i]);
+            const uint64_t h = hashes[(size_t)i];
+            size_t k = (size_t)h & (cap - 1);
+            for (;; k = (k + 1) & (cap - 1)) {
+                Cell& c = table[k];
+                if (c.id < 0) { c = Cell{h, P.n_names++, (int32_t)i}; break; }
+                if (c.hash == h && (size_t)(name_off[c.read + 1] - name_off[c.read]) == len && std::memcmp(base + name_off[c.read], nm, len) == 0) break;
+            }
+            P.name_id[(size_t)i] = table[k].id;
             P.span = std::max(P.span, ref_end[i] - pos[i]);
         }
-        P.n_names = (int32_t)ids.size();
     }
     P.entry_of.assign((size_t)P.n_names, -1);
     P.written.assign((size_t)P.n_names, 0);

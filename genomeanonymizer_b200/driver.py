@@ -398,7 +398,8 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     """Same for an already packed batch (batch.ReadBatch with dense qualities, e.g. from
     genome_files.pack_tumor_normal): names = list of str or (uint8 blob, int64 offsets); read_table = rows with name /
     flag / dataset / pos / end for the planner (not needed when `plan` is given); reference = str / bytes / uint8 array
-    of the contig; as_bytes leaves the six FASTQ texts as bytes (the file writer appends them as they are).
+    of the contig; as_bytes leaves the six FASTQ texts as bytes (the file writer appends them as they are); plan may be
+    a concurrent.futures future of a Plan.
     carry: the sample's unpaired reads so far, {name bytes: (mate, dataset, FASTQ record)} in insertion order - the
     reference keeps them across contigs (to_pair_anonymized_reads, short_read_tumor_normal_anonymizer.py:646) and writes a
     pair the moment its second mate is processed.  With carry given (names must be the (blob, offsets) form and the plan
@@ -408,27 +409,26 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
     import torch
     from . import batch as B
     from .engine import DeviceBatch, DeviceResult, DeviceSessions
+    engine.upload_reference(batch.contig_id, reference if isinstance(reference, (str, bytes)) else np.ascontiguousarray(reference, np.uint8).tobytes())
+    db = DeviceBatch(batch, engine.device)                            # the reads travel while a plan handed over as a future is still being made
     if plan is None:
         plan = plan_sample(read_table, windows, len(reference))
+    elif hasattr(plan, "result"):
+        plan = plan.result()
     sessions = B.pack_sessions(plan.sessions)
-    engine.upload_reference(batch.contig_id, reference if isinstance(reference, (str, bytes)) else np.ascontiguousarray(reference, np.uint8).tobytes())
-    db, ds = DeviceBatch(batch, engine.device), DeviceSessions(sessions, engine.device)
+    ds = DeviceSessions(sessions, engine.device)
     units = batch.seq4.shape[0] // 16
     dres = DeviceResult(sessions.n_sessions, 2 * batch.n_reads + 16, 2 * units + 64, 2 * units + 64, engine.device)
     P = np.asarray(plan.pairs, np.int64).reshape(-1, 5)
     S = np.asarray(plan.singles, np.int64)
     S = S.reshape(-1, S.shape[1] if S.ndim == 2 and S.shape[0] else 3)
-    any_reapply = bool(((P[:, [2, 4]] >= 0) & ((P[:, [2, 4]] & REAPPLY) != 0)).any() or ((S[:, 2] >= 0) & ((S[:, 2] & REAPPLY) != 0)).any())
+    ver_cols = np.concatenate([P[:, 2], P[:, 4], S[:, 2]])
+    any_reapply = bool(((ver_cols >= 0) & ((ver_cols & REAPPLY) != 0)).any())
     if hasattr(engine, "keep_edits"):
         engine.keep_edits(any_reapply)                                # quirk Q12: the edit descriptions of this run are needed on the host
     engine.run_device(db, ds, dres)
-    torch.cuda.synchronize(engine.device)
-    n = int(engine.check_device_status(dres).n_modified)
-    # which modified record (if any) each planned read prints: (session, read) keys, sorted once and searched
-    mod_key = (dres.mod_session[:n].cpu().numpy().astype(np.int64) << 32) | dres.mod_read[:n].cpu().numpy().astype(np.int64)
-    by_key = np.argsort(mod_key, kind="stable")
-    sorted_key = mod_key[by_key]
-    # items in file order: T.1, T.2, N.1, N.2, T.single_end, N.single_end - each file is one slice of the rendered text
+    # (while the device runs) items in file order: T.1, T.2, N.1, N.2, T.single_end, N.single_end - each file is one slice
+    # of the rendered text
     groups = []
     for d in (0, 1):
         rows = P[P[:, 0] == d]
@@ -438,14 +438,28 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
         groups.append((f"{'TN'[d]}.single_end", rows[:, 1], rows[:, 2]))
     item_read = np.concatenate([g[1] for g in groups]) if groups else np.zeros(0, np.int64)
     item_ver = np.concatenate([g[2] for g in groups]) if groups else np.zeros(0, np.int64)
-    reapply = np.nonzero((item_ver >= 0) & ((item_ver & REAPPLY) != 0))[0]
-    item_ver = np.where(item_ver >= 0, item_ver & ~REAPPLY, item_ver)
-    want = (item_ver << 32) | item_read
-    at = np.searchsorted(sorted_key, want)
-    hit = (item_ver >= 0) & (at < n)
-    hit[hit] = sorted_key[at[hit]] == want[hit]
-    item_rec = np.where(hit, by_key[np.minimum(at, max(n - 1, 0))] if n else 0, -1).astype(np.int32)
-    text, off = engine.render_fastq(db, names, item_read.astype(np.int32), item_rec, dres, n, as_view=as_bytes)   # as_bytes: slices of the download buffer, no copies
+    reapply = np.nonzero((item_ver >= 0) & ((item_ver & REAPPLY) != 0))[0] if any_reapply else np.zeros(0, np.int64)
+    if any_reapply:
+        item_ver = np.where(item_ver >= 0, item_ver & ~REAPPLY, item_ver)
+    item_read32 = item_read.astype(np.int32)
+    torch.cuda.synchronize(engine.device)
+    n = int(engine.check_device_status(dres).n_modified)
+    # which modified record (if any) each planned read prints: only reads that have a record at all are searched, by
+    # (session, read) key in the sorted keys of the records
+    mod_read = dres.mod_read[:n].cpu().numpy().astype(np.int64)
+    mod_key = (dres.mod_session[:n].cpu().numpy().astype(np.int64) << 32) | mod_read
+    by_key = np.argsort(mod_key, kind="stable")
+    sorted_key = mod_key[by_key]
+    has_record = np.zeros(batch.n_reads + 1, bool)
+    has_record[mod_read] = True
+    item_rec = np.full(len(item_read), -1, np.int32)
+    cand = np.nonzero(has_record[item_read] & (item_ver >= 0))[0]
+    if len(cand):
+        want = (item_ver[cand] << 32) | item_read[cand]
+        at = np.minimum(np.searchsorted(sorted_key, want), n - 1)
+        found = sorted_key[at] == want
+        item_rec[cand[found]] = by_key[at[found]]
+    text, off = engine.render_fastq(db, names, item_read32, item_rec, dres, n, as_view=as_bytes)   # as_bytes: slices of the download buffer, no copies
     starts = np.concatenate([[0], np.cumsum([len(g[1]) for g in groups])]).astype(np.int64)
     # quirk Q12: the few planned reads whose left-over indels the reference applies twice are printed on the host
     replaced: Dict[int, bytes] = {}

@@ -20,9 +20,12 @@ def _dev(a: Optional[np.ndarray], device, pad=0):
     if a is None:
         return None
     t = torch.from_numpy(np.ascontiguousarray(a))
-    if pad:
-        t = torch.cat([t, torch.zeros(pad, dtype=t.dtype)])
-    return t.to(device, non_blocking=False)
+    if not pad:
+        return t.to(device, non_blocking=False)
+    out = torch.empty(t.numel() + pad, dtype=t.dtype, device=device)      # padded on the device: no host copy of the whole array
+    out[:t.numel()].copy_(t)
+    out[t.numel():].zero_()
+    return out
 
 
 class DeviceBatch:
@@ -36,7 +39,7 @@ class DeviceBatch:
         self.len_flag = v(b.len_flag).to(device)
         self.seq_off16 = v(b.seq_off16).to(device)
         self.cigar_off = v(b.cigar_off).to(device)
-        self.cigar = torch.cat([v(b.cigar), torch.zeros(4, dtype=torch.int32)]).to(device)
+        self.cigar = _dev(np.ascontiguousarray(b.cigar).view(np.int32), device, pad=4)
         self.seq4 = _dev(b.seq4, device, pad=64)
         self.qual = _dev(b.qual, device, pad=64) if b.qual is not None else None
         self.qual_reads = _dev(b.qual_reads, device) if b.qual_reads is not None else None

@@ -59,9 +59,11 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
     fasta = GF.FastaFile(ref_genome_file)
     outs = {("T", "1"): tumor_output_fastq + ".1.fastq", ("T", "2"): tumor_output_fastq + ".2.fastq",
             ("N", "1"): normal_output_fastq + ".1.fastq", ("N", "2"): normal_output_fastq + ".2.fastq"}
-    handles = {k: open(p, "wb", buffering=0) for k, p in outs.items()}      # truncated first, as the reference does (:652-655); unbuffered: whole slices are written
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(5)                               # the four files are written side by side (write() releases the GIL); one thread prepares the next contig
+    pool = ThreadPoolExecutor(8)                               # the four files are opened, written and closed side by side (the calls release the GIL); one thread prepares the next contig
+    # truncated first, as the reference does (:652-655), while the BAM files inflate; unbuffered: whole slices are written
+    opening = {k: pool.submit(open, p, "wb", 0) for k, p in outs.items()}
+    handles = {}
 
     def _append(handle, data):
         for part in (data if isinstance(data, list) else [data]):
@@ -83,7 +85,7 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
                     return None
                 _refuse_unsupported_records(cb.batch.len_flag, contig)
                 reference = fasta.fetch_bytes(contig)
-                plan = GF.plan_contig(cb, windows, len(reference))          # include/ga_plan.h: no per-read Python object
+                plan = pool.submit(GF.plan_contig, cb, windows, len(reference))   # include/ga_plan.h: no per-read Python object; made while the reads go to the device
                 return contig, windows, cb, reference, plan
 
             n_contigs = len(fasta.references)
@@ -95,16 +97,19 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
                     continue
                 contig, windows, cb, reference, plan = ready
                 if cb.batch.n_reads == 0:
+                    plan = plan.result()
                     stats_parts.append((contig, plan, [[0, 0, 0, 0]] * len(plan.sessions)))
                     continue
+                if not handles:
+                    handles.update({k: f.result() for k, f in opening.items()})
                 got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan, as_bytes=True, carry=carry)
                 list(pool.map(lambda k: _append(handles[k], got[f"{k[0]}.{k[1]}"]), list(handles)))   # done before the next contig reuses the buffer
-                stats_parts.append((contig, plan, got["_counts"]))
+                stats_parts.append((contig, got["_plan"], got["_counts"]))
                 n_reads += cb.batch.n_reads
-                n_sessions += len(plan.sessions)
+                n_sessions += len(got["_plan"].sessions)
     finally:
-        for h in handles.values():
-            h.close()
+        handles.update({k: f.result() for k, f in opening.items() if k not in handles and f.exception() is None})
+        list(pool.map(lambda h: h.close(), handles.values()))
         pool.shutdown()
         fasta.close()
     if carry:                                                      # write_single_end_reads opens both files (:603-605)
