@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
         const int n_here = (int)min((int64_t)32, V.n_items - k0);
         // does the record fit a group's slice?  (destination alignment pad + text; at most 32 words of bases, 64 of qualities)
         const int my_pad = (int)(reinterpret_cast<uintptr_t>(text + me.off) & 15u);
-        const bool my_fit = me.ok && my_pad + me.nl + 2ll * me.L + 8 <= (int64_t)kStageBytes && me.L <= 256 && me.nl <= 200;
+        const bool my_fit = me.ok && my_pad + me.nl + 2ll * me.L + 8 + 8 <= (int64_t)kStageBytes && me.L <= 248 && me.nl <= 200;   // + 8: aligned words reach past the record's end
         uint32_t slow_mask = __ballot_sync(0xffffffffu, me.ok && !my_fit);
         const uint32_t fit_mask = __ballot_sync(0xffffffffu, my_fit);
         // ---- four records per step, 8 lanes each
@@ -190,8 +190,10 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
             const bool span = __all_sync(0xffffffffu, chained);
             const int pad0 = (int)(reinterpret_cast<uintptr_t>(text + off0) & 15u);
             const int span_len = (int)(__shfl_sync(0xffffffffu, (unsigned long long)(it.off + total), 31) - off0);
-            uint8_t* sb = stage[threadIdx.x >> 5][g];
-            uint8_t* sg = span ? stage[threadIdx.x >> 5][0] + pad0 + (int)(it.off - off0) : sb + pad;
+            uint8_t* wb = &stage[threadIdx.x >> 5][0][0];                // the warp's staging area, 16-byte aligned
+            uint8_t* sb = wb + g * kStageBytes;
+            const int o_sg = span ? pad0 + (int)(it.off - off0) : g * kStageBytes + pad;   // where this record's text begins in it
+            uint8_t* sg = wb + o_sg;
             // every load first
             uint8_t nm[4];
 #pragma unroll
@@ -203,6 +205,56 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
             for (int t = 0; t < 4; ++t) { const int w = gl + kRenderGroup * t; sw[t] = w < nw ? __ldg(it.seqw + w) : 0u; }
 #pragma unroll
             for (int t = 0; t < 8; ++t) { const int w = gl + kRenderGroup * t; qv[t] = w < nq ? __ldg(qw + w) : 0u; }
+            // The text is produced as ALIGNED 32-bit words of the staging area: the characters of a section start at an
+            // arbitrary byte, so a lane combines its source word with the one before it (held by the lane to its left, or by
+            // lane 7 one round earlier) and shifts.  The first and last word of a section also cover up to three bytes of its
+            // neighbours (up to seven for the bases): sections are therefore written in an order in which the neighbour comes
+            // later - bases, then qualities, then header, separator and final newline - with a warp barrier in between.
+            const int o_ss = o_sg + nl + 4, s_seq = o_ss & 3;             // bases
+            const int o_sq = o_ss + L + 3, s_q = o_sq & 3;                // qualities
+            const int from_left = (lane & ~(kRenderGroup - 1)) | ((gl + kRenderGroup - 1) & (kRenderGroup - 1));
+            const int max_L = __reduce_max_sync(0xffffffffu, act ? L : 0);
+            {
+                // output word pair w covers the characters [8w - s_seq, 8w - s_seq + 8) of the printed sequence R.  Forward reads:
+                // R = the codes, the pair is the 32-bit window of the code words (w-1, w) at 4 * (8 - s_seq) bits.  Reverse reads:
+                // R[i] = complement(code[L-1-i]) = the bit-reversed window of the words (w-1, w) at 4 * ((L + s_seq) & 7) bits, and
+                // it is output pair ((L + s_seq) >> 3) - w.
+                uint32_t* dst = reinterpret_cast<uint32_t*>(wb + (o_ss - s_seq));
+                const int n_pairs = act ? (L + s_seq + 7) >> 3 : 0;
+                const int shift = reverse ? 4 * ((L + s_seq) & 7) : 32 - 4 * s_seq;
+                const int top = (L + s_seq) >> 3;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (8 * kRenderGroup * t >= max_L + 11) break;       // warp-uniform
+                    const int w = gl + kRenderGroup * t;
+                    const uint32_t give = gl == kRenderGroup - 1 ? (t ? sw[t ? t - 1 : 0] : 0u) : sw[t];
+                    const uint32_t left = __shfl_sync(0xffffffffu, give, from_left);
+                    uint32_t win = reverse ? __funnelshift_r(left, sw[t], shift) : __funnelshift_rc(left, sw[t], shift);
+                    if (reverse) win = __brev(win);
+                    const int w_out = reverse ? top - w : w;
+                    if (w_out >= 0 && w_out < n_pairs) {
+                        uint32_t ch[2];
+                        base_chars8(win, ch);
+                        dst[2 * w_out] = ch[0]; dst[2 * w_out + 1] = ch[1];
+                    }
+                }
+            }
+            __syncwarp();
+            {
+                // output word m covers the qualities [4m - s_q, 4m - s_q + 4): source words (m-1, m) shifted by 8 * (4 - s_q) bits
+                uint32_t* dst = reinterpret_cast<uint32_t*>(wb + (o_sq - s_q));
+                const int n_words = act ? (L + s_q + 3) >> 2 : 0;
+                const int shift = 32 - 8 * s_q;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (4 * kRenderGroup * t >= max_L + 7) break;        // warp-uniform
+                    const int m = gl + kRenderGroup * t;
+                    const uint32_t give = gl == kRenderGroup - 1 ? (t ? qv[t ? t - 1 : 0] : 0u) : qv[t];
+                    const uint32_t left = __shfl_sync(0xffffffffu, give, from_left);
+                    if (m < n_words) dst[m] = __funnelshift_rc(left, qv[t], shift) + 0x21212121u;   // anonymizer_methods.py:232 (phred <= 93: no carry between bytes)
+                }
+            }
+            __syncwarp();
             if (act) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -211,48 +263,8 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
                 }
                 for (int c = gl + 4 * kRenderGroup; c < nl + 4; c += kRenderGroup)
                     sg[c] = c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
-                uint8_t* ss = sg + nl + 4;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int w = gl + kRenderGroup * t;
-                    if (w >= nw) break;
-                    uint32_t cw = sw[t];
-                    int j0 = 8 * w;                                       // output position of the word's first character
-                    if (reverse) {                                        // reversed nibble order + complemented codes = the word bit-reversed
-                        cw = __brev(cw);
-                        j0 = L - 8 - 8 * w;
-                    }
-                    uint32_t ch[2];
-                    base_chars8(cw, ch);
-                    if (j0 >= 0 && j0 + 8 <= L) {                         // the whole word lies inside the read (all but the last word): no bound per character
-                        uint8_t* sp = ss + j0;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) sp[u] = (uint8_t)(ch[u >> 2] >> (8 * (u & 3)));
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int jj = j0 + u;
-                            if (jj >= 0 && jj < L) ss[jj] = (uint8_t)(ch[u >> 2] >> (8 * (u & 3)));
-                        }
-                    }
-                }
-                if (gl < 3) ss[L + gl] = gl == 1 ? (uint8_t)'+' : (uint8_t)'\n';
-                uint8_t* sq = ss + L + 3;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int w = gl + kRenderGroup * t;
-                    if (w >= nq) break;
-                    const uint32_t v = qv[t] + 0x21212121u;               // anonymizer_methods.py:232 (phred <= 93: no carry between bytes)
-                    if (4 * w + 4 <= L) {
-                        uint8_t* sp = sq + 4 * w;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) sp[u] = (uint8_t)(v >> (8 * u));
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) if (4 * w + u < L) sq[4 * w + u] = (uint8_t)(v >> (8 * u));
-                    }
-                }
-                if (gl == 0) sq[L] = (uint8_t)'\n';
+                if (gl < 3) wb[o_ss + L + gl] = gl == 1 ? (uint8_t)'+' : (uint8_t)'\n';
+                if (gl == 3) wb[o_sq + L] = (uint8_t)'\n';
             }
             __syncwarp();
             if (span) {                                                   // warp-uniform: the whole warp copies the span

@@ -21,6 +21,7 @@ secondary records; windows as `get_windows` makes them fo
 from __future__ import annotations
 
 import bisect
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -459,6 +460,8 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
         at = np.minimum(np.searchsorted(sorted_key, want), n - 1)
         found = sorted_key[at] == want
         item_rec[cand[found]] = by_key[at[found]]
+    if os.environ.get("GA_FILE_TRACE"):
+        print(f"[ga-file-trace]   masked, {n} records, items ready", flush=True)
     text, off = engine.render_fastq(db, names, item_read32, item_rec, dres, n, as_view=as_bytes)   # as_bytes: slices of the download buffer, no copies
     starts = np.concatenate([[0], np.cumsum([len(g[1]) for g in groups])]).astype(np.int64)
     # quirk Q12: the few planned reads whose left-over indels the reference applies twice are printed on the host

@@ -70,17 +70,23 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
             view = memoryview(part)
             while len(view):                                   # a raw write may be short
                 view = view[handle.write(view):]
+    import os, time
+    t_start = time.perf_counter()
+    trace = (lambda what: print(f"[ga-file-trace] {1e3 * (time.perf_counter() - t_start):8.1f} ms  {what}", flush=True)) if os.environ.get("GA_FILE_TRACE") else (lambda what: None)
     carry = {}                                                 # to_pair_anonymized_reads (:646): unpaired reads, kept across contigs
     stats_parts = []
     n_reads = n_sessions = 0
     try:
         opened = list(pool.map(lambda f: GF.BamFile(f, cpus), (tumor_bam_file, normal_bam_file)))    # both files inflate side by side
+        trace("BAM files open")
         with opened[0] as tumor, opened[1] as normal:
             def prepare(contig_id):
                 """Decode, pack and plan one contig (native code, no GIL): runs one contig ahead of the masking."""
                 contig = fasta.references[contig_id]
                 windows = windows_by_contig.get(contig, [])
+                trace(f"pack {contig} begins")
                 cb = GF.pack_tumor_normal(tumor, normal, contig, contig_id=contig_id)
+                trace(f"pack {contig} done")
                 if cb.batch.n_reads == 0 and not windows:
                     return None
                 _refuse_unsupported_records(cb.batch.len_flag, contig)
@@ -102,8 +108,11 @@ def anonymize_genome(windows_by_contig, tumor_bam_file: str, normal_bam_file: st
                     continue
                 if not handles:
                     handles.update({k: f.result() for k, f in opening.items()})
+                trace(f"mask {contig} begins")
                 got = anonymize_packed(engine, cb.batch, (cb.name_blob, cb.name_off), None, windows, reference, contig, plan=plan, as_bytes=True, carry=carry)
+                trace(f"text of {contig} ready")
                 list(pool.map(lambda k: _append(handles[k], got[f"{k[0]}.{k[1]}"]), list(handles)))   # done before the next contig reuses the buffer
+                trace(f"write {contig} done")
                 stats_parts.append((contig, got["_plan"], got["_counts"]))
                 n_reads += cb.batch.n_reads
                 n_sessions += len(got["_plan"].sessions)

@@ -100,3 +100,36 @@ def test_device_fastq_matches_oracle_on_random_sessions(engine, kw):
     for i, r in enumerate(reads):
         seq, qual = H.final_read(batch, exp, i)
         assert got[i] == OF.render(r["name"], r["flag"], seq, qual), (kw["seed"], i)
+
+
+@pytest.mark.gpu
+def test_device_fastq_every_alignment_of_every_section(engine):
+    """Read lengths from 1 to beyond a staging slice, names of 1 to 60 characters, both strands: the header, base and
+    quality sections of a record start at every byte alignment of the text (the renderer produces aligned words and
+    shifts), records chain into spans or not, and the longest take the general path."""
+    rng = np.random.default_rng(77)
+    lengths = [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 101, 127, 128, 129, 149, 150, 151, 200, 241, 247, 248, 249, 250,
+               255, 256, 257, 300]
+    ref_len = 4000
+    reference = "".join(rng.choice(list("ACGT"), size=ref_len))
+    reads = []
+    for ds in (0, 1):
+        for k in range(400):
+            L = int(lengths[(k * 7 + ds) % len(lengths)]) if k % 3 else int(rng.integers(1, 260))
+            pos = int(rng.integers(0, ref_len - 320))
+            nl = 1 + (k * 5 + ds) % 60
+            name = "".join(rng.choice(list("abcXYZ019:_"), size=nl)) + f"{ds}{k}"
+            flag = (0x40 if k % 2 else 0x80) | (0x10 if (k // 2) % 2 else 0) | 1
+            seq = "".join(rng.choice(list("ACGTN"), size=L, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+            reads.append(dict(name=name, flag=flag, pos=pos, cigar=f"{L}M", seq=seq, qual=[int(x) for x in rng.integers(0, 94, size=L)], dataset=ds))
+    reads.sort(key=lambda r: (r["dataset"], r["pos"]))
+    batch = B.pack_reads(reads)
+    sessions = B.pack_sessions([{"first": 1000, "last": 3001, "keep": None}])
+    exp, st = oracle.run(batch, sessions, reference)
+    assert st == 0
+    engine.upload_reference(0, reference)
+    for idx in (list(range(len(reads))), list(range(len(reads) - 1, -1, -3))):          # file order (records chain into spans) and scattered
+        got, n_masked = device_render(engine, batch, sessions, [r["name"] for r in reads], idx)
+        for k, i in enumerate(idx):
+            seq, qual = H.final_read(batch, exp, i)
+            assert got[k] == OF.render(reads[i]["name"], reads[i]["flag"], seq, qual), (i, len(reads[i]["seq"]))
