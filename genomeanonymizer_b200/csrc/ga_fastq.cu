@@ -55,19 +55,29 @@ __global__ void fastq_block_sums_kernel(FastqView V, int64_t* __restrict__ block
     }
 }
 
-__global__ void fastq_scan_sums_kernel(int64_t* __restrict__ block_sums, int64_t n_blocks, int64_t* __restrict__ total_out) {
-    // one warp walks the block sums 32 at a time (n_blocks = n_items / 1024: a few thousand at most per call)
-    const int lane = threadIdx.x;
-    long long run = 0;
-    for (int64_t b0 = 0; b0 < n_blocks; b0 += 32) {
-        const int64_t b = b0 + lane;
-        const long long v = b < n_blocks ? block_sums[b] : 0;
-        long long inc = v;
-        for (int d = 1; d < 32; d <<= 1) { const long long n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
-        if (b < n_blocks) block_sums[b] = run + inc - v;
-        run += __shfl_sync(0xffffffffu, inc, 31);
+__global__ void __launch_bounds__(kScanBlock) fastq_scan_sums_kernel(int64_t* __restrict__ block_sums, int64_t n_blocks, int64_t* __restrict__ total_out) {
+    // one CTA: every thread takes a run of consecutive block sums (independent loads, all in flight together), the CTA
+    // scans the per-thread totals, and every thread writes the exclusive prefix of its run
+    __shared__ long long s_part[kScanBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (n_blocks + kScanBlock - 1) / kScanBlock;
+    const int64_t b0 = (int64_t)threadIdx.x * per, b1 = min(n_blocks, b0 + per);
+    long long mine = 0;
+    for (int64_t b = b0; b < b1; ++b) mine += block_sums[b];
+    long long inc = mine;
+    for (int d = 1; d < 32; d <<= 1) { const long long n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += n; }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const long long v = s_part[lane];
+        long long t = v;
+        for (int d = 1; d < 32; d <<= 1) { const long long n = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += n; }
+        s_part[lane] = t - v;                                            // exclusive prefix of the warps
+        if (lane == 31) *total_out = t;
     }
-    if (lane == 0) *total_out = run;
+    __syncthreads();
+    long long run = s_part[warp] + inc - mine;
+    for (int64_t b = b0; b < b1; ++b) { const long long v = block_sums[b]; block_sums[b] = run; run += v; }
 }
 
 __global__ void fastq_offsets_kernel(FastqView V, const int64_t* __restrict__ block_sums, int64_t* __restrict__ text_off) {
@@ -259,22 +269,26 @@ __global__ void __launch_bounds__(256, 4) fastq_render_kernel(FastqView V, const
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int c = gl + kRenderGroup * t;
-                    if (c < nl + 4) sg[c] = c == 0 ? (uint8_t)'@' : c <= nl ? nm[t] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
+                    if (c >= 1 && c <= nl) sg[c] = nm[t];
                 }
-                for (int c = gl + 4 * kRenderGroup; c < nl + 4; c += kRenderGroup)
-                    sg[c] = c <= nl ? it.name[c - 1] : c == nl + 1 ? (uint8_t)'/' : c == nl + 2 ? mate : (uint8_t)'\n';
-                if (gl < 3) wb[o_ss + L + gl] = gl == 1 ? (uint8_t)'+' : (uint8_t)'\n';
-                if (gl == 3) wb[o_sq + L] = (uint8_t)'\n';
+                for (int c = gl + 4 * kRenderGroup; c <= nl; c += kRenderGroup) sg[c] = it.name[c - 1];
+                // the eight fixed characters, one per lane: '@' | '/' mate '\n' | '\n' '+' '\n' | '\n'
+                const int at = gl == 0 ? 0 : gl < 4 ? nl + gl : gl < 7 ? nl + 4 + L + (gl - 4) : nl + 4 + 2 * L + 3;
+                const uint32_t fixed_lo = (uint32_t)'@' | ((uint32_t)'/' << 8) | ((uint32_t)mate << 16) | ((uint32_t)'\n' << 24);
+                const uint32_t fixed_hi = (uint32_t)'\n' | ((uint32_t)'+' << 8) | ((uint32_t)'\n' << 16) | ((uint32_t)'\n' << 24);
+                sg[at] = (uint8_t)((gl < 4 ? fixed_lo : fixed_hi) >> (8 * (gl & 3)));
             }
             __syncwarp();
             if (span) {                                                   // warp-uniform: the whole warp copies the span
                 const uint8_t* ws = stage[threadIdx.x >> 5][0];
                 uint8_t* gb = text + off0 - pad0;                         // 16-byte aligned
                 const int end = pad0 + span_len;
-                for (int c16 = lane * 16; c16 < end; c16 += 32 * 16) {
-                    if (c16 >= pad0 && c16 + 16 <= end) *reinterpret_cast<uint4*>(gb + c16) = *reinterpret_cast<const uint4*>(ws + c16);
-                    else for (int t = max(c16, pad0); t < min(c16 + 16, end); ++t) gb[t] = ws[t];   // the neighbours' bytes share these chunks
-                }
+                for (int c16 = lane * 16; c16 + 16 <= end; c16 += 32 * 16)
+                    if (c16 >= pad0) *reinterpret_cast<uint4*>(gb + c16) = *reinterpret_cast<const uint4*>(ws + c16);
+                // the span's first and last 16-byte chunk are shared with the neighbours' bytes: one byte per lane
+                // (lanes 0-15: what is left of the first chunk, lanes 16-31: what is left of the last; a byte may be written twice)
+                const int tb = lane < 16 ? lane : (end & ~15) + (lane - 16);
+                if (tb >= pad0 && tb < end && (lane >= 16 || pad0 != 0)) gb[tb] = ws[tb];
             } else if (act) {
                 uint8_t* gb = out - pad;                                  // 16-byte aligned
                 const int end = pad + total;
@@ -339,7 +353,7 @@ int ga_fastq_layout(ga_engine* e, const ga_reads* R, const ga_result* O, int64_t
     }
     const ga::FastqView V = make_view(R, O, I, n_records);
     ga::fastq_block_sums_kernel<<<(unsigned)n_blocks, ga::kScanBlock, 0, st>>>(V, e->d_fastq_sums);
-    ga::fastq_scan_sums_kernel<<<1, 32, 0, st>>>(e->d_fastq_sums, n_blocks, text_off + I->n_items);
+    ga::fastq_scan_sums_kernel<<<1, ga::kScanBlock, 0, st>>>(e->d_fastq_sums, n_blocks, text_off + I->n_items);
     ga::fastq_offsets_kernel<<<(unsigned)n_blocks, ga::kScanBlock, 0, st>>>(V, e->d_fastq_sums, text_off);
     e->launches += 3;
     GA_CUDA(cudaGetLastError());
