@@ -494,8 +494,8 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     GA_CUDA(cudaStreamWaitEvent(L.side, L.ev_fork, 0));
     ga::emit_many_kernel<<<e->n_sm * 4, ga::kThreads, 0, L.side>>>(B, O, E);   // records of reads with more than two germline indels (usually few)
     ga::session_kernel<false><<<e->n_sm * 2, ga::kThreads, sizeof(ga::SmemLayout), L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr,
-                                                                                               reinterpret_cast<unsigned int*>(L.d_small + 14));
-    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1);
+                                                                                               reinterpret_cast<unsigned int*>(L.d_small + 14), E.edit_keep);
+    ga::session_kernel<true><<<e->big_ctas, ga::kThreads, 0, L.side>>>(B, V, L.d_descs, L.d_big_list, d_nbig, O, scr, d_tickets + 1, E.edit_keep);
     GA_CUDA(cudaEventRecord(L.ev_join, L.side));
     // stage 3: record bodies
     ga::emit_kernel<<<e->n_sm * 8, ga::kThreads, 0, st>>>(B, L.d_descs, O, E);

@@ -51,7 +51,7 @@ struct EmitScratch2 {
     uint32_t* n_rare;             // special records that emit_records_kernel leaves to emit_special_kernel (two edits, many hits, reads beyond 160 bases)
     uint32_t* rare_list;          // [cap_records] their slots in sdesc
     uint4* edit_keep;             // null, or [cap_records][2]: a lasting copy of the EditAux of every indel-masked record, by record index
-                                  // (ga_record_edits; all bits set = not kept: more than two edits, or a record of the fallback kernel)
+                                  // (ga_record_edits; all bits set = not kept: more than two edits)
 };
 
 // Reserves and writes the edit list of modified read k, which has more than two germline indels; the offset is parked

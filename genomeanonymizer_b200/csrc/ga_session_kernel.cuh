@@ -49,6 +49,7 @@ struct SessCtx {
     const uint8_t* keep_allele;
     int32_t keep_alen;
     ga_totals* totals;
+    uint4* edit_keep;       // session_kernel only: null, or where the edit descriptions of indel-masked records are kept (ga_record_edits)
 };
 
 __device__ __forceinline__ int64_t read_of(const SessCtx& c, int i) {
@@ -347,6 +348,12 @@ __device__ void emit_read(const SessCtx& c, const ResultView& O, int i, int64_t 
     analyse_read(c, i, r, edits, &ne, &any_snv, &too_many);
     int n_del = 0;
     while (n_del < ne && !edits[n_del].is_ins) ++n_del;
+    if (c.edit_keep && ne <= 2 && !too_many) {                           // same eight words as the resolve kernels keep (ga_record_edits)
+        const uint32_t l0 = ne > 0 ? (uint32_t)edits[0].len | (edits[0].is_ins ? 0x80000000u : 0u) : 0u;
+        const uint32_t l1 = ne > 1 ? (uint32_t)edits[1].len | (edits[1].is_ins ? 0x80000000u : 0u) : 0u;
+        c.edit_keep[2 * rec_idx] = make_uint4(ne > 0 ? (uint32_t)edits[0].irp : 0u, ne > 0 ? (uint32_t)edits[0].pos : 0u, l0, ne > 1 ? (uint32_t)edits[1].irp : 0u);
+        c.edit_keep[2 * rec_idx + 1] = make_uint4(ne > 1 ? (uint32_t)edits[1].pos : 0u, l1, (uint32_t)ne | ((uint32_t)n_del << 8), 0u);
+    }
     const uint8_t* qrec = qual_record(c.B, r);
     if (!qrec) { raise_error(c.totals, GA_ERR_BAD_ARGUMENT, (uint32_t)r); return; }
     const bool reverse = ((__ldg(c.B.len_flag + r) >> 16) & 0x10u) != 0u;
@@ -418,7 +425,7 @@ struct BigScratch {       // per-CTA slice of global scratch for oversized sessi
 template <bool BIG>
 __global__ void __launch_bounds__(kThreads) session_kernel(BatchView B, SessView S, const SessionDesc* __restrict__ descs,
                                                            const int32_t* __restrict__ big_list, const int32_t* __restrict__ n_big,
-                                                           ResultView O, BigScratch scr, unsigned int* __restrict__ ticket) {
+                                                           ResultView O, BigScratch scr, unsigned int* __restrict__ ticket, uint4* edit_keep) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_scan[kThreads / 32 + 1];
     __shared__ uint32_t s_nobs, s_reads, s_bases, s_cnt[3], s_ncand;
@@ -428,6 +435,7 @@ __global__ void __launch_bounds__(kThreads) session_kernel(BatchView B, SessView
     SessCtx c;
     c.B = B;
     c.totals = O.totals;
+    c.edit_keep = edit_keep;
     if (BIG) {
         uint8_t* p = scr.base + (size_t)blockIdx.x * (size_t)scr.bytes_per_cta;
         c.T.snv = reinterpret_cast<uint32_t*>(p); p += 4ull * scr.cols_cap;

@@ -207,7 +207,7 @@ int   ga_last_fallback_sessions(ga_engine* e, int32_t* reasons, int n_reasons);
  * applied to it; ga_record_edits then copies 8 words per requested record index (indices into the mod_* arrays of the last
  * ga_run on this engine): { in_read_pos 0, reference position 0, length 0 | INS << 31, in_read_pos 1, reference position 1,
  * length 1 | INS << 31, edits | DELs << 8, - } in application order (all DELs, then all INSs).  All bits set: nothing kept
- * (a record without indel edits, one with more than two, or one written by the fallback kernel). */
+ * (a record without indel edits, or one with more than two). */
 int   ga_engine_keep_edits(ga_engine* e, int on);
 int   ga_record_edits(ga_engine* e, const int64_t* rec_idx, int64_t n, uint32_t* out);
 

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Randomised parity: engine (ga_run through the C ABI) against the CPU oracle on many small seeded samples whose shape
 parameters are drawn at random (read length 30-300, indel / clip / SNP / error rates, indel lengths up to 60, coverage,
-window count).  usage: tools/fuzz_parity.py [first seed] [cases] [--twist]     exit code 1 when anything differed."""
+window count).  On the dense-quality pass the edit descriptions (ga_record_edits) and the FASTQ text of every read of the
+sample (ga_fastq_layout + ga_fastq_render over the masked records of every session) are compared as well.
+usage: tools/fuzz_parity.py [first seed] [cases] [--twist]     exit code 1 when anything differed."""
 import os
 import sys
 
@@ -13,6 +15,31 @@ from genomeanonymizer_b200 import synth                # noqa: E402
 from genomeanonymizer_b200.engine import Engine        # noqa: E402
 from oracle import oracle                              # noqa: E402
 from tests import helpers as H                         # noqa: E402
+
+
+def fastq_equal(eng, batch, sessions, reads, exp, seed):
+    """Every (session, read) record and every read as it came in, rendered on the device, against the oracle's renderer."""
+    import torch
+    from genomeanonymizer_b200.engine import DeviceBatch, DeviceResult, DeviceSessions
+    from oracle import fastq as OF
+    db, ds = DeviceBatch(batch, eng.device), DeviceSessions(sessions, eng.device)
+    units = batch.seq4.shape[0] // 16
+    dres = DeviceResult(sessions.n_sessions, 2 * batch.n_reads + 16, 2 * units + 64, 2 * units + 64, eng.device)
+    eng.run_device(db, ds, dres)
+    torch.cuda.synchronize()
+    n = int(eng.check_device_status(dres).n_modified)
+    ms, mr = dres.mod_session[:n].cpu().numpy(), dres.mod_read[:n].cpu().numpy()
+    items = [(int(r), k, int(s)) for k, (s, r) in enumerate(zip(ms, mr))] + [(i, -1, -1) for i in range(len(reads))]
+    text, off = eng.render_fastq(db, [r["name"] for r in reads], [i for i, _, _ in items], [k for _, k, _ in items], dres, n)
+    for j, (i, k, s) in enumerate(items):
+        if k >= 0:
+            seq, qual = H.final_read(batch, exp, i, session=s)
+        else:
+            seq, qual = B.decode_bases(batch.sequence_codes(i)), [int(x) for x in batch.qualities(i)]
+        if text[off[j]:off[j + 1]].decode("ascii") != OF.render(reads[i]["name"], reads[i]["flag"], seq, qual):
+            print("FASTQ text differs", seed, "read", i, "record", k, flush=True)
+            return False
+    return True
 
 
 def main():
@@ -34,10 +61,11 @@ def main():
         for sparse in (False, True):
             batch = B.pack_reads(reads, sparse_qual=sparse)
             sessions = B.pack_sessions(case["windows"])
-            exp, st = oracle.run(batch, sessions, case["reference"])
+            exp, st = oracle.run(batch, sessions, case["reference"], edits=not sparse)
             assert st == 0, (seed, st)
             eng.upload_reference(0, case["reference"])
-            got = eng.run(batch, sessions)
+            got = eng.run(batch, sessions, edits=not sparse)
+            eng.keep_edits(False)
             ok = got.totals == exp.totals and sorted(got.records) == sorted(exp.records) and np.array_equal(got.sess_counts, exp.sess_counts)
             if ok:
                 for k, v in got.records.items():
@@ -46,6 +74,12 @@ def main():
                         ok = False
                         print("record differs", seed, sparse, k, flush=True)
                         break
+                    if not sparse and v.get("edits") != e.get("edits"):
+                        ok = False
+                        print("edit description differs", seed, k, v.get("edits"), e.get("edits"), flush=True)
+                        break
+            if ok and not sparse:
+                ok = fastq_equal(eng, batch, sessions, reads, exp, seed)
             if not ok:
                 bad += 1
                 print("MISMATCH", seed, sparse, kw, got.totals, exp.totals, flush=True)
