@@ -253,6 +253,7 @@ static int index_records(ga_bam* b, uint64_t from, const std::string& path) {
         const int32_t ref_id = (int32_t)le32(d + off + 4);
         if (ref_id >= 0 && (uint32_t)ref_id < n_ref) b->by_ref[ref_id].push_back(off + 4);
         else if (ref_id != -1) return fail(GA_IO_ERR_FORMAT, path + ": alignment record names a reference that is not in the header");
+        b->n_records++;                                                   // records without a reference count too
         off += 4 + (uint64_t)block_size;
     }
     return GA_IO_OK;
@@ -372,13 +373,6 @@ int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
     b->by_ref.resize(b->ref_names.size());
     const int rc = index_records(b.get(), (uint64_t)hdr, path);
     if (rc != GA_IO_OK) return rc;
-    for (const auto& v : b->by_ref) b->n_records += (int64_t)v.size();
-    {   // records without a reference count too
-        const uint8_t* d = b->data.data();
-        int64_t all = 0;
-        for (uint64_t off = (uint64_t)hdr; off < b->data.size(); off += 4 + (uint64_t)le32(d + off)) ++all;
-        b->n_records = all;
-    }
     *out = b.release();
     return GA_IO_OK;
 }
