@@ -114,20 +114,12 @@ def test_device_writes_the_reference_files(entry):
     assert got["statistics"] == gold["N.bam.statistics.txt"], case["name"]
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("seed", [50, 54, 57])
-def test_device_applies_left_over_indels_twice_where_the_reference_does(seed):
-    """Quirk Q12 on the device path: thin, orphan-rich samples in which sessions meet reads that an earlier session parked
-    unpaired; driver.anonymize_sample must print what plan + oracle print with the flagged reads masked twice (the pair is
-    pinned to the reference's own files by the golden sample genome-twice-masked and by tools/fuzz_genome.py)."""
-    from genomeanonymizer_b200.engine import Engine
-    case = synth.make_case(seed, name=f"twice-{seed}", contig_len=9000, n_pairs=(70, 60), read_len=80, somatic_positions=[2500, 4650, 6800],
-                           snp_rate=4e-3, indel_rate=3e-3, clip_frac=0.1)
-    case["reads"] = [r for k, r in enumerate(case["reads"]) if k % 5 != 3]
+def device_sample_equals_plan_and_oracle(eng, case):
+    """driver.anonymize_sample on the device against plan_sample + oracle (flagged reads masked twice) + the oracle's
+    renderer; returns the number of flagged (session, read) pairs."""
     reads = with_ends(H.ordered_reads(case))
     plan = D.plan_sample(reads, case["windows"], len(case["reference"]))
     flagged = D.reapply_pairs(plan)
-    assert flagged
     batch = B.pack_reads(reads)
     res, st = oracle.run(batch, B.pack_sessions(plan.sessions), case["reference"], reapply=flagged)
     assert st == 0
@@ -139,11 +131,26 @@ def test_device_applies_left_over_indels_twice_where_the_reference_does(seed):
             seq, qual = B.decode_bases(batch.sequence_codes(i)), [int(x) for x in batch.qualities(i)]
         return OF.render(reads[i]["name"], reads[i]["flag"], seq, qual)
     want = assemble(plan, reads, text_of)
-    eng = Engine(0)
-    try:
-        got = D.anonymize_sample(eng, H.ordered_reads(case), case["windows"], case["reference"], contig=case["contig"])
-    finally:
-        eng.close()
+    got = D.anonymize_sample(eng, H.ordered_reads(case), case["windows"], case["reference"], contig=case["contig"])
     for p in "TN":
         for s in ("1", "2", "single_end"):
-            assert got[f"{p}.{s}"] == want[f"{p}.anonymized.{s}.fastq"], (seed, p, s)
+            assert got[f"{p}.{s}"] == want[f"{p}.anonymized.{s}.fastq"], (case["name"], p, s)
+    assert got["statistics"] == D.statistics_text(case["contig"], plan, res.sess_counts), case["name"]
+    return len(flagged)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [50, 54, 57])
+def test_device_applies_left_over_indels_twice_where_the_reference_does(seed):
+    """Quirk Q12 on the device path: thin, orphan-rich samples in which sessions meet reads that an earlier session parked
+    unpaired; driver.anonymize_sample must print what plan + oracle print with the flagged reads masked twice (the pair is
+    pinned to the reference's own files by the golden sample genome-twice-masked and by tools/fuzz_genome.py)."""
+    from genomeanonymizer_b200.engine import Engine
+    case = synth.make_case(seed, name=f"twice-{seed}", contig_len=9000, n_pairs=(70, 60), read_len=80, somatic_positions=[2500, 4650, 6800],
+                           snp_rate=4e-3, indel_rate=3e-3, clip_frac=0.1)
+    case["reads"] = [r for k, r in enumerate(case["reads"]) if k % 5 != 3]
+    eng = Engine(0)
+    try:
+        assert device_sample_equals_plan_and_oracle(eng, case) > 0
+    finally:
+        eng.close()
