@@ -29,8 +29,7 @@ struct GermList {
 };
 
 __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
-    __shared__ uint32_t stage[kThreads / kGroup][kGroupStage];
-    const int tid = threadIdx.x, lane = tid & 31, group = tid / kGroup, glane = tid % kGroup, gw = (lane >> 3);
+    const int tid = threadIdx.x, lane = tid & 31, glane = tid % kGroup, gw = (lane >> 3);
     if (*E.n_kind1 == 0u) return;                                       // the resolve kernels wrote every body themselves (the usual case)
     const unsigned long long n_all = O.totals->n_modified;
     const int64_t n = (int64_t)(n_all < (unsigned long long)O.cap_records ? n_all : (unsigned long long)O.cap_records);

@@ -471,7 +471,7 @@ static int run_host_source(ga_engine* e, const HostSource& src, const ga_session
     struct Pending { int32_t s0, s1; int64_t cap_rec, cap_seq, cap_qual; };
     int lane = 0;
     int status = GA_OK;
-    Pending inflight[kLanes]; bool has[kLanes] = {};
+    Pending inflight[kLanes] = {}; bool has[kLanes] = {};
     const int64_t total_units = src.R ? src.R->seq4_bytes / 16 : (int64_t)src.W->dir[src.W->n_blocks].unit;
     auto default_caps = [&](int32_t s0, int32_t s1, Pending* p) {
         // generous first guess from the slice size; an overflowing chunk is re-run with the exact need
