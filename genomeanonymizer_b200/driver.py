@@ -488,6 +488,8 @@ def anonymize_packed(engine, batch, names, read_table: Sequence[dict], windows: 
                 codes2, quals2 = reapply_indel_edits(codes, quals, bool(flag & 0x10), edits, reference)
                 nm = bytes(blob[int(noff[r]):int(noff[r + 1])]) if blob is not None else names[r].encode("ascii")
                 replaced[k] = fastq_text(nm, flag, codes2, quals2)
+    if any_reapply and hasattr(engine, "keep_edits"):
+        engine.keep_edits(False)                                      # the engine is the caller's: later runs do not pay for it
     rep_at = sorted(replaced)
 
     def piece(a, b):                                                  # records [a, b) of the item list

@@ -277,7 +277,10 @@ class Engine:
             self.run_device(db, ds, dres)
             torch.cuda.synchronize(self.device)
             n = int(self.check_device_status(dres).n_modified)
-            return dres.to_host(self.record_edits(np.arange(n)) if edits else None)
+            kept = self.record_edits(np.arange(n)) if edits else None
+            if edits:
+                self.keep_edits(False)                                # only this run pays for keeping them
+            return dres.to_host(kept)
 
 
 def _to_host_batch(db: DeviceBatch) -> ReadBatch:
