@@ -30,18 +30,16 @@ struct GermList {
 
 __global__ void __launch_bounds__(kThreads) emit_kernel(BatchView B, const SessionDesc* __restrict__ descs, ResultView O, EmitScratch2 E) {
     const int tid = threadIdx.x, lane = tid & 31, glane = tid % kGroup, gw = (lane >> 3);
-    if (*E.n_kind1 == 0u) return;                                       // the resolve kernels wrote every body themselves (the usual case)
-    const unsigned long long n_all = O.totals->n_modified;
-    const int64_t n = (int64_t)(n_all < (unsigned long long)O.cap_records ? n_all : (unsigned long long)O.cap_records);
+    const int64_t n = (int64_t)min((unsigned long long)*E.n_kind1, (unsigned long long)O.cap_records);   // 0: the resolve kernels wrote every body themselves (the usual case)
     const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (tid >> 5);
     const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * 32;
     for (int64_t k0 = warp_global * 32; k0 < n; k0 += stride) {
-        // ---- lane = record: kind, descriptor and output slot (two coalesced round trips)
+        // ---- lane = record: its index from the list, descriptor and output slot (two coalesced round trips)
         const int64_t k = k0 + lane;
-        const uint32_t kind = k < n ? E.kind[k] : 0u;
+        const uint32_t kind = k < n ? 1u : 0u;
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
         uint32_t dst16 = 0u;
-        if (kind == 1u) { d = E.edesc[k]; dst16 = O.mod_seq_off16[k]; }
+        if (kind == 1u) { const uint32_t rec = E.kind1_list[k]; d = E.edesc[rec]; dst16 = O.mod_seq_off16[rec]; }
         const uint32_t m1 = __ballot_sync(0xffffffffu, kind == 1u);
         // ---- kind 1: copy + patch, four records per step, 8 lanes each
 #pragma unroll 2

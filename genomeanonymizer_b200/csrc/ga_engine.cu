@@ -286,7 +286,7 @@ static int ensure_stream_scratch(ga_engine* e, Lane& L, int64_t cap_records, int
     if (cap_records > L.cap_kind) {
         cudaFree(L.d_kind); cudaFree(L.d_edesc); cudaFree(L.d_special); cudaFree(L.d_rare_list); cudaFree(L.d_edit_keep); L.d_edit_keep = nullptr; L.d_kind = nullptr; L.d_edesc = nullptr; L.d_special = nullptr; L.d_rare_list = nullptr; L.cap_kind = 0;
         const int64_t cap = cap_records + cap_records / 8 + 1024;
-        GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap));
+        GA_CUDA(cudaMalloc(&L.d_kind, (size_t)cap * sizeof(uint32_t)));
         GA_CUDA(cudaMalloc(&L.d_edesc, (size_t)cap * sizeof(uint4)));
         GA_CUDA(cudaMalloc(&L.d_special, (size_t)cap * 4 * sizeof(uint4)));
         GA_CUDA(cudaMalloc(&L.d_rare_list, (size_t)cap * sizeof(uint32_t)));
@@ -453,7 +453,7 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
     scr.cols_cap = e->big_cols_cap; scr.reads_cap = e->big_reads_cap; scr.obs_cap = e->big_obs_cap;
     rc = ensure_stream_scratch(e, L, out->cap_records, S->n_sessions); if (rc) return rc;
     ga::ScanScratch X; X.ent = L.d_ent; X.obs = reinterpret_cast<ga::ObsRec*>(L.d_obs); X.cnt = reinterpret_cast<uint4*>(L.d_cnt);
-    ga::EmitScratch2 E; E.kind = L.d_kind; E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
+    ga::EmitScratch2 E; E.kind1_list = reinterpret_cast<uint32_t*>(L.d_kind); E.edesc = reinterpret_cast<uint4*>(L.d_edesc); E.germ = L.d_germ;
     E.sdesc = reinterpret_cast<uint4*>(L.d_special); E.n_special = reinterpret_cast<uint32_t*>(L.d_small + 13);
     E.many = reinterpret_cast<uint4*>(L.d_many); E.n_many = reinterpret_cast<uint32_t*>(L.d_small + 15); E.cap_many = (uint32_t)L.cap_many;
     E.many_recs = L.d_many_recs; E.n_many_recs = reinterpret_cast<uint32_t*>(L.d_small + 16); E.n_kind1 = reinterpret_cast<uint32_t*>(L.d_small + 17); E.ticket_large = reinterpret_cast<unsigned int*>(L.d_small + 18); E.ticket_lean = reinterpret_cast<unsigned int*>(L.d_small + 19);
@@ -464,7 +464,6 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
         GA_CUDA(cudaMemsetAsync(L.d_edit_keep, 0xff, (size_t)std::max<int64_t>(out->cap_records, 1) * 32, st));
         E.edit_keep = reinterpret_cast<uint4*>(L.d_edit_keep);
     }
-    GA_CUDA(cudaMemsetAsync(L.d_kind, 0, (size_t)std::max<int64_t>(out->cap_records, 1), st));
     const int tslot = (int)(L.runs % kTimedRuns);
     L.runs++;
     // stage 1: allele discovery, one warp per (session, dataset) item, persistent CTAs

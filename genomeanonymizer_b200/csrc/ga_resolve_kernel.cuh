@@ -30,7 +30,7 @@ static_assert(kReads2 / 32 <= kResThreads, "phase L gives every bitmap word its 
 // record's out_qual slot until the emission kernel overwrites it with the qualities), 4 = clean read, SNV-only:
 // copy, looking every mismatch up in the session's germline list.
 struct EmitScratch2 {
-    uint8_t* kind;       // [cap_records]
+    uint32_t* kind1_list; // [cap_records] record indices of the long clean reads (kind 1), appended through n_kind1: what emit_kernel walks
     uint4* edesc;        // [cap_records] kind 1: {source record unit, pos - col_begin, length | hits << 16, two hits ((column << 4) | reference code)}
                          //               else:   {source record unit, pos, length, session}
     uint32_t* germ;      // [n_sessions][kGermStride]
@@ -462,9 +462,8 @@ __global__ void __launch_bounds__(kResThreads, 6) resolve_kernel(BatchView B, Se
             if (kind == 1 && (lf & 0xffffu) <= 160u) {              // the common record: written here, nothing left for the emission kernels
                 write_common_body(B, O, __ldg(B.seq_off16 + r), s_base[1] + sm->mseq[k], lf & 0xffffu, sm->mpatch[k], sm->mpc[k], pos - c.d.col_begin);
             } else if (kind == 1) {                                   // a long clean read: the copy kernel takes it
-                E.kind[rec_idx] = 1;
                 E.edesc[rec_idx] = make_uint4(__ldg(B.seq_off16 + r), (uint32_t)(pos - c.d.col_begin), (lf & 0xffffu) | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
-                atomicAdd(E.n_kind1, 1u);
+                E.kind1_list[atomicAdd(E.n_kind1, 1u)] = (uint32_t)rec_idx;
             } else {
                 const uint32_t slot = atomicAdd(E.n_special, 1u);
                 uint32_t skind = kind;
@@ -1005,12 +1004,11 @@ __global__ void __launch_bounds__(32 * kWarps, kMinBlocks) resolve_warp_kernel(B
             if (kind == 1u && L0 <= 160u) {
                 // the common record: the lane writes the body itself; the emission kernel skips kind 0
                 write_common_body(B, O, so, base_seq + so_rel, L0, sm->mpatch[k], sm->mpc[k], pos - c.d.col_begin);
-                continue;                                             // E.kind stays 0: nothing left for the emission kernels
+                continue;                                             // nothing left for the emission kernels
             }
             if (kind == 1u) {                                         // a long clean read: the copy kernel takes it
-                E.kind[rec_idx] = 1;
                 E.edesc[rec_idx] = make_uint4(so, (uint32_t)(pos - c.d.col_begin), L0 | ((uint32_t)sm->mpc[k] << 16), sm->mpatch[k]);
-                atomicAdd(E.n_kind1, 1u);
+                E.kind1_list[atomicAdd(E.n_kind1, 1u)] = (uint32_t)rec_idx;
             } else if ((int64_t)my_slot < O.cap_records) {
                 write_special(E, B, c.d, my_slot, kind, so, pos, lf, s, r, new_len, base_seq + so_rel, qual16);
                 if (kind == 5u) { const uint32_t at = atomicAdd(E.n_many_recs, 1u); if (at < E.cap_many) E.many_recs[at] = my_slot; }
