@@ -53,38 +53,61 @@ __global__ void max_span_kernel(const uint32_t* __restrict__ cigar_off, const ui
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
-__device__ __forceinline__ int32_t lower_bound_pos(const int32_t* __restrict__ pos, int64_t b, int64_t e, int64_t v) {
-    while (b < e) { const int64_t m = (b + e) >> 1; if ((int64_t)__ldg(pos + m) < v) b = m + 1; else e = m; }
-    return (int32_t)b;
-}
 
 // K-assign: binary search of the coordinate-sorted read positions for every session
 // (replaces the index fetch inside pileup(), pileup_io.pyx:12-17).
+// Lower bound of v in pos[b, e) by K lanes (the K-lane group of a warp that holds `lane`; every lane of the group gets the
+// answer): each round the lanes test K pivots that cut the range into K + 1 parts, so with K = 8 a search over 2^25
+// positions is 8 dependent loads deep instead of 25 (K = 1 is the binary search) - the chain of dependent loads is the
+// whole cost of assign_sessions_kernel.
+template <int K>
+__device__ __forceinline__ int32_t lower_bound_pos_k(const int32_t* __restrict__ pos, int64_t b, int64_t e, int64_t v, int lane) {
+    const int j = lane % K, g0 = lane - j;
+    for (;;) {
+        const bool live = b < e;                                      // uniform over the group; the groups of a warp finish at different rounds
+        if (!__any_sync(0xffffffffu, live)) break;
+        const int64_t n = e - b;
+        const int64_t m = b + (n * (j + 1)) / (K + 1);                // b <= m < e
+        const bool below = live && (int64_t)__ldg(pos + m) < v;       // monotone in j: the array is sorted
+        const int c = __popc((__ballot_sync(0xffffffffu, below) >> g0) & ((1u << K) - 1u));
+        if (live) {
+            const int64_t nb = c ? b + (n * c) / (K + 1) + 1 : b;     // the last pivot below v, plus one
+            const int64_t ne = c < K ? b + (n * (c + 1)) / (K + 1) : e;   // the first pivot not below v
+            b = nb; e = ne;
+        }
+    }
+    return (int32_t)b;
+}
+
+// 4 * K lanes per session, K lanes per search: the four searches of the read positions run side by side, then the four
+// searches of the sparse quality index; the session's first lane does the rest.  The engine picks the largest K whose
+// threads still fit the device in one wave: few sessions are searched wide and shallow, many sessions one lane each.
+template <int K>
 __global__ void assign_sessions_kernel(BatchView B, SessView S, const int32_t* __restrict__ maxspan_p, SessionDesc* __restrict__ descs,
                                        int32_t* __restrict__ big_list, int32_t* __restrict__ n_big) {
-    // Four lanes per session: the four searches of the read positions run side by side, then the four searches of the
-    // sparse quality index (the chain of dependent loads is the cost of this kernel); lane 0 of the group does the rest.
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s_raw = gid >> 2, q4 = gid & 3, lane = threadIdx.x & 31, g0 = lane & ~3;
+    constexpr int T = 4 * K;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, sl = lane % T, q4 = sl / K, sb = lane - sl;
+    const int64_t s_raw = gid / T;
     const bool active = s_raw < S.n_sessions;
-    const int s = active ? s_raw : S.n_sessions - 1;
+    const int s = active ? (int)s_raw : S.n_sessions - 1;
     const int maxspan = max(1, *maxspan_p);
     const int64_t first = S.first[s], last = S.last[s];
     SessionDesc d;
     {
         const bool normal = q4 >= 2;
-        const int mine = lower_bound_pos(B.pos, normal ? B.n_tumor : 0, normal ? B.n_reads : B.n_tumor, (q4 & 1) ? last : first - maxspan + 1);
-        d.t_begin = __shfl_sync(0xffffffffu, mine, g0); d.t_end = __shfl_sync(0xffffffffu, mine, g0 + 1);
-        d.n_begin = __shfl_sync(0xffffffffu, mine, g0 + 2); d.n_end = __shfl_sync(0xffffffffu, mine, g0 + 3);
+        const int mine = lower_bound_pos_k<K>(B.pos, normal ? B.n_tumor : 0, normal ? B.n_reads : B.n_tumor, (q4 & 1) ? last : first - maxspan + 1, lane);
+        d.t_begin = __shfl_sync(0xffffffffu, mine, sb); d.t_end = __shfl_sync(0xffffffffu, mine, sb + K);
+        d.n_begin = __shfl_sync(0xffffffffu, mine, sb + 2 * K); d.n_end = __shfl_sync(0xffffffffu, mine, sb + 3 * K);
     }
     d.qt_begin = d.qt_end = d.qn_begin = d.qn_end = 0;
     if (B.qual_reads) {                                               // warp-uniform
         const int target = q4 == 0 ? d.t_begin : q4 == 1 ? d.t_end : q4 == 2 ? d.n_begin : d.n_end;
-        const int mine = lower_bound_pos(B.qual_reads, 0, B.n_qual, target);
-        d.qt_begin = __shfl_sync(0xffffffffu, mine, g0); d.qt_end = __shfl_sync(0xffffffffu, mine, g0 + 1);
-        d.qn_begin = __shfl_sync(0xffffffffu, mine, g0 + 2); d.qn_end = __shfl_sync(0xffffffffu, mine, g0 + 3);
+        const int mine = lower_bound_pos_k<K>(B.qual_reads, 0, B.n_qual, target, lane);
+        d.qt_begin = __shfl_sync(0xffffffffu, mine, sb); d.qt_end = __shfl_sync(0xffffffffu, mine, sb + K);
+        d.qn_begin = __shfl_sync(0xffffffffu, mine, sb + 2 * K); d.qn_end = __shfl_sync(0xffffffffu, mine, sb + 3 * K);
     }
-    if (!active || q4 != 0) return;
+    if (!active || sl != 0) return;
     int64_t lo = last;
     if (d.t_end > d.t_begin) lo = min(lo, (int64_t)B.pos[d.t_begin]);
     if (d.n_end > d.n_begin) lo = min(lo, (int64_t)B.pos[d.n_begin]);
@@ -446,7 +469,14 @@ int ga_run_lane(ga_engine* e, int lane, const ga_reads* R, const ga_sessions* S,
         ga::max_span_kernel<<<e->n_sm * 4, 256, 0, st>>>(R->cigar_off, R->cigar, R->n_reads, d_maxspan);
         e->launches++;
     }
-    ga::assign_sessions_kernel<<<(int)((4 * (int64_t)S->n_sessions + 127) / 128), 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
+    {
+        const int64_t room = (int64_t)e->n_sm * 2048 / std::max<int64_t>(1, 4 * (int64_t)S->n_sessions);   // lanes per search that keep the kernel in one wave
+        const auto grid = [&](int k) { return (int)((4 * k * (int64_t)S->n_sessions + 127) / 128); };
+        if (room >= 8) ga::assign_sessions_kernel<8><<<grid(8), 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
+        else if (room >= 4) ga::assign_sessions_kernel<4><<<grid(4), 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
+        else if (room >= 2) ga::assign_sessions_kernel<2><<<grid(2), 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
+        else ga::assign_sessions_kernel<1><<<grid(1), 128, 0, st>>>(B, V, d_maxspan, L.d_descs, L.d_big_list, d_nbig);
+    }
     e->launches++;
     ga::BigScratch scr;
     scr.base = L.d_big_scratch; scr.bytes_per_cta = e->big_bytes_per_cta;
