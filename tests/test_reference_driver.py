@@ -148,7 +148,7 @@ def test_oracle_equals_the_reference_on_random_and_twisted_samples():
     """A slice of tools/fuzz_reference.py: seeded samples with random shape parameters - and with the edge shapes the
     generator never makes (an insertion as the last / first aligned op, hard clips, reference skips: tests/helpers.twist_reads)
     - go through the reference's unmodified CompleteGermlineAnonymizer.anonymize and through the oracle.  (The whole tool:
-    5,500 samples without a difference after the normal-column rule of anonymizer_methods.py:474-481 was restated.)"""
+    8,000 samples without a difference after the normal-column rule of anonymizer_methods.py:474-481 was restated.)"""
     import subprocess
     for extra in ([], ["--twist"]):
         res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_reference.py"), "910000", "25"] + extra, capture_output=True, text=True, timeout=600)
