@@ -540,7 +540,34 @@ int ga_fasta_open(const char* path, ga_fasta** out) {
     *out = nullptr;
     std::vector<uint8_t> file;
     if (!read_file(path, file)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
-    if (file.size() >= 2 && file[0] == 31 && file[1] == 139) return fail(GA_IO_ERR_UNSUPPORTED, std::string(path) + ": compressed FASTA is not supported");
+    if (file.size() >= 2 && file[0] == 31 && file[1] == 139) {
+        // gzip or bgzip (what pysam.FastaFile reads besides plain text): a sequence of gzip members, inflated one after the
+        // other; zlib checks every member's CRC32 and length
+        std::vector<uint8_t> text;
+        text.reserve(file.size() * 4);
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, 15 + 16) != Z_OK) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": zlib refused to start");
+        zs.next_in = file.data();
+        uint64_t left = file.size();
+        std::vector<uint8_t> chunk(1u << 22);
+        bool ok = true, in_member = false;
+        for (;;) {
+            if (zs.avail_in == 0 && left) { const uint64_t n = std::min<uint64_t>(left, 1u << 30); zs.avail_in = (uInt)n; left -= n; }
+            if (zs.avail_in == 0 && !in_member) break;                   // the end of the file, between members
+            zs.next_out = chunk.data(); zs.avail_out = (uInt)chunk.size();
+            in_member = true;
+            const int rc = inflate(&zs, Z_NO_FLUSH);
+            text.insert(text.end(), chunk.data(), chunk.data() + (chunk.size() - zs.avail_out));
+            if (rc == Z_STREAM_END) {                                    // one member done; another may follow
+                in_member = false;
+                if (inflateReset(&zs) != Z_OK) { ok = false; break; }
+            } else if (rc != Z_OK || (zs.avail_in == 0 && left == 0 && zs.avail_out != 0)) { ok = false; break; }   // corrupt or truncated
+        }
+        inflateEnd(&zs);
+        if (!ok) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": the gzip stream is corrupt or truncated");
+        file.swap(text);
+    }
     ga_fasta* f = new ga_fasta();
     const uint8_t* p = file.data();
     const uint8_t* end = p + file.size();

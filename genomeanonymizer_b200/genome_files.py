@@ -282,7 +282,7 @@ def pack_tumor_normal(tumor: BamFile, normal: BamFile, contig: str, contig_id: i
 
 
 class FastaFile:
-    """Plain-text FASTA (stands where the reference has pysam.FastaFile: .references, .lengths, .fetch)."""
+    """FASTA, plain text or gzip / bgzip (stands where the reference has pysam.FastaFile: .references, .lengths, .fetch)."""
 
     def __init__(self, path: str):
         self._L = _io()

@@ -91,7 +91,7 @@ int  ga_bam_pack_contig(const ga_bam* b, int ref_id, uint32_t flag_exclude, cons
 
 /* ------------------------------------------------------------------ FASTA */
 typedef struct ga_fasta ga_fasta;
-int  ga_fasta_open(const char* path, ga_fasta** out);      /* plain-text FASTA; sequences in file order */
+int  ga_fasta_open(const char* path, ga_fasta** out);      /* FASTA, plain text or gzip / bgzip; sequences in file order */
 void ga_fasta_close(ga_fasta* f);
 int  ga_fasta_n_references(const ga_fasta* f);
 const char* ga_fasta_reference_name(const ga_fasta* f, int idx);

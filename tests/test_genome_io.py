@@ -389,3 +389,42 @@ def test_bam_without_sequence_and_long_cigar_records(tmp_path):
     with pytest.raises((GF.GenomeFileError, ValueError)):
         with GF.BamFile(p) as f:
             GF.pack_tumor_normal(f, f, "c")
+
+
+def test_fasta_reader_takes_gzip_and_bgzip_files(tmp_path):
+    """pysam.FastaFile reads bgzip-compressed FASTA as well as plain text; the reader takes any sequence of gzip members
+    (one member: gzip, many 64 KiB members + the empty EOF member: bgzip) and refuses a truncated or corrupt stream."""
+    import gzip
+    rng = np.random.default_rng(5)
+    contigs = [("chrA", "".join(rng.choice(list("ACGTNacgt"), size=150001))), ("chrB some description", "".join(rng.choice(list("ACGT"), size=70))),
+               ("chrC", "")]
+    plain = str(tmp_path / "ref.fa")
+    H.write_fasta(plain, contigs, width=61)
+    raw = open(plain, "rb").read()
+    one = str(tmp_path / "ref.fa.gz")
+    with open(one, "wb") as f:
+        f.write(gzip.compress(raw))
+    many = str(tmp_path / "ref.bgz.fa.gz")
+    with open(many, "wb") as f:
+        for k in range(0, len(raw), 0xff00):
+            f.write(H._bgzf_block(raw[k:k + 0xff00]))
+        f.write(H._bgzf_block(b""))
+    want = GF.FastaFile(plain)
+    for path in (one, many):
+        got = GF.FastaFile(path)
+        assert got.references == want.references == ("chrA", "chrB", "chrC") and got.lengths == want.lengths
+        for name in got.references:
+            assert got.fetch(name) == want.fetch(name)
+        assert got.fetch("chrA", 149990, 150010) == want.fetch("chrA", 149990, 150010)
+        got.close()
+    cut = str(tmp_path / "cut.fa.gz")
+    with open(cut, "wb") as f:
+        f.write(open(many, "rb").read()[:40000])
+    with pytest.raises(GF.GenomeFileError):
+        GF.FastaFile(cut)
+    bad = bytearray(open(one, "rb").read())
+    bad[len(bad) // 2] ^= 0x55
+    with open(cut, "wb") as f:
+        f.write(bytes(bad))
+    with pytest.raises(GF.GenomeFileError):
+        GF.FastaFile(cut)
