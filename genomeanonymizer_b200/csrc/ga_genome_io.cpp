@@ -20,6 +20,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -223,6 +224,119 @@ int64_t parse_header(const uint8_t* d, uint64_t n, std::vector<std::string>& nam
     return (int64_t)off;
 }
 
+// SAM text (SAM v1.6 section 1) -> the uncompressed BAM stream the rest of the reader works on (section 4.2): header
+// dictionary from the @SQ lines, one record per alignment line.  Optional fields are dropped (nothing on the path reads
+// them); a '*' sequence is a record without stored bases, '*' qualities are 0xff as in BAM.
+bool sam_to_stream(const uint8_t* text, size_t n, std::vector<uint8_t>& out, std::string* why) {
+    auto put32 = [&](uint32_t v) { for (int k = 0; k < 4; ++k) out.push_back((uint8_t)(v >> (8 * k))); };
+    auto put16 = [&](uint32_t v) { out.push_back((uint8_t)v); out.push_back((uint8_t)(v >> 8)); };
+    std::vector<std::string> names;
+    std::vector<uint32_t> lens;
+    size_t p = 0;
+    while (p < n && text[p] == '@') {                                  // header lines
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(text + p, '\n', n - p));
+        const size_t e = nl ? (size_t)(nl - text) : n;
+        if (e - p >= 3 && text[p + 1] == 'S' && text[p + 2] == 'Q') {
+            std::string sn; long long ln = -1;
+            size_t f = p;
+            while (f < e) {
+                size_t g = f;
+                while (g < e && text[g] != '\t') ++g;
+                if (g - f > 3 && text[f + 2] == ':') {
+                    if (text[f] == 'S' && text[f + 1] == 'N') { sn.assign(reinterpret_cast<const char*>(text + f + 3), g - f - 3); }
+                    else if (text[f] == 'L' && text[f + 1] == 'N') ln = std::strtoll(std::string(reinterpret_cast<const char*>(text + f + 3), g - f - 3).c_str(), nullptr, 10);
+                }
+                f = g + 1;
+            }
+            while (!sn.empty() && sn.back() == '\r') sn.pop_back();
+            if (sn.empty() || ln < 0 || ln > 0x7fffffffLL) { *why = "@SQ line without SN / LN"; return false; }
+            names.push_back(sn); lens.push_back((uint32_t)ln);
+        }
+        p = nl ? e + 1 : n;
+    }
+    out.clear();
+    out.insert(out.end(), {'B', 'A', 'M', 1});
+    put32(0);                                                          // l_text: the text is not kept
+    put32((uint32_t)names.size());
+    for (size_t k = 0; k < names.size(); ++k) {
+        put32((uint32_t)names[k].size() + 1);
+        out.insert(out.end(), names[k].begin(), names[k].end());
+        out.push_back(0);
+        put32(lens[k]);
+    }
+    auto ref_of = [&](const uint8_t* s, size_t len, int same) -> int {
+        if (len == 1 && s[0] == '*') return -1;
+        if (len == 1 && s[0] == '=' && same > -2) return same;
+        for (size_t k = 0; k < names.size(); ++k) if (names[k].size() == len && std::memcmp(names[k].data(), s, len) == 0) return (int)k;
+        return -2;
+    };
+    uint8_t code_of[256];
+    std::memset(code_of, 15, sizeof code_of);                          // anything else is N, as in htslib's table
+    { const char* t = "=ACMGRSVTWYHKDBN"; for (int k = 0; k < 16; ++k) { code_of[(uint8_t)t[k]] = (uint8_t)k; code_of[(uint8_t)std::tolower(t[k])] = (uint8_t)k; } }
+    while (p < n) {                                                    // alignment lines
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(text + p, '\n', n - p));
+        size_t e = nl ? (size_t)(nl - text) : n;
+        const size_t next = nl ? e + 1 : n;
+        if (e > p && text[e - 1] == '\r') --e;
+        if (e == p) { p = next; continue; }
+        const uint8_t* f[11]; size_t fl[11];
+        size_t q = p; int nf = 0;
+        while (nf < 11) {
+            size_t g = q;
+            while (g < e && text[g] != '\t') ++g;
+            f[nf] = text + q; fl[nf] = g - q; ++nf;
+            if (g >= e) break;
+            q = g + 1;
+        }
+        if (nf < 11) { *why = "alignment line with fewer than 11 fields"; return false; }
+        auto num = [&](int k) { return std::strtoll(std::string(reinterpret_cast<const char*>(f[k]), fl[k]).c_str(), nullptr, 10); };
+        const int ref = ref_of(f[2], fl[2], -2);
+        if (ref == -2) { *why = "alignment line names a reference without an @SQ line"; return false; }
+        int nref = ref_of(f[6], fl[6], ref);
+        if (nref == -2) nref = -1;
+        if (fl[0] == 0 || fl[0] > 254) { *why = "read name longer than 254 characters"; return false; }
+        std::vector<uint32_t> ops;
+        if (!(fl[5] == 1 && f[5][0] == '*')) {
+            uint64_t len = 0; bool have = false;
+            for (size_t k = 0; k < fl[5]; ++k) {
+                const uint8_t ch = f[5][k];
+                if (ch >= '0' && ch <= '9') { len = len * 10 + (ch - '0'); have = true; if (len >= (1u << 28)) { *why = "CIGAR operation longer than 2^28"; return false; } continue; }
+                const char* t = "MIDNSHP=X";
+                const char* at = std::strchr(t, (char)ch);
+                if (!at || !have || ch == 0) { *why = "malformed CIGAR"; return false; }
+                ops.push_back((uint32_t)(len << 4) | (uint32_t)(at - t));
+                len = 0; have = false;
+            }
+            if (have) { *why = "malformed CIGAR"; return false; }
+        }
+        if (ops.size() > 65535) { *why = "more than 65535 CIGAR operations: not supported"; return false; }
+        const bool no_seq = fl[9] == 1 && f[9][0] == '*';
+        const uint32_t l_seq = no_seq ? 0u : (uint32_t)fl[9];
+        const bool no_qual = fl[10] == 1 && f[10][0] == '*';               // also for a one-base read, as htslib reads it
+        if (!no_qual && !no_seq && fl[10] != fl[9]) { *why = "SEQ and QUAL differ in length"; return false; }
+        const uint32_t l_name = (uint32_t)fl[0] + 1;
+        put32(32 + l_name + 4 * (uint32_t)ops.size() + (l_seq + 1) / 2 + l_seq);
+        put32((uint32_t)ref);
+        put32((uint32_t)(num(3) - 1));
+        out.push_back((uint8_t)l_name);
+        out.push_back((uint8_t)num(4));
+        put16(0);                                                      // bin: nothing on the path reads it
+        put16((uint32_t)ops.size());
+        put16((uint32_t)num(1));
+        put32(l_seq);
+        put32((uint32_t)nref);
+        put32((uint32_t)(num(7) - 1));
+        put32((uint32_t)num(8));
+        out.insert(out.end(), f[0], f[0] + fl[0]);
+        out.push_back(0);
+        for (const uint32_t w : ops) put32(w);
+        for (uint32_t k = 0; k < l_seq; k += 2) out.push_back((uint8_t)((code_of[f[9][k]] << 4) | (k + 1 < l_seq ? code_of[f[9][k + 1]] : 0)));
+        for (uint32_t k = 0; k < l_seq; ++k) out.push_back(no_qual ? (uint8_t)0xff : (uint8_t)(f[10][k] - 33));
+        p = next;
+    }
+    return true;
+}
+
 uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* v = std::getenv(name);
     return v && *v ? std::strtoull(v, nullptr, 10) : dflt;
@@ -350,9 +464,16 @@ int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
     b->threads = n_threads;
     if (!b->file.open(path)) return fail(GA_IO_ERR_OPEN, std::string("cannot read ") + path);
     std::string why;
-    if (!index_bgzf(b->file, b->blocks, &b->total, &why)) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + why);
+    const bool is_text = b->file.size() > 0 && b->file.data()[0] != 31;    // no gzip magic: SAM text (pysam.AlignmentFile reads it too)
+    if (is_text) {
+        std::vector<uint8_t> stream;
+        if (!sam_to_stream(b->file.data(), b->file.size(), stream, &why)) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": SAM: " + why);
+        b->total = stream.size();
+        b->data.resize(stream.size());
+        std::memcpy(b->data.data(), stream.data(), stream.size());
+    } else if (!index_bgzf(b->file, b->blocks, &b->total, &why)) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": " + why);
     // Files above the threshold are opened lazily when their records are grouped by reference
-    if (b->total > env_u64("GA_BAM_EAGER_BYTES", 2ull << 30)) {
+    if (!is_text && b->total > env_u64("GA_BAM_EAGER_BYTES", 2ull << 30)) {
         bool grouped = false;
         const int rc = scan_spans(b.get(), path, &grouped);
         if (rc != GA_IO_OK) return rc;
@@ -365,7 +486,7 @@ int ga_bam_open(const char* path, int n_threads, ga_bam** out) {
         b->n_records = 0; b->spans.clear();                                // interleaved references: keep the whole stream
     }
     uint64_t base = 0;
-    if (!inflate_range(b->file, b->blocks, 0, b->total, n_threads, b->data, &base))
+    if (!is_text && !inflate_range(b->file, b->blocks, 0, b->total, n_threads, b->data, &base))
         return fail(GA_IO_ERR_FORMAT, std::string(path) + ": a BGZF block failed to inflate or its CRC32 does not match");
     const int64_t hdr = parse_header(b->data.data(), b->data.size(), b->ref_names, b->ref_lens);
     if (hdr < 0) return fail(GA_IO_ERR_FORMAT, std::string(path) + ": BAM magic missing");

@@ -47,7 +47,8 @@ typedef struct ga_bam ga_bam;
  * A file whose uncompressed stream exceeds GA_BAM_EAGER_BYTES (environment, default 2 GiB) and whose records are
  * grouped by reference is walked once, window by window, and then kept mapped: the records of one reference at a time
  * are inflated when ga_bam_contig_sizes / ga_bam_pack_contig ask for them (the handle caches one reference, so it is
- * for one thread at a time). */
+ * for one thread at a time).  A file that does not begin with the gzip magic is read as SAM text (SAM v1.6 section 1:
+ * header dictionary from the @SQ lines, eleven mandatory fields per line; optional fields are not kept). */
 int  ga_bam_open(const char* path, int n_threads, ga_bam** out);
 void ga_bam_close(ga_bam* b);
 int  ga_bam_n_references(const ga_bam* b);

@@ -145,6 +145,19 @@ def write_bam(path, contigs, reads, block_bytes: int = 0xff00, level: int = 6):
         fh.write(_BAM_EOF)
 
 
+def write_sam(path, contigs, reads, crlf: bool = False):
+    """The same reads as SAM text (SAM v1.6 section 1): header dictionary, eleven mandatory fields, one optional field."""
+    names = [c for c, _ in contigs]
+    nl = "\r\n" if crlf else "\n"
+    with open(path, "w", newline="") as fh:
+        fh.write("@HD\tVN:1.6\tSO:coordinate" + nl + "".join(f"@SQ\tSN:{c}\tLN:{n}{nl}" for c, n in contigs) + "@PG\tID:test" + nl)
+        for r in reads:
+            unmapped = bool(r["flag"] & 4) and r["cigar"] == "*"
+            qual = "".join(chr(int(q) + 33) for q in r["qual"]) or "*"
+            fh.write("\t".join([r["name"], str(r["flag"]), r.get("contig", names[0]), str(r["pos"] + 1), "0" if unmapped else "60", r["cigar"], "=", str(r["pos"] + 1), "0",
+                                r["seq"] or "*", qual, "NM:i:0"]) + nl)
+
+
 def write_fasta(path, contigs, width: int = 60):
     """contigs: [(name, bases)]"""
     with open(path, "w") as fh:

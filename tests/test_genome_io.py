@@ -428,3 +428,80 @@ def test_fasta_reader_takes_gzip_and_bgzip_files(tmp_path):
         f.write(bytes(bad))
     with pytest.raises(GF.GenomeFileError):
         GF.FastaFile(cut)
+
+
+@pytest.mark.parametrize("entry", [GENOME[1], GENOME[5]], ids=[IDS[1], IDS[5]])
+@pytest.mark.parametrize("crlf", [False, True], ids=["lf", "crlf"])
+def test_sam_text_packs_the_same_batch_as_the_bam(entry, crlf, tmp_path):
+    """pysam.AlignmentFile opens SAM text as it opens BAM (the reference's name_output knows '.sam'); the reader turns the
+    text into the uncompressed BAM stream and everything behind it is shared."""
+    case = entry["case"]
+    contigs = [(case["contig"], len(case["reference"]))]
+    t, n, _, _ = H.write_sample_files(str(tmp_path), case, entry["vcf"])
+    ts, ns = str(tmp_path / "T.sam"), str(tmp_path / "N.sam")
+    H.write_sam(ts, contigs, [r for r in case["reads"] if r["dataset"] == 0], crlf)
+    H.write_sam(ns, contigs, [r for r in case["reads"] if r["dataset"] == 1], crlf)
+    with GF.BamFile(t, 2) as T, GF.BamFile(n, 2) as N, GF.BamFile(ts, 2) as TS, GF.BamFile(ns, 2) as NS:
+        assert TS.references == T.references and TS.lengths == T.lengths and (TS.n_records, NS.n_records) == (T.n_records, N.n_records)
+        a, b = GF.pack_tumor_normal(T, N, case["contig"]), GF.pack_tumor_normal(TS, NS, case["contig"])
+    for f in ARRAYS:
+        assert np.array_equal(getattr(a.batch, f), getattr(b.batch, f)), f
+    assert a.batch.n_tumor == b.batch.n_tumor and a.batch.max_ref_span == b.batch.max_ref_span
+    assert np.array_equal(a.ref_end, b.ref_end) and np.array_equal(a.name_off, b.name_off) and np.array_equal(a.name_blob, b.name_blob)
+
+
+def test_sam_text_edge_cases_and_errors(tmp_path):
+    contigs = [("c", 1000), ("d", 500)]
+    reads = [dict(name="r1", flag=0x41, pos=10, cigar="3S5M2I4M1D3M2H", seq="ACGTNACGTTACGTACG", qual=list(range(17)), contig="c"),
+             dict(name="r2", flag=0x91, pos=20, cigar="4M", seq="", qual=[], contig="c"),                      # no stored sequence
+             dict(name="r3", flag=0x81, pos=5, cigar="6M", seq="acgtRY", qual=[40] * 6, contig="d")]            # lower case, ambiguity codes
+    sam, bam = str(tmp_path / "x.sam"), str(tmp_path / "x.bam")
+    H.write_sam(sam, contigs, reads)
+    H.write_bam(bam, contigs, [dict(r, seq=r["seq"].upper()) for r in reads])
+    with GF.BamFile(sam, 1) as S, GF.BamFile(bam, 1) as Bm:
+        assert S.references == ("c", "d") and S.lengths == (1000, 500) and S.n_records == 3
+        for contig in ("c", "d"):
+            a, b = GF.pack_tumor_normal(S, S, contig), GF.pack_tumor_normal(Bm, Bm, contig)
+            for f in ARRAYS:
+                assert np.array_equal(getattr(a.batch, f), getattr(b.batch, f)), (contig, f)
+    head = "@SQ\tSN:c\tLN:100\n"
+    for body in ("r\t0\tzz\t1\t60\t4M\t*\t0\t0\tACGT\tIIII\n",            # a reference without @SQ
+                 "r\t0\tc\t1\t60\t4M\t*\t0\t0\tACGT\n",                   # ten fields
+                 "r\t0\tc\t1\t60\t4Q\t*\t0\t0\tACGT\tIIII\n",             # CIGAR
+                 "r\t0\tc\t1\t60\tM\t*\t0\t0\tACGT\tIIII\n",
+                 "r\t0\tc\t1\t60\t4M\t*\t0\t0\tACGT\tIII\n"):             # SEQ / QUAL lengths
+        path = str(tmp_path / "bad.sam")
+        with open(path, "w") as fh:
+            fh.write(head + body)
+        with pytest.raises(GF.GenomeFileError):
+            GF.BamFile(path, 1)
+    with open(str(tmp_path / "only_header.sam"), "w") as fh:
+        fh.write(head)
+    with GF.BamFile(str(tmp_path / "only_header.sam"), 1) as E:
+        assert E.n_records == 0 and E.references == ("c",)
+
+
+@pytest.mark.gpu
+def test_entry_point_reads_sam_text(tmp_path):
+    from genomeanonymizer_b200.engine import Engine
+    from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import name_output, run_short_read_tumor_normal_anonymizer
+    entry = GENOME[1]
+    case = entry["case"]
+    contigs = [(case["contig"], len(case["reference"]))]
+    _, _, fa, vc = H.write_sample_files(str(tmp_path), case, entry["vcf"])
+    ts, ns = str(tmp_path / "T.sam"), str(tmp_path / "N.sam")
+    H.write_sam(ts, contigs, [r for r in case["reads"] if r["dataset"] == 0])
+    H.write_sam(ns, contigs, [r for r in case["reads"] if r["dataset"] == 1])
+    outs = (name_output(ts), name_output(ns))
+    assert outs[0].endswith("T.anonymized")
+    eng = Engine(0)
+    try:
+        run_short_read_tumor_normal_anonymizer([vc], [(ts, ns)], fa, eng, [outs], True, 2, False)
+    finally:
+        eng.close()
+    for name, text in entry["expected"]["files"].items():
+        path = os.path.join(str(tmp_path), name.replace("N.bam.statistics", "N.sam.statistics"))
+        if text is None:
+            assert not os.path.exists(path), name
+        else:
+            assert open(path).read() == text, name
