@@ -96,6 +96,31 @@ inline bool is_generic(const ga_reads* R, int64_t r, uint32_t L) {
 inline uint32_t units_of_len(uint32_t L) { return L ? (L + 31u) / 32u : 1u; }
 inline bool plain_code(uint32_t c) { return c == 1u || c == 2u || c == 4u || c == 8u; }
 
+// Sixteen base codes at a time (one 64-bit word of seq4, low nibble first).  not_plain: bit 4k set when nibble k is not one
+// of A C G T (1 2 4 8); two_bits: the sixteen 2-bit codes (A C G T = 0 1 2 3, anything else 0) packed into 32 bits.
+constexpr uint64_t kNib1 = 0x1111111111111111ull;
+inline uint64_t load_nibbles16(const uint8_t* rec, uint32_t q, uint32_t L) {   // bases [q, q + 16) of a record of L bases, zero behind the read
+    uint64_t w;
+    memcpy(&w, rec + (q >> 1), 8);                                      // records are whole 16-byte units: the load stays inside
+    const uint32_t left = L - q;
+    return left >= 16u ? w : (w & ((1ull << (4u * left)) - 1ull));
+}
+inline uint64_t not_plain16(uint64_t w) {
+    const uint64_t sum = (w & kNib1) + ((w >> 1) & kNib1) + ((w >> 2) & kNib1) + ((w >> 3) & kNib1);   // set bits per nibble, 0 .. 4
+    const uint64_t t = sum ^ kNib1;                                      // zero exactly where one bit is set
+    return (t | (t >> 1) | (t >> 2)) & kNib1;
+}
+inline uint32_t two_bits16(uint64_t w, uint64_t not_plain) {
+    const uint64_t ok = ~not_plain & kNib1;
+    const uint64_t lo = ((w >> 1) | (w >> 3)) & ok, hi = ((w >> 2) | (w >> 3)) & ok;
+    uint64_t x = lo | (hi << 1);                                         // a 2-bit code in the low half of every nibble
+    x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+    x = (x | (x >> 16)) & 0x00000000ffffffffull;
+    return (uint32_t)x;
+}
+
 // Block boundaries of one dataset: at most GA_WIRE_BLOCK_READS reads, position differences below 65,536.
 bool cut_blocks(const ga_reads* R, int64_t lo, int64_t hi, std::vector<BlockPlan>& out) {
     int64_t r = lo;
@@ -145,7 +170,12 @@ void size_block(const ga_reads* R, BlockPlan& b) {
         b.ops += nops;
         if (is_generic(R, r, L)) { ++b.n_gen; b.n_gen_ops += nops; }
         const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
-        for (uint32_t q = 0; q < L; ++q) { const uint32_t c = (rec[q >> 1] >> (4 * (q & 1))) & 15u; if (!plain_code(c)) ++b.n_exc; }
+        for (uint32_t q = 0; q < L; q += 16) {
+            const uint32_t left = L - q;
+            uint64_t np = not_plain16(load_nibbles16(rec, q, L));
+            if (left < 16u) np &= (1ull << (4u * left)) - 1ull;            // the zero nibbles behind the read are not bases
+            b.n_exc += (uint32_t)__builtin_popcountll(np);
+        }
     }
     b.n_words = (uint32_t)((n_bases + 15) / 16) + 3;                      // three zero words behind: the expansion reads two words ahead of any base
     // flags: a dictionary of up to 16 values and 4-bit indices when the block has no more distinct flags (the usual case), else 16 bits each
@@ -200,12 +230,21 @@ void write_block(const ga_reads* R, const BlockPlan& b, uint8_t* dst) {
             for (uint32_t c = R->cigar_off[r]; c < R->cigar_off[r + 1]; ++c) gen_cig[ngo++] = R->cigar[c];
         }
         const uint8_t* rec = R->seq4 + 16ull * R->seq_off16[r];
-        for (uint32_t q = 0; q < L; ++q, ++at) {
-            const uint32_t c = (rec[q >> 1] >> (4 * (q & 1))) & 15u;
-            uint32_t two = 0;
-            if (c == 2u) two = 1; else if (c == 4u) two = 2; else if (c == 8u) two = 3;
-            else if (c != 1u) exc[ne++] = (i << 20) | (q << 4) | c;
-            bases[at >> 4] |= two << (2 * (at & 15));
+        for (uint32_t q = 0; q < L; q += 16) {                             // sixteen bases per step into the block's continuous 2-bit stream
+            const uint32_t left = L - q, take = left < 16u ? left : 16u;
+            const uint64_t w = load_nibbles16(rec, q, L);
+            uint64_t np = not_plain16(w);
+            if (left < 16u) np &= (1ull << (4u * left)) - 1ull;
+            const uint64_t two = two_bits16(w, np);                        // zero behind the read (the nibbles there are zero: not plain)
+            const uint32_t word = (uint32_t)(at >> 4), sh = 2u * (uint32_t)(at & 15);
+            bases[word] |= (uint32_t)(two << sh);
+            if (sh) bases[word + 1] |= (uint32_t)(two >> (32u - sh));     // n_words has three spare words behind the last base
+            while (np) {                                                 // the rare other codes, in read order
+                const uint32_t k = (uint32_t)__builtin_ctzll(np) >> 2;
+                np &= np - 1ull;
+                exc[ne++] = (i << 20) | ((q + k) << 4) | (uint32_t)((w >> (4u * k)) & 15u);
+            }
+            at += take;
         }
     }
     gen_off[ng] = ngo;
