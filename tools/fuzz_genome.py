@@ -5,7 +5,9 @@ layout, orphans and unmapped mates go through the reference's unmodified anonymi
 CompleteGermlineAnonymizer (under tests/ref_stub) and through driver.plan_sample + the oracle; the seven files must be
 equal.  Two known quirks of the reference are reported separately and do not fail the run: a difference that is only the
 ORDER of the records of a file (Q11 of DESIGN.md: the reference's buffered streams; exact only while a region's pass-through
-text stays below the 8 KiB stream buffer) and bodies of reads whose left-over indels the reference applies twice (Q12).
+text stays below the 8 KiB stream buffer) and bodies of reads whose left-over indels the reference applies twice (Q12:
+the plan flags those reads and the oracle applies their indels twice, so this class has been empty since that was built;
+the classifier stays as a tripwire).
 usage: tools/fuzz_genome.py [first seed] [cases]"""
 import os
 import shutil
